@@ -1,0 +1,229 @@
+"""ctypes / numpy mirrors of the structs in include/gfpl_c.h.
+
+numpy structured dtypes (align=True) give the C layout of the record arrays; the `*NP` containers
+own the arrays of one batched view and hand out the ctypes view struct the C ABI takes.
+"""
+import ctypes as C
+
+import numpy as np
+
+DESC_BYTES = 32
+NORM_HAMMING = 6
+NORM_HAMMING2 = 7
+
+STEREO_INITIAL, STEREO_BRUTE = 0, 1
+F2F_HYBRID, F2F_BRUTE = 0, 1
+POSE_SEED_PREV_DT, POSE_SEED_GIVEN = 0, 1
+TRACK_LINECUT, TRACK_F2F_BRUTE, TRACK_SEED_GIVEN, TRACK_STEREO_INITIAL = 1, 2, 4, 8
+NUM_STAGES = 7
+
+OK, E_INVALID, E_NO_DEVICE, E_CUDA, E_NOMEM, E_CAPACITY = 0, -1, -2, -3, -4, -5
+
+
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("b", C.c_double), ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("has_points", C.c_int32), ("has_lines", C.c_int32), ("lr_in_parallel", C.c_int32),
+        ("best_lr_matches", C.c_int32), ("use_line_conf_cut", C.c_int32), ("max_vol_line_cut", C.c_int32),
+        ("max_line_match_num", C.c_int32), ("max_point_match_num", C.c_int32), ("min_features", C.c_int32),
+        ("max_iters", C.c_int32), ("max_iters_ref", C.c_int32), ("max_iters_lba", C.c_int32),
+        ("ratio_disp_std", C.c_double), ("ratio_disp_std_hor", C.c_double), ("max_dist_epip", C.c_double),
+        ("min_disp", C.c_double), ("max_ratio_12_p", C.c_double), ("point_match_radius", C.c_double),
+        ("stereo_overlap_th", C.c_double), ("line_horiz_th", C.c_double), ("desc_th_l", C.c_double),
+        ("line_cov_th", C.c_double), ("line_match_radius", C.c_double), ("homog_th", C.c_double),
+        ("min_error", C.c_double), ("min_error_change", C.c_double), ("inlier_k", C.c_double),
+        ("motion_step_th", C.c_double), ("orb_scale_factor", C.c_double), ("lsd_scale", C.c_double),
+        ("lambda_lba_lm", C.c_double), ("lambda_lba_k", C.c_double), ("f2f_point_window", C.c_double),
+        ("budget_slack", C.c_double), ("cut_step", C.c_double), ("cut_rng", C.c_double * 2),
+        ("mad_uninit_value", C.c_double),
+    ]
+
+
+keypoint_dt = np.dtype([("x", "f4"), ("y", "f4"), ("octave", "i4"), ("class_id", "i4")], align=True)
+keyline_dt = np.dtype([("startPointX", "f4"), ("startPointY", "f4"), ("endPointX", "f4"), ("endPointY", "f4"),
+                       ("angle", "f4"), ("octave", "i4"), ("lineLength", "f4"), ("response", "f4")], align=True)
+point_feature_dt = np.dtype([("P", "f8", 3), ("pl", "f8", 2), ("disp", "f8"), ("sigma2", "f8"), ("level", "i4"),
+                             ("idx", "i4"), ("src_l", "i4"), ("src_r", "i4")], align=True)
+line_feature_dt = np.dtype([("sP", "f8", 3), ("eP", "f8", 3), ("spl", "f8", 2), ("epl", "f8", 2), ("sdisp", "f8"),
+                            ("edisp", "f8"), ("le", "f8", 3), ("angle", "f8"), ("sigma2", "f8"), ("level", "i4"),
+                            ("idx", "i4"), ("src_l", "i4"), ("src_r", "i4")], align=True)
+line_cov_dt = np.dtype([("covS", "f8", 9), ("covE", "f8", 9)], align=True)
+pt_obs_dt = np.dtype([("P", "f8", 3), ("pl_obs", "f8", 2), ("sigma2", "f8"), ("prev_idx", "i4"), ("curr_idx", "i4")],
+                     align=True)
+ln_obs_dt = np.dtype([("sP", "f8", 3), ("eP", "f8", 3), ("le_obs", "f8", 3), ("sigma2", "f8"), ("prev_idx", "i4"),
+                      ("curr_idx", "i4")], align=True)
+line_cut_dt = np.dtype([("cutRatio", "f8", 2), ("invCovPose", "f8", 36), ("spl", "f8", 2), ("epl", "f8", 2),
+                        ("sdisp", "f8"), ("edisp", "f8")], align=True)
+frame_state_dt = np.dtype([("Tfw", "f8", 16), ("DT", "f8", 16), ("DT_cov", "f8", 36), ("Tfw_cov", "f8", 36),
+                           ("time_stamp", "f8"), ("time_stamp_curr", "f8")], align=True)
+pose_result_dt = np.dtype([("DT", "f8", 16), ("Tfw", "f8", 16), ("DT_cov", "f8", 36), ("DT_cov_eig", "f8", 6),
+                           ("Tfw_cov", "f8", 36), ("err_norm", "f8"), ("status", "i4"), ("n_inliers", "i4"),
+                           ("n_inliers_pt", "i4"), ("n_inliers_ls", "i4"), ("iters_first", "i4"),
+                           ("iters_ref", "i4")], align=True)
+
+assert keypoint_dt.itemsize == 16 and keyline_dt.itemsize == 32
+assert point_feature_dt.itemsize == 72 and line_feature_dt.itemsize == 152
+assert line_cov_dt.itemsize == 144 and pt_obs_dt.itemsize == 56 and ln_obs_dt.itemsize == 88
+assert line_cut_dt.itemsize == 352 and frame_state_dt.itemsize == 848 and pose_result_dt.itemsize == 912
+
+_vp = C.c_void_p
+
+
+class RawFrames(C.Structure):
+    _fields_ = [("B", C.c_int32), ("cap_pt", C.c_int32), ("cap_ln", C.c_int32),
+                ("n_pt_l", _vp), ("n_pt_r", _vp), ("n_ln_l", _vp), ("n_ln_r", _vp),
+                ("pt_l", _vp), ("pt_r", _vp), ("pdesc_l", _vp), ("pdesc_r", _vp),
+                ("ln_l", _vp), ("ln_r", _vp), ("ldesc_l", _vp), ("ldesc_r", _vp)]
+
+
+class StereoFrames(C.Structure):
+    _fields_ = [("B", C.c_int32), ("cap_pt", C.c_int32), ("cap_ln", C.c_int32),
+                ("n_pt", _vp), ("n_ln", _vp), ("pt", _vp), ("pdesc", _vp), ("ln", _vp), ("ldesc", _vp)]
+
+
+class TrackObs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("cap_pt", C.c_int32), ("cap_ln", C.c_int32),
+                ("n_pt", _vp), ("n_ln", _vp), ("pt", _vp), ("pt_inlier", _vp), ("ln", _vp), ("ln_inlier", _vp)]
+
+
+class LbaProblem(C.Structure):
+    _fields_ = [("Nkf", C.c_int32), ("Npt", C.c_int32), ("Nls", C.c_int32), ("n_pt_obs", C.c_int32),
+                ("n_ls_obs", C.c_int32), ("kf_Tkw", _vp), ("X_pt", _vp), ("X_ls", _vp),
+                ("pt_obs_lm", _vp), ("pt_obs_kf", _vp), ("pt_obs_fix", _vp), ("pt_obs_uv", _vp), ("pt_obs_s2", _vp),
+                ("ls_obs_lm", _vp), ("ls_obs_kf", _vp), ("ls_obs_fix", _vp), ("ls_obs_le", _vp), ("ls_obs_s2", _vp),
+                ("fix_Tkw", _vp), ("n_fix", C.c_int32)]
+
+
+class LbaBlocks(C.Structure):
+    _fields_ = [("Hkk", _vp), ("Hpp", _vp), ("Hll", _vp), ("Hpk", _vp), ("Hlk", _vp), ("g", _vp), ("err", _vp)]
+
+
+def ptr(a):
+    """void* of a C-contiguous numpy array (None -> NULL)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+    return a.ctypes.data
+
+
+def _alloc(shape, dtype, pinned):
+    """Host array; `pinned` allocates page-locked memory through torch (bench e2e path)."""
+    if not pinned:
+        return np.zeros(shape, dtype=dtype)
+    import torch
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    buf = torch.zeros(max(n, 1), dtype=torch.uint8).pin_memory()
+    # the numpy view keeps the pinned tensor's storage alive through its base chain
+    return buf.numpy()[:n].view(dt).reshape(shape)
+
+
+class RawFramesNP:
+    """points_l/r, pdesc_l/r, lines_l/r, ldesc_l/r of B stereo frames."""
+
+    def __init__(self, B, cap_pt, cap_ln, pinned=False):
+        self.B, self.cap_pt, self.cap_ln = B, cap_pt, cap_ln
+        a = lambda s, d: _alloc(s, d, pinned)
+        self.n_pt_l, self.n_pt_r = a(B, "i4"), a(B, "i4")
+        self.n_ln_l, self.n_ln_r = a(B, "i4"), a(B, "i4")
+        self.pt_l, self.pt_r = a((B, cap_pt), keypoint_dt), a((B, cap_pt), keypoint_dt)
+        self.pdesc_l, self.pdesc_r = a((B, cap_pt, 32), "u1"), a((B, cap_pt, 32), "u1")
+        self.ln_l, self.ln_r = a((B, cap_ln), keyline_dt), a((B, cap_ln), keyline_dt)
+        self.ldesc_l, self.ldesc_r = a((B, cap_ln, 32), "u1"), a((B, cap_ln, 32), "u1")
+
+    def view(self):
+        return RawFrames(self.B, self.cap_pt, self.cap_ln, ptr(self.n_pt_l), ptr(self.n_pt_r), ptr(self.n_ln_l),
+                         ptr(self.n_ln_r), ptr(self.pt_l), ptr(self.pt_r), ptr(self.pdesc_l), ptr(self.pdesc_r),
+                         ptr(self.ln_l), ptr(self.ln_r), ptr(self.ldesc_l), ptr(self.ldesc_r))
+
+    def nbytes(self):
+        return sum(getattr(self, k).nbytes for k in ("n_pt_l", "n_pt_r", "n_ln_l", "n_ln_r", "pt_l", "pt_r",
+                                                      "pdesc_l", "pdesc_r", "ln_l", "ln_r", "ldesc_l", "ldesc_r"))
+
+    def slice(self, lo, hi):
+        out = RawFramesNP.__new__(RawFramesNP)
+        out.B, out.cap_pt, out.cap_ln = hi - lo, self.cap_pt, self.cap_ln
+        for k in ("n_pt_l", "n_pt_r", "n_ln_l", "n_ln_r", "pt_l", "pt_r", "pdesc_l", "pdesc_r", "ln_l", "ln_r",
+                  "ldesc_l", "ldesc_r"):
+            setattr(out, k, getattr(self, k)[lo:hi])
+        return out
+
+
+class StereoFramesNP:
+    """stereo_pt / stereo_ls and compacted descriptors of B stereo frames."""
+    _keys = ("n_pt", "n_ln", "pt", "pdesc", "ln", "ldesc")
+
+    def __init__(self, B, cap_pt, cap_ln, pinned=False):
+        self.B, self.cap_pt, self.cap_ln = B, cap_pt, cap_ln
+        a = lambda s, d: _alloc(s, d, pinned)
+        self.n_pt, self.n_ln = a(B, "i4"), a(B, "i4")
+        self.pt, self.pdesc = a((B, cap_pt), point_feature_dt), a((B, cap_pt, 32), "u1")
+        self.ln, self.ldesc = a((B, cap_ln), line_feature_dt), a((B, cap_ln, 32), "u1")
+
+    def view(self):
+        return StereoFrames(self.B, self.cap_pt, self.cap_ln, ptr(self.n_pt), ptr(self.n_ln), ptr(self.pt),
+                            ptr(self.pdesc), ptr(self.ln), ptr(self.ldesc))
+
+    def nbytes(self):
+        return sum(getattr(self, k).nbytes for k in self._keys)
+
+    def slice(self, lo, hi):
+        out = StereoFramesNP.__new__(StereoFramesNP)
+        out.B, out.cap_pt, out.cap_ln = hi - lo, self.cap_pt, self.cap_ln
+        for k in self._keys:
+            setattr(out, k, getattr(self, k)[lo:hi])
+        return out
+
+    def copy(self):
+        out = StereoFramesNP.__new__(StereoFramesNP)
+        out.B, out.cap_pt, out.cap_ln = self.B, self.cap_pt, self.cap_ln
+        for k in self._keys:
+            setattr(out, k, getattr(self, k).copy())
+        return out
+
+
+class TrackObsNP:
+    """matched_pt / matched_ls of B frame pairs as observation lists + inlier masks."""
+    _keys = ("n_pt", "n_ln", "pt", "pt_inlier", "ln", "ln_inlier")
+
+    def __init__(self, B, cap_pt, cap_ln, pinned=False):
+        self.B, self.cap_pt, self.cap_ln = B, cap_pt, cap_ln
+        a = lambda s, d: _alloc(s, d, pinned)
+        self.n_pt, self.n_ln = a(B, "i4"), a(B, "i4")
+        self.pt, self.pt_inlier = a((B, cap_pt), pt_obs_dt), a((B, cap_pt), "u1")
+        self.ln, self.ln_inlier = a((B, cap_ln), ln_obs_dt), a((B, cap_ln), "u1")
+
+    def view(self):
+        return TrackObs(self.B, self.cap_pt, self.cap_ln, ptr(self.n_pt), ptr(self.n_ln), ptr(self.pt),
+                        ptr(self.pt_inlier), ptr(self.ln), ptr(self.ln_inlier))
+
+    def copy(self):
+        out = TrackObsNP.__new__(TrackObsNP)
+        out.B, out.cap_pt, out.cap_ln = self.B, self.cap_pt, self.cap_ln
+        for k in self._keys:
+            setattr(out, k, getattr(self, k).copy())
+        return out
+
+
+_LBA_FIELDS = (("kf_Tkw", "f8"), ("X_pt", "f8"), ("X_ls", "f8"), ("pt_obs_lm", "i4"), ("pt_obs_kf", "i4"),
+               ("pt_obs_fix", "i4"), ("pt_obs_uv", "f8"), ("pt_obs_s2", "f8"), ("ls_obs_lm", "i4"),
+               ("ls_obs_kf", "i4"), ("ls_obs_fix", "i4"), ("ls_obs_le", "f8"), ("ls_obs_s2", "f8"), ("fix_Tkw", "f8"))
+
+
+def lba_problem_from_arrays(a):
+    """dict of numpy arrays (named like gfpl_lba_problem's pointer fields) -> (LbaProblem, keepalive dict)."""
+    keep = {k: np.ascontiguousarray(a[k], dt) for k, dt in _LBA_FIELDS}
+    p = LbaProblem()
+    p.Nkf = len(keep["kf_Tkw"].reshape(-1, 16))
+    p.Npt = len(keep["X_pt"].reshape(-1, 3))
+    p.Nls = len(keep["X_ls"].reshape(-1, 6))
+    p.n_pt_obs = len(keep["pt_obs_lm"])
+    p.n_ls_obs = len(keep["ls_obs_lm"])
+    p.n_fix = len(keep["fix_Tkw"].reshape(-1, 16))
+    for k, _ in _LBA_FIELDS:
+        setattr(p, k, ptr(keep[k]))
+    return p, keep
