@@ -1,0 +1,105 @@
+// gfpl_internal.h — host-side internals shared by the .cu translation units of libgfpl.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gfpl_c.h"
+
+namespace gfpl {
+
+// device-side views: same structs as the C ABI, but every pointer is a DEVICE pointer
+typedef gfpl_raw_frames DevRawFrames;
+typedef gfpl_stereo_frames DevStereoFrames;
+typedef gfpl_track_obs DevTrackObs;
+
+struct Knn2Out {  // knn k=2 results of one direction, [B][cap_q]
+  int2* idx;      // (i0, i1), -1 when missing
+  float2* dist;   // (d0, d1), +inf when missing
+};
+
+void set_last_error(gfpl_ctx* ctx, const char* fmt, ...);
+
+}  // namespace gfpl
+
+struct gfpl_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  gfpl_camera cam{};
+  gfpl_config cfg{};
+  int64_t launches = 0;
+  std::string last_error;
+  // scratch arena for the host-pointer entry points (grown on demand, freed with the ctx)
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  size_t scratch_used = 0;
+};
+
+#define GFPL_CUDA_OK(ctx, expr)                                                              \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      gfpl::set_last_error(ctx, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return GFPL_E_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+#define GFPL_LAUNCH_OK(ctx)                                                                  \
+  do {                                                                                       \
+    (ctx)->launches++;                                                                       \
+    cudaError_t _e = cudaGetLastError();                                                     \
+    if (_e != cudaSuccess) {                                                                 \
+      gfpl::set_last_error(ctx, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return GFPL_E_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+namespace gfpl {
+
+// ---- kernel launchers (all asynchronous on ctx->stream, device pointers only) --------------------
+
+// K1: knn k=2 for B problems, optionally both directions in one launch.
+// dir 0: queries = a (na rows), train = b (nb rows) -> out_ab ; dir 1 (if out_ba.idx): queries = b, train = a.
+int launch_knn2(gfpl_ctx* ctx, int B, const uint8_t* a, const int32_t* na, int cap_a, const uint8_t* b,
+                const int32_t* nb, int cap_b, int norm, Knn2Out out_ab, Knn2Out out_ba);
+
+// K2: radius match for one problem (CSR), two passes
+int launch_radius_count(gfpl_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int norm, float radius,
+                        int32_t* counts);
+int launch_radius_fill(gfpl_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int norm, float radius,
+                       const int32_t* offsets, int32_t* out_idx, float* out_dist);
+
+// K3: stereo accept loops (points + lines) for B frames, one CTA per frame
+int launch_stereo_accept(gfpl_ctx* ctx, const DevRawFrames& raw, int variant, Knn2Out pt_lr, Knn2Out pt_rl,
+                         Knn2Out ln_lr, Knn2Out ln_rl, DevStereoFrames out);
+int launch_stereo_uncertainty(gfpl_ctx* ctx, const DevStereoFrames& fr, gfpl_line_cov* out);
+
+// f2f: fused radius + projection-gate search (hybrid points), knn-candidate variant, and accept loops
+int launch_f2f_hybrid_points(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr,
+                             const gfpl_frame_state* state, uint32_t* best_key /*[B][curr.cap_pt]*/);
+int launch_f2f_hybrid_points_knn(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr,
+                                 const gfpl_frame_state* state, Knn2Out pt_12, uint32_t* best_key);
+int launch_f2f_accept(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr, int mode,
+                      const uint32_t* best_key, Knn2Out pt_12, Knn2Out pt_21, Knn2Out ln_12, Knn2Out ln_21,
+                      DevTrackObs out);
+
+// K5: line cut.  DT_inv may be NULL: then it is formed from `state` (curr->Tfw^-1 * prev->Tfw with the
+// predicted curr->Tfw = prev->Tfw * prev->DT).
+int launch_linecut(gfpl_ctx* ctx, const double* DT_inv, const gfpl_frame_state* state, DevTrackObs obs,
+                   const gfpl_line_cov* prev_cov, int cov_cap, gfpl_line_cut* cut);
+
+// K4: pose
+int launch_pose_hg(gfpl_ctx* ctx, const double* DT, const DevTrackObs& obs, double* H, double* g, double* e);
+int launch_pose_optimize(gfpl_ctx* ctx, DevTrackObs obs, const gfpl_frame_state* state, const double* DT_ini,
+                         int overload, gfpl_pose_result* out);
+
+// K6: LBA assembly (device copies of the flat problem)
+int launch_lba_assemble(gfpl_ctx* ctx, const gfpl_lba_problem& dprob, gfpl_lba_blocks dout);
+
+int launch_measure_peaks(gfpl_ctx* ctx, double* popc_tops, double* fp64_tflops);
+
+}  // namespace gfpl

@@ -1,0 +1,291 @@
+// k_stereo.cu — K3 (stereo half): accept loops that turn knn k=2 results into stereo_pt / stereo_ls, and
+// StereoFrame::estimateStereoUncertainty.
+//
+// Replaces the loops of StereoFrame::extractInitialStereoFeatures (reference stereoFrame.cpp:206-245,
+// 287-332) and extractStereoFeatures_Brute (:829-878, :919-1012; line half identical to _ORBSLAM :670-763),
+// lineDescriptorMAD (:1287-1313), lineSegmentOverlapStereo (:1343-1371), estimateStereoUncertainty
+// (:1448-1484) with getCovMat2D_3D / getJacob2D_3D (:1375-1392, 1434-1446).
+//
+// One CTA per stereo frame.  Accepted features keep the reference's output order (ascending left index):
+// a block-wide ordered compaction (ballot + warp totals) assigns the output slot.  HBM-/latency-bound,
+// O(N) per frame: algorithmic bytes = knn results (16 B/query, two directions) + key points (16 B) +
+// key lines (32 B) in, feature records (72 B / 152 B) + 32 B descriptor out.
+#include "gfpl_internal.h"
+#include "gfpl_math.cuh"
+
+namespace gfpl {
+
+constexpr int ACCEPT_THREADS = 256;
+
+// ordered block compaction: returns the output slot of this thread's element (valid when pred), advances
+// `base` (uniform across the CTA) by the number of accepted elements of this round.
+__device__ __forceinline__ int block_compact(bool pred, int& base, int* s_warp /*[ACCEPT_THREADS/32 + 1]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, pred);
+  if (lane == 0) s_warp[warp] = __popc(bal);
+  __syncthreads();
+  int before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < ACCEPT_THREADS / 32; w++) {
+    int c = s_warp[w];
+    before += (w < warp) ? c : 0;
+    total += c;
+  }
+  const int slot = base + before + __popc(bal & ((1u << lane) - 1));
+  base += total;
+  __syncthreads();
+  return slot;
+}
+
+// element of rank `rank` (0-based) of v[0..n): what `sort(v); v[rank]` reads.  Every thread returns it.
+__device__ float block_select(const float* v, int n, int rank, float* s_out) {
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const float x = v[j];
+    int r = 0;
+    for (int k = 0; k < n; k++) {
+      const float y = v[k];
+      r += (y < x) || (y == x && k < j);
+    }
+    if (r == rank) *s_out = x;
+  }
+  __syncthreads();
+  const float out = *s_out;
+  __syncthreads();
+  return out;
+}
+
+// PointFeature / LineFeature sigma2 (stereoFeatures.cpp:41-48, 93-101)
+__device__ __forceinline__ double level_sigma2(int level, double scale) {
+  double sigma2 = 1.0;
+  for (int i = 0; i < level + 1; i++) sigma2 *= scale;
+  return 1.0 / (sigma2 * sigma2);
+}
+
+// StereoFrame::lineSegmentOverlapStereo (stereoFrame.cpp:1343-1371)
+__device__ __forceinline__ double line_segment_overlap_stereo(double spl_obs, double epl_obs, double spl_proj,
+                                                              double epl_proj) {
+  const double sln = fmin(spl_obs, epl_obs), eln = fmax(spl_obs, epl_obs);
+  const double spn = fmin(spl_proj, epl_proj), epn = fmax(spl_proj, epl_proj);
+  const double length = eln - spn;
+  double overlap;
+  if ((epn < sln) || (spn > eln)) overlap = 0.0;
+  else {
+    if ((epn > eln) && (spn < sln)) overlap = eln - sln;
+    else overlap = fmin(eln, epn) - fmax(sln, spn);
+  }
+  if (length > (double)0.01f) overlap = overlap / length;
+  else overlap = 0.0;
+  return overlap;
+}
+
+// analytic endpoint covariance and its largest eigenvalue (stereoFrame.cpp:956-998)
+__device__ double endpoint_cov_max_eig(const gfpl_camera& cam, double px, double py, double disp) {
+  const double f = cam.fx;
+  const double px_hat = px - cam.cx, py_hat = py - cam.cy;
+  const double disp2 = disp * disp;
+  double c[9];
+  c[0] = disp2 + 2.0 * px_hat * px_hat;
+  c[1] = 2.0 * px_hat * py_hat;
+  c[2] = 2.0 * f * px_hat;
+  c[4] = disp2 + 2.0 * py_hat * py_hat;
+  c[5] = 2.0 * f * py_hat;
+  c[8] = 2.0 * f * f;
+  c[3] = c[1]; c[6] = c[2]; c[7] = c[5];
+  const double d4 = disp2 * disp2;
+  for (int i = 0; i < 9; i++) c[i] = c[i] * cam.b * cam.b / d4;
+  double ev[3];
+  sym_eigenvalues<3>(c, ev);
+  return ev[2];
+}
+
+__global__ void __launch_bounds__(ACCEPT_THREADS)
+stereo_accept_kernel(DevRawFrames raw, int variant, Knn2Out pt_lr, Knn2Out pt_rl, Knn2Out ln_lr, Knn2Out ln_rl,
+                     DevStereoFrames out, gfpl_camera cam, gfpl_config cfg) {
+  extern __shared__ float s_v[];  // [raw.cap_ln] MAD scratch
+  __shared__ int s_warp[ACCEPT_THREADS / 32 + 1];
+  __shared__ float s_sel;
+  const int p = blockIdx.x;
+  const size_t rp = (size_t)p * raw.cap_pt, rl_ = (size_t)p * raw.cap_ln;
+  const size_t op = (size_t)p * out.cap_pt, ol = (size_t)p * out.cap_ln;
+
+  // ---- points (stereoFrame.cpp:206-245 / 829-878) -------------------------------------------------
+  {
+    const int n_l = raw.n_pt_l[p], n_r = raw.n_pt_r[p];
+    int base = 0;
+    if (cfg.has_points && n_l >= 2 && n_r >= 2) {  // D3
+      for (int i0 = 0; i0 < n_l; i0 += ACCEPT_THREADS) {
+        const int i = i0 + threadIdx.x;
+        bool keep = false;
+        int tdx = 0;
+        float disp_sub = 0.f;
+        gfpl_keypoint kl{};
+        if (i < n_l) {
+          const int2 mi = pt_lr.idx[rp + i];
+          const float2 md = pt_lr.dist[rp + i];
+          tdx = mi.x;
+          const int rl_tdx = cfg.best_lr_matches ? pt_rl.idx[rp + tdx].x : i;
+          const double dist_12 = (double)(md.x / md.y);  // float / float, widened (stereoFrame.cpp:219,842)
+          if (i == rl_tdx && dist_12 <= cfg.max_ratio_12_p) {
+            kl = raw.pt_l[rp + i];
+            const gfpl_keypoint kr = raw.pt_r[rp + tdx];
+            if ((double)fabsf(kl.y - kr.y) <= cfg.max_dist_epip) {
+              const double disp_ = (double)(kl.x - kr.x);
+              if (disp_ >= cfg.min_disp) {
+                disp_sub = (float)disp_;
+                keep = disp_sub >= 0.f;
+              }
+            }
+          }
+        }
+        const int slot = block_compact(keep, base, s_warp);
+        if (keep) {
+          gfpl_point_feature f;
+          f.pl[0] = kl.x; f.pl[1] = kl.y;
+          back_projection(cam, f.pl[0], f.pl[1], (double)disp_sub, f.P);
+          f.disp = disp_sub;
+          f.level = kl.octave;
+          f.sigma2 = level_sigma2(f.level, cfg.orb_scale_factor);
+          f.idx = slot; f.src_l = i; f.src_r = tdx;
+          out.pt[op + slot] = f;
+          const uint4* s = reinterpret_cast<const uint4*>(raw.pdesc_l + (rp + i) * 32);
+          uint4* d = reinterpret_cast<uint4*>(out.pdesc + (op + slot) * 32);
+          d[0] = s[0]; d[1] = s[1];
+        }
+      }
+    }
+    if (threadIdx.x == 0) out.n_pt[p] = base;
+  }
+
+  // ---- lines (stereoFrame.cpp:248-334 / 881-1014) ---------------------------------------------------
+  {
+    const int n_l = raw.n_ln_l[p], n_r = raw.n_ln_r[p];
+    int base = 0;
+    if (cfg.has_lines && n_l >= 2 && n_r >= 2) {  // D3
+      // lineDescriptorMAD: 1.4826 * element[n/2] of ascending fabsf(d1 - d0 - U)  (U: SURVEY A.4 D1)
+      for (int j = threadIdx.x; j < n_l; j += ACCEPT_THREADS) {
+        const float2 md = ln_lr.dist[rl_ + j];
+        s_v[j] = fabsf((float)((double)(md.y - md.x) - cfg.mad_uninit_value));
+      }
+      __syncthreads();
+      const float med = block_select(s_v, n_l, n_l / 2, &s_sel);
+      const double nn12_dist_th = (1.4826 * (double)med) * cfg.desc_th_l;
+      const int n_matches = cfg.best_lr_matches ? min(n_l, n_r) : n_l;  // D4
+      for (int i0 = 0; i0 < n_matches; i0 += ACCEPT_THREADS) {
+        const int i = i0 + threadIdx.x;
+        bool keep = false;
+        gfpl_line_feature f{};
+        if (i < n_matches) {
+          const int tdx = ln_lr.idx[rl_ + i].x;
+          const float2 md = ln_lr.dist[rl_ + i];
+          const int rl_tdx = cfg.best_lr_matches ? ln_rl.idx[rl_ + tdx].x : i;
+          const double dist_12 = (double)(md.y - md.x);
+          if (i == rl_tdx && dist_12 > nn12_dist_th) {
+            const gfpl_keyline L = raw.ln_l[rl_ + i];
+            const gfpl_keyline R = raw.ln_r[rl_ + tdx];
+            const double sp_l[3] = {L.startPointX, L.startPointY, 1.0};
+            const double ep_l[3] = {L.endPointX, L.endPointY, 1.0};
+            double le_l[3] = {sp_l[1] * ep_l[2] - sp_l[2] * ep_l[1], sp_l[2] * ep_l[0] - sp_l[0] * ep_l[2],
+                              sp_l[0] * ep_l[1] - sp_l[1] * ep_l[0]};
+            const double nrm = sqrt(le_l[0] * le_l[0] + le_l[1] * le_l[1]);
+            le_l[0] = le_l[0] / nrm; le_l[1] = le_l[1] / nrm; le_l[2] = le_l[2] / nrm;
+            const double sp_r[3] = {R.startPointX, R.startPointY, 1.0};
+            const double ep_r[3] = {R.endPointX, R.endPointY, 1.0};
+            const double le_r[3] = {sp_r[1] * ep_r[2] - sp_r[2] * ep_r[1], sp_r[2] * ep_r[0] - sp_r[0] * ep_r[2],
+                                    sp_r[0] * ep_r[1] - sp_r[1] * ep_r[0]};
+            const double overlap = line_segment_overlap_stereo(sp_l[1], ep_l[1], sp_r[1], ep_r[1]);
+            const double spr0 = -(le_r[2] + le_r[1] * (double)L.startPointY) / le_r[0];
+            const double epr0 = -(le_r[2] + le_r[1] * (double)L.endPointY) / le_r[0];
+            const double disp_s = (double)L.startPointX - spr0;
+            const double disp_e = (double)L.endPointX - epr0;
+            const double horiz = variant == GFPL_STEREO_INITIAL ? le_r[0] : le_l[0];  // :316 vs :949
+            if (disp_s >= cfg.min_disp && disp_e >= cfg.min_disp && (double)fabsf((float)horiz) > cfg.line_horiz_th &&
+                overlap > cfg.stereo_overlap_th) {
+              keep = true;
+              if (variant != GFPL_STEREO_INITIAL) {
+                const double max_eig = fmax(endpoint_cov_max_eig(cam, sp_l[0], sp_l[1], disp_s),
+                                            endpoint_cov_max_eig(cam, ep_l[0], ep_l[1], disp_e));
+                keep = max_eig < cfg.line_cov_th;
+              }
+              if (keep) {
+                f.spl[0] = sp_l[0]; f.spl[1] = sp_l[1]; f.epl[0] = ep_l[0]; f.epl[1] = ep_l[1];
+                f.sdisp = disp_s; f.edisp = disp_e;
+                back_projection(cam, sp_l[0], sp_l[1], disp_s, f.sP);
+                back_projection(cam, ep_l[0], ep_l[1], disp_e, f.eP);
+                f.le[0] = le_l[0]; f.le[1] = le_l[1]; f.le[2] = le_l[2];
+                f.angle = L.angle;
+                f.level = L.octave;
+                f.sigma2 = level_sigma2(f.level, cfg.lsd_scale);
+                f.src_l = i; f.src_r = tdx;
+              }
+            }
+          }
+        }
+        const int slot = block_compact(keep, base, s_warp);
+        if (keep) {
+          f.idx = variant == GFPL_STEREO_INITIAL ? slot : -1;
+          out.ln[ol + slot] = f;
+          const uint4* s = reinterpret_cast<const uint4*>(raw.ldesc_l + (rl_ + i) * 32);
+          uint4* d = reinterpret_cast<uint4*>(out.ldesc + (ol + slot) * 32);
+          d[0] = s[0]; d[1] = s[1];
+        }
+      }
+    }
+    if (threadIdx.x == 0) out.n_ln[p] = base;
+  }
+}
+
+int launch_stereo_accept(gfpl_ctx* ctx, const DevRawFrames& raw, int variant, Knn2Out pt_lr, Knn2Out pt_rl,
+                         Knn2Out ln_lr, Knn2Out ln_rl, DevStereoFrames out) {
+  if (raw.B <= 0) return GFPL_OK;
+  const size_t smem = (size_t)(raw.cap_ln > 0 ? raw.cap_ln : 1) * sizeof(float);
+  if (smem > 48 * 1024)
+    GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(stereo_accept_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  stereo_accept_kernel<<<raw.B, ACCEPT_THREADS, smem, ctx->stream>>>(raw, variant, pt_lr, pt_rl, ln_lr, ln_rl, out,
+                                                                      ctx->cam, ctx->cfg);
+  GFPL_LAUNCH_OK(ctx);
+  return GFPL_OK;
+}
+
+// ---- C1: estimateStereoUncertainty (stereoFrame.cpp:1448-1484) -------------------------------------
+__device__ __forceinline__ void cov_mat_2d_3d(const gfpl_camera& cam, double u, double v, double u_std, double d,
+                                              double d_std, double* cov) {
+  double cov2D[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // D5: off-diagonals are zero
+  cov2D[0] = u_std * u_std; cov2D[4] = u_std * u_std; cov2D[8] = d_std * d_std;
+  const double b = cam.b, d_2 = d * d;
+  double J[9], Jt[9], tmp[9];
+  J[0] = b / d; J[3] = 0.0; J[6] = 0.0;
+  J[1] = 0.0; J[4] = b / d; J[7] = 0.0;
+  J[2] = -(u - cam.cx) * b / d_2;
+  J[5] = -(v - cam.cy) * b / d_2;
+  J[8] = -cam.fx * b / d_2;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) Jt[j * 3 + i] = J[i * 3 + j];
+  matmul<3, 3, 3>(J, cov2D, tmp);
+  matmul<3, 3, 3>(tmp, Jt, cov);
+}
+
+__global__ void __launch_bounds__(128) stereo_uncertainty_kernel(DevStereoFrames fr, gfpl_line_cov* out,
+                                                                 gfpl_camera cam, gfpl_config cfg) {
+  const int p = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= fr.n_ln[p]) return;
+  const gfpl_line_feature& l = fr.ln[(size_t)p * fr.cap_ln + i];
+  const double ratio = fabs(l.le[0]) > 0.15 ? cfg.ratio_disp_std : cfg.ratio_disp_std_hor;
+  const double sdisp_std = ratio * l.sdisp, edisp_std = ratio * l.edisp;
+  gfpl_line_cov c;
+  cov_mat_2d_3d(cam, l.spl[0], l.spl[1], 1.0, l.sdisp, sdisp_std, c.covS);
+  cov_mat_2d_3d(cam, l.epl[0], l.epl[1], 1.0, l.edisp, edisp_std, c.covE);
+  out[(size_t)p * fr.cap_ln + i] = c;
+}
+
+int launch_stereo_uncertainty(gfpl_ctx* ctx, const DevStereoFrames& fr, gfpl_line_cov* out) {
+  if (fr.B <= 0 || fr.cap_ln <= 0) return GFPL_OK;
+  dim3 grid((fr.cap_ln + 127) / 128, fr.B);
+  stereo_uncertainty_kernel<<<grid, 128, 0, ctx->stream>>>(fr, out, ctx->cam, ctx->cfg);
+  GFPL_LAUNCH_OK(ctx);
+  return GFPL_OK;
+}
+
+}  // namespace gfpl
