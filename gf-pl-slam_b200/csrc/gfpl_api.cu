@@ -339,3 +339,451 @@ int gfpl_measure_peaks(gfpl_ctx* ctx, double* popc_tops, double* fp64_tflops) {
 }
 
 }  // extern "C"
+
+// =========================================================================================================
+// Stage entry points, whole step, resident replay
+// =========================================================================================================
+namespace gfpl {
+
+// scratch of one tracking step for B pairs
+struct StepWork {
+  Knn2Out pt_lr{}, pt_rl{}, ln_lr{}, ln_rl{};   // stereo knn (current frame)
+  Knn2Out pt_12{}, pt_21{}, ln_12{}, ln_21{};   // f2f knn
+  uint32_t* best_key = nullptr;                 // [B][cap_pt] hybrid point resolver
+  gfpl_line_cov* prev_cov = nullptr;            // [B][cap_ln]
+};
+
+static bool alloc_work(DevMem& m, int B, int cap_pt, int cap_ln, StepWork* w) {
+  size_t np = (size_t)B * cap_pt, nl = (size_t)B * cap_ln;
+  bool ok = alloc_knn(m, np, &w->pt_lr) && alloc_knn(m, np, &w->pt_rl) && alloc_knn(m, nl, &w->ln_lr) &&
+            alloc_knn(m, nl, &w->ln_rl) && alloc_knn(m, np, &w->pt_12) && alloc_knn(m, np, &w->pt_21) &&
+            alloc_knn(m, nl, &w->ln_12) && alloc_knn(m, nl, &w->ln_21);
+  w->best_key = m.alloc<uint32_t>(np);
+  w->prev_cov = m.alloc<gfpl_line_cov>(nl);
+  return ok && w->best_key && w->prev_cov;
+}
+
+static int run_stereo(gfpl_ctx* ctx, const DevRawFrames& raw, int variant, StepWork& w, DevStereoFrames curr) {
+  const int B = raw.B;
+  if (ctx->cfg.has_points)
+    CHECK(launch_knn2(ctx, B, raw.pdesc_l, raw.n_pt_l, raw.cap_pt, raw.pdesc_r, raw.n_pt_r, raw.cap_pt,
+                      GFPL_NORM_HAMMING, w.pt_lr, ctx->cfg.best_lr_matches ? w.pt_rl : Knn2Out{}));
+  if (ctx->cfg.has_lines)
+    CHECK(launch_knn2(ctx, B, raw.ldesc_l, raw.n_ln_l, raw.cap_ln, raw.ldesc_r, raw.n_ln_r, raw.cap_ln,
+                      variant == GFPL_STEREO_INITIAL ? GFPL_NORM_HAMMING : GFPL_NORM_HAMMING2, w.ln_lr,
+                      ctx->cfg.best_lr_matches ? w.ln_rl : Knn2Out{}));
+  return GFPL_OK;
+}
+
+static int run_f2f_knn(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr,
+                       const gfpl_frame_state* state, int mode, StepWork& w) {
+  const int B = prev.B;
+  const bool use_radius = ctx->cfg.best_lr_matches && ctx->cfg.lr_in_parallel;
+  if (ctx->cfg.has_points) {
+    if (mode == GFPL_F2F_BRUTE)
+      CHECK(launch_knn2(ctx, B, prev.pdesc, prev.n_pt, prev.cap_pt, curr.pdesc, curr.n_pt, curr.cap_pt,
+                        GFPL_NORM_HAMMING, w.pt_12, ctx->cfg.best_lr_matches ? w.pt_21 : Knn2Out{}));
+    else if (use_radius)
+      CHECK(launch_f2f_hybrid_points(ctx, prev, curr, state, w.best_key));
+    else {
+      CHECK(launch_knn2(ctx, B, prev.pdesc, prev.n_pt, prev.cap_pt, curr.pdesc, curr.n_pt, curr.cap_pt,
+                        GFPL_NORM_HAMMING, w.pt_12, Knn2Out{}));
+      CHECK(launch_f2f_hybrid_points_knn(ctx, prev, curr, state, w.pt_12, w.best_key));
+    }
+  }
+  if (ctx->cfg.has_lines)
+    CHECK(launch_knn2(ctx, B, prev.ldesc, prev.n_ln, prev.cap_ln, curr.ldesc, curr.n_ln, curr.cap_ln,
+                      GFPL_NORM_HAMMING, w.ln_12, ctx->cfg.best_lr_matches ? w.ln_21 : Knn2Out{}));
+  return GFPL_OK;
+}
+
+}  // namespace gfpl
+
+struct gfpl_replay {
+  gfpl_ctx* ctx = nullptr;
+  int B = 0, cap_pt = 0, cap_ln = 0;
+  std::vector<void*> owned;
+  DevRawFrames raw{};
+  DevStereoFrames prev{}, curr{};
+  DevTrackObs obs{};
+  gfpl_frame_state* state = nullptr;
+  gfpl_line_cut* cut = nullptr;
+  gfpl_pose_result* pose = nullptr;
+  StepWork w{};
+  cudaEvent_t ev[GFPL_NUM_STAGES + 1] = {};
+  int64_t h2d = 0, d2h = 0;
+  bool timed = false;
+  template <typename T>
+  T* alloc(size_t n) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+    owned.push_back(p);
+    return (T*)p;
+  }
+};
+
+extern "C" {
+
+int gfpl_stereo_match(gfpl_ctx* ctx, const gfpl_raw_frames* raw, int32_t variant, gfpl_stereo_frames* out) {
+  if (!ctx) return GFPL_E_INVALID;
+  REQUIRE(ctx, raw && out && raw->B >= 0 && raw->B == out->B);
+  REQUIRE(ctx, out->cap_pt >= raw->cap_pt && out->cap_ln >= raw->cap_ln);
+  REQUIRE(ctx, variant == GFPL_STEREO_INITIAL || variant == GFPL_STEREO_BRUTE);
+  if (raw->B == 0) return GFPL_OK;
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DevMem m(ctx);
+  DevRawFrames draw;
+  DevStereoFrames dcur;
+  StepWork w;
+  REQUIRE_MEM(ctx, mirror_raw(m, raw, &draw) && alloc_stereo(m, raw->B, raw->cap_pt, raw->cap_ln, &dcur) &&
+                       alloc_work(m, raw->B, raw->cap_pt, raw->cap_ln, &w));
+  CHECK(run_stereo(ctx, draw, variant, w, dcur));
+  CHECK(launch_stereo_accept(ctx, draw, variant, w.pt_lr, w.pt_rl, w.ln_lr, w.ln_rl, dcur));
+  download_stereo(ctx, out, dcur);
+  return finish(ctx);
+}
+
+int gfpl_stereo_uncertainty(gfpl_ctx* ctx, const gfpl_stereo_frames* frames, gfpl_line_cov* out) {
+  if (!ctx) return GFPL_E_INVALID;
+  REQUIRE(ctx, frames && out && frames->B >= 0);
+  if (frames->B == 0 || frames->cap_ln == 0) return GFPL_OK;
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DevMem m(ctx);
+  DevStereoFrames d;
+  REQUIRE_MEM(ctx, mirror_stereo(m, frames, &d));
+  size_t n = (size_t)frames->B * frames->cap_ln;
+  gfpl_line_cov* dc = m.alloc<gfpl_line_cov>(n);
+  REQUIRE_MEM(ctx, dc);
+  GFPL_CUDA_OK(ctx, cudaMemsetAsync(dc, 0, n * sizeof(gfpl_line_cov), ctx->stream));
+  CHECK(launch_stereo_uncertainty(ctx, d, dc));
+  download(ctx, out, dc, n);
+  return finish(ctx);
+}
+
+int gfpl_f2f_match(gfpl_ctx* ctx, const gfpl_stereo_frames* prev, const gfpl_stereo_frames* curr,
+                   const gfpl_frame_state* state, int32_t mode, gfpl_track_obs* out) {
+  if (!ctx) return GFPL_E_INVALID;
+  REQUIRE(ctx, prev && curr && state && out && prev->B == curr->B && prev->B == out->B && prev->B >= 0);
+  REQUIRE(ctx, mode == GFPL_F2F_HYBRID || mode == GFPL_F2F_BRUTE);
+  REQUIRE(ctx, out->cap_pt > 0 && out->cap_ln > 0);
+  if (prev->B == 0) return GFPL_OK;
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DevMem m(ctx);
+  DevStereoFrames dp, dc;
+  DevTrackObs dobs;
+  StepWork w;
+  const int cp = prev->cap_pt > curr->cap_pt ? prev->cap_pt : curr->cap_pt;
+  const int cl = prev->cap_ln > curr->cap_ln ? prev->cap_ln : curr->cap_ln;
+  REQUIRE_MEM(ctx, mirror_stereo(m, prev, &dp) && mirror_stereo(m, curr, &dc) &&
+                       alloc_obs(m, prev->B, out->cap_pt, out->cap_ln, &dobs) && alloc_work(m, prev->B, cp, cl, &w));
+  gfpl_frame_state* dstate = m.upload(state, prev->B);
+  REQUIRE_MEM(ctx, dstate);
+  CHECK(run_f2f_knn(ctx, dp, dc, dstate, mode, w));
+  CHECK(launch_f2f_accept(ctx, dp, dc, mode, w.best_key, w.pt_12, w.pt_21, w.ln_12, w.ln_21, dobs));
+  download_obs(ctx, out, dobs);
+  return finish(ctx);
+}
+
+int gfpl_linecut_submodular(gfpl_ctx* ctx, const double* DT_inv, gfpl_track_obs* obs, const gfpl_line_cov* prev_cov,
+                            int32_t cov_cap, gfpl_line_cut* cut) {
+  if (!ctx) return GFPL_E_INVALID;
+  REQUIRE(ctx, DT_inv && obs && prev_cov && cut && obs->B >= 0 && cov_cap > 0);
+  if (obs->B == 0) return GFPL_OK;
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DevMem m(ctx);
+  DevTrackObs dobs;
+  REQUIRE_MEM(ctx, mirror_obs(m, obs, &dobs));
+  size_t B = obs->B;
+  double* dDT = m.upload(DT_inv, B * 16);
+  gfpl_line_cov* dcov = m.upload(prev_cov, B * cov_cap);
+  gfpl_line_cut* dcut = m.alloc<gfpl_line_cut>(B * obs->cap_ln);
+  REQUIRE_MEM(ctx, dDT && dcov && dcut);
+  GFPL_CUDA_OK(ctx, cudaMemsetAsync(dcut, 0, B * obs->cap_ln * sizeof(gfpl_line_cut), ctx->stream));
+  CHECK(launch_linecut(ctx, dDT, nullptr, dobs, dcov, cov_cap, dcut));
+  download(ctx, cut, dcut, B * obs->cap_ln);
+  download(ctx, obs->ln, dobs.ln, B * obs->cap_ln);
+  return finish(ctx);
+}
+
+int gfpl_pose_hg(gfpl_ctx* ctx, const double* DT, const gfpl_track_obs* obs, double* H, double* g, double* e) {
+  if (!ctx) return GFPL_E_INVALID;
+  REQUIRE(ctx, DT && obs && H && g && e && obs->B >= 0);
+  if (obs->B == 0) return GFPL_OK;
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DevMem m(ctx);
+  DevTrackObs dobs;
+  REQUIRE_MEM(ctx, mirror_obs(m, obs, &dobs));
+  size_t B = obs->B;
+  double* dDT = m.upload(DT, B * 16);
+  double* dH = m.alloc<double>(B * 36);
+  double* dg = m.alloc<double>(B * 6);
+  double* de = m.alloc<double>(B);
+  REQUIRE_MEM(ctx, dDT && dH && dg && de);
+  CHECK(launch_pose_hg(ctx, dDT, dobs, dH, dg, de));
+  download(ctx, H, dH, B * 36);
+  download(ctx, g, dg, B * 6);
+  download(ctx, e, de, B);
+  return finish(ctx);
+}
+
+int gfpl_pose_optimize(gfpl_ctx* ctx, gfpl_track_obs* obs, const gfpl_frame_state* state, const double* DT_ini,
+                       int32_t overload, gfpl_pose_result* out) {
+  if (!ctx) return GFPL_E_INVALID;
+  REQUIRE(ctx, obs && state && out && obs->B >= 0);
+  REQUIRE(ctx, overload == GFPL_POSE_SEED_PREV_DT || overload == GFPL_POSE_SEED_GIVEN);
+  if (obs->B == 0) return GFPL_OK;
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DevMem m(ctx);
+  DevTrackObs dobs;
+  REQUIRE_MEM(ctx, mirror_obs(m, obs, &dobs));
+  size_t B = obs->B;
+  gfpl_frame_state* dstate = m.upload(state, B);
+  double* dDT = DT_ini ? m.upload(DT_ini, B * 16) : nullptr;
+  gfpl_pose_result* dout = m.alloc<gfpl_pose_result>(B);
+  REQUIRE_MEM(ctx, dstate && dout && (!DT_ini || dDT));
+  CHECK(launch_pose_optimize(ctx, dobs, dstate, dDT, overload, dout));
+  download(ctx, out, dout, B);
+  download(ctx, obs->pt_inlier, dobs.pt_inlier, B * obs->cap_pt);
+  download(ctx, obs->ln_inlier, dobs.ln_inlier, B * obs->cap_ln);
+  return finish(ctx);
+}
+
+// ---- whole step ------------------------------------------------------------------------------------------
+static int run_step(gfpl_ctx* ctx, const DevStereoFrames& prev, const gfpl_frame_state* state, const DevRawFrames& raw,
+                    int flags, DevStereoFrames curr, DevTrackObs obs, gfpl_line_cut* cut, gfpl_pose_result* pose,
+                    StepWork& w, cudaEvent_t* ev) {
+  const int variant = (flags & GFPL_TRACK_STEREO_INITIAL) ? GFPL_STEREO_INITIAL : GFPL_STEREO_BRUTE;
+  const int mode = (flags & GFPL_TRACK_F2F_BRUTE) ? GFPL_F2F_BRUTE : GFPL_F2F_HYBRID;
+  if (ev) cudaEventRecord(ev[0], ctx->stream);
+  CHECK(run_stereo(ctx, raw, variant, w, curr));
+  if (ev) cudaEventRecord(ev[1], ctx->stream);
+  CHECK(launch_stereo_accept(ctx, raw, variant, w.pt_lr, w.pt_rl, w.ln_lr, w.ln_rl, curr));
+  if (ev) cudaEventRecord(ev[2], ctx->stream);
+  CHECK(run_f2f_knn(ctx, prev, curr, state, mode, w));
+  if (ev) cudaEventRecord(ev[3], ctx->stream);
+  CHECK(launch_f2f_accept(ctx, prev, curr, mode, w.best_key, w.pt_12, w.pt_21, w.ln_12, w.ln_21, obs));
+  if (ev) cudaEventRecord(ev[4], ctx->stream);
+  if ((flags & GFPL_TRACK_LINECUT) && ctx->cfg.use_line_conf_cut && cut) {
+    CHECK(launch_stereo_uncertainty(ctx, prev, w.prev_cov));
+    CHECK(launch_linecut(ctx, nullptr, state, obs, w.prev_cov, prev.cap_ln, cut));
+  }
+  if (ev) cudaEventRecord(ev[5], ctx->stream);
+  CHECK(launch_pose_optimize(ctx, obs, state, nullptr,
+                             (flags & GFPL_TRACK_SEED_GIVEN) ? GFPL_POSE_SEED_GIVEN : GFPL_POSE_SEED_PREV_DT, pose));
+  if (ev) cudaEventRecord(ev[6], ctx->stream);
+  return GFPL_OK;
+}
+
+int gfpl_track(gfpl_ctx* ctx, const gfpl_stereo_frames* prev, const gfpl_frame_state* state,
+               const gfpl_raw_frames* curr_raw, int32_t flags, gfpl_stereo_frames* curr, gfpl_track_obs* obs,
+               gfpl_line_cut* cut, gfpl_pose_result* pose) {
+  if (!ctx) return GFPL_E_INVALID;
+  REQUIRE(ctx, prev && state && curr_raw && curr && obs && pose);
+  const int B = curr_raw->B;
+  REQUIRE(ctx, B >= 0 && prev->B == B && curr->B == B && obs->B == B);
+  REQUIRE(ctx, curr->cap_pt == curr_raw->cap_pt && curr->cap_ln == curr_raw->cap_ln);
+  REQUIRE(ctx, obs->cap_pt > 0 && obs->cap_ln > 0);
+  if (B == 0) return GFPL_OK;
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DevMem m(ctx);
+  DevRawFrames draw;
+  DevStereoFrames dprev, dcurr;
+  DevTrackObs dobs;
+  StepWork w;
+  const int cp = prev->cap_pt > curr->cap_pt ? prev->cap_pt : curr->cap_pt;
+  const int cl = prev->cap_ln > curr->cap_ln ? prev->cap_ln : curr->cap_ln;
+  REQUIRE_MEM(ctx, mirror_raw(m, curr_raw, &draw) && mirror_stereo(m, prev, &dprev) &&
+                       alloc_stereo(m, B, curr->cap_pt, curr->cap_ln, &dcurr) &&
+                       alloc_obs(m, B, obs->cap_pt, obs->cap_ln, &dobs) && alloc_work(m, B, cp, cl, &w));
+  gfpl_frame_state* dstate = m.upload(state, (size_t)B);
+  gfpl_pose_result* dpose = m.alloc<gfpl_pose_result>(B);
+  gfpl_line_cut* dcut = cut ? m.alloc<gfpl_line_cut>((size_t)B * obs->cap_ln) : nullptr;
+  REQUIRE_MEM(ctx, dstate && dpose && (!cut || dcut));
+  if (dcut) GFPL_CUDA_OK(ctx, cudaMemsetAsync(dcut, 0, (size_t)B * obs->cap_ln * sizeof(gfpl_line_cut), ctx->stream));
+  CHECK(run_step(ctx, dprev, dstate, draw, flags, dcurr, dobs, dcut, dpose, w, nullptr));
+  download_stereo(ctx, curr, dcurr);
+  download_obs(ctx, obs, dobs);
+  if (cut) download(ctx, cut, dcut, (size_t)B * obs->cap_ln);
+  download(ctx, pose, dpose, (size_t)B);
+  return finish(ctx);
+}
+
+// ---- resident replay ---------------------------------------------------------------------------------------
+int gfpl_replay_create(gfpl_ctx* ctx, int32_t B, int32_t cap_pt, int32_t cap_ln, gfpl_replay** out) {
+  if (!ctx || !out) return GFPL_E_INVALID;
+  REQUIRE(ctx, B > 0 && cap_pt > 0 && cap_ln > 0);
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  gfpl_replay* rp = new (std::nothrow) gfpl_replay();
+  if (!rp) return GFPL_E_NOMEM;
+  rp->ctx = ctx; rp->B = B; rp->cap_pt = cap_pt; rp->cap_ln = cap_ln;
+  size_t np = (size_t)B * cap_pt, nl = (size_t)B * cap_ln;
+  const int ocp = ctx->cfg.max_point_match_num, ocl = ctx->cfg.max_line_match_num;
+  DevRawFrames& r = rp->raw;
+  r.B = B; r.cap_pt = cap_pt; r.cap_ln = cap_ln;
+  r.n_pt_l = rp->alloc<int32_t>(B); r.n_pt_r = rp->alloc<int32_t>(B);
+  r.n_ln_l = rp->alloc<int32_t>(B); r.n_ln_r = rp->alloc<int32_t>(B);
+  r.pt_l = rp->alloc<gfpl_keypoint>(np); r.pt_r = rp->alloc<gfpl_keypoint>(np);
+  r.pdesc_l = rp->alloc<uint8_t>(np * 32); r.pdesc_r = rp->alloc<uint8_t>(np * 32);
+  r.ln_l = rp->alloc<gfpl_keyline>(nl); r.ln_r = rp->alloc<gfpl_keyline>(nl);
+  r.ldesc_l = rp->alloc<uint8_t>(nl * 32); r.ldesc_r = rp->alloc<uint8_t>(nl * 32);
+  for (DevStereoFrames* f : {&rp->prev, &rp->curr}) {
+    f->B = B; f->cap_pt = cap_pt; f->cap_ln = cap_ln;
+    f->n_pt = rp->alloc<int32_t>(B); f->n_ln = rp->alloc<int32_t>(B);
+    f->pt = rp->alloc<gfpl_point_feature>(np); f->pdesc = rp->alloc<uint8_t>(np * 32);
+    f->ln = rp->alloc<gfpl_line_feature>(nl); f->ldesc = rp->alloc<uint8_t>(nl * 32);
+  }
+  DevTrackObs& o = rp->obs;
+  o.B = B; o.cap_pt = ocp; o.cap_ln = ocl;
+  o.n_pt = rp->alloc<int32_t>(B); o.n_ln = rp->alloc<int32_t>(B);
+  o.pt = rp->alloc<gfpl_pt_obs>((size_t)B * ocp); o.pt_inlier = rp->alloc<uint8_t>((size_t)B * ocp);
+  o.ln = rp->alloc<gfpl_ln_obs>((size_t)B * ocl); o.ln_inlier = rp->alloc<uint8_t>((size_t)B * ocl);
+  rp->state = rp->alloc<gfpl_frame_state>(B);
+  rp->cut = rp->alloc<gfpl_line_cut>((size_t)B * ocl);
+  rp->pose = rp->alloc<gfpl_pose_result>(B);
+  StepWork& w = rp->w;
+  for (Knn2Out* k : {&w.pt_lr, &w.pt_rl, &w.pt_12, &w.pt_21}) { k->idx = rp->alloc<int2>(np); k->dist = rp->alloc<float2>(np); }
+  for (Knn2Out* k : {&w.ln_lr, &w.ln_rl, &w.ln_12, &w.ln_21}) { k->idx = rp->alloc<int2>(nl); k->dist = rp->alloc<float2>(nl); }
+  w.best_key = rp->alloc<uint32_t>(np);
+  w.prev_cov = rp->alloc<gfpl_line_cov>(nl);
+  bool ok = true;
+  for (void* p : rp->owned) ok = ok && p;
+  ok = ok && rp->owned.size() == 12 + 12 + 6 + 3 + 16 + 2;
+  if (!ok || !w.prev_cov) {
+    gfpl_replay_destroy(rp);
+    set_last_error(ctx, "device allocation failed for a replay of %d pairs", B);
+    return GFPL_E_NOMEM;
+  }
+  cudaMemset(rp->cut, 0, (size_t)B * ocl * sizeof(gfpl_line_cut));
+  for (auto& e : rp->ev) cudaEventCreate(&e);
+  *out = rp;
+  return GFPL_OK;
+}
+
+void gfpl_replay_destroy(gfpl_replay* rp) {
+  if (!rp) return;
+  cudaSetDevice(rp->ctx->device);
+  cudaStreamSynchronize(rp->ctx->stream);
+  for (void* p : rp->owned) cudaFree(p);
+  for (auto& e : rp->ev)
+    if (e) cudaEventDestroy(e);
+  delete rp;
+}
+
+#define H2D(dst, src, n)                                                                                   \
+  do {                                                                                                     \
+    size_t _b = (size_t)(n) * sizeof(*(src));                                                              \
+    GFPL_CUDA_OK(ctx, cudaMemcpyAsync((void*)(dst), (src), _b, cudaMemcpyHostToDevice, ctx->stream));      \
+    rp->h2d += (int64_t)_b;                                                                                \
+  } while (0)
+#define D2H(dst, src, n)                                                                                   \
+  do {                                                                                                     \
+    size_t _b = (size_t)(n) * sizeof(*(src));                                                              \
+    GFPL_CUDA_OK(ctx, cudaMemcpyAsync((dst), (src), _b, cudaMemcpyDeviceToHost, ctx->stream));             \
+    rp->d2h += (int64_t)_b;                                                                                \
+  } while (0)
+
+int gfpl_replay_upload(gfpl_replay* rp, const gfpl_stereo_frames* prev, const gfpl_frame_state* state,
+                       const gfpl_raw_frames* raw) {
+  if (!rp) return GFPL_E_INVALID;
+  gfpl_ctx* ctx = rp->ctx;
+  REQUIRE(ctx, prev && state && raw);
+  REQUIRE(ctx, prev->B == rp->B && raw->B == rp->B);
+  REQUIRE(ctx, prev->cap_pt == rp->cap_pt && prev->cap_ln == rp->cap_ln && raw->cap_pt == rp->cap_pt && raw->cap_ln == rp->cap_ln);
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  rp->h2d = 0;
+  size_t B = rp->B, np = B * rp->cap_pt, nl = B * rp->cap_ln;
+  H2D(rp->raw.n_pt_l, raw->n_pt_l, B); H2D(rp->raw.n_pt_r, raw->n_pt_r, B);
+  H2D(rp->raw.n_ln_l, raw->n_ln_l, B); H2D(rp->raw.n_ln_r, raw->n_ln_r, B);
+  H2D(rp->raw.pt_l, raw->pt_l, np); H2D(rp->raw.pt_r, raw->pt_r, np);
+  H2D(rp->raw.pdesc_l, raw->pdesc_l, np * 32); H2D(rp->raw.pdesc_r, raw->pdesc_r, np * 32);
+  H2D(rp->raw.ln_l, raw->ln_l, nl); H2D(rp->raw.ln_r, raw->ln_r, nl);
+  H2D(rp->raw.ldesc_l, raw->ldesc_l, nl * 32); H2D(rp->raw.ldesc_r, raw->ldesc_r, nl * 32);
+  H2D(rp->prev.n_pt, prev->n_pt, B); H2D(rp->prev.n_ln, prev->n_ln, B);
+  H2D(rp->prev.pt, prev->pt, np); H2D(rp->prev.pdesc, prev->pdesc, np * 32);
+  H2D(rp->prev.ln, prev->ln, nl); H2D(rp->prev.ldesc, prev->ldesc, nl * 32);
+  H2D(rp->state, state, B);
+  return GFPL_OK;
+}
+
+int gfpl_replay_run(gfpl_replay* rp, int32_t flags) {
+  if (!rp) return GFPL_E_INVALID;
+  gfpl_ctx* ctx = rp->ctx;
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  rp->timed = true;
+  return run_step(ctx, rp->prev, rp->state, rp->raw, flags, rp->curr, rp->obs, rp->cut, rp->pose, rp->w, rp->ev);
+}
+
+int gfpl_replay_download(gfpl_replay* rp, gfpl_pose_result* pose, gfpl_track_obs* obs, gfpl_line_cut* cut,
+                         gfpl_stereo_frames* curr) {
+  if (!rp) return GFPL_E_INVALID;
+  gfpl_ctx* ctx = rp->ctx;
+  REQUIRE(ctx, pose);
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  rp->d2h = 0;
+  size_t B = rp->B;
+  D2H(pose, rp->pose, B);
+  if (obs) {
+    REQUIRE(ctx, obs->B == rp->B && obs->cap_pt == rp->obs.cap_pt && obs->cap_ln == rp->obs.cap_ln);
+    D2H(obs->n_pt, rp->obs.n_pt, B); D2H(obs->n_ln, rp->obs.n_ln, B);
+    D2H(obs->pt, rp->obs.pt, B * rp->obs.cap_pt); D2H(obs->pt_inlier, rp->obs.pt_inlier, B * rp->obs.cap_pt);
+    D2H(obs->ln, rp->obs.ln, B * rp->obs.cap_ln); D2H(obs->ln_inlier, rp->obs.ln_inlier, B * rp->obs.cap_ln);
+  }
+  if (cut) D2H(cut, rp->cut, B * rp->obs.cap_ln);
+  if (curr) {
+    REQUIRE(ctx, curr->B == rp->B && curr->cap_pt == rp->cap_pt && curr->cap_ln == rp->cap_ln);
+    D2H(curr->n_pt, rp->curr.n_pt, B); D2H(curr->n_ln, rp->curr.n_ln, B);
+    D2H(curr->pt, rp->curr.pt, B * rp->cap_pt); D2H(curr->pdesc, rp->curr.pdesc, B * rp->cap_pt * 32);
+    D2H(curr->ln, rp->curr.ln, B * rp->cap_ln); D2H(curr->ldesc, rp->curr.ldesc, B * rp->cap_ln * 32);
+  }
+  return GFPL_OK;
+}
+
+int64_t gfpl_replay_h2d_bytes(const gfpl_replay* rp) { return rp ? rp->h2d : 0; }
+int64_t gfpl_replay_d2h_bytes(const gfpl_replay* rp) { return rp ? rp->d2h : 0; }
+void* gfpl_replay_pose_device_ptr(gfpl_replay* rp) { return rp ? (void*)rp->pose : nullptr; }
+
+int gfpl_replay_stage_ms(gfpl_replay* rp, float* ms) {
+  if (!rp || !ms) return GFPL_E_INVALID;
+  gfpl_ctx* ctx = rp->ctx;
+  REQUIRE(ctx, rp->timed);
+  GFPL_CUDA_OK(ctx, cudaEventSynchronize(rp->ev[6]));
+  for (int i = 0; i < 6; i++) GFPL_CUDA_OK(ctx, cudaEventElapsedTime(&ms[i], rp->ev[i], rp->ev[i + 1]));
+  GFPL_CUDA_OK(ctx, cudaEventElapsedTime(&ms[6], rp->ev[0], rp->ev[6]));
+  return GFPL_OK;
+}
+
+// ---- L2 ---------------------------------------------------------------------------------------------------
+int gfpl_lba_assemble(gfpl_ctx* ctx, const gfpl_lba_problem* pb, gfpl_lba_blocks* out) {
+  if (!ctx) return GFPL_E_INVALID;
+  REQUIRE(ctx, pb && out && pb->Nkf >= 0 && pb->Npt >= 0 && pb->Nls >= 0 && pb->n_pt_obs >= 0 && pb->n_ls_obs >= 0);
+  REQUIRE(ctx, out->Hkk && out->Hpp && out->Hll && out->Hpk && out->Hlk && out->g && out->err);
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DevMem m(ctx);
+  gfpl_lba_problem d = *pb;
+  d.kf_Tkw = m.upload(pb->kf_Tkw, (size_t)pb->Nkf * 16);
+  d.X_pt = m.upload(pb->X_pt, (size_t)pb->Npt * 3);
+  d.X_ls = m.upload(pb->X_ls, (size_t)pb->Nls * 6);
+  d.pt_obs_lm = m.upload(pb->pt_obs_lm, pb->n_pt_obs); d.pt_obs_kf = m.upload(pb->pt_obs_kf, pb->n_pt_obs);
+  d.pt_obs_fix = m.upload(pb->pt_obs_fix, pb->n_pt_obs);
+  d.pt_obs_uv = m.upload(pb->pt_obs_uv, (size_t)pb->n_pt_obs * 2); d.pt_obs_s2 = m.upload(pb->pt_obs_s2, pb->n_pt_obs);
+  d.ls_obs_lm = m.upload(pb->ls_obs_lm, pb->n_ls_obs); d.ls_obs_kf = m.upload(pb->ls_obs_kf, pb->n_ls_obs);
+  d.ls_obs_fix = m.upload(pb->ls_obs_fix, pb->n_ls_obs);
+  d.ls_obs_le = m.upload(pb->ls_obs_le, (size_t)pb->n_ls_obs * 3); d.ls_obs_s2 = m.upload(pb->ls_obs_s2, pb->n_ls_obs);
+  d.fix_Tkw = m.upload(pb->fix_Tkw, (size_t)pb->n_fix * 16);
+  const size_t N = 6 * (size_t)pb->Nkf + 3 * (size_t)pb->Npt + 6 * (size_t)pb->Nls;
+  gfpl_lba_blocks o;
+  o.Hkk = m.alloc<double>((size_t)pb->Nkf * 36); o.Hpp = m.alloc<double>((size_t)pb->Npt * 9);
+  o.Hll = m.alloc<double>((size_t)pb->Nls * 36); o.Hpk = m.alloc<double>((size_t)pb->n_pt_obs * 18);
+  o.Hlk = m.alloc<double>((size_t)pb->n_ls_obs * 36); o.g = m.alloc<double>(N); o.err = m.alloc<double>(1);
+  REQUIRE_MEM(ctx, d.kf_Tkw && d.X_pt && d.X_ls && d.pt_obs_lm && d.pt_obs_kf && d.pt_obs_fix && d.pt_obs_uv &&
+                       d.pt_obs_s2 && d.ls_obs_lm && d.ls_obs_kf && d.ls_obs_fix && d.ls_obs_le && d.ls_obs_s2 &&
+                       d.fix_Tkw && o.Hkk && o.Hpp && o.Hll && o.Hpk && o.Hlk && o.g && o.err);
+  CHECK(launch_lba_assemble(ctx, d, o));
+  download(ctx, out->Hkk, o.Hkk, (size_t)pb->Nkf * 36); download(ctx, out->Hpp, o.Hpp, (size_t)pb->Npt * 9);
+  download(ctx, out->Hll, o.Hll, (size_t)pb->Nls * 36); download(ctx, out->Hpk, o.Hpk, (size_t)pb->n_pt_obs * 18);
+  download(ctx, out->Hlk, o.Hlk, (size_t)pb->n_ls_obs * 36); download(ctx, out->g, o.g, N);
+  download(ctx, out->err, o.err, 1);
+  return finish(ctx);
+}
+
+}  // extern "C"

@@ -212,7 +212,7 @@ __device__ __noinline__ void sym_eigenvalues(const double* Ain, double* ev) {
 }
 
 // ---- 6x6 pivoted LDLT solve (LDLT<Matrix6d>::solve, stereoFrameHandler.cpp:2045-2046) --------------
-__device__ __noinline__ void ldlt6_solve(const double* Hin, const double* g, double* x) {
+static __device__ __noinline__ void ldlt6_solve(const double* Hin, const double* g, double* x) {
   const int n = 6;
   double A[36];
   int perm[6];
@@ -260,7 +260,7 @@ __device__ __noinline__ void ldlt6_solve(const double* Hin, const double* g, dou
 }
 
 // ---- 6x6 inverse by partial-pivot LU (Matrix6d::inverse(), stereoFrameHandler.cpp:2054) -----------
-__device__ __noinline__ void inverse6(const double* Hin, double* inv) {
+static __device__ __noinline__ void inverse6(const double* Hin, double* inv) {
   const int n = 6;
   double A[36], B[36];
   for (int i = 0; i < 36; i++) { A[i] = Hin[i]; B[i] = (i % 7 == 0) ? 1.0 : 0.0; }

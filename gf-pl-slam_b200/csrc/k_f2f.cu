@@ -1,0 +1,339 @@
+// k_f2f.cu — frame-to-frame matching: the fused radius + projection-gate search of
+// StereoFrameHandler::crossFrameMatching_Hybrid (reference stereoFrameHandler.cpp:451-603) and the accept
+// loops of _Hybrid (lines, :607-686) and _Brute (:698-860).
+//
+// Hybrid points.  The reference radius-matches every previous point against the current frame, keeps
+// every candidate whose projection (projectPrev3DPoint, stereoFrame.cpp:1550-1570) lies within 10 px,
+// inserts them in a multimap keyed by the CURRENT index and resolves each key to the smallest distance
+// (ties -> first inserted = lowest previous index).  That is a per-current-point arg-min over previous
+// points under two gates, so it needs no variable-length lists: one thread per current point streams the
+// previous descriptors (TMA-bulk staged) and keeps min(distance<<20 | prev_idx) over gated candidates.
+// POPC-bound like K1; algorithmic work = n_prev*n_curr pair distances.
+#include "gfpl_hamming.cuh"
+#include "gfpl_internal.h"
+#include "gfpl_math.cuh"
+
+namespace gfpl {
+
+constexpr int F2F_TILE_ROWS = 256;
+constexpr int F2F_THREADS = 160;  // 300 current points -> 2 CTAs x 160 (94 % lane use)
+
+__device__ __forceinline__ void project_prev_point(const gfpl_camera& cam, const double* prev_Tfw,
+                                                   const double* curr_Tfw_inv, const double* P, double* uv) {
+  const double v[4] = {P[0], P[1], P[2], 1.0};
+  double w[4], c[4];
+  matmul<4, 4, 1>(prev_Tfw, v, w);
+  matmul<4, 4, 1>(curr_Tfw_inv, w, c);
+  projection(cam, c, uv);
+}
+
+// shared prologue: predicted pose, its inverse, and the projections of all previous points into smem
+__device__ __forceinline__ void stage_projections(const DevStereoFrames& prev, const gfpl_frame_state* state, int p,
+                                                  int n_prev, const gfpl_camera& cam, double* s_T /*[32]*/,
+                                                  double2* s_proj) {
+  if (threadIdx.x == 0) {
+    double Tc[16], Tci[16];
+    matmul<4, 4, 4>(state[p].Tfw, state[p].DT, Tc);  // predictFramePose (stereoFrameHandler.cpp:157)
+    inverse4(Tc, Tci);
+    for (int i = 0; i < 16; i++) { s_T[i] = state[p].Tfw[i]; s_T[16 + i] = Tci[i]; }
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < n_prev; q += blockDim.x) {
+    double uv[2];
+    project_prev_point(cam, s_T, s_T + 16, prev.pt[(size_t)p * prev.cap_pt + q].P, uv);
+    s_proj[q] = make_double2(uv[0], uv[1]);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(F2F_THREADS)
+f2f_hybrid_points_kernel(DevStereoFrames prev, DevStereoFrames curr, const gfpl_frame_state* __restrict__ state,
+                         uint32_t* __restrict__ best_key, gfpl_camera cam, gfpl_config cfg) {
+  extern __shared__ __align__(128) uint8_t s_dyn[];
+  uint8_t* s_train = s_dyn;                                                  // [2][TILE*32]
+  double2* s_proj = reinterpret_cast<double2*>(s_dyn + 2 * F2F_TILE_ROWS * 32);  // [prev.cap_pt]
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ double s_T[32];
+
+  const int p = blockIdx.y;
+  const int n_prev = prev.n_pt[p], n_curr = curr.n_pt[p];
+  const int t0 = blockIdx.x * blockDim.x;
+  if (t0 >= n_curr) return;
+  const int t = t0 + threadIdx.x;
+  const bool active = cfg.has_points && n_prev > 0;
+
+  uint32_t best = KEY_NONE;
+  if (active) {
+    stage_projections(prev, state, p, n_prev, cam, s_T, s_proj);
+    const int tq = min(t, n_curr - 1);
+    const Desc256 qd = load_desc_global(curr.pdesc + ((size_t)p * curr.cap_pt + tq) * 32);
+    const gfpl_point_feature& cf = curr.pt[(size_t)p * curr.cap_pt + tq];
+    const double plx = cf.pl[0], ply = cf.pl[1];
+    const float radius = (float)cfg.point_match_radius;
+    TrainPipe<F2F_TILE_ROWS> pipe;
+    pipe.init(s_train, s_bar, prev.pdesc + (size_t)p * prev.cap_pt * 32, n_prev);
+    for (int tile = 0; tile < pipe.ntiles; tile++) {
+      const uint4* rows = reinterpret_cast<const uint4*>(pipe.acquire(tile));
+      const int n = pipe.rows_in(tile);
+      const int q0 = tile * F2F_TILE_ROWS;
+#pragma unroll 4
+      for (int r = 0; r < n; r++) {
+        const uint32_t d = hamming256<GFPL_NORM_HAMMING>(qd, rows[2 * r], rows[2 * r + 1]);
+        if ((float)d <= radius) {  // radiusMatch is inclusive
+          const double2 pr = s_proj[q0 + r];
+          const double dx = pr.x - plx, dy = pr.y - ply;
+          if (!(sqrt(dx * dx + dy * dy) > cfg.f2f_point_window)) best = min(best, make_key(d, q0 + r));
+        }
+      }
+      pipe.release(tile);
+    }
+  }
+  if (t < n_curr) best_key[(size_t)p * curr.cap_pt + t] = best;
+}
+
+int launch_f2f_hybrid_points(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr,
+                             const gfpl_frame_state* state, uint32_t* best_key) {
+  if (prev.B <= 0 || curr.cap_pt <= 0) return GFPL_OK;
+  const size_t smem = 2 * F2F_TILE_ROWS * 32 + (size_t)prev.cap_pt * sizeof(double2);
+  if (smem > 48 * 1024)
+    GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(f2f_hybrid_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((curr.cap_pt + F2F_THREADS - 1) / F2F_THREADS, prev.B);
+  f2f_hybrid_points_kernel<<<grid, F2F_THREADS, smem, ctx->stream>>>(prev, curr, state, best_key, ctx->cam, ctx->cfg);
+  GFPL_LAUNCH_OK(ctx);
+  return GFPL_OK;
+}
+
+// knn-candidate variant (bestLRMatches && lrInParallel false, stereoFrameHandler.cpp:484-493): the two nearest
+// current rows of every previous point are the candidates.
+__global__ void __launch_bounds__(256)
+f2f_hybrid_points_knn_kernel(DevStereoFrames prev, DevStereoFrames curr, const gfpl_frame_state* __restrict__ state,
+                             Knn2Out pt_12, uint32_t* __restrict__ best_key, gfpl_camera cam, gfpl_config cfg) {
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  double2* s_proj = reinterpret_cast<double2*>(s_dyn);                               // [prev.cap_pt]
+  uint32_t* s_best = reinterpret_cast<uint32_t*>(s_dyn + (size_t)prev.cap_pt * 16);  // [curr.cap_pt]
+  __shared__ double s_T[32];
+  const int p = blockIdx.x;
+  const int n_prev = prev.n_pt[p], n_curr = curr.n_pt[p];
+  for (int t = threadIdx.x; t < n_curr; t += blockDim.x) s_best[t] = KEY_NONE;
+  if (cfg.has_points && n_prev > 0 && n_curr >= 2) {  // D3
+    stage_projections(prev, state, p, n_prev, cam, s_T, s_proj);
+    for (int q = threadIdx.x; q < n_prev; q += blockDim.x) {
+      const int2 mi = pt_12.idx[(size_t)p * prev.cap_pt + q];
+      const float2 md = pt_12.dist[(size_t)p * prev.cap_pt + q];
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const int t = k ? mi.y : mi.x;
+        const float d = k ? md.y : md.x;
+        const gfpl_point_feature& cf = curr.pt[(size_t)p * curr.cap_pt + t];
+        const double dx = s_proj[q].x - cf.pl[0], dy = s_proj[q].y - cf.pl[1];
+        if (!(sqrt(dx * dx + dy * dy) > cfg.f2f_point_window)) atomicMin(&s_best[t], make_key((uint32_t)d, q));
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < n_curr; t += blockDim.x) best_key[(size_t)p * curr.cap_pt + t] = s_best[t];
+}
+
+int launch_f2f_hybrid_points_knn(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr,
+                                 const gfpl_frame_state* state, Knn2Out pt_12, uint32_t* best_key) {
+  if (prev.B <= 0 || curr.cap_pt <= 0) return GFPL_OK;
+  const size_t smem = (size_t)prev.cap_pt * 16 + (size_t)curr.cap_pt * 4;
+  if (smem > 48 * 1024)
+    GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(f2f_hybrid_points_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  f2f_hybrid_points_knn_kernel<<<prev.B, 256, smem, ctx->stream>>>(prev, curr, state, pt_12, best_key, ctx->cam, ctx->cfg);
+  GFPL_LAUNCH_OK(ctx);
+  return GFPL_OK;
+}
+
+// ---- accept loops ------------------------------------------------------------------------------------
+constexpr int ACC_THREADS = 256;
+
+__device__ __forceinline__ int block_compact_acc(bool pred, int& base, int* s_warp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, pred);
+  if (lane == 0) s_warp[warp] = __popc(bal);
+  __syncthreads();
+  int before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < ACC_THREADS / 32; w++) {
+    int c = s_warp[w];
+    before += (w < warp) ? c : 0;
+    total += c;
+  }
+  const int slot = base + before + __popc(bal & ((1u << lane) - 1));
+  base += total;
+  __syncthreads();
+  return slot;
+}
+
+__device__ float block_select_acc(const float* v, int n, int rank, float* s_out) {
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const float x = v[j];
+    int r = 0;
+    for (int k = 0; k < n; k++) {
+      const float y = v[k];
+      r += (y < x) || (y == x && k < j);
+    }
+    if (r == rank) *s_out = x;
+  }
+  __syncthreads();
+  const float out = *s_out;
+  __syncthreads();
+  return out;
+}
+
+__device__ __forceinline__ void write_pt_obs(const DevStereoFrames& prev, const DevStereoFrames& curr, int p, int q,
+                                             int t, gfpl_pt_obs* o) {
+  const gfpl_point_feature& pf = prev.pt[(size_t)p * prev.cap_pt + q];
+  const gfpl_point_feature& cf = curr.pt[(size_t)p * curr.cap_pt + t];
+  o->P[0] = pf.P[0]; o->P[1] = pf.P[1]; o->P[2] = pf.P[2];
+  o->pl_obs[0] = cf.pl[0]; o->pl_obs[1] = cf.pl[1];
+  o->sigma2 = pf.sigma2;
+  o->prev_idx = q; o->curr_idx = t;
+}
+
+__global__ void __launch_bounds__(ACC_THREADS)
+f2f_accept_kernel(DevStereoFrames prev, DevStereoFrames curr, int mode, const uint32_t* __restrict__ best_key,
+                  Knn2Out pt_12, Knn2Out pt_21, Knn2Out ln_12, Knn2Out ln_21, DevTrackObs out, gfpl_config cfg) {
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  const int vcap = max(prev.cap_pt, prev.cap_ln);
+  float* s_v = reinterpret_cast<float*>(s_dyn);                  // [max(prev.cap_pt, prev.cap_ln)]
+  int* s_last = reinterpret_cast<int*>(s_dyn + (size_t)vcap * 4);  // [prev.cap_pt]
+  __shared__ int s_warp[ACC_THREADS / 32 + 1];
+  __shared__ float s_sel;
+  const int p = blockIdx.x;
+  const size_t op = (size_t)p * out.cap_pt, ol = (size_t)p * out.cap_ln;
+  const int pt_cap = min(cfg.max_point_match_num, out.cap_pt);
+  const int ln_cap = min(cfg.max_line_match_num, out.cap_ln);
+
+  // ---- points --------------------------------------------------------------------------------------
+  {
+    const int n_prev = prev.n_pt[p], n_curr = curr.n_pt[p];
+    int base = 0;
+    if (mode == GFPL_F2F_HYBRID) {
+      // resolver of stereoFrameHandler.cpp:551-599 with the semantics of SURVEY A.4 D2: ascending current index
+      if (cfg.has_points && n_prev > 0 && n_curr > 0) {
+        for (int q = threadIdx.x; q < n_prev; q += ACC_THREADS) s_last[q] = -1;
+        __syncthreads();
+        for (int t0 = 0; t0 < n_curr; t0 += ACC_THREADS) {
+          const int t = t0 + threadIdx.x;
+          const uint32_t key = t < n_curr ? best_key[(size_t)p * curr.cap_pt + t] : KEY_NONE;
+          const bool keep = key != KEY_NONE;
+          const int slot = block_compact_acc(keep, base, s_warp);
+          if (keep && slot < pt_cap) {
+            const int q = (int)(key & KEY_IDX_MASK);
+            write_pt_obs(prev, curr, p, q, t, &out.pt[op + slot]);
+            out.pt_inlier[op + slot] = 1;
+            atomicMax(&s_last[q], t);
+          }
+        }
+        base = min(base, pt_cap);
+        __syncthreads();
+        // D9: a previous point that won several keys is one PointFeature: pl_obs = its last assignment
+        for (int k = threadIdx.x; k < base; k += ACC_THREADS) {
+          gfpl_pt_obs& o = out.pt[op + k];
+          const int tl = s_last[o.prev_idx];
+          if (tl != o.curr_idx) {
+            const gfpl_point_feature& cf = curr.pt[(size_t)p * curr.cap_pt + tl];
+            o.pl_obs[0] = cf.pl[0]; o.pl_obs[1] = cf.pl[1];
+          }
+        }
+      }
+    } else {
+      // crossFrameMatching_Brute (stereoFrameHandler.cpp:701-771)
+      if (cfg.has_points && n_prev >= 2 && n_curr >= 2) {  // D3
+        for (int j = threadIdx.x; j < n_prev; j += ACC_THREADS) s_v[j] = pt_12.dist[(size_t)p * prev.cap_pt + j].x;
+        __syncthreads();
+        const float budget = block_select_acc(s_v, n_prev, min(cfg.max_point_match_num, n_prev) - 1, &s_sel);
+        const double budget_dist_th = (double)budget;
+        for (int i0 = 0; i0 < n_prev; i0 += ACC_THREADS) {
+          const int i = i0 + threadIdx.x;
+          bool keep = false;
+          int tdx = 0;
+          if (i < n_prev) {
+            const int2 mi = pt_12.idx[(size_t)p * prev.cap_pt + i];
+            const float2 md = pt_12.dist[(size_t)p * prev.cap_pt + i];
+            tdx = mi.x;
+            const int rl = cfg.best_lr_matches ? pt_21.idx[(size_t)p * curr.cap_pt + tdx].x : i;
+            if (!((double)md.x > cfg.budget_slack * budget_dist_th)) {
+              const double dist_12 = (double)(md.x / md.y);
+              keep = (i == rl) && dist_12 <= cfg.max_ratio_12_p;
+            }
+          }
+          const int slot = block_compact_acc(keep, base, s_warp);
+          if (keep && slot < pt_cap) {
+            write_pt_obs(prev, curr, p, i, tdx, &out.pt[op + slot]);
+            out.pt_inlier[op + slot] = 1;
+          }
+        }
+        base = min(base, pt_cap);
+      }
+    }
+    if (threadIdx.x == 0) out.n_pt[p] = base;
+    __syncthreads();
+  }
+
+  // ---- lines (stereoFrameHandler.cpp:607-686 == 775-851) -------------------------------------------------
+  {
+    const int n_prev = prev.n_ln[p], n_curr = curr.n_ln[p];
+    int base = 0;
+    if (cfg.has_lines && n_prev >= 2 && n_curr >= 2) {  // D3
+      for (int j = threadIdx.x; j < n_prev; j += ACC_THREADS) {
+        const float2 md = ln_12.dist[(size_t)p * prev.cap_ln + j];
+        s_v[j] = fabsf((float)((double)(md.y - md.x) - cfg.mad_uninit_value));
+      }
+      __syncthreads();
+      const float med = block_select_acc(s_v, n_prev, n_prev / 2, &s_sel);
+      const double nn12_dist_th = (1.4826 * (double)med) * cfg.desc_th_l;
+      for (int j = threadIdx.x; j < n_prev; j += ACC_THREADS) s_v[j] = ln_12.dist[(size_t)p * prev.cap_ln + j].x;
+      __syncthreads();
+      const double budget_dist_th =
+          (double)block_select_acc(s_v, n_prev, min(cfg.max_line_match_num, n_prev) - 1, &s_sel);
+      for (int i0 = 0; i0 < n_prev; i0 += ACC_THREADS) {
+        const int i = i0 + threadIdx.x;
+        bool keep = false;
+        int tdx = 0;
+        if (i < n_prev) {
+          const int2 mi = ln_12.idx[(size_t)p * prev.cap_ln + i];
+          const float2 md = ln_12.dist[(size_t)p * prev.cap_ln + i];
+          tdx = mi.x;
+          const int rl = cfg.best_lr_matches ? ln_21.idx[(size_t)p * curr.cap_ln + tdx].x : i;
+          if (!((double)md.x > cfg.budget_slack * budget_dist_th)) {
+            const double dist_12 = (double)(md.y - md.x);
+            keep = (i == rl) && dist_12 > nn12_dist_th;
+          }
+        }
+        const int slot = block_compact_acc(keep, base, s_warp);
+        if (keep && slot < ln_cap) {
+          const gfpl_line_feature& pf = prev.ln[(size_t)p * prev.cap_ln + i];
+          const gfpl_line_feature& cf = curr.ln[(size_t)p * curr.cap_ln + tdx];
+          gfpl_ln_obs o;
+#pragma unroll
+          for (int k = 0; k < 3; k++) { o.sP[k] = pf.sP[k]; o.eP[k] = pf.eP[k]; o.le_obs[k] = cf.le[k]; }
+          o.sigma2 = pf.sigma2;
+          o.prev_idx = i; o.curr_idx = tdx;
+          out.ln[ol + slot] = o;
+          out.ln_inlier[ol + slot] = 1;
+        }
+      }
+      base = min(base, ln_cap);
+    }
+    if (threadIdx.x == 0) out.n_ln[p] = base;
+  }
+}
+
+int launch_f2f_accept(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr, int mode,
+                      const uint32_t* best_key, Knn2Out pt_12, Knn2Out pt_21, Knn2Out ln_12, Knn2Out ln_21,
+                      DevTrackObs out) {
+  if (prev.B <= 0) return GFPL_OK;
+  const int vcap = prev.cap_pt > prev.cap_ln ? prev.cap_pt : prev.cap_ln;
+  const size_t smem = (size_t)(vcap > 0 ? vcap : 1) * 4 + (size_t)(prev.cap_pt > 0 ? prev.cap_pt : 1) * 4;
+  if (smem > 48 * 1024)
+    GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(f2f_accept_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  f2f_accept_kernel<<<prev.B, ACC_THREADS, smem, ctx->stream>>>(prev, curr, mode, best_key, pt_12, pt_21, ln_12, ln_21,
+                                                               out, ctx->cfg);
+  GFPL_LAUNCH_OK(ctx);
+  return GFPL_OK;
+}
+
+}  // namespace gfpl

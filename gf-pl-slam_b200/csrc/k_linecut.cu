@@ -1,0 +1,285 @@
+// k_linecut.cu — K5: good-line-cutting, the per-line cut-ratio search that maximises the log-det (or the
+// smallest eigenvalue) of the pose information matrix.
+//
+// Replaces StereoFrameHandler::estimateProjUncertainty_submodular (reference stereoFrameHandler.cpp:1618-1764),
+// getPoseInfoOnLine (:1342-1411), getPoseInfoPoint (:1414-1447), updateEndPointByRatio (:1451-1470),
+// logdet (linespec.h:43-56) and getMinEigenValue (linespec.cpp:53-66).
+//
+// The search is sequential over the lines of one frame pair (every line sees the information of all the
+// others through invCov_sum), so the parallelism is 8 neighbour candidates x B pairs: a group of 8 lanes
+// owns one pair, lane j evaluates neighbour j (information matrix + 6x6 Cholesky + 6 logs, all in
+// registers), and the reference's "first strictly better in j order" rule is replayed with width-8
+// shuffles.  Four pairs share a warp.  invCov_sum is accumulated in the reference's order (lines, then
+// points, sequentially), and -fmad=false keeps every candidate metric bit-comparable with an IEEE CPU
+// evaluation, so the discrete cut decisions are reproducible.  FP64-ALU / latency bound.
+#include "gfpl_internal.h"
+#include "gfpl_math.cuh"
+
+namespace gfpl {
+
+constexpr int CUT_THREADS = 128;
+constexpr int CUT_GROUP = 8;
+
+// StereoFrame::getJacob3D_2D rows 0-1 (stereoFrame.cpp:1394-1413)
+__device__ __forceinline__ void jacob3d_2d(const gfpl_camera& cam, double px, double py, double pz, double* J23) {
+  const double f = cam.fx, pz_2 = pz * pz;
+  J23[0] = f / pz; J23[1] = 0.0; J23[2] = -f * px / pz_2;
+  J23[3] = 0.0; J23[4] = f / pz; J23[5] = -f * py / pz_2;
+}
+
+// J_loss^T * (Jp * R * cov * R^T * Jp^T) * J_loss   (stereoFrameHandler.cpp:1359-1362)
+__device__ __forceinline__ double residual_var(const double* Jp23, const double* R, const double* cov,
+                                               const double* Jl) {
+  double A[6], Bm[6], Rt[9], Cm[6], Jpt[6], D[4];
+  matmul<2, 3, 3>(Jp23, R, A);
+  matmul<2, 3, 3>(A, cov, Bm);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) Rt[j * 3 + i] = R[i * 3 + j];
+  matmul<2, 3, 3>(Bm, Rt, Cm);
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) Jpt[j * 2 + i] = Jp23[i * 3 + j];
+  matmul<2, 3, 2>(Cm, Jpt, D);
+  const double r0 = Jl[0] * D[0] + Jl[1] * D[2];
+  const double r1 = Jl[0] * D[1] + Jl[1] * D[3];
+  return r0 * Jl[0] + r1 * Jl[1];
+}
+
+struct LineInfo {  // what getPoseInfoOnLine needs to form info = [Js Je] * inv(diag(cov_sR, cov_eR)) * [Js Je]^T
+  double Js[6], Je[6];
+  double i00, i01, i10, i11;
+};
+
+struct LineData {
+  double sP[3], eP[3], le[2];
+  double covS[9], covE[9];
+};
+
+__device__ __forceinline__ void pose_info_on_line(const gfpl_camera& cam, const gfpl_config& cfg, const double* DT_inv,
+                                                  const LineData& L, double c0, double c1, LineInfo& out) {
+  double sP_tmp[3], eP_tmp[3], cov_sP[9], cov_eP[9], R[9];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    sP_tmp[k] = (1 - c0) * L.sP[k] + c0 * L.eP[k];
+    eP_tmp[k] = (1 - c1) * L.eP[k] + c1 * L.sP[k];
+  }
+  const double a0 = (1 - c0) * (1 - c0), b0 = c0 * c0;
+  const double a1 = (1 - c1) * (1 - c1), b1 = c1 * c1;
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    cov_sP[k] = a0 * L.covS[k] + b0 * L.covE[k];
+    cov_eP[k] = a1 * L.covE[k] + b1 * L.covS[k];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) R[i * 3 + j] = DT_inv[i * 4 + j];
+  double cur_s[3], cur_e[3], Jp[6];
+  se3_apply(DT_inv, sP_tmp, cur_s);
+  jacob3d_2d(cam, cur_s[0], cur_s[1], cur_s[2], Jp);
+  const double cov_sR = residual_var(Jp, R, cov_sP, L.le);
+  se3_apply(DT_inv, eP_tmp, cur_e);
+  jacob3d_2d(cam, cur_e[0], cur_e[1], cur_e[2], Jp);
+  const double cov_eR = residual_var(Jp, R, cov_eP, L.le);
+  jac6(cam.fx / fmax(cfg.homog_th, cur_s[2] * cur_s[2]), cur_s[0], cur_s[1], cur_s[2], L.le[0], L.le[1], out.Js);
+  jac6(cam.fx / fmax(cfg.homog_th, cur_e[2] * cur_e[2]), cur_e[0], cur_e[1], cur_e[2], L.le[0], L.le[1], out.Je);
+  // 2x2 inverse of diag(cov_sR, cov_eR) as adjugate * (1/det)
+  const double det = cov_sR * cov_eR - 0.0 * 0.0;
+  const double invdet = 1.0 / det;
+  out.i00 = cov_eR * invdet;
+  out.i11 = cov_sR * invdet;
+  out.i01 = -0.0 * invdet;
+  out.i10 = -0.0 * invdet;
+}
+
+__device__ __forceinline__ double info_entry(const LineInfo& I, int i, int j) {
+  const double Ai0 = I.Js[i] * I.i00 + I.Je[i] * I.i10;
+  const double Ai1 = I.Js[i] * I.i01 + I.Je[i] * I.i11;
+  return Ai0 * I.Js[j] + Ai1 * I.Je[j];
+}
+
+__device__ __forceinline__ void load_line(const gfpl_ln_obs& o, const gfpl_line_cov& c, LineData& L) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) { L.sP[k] = o.sP[k]; L.eP[k] = o.eP[k]; }
+  L.le[0] = o.le_obs[0]; L.le[1] = o.le_obs[1];
+#pragma unroll
+  for (int k = 0; k < 9; k++) { L.covS[k] = c.covS[k]; L.covE[k] = c.covE[k]; }
+}
+
+// metric on a lower-triangle-packed matrix
+__device__ __forceinline__ double cut_metric(const gfpl_config& cfg, const double* M21) {
+  if (cfg.max_vol_line_cut) return logdet6_packed(M21);
+  double S[36], ev[6];
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j <= i; j++) { S[i * 6 + j] = M21[tri(i, j)]; S[j * 6 + i] = M21[tri(i, j)]; }
+  sym_eigenvalues<6>(S, ev);
+  return ev[0];
+}
+
+__global__ void __launch_bounds__(CUT_THREADS)
+linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __restrict__ state, DevTrackObs obs,
+               const gfpl_line_cov* __restrict__ prev_cov, int cov_cap, gfpl_line_cut* __restrict__ cut_all,
+               gfpl_camera cam, gfpl_config cfg) {
+  const int lane = threadIdx.x & 31;
+  const int j = lane & (CUT_GROUP - 1);             // neighbour index of this lane
+  const int grp = lane / CUT_GROUP;                 // pair slot inside the warp
+  const unsigned gmask = 0xFFu << (grp * CUT_GROUP);
+  const int p = (blockIdx.x * (CUT_THREADS / 32) + (threadIdx.x >> 5)) * (32 / CUT_GROUP) + grp;
+  if (p >= obs.B) return;
+  const int nln = obs.n_ln[p], npt = obs.n_pt[p];
+  if (nln == 0) return;  // :1621
+  gfpl_ln_obs* lns = obs.ln + (size_t)p * obs.cap_ln;
+  const gfpl_pt_obs* pts = obs.pt + (size_t)p * obs.cap_pt;
+  const gfpl_line_cov* cov = prev_cov + (size_t)p * cov_cap;
+  gfpl_line_cut* cut = cut_all + (size_t)p * obs.cap_ln;
+
+  double DT_inv[16];
+  if (DT_inv_all) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) DT_inv[i] = DT_inv_all[(size_t)p * 16 + i];
+  } else {
+    double Tc[16], Tci[16];
+    matmul<4, 4, 4>(state[p].Tfw, state[p].DT, Tc);  // predicted curr->Tfw (:157)
+    inverse4(Tc, Tci);
+    matmul<4, 4, 4>(Tci, state[p].Tfw, DT_inv);      // :1635
+  }
+
+  const double step = cfg.cut_step;
+  const double nb0 = (j == 0 || j == 4 || j == 5) ? step : ((j == 1 || j == 6 || j == 7) ? -step : 0.0);
+  const double nb1 = (j == 2 || j == 4 || j == 6) ? step : ((j == 3 || j == 5 || j == 7) ? -step : 0.0);
+
+  // pass 1a: initial information of every line (cut = 0), lanes stride over the lines (:1638-1649)
+  for (int l = j; l < nln; l += CUT_GROUP) {
+    LineData L;
+    LineInfo I;
+    load_line(lns[l], cov[lns[l].prev_idx], L);
+    pose_info_on_line(cam, cfg, DT_inv, L, 0.0, 0.0, I);
+    gfpl_line_cut& C = cut[l];
+    C.cutRatio[0] = 0.0; C.cutRatio[1] = 0.0;
+    for (int a = 0; a < 6; a++)
+      for (int b = 0; b < 6; b++) C.invCovPose[a * 6 + b] = info_entry(I, a, b);
+  }
+  __syncwarp(gmask);
+
+  // pass 1b/2: invCov_sum in the reference's order — lines, then points — held by every lane (lower triangle)
+  double sum[21];
+#pragma unroll
+  for (int e = 0; e < 21; e++) sum[e] = 0.0;
+  for (int l = 0; l < nln; l++) {
+    const double* info = cut[l].invCovPose;
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+      for (int b = 0; b <= a; b++) sum[tri(a, b)] = sum[tri(a, b)] + info[a * 6 + b];
+  }
+  for (int k = 0; k < npt; k++) {  // getPoseInfoPoint (:1414-1447)
+    double c[3], uv[2], J[6];
+    se3_apply(DT_inv, pts[k].P, c);
+    projection(cam, c, uv);
+    const double dx = uv[0] - pts[k].pl_obs[0], dy = uv[1] - pts[k].pl_obs[1];
+    jac6(cam.fx / fmax(cfg.homog_th, c[2] * c[2]), c[0], c[1], c[2], dx, dy, J);
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+      for (int b = 0; b <= a; b++) sum[tri(a, b)] = sum[tri(a, b)] + J[a] * J[b];
+  }
+
+  // pass 3: sequential greedy search per line (:1662-1763)
+  for (int l = 0; l < nln; l++) {
+    LineData L;
+    load_line(lns[l], cov[lns[l].prev_idx], L);
+    gfpl_line_cut& C = cut[l];
+    double metric_last = cut_metric(cfg, sum);
+    {
+      const double* info = C.invCovPose;
+#pragma unroll
+      for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int b = 0; b <= a; b++) sum[tri(a, b)] = sum[tri(a, b)] - info[a * 6 + b];
+    }
+    double cur0 = 0.0, cur1 = 0.0;
+    while (cur0 + cur1 <= 1.0) {
+      const double ct0 = cur0 + nb0, ct1 = cur1 + nb1;
+      bool valid = !(ct0 + ct1 > 1.0);
+      valid = valid && !(ct0 < cfg.cut_rng[0] || ct0 > cfg.cut_rng[1]);
+      valid = valid && !(ct1 < cfg.cut_rng[0] || ct1 > cfg.cut_rng[1]);
+      double metric = 0.0;
+      LineInfo I;
+      if (valid) {
+        pose_info_on_line(cam, cfg, DT_inv, L, ct0, ct1, I);
+        double M[21];
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+          for (int b = 0; b <= a; b++) M[tri(a, b)] = info_entry(I, a, b) + sum[tri(a, b)];
+        metric = cut_metric(cfg, M);
+      }
+      // "first strictly better in j order" (:1722-1730)
+      double best = metric_last;
+      int cand = -1;
+#pragma unroll
+      for (int jj = 0; jj < CUT_GROUP; jj++) {
+        const double mj = shfl_f64(gmask, metric, jj, CUT_GROUP);
+        const int vj = __shfl_sync(gmask, (int)valid, jj, CUT_GROUP);
+        if (vj && mj > best) { best = mj; cand = jj; }
+      }
+      if (cand < 0) break;  // early termination (:1741-1743)
+      if (j == cand) {
+        for (int a = 0; a < 6; a++)
+          for (int b = 0; b < 6; b++) C.invCovPose[a * 6 + b] = info_entry(I, a, b);
+      }
+      cur0 = shfl_f64(gmask, ct0, cand, CUT_GROUP);
+      cur1 = shfl_f64(gmask, ct1, cand, CUT_GROUP);
+      metric_last = best;
+    }
+    __syncwarp(gmask);
+    // updateEndPointByRatio (:1451-1470) — lane 0 of the group writes the results
+    if (j == 0) {
+      C.cutRatio[0] = cur0; C.cutRatio[1] = cur1;
+      C.spl[0] = C.spl[1] = C.epl[0] = C.epl[1] = 0.0;
+      C.sdisp = 0.0; C.edisp = 0.0;
+      if (!(fabs(cur0) < 0.0001 && fabs(cur1) < 0.0001)) {
+        double sP[3] = {L.sP[0], L.sP[1], L.sP[2]};
+        if (fabs(cur0) > 0.0001) {
+#pragma unroll
+          for (int k = 0; k < 3; k++) sP[k] = (1 - cur0) * L.sP[k] + cur0 * L.eP[k];
+#pragma unroll
+          for (int k = 0; k < 3; k++) lns[l].sP[k] = sP[k];
+          projection(cam, sP, C.spl);
+          C.sdisp = get_disparity(cam, sP[2]);
+        }
+        if (fabs(cur1) > 0.0001) {
+          double eP[3];
+#pragma unroll
+          for (int k = 0; k < 3; k++) eP[k] = (1 - cur1) * L.eP[k] + cur1 * sP[k];  // reads the MOVED start point
+#pragma unroll
+          for (int k = 0; k < 3; k++) lns[l].eP[k] = eP[k];
+          projection(cam, eP, C.epl);
+          C.edisp = get_disparity(cam, eP[2]);
+        }
+      }
+    }
+    {
+      const double* info = C.invCovPose;
+#pragma unroll
+      for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int b = 0; b <= a; b++) sum[tri(a, b)] = sum[tri(a, b)] + info[a * 6 + b];
+    }
+  }
+}
+
+int launch_linecut(gfpl_ctx* ctx, const double* DT_inv, const gfpl_frame_state* state, DevTrackObs obs,
+                   const gfpl_line_cov* prev_cov, int cov_cap, gfpl_line_cut* cut) {
+  if (obs.B <= 0 || obs.cap_ln <= 0) return GFPL_OK;
+  const int pairs_per_cta = (CUT_THREADS / 32) * (32 / CUT_GROUP);
+  const int grid = (obs.B + pairs_per_cta - 1) / pairs_per_cta;
+  linecut_kernel<<<grid, CUT_THREADS, 0, ctx->stream>>>(DT_inv, state, obs, prev_cov, cov_cap, cut, ctx->cam, ctx->cfg);
+  GFPL_LAUNCH_OK(ctx);
+  return GFPL_OK;
+}
+
+}  // namespace gfpl

@@ -1,0 +1,383 @@
+// k_pose.cu — K4: the Gauss-Newton pose optimiser of StVO::StereoFrameHandler for sm_100a.
+//
+// Replaces optimizeFunctions (reference stereoFrameHandler.cpp:2118-2245), gaussNewtonOptimization
+// (:2032-2056), removeOutliers (:2058-2116) + vector_stdv_mad (auxiliar.cpp:521-537) and both
+// optimizePose overloads (:1864-2030).
+//
+// One warp owns one frame pair for the whole optimisation (both GN stages and the outlier pass), so the
+// kernel is persistent across iterations: the observation lists are read from L1/L2, the pose and the
+// 28 normal-equation partials (21 lower-triangle H + 6 g + 1 e) live in registers, and each iteration
+// ends in a fixed xor-butterfly of fp64 warp shuffles — every lane ends with bit-identical H, g, e and
+// the result is run-to-run reproducible.  All lanes then run the 6x6 pivoted LDLT solve and the SE(3)
+// update redundantly (no broadcast, no divergence).  FP64-ALU / latency bound:
+// flops per iteration ~ 114 per point + 212 per line.
+#include "gfpl_internal.h"
+#include "gfpl_math.cuh"
+
+namespace gfpl {
+
+constexpr int POSE_WARPS = 4;
+
+struct Acc {
+  double v[28];  // [0,21) lower triangle of H, [21,27) g, [27] e
+};
+
+__device__ __forceinline__ void acc_add(Acc& a, const double* J, double r, double w) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+#pragma unroll
+    for (int j = 0; j <= i; j++) a.v[tri(i, j)] = a.v[tri(i, j)] + J[i] * J[j] * w;
+    a.v[21 + i] = a.v[21 + i] + J[i] * r * w;
+  }
+  a.v[27] = a.v[27] + r * r * w;
+}
+
+// point term (stereoFrameHandler.cpp:2131-2167); returns the residual norm
+__device__ __forceinline__ double point_residual(const double* DT, const gfpl_pt_obs& o, const gfpl_camera& cam,
+                                                 double* P_, double* dxy) {
+  double uv[2];
+  se3_apply(DT, o.P, P_);
+  projection(cam, P_, uv);
+  dxy[0] = uv[0] - o.pl_obs[0];
+  dxy[1] = uv[1] - o.pl_obs[1];
+  return sqrt(dxy[0] * dxy[0] + dxy[1] * dxy[1]);
+}
+
+// line term (:2171-2235)
+__device__ __forceinline__ double line_residual(const double* DT, const gfpl_ln_obs& o, const gfpl_camera& cam,
+                                                double* sP_, double* eP_, double* dse) {
+  double sp[2], ep[2];
+  se3_apply(DT, o.sP, sP_);
+  projection(cam, sP_, sp);
+  se3_apply(DT, o.eP, eP_);
+  projection(cam, eP_, ep);
+  dse[0] = o.le_obs[0] * sp[0] + o.le_obs[1] * sp[1] + o.le_obs[2];
+  dse[1] = o.le_obs[0] * ep[0] + o.le_obs[1] * ep[1] + o.le_obs[2];
+  return sqrt(dse[0] * dse[0] + dse[1] * dse[1]);
+}
+
+struct PairObs {
+  int npt, nln;
+  const gfpl_pt_obs* pts;
+  const gfpl_ln_obs* lns;
+  uint8_t* pin;
+  uint8_t* lin;
+};
+
+// optimizeFunctions for one pair by one warp.  Returns H (full 6x6), g, e in every lane.
+__device__ void warp_optimize_functions(const double* DT, const PairObs& o, const gfpl_camera& cam,
+                                        const gfpl_config& cfg, double* H, double* g, double* e) {
+  const int lane = threadIdx.x & 31;
+  Acc a;
+#pragma unroll
+  for (int i = 0; i < 28; i++) a.v[i] = 0.0;
+  int N = 0;
+  for (int k = lane; k < o.npt; k += 32) {
+    if (!o.pin[k]) continue;
+    double P_[3], d[2], J[6];
+    const gfpl_pt_obs ob = o.pts[k];
+    const double r = point_residual(DT, ob, cam, P_, d);
+    const double fgz2 = cam.fx / fmax(cfg.homog_th, P_[2] * P_[2]);
+    jac6(fgz2, P_[0], P_[1], P_[2], d[0], d[1], J);
+    const double dn = fmax(cfg.homog_th, r);
+#pragma unroll
+    for (int i = 0; i < 6; i++) J[i] = J[i] / dn;
+    const double w = 1.0 / (1.0 + r * r * ob.sigma2);
+    acc_add(a, J, r, w);
+    N++;
+  }
+  for (int k = lane; k < o.nln; k += 32) {
+    if (!o.lin[k]) continue;
+    double sP_[3], eP_[3], d[2], Js[6], Je[6], J[6];
+    const gfpl_ln_obs ob = o.lns[k];
+    const double r = line_residual(DT, ob, cam, sP_, eP_, d);
+    jac6(cam.fx / fmax(cfg.homog_th, sP_[2] * sP_[2]), sP_[0], sP_[1], sP_[2], ob.le_obs[0], ob.le_obs[1], Js);
+    jac6(cam.fx / fmax(cfg.homog_th, eP_[2] * eP_[2]), eP_[0], eP_[1], eP_[2], ob.le_obs[0], ob.le_obs[1], Je);
+    const double dn = fmax(cfg.homog_th, r);
+#pragma unroll
+    for (int i = 0; i < 6; i++) J[i] = (Js[i] * d[0] + Je[i] * d[1]) / dn;
+    const double w = 1.0 / (1.0 + r * r * ob.sigma2);
+    acc_add(a, J, r, w);
+    N++;
+  }
+  // fixed xor-butterfly: identical association in every lane, deterministic run to run
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 28; i++) a.v[i] = a.v[i] + shfl_xor_f64(0xffffffffu, a.v[i], s);
+    N += __shfl_xor_sync(0xffffffffu, N, s);
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+#pragma unroll
+    for (int j = 0; j <= i; j++) { H[i * 6 + j] = a.v[tri(i, j)]; H[j * 6 + i] = a.v[tri(i, j)]; }
+    g[i] = a.v[21 + i];
+  }
+  *e = a.v[27] / (double)N;  // e /= (N_l + N_p), 0/0 -> NaN like the reference
+}
+
+// gaussNewtonOptimization (:2032-2056); H of the last evaluation is returned for DT_cov = H^-1
+__device__ int warp_gauss_newton(double* DT, const PairObs& o, const gfpl_camera& cam, const gfpl_config& cfg,
+                                 int max_iters, double* H, double* err_) {
+  double g[6], inc[6];
+  double err = 0.0, err_prev = 999999999.9;
+  for (int i = 0; i < 36; i++) H[i] = 0.0;
+  int iters = 0;
+  for (; iters < max_iters; iters++) {
+    warp_optimize_functions(DT, o, cam, cfg, H, g, &err);
+    if ((fabs(err - err_prev) < cfg.min_error_change) || (err < cfg.min_error)) break;
+    ldlt6_solve(H, g, inc);
+    double E[16], Ei[16];
+    expmap_se3(inc, E);
+    inverse_se3(E, Ei);
+    matmul<4, 4, 4>(DT, Ei, DT);
+    double nrm = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) nrm = nrm + inc[i] * inc[i];
+    if (sqrt(nrm) < 2.220446049250313e-16) break;
+    err_prev = err;
+  }
+  *err_ = err;
+  return iters;
+}
+
+// 1.4826 * MAD of res[0..n) exactly as vector_stdv_mad (auxiliar.cpp:521-537) computes it:
+// median = sorted[n/2]; a = (double)fabsf(res - median); MAD = sorted(a)[n/2].  Warp-cooperative rank selection.
+__device__ double warp_stdv_mad(const double* res, int n) {
+  if (n == 0) return 0.0;
+  const int lane = threadIdx.x & 31;
+  const int rank = n / 2;
+  double median = 0.0;
+  {
+    double found = 0.0;
+    bool have = false;
+    for (int j = lane; j < n; j += 32) {
+      const double x = res[j];
+      int r = 0;
+      for (int k = 0; k < n; k++) {
+        const double y = res[k];
+        r += (y < x) || (y == x && k < j);
+      }
+      if (r == rank) { found = x; have = true; }
+    }
+    const unsigned who = __ballot_sync(0xffffffffu, have);
+    median = shfl_f64(0xffffffffu, found, who ? __ffs(who) - 1 : 0);
+  }
+  double mad = 0.0;
+  {
+    double found = 0.0;
+    bool have = false;
+    for (int j = lane; j < n; j += 32) {
+      const double x = (double)fabsf((float)(res[j] - median));
+      int r = 0;
+      for (int k = 0; k < n; k++) {
+        const double y = (double)fabsf((float)(res[k] - median));
+        r += (y < x) || (y == x && k < j);
+      }
+      if (r == rank) { found = x; have = true; }
+    }
+    const unsigned who = __ballot_sync(0xffffffffu, have);
+    mad = shfl_f64(0xffffffffu, found, who ? __ffs(who) - 1 : 0);
+  }
+  return 1.4826 * mad;
+}
+
+// removeOutliers (:2058-2116): returns the number of points / lines flagged
+__device__ void warp_remove_outliers(const double* DT, const PairObs& o, const gfpl_camera& cam,
+                                     const gfpl_config& cfg, double* s_res, int* drop_pt, int* drop_ln) {
+  const int lane = threadIdx.x & 31;
+  double* res_p = s_res;
+  double* res_l = s_res + o.npt;
+  for (int k = lane; k < o.npt; k += 32) {
+    double P_[3], d[2];
+    const gfpl_pt_obs ob = o.pts[k];
+    const double r = point_residual(DT, ob, cam, P_, d);
+    res_p[k] = r * sqrt(ob.sigma2);
+  }
+  for (int k = lane; k < o.nln; k += 32) {
+    double sP_[3], eP_[3], d[2];
+    const gfpl_ln_obs ob = o.lns[k];
+    const double r = line_residual(DT, ob, cam, sP_, eP_, d);
+    res_l[k] = r * sqrt(ob.sigma2);
+  }
+  __syncwarp();
+  const double th_p = cfg.inlier_k * warp_stdv_mad(res_p, o.npt);
+  const double th_l = cfg.inlier_k * warp_stdv_mad(res_l, o.nln);
+  int dp = 0, dl = 0;
+  for (int k = lane; k < o.npt; k += 32)
+    if (res_p[k] > th_p) { o.pin[k] = 0; dp++; }
+  for (int k = lane; k < o.nln; k += 32)
+    if (res_l[k] > th_l) { o.lin[k] = 0; dl++; }
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    dp += __shfl_xor_sync(0xffffffffu, dp, s);
+    dl += __shfl_xor_sync(0xffffffffu, dl, s);
+  }
+  *drop_pt = dp;
+  *drop_ln = dl;
+  __syncwarp();
+}
+
+// lane-0 epilogue helpers (local-memory loops; executed once per pair)
+__device__ __noinline__ void unccomp_se3(const double* T1, const double* covT1, const double* covTinc, double* covT2) {
+  double Ad[36], tmp[36];
+  double sk[9], skR[9];
+  const double t[3] = {T1[3], T1[7], T1[11]};
+  skew(t, sk);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double s = sk[i * 3 + 0] * T1[0 * 4 + j];
+      s = s + sk[i * 3 + 1] * T1[1 * 4 + j];
+      s = s + sk[i * 3 + 2] * T1[2 * 4 + j];
+      skR[i * 3 + j] = s;
+    }
+  for (int i = 0; i < 36; i++) Ad[i] = 0.0;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      Ad[i * 6 + j] = T1[i * 4 + j];
+      Ad[i * 6 + 3 + j] = skR[i * 3 + j];
+      Ad[(i + 3) * 6 + 3 + j] = T1[i * 4 + j];
+    }
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < 6; j++) {
+      double s = Ad[i * 6 + 0] * covTinc[0 * 6 + j];
+      for (int k = 1; k < 6; k++) s = s + Ad[i * 6 + k] * covTinc[k * 6 + j];
+      tmp[i * 6 + j] = s;
+    }
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < 6; j++) {
+      double s = tmp[i * 6 + 0] * Ad[j * 6 + 0];
+      for (int k = 1; k < 6; k++) s = s + tmp[i * 6 + k] * Ad[j * 6 + k];
+      covT2[i * 6 + j] = covT1[i * 6 + j] + s;
+    }
+}
+
+__global__ void __launch_bounds__(POSE_WARPS * 32)
+pose_optimize_kernel(DevTrackObs obs, const gfpl_frame_state* __restrict__ state, const double* __restrict__ DT_ini,
+                     int overload, gfpl_pose_result* __restrict__ out, gfpl_camera cam, gfpl_config cfg) {
+  extern __shared__ double s_res_all[];  // [POSE_WARPS][cap_pt + cap_ln]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = blockIdx.x * POSE_WARPS + warp;
+  if (p >= obs.B) return;
+  double* s_res = s_res_all + (size_t)warp * (obs.cap_pt + obs.cap_ln);
+  PairObs o;
+  o.npt = obs.n_pt[p]; o.nln = obs.n_ln[p];
+  o.pts = obs.pt + (size_t)p * obs.cap_pt; o.pin = obs.pt_inlier + (size_t)p * obs.cap_pt;
+  o.lns = obs.ln + (size_t)p * obs.cap_ln; o.lin = obs.ln_inlier + (size_t)p * obs.cap_ln;
+  const gfpl_frame_state& st = state[p];
+
+  double DT[16], H[36], err = 0.0;
+  const double* seed = (overload == GFPL_POSE_SEED_GIVEN && DT_ini) ? DT_ini + (size_t)p * 16 : st.DT;
+#pragma unroll
+  for (int i = 0; i < 16; i++) DT[i] = seed[i];
+  int n_inliers_pt = o.npt, n_inliers_ls = o.nln, n_inliers = o.npt + o.nln;
+  int status = GFPL_POSE_OK, it1 = 0, it2 = 0;
+  bool cov_from_H = false, cov_prev = true;  // DT_cov starts as prev_frame->DT_cov (:1875,1950)
+  if (n_inliers > cfg.min_features) {
+    double DT_[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) DT_[i] = DT[i];
+    it1 = warp_gauss_newton(DT_, o, cam, cfg, cfg.max_iters, H, &err);
+    cov_prev = false;
+    if (is_finite16(DT_)) {
+      int dp, dl;
+      warp_remove_outliers(DT_, o, cam, cfg, s_res, &dp, &dl);
+      n_inliers_pt -= dp; n_inliers_ls -= dl; n_inliers -= dp + dl;
+      if (n_inliers > cfg.min_features) {
+        it2 = warp_gauss_newton(DT, o, cam, cfg, cfg.max_iters_ref, H, &err);  // D8: restarts from the seed
+        cov_from_H = true;
+      } else {
+        eye4(DT);
+        status |= GFPL_POSE_FEW_INLIERS;
+      }
+    } else {
+      eye4(DT);
+      status |= GFPL_POSE_NONFINITE_1;
+    }
+  } else {
+    eye4(DT);
+    cov_prev = false;
+    status |= GFPL_POSE_FEW_FEATURES;
+  }
+
+  if (lane != 0) return;
+  gfpl_pose_result& r = out[p];
+  double DT_cov[36];
+  if (cov_from_H) inverse6(H, DT_cov);
+  else
+    for (int i = 0; i < 36; i++) DT_cov[i] = cov_prev ? st.DT_cov[i] : 0.0;
+  bool accept = false;
+  double DTinv[16];
+  if (is_finite16(DT)) {
+    inverse_se3(DT, DTinv);
+    accept = true;
+    if (overload == GFPL_POSE_SEED_GIVEN) {
+      const double tn = sqrt(DTinv[3] * DTinv[3] + DTinv[7] * DTinv[7] + DTinv[11] * DTinv[11]);
+      if (!(tn < cfg.motion_step_th * (st.time_stamp_curr - st.time_stamp))) {
+        accept = false;
+        status |= GFPL_POSE_STEP_REJECTED;
+      }
+    }
+  } else
+    status |= GFPL_POSE_NONFINITE_2;
+  for (int i = 0; i < 36; i++) r.DT_cov[i] = DT_cov[i];
+  sym_eigenvalues<6>(DT_cov, r.DT_cov_eig);
+  if (accept) {
+    double Tfw[16];
+    matmul<4, 4, 4>(st.Tfw, DTinv, Tfw);
+    for (int i = 0; i < 16; i++) { r.DT[i] = DTinv[i]; r.Tfw[i] = Tfw[i]; }
+    unccomp_se3(st.Tfw, st.Tfw_cov, DT_cov, r.Tfw_cov);
+    r.err_norm = err;
+  } else {
+    for (int i = 0; i < 16; i++) { r.DT[i] = (i % 5 == 0) ? 1.0 : 0.0; r.Tfw[i] = st.Tfw[i]; }
+    for (int i = 0; i < 36; i++) r.Tfw_cov[i] = st.Tfw_cov[i];
+    r.err_norm = -1.0;
+  }
+  r.status = status;
+  r.n_inliers = n_inliers; r.n_inliers_pt = n_inliers_pt; r.n_inliers_ls = n_inliers_ls;
+  r.iters_first = it1; r.iters_ref = it2;
+}
+
+int launch_pose_optimize(gfpl_ctx* ctx, DevTrackObs obs, const gfpl_frame_state* state, const double* DT_ini,
+                         int overload, gfpl_pose_result* out) {
+  if (obs.B <= 0) return GFPL_OK;
+  const size_t smem = (size_t)POSE_WARPS * (obs.cap_pt + obs.cap_ln) * sizeof(double);
+  if (smem > 48 * 1024)
+    GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(pose_optimize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (obs.B + POSE_WARPS - 1) / POSE_WARPS;
+  pose_optimize_kernel<<<grid, POSE_WARPS * 32, smem, ctx->stream>>>(obs, state, DT_ini, overload, out, ctx->cam, ctx->cfg);
+  GFPL_LAUNCH_OK(ctx);
+  return GFPL_OK;
+}
+
+// ---- P1 alone: H, g, e at given poses ------------------------------------------------------------------
+__global__ void __launch_bounds__(POSE_WARPS * 32)
+pose_hg_kernel(DevTrackObs obs, const double* __restrict__ DT_all, double* __restrict__ Hout,
+               double* __restrict__ gout, double* __restrict__ eout, gfpl_camera cam, gfpl_config cfg) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = blockIdx.x * POSE_WARPS + warp;
+  if (p >= obs.B) return;
+  PairObs o;
+  o.npt = obs.n_pt[p]; o.nln = obs.n_ln[p];
+  o.pts = obs.pt + (size_t)p * obs.cap_pt; o.pin = obs.pt_inlier + (size_t)p * obs.cap_pt;
+  o.lns = obs.ln + (size_t)p * obs.cap_ln; o.lin = obs.ln_inlier + (size_t)p * obs.cap_ln;
+  double DT[16], H[36], g[6], e;
+#pragma unroll
+  for (int i = 0; i < 16; i++) DT[i] = DT_all[(size_t)p * 16 + i];
+  warp_optimize_functions(DT, o, cam, cfg, H, g, &e);
+  if (lane == 0) {
+    for (int i = 0; i < 36; i++) Hout[(size_t)p * 36 + i] = H[i];
+    for (int i = 0; i < 6; i++) gout[(size_t)p * 6 + i] = g[i];
+    eout[p] = e;
+  }
+}
+
+int launch_pose_hg(gfpl_ctx* ctx, const double* DT, const DevTrackObs& obs, double* H, double* g, double* e) {
+  if (obs.B <= 0) return GFPL_OK;
+  const int grid = (obs.B + POSE_WARPS - 1) / POSE_WARPS;
+  pose_hg_kernel<<<grid, POSE_WARPS * 32, 0, ctx->stream>>>(obs, DT, H, g, e, ctx->cam, ctx->cfg);
+  GFPL_LAUNCH_OK(ctx);
+  return GFPL_OK;
+}
+
+}  // namespace gfpl

@@ -667,7 +667,7 @@ extern "C" double orc_logdet6(const double* M) { return logdet6(M); }
 extern "C" double orc_min_eig6(const double* M) {
   double S[36], ev[6];
   for (int i = 0; i < 6; i++)
-    for (int j = 0; j < 6; j++) S[i * 6 + j] = 0.5 * (M[i * 6 + j] + M[j * 6 + i]);
+    for (int j = 0; j <= i; j++) { S[i * 6 + j] = M[i * 6 + j]; S[j * 6 + i] = M[i * 6 + j]; }
   sym_eigenvalues<6>(S, ev);
   return ev[0];
 }

@@ -1,0 +1,385 @@
+"""GPU parity: every stage of the CUDA path, called through the C ABI (libgfpl.so via ctypes, host buffers),
+against the CPU oracle on the same seeded inputs and against the committed cv2 golden vectors.
+
+Bars (BASELINE.json north_star): bit-exact match indices, distances, accepted-feature lists, inlier masks
+and cut ratios; fp64 outputs (H, g, e, poses, covariances, information matrices) within RTOL = 1e-9
+relative to the magnitude of the quantity.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from gfpl import _structs as S
+from gfpl import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "bfmatcher_*.npz")))
+
+
+def close(a, b, rtol=RTOL):
+    """relative to the largest magnitude of the reference quantity (matrix-level tolerance)"""
+    a, b = np.asarray(a), np.asarray(b)
+    scale = max(float(np.abs(b).max()) if b.size else 0.0, 1e-300)
+    return bool(np.all(np.abs(a - b) <= rtol * scale) and np.array_equal(np.isnan(a), np.isnan(b)))
+
+
+def assert_records_equal(a, b, n=None, exact_fields=None, tol_fields=()):
+    names = a.dtype.names
+    for f in names:
+        x, y = (a[f], b[f]) if n is None else (a[f][:n], b[f][:n])
+        if f in tol_fields:
+            assert close(x, y), f
+        else:
+            assert np.array_equal(x, y), f
+
+
+# ---------------------------------------------------------------------------------------------------------
+# M1-M3
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[10:-4] for p in GOLDEN])
+@pytest.mark.parametrize("norm", [6, 7])
+def test_knn2_radius_vs_cv2_golden(ctx, path, norm):
+    g = np.load(path)
+    idx, dist = ctx.knn2(g["q"], g["t"], norm)
+    assert np.array_equal(idx, g[f"knn_idx_{norm}"]) and np.array_equal(dist, g[f"knn_dist_{norm}"])
+    rc, off, ri, rd = ctx.radius(g["q"], g["t"], float(g["radius"]), norm)
+    assert rc == 0 and np.array_equal(off, g[f"rad_off_{norm}"])
+    assert np.array_equal(ri, g[f"rad_idx_{norm}"]) and np.array_equal(rd, g[f"rad_dist_{norm}"])
+
+
+@pytest.mark.parametrize("shape", [(300, 300), (100, 100), (2000, 2000), (500, 500), (1, 2), (37, 1025), (513, 255),
+                                   (257, 256), (31, 33)])
+@pytest.mark.parametrize("norm", [6, 7])
+@pytest.mark.parametrize("tie", [False, True])
+def test_knn2_vs_oracle(ctx, orc, shape, norm, tie):
+    rng = np.random.default_rng(hash((shape, norm, tie)) % 2**32)
+    nq, nt = shape
+    mk = (lambda n: synth.tie_stress_descriptors(rng, n)) if tie else (lambda n: rng.integers(0, 256, (n, 32), dtype=np.uint8))
+    q, t = mk(nq), mk(nt)
+    gi, gd = ctx.knn2(q, t, norm)
+    oi, od = orc.knn2(q, t, norm)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+
+
+def test_knn2_batch_ragged(ctx, orc):
+    rng = np.random.default_rng(7)
+    B, cq, ct = 9, 130, 90
+    q = rng.integers(0, 256, (B, cq, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (B, ct, 32), dtype=np.uint8)
+    nq = rng.integers(0, cq + 1, B).astype(np.int32)
+    nt = rng.integers(2, ct + 1, B).astype(np.int32)
+    nq[0], nq[1], nt[2] = 0, cq, 1          # empty query set, full, single train row
+    idx, dist = ctx.knn2_batch(q, nq, t, nt)
+    for p in range(B):
+        if nt[p] >= 2 and nq[p] > 0:
+            oi, od = orc.knn2(q[p, :nq[p]], t[p, :nt[p]])
+            assert np.array_equal(idx[p, :nq[p]], oi) and np.array_equal(dist[p, :nq[p]], od)
+    assert (idx[2, :nq[2], 1] == -1).all() and np.isinf(dist[2, :nq[2], 1]).all()   # nt == 1: no second neighbour
+    assert (idx[2, :nq[2], 0] == 0).all()
+
+
+def test_knn2_errors(ctx):
+    from gfpl.api import GfplError
+    q = np.zeros((4, 32), np.uint8)
+    with pytest.raises(GfplError) as e:
+        ctx.knn2(q, q[:1])                  # Nt >= 2
+    assert e.value.code == S.E_INVALID
+    with pytest.raises(GfplError):
+        ctx.knn2(q, q, norm=4)
+    idx, dist = ctx.knn2(q[:0], q)          # empty query set is fine
+    assert idx.shape == (0, 2)
+
+
+def test_radius_capacity_and_empty(ctx, orc):
+    rng = np.random.default_rng(8)
+    q = rng.integers(0, 256, (50, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (60, 32), dtype=np.uint8)
+    rc, off, _, _ = ctx.radius(q, t, 300.0, cap=100)
+    assert rc == S.E_CAPACITY and off[-1] == 3000
+    rc, off, ri, rd = ctx.radius(q, t, 20.0)            # nothing within 20 bits of random rows
+    assert rc == 0 and off[-1] == 0 and len(ri) == 0
+    rc, off, ri, rd = ctx.radius(q, t, 128.0)
+    rc2, off2, ri2, rd2 = orc.radius(q, t, 128.0)
+    assert np.array_equal(off, off2) and np.array_equal(ri, ri2) and np.array_equal(rd, rd2)
+
+
+def test_knn2_full_size_properties(ctx):
+    """C4-sized problem: size-independent properties (self-match, symmetry of the distance, sortedness)."""
+    rng = np.random.default_rng(9)
+    a = rng.integers(0, 256, (2000, 32), dtype=np.uint8)
+    perm = rng.permutation(2000)
+    idx, dist = ctx.knn2(a, a[perm])
+    assert np.array_equal(perm[idx[:, 0]], np.arange(2000)) and (dist[:, 0] == 0).all()   # every row finds itself
+    assert (dist[:, 0] <= dist[:, 1]).all()
+    bits = np.unpackbits(a, axis=1).astype(np.int32)
+    j = idx[:, 1]
+    d1 = (bits != bits[perm][j]).sum(1)
+    assert np.array_equal(d1.astype(np.float32), dist[:, 1])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# M4-M8, C1
+# ---------------------------------------------------------------------------------------------------------
+def _data(B, seed, **kw):
+    return synth.make_pairs(B, seed=seed, **kw)
+
+
+def _cmp_stereo(g, o):
+    assert np.array_equal(g.n_pt, o.n_pt) and np.array_equal(g.n_ln, o.n_ln)
+    for p in range(g.B):
+        assert_records_equal(g.pt[p], o.pt[p], n=g.n_pt[p])                      # bit-exact incl. fp64 back-projection
+        assert np.array_equal(g.pdesc[p, :g.n_pt[p]], o.pdesc[p, :o.n_pt[p]])
+        assert_records_equal(g.ln[p], o.ln[p], n=g.n_ln[p])
+        assert np.array_equal(g.ldesc[p, :g.n_ln[p]], o.ldesc[p, :o.n_ln[p]])
+
+
+@pytest.mark.parametrize("variant", [S.STEREO_BRUTE, S.STEREO_INITIAL])
+@pytest.mark.parametrize("ragged", [False, True])
+def test_stereo_match(ctx, orc, variant, ragged):
+    d = _data(12, 100 + variant, ragged=ragged)
+    g = ctx.stereo_match(d["curr_raw"], variant)
+    o = orc.stereo_match(d["cam"], ctx.cfg, d["curr_raw"], variant)
+    assert (o.n_pt > 100).all() and (o.n_ln > 3).all()
+    _cmp_stereo(g, o)
+
+
+def test_stereo_match_dense_and_degenerate(ctx, orc):
+    d = _data(2, 7, n_pt=2000, n_ln=500)                # C4 sizes
+    _cmp_stereo(ctx.stereo_match(d["curr_raw"]), orc.stereo_match(d["cam"], ctx.cfg, d["curr_raw"]))
+    d = _data(4, 8, n_pt=64, n_ln=24)
+    raw = d["curr_raw"]
+    raw.n_pt_l[0] = 0; raw.n_pt_r[1] = 1; raw.n_ln_l[2] = 1; raw.n_ln_r[3] = 0    # empty / single-row sets (D3)
+    raw.pdesc_r[2, :32] = raw.pdesc_l[2, :32]                                       # zero distances
+    raw.pdesc_r[2, 32:64] = raw.pdesc_l[2, :32]                                     # duplicates: d0 == d1 == 0 -> NaN ratio
+    g, o = ctx.stereo_match(raw), orc.stereo_match(d["cam"], ctx.cfg, raw)
+    _cmp_stereo(g, o)
+    assert g.n_pt[0] == 0 and g.n_pt[1] == 0 and g.n_ln[2] == 0 and g.n_ln[3] == 0
+
+
+def test_stereo_uncertainty(ctx, orc):
+    d = _data(6, 11)
+    fr = orc.stereo_match(d["cam"], ctx.cfg, d["prev_raw"])
+    g, o = ctx.stereo_uncertainty(fr), orc.stereo_uncertainty(d["cam"], ctx.cfg, fr)
+    for p in range(6):
+        n = fr.n_ln[p]
+        assert np.array_equal(g["covS"][p, :n], o["covS"][p, :n]) and np.array_equal(g["covE"][p, :n], o["covE"][p, :n])
+
+
+def _cmp_obs(g, o, exact=True):
+    assert np.array_equal(g.n_pt, o.n_pt) and np.array_equal(g.n_ln, o.n_ln)
+    for p in range(g.B):
+        assert_records_equal(g.pt[p], o.pt[p], n=g.n_pt[p])
+        assert_records_equal(g.ln[p], o.ln[p], n=g.n_ln[p])
+        assert np.array_equal(g.pt_inlier[p, :g.n_pt[p]], o.pt_inlier[p, :o.n_pt[p]])
+        assert np.array_equal(g.ln_inlier[p, :g.n_ln[p]], o.ln_inlier[p, :o.n_ln[p]])
+
+
+def _frames(orc, cfg, d):
+    return orc.stereo_match(d["cam"], cfg, d["prev_raw"]), orc.stereo_match(d["cam"], cfg, d["curr_raw"])
+
+
+@pytest.mark.parametrize("mode", [S.F2F_HYBRID, S.F2F_BRUTE])
+@pytest.mark.parametrize("ragged", [False, True])
+def test_f2f_match(ctx, orc, mode, ragged):
+    d = _data(10, 200 + mode, ragged=ragged)
+    prev, curr = _frames(orc, ctx.cfg, d)
+    g = ctx.f2f_match(prev, curr, d["state"], mode)
+    o = orc.f2f_match(d["cam"], ctx.cfg, prev, curr, d["state"], mode)
+    assert (o.n_pt > 50).all() and (o.n_ln > 2).all()
+    _cmp_obs(g, o)
+
+
+def test_f2f_hybrid_knn_candidates_and_caps(ctx, orc):
+    from gfpl import api
+    d = _data(6, 300)
+    cfg = api.default_config()
+    cfg.lr_in_parallel = 0                   # knn k=2 candidates instead of radius lists (:484-493)
+    cfg.max_point_match_num = 40             # force the early exit (:595)
+    cfg.max_line_match_num = 5
+    c2 = api.Context(0, cam=d["cam"], cfg=cfg)
+    prev, curr = _frames(orc, cfg, d)
+    g = c2.f2f_match(prev, curr, d["state"])
+    o = orc.f2f_match(d["cam"], cfg, prev, curr, d["state"])
+    assert (o.n_pt == 40).all() and (o.n_ln == 5).all()
+    _cmp_obs(g, o)
+
+
+def test_f2f_hybrid_duplicates_tie_stress(ctx, orc):
+    """low-entropy descriptors + zero motion: many candidates per previous point, previous points winning
+    several current keys and ties resolved to the lowest previous index (D2)."""
+    d = _data(3, 400, n_pt=200, n_ln=40)
+    rng = np.random.default_rng(4)
+    prev, curr = _frames(orc, ctx.cfg, d)
+    for fr in (prev, curr):
+        fr.pdesc[...] = 0
+        fr.pdesc[..., :1] = rng.integers(0, 4, fr.pdesc[..., :1].shape, dtype=np.uint8)
+    curr.pt["pl"][:, 1::2] = curr.pt["pl"][:, 0::2] + 3.0          # clusters of current points within the 10 px window
+    g = ctx.f2f_match(prev, curr, d["state"])
+    o = orc.f2f_match(d["cam"], ctx.cfg, prev, curr, d["state"])
+    dup = max(np.bincount(o.pt[p, :o.n_pt[p]]["prev_idx"]).max() for p in range(3) if o.n_pt[p])
+    assert dup >= 2
+    _cmp_obs(g, o)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# C2-C5, P1-P4
+# ---------------------------------------------------------------------------------------------------------
+def _obs(orc, cfg, d):
+    prev, curr = _frames(orc, cfg, d)
+    return prev, curr, orc.f2f_match(d["cam"], cfg, prev, curr, d["state"])
+
+
+def _dt_inv(state):
+    Tc = state["Tfw"].reshape(-1, 4, 4) @ state["DT"].reshape(-1, 4, 4)
+    return (np.linalg.inv(Tc) @ state["Tfw"].reshape(-1, 4, 4)).reshape(-1, 16)
+
+
+@pytest.mark.parametrize("max_vol", [1, 0])
+def test_linecut(ctx, orc, max_vol):
+    from gfpl import api
+    d = _data(8, 500 + max_vol)
+    cfg = api.default_config()
+    cfg.max_vol_line_cut = max_vol
+    c2 = api.Context(0, cam=d["cam"], cfg=cfg)
+    prev, curr, obs = _obs(orc, cfg, d)
+    cov = orc.stereo_uncertainty(d["cam"], cfg, prev)
+    DT_inv = _dt_inv(d["state"])
+    og, oo = obs.copy(), obs.copy()
+    cg = c2.linecut(DT_inv, og, cov)
+    co = orc.linecut(d["cam"], cfg, DT_inv, oo, cov)
+    flips = 0
+    for p in range(8):
+        n = obs.n_ln[p]
+        same = np.array_equal(cg["cutRatio"][p, :n], co["cutRatio"][p, :n])
+        flips += not same
+        if max_vol:
+            assert same, f"cut decisions differ in pair {p}"                     # exact cut ratios
+            assert close(cg["invCovPose"][p, :n], co["invCovPose"][p, :n])
+            for f in ("spl", "epl", "sdisp", "edisp"):
+                assert close(cg[f][p, :n], co[f][p, :n]), f
+            assert close(og.ln[p, :n]["sP"], oo.ln[p, :n]["sP"]) and close(og.ln[p, :n]["eP"], oo.ln[p, :n]["eP"])
+    # the min-eigenvalue metric (non-default) is an iterative eigen-solve: report, don't hide, decision flips
+    assert flips <= (0 if max_vol else 2), f"{flips} pairs with differing cut decisions"
+
+
+def test_pose_hg(ctx, orc):
+    d = _data(16, 600, ragged=True)
+    prev, curr, obs = _obs(orc, ctx.cfg, d)
+    obs.pt_inlier[:, ::7] = 0                                  # some outliers flagged
+    DT = np.linalg.inv(d["state"]["DT"].reshape(-1, 4, 4)).reshape(-1, 16)
+    Hg, gg, eg = ctx.pose_hg(DT, obs)
+    Ho, go, eo = orc.pose_hg(d["cam"], ctx.cfg, DT, obs)
+    for p in range(16):
+        assert close(Hg[p], Ho[p]) and close(gg[p], go[p]) and close(eg[p], eo[p])
+
+
+def _cmp_pose(pg, po, B):
+    assert np.array_equal(pg["status"], po["status"])
+    for f in ("n_inliers", "n_inliers_pt", "n_inliers_ls", "iters_first", "iters_ref"):
+        assert np.array_equal(pg[f], po[f]), f
+    for p in range(B):
+        for f in ("DT", "Tfw", "DT_cov", "Tfw_cov", "err_norm"):
+            assert close(pg[f][p], po[f][p]), (f, p)
+        assert close(pg["DT_cov_eig"][p], po["DT_cov_eig"][p], rtol=1e-7), p      # eigenvalues: relative to the largest
+
+
+@pytest.mark.parametrize("overload", [S.POSE_SEED_PREV_DT, S.POSE_SEED_GIVEN])
+def test_pose_optimize(ctx, orc, overload):
+    d = _data(24, 700 + overload, ragged=True)
+    prev, curr, obs = _obs(orc, ctx.cfg, d)
+    og, oo = obs.copy(), obs.copy()
+    ini = d["state"]["DT"].copy() if overload == S.POSE_SEED_GIVEN else None
+    pg = ctx.pose_optimize(og, d["state"], ini, overload)
+    po = orc.pose_optimize(d["cam"], ctx.cfg, oo, d["state"], ini, overload)
+    assert (po["status"] == 0).all()
+    assert np.array_equal(og.pt_inlier, oo.pt_inlier) and np.array_equal(og.ln_inlier, oo.ln_inlier)   # exact masks
+    _cmp_pose(pg, po, 24)
+
+
+def test_pose_optimize_gates(ctx, orc):
+    d = _data(6, 800)
+    prev, curr, obs = _obs(orc, ctx.cfg, d)
+    obs.n_pt[0] = 5; obs.n_ln[0] = 2                                   # too few features (:1953)
+    obs.pt[1]["P"][:, 2] = 0.0                                         # division by zero depth -> non-finite (:1959)
+    d["state"]["time_stamp_curr"][2] = d["state"]["time_stamp"][2]     # zero time step -> motion gate rejects (:1992)
+    obs.n_pt[3] = 0                                                     # lines only
+    og, oo = obs.copy(), obs.copy()
+    pg = ctx.pose_optimize(og, d["state"], d["state"]["DT"].copy(), S.POSE_SEED_GIVEN)
+    po = orc.pose_optimize(d["cam"], ctx.cfg, oo, d["state"], d["state"]["DT"].copy(), S.POSE_SEED_GIVEN)
+    assert po["status"][0] & 1 and po["status"][2] & 16 and po["status"][1] != 0
+    assert np.array_equal(pg["status"], po["status"])
+    assert np.array_equal(og.pt_inlier, oo.pt_inlier) and np.array_equal(og.ln_inlier, oo.ln_inlier)
+    for p in (0, 2, 3, 4, 5):
+        for f in ("DT", "Tfw", "Tfw_cov", "err_norm", "DT_cov"):
+            assert close(pg[f][p], po[f][p]), (f, p)
+    assert pg["err_norm"][1] == -1.0 and np.array_equal(pg["DT"][1], np.eye(4).reshape(16))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# whole step + resident replay
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flags", [S.TRACK_LINECUT | S.TRACK_SEED_GIVEN, 0, S.TRACK_F2F_BRUTE | S.TRACK_STEREO_INITIAL])
+def test_track_whole_step(ctx, orc, flags):
+    d = _data(16, 900 + flags, ragged=True)
+    prev = orc.stereo_match(d["cam"], ctx.cfg, d["prev_raw"])
+    cg, og, kg, pg = ctx.track(prev, d["state"], d["curr_raw"], flags)
+    co, oo, ko, po = orc.track(d["cam"], ctx.cfg, prev, d["state"], d["curr_raw"], flags)
+    _cmp_stereo(cg, co)
+    assert np.array_equal(og.n_pt, oo.n_pt) and np.array_equal(og.n_ln, oo.n_ln)
+    for p in range(16):
+        assert_records_equal(og.pt[p], oo.pt[p], n=og.n_pt[p])
+        assert_records_equal(og.ln[p], oo.ln[p], n=og.n_ln[p], tol_fields=("sP", "eP"))
+        assert np.array_equal(og.pt_inlier[p, :og.n_pt[p]], oo.pt_inlier[p, :oo.n_pt[p]])
+        assert np.array_equal(og.ln_inlier[p, :og.n_ln[p]], oo.ln_inlier[p, :oo.n_ln[p]])
+        if flags & S.TRACK_LINECUT:
+            assert np.array_equal(kg["cutRatio"][p, :og.n_ln[p]], ko["cutRatio"][p, :oo.n_ln[p]])
+    _cmp_pose(pg, po, 16)
+
+
+def test_replay_matches_track_and_is_deterministic(ctx, orc):
+    from gfpl import api
+    d = _data(64, 1000)
+    flags = S.TRACK_LINECUT | S.TRACK_SEED_GIVEN
+    prev = orc.stereo_match(d["cam"], ctx.cfg, d["prev_raw"])
+    _, og, kg, pg = ctx.track(prev, d["state"], d["curr_raw"], flags)
+    rp = api.Replay(ctx, 64, d["curr_raw"].cap_pt, d["curr_raw"].cap_ln)
+    rp.upload(prev, d["state"], d["curr_raw"])
+    poses = []
+    for _ in range(2):
+        rp.run(flags)
+        pose = np.zeros(64, S.pose_result_dt)
+        obs = S.TrackObsNP(64, ctx.cfg.max_point_match_num, ctx.cfg.max_line_match_num)
+        rp.download(pose, obs)
+        ctx.sync()
+        poses.append(pose.copy())
+    assert poses[0].tobytes() == poses[1].tobytes()                    # run-to-run bit-reproducible
+    assert poses[0].tobytes() == pg.tobytes()                          # resident path == host-pointer path
+    assert np.array_equal(obs.pt_inlier, og.pt_inlier)
+    assert rp.h2d_bytes() > 0 and rp.d2h_bytes() > 0
+    ms = rp.stage_ms()
+    assert len(ms) == S.NUM_STAGES and ms[6] > 0
+    assert ctx.launch_count() > 0
+
+
+def test_lba_assemble(ctx, orc):
+    for seed, kw in ((1, dict(n_kf=10, n_pt=1000, n_ls=300)), (2, dict(n_kf=3, n_pt=20, n_ls=5, n_fix=1))):
+        w = synth.make_lba_window(seed=seed, **kw)
+        c2 = ctx
+        c2.set_camera(w["cam"])
+        g = c2.lba_assemble(w)
+        o = orc.lba_assemble(w["cam"], ctx.cfg, w)
+        for k in ("Hpk", "Hlk"):
+            assert np.array_equal(g[k], o[k]), k                      # per-observation blocks: no reduction, bit-exact
+        for k in ("Hkk", "Hpp", "Hll", "g", "err"):
+            assert close(g[k], o[k]), k
+    from gfpl import api
+    ctx.set_camera(api.euroc_camera())
+
+
+def test_measure_peaks(ctx):
+    popc, fp64 = ctx.measure_peaks()
+    assert 1.0 < popc < 10.0 and 5.0 < fp64 < 100.0
