@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py — stereo frame pairs / s of the tracking hot path (stereo + f2f Hamming matching, good line
+cutting, pose Gauss-Newton) on a batched replay of independent frame pairs.
+
+    python bench.py --gpus N --steps K --warmup W            # the B200 path (libgfpl.so through the C ABI)
+    python bench.py --impl reference --gpus N ...            # the reference's CPU algorithm (oracle port)
+
+Workload (BASELINE.json configs[4] at configs[1]'s shape): 8192 independent EuRoC-shaped frame pairs PER GPU
+(752x480, 300 ORB points + 100 LSD lines per image, line cutting on); a step = one pass of the whole path
+over the batch.  Weak scaling: every rank owns its own 8192 pairs; NCCL only gathers the pose records.
+Prints ONE JSON line on rank 0.  See DESIGN.md §6 for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "gf-pl-slam_b200", "python"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "stereo frame pairs/s (stereo+f2f Hamming matching, line cut, pose GN)"
+UNIT = "frame_pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gfpl", choices=["gfpl", "reference"])
+    ap.add_argument("--pairs", type=int, default=8192, help="frame pairs per GPU")
+    ap.add_argument("--n-pt", type=int, default=300)
+    ap.add_argument("--n-ln", type=int, default=100)
+    ap.add_argument("--no-linecut", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=2048, help="pairs per step of the CPU reference arm")
+    ap.add_argument("--e2e-chunks", type=int, default=4)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a):
+    return {"workload": "batched replay of independent EuRoC-shaped frame pairs (752x480, %d ORB pts + %d LSD lines "
+                        "per image), good line cutting %s" % (a.n_pt, a.n_ln, "off" if a.no_linecut else "on"),
+            "pairs_per_gpu": a.pairs, "points_per_image": a.n_pt, "lines_per_image": a.n_ln,
+            "stages": "stereo knn+accept -> f2f hybrid search+accept -> stereo uncertainty+line cut -> pose GN(5)+MAD+GN(10)",
+            "l2_policy": "inputs larger than L2 (>=700 MB read per step vs 126 MB L2)", "parallelism": "pairs sharded over ranks, NCCL all_gather of pose records only"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        load = sorted(x for x in sm if x > 0)
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference(a, rank_seed=0):
+    """The reference's CPU algorithm for the path: the oracle port (the reference itself cannot be built here,
+    DESIGN.md §3), all host threads, on a bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    from gfpl import synth, _structs as S
+    n = min(a.pairs, a.cpu_sample)
+    cores = os.cpu_count() or 1
+    d = synth.make_pairs(n, n_pt=a.n_pt, n_ln=a.n_ln, seed=1000 + rank_seed)
+    cfg = orc.default_config()
+    flags = (0 if a.no_linecut else S.TRACK_LINECUT) | S.TRACK_SEED_GIVEN
+    prev = orc.stereo_match(d["cam"], cfg, d["prev_raw"])
+
+    def step():
+        t0 = time.perf_counter()
+        orc.track(d["cam"], cfg, prev, d["state"], d["curr_raw"], flags, n_threads=cores)
+        return time.perf_counter() - t0
+    return n, cores, step
+
+
+def run_reference(a, rank):
+    if rank != 0:
+        return
+    n, cores, step = cpu_reference(a)
+    for _ in range(max(a.warmup, 1)):
+        step()
+    ts = [step() for _ in range(a.steps)]
+    dt = sum(ts)
+    v = n * a.steps / dt
+    sample = "%d of %d pairs per step, %d std::threads over pairs" % (n, a.pairs, cores)
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+                      "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "u8/int32 matching + f64 optimisation", "data": "synthetic",
+                      "config": workload_config(a),
+                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+class DevArray:
+    """zero-copy torch view of a raw device pointer (for the NCCL gather of the pose records)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from gfpl import api, synth, _structs as S
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = a.pairs
+    flags = (0 if a.no_linecut else S.TRACK_LINECUT) | S.TRACK_SEED_GIVEN
+
+    # ---- synthetic inputs in pinned host memory (detector output of B frame pairs) -----------------------
+    d = synth.make_pairs(B, n_pt=a.n_pt, n_ln=a.n_ln, seed=1000 + rank, pinned=True)
+    ctx = api.Context(local, cam=d["cam"])
+    prev = S.StereoFramesNP(B, a.n_pt, a.n_ln, pinned=True)
+    CH = 1024
+    for lo in range(0, B, CH):            # previous frames' stereo features: the GPU stereo stage, untimed setup
+        hi = min(B, lo + CH)
+        part = ctx.stereo_match(d["prev_raw"].slice(lo, hi))
+        for k in S.StereoFramesNP._keys:
+            getattr(prev, k)[lo:hi] = getattr(part, k)
+    popc_peak, fp64_peak = ctx.measure_peaks()
+
+    rp = api.Replay(ctx, B, a.n_pt, a.n_ln)
+    rp.upload(prev, d["state"], d["curr_raw"])
+    ctx.sync()
+    pose_host = S._alloc(B, S.pose_result_dt, True)
+    pose_bytes = B * S.pose_result_dt.itemsize
+    gather_out = torch.empty(world * pose_bytes, dtype=torch.uint8, device="cuda") if world > 1 else None
+    pose_dev = torch.as_tensor(DevArray(rp.pose_device_ptr(), pose_bytes), device="cuda") if world > 1 else None
+
+    def step():
+        rp.run(flags)
+        if world > 1:                     # K7: the only collective — gather the per-pair pose records
+            ctx.sync()
+            dist.all_gather_into_tensor(gather_out, pose_dev)
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    # ---- value: inputs resident in HBM, K steps, CUDA events on the launching stream ----------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = ctx.launch_count()
+    stage = np.zeros(S.NUM_STAGES)
+    barrier()
+    ctx.timer_record(0)
+    for _ in range(a.steps):
+        step()
+        stage += np.array(rp.stage_ms())  # per-kernel CUDA-event times of this step (sync on the step's last event)
+    torch.cuda.synchronize()
+    ctx.timer_record(1)
+    ms = ctx.timer_elapsed_ms(0, 1)
+    barrier()
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    stage /= a.steps
+    pairs = rp.pair_counts()
+
+    # ---- e2e: host buffers in, pose records out, chunked over two contexts so copies overlap compute --------
+    nchunk = max(1, min(a.e2e_chunks, B))
+    bounds = np.linspace(0, B, nchunk + 1).astype(int)
+    ctxs = [ctx, api.Context(local, cam=d["cam"])]
+    chunks = []
+    for i in range(nchunk):
+        lo, hi = int(bounds[i]), int(bounds[i + 1])
+        c = ctxs[i % 2]
+        chunks.append((c, api.Replay(c, hi - lo, a.n_pt, a.n_ln), prev.slice(lo, hi), d["state"][lo:hi],
+                       d["curr_raw"].slice(lo, hi), pose_host[lo:hi]))
+    h2d = d2h = 0
+
+    def e2e_step():
+        nonlocal h2d, d2h
+        h2d = d2h = 0
+        for c, r, pv, st, raw, ph in chunks:
+            r.upload(pv, st, raw)
+            r.run(flags)
+            r.download(ph)
+            h2d += r.h2d_bytes()
+            d2h += r.d2h_bytes()
+        for c in ctxs:
+            c.sync()
+        if world > 1:
+            dist.all_gather_into_tensor(gather_out, pose_dev)
+            torch.cuda.synchronize()
+
+    for _ in range(max(2, a.warmup // 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        e2e_step()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    assert (pose_host["status"] == 0).mean() > 0.99, "tracking failed on the synthetic batch"
+
+    # ---- max over ranks ----------------------------------------------------------------------------------------
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        value = world * B * a.steps / (ms * 1e-3)
+        e2e_value = world * B * a.steps / (e2e_ms * 1e-3)
+        # dominant kernel: the Hamming matching kernels (kernels 0,1,3,4: same inner loop, POPC-pipe bound)
+        k_ms = [stage[0], stage[1], stage[3], stage[4]]
+        dom = int(np.argmax(k_ms))
+        names = ["knn2 stereo points (2 directions)", "knn2 stereo lines NORM_HAMMING2 (2 directions)",
+                 "f2f hybrid fused radius+projection search", "knn2 f2f lines (2 directions)"]
+        popc = 8.0 * pairs[dom]
+        achieved = popc / (k_ms[dom] * 1e-3) / 1e12
+        n_pt_l = float(np.mean(d["curr_raw"].n_pt_l))
+        alg_bytes = B * (2 * a.n_pt * 32 + 2 * a.n_pt * 16) if dom == 0 else None
+        roofline = {"bound": "alu", "pipe": "INT popc.b32 (16 lanes/clk/SM); not HBM-, not tensor-bound (SURVEY.md §8d)",
+                    "kernel": names[dom], "achieved": achieved, "peak": popc_peak, "unit": "Tpopc/s",
+                    "frac": achieved / popc_peak, "peak_source": "measured live by gfpl_measure_peaks (popc micro-benchmark)",
+                    "kernel_ms": k_ms[dom], "pairs_per_launch": pairs[dom], "traffic": None,
+                    "hbm": {"achieved_GBps": (alg_bytes / (k_ms[dom] * 1e-3) / 1e9) if alg_bytes else None,
+                            "peak_GBps": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+                            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0},
+                    "all_matching_kernels_frac": 8.0 * sum(pairs) / (sum(k_ms) * 1e-3) / 1e12 / popc_peak}
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+               "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "u8/int32 matching + f64 optimisation", "data": "synthetic", "config": workload_config(a),
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "ms_per_step": e2e_ms / a.steps, "chunks": nchunk, "timing": "host wall clock around upload+run+download+sync"},
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+               "kernel_ms_per_step": dict(zip(["knn_stereo_pt", "knn_stereo_ln", "stereo_accept", "f2f_pt_search", "knn_f2f_ln",
+                                               "f2f_accept", "uncertainty+linecut", "pose_gn", "step"], [float(x) for x in stage])),
+               "peaks": {"popc_Tops": popc_peak, "fp64_TFLOPs": fp64_peak}}
+        if not a.skip_cpu_baseline:
+            n, cores, cstep = cpu_reference(a)
+            cstep()
+            dt = cstep()
+            out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": "%d of %d pairs, one pass, %d std::threads over pairs (oracle port of the "
+                                             "reference algorithm)" % (n, B, cores)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -239,6 +239,8 @@ void gfpl_ctx_destroy(gfpl_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (auto& e : ctx->timer)
+    if (e) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -363,11 +365,13 @@ static bool alloc_work(DevMem& m, int B, int cap_pt, int cap_ln, StepWork* w) {
   return ok && w->best_key && w->prev_cov;
 }
 
-static int run_stereo(gfpl_ctx* ctx, const DevRawFrames& raw, int variant, StepWork& w, DevStereoFrames curr) {
+static int run_stereo(gfpl_ctx* ctx, const DevRawFrames& raw, int variant, StepWork& w, DevStereoFrames curr,
+                      cudaEvent_t mid = nullptr) {
   const int B = raw.B;
   if (ctx->cfg.has_points)
     CHECK(launch_knn2(ctx, B, raw.pdesc_l, raw.n_pt_l, raw.cap_pt, raw.pdesc_r, raw.n_pt_r, raw.cap_pt,
                       GFPL_NORM_HAMMING, w.pt_lr, ctx->cfg.best_lr_matches ? w.pt_rl : Knn2Out{}));
+  if (mid) cudaEventRecord(mid, ctx->stream);
   if (ctx->cfg.has_lines)
     CHECK(launch_knn2(ctx, B, raw.ldesc_l, raw.n_ln_l, raw.cap_ln, raw.ldesc_r, raw.n_ln_r, raw.cap_ln,
                       variant == GFPL_STEREO_INITIAL ? GFPL_NORM_HAMMING : GFPL_NORM_HAMMING2, w.ln_lr,
@@ -376,7 +380,7 @@ static int run_stereo(gfpl_ctx* ctx, const DevRawFrames& raw, int variant, StepW
 }
 
 static int run_f2f_knn(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr,
-                       const gfpl_frame_state* state, int mode, StepWork& w) {
+                       const gfpl_frame_state* state, int mode, StepWork& w, cudaEvent_t mid = nullptr) {
   const int B = prev.B;
   const bool use_radius = ctx->cfg.best_lr_matches && ctx->cfg.lr_in_parallel;
   if (ctx->cfg.has_points) {
@@ -391,6 +395,7 @@ static int run_f2f_knn(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevSter
       CHECK(launch_f2f_hybrid_points_knn(ctx, prev, curr, state, w.pt_12, w.best_key));
     }
   }
+  if (mid) cudaEventRecord(mid, ctx->stream);
   if (ctx->cfg.has_lines)
     CHECK(launch_knn2(ctx, B, prev.ldesc, prev.n_ln, prev.cap_ln, curr.ldesc, curr.n_ln, curr.cap_ln,
                       GFPL_NORM_HAMMING, w.ln_12, ctx->cfg.best_lr_matches ? w.ln_21 : Knn2Out{}));
@@ -410,7 +415,7 @@ struct gfpl_replay {
   gfpl_line_cut* cut = nullptr;
   gfpl_pose_result* pose = nullptr;
   StepWork w{};
-  cudaEvent_t ev[GFPL_NUM_STAGES + 1] = {};
+  cudaEvent_t ev[GFPL_NUM_STAGES] = {};
   int64_t h2d = 0, d2h = 0;
   bool timed = false;
   template <typename T>
@@ -555,22 +560,22 @@ static int run_step(gfpl_ctx* ctx, const DevStereoFrames& prev, const gfpl_frame
   const int variant = (flags & GFPL_TRACK_STEREO_INITIAL) ? GFPL_STEREO_INITIAL : GFPL_STEREO_BRUTE;
   const int mode = (flags & GFPL_TRACK_F2F_BRUTE) ? GFPL_F2F_BRUTE : GFPL_F2F_HYBRID;
   if (ev) cudaEventRecord(ev[0], ctx->stream);
-  CHECK(run_stereo(ctx, raw, variant, w, curr));
-  if (ev) cudaEventRecord(ev[1], ctx->stream);
-  CHECK(launch_stereo_accept(ctx, raw, variant, w.pt_lr, w.pt_rl, w.ln_lr, w.ln_rl, curr));
+  CHECK(run_stereo(ctx, raw, variant, w, curr, ev ? ev[1] : nullptr));
   if (ev) cudaEventRecord(ev[2], ctx->stream);
-  CHECK(run_f2f_knn(ctx, prev, curr, state, mode, w));
+  CHECK(launch_stereo_accept(ctx, raw, variant, w.pt_lr, w.pt_rl, w.ln_lr, w.ln_rl, curr));
   if (ev) cudaEventRecord(ev[3], ctx->stream);
+  CHECK(run_f2f_knn(ctx, prev, curr, state, mode, w, ev ? ev[4] : nullptr));
+  if (ev) cudaEventRecord(ev[5], ctx->stream);
   CHECK(launch_f2f_accept(ctx, prev, curr, mode, w.best_key, w.pt_12, w.pt_21, w.ln_12, w.ln_21, obs));
-  if (ev) cudaEventRecord(ev[4], ctx->stream);
+  if (ev) cudaEventRecord(ev[6], ctx->stream);
   if ((flags & GFPL_TRACK_LINECUT) && ctx->cfg.use_line_conf_cut && cut) {
     CHECK(launch_stereo_uncertainty(ctx, prev, w.prev_cov));
     CHECK(launch_linecut(ctx, nullptr, state, obs, w.prev_cov, prev.cap_ln, cut));
   }
-  if (ev) cudaEventRecord(ev[5], ctx->stream);
+  if (ev) cudaEventRecord(ev[7], ctx->stream);
   CHECK(launch_pose_optimize(ctx, obs, state, nullptr,
                              (flags & GFPL_TRACK_SEED_GIVEN) ? GFPL_POSE_SEED_GIVEN : GFPL_POSE_SEED_PREV_DT, pose));
-  if (ev) cudaEventRecord(ev[6], ctx->stream);
+  if (ev) cudaEventRecord(ev[8], ctx->stream);
   return GFPL_OK;
 }
 
@@ -746,9 +751,48 @@ int gfpl_replay_stage_ms(gfpl_replay* rp, float* ms) {
   if (!rp || !ms) return GFPL_E_INVALID;
   gfpl_ctx* ctx = rp->ctx;
   REQUIRE(ctx, rp->timed);
-  GFPL_CUDA_OK(ctx, cudaEventSynchronize(rp->ev[6]));
-  for (int i = 0; i < 6; i++) GFPL_CUDA_OK(ctx, cudaEventElapsedTime(&ms[i], rp->ev[i], rp->ev[i + 1]));
-  GFPL_CUDA_OK(ctx, cudaEventElapsedTime(&ms[6], rp->ev[0], rp->ev[6]));
+  GFPL_CUDA_OK(ctx, cudaEventSynchronize(rp->ev[8]));
+  for (int i = 0; i < 8; i++) GFPL_CUDA_OK(ctx, cudaEventElapsedTime(&ms[i], rp->ev[i], rp->ev[i + 1]));
+  GFPL_CUDA_OK(ctx, cudaEventElapsedTime(&ms[8], rp->ev[0], rp->ev[8]));
+  return GFPL_OK;
+}
+
+int gfpl_replay_pair_counts(gfpl_replay* rp, int64_t* pairs) {
+  if (!rp || !pairs) return GFPL_E_INVALID;
+  gfpl_ctx* ctx = rp->ctx;
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  const int B = rp->B;
+  std::vector<int32_t> n(8 * (size_t)B);
+  const int32_t* src[8] = {rp->raw.n_pt_l, rp->raw.n_pt_r, rp->raw.n_ln_l, rp->raw.n_ln_r,
+                           rp->prev.n_pt, rp->curr.n_pt, rp->prev.n_ln, rp->curr.n_ln};
+  for (int k = 0; k < 8; k++)
+    GFPL_CUDA_OK(ctx, cudaMemcpyAsync(n.data() + (size_t)k * B, src[k], (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CHECK(finish(ctx));
+  const bool both = ctx->cfg.best_lr_matches;
+  pairs[0] = pairs[1] = pairs[2] = pairs[3] = 0;
+  for (int p = 0; p < B; p++) {
+    pairs[0] += (int64_t)n[p] * n[B + p] * (both ? 2 : 1);
+    pairs[1] += (int64_t)n[2 * B + p] * n[3 * B + p] * (both ? 2 : 1);
+    pairs[2] += (int64_t)n[4 * B + p] * n[5 * B + p];  // hybrid fused search: one direction
+    pairs[3] += (int64_t)n[6 * B + p] * n[7 * B + p] * (both ? 2 : 1);
+  }
+  return GFPL_OK;
+}
+
+int gfpl_timer_record(gfpl_ctx* ctx, int32_t slot) {
+  if (!ctx) return GFPL_E_INVALID;
+  REQUIRE(ctx, slot >= 0 && slot < 8);
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->timer[slot]) GFPL_CUDA_OK(ctx, cudaEventCreate(&ctx->timer[slot]));
+  GFPL_CUDA_OK(ctx, cudaEventRecord(ctx->timer[slot], ctx->stream));
+  return GFPL_OK;
+}
+
+int gfpl_timer_elapsed_ms(gfpl_ctx* ctx, int32_t a, int32_t b, float* ms) {
+  if (!ctx || !ms) return GFPL_E_INVALID;
+  REQUIRE(ctx, a >= 0 && a < 8 && b >= 0 && b < 8 && ctx->timer[a] && ctx->timer[b]);
+  GFPL_CUDA_OK(ctx, cudaEventSynchronize(ctx->timer[b]));
+  GFPL_CUDA_OK(ctx, cudaEventElapsedTime(ms, ctx->timer[a], ctx->timer[b]));
   return GFPL_OK;
 }
 

@@ -37,6 +37,7 @@ struct gfpl_ctx {
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
   size_t scratch_used = 0;
+  cudaEvent_t timer[8] = {};
 };
 
 #define GFPL_CUDA_OK(ctx, expr)                                                              \

@@ -15,7 +15,7 @@ STEREO_INITIAL, STEREO_BRUTE = 0, 1
 F2F_HYBRID, F2F_BRUTE = 0, 1
 POSE_SEED_PREV_DT, POSE_SEED_GIVEN = 0, 1
 TRACK_LINECUT, TRACK_F2F_BRUTE, TRACK_SEED_GIVEN, TRACK_STEREO_INITIAL = 1, 2, 4, 8
-NUM_STAGES = 7
+NUM_STAGES = 9
 
 OK, E_INVALID, E_NO_DEVICE, E_CUDA, E_NOMEM, E_CAPACITY = 0, -1, -2, -3, -4, -5
 

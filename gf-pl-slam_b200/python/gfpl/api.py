@@ -115,6 +115,14 @@ class Context:
     def launch_count(self):
         return int(lib().gfpl_ctx_launch_count(self._h))
 
+    def timer_record(self, slot):
+        self._check(lib().gfpl_timer_record(self._h, slot))
+
+    def timer_elapsed_ms(self, a, b):
+        ms = C.c_float()
+        self._check(lib().gfpl_timer_elapsed_ms(self._h, a, b, C.byref(ms)))
+        return ms.value
+
     def measure_peaks(self):
         p, f = C.c_double(), C.c_double()
         self._check(lib().gfpl_measure_peaks(self._h, C.byref(p), C.byref(f)))
@@ -261,6 +269,11 @@ class Replay:
 
     def pose_device_ptr(self):
         return lib().gfpl_replay_pose_device_ptr(self._h)
+
+    def pair_counts(self):
+        n = (C.c_int64 * 4)()
+        self.ctx._check(lib().gfpl_replay_pair_counts(self._h, n))
+        return list(n)
 
     def stage_ms(self):
         ms = (C.c_float * S.NUM_STAGES)()

@@ -139,7 +139,7 @@ typedef struct gfpl_dmatch {
   float distance;
 } gfpl_dmatch;
 
-/* StVO::PointFeature (stereoFeatures.h:36-62), fields on the path. 80 B */
+/* StVO::PointFeature (stereoFeatures.h:36-62), fields on the path. 72 B */
 typedef struct gfpl_point_feature {
   double P[3];
   double pl[2];
@@ -402,11 +402,20 @@ int64_t gfpl_replay_d2h_bytes(const gfpl_replay* rp);
 /* device pointer of the [B] gfpl_pose_result records (for an NCCL gather without a host bounce) */
 void* gfpl_replay_pose_device_ptr(gfpl_replay* rp);
 
-/* stage timing of the last gfpl_replay_run, from CUDA events on the context stream (TimeLog analogue,
- * stereoFrame.h:66-86): ms for [0] stereo matching kernels, [1] stereo accept, [2] f2f matching,
- * [3] f2f accept, [4] stereo uncertainty + line cut, [5] pose optimisation, [6] whole step. */
-#define GFPL_NUM_STAGES 7
+/* per-kernel timing of the last gfpl_replay_run, from CUDA events on the context stream (TimeLog analogue,
+ * stereoFrame.h:66-86).  ms[k] for kernel k, ms[GFPL_NUM_STAGES-1] = whole step:
+ *   0 stereo point knn (both directions)   1 stereo line knn (both directions)   2 stereo accept loops
+ *   3 f2f point search (hybrid fused / knn) 4 f2f line knn (both directions)     5 f2f accept loops
+ *   6 stereo uncertainty + line cut         7 pose optimisation                    8 whole step */
+#define GFPL_NUM_STAGES 9
 int gfpl_replay_stage_ms(gfpl_replay* rp, float* ms /*[GFPL_NUM_STAGES]*/);
+/* algorithmic work of the last uploaded batch: descriptor pairs compared by kernels 0,1,3,4 (each pair = 8 popc.b32);
+ * valid after gfpl_replay_run + sync (counts of the current stereo stage are read back). pairs: [4] */
+int gfpl_replay_pair_counts(gfpl_replay* rp, int64_t* pairs /*[4]*/);
+
+/* CUDA-event stopwatch on the context stream: record slot a/b (0..7), then elapsed (synchronises on b) */
+int gfpl_timer_record(gfpl_ctx* ctx, int32_t slot);
+int gfpl_timer_elapsed_ms(gfpl_ctx* ctx, int32_t slot_a, int32_t slot_b, float* ms);
 
 /* ------------------------------------------------------------------------- */
 /* L2 — local bundle adjustment assembly                                      */

@@ -361,7 +361,7 @@ def test_replay_matches_track_and_is_deterministic(ctx, orc):
     assert np.array_equal(obs.pt_inlier, og.pt_inlier)
     assert rp.h2d_bytes() > 0 and rp.d2h_bytes() > 0
     ms = rp.stage_ms()
-    assert len(ms) == S.NUM_STAGES and ms[6] > 0
+    assert len(ms) == S.NUM_STAGES and ms[-1] > 0
     assert ctx.launch_count() > 0
 
 
