@@ -46,7 +46,7 @@ __device__ __forceinline__ void stage_projections(const DevStereoFrames& prev, c
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(F2F_THREADS)
+__global__ void __launch_bounds__(F2F_THREADS, 6)
 f2f_hybrid_points_kernel(DevStereoFrames prev, DevStereoFrames curr, const gfpl_frame_state* __restrict__ state,
                          uint32_t* __restrict__ best_key, gfpl_camera cam, gfpl_config cfg) {
   extern __shared__ __align__(128) uint8_t s_dyn[];

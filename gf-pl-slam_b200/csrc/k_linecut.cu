@@ -53,39 +53,46 @@ struct LineInfo {  // what getPoseInfoOnLine needs to form info = [Js Je] * inv(
   double i00, i01, i10, i11;
 };
 
-struct LineData {
-  double sP[3], eP[3], le[2];
-  double covS[9], covE[9];
-};
+// line data layout used by the evaluation: sP[3] eP[3] le[2] covS[9] covE[9] = 26 doubles
+constexpr int LD_SP = 0, LD_EP = 3, LD_LE = 6, LD_CS = 8, LD_CE = 17, LD_SIZE = 26;
 
-__device__ __forceinline__ void pose_info_on_line(const gfpl_camera& cam, const gfpl_config& cfg, const double* DT_inv,
-                                                  const LineData& L, double c0, double c1, LineInfo& out) {
-  double sP_tmp[3], eP_tmp[3], cov_sP[9], cov_eP[9], R[9];
+// getPoseInfoOnLine up to the two Jacobian columns and the 2x2 inverse.  `DT` = [R (9) | t (3)], `L` = line data;
+// both may live in shared memory (pass 3: one copy per 8-lane group) or be read straight from global (pass 1).
+__device__ __forceinline__ void pose_info_on_line(const gfpl_camera& cam, const gfpl_config& cfg, const double* DT,
+                                                  const double* L, double c0, double c1, LineInfo& out) {
+  double R[9], T4[16];
 #pragma unroll
-  for (int k = 0; k < 3; k++) {
-    sP_tmp[k] = (1 - c0) * L.sP[k] + c0 * L.eP[k];
-    eP_tmp[k] = (1 - c1) * L.eP[k] + c1 * L.sP[k];
+  for (int i = 0; i < 9; i++) R[i] = DT[i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    T4[i * 4 + 0] = R[i * 3 + 0]; T4[i * 4 + 1] = R[i * 3 + 1]; T4[i * 4 + 2] = R[i * 3 + 2]; T4[i * 4 + 3] = DT[9 + i];
   }
-  const double a0 = (1 - c0) * (1 - c0), b0 = c0 * c0;
-  const double a1 = (1 - c1) * (1 - c1), b1 = c1 * c1;
+  const double le[2] = {L[LD_LE], L[LD_LE + 1]};
+  double cov_sR, cov_eR;
+  {
+    double P[3], cur[3], cv[9], Jp[6];
+    const double a0 = (1 - c0) * (1 - c0), b0 = c0 * c0;
 #pragma unroll
-  for (int k = 0; k < 9; k++) {
-    cov_sP[k] = a0 * L.covS[k] + b0 * L.covE[k];
-    cov_eP[k] = a1 * L.covE[k] + b1 * L.covS[k];
+    for (int k = 0; k < 3; k++) P[k] = (1 - c0) * L[LD_SP + k] + c0 * L[LD_EP + k];
+#pragma unroll
+    for (int k = 0; k < 9; k++) cv[k] = a0 * L[LD_CS + k] + b0 * L[LD_CE + k];
+    se3_apply(T4, P, cur);
+    jacob3d_2d(cam, cur[0], cur[1], cur[2], Jp);
+    cov_sR = residual_var(Jp, R, cv, le);
+    jac6(cam.fx / fmax(cfg.homog_th, cur[2] * cur[2]), cur[0], cur[1], cur[2], le[0], le[1], out.Js);
   }
+  {
+    double P[3], cur[3], cv[9], Jp[6];
+    const double a1 = (1 - c1) * (1 - c1), b1 = c1 * c1;
 #pragma unroll
-  for (int i = 0; i < 3; i++)
+    for (int k = 0; k < 3; k++) P[k] = (1 - c1) * L[LD_EP + k] + c1 * L[LD_SP + k];
 #pragma unroll
-    for (int j = 0; j < 3; j++) R[i * 3 + j] = DT_inv[i * 4 + j];
-  double cur_s[3], cur_e[3], Jp[6];
-  se3_apply(DT_inv, sP_tmp, cur_s);
-  jacob3d_2d(cam, cur_s[0], cur_s[1], cur_s[2], Jp);
-  const double cov_sR = residual_var(Jp, R, cov_sP, L.le);
-  se3_apply(DT_inv, eP_tmp, cur_e);
-  jacob3d_2d(cam, cur_e[0], cur_e[1], cur_e[2], Jp);
-  const double cov_eR = residual_var(Jp, R, cov_eP, L.le);
-  jac6(cam.fx / fmax(cfg.homog_th, cur_s[2] * cur_s[2]), cur_s[0], cur_s[1], cur_s[2], L.le[0], L.le[1], out.Js);
-  jac6(cam.fx / fmax(cfg.homog_th, cur_e[2] * cur_e[2]), cur_e[0], cur_e[1], cur_e[2], L.le[0], L.le[1], out.Je);
+    for (int k = 0; k < 9; k++) cv[k] = a1 * L[LD_CE + k] + b1 * L[LD_CS + k];
+    se3_apply(T4, P, cur);
+    jacob3d_2d(cam, cur[0], cur[1], cur[2], Jp);
+    cov_eR = residual_var(Jp, R, cv, le);
+    jac6(cam.fx / fmax(cfg.homog_th, cur[2] * cur[2]), cur[0], cur[1], cur[2], le[0], le[1], out.Je);
+  }
   // 2x2 inverse of diag(cov_sR, cov_eR) as adjugate * (1/det)
   const double det = cov_sR * cov_eR - 0.0 * 0.0;
   const double invdet = 1.0 / det;
@@ -101,14 +108,6 @@ __device__ __forceinline__ double info_entry(const LineInfo& I, int i, int j) {
   return Ai0 * I.Js[j] + Ai1 * I.Je[j];
 }
 
-__device__ __forceinline__ void load_line(const gfpl_ln_obs& o, const gfpl_line_cov& c, LineData& L) {
-#pragma unroll
-  for (int k = 0; k < 3; k++) { L.sP[k] = o.sP[k]; L.eP[k] = o.eP[k]; }
-  L.le[0] = o.le_obs[0]; L.le[1] = o.le_obs[1];
-#pragma unroll
-  for (int k = 0; k < 9; k++) { L.covS[k] = c.covS[k]; L.covE[k] = c.covE[k]; }
-}
-
 // metric on a lower-triangle-packed matrix
 __device__ __forceinline__ double cut_metric(const gfpl_config& cfg, const double* M21) {
   if (cfg.max_vol_line_cut) return logdet6_packed(M21);
@@ -119,10 +118,24 @@ __device__ __forceinline__ double cut_metric(const gfpl_config& cfg, const doubl
   return ev[0];
 }
 
-__global__ void __launch_bounds__(CUT_THREADS)
+// per-group (one frame pair) state kept in shared memory: every lane of the group reads the same addresses
+// (broadcast), which frees ~120 registers per thread and lets 16 warps / SM hide the fp64 dependency chains.
+struct GroupState {
+  double DT[12];        // R | t of DT_inv
+  double L[LD_SIZE];    // current line
+  double sum[21];       // invCov_sum, lower triangle
+  double pad;
+};
+
+#ifndef CUT_MIN_BLOCKS
+#define CUT_MIN_BLOCKS 4
+#endif
+
+__global__ void __launch_bounds__(CUT_THREADS, CUT_MIN_BLOCKS)
 linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __restrict__ state, DevTrackObs obs,
                const gfpl_line_cov* __restrict__ prev_cov, int cov_cap, gfpl_line_cut* __restrict__ cut_all,
                gfpl_camera cam, gfpl_config cfg) {
+  __shared__ GroupState s_grp[CUT_THREADS / CUT_GROUP];
   const int lane = threadIdx.x & 31;
   const int j = lane & (CUT_GROUP - 1);             // neighbour index of this lane
   const int grp = lane / CUT_GROUP;                 // pair slot inside the warp
@@ -131,21 +144,30 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
   if (p >= obs.B) return;
   const int nln = obs.n_ln[p], npt = obs.n_pt[p];
   if (nln == 0) return;  // :1621
+  GroupState& G = s_grp[threadIdx.x / CUT_GROUP];
   gfpl_ln_obs* lns = obs.ln + (size_t)p * obs.cap_ln;
   const gfpl_pt_obs* pts = obs.pt + (size_t)p * obs.cap_pt;
   const gfpl_line_cov* cov = prev_cov + (size_t)p * cov_cap;
   gfpl_line_cut* cut = cut_all + (size_t)p * obs.cap_ln;
 
-  double DT_inv[16];
-  if (DT_inv_all) {
+  if (j == 0) {
+    double DT_inv[16];
+    if (DT_inv_all) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) DT_inv[i] = DT_inv_all[(size_t)p * 16 + i];
-  } else {
-    double Tc[16], Tci[16];
-    matmul<4, 4, 4>(state[p].Tfw, state[p].DT, Tc);  // predicted curr->Tfw (:157)
-    inverse4(Tc, Tci);
-    matmul<4, 4, 4>(Tci, state[p].Tfw, DT_inv);      // :1635
+      for (int i = 0; i < 16; i++) DT_inv[i] = DT_inv_all[(size_t)p * 16 + i];
+    } else {
+      double Tc[16], Tci[16];
+      matmul<4, 4, 4>(state[p].Tfw, state[p].DT, Tc);  // predicted curr->Tfw (:157)
+      inverse4(Tc, Tci);
+      matmul<4, 4, 4>(Tci, state[p].Tfw, DT_inv);      // :1635
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      G.DT[i * 3 + 0] = DT_inv[i * 4 + 0]; G.DT[i * 3 + 1] = DT_inv[i * 4 + 1]; G.DT[i * 3 + 2] = DT_inv[i * 4 + 2];
+      G.DT[9 + i] = DT_inv[i * 4 + 3];
+    }
   }
+  __syncwarp(gmask);
 
   const double step = cfg.cut_step;
   const double nb0 = (j == 0 || j == 4 || j == 5) ? step : ((j == 1 || j == 6 || j == 7) ? -step : 0.0);
@@ -153,10 +175,16 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
 
   // pass 1a: initial information of every line (cut = 0), lanes stride over the lines (:1638-1649)
   for (int l = j; l < nln; l += CUT_GROUP) {
-    LineData L;
+    double Lr[LD_SIZE];
     LineInfo I;
-    load_line(lns[l], cov[lns[l].prev_idx], L);
-    pose_info_on_line(cam, cfg, DT_inv, L, 0.0, 0.0, I);
+    const gfpl_ln_obs& o = lns[l];
+    const gfpl_line_cov& c = cov[o.prev_idx];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { Lr[LD_SP + k] = o.sP[k]; Lr[LD_EP + k] = o.eP[k]; }
+    Lr[LD_LE] = o.le_obs[0]; Lr[LD_LE + 1] = o.le_obs[1];
+#pragma unroll
+    for (int k = 0; k < 9; k++) { Lr[LD_CS + k] = c.covS[k]; Lr[LD_CE + k] = c.covE[k]; }
+    pose_info_on_line(cam, cfg, G.DT, Lr, 0.0, 0.0, I);
     gfpl_line_cut& C = cut[l];
     C.cutRatio[0] = 0.0; C.cutRatio[1] = 0.0;
     for (int a = 0; a < 6; a++)
@@ -164,42 +192,77 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
   }
   __syncwarp(gmask);
 
-  // pass 1b/2: invCov_sum in the reference's order — lines, then points — held by every lane (lower triangle)
-  double sum[21];
+  // pass 1b/2: invCov_sum in the reference's order — lines, then points, each element summed sequentially.
+  // Lane j owns lower-triangle elements e = j, j+8, j+16.
+  {
+    int ea[3], eb[3];
+    double acc[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-  for (int e = 0; e < 21; e++) sum[e] = 0.0;
-  for (int l = 0; l < nln; l++) {
-    const double* info = cut[l].invCovPose;
+    for (int q = 0; q < 3; q++) {
+      const int e = min(j + 8 * q, 20);
+      int a = 0;
+      while ((a + 1) * (a + 2) / 2 <= e) a++;
+      ea[q] = a; eb[q] = e - a * (a + 1) / 2;
+    }
+    for (int l = 0; l < nln; l++) {
+      const double* info = cut[l].invCovPose;
 #pragma unroll
-    for (int a = 0; a < 6; a++)
+      for (int q = 0; q < 3; q++) acc[q] = acc[q] + info[ea[q] * 6 + eb[q]];
+    }
+    double T4[16];
 #pragma unroll
-      for (int b = 0; b <= a; b++) sum[tri(a, b)] = sum[tri(a, b)] + info[a * 6 + b];
+    for (int i = 0; i < 3; i++) {
+      T4[i * 4 + 0] = G.DT[i * 3 + 0]; T4[i * 4 + 1] = G.DT[i * 3 + 1]; T4[i * 4 + 2] = G.DT[i * 3 + 2]; T4[i * 4 + 3] = G.DT[9 + i];
+    }
+    for (int k = 0; k < npt; k++) {  // getPoseInfoPoint (:1414-1447)
+      double c[3], uv[2], J[6];
+      se3_apply(T4, pts[k].P, c);
+      projection(cam, c, uv);
+      const double dx = uv[0] - pts[k].pl_obs[0], dy = uv[1] - pts[k].pl_obs[1];
+      jac6(cam.fx / fmax(cfg.homog_th, c[2] * c[2]), c[0], c[1], c[2], dx, dy, J);
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        double Ja = 0.0, Jb = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) { Ja = (ea[q] == i) ? J[i] : Ja; Jb = (eb[q] == i) ? J[i] : Jb; }
+        acc[q] = acc[q] + Ja * Jb;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 3; q++)
+      if (j + 8 * q < 21) G.sum[j + 8 * q] = acc[q];
   }
-  for (int k = 0; k < npt; k++) {  // getPoseInfoPoint (:1414-1447)
-    double c[3], uv[2], J[6];
-    se3_apply(DT_inv, pts[k].P, c);
-    projection(cam, c, uv);
-    const double dx = uv[0] - pts[k].pl_obs[0], dy = uv[1] - pts[k].pl_obs[1];
-    jac6(cam.fx / fmax(cfg.homog_th, c[2] * c[2]), c[0], c[1], c[2], dx, dy, J);
-#pragma unroll
-    for (int a = 0; a < 6; a++)
-#pragma unroll
-      for (int b = 0; b <= a; b++) sum[tri(a, b)] = sum[tri(a, b)] + J[a] * J[b];
-  }
+  __syncwarp(gmask);
 
   // pass 3: sequential greedy search per line (:1662-1763)
   for (int l = 0; l < nln; l++) {
-    LineData L;
-    load_line(lns[l], cov[lns[l].prev_idx], L);
     gfpl_line_cut& C = cut[l];
-    double metric_last = cut_metric(cfg, sum);
+    {  // stage the line into the group's shared memory
+      const gfpl_ln_obs& o = lns[l];
+      const gfpl_line_cov& c = cov[o.prev_idx];
+      for (int k = j; k < LD_SIZE; k += CUT_GROUP) {
+        double v;
+        if (k < 3) v = o.sP[k];
+        else if (k < 6) v = o.eP[k - 3];
+        else if (k < 8) v = o.le_obs[k - 6];
+        else if (k < 17) v = c.covS[k - 8];
+        else v = c.covE[k - 17];
+        G.L[k] = v;
+      }
+    }
+    __syncwarp(gmask);
+    double metric_last = cut_metric(cfg, G.sum);
+    __syncwarp(gmask);
     {
       const double* info = C.invCovPose;
-#pragma unroll
-      for (int a = 0; a < 6; a++)
-#pragma unroll
-        for (int b = 0; b <= a; b++) sum[tri(a, b)] = sum[tri(a, b)] - info[a * 6 + b];
+      for (int e = j; e < 21; e += CUT_GROUP) {
+        int a = 0;
+        while ((a + 1) * (a + 2) / 2 <= e) a++;
+        const int b = e - a * (a + 1) / 2;
+        G.sum[e] = G.sum[e] - info[a * 6 + b];
+      }
     }
+    __syncwarp(gmask);
     double cur0 = 0.0, cur1 = 0.0;
     while (cur0 + cur1 <= 1.0) {
       const double ct0 = cur0 + nb0, ct1 = cur1 + nb1;
@@ -209,12 +272,12 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
       double metric = 0.0;
       LineInfo I;
       if (valid) {
-        pose_info_on_line(cam, cfg, DT_inv, L, ct0, ct1, I);
+        pose_info_on_line(cam, cfg, G.DT, G.L, ct0, ct1, I);
         double M[21];
 #pragma unroll
         for (int a = 0; a < 6; a++)
 #pragma unroll
-          for (int b = 0; b <= a; b++) M[tri(a, b)] = info_entry(I, a, b) + sum[tri(a, b)];
+          for (int b = 0; b <= a; b++) M[tri(a, b)] = info_entry(I, a, b) + G.sum[tri(a, b)];
         metric = cut_metric(cfg, M);
       }
       // "first strictly better in j order" (:1722-1730)
@@ -242,10 +305,10 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
       C.spl[0] = C.spl[1] = C.epl[0] = C.epl[1] = 0.0;
       C.sdisp = 0.0; C.edisp = 0.0;
       if (!(fabs(cur0) < 0.0001 && fabs(cur1) < 0.0001)) {
-        double sP[3] = {L.sP[0], L.sP[1], L.sP[2]};
+        double sP[3] = {G.L[LD_SP], G.L[LD_SP + 1], G.L[LD_SP + 2]};
         if (fabs(cur0) > 0.0001) {
 #pragma unroll
-          for (int k = 0; k < 3; k++) sP[k] = (1 - cur0) * L.sP[k] + cur0 * L.eP[k];
+          for (int k = 0; k < 3; k++) sP[k] = (1 - cur0) * G.L[LD_SP + k] + cur0 * G.L[LD_EP + k];
 #pragma unroll
           for (int k = 0; k < 3; k++) lns[l].sP[k] = sP[k];
           projection(cam, sP, C.spl);
@@ -254,7 +317,7 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
         if (fabs(cur1) > 0.0001) {
           double eP[3];
 #pragma unroll
-          for (int k = 0; k < 3; k++) eP[k] = (1 - cur1) * L.eP[k] + cur1 * sP[k];  // reads the MOVED start point
+          for (int k = 0; k < 3; k++) eP[k] = (1 - cur1) * G.L[LD_EP + k] + cur1 * sP[k];  // reads the MOVED start point
 #pragma unroll
           for (int k = 0; k < 3; k++) lns[l].eP[k] = eP[k];
           projection(cam, eP, C.epl);
@@ -264,11 +327,14 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
     }
     {
       const double* info = C.invCovPose;
-#pragma unroll
-      for (int a = 0; a < 6; a++)
-#pragma unroll
-        for (int b = 0; b <= a; b++) sum[tri(a, b)] = sum[tri(a, b)] + info[a * 6 + b];
+      for (int e = j; e < 21; e += CUT_GROUP) {
+        int a = 0;
+        while ((a + 1) * (a + 2) / 2 <= e) a++;
+        const int b = e - a * (a + 1) / 2;
+        G.sum[e] = G.sum[e] + info[a * 6 + b];
+      }
     }
+    __syncwarp(gmask);
   }
 }
 

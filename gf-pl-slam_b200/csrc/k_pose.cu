@@ -17,6 +17,17 @@
 namespace gfpl {
 
 constexpr int POSE_WARPS = 4;
+#ifndef POSE_MIN_BLOCKS
+#define POSE_MIN_BLOCKS 4  // <= 128 registers: 16 warps / SM hide the fp64 and L1 latencies of the GN loop
+#endif
+
+// hand-off record between the GN kernel and the finalize kernel
+struct PoseRaw {
+  double DT[16];
+  double H[36];
+  double err;
+  int status, cov_from_H, n_inliers, n_inliers_pt, n_inliers_ls, iters_first, iters_ref, pad;
+};
 
 struct Acc {
   double v[28];  // [0,21) lower triangle of H, [21,27) g, [27] e
@@ -56,6 +67,97 @@ __device__ __forceinline__ double line_residual(const double* DT, const gfpl_ln_
   return sqrt(dse[0] * dse[0] + dse[1] * dse[1]);
 }
 
+
+// ---- LDLT<Matrix6d>(H).solve(g) in registers ------------------------------------------------------------
+// Same algorithm as Eigen's ldlt_inplace<Lower>::unblocked (largest |diagonal| pivot, left-looking update,
+// D^-1 with a zero-pivot guard) but fully unrolled: the runtime pivot index is applied with predicated
+// swaps, so nothing is indexed dynamically and nothing spills to local memory.
+__device__ __forceinline__ void swap_rc(double* A, int* perm, int k, int p, bool doit) {
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    const double a = A[k * 6 + j], b = A[p * 6 + j];
+    A[k * 6 + j] = doit ? b : a;
+    A[p * 6 + j] = doit ? a : b;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const double a = A[i * 6 + k], b = A[i * 6 + p];
+    A[i * 6 + k] = doit ? b : a;
+    A[i * 6 + p] = doit ? a : b;
+  }
+  const int pa = perm[k], pb = perm[p];
+  perm[k] = doit ? pb : pa;
+  perm[p] = doit ? pa : pb;
+}
+
+__device__ __forceinline__ void ldlt6_solve_reg(const double* Hin, const double* g, double* x) {
+  double A[36];
+  int perm[6];
+#pragma unroll
+  for (int i = 0; i < 36; i++) A[i] = Hin[i];
+#pragma unroll
+  for (int i = 0; i < 6; i++) perm[i] = i;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    int p = k;
+    double best = fabs(A[k * 6 + k]);
+#pragma unroll
+    for (int i = k + 1; i < 6; i++) {
+      const double v = fabs(A[i * 6 + i]);
+      if (v > best) { best = v; p = i; }
+    }
+#pragma unroll
+    for (int pp = k + 1; pp < 6; pp++) swap_rc(A, perm, k, pp, p == pp);
+    double temp[6];
+#pragma unroll
+    for (int j = 0; j < k; j++) temp[j] = A[j * 6 + j] * A[k * 6 + j];
+    if (k > 0) {
+      double dot = A[k * 6 + 0] * temp[0];
+#pragma unroll
+      for (int j = 1; j < k; j++) dot = dot + A[k * 6 + j] * temp[j];
+      A[k * 6 + k] = A[k * 6 + k] - dot;
+    }
+    const double d = A[k * 6 + k];
+#pragma unroll
+    for (int i = k + 1; i < 6; i++) {
+      double sv = A[i * 6 + k];
+      if (k > 0) {
+        double dot = A[i * 6 + 0] * temp[0];
+#pragma unroll
+        for (int j = 1; j < k; j++) dot = dot + A[i * 6 + j] * temp[j];
+        sv = sv - dot;
+      }
+      A[i * 6 + k] = (fabs(d) > 0.0) ? sv / d : sv;
+    }
+  }
+  double y[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    double v = 0.0;
+#pragma unroll
+    for (int j = 0; j < 6; j++) v = (perm[i] == j) ? g[j] : v;
+    y[i] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j < i; j++) y[i] = y[i] - A[i * 6 + j] * y[j];
+  const double tol = 1.0 / 1.7976931348623157e308;
+#pragma unroll
+  for (int i = 0; i < 6; i++) y[i] = (fabs(A[i * 6 + i]) > tol) ? y[i] / A[i * 6 + i] : 0.0;
+#pragma unroll
+  for (int i = 5; i >= 0; i--)
+#pragma unroll
+    for (int j = i + 1; j < 6; j++) y[i] = y[i] - A[j * 6 + i] * y[j];
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    double v = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) v = (perm[i] == j) ? y[i] : v;
+    x[j] = v;
+  }
+}
+
 struct PairObs {
   int npt, nln;
   const gfpl_pt_obs* pts;
@@ -65,7 +167,7 @@ struct PairObs {
 };
 
 // optimizeFunctions for one pair by one warp.  Returns H (full 6x6), g, e in every lane.
-__device__ void warp_optimize_functions(const double* DT, const PairObs& o, const gfpl_camera& cam,
+__device__ __forceinline__ void warp_optimize_functions(const double* DT, const PairObs& o, const gfpl_camera& cam,
                                         const gfpl_config& cfg, double* H, double* g, double* e) {
   const int lane = threadIdx.x & 31;
   Acc a;
@@ -117,7 +219,7 @@ __device__ void warp_optimize_functions(const double* DT, const PairObs& o, cons
 }
 
 // gaussNewtonOptimization (:2032-2056); H of the last evaluation is returned for DT_cov = H^-1
-__device__ int warp_gauss_newton(double* DT, const PairObs& o, const gfpl_camera& cam, const gfpl_config& cfg,
+__device__ __forceinline__ int warp_gauss_newton(double* DT, const PairObs& o, const gfpl_camera& cam, const gfpl_config& cfg,
                                  int max_iters, double* H, double* err_) {
   double g[6], inc[6];
   double err = 0.0, err_prev = 999999999.9;
@@ -126,7 +228,7 @@ __device__ int warp_gauss_newton(double* DT, const PairObs& o, const gfpl_camera
   for (; iters < max_iters; iters++) {
     warp_optimize_functions(DT, o, cam, cfg, H, g, &err);
     if ((fabs(err - err_prev) < cfg.min_error_change) || (err < cfg.min_error)) break;
-    ldlt6_solve(H, g, inc);
+    ldlt6_solve_reg(H, g, inc);
     double E[16], Ei[16];
     expmap_se3(inc, E);
     inverse_se3(E, Ei);
@@ -141,49 +243,39 @@ __device__ int warp_gauss_newton(double* DT, const PairObs& o, const gfpl_camera
   return iters;
 }
 
-// 1.4826 * MAD of res[0..n) exactly as vector_stdv_mad (auxiliar.cpp:521-537) computes it:
-// median = sorted[n/2]; a = (double)fabsf(res - median); MAD = sorted(a)[n/2].  Warp-cooperative rank selection.
-__device__ double warp_stdv_mad(const double* res, int n) {
-  if (n == 0) return 0.0;
+// element [rank] of the ascending sort of n non-negative doubles, without sorting: MSB-first binary search on
+// the IEEE bit patterns (monotone for x >= 0).  Every probe is one warp-wide count (REDUX.SUM).
+// `TRANSFORM` applies a = (double)fabsf((float)(x - median)) on the fly for the second pass.
+template <bool TRANSFORM>
+__device__ __forceinline__ double warp_select(const double* res, int n, int rank, double median) {
   const int lane = threadIdx.x & 31;
-  const int rank = n / 2;
-  double median = 0.0;
-  {
-    double found = 0.0;
-    bool have = false;
-    for (int j = lane; j < n; j += 32) {
-      const double x = res[j];
-      int r = 0;
-      for (int k = 0; k < n; k++) {
-        const double y = res[k];
-        r += (y < x) || (y == x && k < j);
-      }
-      if (r == rank) { found = x; have = true; }
+  unsigned long long prefix = 0ull;
+  for (int bit = 62; bit >= 0; bit--) {
+    const unsigned long long trial = prefix | (1ull << bit);
+    const double tv = __longlong_as_double((long long)trial);
+    int cnt = 0;
+    for (int k = lane; k < n; k += 32) {
+      double x = res[k];
+      if (TRANSFORM) x = (double)fabsf((float)(x - median));
+      cnt += (x < tv) ? 1 : 0;
     }
-    const unsigned who = __ballot_sync(0xffffffffu, have);
-    median = shfl_f64(0xffffffffu, found, who ? __ffs(who) - 1 : 0);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (cnt <= rank) prefix = trial;
   }
-  double mad = 0.0;
-  {
-    double found = 0.0;
-    bool have = false;
-    for (int j = lane; j < n; j += 32) {
-      const double x = (double)fabsf((float)(res[j] - median));
-      int r = 0;
-      for (int k = 0; k < n; k++) {
-        const double y = (double)fabsf((float)(res[k] - median));
-        r += (y < x) || (y == x && k < j);
-      }
-      if (r == rank) { found = x; have = true; }
-    }
-    const unsigned who = __ballot_sync(0xffffffffu, have);
-    mad = shfl_f64(0xffffffffu, found, who ? __ffs(who) - 1 : 0);
-  }
+  return __longlong_as_double((long long)prefix);
+}
+
+// 1.4826 * MAD of res[0..n) exactly as vector_stdv_mad (auxiliar.cpp:521-537) computes it:
+// median = sorted[n/2]; a = (double)fabsf(res - median) (float truncation); MAD = sorted(a)[n/2].
+__device__ __forceinline__ double warp_stdv_mad(const double* res, int n) {
+  if (n == 0) return 0.0;
+  const double median = warp_select<false>(res, n, n / 2, 0.0);
+  const double mad = warp_select<true>(res, n, n / 2, median);
   return 1.4826 * mad;
 }
 
 // removeOutliers (:2058-2116): returns the number of points / lines flagged
-__device__ void warp_remove_outliers(const double* DT, const PairObs& o, const gfpl_camera& cam,
+__device__ __forceinline__ void warp_remove_outliers(const double* DT, const PairObs& o, const gfpl_camera& cam,
                                      const gfpl_config& cfg, double* s_res, int* drop_pt, int* drop_ln) {
   const int lane = threadIdx.x & 31;
   double* res_p = s_res;
@@ -252,9 +344,9 @@ __device__ __noinline__ void unccomp_se3(const double* T1, const double* covT1, 
     }
 }
 
-__global__ void __launch_bounds__(POSE_WARPS * 32)
+__global__ void __launch_bounds__(POSE_WARPS * 32, POSE_MIN_BLOCKS)
 pose_optimize_kernel(DevTrackObs obs, const gfpl_frame_state* __restrict__ state, const double* __restrict__ DT_ini,
-                     int overload, gfpl_pose_result* __restrict__ out, gfpl_camera cam, gfpl_config cfg) {
+                     int overload, PoseRaw* __restrict__ raw, gfpl_camera cam, gfpl_config cfg) {
   extern __shared__ double s_res_all[];  // [POSE_WARPS][cap_pt + cap_ln]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p = blockIdx.x * POSE_WARPS + warp;
@@ -272,40 +364,71 @@ pose_optimize_kernel(DevTrackObs obs, const gfpl_frame_state* __restrict__ state
   for (int i = 0; i < 16; i++) DT[i] = seed[i];
   int n_inliers_pt = o.npt, n_inliers_ls = o.nln, n_inliers = o.npt + o.nln;
   int status = GFPL_POSE_OK, it1 = 0, it2 = 0;
-  bool cov_from_H = false, cov_prev = true;  // DT_cov starts as prev_frame->DT_cov (:1875,1950)
+  bool cov_from_H = false;  // DT_cov ends as H^-1 of the refinement or as zero (:1889-1906)
   if (n_inliers > cfg.min_features) {
-    double DT_[16];
+    // two GN stages share one inlined loop body: stage 0 = first estimate on a copy (5 iterations) followed by
+    // the MAD outlier pass, stage 1 = refinement restarting from the seed (D8) (10 iterations)
+    double DTw[16];
+    for (int stage = 0; stage < 2; stage++) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) DT_[i] = DT[i];
-    it1 = warp_gauss_newton(DT_, o, cam, cfg, cfg.max_iters, H, &err);
-    cov_prev = false;
-    if (is_finite16(DT_)) {
-      int dp, dl;
-      warp_remove_outliers(DT_, o, cam, cfg, s_res, &dp, &dl);
-      n_inliers_pt -= dp; n_inliers_ls -= dl; n_inliers -= dp + dl;
-      if (n_inliers > cfg.min_features) {
-        it2 = warp_gauss_newton(DT, o, cam, cfg, cfg.max_iters_ref, H, &err);  // D8: restarts from the seed
+      for (int i = 0; i < 16; i++) DTw[i] = DT[i];
+      const int iters = warp_gauss_newton(DTw, o, cam, cfg, stage == 0 ? cfg.max_iters : cfg.max_iters_ref, H, &err);
+      if (stage == 1) {
+        it2 = iters;
         cov_from_H = true;
-      } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) DT[i] = DTw[i];
+        break;
+      }
+      it1 = iters;
+      if (!is_finite16(DTw)) {
+        eye4(DT);
+        status |= GFPL_POSE_NONFINITE_1;
+        break;
+      }
+      int dp, dl;
+      warp_remove_outliers(DTw, o, cam, cfg, s_res, &dp, &dl);
+      n_inliers_pt -= dp; n_inliers_ls -= dl; n_inliers -= dp + dl;
+      if (!(n_inliers > cfg.min_features)) {
         eye4(DT);
         status |= GFPL_POSE_FEW_INLIERS;
+        break;
       }
-    } else {
-      eye4(DT);
-      status |= GFPL_POSE_NONFINITE_1;
     }
   } else {
     eye4(DT);
-    cov_prev = false;
     status |= GFPL_POSE_FEW_FEATURES;
   }
 
   if (lane != 0) return;
+  PoseRaw& w = raw[p];
+#pragma unroll
+  for (int i = 0; i < 16; i++) w.DT[i] = DT[i];
+#pragma unroll
+  for (int i = 0; i < 36; i++) w.H[i] = H[i];
+  w.err = err;
+  w.status = status; w.cov_from_H = cov_from_H ? 1 : 0;
+  w.n_inliers = n_inliers; w.n_inliers_pt = n_inliers_pt; w.n_inliers_ls = n_inliers_ls;
+  w.iters_first = it1; w.iters_ref = it2;
+}
+
+// serial tail of optimizePose (:1984-2028): DT_cov = H^-1, inverse_se3, motion-step gate, Tfw, eigenvalues of
+// DT_cov, unccomp_se3.  One THREAD per pair (the GN kernel spends a warp per pair; this part has no
+// parallelism inside a pair, so it runs 32 pairs per warp here).
+__global__ void __launch_bounds__(128)
+pose_finalize_kernel(int B, const PoseRaw* __restrict__ raw, const gfpl_frame_state* __restrict__ state, int overload,
+                     gfpl_pose_result* __restrict__ out, gfpl_config cfg) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= B) return;
+  const PoseRaw& w = raw[p];
+  const gfpl_frame_state& st = state[p];
   gfpl_pose_result& r = out[p];
-  double DT_cov[36];
-  if (cov_from_H) inverse6(H, DT_cov);
+  int status = w.status;
+  double DT[16], DT_cov[36];
+  for (int i = 0; i < 16; i++) DT[i] = w.DT[i];
+  if (w.cov_from_H) inverse6(w.H, DT_cov);
   else
-    for (int i = 0; i < 36; i++) DT_cov[i] = cov_prev ? st.DT_cov[i] : 0.0;
+    for (int i = 0; i < 36; i++) DT_cov[i] = 0.0;
   bool accept = false;
   double DTinv[16];
   if (is_finite16(DT)) {
@@ -327,26 +450,32 @@ pose_optimize_kernel(DevTrackObs obs, const gfpl_frame_state* __restrict__ state
     matmul<4, 4, 4>(st.Tfw, DTinv, Tfw);
     for (int i = 0; i < 16; i++) { r.DT[i] = DTinv[i]; r.Tfw[i] = Tfw[i]; }
     unccomp_se3(st.Tfw, st.Tfw_cov, DT_cov, r.Tfw_cov);
-    r.err_norm = err;
+    r.err_norm = w.err;
   } else {
     for (int i = 0; i < 16; i++) { r.DT[i] = (i % 5 == 0) ? 1.0 : 0.0; r.Tfw[i] = st.Tfw[i]; }
     for (int i = 0; i < 36; i++) r.Tfw_cov[i] = st.Tfw_cov[i];
     r.err_norm = -1.0;
   }
   r.status = status;
-  r.n_inliers = n_inliers; r.n_inliers_pt = n_inliers_pt; r.n_inliers_ls = n_inliers_ls;
-  r.iters_first = it1; r.iters_ref = it2;
+  r.n_inliers = w.n_inliers; r.n_inliers_pt = w.n_inliers_pt; r.n_inliers_ls = w.n_inliers_ls;
+  r.iters_first = w.iters_first; r.iters_ref = w.iters_ref;
 }
 
 int launch_pose_optimize(gfpl_ctx* ctx, DevTrackObs obs, const gfpl_frame_state* state, const double* DT_ini,
                          int overload, gfpl_pose_result* out) {
   if (obs.B <= 0) return GFPL_OK;
+  // the hand-off buffer lives in the (stream-ordered) default pool; it is tiny: 456 B per pair
+  PoseRaw* raw = nullptr;
+  GFPL_CUDA_OK(ctx, cudaMallocAsync((void**)&raw, (size_t)obs.B * sizeof(PoseRaw), ctx->stream));
   const size_t smem = (size_t)POSE_WARPS * (obs.cap_pt + obs.cap_ln) * sizeof(double);
   if (smem > 48 * 1024)
     GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(pose_optimize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (obs.B + POSE_WARPS - 1) / POSE_WARPS;
-  pose_optimize_kernel<<<grid, POSE_WARPS * 32, smem, ctx->stream>>>(obs, state, DT_ini, overload, out, ctx->cam, ctx->cfg);
+  pose_optimize_kernel<<<grid, POSE_WARPS * 32, smem, ctx->stream>>>(obs, state, DT_ini, overload, raw, ctx->cam, ctx->cfg);
   GFPL_LAUNCH_OK(ctx);
+  pose_finalize_kernel<<<(obs.B + 127) / 128, 128, 0, ctx->stream>>>(obs.B, raw, state, overload, out, ctx->cfg);
+  GFPL_LAUNCH_OK(ctx);
+  GFPL_CUDA_OK(ctx, cudaFreeAsync(raw, ctx->stream));
   return GFPL_OK;
 }
 
