@@ -1,0 +1,335 @@
+// mapHandler.cpp — PLSLAM::MapHandler local-BA facade over gfpl_lba_assemble (see mapHandler.hpp).
+#include "mapHandler.hpp"
+
+#include <cmath>
+#include <limits>
+
+namespace PLSLAM {
+
+// ---- SE(3) glue (auxiliar.cpp:154-214) --------------------------------------------------------------------
+Matrix4d inverse_se3(const Matrix4d& T) {
+  Matrix4d Ti = Matrix4d::Identity();
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) Ti(i, j) = T(j, i);
+    Ti(i, 3) = -(T(0, i) * T(0, 3) + T(1, i) * T(1, 3) + T(2, i) * T(2, 3));
+  }
+  return Ti;
+}
+
+static void skew(const double* v, double S[3][3]) {
+  S[0][0] = 0; S[0][1] = -v[2]; S[0][2] = v[1];
+  S[1][0] = v[2]; S[1][1] = 0; S[1][2] = -v[0];
+  S[2][0] = -v[1]; S[2][1] = v[0]; S[2][2] = 0;
+}
+
+Matrix4d expmap_se3(const Vector6d& x) {
+  double w[3] = {x(3), x(4), x(5)}, t[3] = {x(0), x(1), x(2)};
+  double R[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  const double theta = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  if (!(theta < 0.000001)) {
+    double s[3][3], ss[3][3], V[3][3];
+    skew(w, s);
+    for (auto& r : s) for (double& v : r) v /= theta;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { ss[i][j] = 0; for (int k = 0; k < 3; k++) ss[i][j] += s[i][k] * s[k][j]; }
+    const double sn = std::sin(theta), cs = std::cos(theta);
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        const double I = i == j ? 1.0 : 0.0;
+        R[i][j] = I + s[i][j] * sn + ss[i][j] * (1.0 - cs);
+        V[i][j] = I + s[i][j] * (1.0 - cs) / theta + ss[i][j] * (theta - sn) / theta;
+      }
+    double tn[3];
+    for (int i = 0; i < 3; i++) tn[i] = V[i][0] * t[0] + V[i][1] * t[1] + V[i][2] * t[2];
+    for (int i = 0; i < 3; i++) t[i] = tn[i];
+  }
+  Matrix4d T = Matrix4d::Identity();
+  for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) T(i, j) = R[i][j]; T(i, 3) = t[i]; }
+  return T;
+}
+
+static bool inv3(const double m[3][3], double o[3][3]) {
+  const double c00 = m[1][1] * m[2][2] - m[1][2] * m[2][1], c10 = m[1][2] * m[2][0] - m[1][0] * m[2][2],
+               c20 = m[1][0] * m[2][1] - m[1][1] * m[2][0];
+  const double det = m[0][0] * c00 + m[0][1] * c10 + m[0][2] * c20;
+  const double id = 1.0 / det;
+  o[0][0] = c00 * id; o[0][1] = (m[0][2] * m[2][1] - m[0][1] * m[2][2]) * id; o[0][2] = (m[0][1] * m[1][2] - m[0][2] * m[1][1]) * id;
+  o[1][0] = c10 * id; o[1][1] = (m[0][0] * m[2][2] - m[0][2] * m[2][0]) * id; o[1][2] = (m[0][2] * m[1][0] - m[0][0] * m[1][2]) * id;
+  o[2][0] = c20 * id; o[2][1] = (m[0][1] * m[2][0] - m[0][0] * m[2][1]) * id; o[2][2] = (m[0][0] * m[1][1] - m[0][1] * m[1][0]) * id;
+  return det != 0.0;
+}
+
+Vector6d logmap_se3(const Matrix4d& T) {
+  double w[3] = {0, 0, 0}, V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  double cosine = (T(0, 0) + T(1, 1) + T(2, 2) - 1.0) / 2.0;
+  cosine = std::fmin(1.0, std::fmax(-1.0, cosine));
+  double sine = std::sqrt(1.0 - cosine * cosine);
+  const double theta = std::acos(cosine);
+  if (theta > 0.000001) {
+    w[0] = theta * (T(2, 1) - T(1, 2)) / (2.0 * sine);
+    w[1] = theta * (T(0, 2) - T(2, 0)) / (2.0 * sine);
+    w[2] = theta * (T(1, 0) - T(0, 1)) / (2.0 * sine);
+    double s[3][3], ss[3][3];
+    skew(w, s);
+    for (auto& r : s) for (double& v : r) v /= theta;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { ss[i][j] = 0; for (int k = 0; k < 3; k++) ss[i][j] += s[i][k] * s[k][j]; }
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+        V[i][j] = (i == j ? 1.0 : 0.0) + s[i][j] * (1.0 - cosine) / theta + ss[i][j] * (theta - sine) / theta;
+  }
+  double Vi[3][3];
+  inv3(V, Vi);
+  Vector6d x;
+  for (int i = 0; i < 3; i++) x(i) = Vi[i][0] * T(0, 3) + Vi[i][1] * T(1, 3) + Vi[i][2] * T(2, 3);
+  x(3) = w[0]; x(4) = w[1]; x(5) = w[2];
+  return x;
+}
+
+// ---- small dense solver: Gaussian elimination with partial pivoting, n x n, in place ---------------------------
+static bool solve_dense(int n, vector<double>& A, vector<double>& B, int nrhs) {
+  bool ok = true;
+  for (int k = 0; k < n; k++) {
+    int p = k;
+    for (int i = k + 1; i < n; i++) if (std::fabs(A[(size_t)i * n + k]) > std::fabs(A[(size_t)p * n + k])) p = i;
+    if (A[(size_t)p * n + k] == 0.0) { ok = false; continue; }
+    if (p != k) {
+      for (int j = 0; j < n; j++) std::swap(A[(size_t)k * n + j], A[(size_t)p * n + j]);
+      for (int j = 0; j < nrhs; j++) std::swap(B[(size_t)k * nrhs + j], B[(size_t)p * nrhs + j]);
+    }
+    for (int i = k + 1; i < n; i++) {
+      const double f = A[(size_t)i * n + k] / A[(size_t)k * n + k];
+      if (f == 0.0) continue;
+      for (int j = k; j < n; j++) A[(size_t)i * n + j] -= f * A[(size_t)k * n + j];
+      for (int j = 0; j < nrhs; j++) B[(size_t)i * nrhs + j] -= f * B[(size_t)k * nrhs + j];
+    }
+  }
+  for (int i = n - 1; i >= 0; i--)
+    for (int j = 0; j < nrhs; j++) {
+      double s = B[(size_t)i * nrhs + j];
+      for (int k = i + 1; k < n; k++) s -= A[(size_t)i * n + k] * B[(size_t)k * nrhs + j];
+      B[(size_t)i * nrhs + j] = A[(size_t)i * n + i] != 0.0 ? s / A[(size_t)i * n + i] : 0.0;
+    }
+  return ok;
+}
+
+// ---- localBundleAdjustment: gather (mapHandler.cpp:1108-1215) ------------------------------------------------------
+void MapHandler::localBundleAdjustment() {
+  vector<double> X_aux;
+  vector<int> kf_list, pt_list, ls_list;
+  vector<Vector6i> pt_obs_list, ls_obs_list;
+  for (KeyFrame* kf : map_keyframes)
+    if (kf && kf->local && kf->kf_idx != 0) {
+      for (int i = 0; i < 6; i++) X_aux.push_back(kf->x_kf_w(i));
+      kf_list.push_back(kf->kf_idx);
+    }
+  auto local_kf = [&](int kf_map) {
+    for (size_t j = 0; j < kf_list.size(); j++) if (kf_list[j] == kf_map) return (int)j;
+    return -1;
+  };
+  int lm_local_idx = 0;
+  for (MapPoint* pt : map_points)
+    if (pt && pt->local) {
+      for (int i = 0; i < 3; i++) X_aux.push_back(pt->point3D(i));
+      for (size_t i = 0; i < pt->obs_list.size(); i++)
+        pt_obs_list.push_back(Vector6i{pt->idx, lm_local_idx, (int)i, pt->kf_obs_list[i], local_kf(pt->kf_obs_list[i]), 1});
+      lm_local_idx++;
+      pt_list.push_back(pt->idx);
+    }
+  lm_local_idx = 0;
+  for (MapLine* ls : map_lines)
+    if (ls && ls->local) {
+      for (int i = 0; i < 6; i++) X_aux.push_back(ls->line3D(i));
+      for (size_t i = 0; i < ls->obs_list.size(); i++)
+        ls_obs_list.push_back(Vector6i{ls->idx, lm_local_idx, (int)i, ls->kf_obs_list[i], local_kf(ls->kf_obs_list[i]), 1});
+      lm_local_idx++;
+      ls_list.push_back(ls->idx);
+    }
+  if (pt_obs_list.size() + ls_obs_list.size() != 0)
+    levMarquardtOptimizationLBA(X_aux, kf_list, pt_list, ls_list, pt_obs_list, ls_obs_list);
+}
+
+// ---- levMarquardtOptimizationLBA (mapHandler.cpp:1217-1712) --------------------------------------------------------
+void MapHandler::levMarquardtOptimizationLBA(vector<double> X_aux, vector<int> kf_list, vector<int> pt_list,
+                                             vector<int> ls_list, vector<Vector6i> pt_obs_list,
+                                             vector<Vector6i> ls_obs_list) {
+  const gfpl_config& cfg = gfpl->config();
+  const int Nkf = (int)kf_list.size(), N = (int)X_aux.size();
+  const int Npt = pt_obs_list.empty() ? 0 : pt_obs_list.back()[1] + 1;   // :1241-1242
+  const int Nls = ls_obs_list.empty() ? 0 : ls_obs_list.back()[1] + 1;   // :1320-1321
+  const int npo = (int)pt_obs_list.size(), nlo = (int)ls_obs_list.size();
+  vector<double> X = X_aux, DX(N, 0.0);
+
+  // flat, pass-independent observation arrays
+  vector<int32_t> pt_lm(npo), pt_kf(npo), pt_fix(npo), ls_lm(nlo), ls_kf(nlo), ls_fix(nlo);
+  vector<double> pt_uv(2 * (size_t)npo), pt_s2(npo), ls_le(3 * (size_t)nlo), ls_s2(nlo), fix_T;
+  vector<int> fix_ids;
+  auto fix_slot = [&](int kf_map) {
+    for (size_t i = 0; i < fix_ids.size(); i++) if (fix_ids[i] == kf_map) return (int)i;
+    fix_ids.push_back(kf_map);
+    double T[16];
+    map_keyframes[kf_map]->T_kf_w.to_row_major(T);
+    fix_T.insert(fix_T.end(), T, T + 16);
+    return (int)fix_ids.size() - 1;
+  };
+  for (int o = 0; o < npo; o++) {
+    const Vector6i& ob = pt_obs_list[o];
+    const MapPoint* mp = map_points[ob[0]];
+    pt_lm[o] = ob[1]; pt_kf[o] = ob[4]; pt_fix[o] = ob[4] < 0 ? fix_slot(ob[3]) : 0;
+    pt_uv[2 * o] = mp->obs_list[ob[2]](0); pt_uv[2 * o + 1] = mp->obs_list[ob[2]](1);
+    pt_s2[o] = mp->sigma_list[ob[2]];
+  }
+  for (int o = 0; o < nlo; o++) {
+    const Vector6i& ob = ls_obs_list[o];
+    const MapLine* ml = map_lines[ob[0]];
+    ls_lm[o] = ob[1]; ls_kf[o] = ob[4]; ls_fix[o] = ob[4] < 0 ? fix_slot(ob[3]) : 0;
+    for (int i = 0; i < 3; i++) ls_le[3 * o + i] = ml->obs_list[ob[2]](i);
+    ls_s2[o] = ml->sigma_list[ob[2]];
+  }
+  if (fix_T.empty()) fix_T.assign(16, 0.0);
+  // quirk (i) of SURVEY.md §8a L2: line landmarks are always linearised at the MAP values (:1555-1558)
+  vector<double> X_ls_map(6 * (size_t)std::max(Nls, 1), 0.0);
+  for (int j = 0; j < Nls; j++)
+    for (int i = 0; i < 6; i++) X_ls_map[6 * j + i] = map_lines[ls_list[j]]->line3D(i);
+
+  vector<double> kf_T(16 * (size_t)std::max(Nkf, 1)), X_pt(3 * (size_t)std::max(Npt, 1));
+  vector<double> Hkk(36 * (size_t)std::max(Nkf, 1)), Hpp(9 * (size_t)std::max(Npt, 1)), Hll(36 * (size_t)std::max(Nls, 1));
+  vector<double> Hpk(18 * (size_t)std::max(npo, 1)), Hlk(36 * (size_t)std::max(nlo, 1)), g(std::max(N, 1));
+  double err_sum = 0.0;
+
+  auto assemble = [&](bool first_pass) {
+    for (int k = 0; k < Nkf; k++) {
+      Matrix4d T;
+      if (first_pass) T = map_keyframes[kf_list[k]]->T_kf_w;   // :1255
+      else { Vector6d x; for (int i = 0; i < 6; i++) x(i) = X[6 * k + i]; T = expmap_se3(x); }   // :1480
+      T.to_row_major(&kf_T[16 * (size_t)k]);
+    }
+    for (int j = 0; j < Npt; j++)
+      for (int i = 0; i < 3; i++)
+        X_pt[3 * j + i] = first_pass ? map_points[pt_list[j]]->point3D(i) : X[6 * Nkf + 3 * j + i];   // :1253 / :1476
+    gfpl_lba_problem pb{Nkf, Npt, Nls, npo, nlo, kf_T.data(), X_pt.data(), X_ls_map.data(), pt_lm.data(), pt_kf.data(),
+                        pt_fix.data(), pt_uv.data(), pt_s2.data(), ls_lm.data(), ls_kf.data(), ls_fix.data(), ls_le.data(),
+                        ls_s2.data(), fix_T.data(), (int32_t)fix_ids.size()};
+    gfpl_lba_blocks out{Hkk.data(), Hpp.data(), Hll.data(), Hpk.data(), Hlk.data(), g.data(), &err_sum};
+    gfpl->check(gfpl_lba_assemble(gfpl->get(), &pb, &out));
+  };
+
+  // damped solve: (H + lambda*diag(H)) DX = g through the Schur complement of the landmark blocks
+  auto solve = [&](double lambda) {
+    const int nk = 6 * Nkf;
+    vector<double> S((size_t)nk * nk, 0.0), rhs(std::max(nk, 1), 0.0);
+    for (int k = 0; k < Nkf; k++)
+      for (int i = 0; i < 6; i++) {
+        for (int j = 0; j < 6; j++) S[(size_t)(6 * k + i) * nk + 6 * k + j] = Hkk[36 * (size_t)k + i * 6 + j];
+        S[(size_t)(6 * k + i) * nk + 6 * k + i] += lambda * Hkk[36 * (size_t)k + i * 7];
+        rhs[6 * k + i] = g[6 * k + i];
+      }
+    // per landmark: D^-1 [B | g_j], where B = sum of that landmark's off-diagonal blocks, one per observing local KF
+    struct Lm { int dim; vector<double> Dinv_B; vector<double> Dinv_g; vector<int> kfs; vector<double> B; };
+    vector<Lm> lms(Npt + Nls);
+    auto add_obs = [&](int lm_global, int dim, int kf, const double* blk) {
+      Lm& L = lms[lm_global];
+      L.dim = dim;
+      size_t s = 0;
+      for (; s < L.kfs.size(); s++) if (L.kfs[s] == kf) break;
+      if (s == L.kfs.size()) { L.kfs.push_back(kf); L.B.resize(L.B.size() + (size_t)dim * 6, 0.0); }
+      for (int i = 0; i < dim * 6; i++) L.B[s * dim * 6 + i] += blk[i];
+    };
+    for (int o = 0; o < npo; o++) if (pt_kf[o] >= 0) add_obs(pt_lm[o], 3, pt_kf[o], &Hpk[18 * (size_t)o]);
+    for (int o = 0; o < nlo; o++) if (ls_kf[o] >= 0) add_obs(Npt + ls_lm[o], 6, ls_kf[o], &Hlk[36 * (size_t)o]);
+    for (int j = 0; j < Npt + Nls; j++) {
+      Lm& L = lms[j];
+      const bool is_pt = j < Npt;
+      const int dim = is_pt ? 3 : 6;
+      L.dim = dim;
+      const double* D = is_pt ? &Hpp[9 * (size_t)j] : &Hll[36 * (size_t)(j - Npt)];
+      const double* gj = &g[6 * Nkf + (is_pt ? 3 * j : 3 * Npt + 6 * (j - Npt))];
+      const int nrhs = 6 * (int)L.kfs.size() + 1;
+      vector<double> A((size_t)dim * dim), R((size_t)dim * nrhs);
+      for (int i = 0; i < dim; i++) {
+        for (int c = 0; c < dim; c++) A[(size_t)i * dim + c] = D[i * dim + c] + (i == c ? lambda * D[i * dim + c] : 0.0);
+        for (size_t s = 0; s < L.kfs.size(); s++)
+          for (int c = 0; c < 6; c++) R[(size_t)i * nrhs + 6 * s + c] = L.B[s * dim * 6 + i * 6 + c];
+        R[(size_t)i * nrhs + nrhs - 1] = gj[i];
+      }
+      solve_dense(dim, A, R, nrhs);
+      L.Dinv_B.assign(R.begin(), R.end());   // [dim][nrhs]: D^-1 B (per KF) | D^-1 g_j
+      // S -= B^T D^-1 B ; rhs -= B^T D^-1 g_j
+      for (size_t a = 0; a < L.kfs.size(); a++)
+        for (int r = 0; r < 6; r++) {
+          double acc = 0.0;
+          for (int i = 0; i < dim; i++) acc += L.B[a * dim * 6 + i * 6 + r] * R[(size_t)i * nrhs + nrhs - 1];
+          rhs[6 * L.kfs[a] + r] -= acc;
+          for (size_t b = 0; b < L.kfs.size(); b++)
+            for (int c = 0; c < 6; c++) {
+              double v = 0.0;
+              for (int i = 0; i < dim; i++) v += L.B[a * dim * 6 + i * 6 + r] * R[(size_t)i * nrhs + 6 * b + c];
+              S[(size_t)(6 * L.kfs[a] + r) * nk + 6 * L.kfs[b] + c] -= v;
+            }
+        }
+    }
+    if (nk > 0) solve_dense(nk, S, rhs, 1);
+    for (int i = 0; i < nk; i++) DX[i] = rhs[i];
+    for (int j = 0; j < Npt + Nls; j++) {
+      const Lm& L = lms[j];
+      const int dim = L.dim, nrhs = 6 * (int)L.kfs.size() + 1;
+      const int off = 6 * Nkf + (j < Npt ? 3 * j : 3 * Npt + 6 * (j - Npt));
+      for (int i = 0; i < dim; i++) {
+        double v = L.Dinv_B[(size_t)i * nrhs + nrhs - 1];
+        for (size_t s = 0; s < L.kfs.size(); s++)
+          for (int c = 0; c < 6; c++) v -= L.Dinv_B[(size_t)i * nrhs + 6 * s + c] * DX[6 * L.kfs[s] + c];
+        DX[off + i] = v;
+      }
+    }
+  };
+
+  auto update = [&]() {  // :1443-1451
+    for (int i = 0; i < Nkf; i++) {
+      Vector6d x, dx;
+      for (int k = 0; k < 6; k++) { x(k) = X[6 * i + k]; dx(k) = DX[6 * i + k]; }
+      const Matrix4d Tcurr = expmap_se3(x) * inverse_se3(expmap_se3(dx));
+      const Vector6d xn = logmap_se3(Tcurr);
+      for (int k = 0; k < 6; k++) X[6 * i + k] = xn(k);
+    }
+    for (int i = 6 * Nkf; i < N; i++) X[i] += DX[i];
+  };
+
+  double err, err_prev;
+  double lambda = cfg.lambda_lba_lm;
+  const double lambda_k = cfg.lambda_lba_k;
+  const double eps = std::numeric_limits<double>::epsilon();
+  assemble(true);
+  err = err_sum / 0.0;                       // quirk (ii): Npt_obs + Nls_obs are never incremented (:1427)
+  int Hmax = 0;                              // quirk (iii): int (:1429-1435)
+  auto diag_scan = [&](double h) { if (h > Hmax || h < -Hmax) Hmax = (int)std::fabs(h); };
+  for (int k = 0; k < Nkf; k++) for (int i = 0; i < 6; i++) diag_scan(Hkk[36 * (size_t)k + i * 7]);
+  for (int j = 0; j < Npt; j++) for (int i = 0; i < 3; i++) diag_scan(Hpp[9 * (size_t)j + i * 4]);
+  for (int j = 0; j < Nls; j++) for (int i = 0; i < 6; i++) diag_scan(Hll[36 * (size_t)j + i * 7]);
+  lambda *= Hmax;
+  solve(lambda);
+  update();
+  err_prev = err;
+  int iters;
+  for (iters = 1; iters < cfg.max_iters_lba; iters++) {
+    assemble(false);
+    err = err_sum / (Npt + Nls);             // :1650
+    if (std::fabs(err - err_prev) < eps || err < eps) break;
+    solve(lambda);
+    if (err > err_prev) lambda /= lambda_k;
+    else { lambda *= lambda_k; update(); }
+    double n2 = 0.0;
+    for (double v : DX) n2 += v * v;
+    if (std::sqrt(n2) < eps) break;
+    err_prev = err;
+  }
+  lba_iterations = iters;
+  lba_last_err = err;
+  // write back (:1691-1712); x_kf_w is NOT refreshed (quirk vi)
+  for (int i = 0; i < Nkf; i++) {
+    Vector6d x;
+    for (int k = 0; k < 6; k++) x(k) = X[6 * i + k];
+    map_keyframes[kf_list[i]]->T_kf_w = expmap_se3(x);
+  }
+  for (int i = 0; i < Npt; i++) for (int k = 0; k < 3; k++) map_points[pt_list[i]]->point3D(k) = X[6 * Nkf + 3 * i + k];
+  for (int i = 0; i < Nls; i++) for (int k = 0; k < 6; k++) map_lines[ls_list[i]]->line3D(k) = X[6 * Nkf + 3 * Npt + 6 * i + k];
+}
+
+}  // namespace PLSLAM

@@ -271,7 +271,7 @@ def make_lba_window(seed=0, shape="kitti", n_kf=10, n_pt=1000, n_ls=300, pt_obs_
                 else:
                     kf.append(-1); fix.append(k - n_kf)
                 obs.append(k)
-        return np.array(lm, np.int32), np.array(kf, np.int32), np.array(fix, np.int32), np.array(obs)
+        return np.array(lm, np.int32), np.array(kf, np.int32), np.array(fix, np.int32), np.array(obs, np.int64)
 
     X_pt = world_pts(n_pt)
     lm, kf, fix, k_all = observe(X_pt, pt_obs_per)
