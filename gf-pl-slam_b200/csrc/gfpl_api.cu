@@ -615,8 +615,14 @@ int gfpl_track(gfpl_ctx* ctx, const gfpl_stereo_frames* prev, const gfpl_frame_s
 
 // ---- resident replay ---------------------------------------------------------------------------------------
 int gfpl_replay_create(gfpl_ctx* ctx, int32_t B, int32_t cap_pt, int32_t cap_ln, gfpl_replay** out) {
+  return gfpl_replay_create_ex(ctx, B, cap_pt, cap_ln, cap_pt, cap_ln, out);
+}
+
+int gfpl_replay_create_ex(gfpl_ctx* ctx, int32_t B, int32_t cap_pt, int32_t cap_ln, int32_t prev_cap_pt,
+                          int32_t prev_cap_ln, gfpl_replay** out) {
   if (!ctx || !out) return GFPL_E_INVALID;
-  REQUIRE(ctx, B > 0 && cap_pt > 0 && cap_ln > 0);
+  REQUIRE(ctx, B > 0 && cap_pt > 0 && cap_ln > 0 && prev_cap_pt > 0 && prev_cap_ln > 0);
+  REQUIRE(ctx, prev_cap_pt <= cap_pt && prev_cap_ln <= cap_ln);
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   gfpl_replay* rp = new (std::nothrow) gfpl_replay();
   if (!rp) return GFPL_E_NOMEM;
@@ -632,10 +638,12 @@ int gfpl_replay_create(gfpl_ctx* ctx, int32_t B, int32_t cap_pt, int32_t cap_ln,
   r.ln_l = rp->alloc<gfpl_keyline>(nl); r.ln_r = rp->alloc<gfpl_keyline>(nl);
   r.ldesc_l = rp->alloc<uint8_t>(nl * 32); r.ldesc_r = rp->alloc<uint8_t>(nl * 32);
   for (DevStereoFrames* f : {&rp->prev, &rp->curr}) {
-    f->B = B; f->cap_pt = cap_pt; f->cap_ln = cap_ln;
+    const bool is_prev = f == &rp->prev;
+    f->B = B; f->cap_pt = is_prev ? prev_cap_pt : cap_pt; f->cap_ln = is_prev ? prev_cap_ln : cap_ln;
+    const size_t fp = (size_t)B * f->cap_pt, fl = (size_t)B * f->cap_ln;
     f->n_pt = rp->alloc<int32_t>(B); f->n_ln = rp->alloc<int32_t>(B);
-    f->pt = rp->alloc<gfpl_point_feature>(np); f->pdesc = rp->alloc<uint8_t>(np * 32);
-    f->ln = rp->alloc<gfpl_line_feature>(nl); f->ldesc = rp->alloc<uint8_t>(nl * 32);
+    f->pt = rp->alloc<gfpl_point_feature>(fp); f->pdesc = rp->alloc<uint8_t>(fp * 32);
+    f->ln = rp->alloc<gfpl_line_feature>(fl); f->ldesc = rp->alloc<uint8_t>(fl * 32);
   }
   DevTrackObs& o = rp->obs;
   o.B = B; o.cap_pt = ocp; o.cap_ln = ocl;
@@ -693,7 +701,8 @@ int gfpl_replay_upload(gfpl_replay* rp, const gfpl_stereo_frames* prev, const gf
   gfpl_ctx* ctx = rp->ctx;
   REQUIRE(ctx, prev && state && raw);
   REQUIRE(ctx, prev->B == rp->B && raw->B == rp->B);
-  REQUIRE(ctx, prev->cap_pt == rp->cap_pt && prev->cap_ln == rp->cap_ln && raw->cap_pt == rp->cap_pt && raw->cap_ln == rp->cap_ln);
+  REQUIRE(ctx, prev->cap_pt == rp->prev.cap_pt && prev->cap_ln == rp->prev.cap_ln);
+  REQUIRE(ctx, raw->cap_pt == rp->cap_pt && raw->cap_ln == rp->cap_ln);
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   rp->h2d = 0;
   size_t B = rp->B, np = B * rp->cap_pt, nl = B * rp->cap_ln;
@@ -703,9 +712,10 @@ int gfpl_replay_upload(gfpl_replay* rp, const gfpl_stereo_frames* prev, const gf
   H2D(rp->raw.pdesc_l, raw->pdesc_l, np * 32); H2D(rp->raw.pdesc_r, raw->pdesc_r, np * 32);
   H2D(rp->raw.ln_l, raw->ln_l, nl); H2D(rp->raw.ln_r, raw->ln_r, nl);
   H2D(rp->raw.ldesc_l, raw->ldesc_l, nl * 32); H2D(rp->raw.ldesc_r, raw->ldesc_r, nl * 32);
+  const size_t pp = B * rp->prev.cap_pt, pl = B * rp->prev.cap_ln;
   H2D(rp->prev.n_pt, prev->n_pt, B); H2D(rp->prev.n_ln, prev->n_ln, B);
-  H2D(rp->prev.pt, prev->pt, np); H2D(rp->prev.pdesc, prev->pdesc, np * 32);
-  H2D(rp->prev.ln, prev->ln, nl); H2D(rp->prev.ldesc, prev->ldesc, nl * 32);
+  H2D(rp->prev.pt, prev->pt, pp); H2D(rp->prev.pdesc, prev->pdesc, pp * 32);
+  H2D(rp->prev.ln, prev->ln, pl); H2D(rp->prev.ldesc, prev->ldesc, pl * 32);
   H2D(rp->state, state, B);
   return GFPL_OK;
 }

@@ -185,6 +185,17 @@ class StereoFramesNP:
             setattr(out, k, getattr(self, k).copy())
         return out
 
+    def repack(self, cap_pt=None, cap_ln=None, pinned=False):
+        """same frames with tighter row strides (default: the largest count in the batch)"""
+        cap_pt = cap_pt or max(int(self.n_pt.max()), 1)
+        cap_ln = cap_ln or max(int(self.n_ln.max()), 1)
+        assert cap_pt >= self.n_pt.max() and cap_ln >= self.n_ln.max()
+        out = StereoFramesNP(self.B, cap_pt, cap_ln, pinned)
+        out.n_pt[:], out.n_ln[:] = self.n_pt, self.n_ln
+        out.pt[:], out.pdesc[:] = self.pt[:, :cap_pt], self.pdesc[:, :cap_pt]
+        out.ln[:], out.ldesc[:] = self.ln[:, :cap_ln], self.ldesc[:, :cap_ln]
+        return out
+
 
 class TrackObsNP:
     """matched_pt / matched_ls of B frame pairs as observation lists + inlier masks."""

@@ -232,10 +232,11 @@ class Context:
 class Replay:
     """gfpl_replay: device-resident batch of B frame pairs (upload once / run many / download)."""
 
-    def __init__(self, ctx, B, cap_pt, cap_ln):
+    def __init__(self, ctx, B, cap_pt, cap_ln, prev_cap_pt=None, prev_cap_ln=None):
         self.ctx, self.B, self.cap_pt, self.cap_ln = ctx, B, cap_pt, cap_ln
         self._h = C.c_void_p()
-        ctx._check(lib().gfpl_replay_create(ctx._h, B, cap_pt, cap_ln, C.byref(self._h)))
+        ctx._check(lib().gfpl_replay_create_ex(ctx._h, B, cap_pt, cap_ln, prev_cap_pt or cap_pt, prev_cap_ln or cap_ln,
+                                               C.byref(self._h)))
 
     def close(self):
         if self._h:

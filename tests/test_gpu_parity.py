@@ -383,3 +383,21 @@ def test_lba_assemble(ctx, orc):
 def test_measure_peaks(ctx):
     popc, fp64 = ctx.measure_peaks()
     assert 1.0 < popc < 10.0 and 5.0 < fp64 < 100.0
+
+
+def test_replay_with_packed_previous_frames(ctx, orc):
+    """tighter row strides for the previous frames (gfpl_replay_create_ex) do not change any result"""
+    from gfpl import api
+    d = _data(32, 1100, ragged=True)
+    flags = S.TRACK_LINECUT | S.TRACK_SEED_GIVEN
+    prev = orc.stereo_match(d["cam"], ctx.cfg, d["prev_raw"])
+    _, _, _, pg = ctx.track(prev, d["state"], d["curr_raw"], flags)
+    packed = prev.repack()
+    assert packed.cap_pt < prev.cap_pt and packed.cap_ln < prev.cap_ln
+    rp = api.Replay(ctx, 32, d["curr_raw"].cap_pt, d["curr_raw"].cap_ln, packed.cap_pt, packed.cap_ln)
+    rp.upload(packed, d["state"], d["curr_raw"])
+    rp.run(flags)
+    pose = np.zeros(32, S.pose_result_dt)
+    rp.download(pose)
+    ctx.sync()
+    assert pose.tobytes() == pg.tobytes()
