@@ -334,6 +334,12 @@ int gfpl_radius_hamming256(gfpl_ctx* ctx, const uint8_t* q, int32_t nq, const ui
   return finish(ctx);
 }
 
+int gfpl_measure_alu_peak(gfpl_ctx* ctx, double* lop3_tops) {
+  if (!ctx || !lop3_tops) return GFPL_E_INVALID;
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  return launch_measure_alu_peak(ctx, lop3_tops);
+}
+
 int gfpl_measure_peaks(gfpl_ctx* ctx, double* popc_tops, double* fp64_tflops) {
   if (!ctx || !popc_tops || !fp64_tflops) return GFPL_E_INVALID;
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));

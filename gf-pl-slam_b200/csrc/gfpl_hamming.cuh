@@ -4,8 +4,8 @@
 // Descriptor rows are 32 B = two 128-bit words.  A query row lives in 8 registers; train rows are
 // staged in shared memory with 1-D bulk TMA (cp.async.bulk.shared::cluster.global + mbarrier
 // complete_tx) and read back with two broadcast LDS.128 per row (all lanes of a warp read the same
-// address -> one wavefront, no bank conflict).  The distance is 8 x (LOP3 xor, POPC) + IADD3 tree:
-// the POPC pipe is the roofline of these kernels, not HBM and not the tensor cores.
+// address -> one wavefront, no bank conflict).  The distance is 8 x LOP3 xor, a 3-CSA carry-save compression
+// and 5 POPC: the POPC pipe (16 lanes/clk/SM) is the roofline of these kernels, not HBM and not the tensor cores.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,6 +27,17 @@ __device__ __forceinline__ Desc256 load_desc_global(const uint8_t* row) {
   return d;
 }
 
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
 // NORM_HAMMING: popcount of the xor.  NORM_HAMMING2: number of non-zero aligned 2-bit groups.
 template <int NORM>
 __device__ __forceinline__ uint32_t hamming256(const Desc256& q, const uint4& a, const uint4& b) {
@@ -38,7 +49,17 @@ __device__ __forceinline__ uint32_t hamming256(const Desc256& q, const uint4& a,
     x4 = (x4 | (x4 >> 1)) & 0x55555555u; x5 = (x5 | (x5 >> 1)) & 0x55555555u;
     x6 = (x6 | (x6 >> 1)) & 0x55555555u; x7 = (x7 | (x7 >> 1)) & 0x55555555u;
   }
-  return (__popc(x0) + __popc(x1) + __popc(x2)) + (__popc(x3) + __popc(x4) + __popc(x5)) + (__popc(x6) + __popc(x7));
+  if (NORM == GFPL_NORM_HAMMING2)  // already ALU-pipe bound (8 xor + 16 fold ops): plain 8 popcounts
+    return (__popc(x0) + __popc(x1) + __popc(x2)) + (__popc(x3) + __popc(x4) + __popc(x5)) + (__popc(x6) + __popc(x7));
+  // Carry-save compression (exact): popc(a) + popc(b) + popc(c) = popc(a^b^c) + 2*popc(maj(a,b,c)).  Three CSAs
+  // (6 LOP3 on the ALU pipe, which has slack) turn the 8 popcounts into 5, so the 16-lane POPC pipe — the roofline
+  // of the naive loop — does 5/8 of the work: ~40 POPC-pipe cycles and ~40 ALU-pipe cycles per warp-row, balanced.
+  // (explicit lop3 so that the 8 xors stay materialised: 8 + 6 LOP3 per pair; left to itself the compiler
+  //  re-associates the xors into the adders and ends up with ~21)
+  const uint32_t s0 = lop3_xor3(x0, x1, x2), c0 = lop3_maj(x0, x1, x2);
+  const uint32_t s1 = lop3_xor3(x3, x4, x5), c1 = lop3_maj(x3, x4, x5);
+  const uint32_t s2 = lop3_xor3(s0, s1, x6), c2 = lop3_maj(s0, s1, x6);
+  return (__popc(s2) + __popc(x7)) + 2u * (__popc(c0) + __popc(c1) + __popc(c2));
 }
 
 // (distance, trainIdx) packed so that unsigned order == (distance asc, trainIdx asc): the tie rule of

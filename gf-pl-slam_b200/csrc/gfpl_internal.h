@@ -102,5 +102,6 @@ int launch_pose_optimize(gfpl_ctx* ctx, DevTrackObs obs, const gfpl_frame_state*
 int launch_lba_assemble(gfpl_ctx* ctx, const gfpl_lba_problem& dprob, gfpl_lba_blocks dout);
 
 int launch_measure_peaks(gfpl_ctx* ctx, double* popc_tops, double* fp64_tflops);
+int launch_measure_alu_peak(gfpl_ctx* ctx, double* lop3_tops);
 
 }  // namespace gfpl

@@ -46,6 +46,15 @@ __device__ __forceinline__ void stage_projections(const DevStereoFrames& prev, c
   __syncthreads();
 }
 
+// rare path of the hybrid search (a previous descriptor within the radius): the 10 px projection gate of
+// stereoFrameHandler.cpp:534-538.  Out of line so that its fp64 registers are not live in the POPC loop.
+__device__ __noinline__ uint32_t f2f_gate(uint32_t best, uint32_t key, double2 pr, double plx, double ply, double window) {
+  const double dx = pr.x - plx, dy = pr.y - ply;
+  return (!(sqrt(dx * dx + dy * dy) > window)) ? min(best, key) : best;
+}
+
+constexpr int F2F_QPT = 2;  // current points per thread: halves the LDS traffic and the per-CTA projection prologue
+
 __global__ void __launch_bounds__(F2F_THREADS, 6)
 f2f_hybrid_points_kernel(DevStereoFrames prev, DevStereoFrames curr, const gfpl_frame_state* __restrict__ state,
                          uint32_t* __restrict__ best_key, gfpl_camera cam, gfpl_config cfg) {
@@ -57,19 +66,35 @@ f2f_hybrid_points_kernel(DevStereoFrames prev, DevStereoFrames curr, const gfpl_
 
   const int p = blockIdx.y;
   const int n_prev = prev.n_pt[p], n_curr = curr.n_pt[p];
-  const int t0 = blockIdx.x * blockDim.x;
+  const int t0 = blockIdx.x * (blockDim.x * F2F_QPT);
   if (t0 >= n_curr) return;
-  const int t = t0 + threadIdx.x;
   const bool active = cfg.has_points && n_prev > 0;
 
-  uint32_t best = KEY_NONE;
+  uint32_t best[F2F_QPT];
+  int tq[F2F_QPT];
+#pragma unroll
+  for (int k = 0; k < F2F_QPT; k++) { best[k] = KEY_NONE; tq[k] = t0 + k * blockDim.x + threadIdx.x; }
   if (active) {
     stage_projections(prev, state, p, n_prev, cam, s_T, s_proj);
-    const int tq = min(t, n_curr - 1);
-    const Desc256 qd = load_desc_global(curr.pdesc + ((size_t)p * curr.cap_pt + tq) * 32);
-    const gfpl_point_feature& cf = curr.pt[(size_t)p * curr.cap_pt + tq];
-    const double plx = cf.pl[0], ply = cf.pl[1];
+    Desc256 qd[F2F_QPT];
+    double plx[F2F_QPT], ply[F2F_QPT];
+#pragma unroll
+    for (int k = 0; k < F2F_QPT; k++) {
+      const int t = min(tq[k], n_curr - 1);
+      qd[k] = load_desc_global(curr.pdesc + ((size_t)p * curr.cap_pt + t) * 32);
+      const gfpl_point_feature& cf = curr.pt[(size_t)p * curr.cap_pt + t];
+      plx[k] = cf.pl[0]; ply[k] = cf.pl[1];
+    }
+    // integer form of `(float)d <= radius` (radiusMatch is inclusive): d <= floor(radius)
     const float radius = (float)cfg.point_match_radius;
+    const int rint = radius >= 0.f ? (int)floorf(fminf(radius, 1024.f)) : -1;
+    const double window = cfg.f2f_point_window;
+    // Hot loop is branch-free: count the previous rows within the radius and keep the smallest key among them.
+    // Candidates are rare (non-matching descriptors sit at ~128 +- 8 bits, the radius is 50), so the projection
+    // gate runs after the loop: one candidate -> gate it; several -> exact rescan of this query (rare path).
+    uint32_t cnt[F2F_QPT];
+#pragma unroll
+    for (int k = 0; k < F2F_QPT; k++) cnt[k] = 0;
     TrainPipe<F2F_TILE_ROWS> pipe;
     pipe.init(s_train, s_bar, prev.pdesc + (size_t)p * prev.cap_pt * 32, n_prev);
     for (int tile = 0; tile < pipe.ntiles; tile++) {
@@ -78,17 +103,36 @@ f2f_hybrid_points_kernel(DevStereoFrames prev, DevStereoFrames curr, const gfpl_
       const int q0 = tile * F2F_TILE_ROWS;
 #pragma unroll 4
       for (int r = 0; r < n; r++) {
-        const uint32_t d = hamming256<GFPL_NORM_HAMMING>(qd, rows[2 * r], rows[2 * r + 1]);
-        if ((float)d <= radius) {  // radiusMatch is inclusive
-          const double2 pr = s_proj[q0 + r];
-          const double dx = pr.x - plx, dy = pr.y - ply;
-          if (!(sqrt(dx * dx + dy * dy) > cfg.f2f_point_window)) best = min(best, make_key(d, q0 + r));
+        const uint4 ra = rows[2 * r], rb = rows[2 * r + 1];
+#pragma unroll
+        for (int k = 0; k < F2F_QPT; k++) {
+          const uint32_t d = hamming256<GFPL_NORM_HAMMING>(qd[k], ra, rb);
+          const bool hit = (int)d <= rint;
+          cnt[k] += hit ? 1u : 0u;
+          best[k] = min(best[k], hit ? make_key(d, q0 + r) : KEY_NONE);
         }
       }
       pipe.release(tile);
     }
+#pragma unroll
+    for (int k = 0; k < F2F_QPT; k++) {
+      if (cnt[k] == 1) {
+        best[k] = f2f_gate(KEY_NONE, best[k], s_proj[best[k] & KEY_IDX_MASK], plx[k], ply[k], window);
+      } else if (cnt[k] > 1) {
+        uint32_t b = KEY_NONE;
+        const uint8_t* rows_g = prev.pdesc + (size_t)p * prev.cap_pt * 32;
+        for (int q = 0; q < n_prev; q++) {
+          const uint4* rp = reinterpret_cast<const uint4*>(rows_g + (size_t)q * 32);
+          const uint32_t d = hamming256<GFPL_NORM_HAMMING>(qd[k], __ldg(rp), __ldg(rp + 1));
+          if ((int)d <= rint) b = f2f_gate(b, make_key(d, q), s_proj[q], plx[k], ply[k], window);
+        }
+        best[k] = b;
+      }
+    }
   }
-  if (t < n_curr) best_key[(size_t)p * curr.cap_pt + t] = best;
+#pragma unroll
+  for (int k = 0; k < F2F_QPT; k++)
+    if (tq[k] < n_curr) best_key[(size_t)p * curr.cap_pt + tq[k]] = best[k];
 }
 
 int launch_f2f_hybrid_points(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr,
@@ -97,7 +141,8 @@ int launch_f2f_hybrid_points(gfpl_ctx* ctx, const DevStereoFrames& prev, const D
   const size_t smem = 2 * F2F_TILE_ROWS * 32 + (size_t)prev.cap_pt * sizeof(double2);
   if (smem > 48 * 1024)
     GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(f2f_hybrid_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((curr.cap_pt + F2F_THREADS - 1) / F2F_THREADS, prev.B);
+  const int per_cta = F2F_THREADS * F2F_QPT;
+  dim3 grid((curr.cap_pt + per_cta - 1) / per_cta, prev.B);
   f2f_hybrid_points_kernel<<<grid, F2F_THREADS, smem, ctx->stream>>>(prev, curr, state, best_key, ctx->cam, ctx->cfg);
   GFPL_LAUNCH_OK(ctx);
   return GFPL_OK;

@@ -188,6 +188,18 @@ __global__ void __launch_bounds__(256) popc_peak_kernel(uint32_t* out, int iters
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+__global__ void __launch_bounds__(256) lop3_peak_kernel(uint32_t* out, int iters) {
+  uint32_t a0 = threadIdx.x * 2654435761u + blockIdx.x, a1 = a0 ^ 0x9e3779b9u, a2 = a0 * 3u, a3 = ~a0;
+  uint32_t a4 = a0 + 77u, a5 = a1 + 1234567u, a6 = a2 ^ 0xdeadbeefu, a7 = a3 * 5u;
+  const uint32_t b = blockIdx.x * 747796405u + 1u, c = threadIdx.x * 2891336453u + 7u;
+  for (int i = 0; i < iters; i++) {
+    // 8 independent 3-input LOP3 per iteration (ALU pipe); the asm keeps them from being folded
+    a0 = lop3_maj(a0, b, c); a1 = lop3_xor3(a1, b, c); a2 = lop3_maj(a2, c, b); a3 = lop3_xor3(a3, c, b);
+    a4 = lop3_maj(a4, b, c); a5 = lop3_xor3(a5, b, c); a6 = lop3_maj(a6, c, b); a7 = lop3_xor3(a7, c, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters) {
   double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
   const double m = 0.999999, c = 1e-9;
@@ -196,6 +208,31 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters) 
     a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int launch_measure_alu_peak(gfpl_ctx* ctx, double* lop3_tops) {
+  const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+  void* buf = nullptr;
+  GFPL_CUDA_OK(ctx, cudaMalloc(&buf, (size_t)blocks * threads * sizeof(uint32_t)));
+  cudaEvent_t e0, e1;
+  GFPL_CUDA_OK(ctx, cudaEventCreate(&e0));
+  GFPL_CUDA_OK(ctx, cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    float ms;
+    cudaEventRecord(e0, ctx->stream);
+    lop3_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)buf, iters);
+    cudaEventRecord(e1, ctx->stream);
+    GFPL_LAUNCH_OK(ctx);
+    GFPL_CUDA_OK(ctx, cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  *lop3_tops = (double)blocks * threads * iters * 8.0 / (best * 1e-3) / 1e12;
+  return GFPL_OK;
 }
 
 int launch_measure_peaks(gfpl_ctx* ctx, double* popc_tops, double* fp64_tflops) {

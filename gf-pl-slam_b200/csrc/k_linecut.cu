@@ -11,7 +11,8 @@
 // registers), and the reference's "first strictly better in j order" rule is replayed with width-8
 // shuffles.  Four pairs share a warp.  invCov_sum is accumulated in the reference's order (lines, then
 // points, sequentially), and -fmad=false keeps every candidate metric bit-comparable with an IEEE CPU
-// evaluation, so the discrete cut decisions are reproducible.  FP64-ALU / latency bound.
+// evaluation, so the discrete cut decisions are reproducible.  A determinant-lemma evaluation screens the rounds
+// (see `Screening path` below); ambiguous rounds are re-decided with the exact arithmetic.  FP64-ALU / latency bound.
 #include "gfpl_internal.h"
 #include "gfpl_math.cuh"
 
@@ -118,13 +119,122 @@ __device__ __forceinline__ double cut_metric(const gfpl_config& cfg, const doubl
   return ev[0];
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Screening path.  All candidates of one line share S = invCov_sum - info(line), and a candidate adds the rank-2
+// term  a*u*u^T + b*v*v^T  (u = Js(c0), a = 1/cov_sR(c0), v = Je(c1), b = 1/cov_eR(c1)), so by the matrix
+// determinant lemma   logdet(S + info(c0,c1)) - logdet(S) = log( (1 + a u'S^-1 u)(1 + b v'S^-1 v) - a b (u'S^-1 v)^2 ).
+// That difference ("gain") orders the candidates exactly like the reference's metric does, costs one 6x6 mat-vec per
+// half instead of a 6x6 Cholesky + 6 logs per candidate, and the u- and v-halves are shared by the three candidates
+// that have the same c0 resp. c1.  It is NOT the reference's arithmetic, so it only SCREENS: a round is decided by
+// the gains when every comparison the reference would make is clear by more than CUT_TAU (>= 100x the combined
+// rounding error of both evaluations); otherwise the round is re-evaluated with the exact path below, which then
+// decides exactly as before.  Outputs (cutRatio, invCovPose, moved endpoints, invCov_sum) always come from the
+// exact arithmetic.  FMAs are written explicitly here (the file is compiled with -fmad=false).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr double CUT_TAU = 1e-8;
+
+struct HalfFast {
+  double u[6];   // Jacobian column of this endpoint
+  double w[6];   // S^-1 u
+  double a;      // 1 / residual variance
+  double g;      // u' S^-1 u
+};
+
+__device__ __forceinline__ double dot3f(const double* a, const double* b) { return fma(a[2], b[2], fma(a[1], b[1], a[0] * b[0])); }
+
+// one endpoint of getPoseInfoOnLine at cut ratio c: A/SA = the endpoint that shrinks towards B/SB
+__device__ __forceinline__ void half_fast(const gfpl_camera& cam, const gfpl_config& cfg, const double* DT, const double* A,
+                                          const double* Bp, const double* SA, const double* SB, const double* le,
+                                          const double* Sinv, double c, HalfFast& h) {
+  const double omc = 1.0 - c;
+  double P[3], cur[3], cv[9];
+#pragma unroll
+  for (int k = 0; k < 3; k++) P[k] = fma(c, Bp[k], omc * A[k]);
+  const double a2 = omc * omc, b2 = c * c;
+#pragma unroll
+  for (int k = 0; k < 9; k++) cv[k] = fma(b2, SB[k], a2 * SA[k]);
+#pragma unroll
+  for (int i = 0; i < 3; i++) cur[i] = fma(DT[i * 3 + 2], P[2], fma(DT[i * 3 + 1], P[1], fma(DT[i * 3], P[0], DT[9 + i])));
+  // q = R^T Jp^T l  (3-vector), variance = q' cov q
+  const double f = cam.fx, iz = 1.0 / cur[2];
+  const double j0 = f * iz * le[0], j1 = f * iz * le[1], j2 = -(f * iz * iz) * fma(cur[1], le[1], cur[0] * le[0]);
+  double q[3], t[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) q[k] = fma(DT[6 + k], j2, fma(DT[3 + k], j1, DT[k] * j0));
+#pragma unroll
+  for (int i = 0; i < 3; i++) t[i] = dot3f(&cv[i * 3], q);
+  h.a = 1.0 / dot3f(q, t);
+  jac6(cam.fx / fmax(cfg.homog_th, cur[2] * cur[2]), cur[0], cur[1], cur[2], le[0], le[1], h.u);
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) sacc = fma(Sinv[i >= k ? tri(i, k) : tri(k, i)], h.u[k], sacc);
+    h.w[i] = sacc;
+  }
+  double g = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) g = fma(h.u[i], h.w[i], g);
+  h.g = g;
+}
+
+// S^-1 of the lower-packed SPD matrix S (21) by Cholesky; returns false when S is not safely positive definite
+__device__ __forceinline__ bool spd_inverse6(const double* S, double* Sinv) {
+  double L[21];
+#pragma unroll
+  for (int i = 0; i < 21; i++) L[i] = S[i];
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    double x = L[tri(k, k)];
+#pragma unroll
+    for (int jx = 0; jx < k; jx++) x = fma(-L[tri(k, jx)], L[tri(k, jx)], x);
+    ok = ok && (x > 0.0);
+    const double r = rsqrt(x);
+    L[tri(k, k)] = r;  // store 1/L_kk
+#pragma unroll
+    for (int i = k + 1; i < 6; i++) {
+      double sv = L[tri(i, k)];
+#pragma unroll
+      for (int jx = 0; jx < k; jx++) sv = fma(-L[tri(i, jx)], L[tri(k, jx)], sv);
+      L[tri(i, k)] = sv * r;
+    }
+  }
+  // columns of S^-1: solve L y = e_c, L^T x = y
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      double sv = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < i; k++) sv = fma(-L[tri(i, k)], y[k], sv);
+      y[i] = (i < c) ? 0.0 : sv * L[tri(i, i)];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+      double sv = y[i];
+#pragma unroll
+      for (int k = i + 1; k < 6; k++) sv = fma(-L[tri(k, i)], y[k], sv);
+      y[i] = sv * L[tri(i, i)];
+    }
+#pragma unroll
+    for (int i = c; i < 6; i++) Sinv[tri(i, c)] = y[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 21; i++) ok = ok && (fabs(Sinv[i]) < 1e300);
+  return ok;
+}
+
 // per-group (one frame pair) state kept in shared memory: every lane of the group reads the same addresses
 // (broadcast), which frees ~120 registers per thread and lets 16 warps / SM hide the fp64 dependency chains.
 struct GroupState {
   double DT[12];        // R | t of DT_inv
   double L[LD_SIZE];    // current line
   double sum[21];       // invCov_sum, lower triangle
-  double pad;
+  double Sinv[21];      // inverse of (invCov_sum - info(line)) for the screening path
+  double pad[2];
 };
 
 #ifndef CUT_MIN_BLOCKS
@@ -263,40 +373,106 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
       }
     }
     __syncwarp(gmask);
+    // screening set-up: S^-1 once per line (every lane computes it redundantly, lane 0 publishes it)
+    bool fast_ok = cfg.max_vol_line_cut != 0;
+    if (fast_ok) {
+      double Sinv[21];
+      fast_ok = spd_inverse6(G.sum, Sinv);
+      if (j == 0) {
+#pragma unroll
+        for (int e = 0; e < 21; e++) G.Sinv[e] = Sinv[e];
+      }
+    }
+    __syncwarp(gmask);
     double cur0 = 0.0, cur1 = 0.0;
+    bool have_exact_last = true;   // metric_last holds the reference's metric of the current cut
     while (cur0 + cur1 <= 1.0) {
       const double ct0 = cur0 + nb0, ct1 = cur1 + nb1;
       bool valid = !(ct0 + ct1 > 1.0);
       valid = valid && !(ct0 < cfg.cut_rng[0] || ct0 > cfg.cut_rng[1]);
       valid = valid && !(ct1 < cfg.cut_rng[0] || ct1 > cfg.cut_rng[1]);
-      double metric = 0.0;
-      LineInfo I;
-      if (valid) {
-        pose_info_on_line(cam, cfg, G.DT, G.L, ct0, ct1, I);
-        double M[21];
-#pragma unroll
-        for (int a = 0; a < 6; a++)
-#pragma unroll
-          for (int b = 0; b <= a; b++) M[tri(a, b)] = info_entry(I, a, b) + G.sum[tri(a, b)];
-        metric = cut_metric(cfg, M);
-      }
-      // "first strictly better in j order" (:1722-1730)
-      double best = metric_last;
       int cand = -1;
+      bool decided = false;
+      if (fast_ok) {
+        // lanes 0..2: start-point halves at c0 - step, c0, c0 + step; lanes 3..5: end-point halves likewise
+        const bool isS = j < 3;
+        const int kk = (j % 3) - 1;
+        const double ch = (isS ? cur0 : cur1) + (kk < 0 ? -step : (kk > 0 ? step : 0.0));
+        HalfFast h;
+        half_fast(cam, cfg, G.DT, isS ? &G.L[LD_SP] : &G.L[LD_EP], isS ? &G.L[LD_EP] : &G.L[LD_SP],
+                  isS ? &G.L[LD_CS] : &G.L[LD_CE], isS ? &G.L[LD_CE] : &G.L[LD_CS], &G.L[LD_LE], G.Sinv, ch, h);
+        // gain of (si, ei): u, a, g from the s-half lane; w, b, g from the e-half lane
+        auto gain = [&](int si, int ei) {
+          double guv = 0.0;
 #pragma unroll
-      for (int jj = 0; jj < CUT_GROUP; jj++) {
-        const double mj = shfl_f64(gmask, metric, jj, CUT_GROUP);
-        const int vj = __shfl_sync(gmask, (int)valid, jj, CUT_GROUP);
-        if (vj && mj > best) { best = mj; cand = jj; }
+          for (int i = 0; i < 6; i++)
+            guv = fma(shfl_f64(gmask, h.u[i], si, CUT_GROUP), shfl_f64(gmask, h.w[i], ei, CUT_GROUP), guv);
+          const double a = shfl_f64(gmask, h.a, si, CUT_GROUP), gu = shfl_f64(gmask, h.g, si, CUT_GROUP);
+          const double b = shfl_f64(gmask, h.a, ei, CUT_GROUP), gv = shfl_f64(gmask, h.g, ei, CUT_GROUP);
+          const double D = fma(-(a * b) * guv, guv, fma(a, gu, 1.0) * fma(b, gv, 1.0));
+          return log(D);
+        };
+        const int si = (nb0 < 0.0) ? 0 : ((nb0 > 0.0) ? 2 : 1);
+        const int ei = 3 + ((nb1 < 0.0) ? 0 : ((nb1 > 0.0) ? 2 : 1));
+        const double gj = gain(si, ei);      // this lane's candidate
+        const double gc = gain(1, 4);        // the current cut (same value in every lane)
+        // replay the reference's selection on the gains, but only if every comparison is clear by > CUT_TAU
+        double best = gc;
+        int bj = -1;
+        bool clear = (gc == gc) && fabs(gc) < 1e300;
+#pragma unroll
+        for (int jj = 0; jj < CUT_GROUP; jj++) {
+          const double mj = shfl_f64(gmask, gj, jj, CUT_GROUP);
+          const int vj = __shfl_sync(gmask, (int)valid, jj, CUT_GROUP);
+          if (vj) {
+            clear = clear && (mj == mj) && fabs(mj) < 1e300 && fabs(mj - best) > CUT_TAU * (1.0 + fabs(best));
+            if (mj > best) { best = mj; bj = jj; }
+          }
+        }
+        if (clear) { decided = true; cand = bj; have_exact_last = false; }
+      }
+      LineInfo I;
+      if (!decided) {
+        // exact round: the reference's arithmetic (also the only path for the min-eigenvalue metric)
+        if (!have_exact_last) {  // metric of the current cut, needed as the running best
+          pose_info_on_line(cam, cfg, G.DT, G.L, cur0, cur1, I);
+          double M[21];
+#pragma unroll
+          for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int b = 0; b <= a; b++) M[tri(a, b)] = info_entry(I, a, b) + G.sum[tri(a, b)];
+          metric_last = cut_metric(cfg, M);
+          have_exact_last = true;
+        }
+        double metric = 0.0;
+        if (valid) {
+          pose_info_on_line(cam, cfg, G.DT, G.L, ct0, ct1, I);
+          double M[21];
+#pragma unroll
+          for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int b = 0; b <= a; b++) M[tri(a, b)] = info_entry(I, a, b) + G.sum[tri(a, b)];
+          metric = cut_metric(cfg, M);
+        }
+        // "first strictly better in j order" (:1722-1730)
+        double best = metric_last;
+#pragma unroll
+        for (int jj = 0; jj < CUT_GROUP; jj++) {
+          const double mj = shfl_f64(gmask, metric, jj, CUT_GROUP);
+          const int vj = __shfl_sync(gmask, (int)valid, jj, CUT_GROUP);
+          if (vj && mj > best) { best = mj; cand = jj; }
+        }
+        metric_last = best;
       }
       if (cand < 0) break;  // early termination (:1741-1743)
-      if (j == cand) {
-        for (int a = 0; a < 6; a++)
-          for (int b = 0; b < 6; b++) C.invCovPose[a * 6 + b] = info_entry(I, a, b);
-      }
       cur0 = shfl_f64(gmask, ct0, cand, CUT_GROUP);
       cur1 = shfl_f64(gmask, ct1, cand, CUT_GROUP);
-      metric_last = best;
+    }
+    // invCovPose of the accepted cut, in the reference's arithmetic (cut {0,0} is already stored by pass 1)
+    if (cur0 != 0.0 || cur1 != 0.0) {
+      LineInfo I;
+      pose_info_on_line(cam, cfg, G.DT, G.L, cur0, cur1, I);
+      for (int e = j; e < 36; e += CUT_GROUP) C.invCovPose[e] = info_entry(I, e / 6, e % 6);
     }
     __syncwarp(gmask);
     // updateEndPointByRatio (:1451-1470) — lane 0 of the group writes the results

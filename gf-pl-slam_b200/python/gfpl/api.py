@@ -128,6 +128,11 @@ class Context:
         self._check(lib().gfpl_measure_peaks(self._h, C.byref(p), C.byref(f)))
         return p.value, f.value
 
+    def measure_alu_peak(self):
+        p = C.c_double()
+        self._check(lib().gfpl_measure_alu_peak(self._h, C.byref(p)))
+        return p.value
+
     # ---- M1-M3 ----
     def knn2(self, q, t, norm=S.NORM_HAMMING):
         q, t = _u8(q), _u8(t)

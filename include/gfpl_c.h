@@ -469,6 +469,8 @@ int gfpl_lba_assemble(gfpl_ctx* ctx, const gfpl_lba_problem* prob, gfpl_lba_bloc
 
 /* measured popc.b32 throughput (T popc/s) and fp64 FMA throughput (TFLOP/s, FMA = 2 flop) */
 int gfpl_measure_peaks(gfpl_ctx* ctx, double* popc_tops, double* fp64_tflops);
+/* measured 3-input LOP3 throughput of the ALU pipe (T op/s): the second pipe of the matching loop */
+int gfpl_measure_alu_peak(gfpl_ctx* ctx, double* lop3_tops);
 
 #ifdef __cplusplus
 }

@@ -401,3 +401,21 @@ def test_replay_with_packed_previous_frames(ctx, orc):
     rp.download(pose)
     ctx.sync()
     assert pose.tobytes() == pg.tobytes()
+
+
+def test_linecut_decisions_exact_at_scale(ctx, orc):
+    """the determinant-lemma screening of the cut search must never change a decision: 1024 frame pairs
+    (~20k lines, ~2M candidate comparisons) against the oracle, cut ratios and information matrices"""
+    d = _data(1024, 1200)
+    prev, curr, obs = _obs(orc, ctx.cfg, d)
+    cov = orc.stereo_uncertainty(d["cam"], ctx.cfg, prev)
+    DT_inv = _dt_inv(d["state"])
+    og, oo = obs.copy(), obs.copy()
+    cg = ctx.linecut(DT_inv, og, cov)
+    co = orc.linecut(d["cam"], ctx.cfg, DT_inv, oo, cov)
+    mask = np.arange(obs.cap_ln)[None, :] < obs.n_ln[:, None]
+    assert mask.sum() > 10000
+    diff = (cg["cutRatio"] != co["cutRatio"]).any(-1) & mask
+    assert diff.sum() == 0, f"{diff.sum()} of {mask.sum()} lines with a different cut decision"
+    assert close(cg["invCovPose"][mask], co["invCovPose"][mask])
+    assert close(og.ln["sP"][mask], oo.ln["sP"][mask]) and close(og.ln["eP"][mask], oo.ln["eP"][mask])
