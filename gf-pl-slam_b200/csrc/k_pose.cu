@@ -18,7 +18,7 @@ namespace gfpl {
 
 constexpr int POSE_WARPS = 4;
 #ifndef POSE_MIN_BLOCKS
-#define POSE_MIN_BLOCKS 4  // <= 128 registers: 16 warps / SM hide the fp64 and L1 latencies of the GN loop
+#define POSE_MIN_BLOCKS 3  // <= 168 registers (measured: 1.70 ms vs 1.98 ms at 4 blocks = 128 registers with spills in the GN loop)
 #endif
 
 // hand-off record between the GN kernel and the finalize kernel
@@ -34,36 +34,40 @@ struct Acc {
 };
 
 __device__ __forceinline__ void acc_add(Acc& a, const double* J, double r, double w) {
+  const double rw = r * w;
 #pragma unroll
   for (int i = 0; i < 6; i++) {
+    const double Jw = J[i] * w;
 #pragma unroll
-    for (int j = 0; j <= i; j++) a.v[tri(i, j)] = a.v[tri(i, j)] + J[i] * J[j] * w;
-    a.v[21 + i] = a.v[21 + i] + J[i] * r * w;
+    for (int j = 0; j <= i; j++) a.v[tri(i, j)] = fma(Jw, J[j], a.v[tri(i, j)]);
+    a.v[21 + i] = fma(J[i], rw, a.v[21 + i]);
   }
-  a.v[27] = a.v[27] + r * r * w;
+  a.v[27] = fma(r, rw, a.v[27]);
 }
+
+// This translation unit is tolerance-compared (1e-9) and compiled with FMA contraction: divisions that the
+// reference performs element-wise (J/max(eps,r), fx*X/Z, ...) are done as one reciprocal and multiplies.
 
 // point term (stereoFrameHandler.cpp:2131-2167); returns the residual norm
 __device__ __forceinline__ double point_residual(const double* DT, const gfpl_pt_obs& o, const gfpl_camera& cam,
                                                  double* P_, double* dxy) {
-  double uv[2];
   se3_apply(DT, o.P, P_);
-  projection(cam, P_, uv);
-  dxy[0] = uv[0] - o.pl_obs[0];
-  dxy[1] = uv[1] - o.pl_obs[1];
+  const double iz = 1.0 / P_[2];
+  dxy[0] = (cam.cx + cam.fx * P_[0] * iz) - o.pl_obs[0];
+  dxy[1] = (cam.cy + cam.fy * P_[1] * iz) - o.pl_obs[1];
   return sqrt(dxy[0] * dxy[0] + dxy[1] * dxy[1]);
 }
 
 // line term (:2171-2235)
 __device__ __forceinline__ double line_residual(const double* DT, const gfpl_ln_obs& o, const gfpl_camera& cam,
                                                 double* sP_, double* eP_, double* dse) {
-  double sp[2], ep[2];
   se3_apply(DT, o.sP, sP_);
-  projection(cam, sP_, sp);
   se3_apply(DT, o.eP, eP_);
-  projection(cam, eP_, ep);
-  dse[0] = o.le_obs[0] * sp[0] + o.le_obs[1] * sp[1] + o.le_obs[2];
-  dse[1] = o.le_obs[0] * ep[0] + o.le_obs[1] * ep[1] + o.le_obs[2];
+  const double izs = 1.0 / sP_[2], ize = 1.0 / eP_[2];
+  const double su = cam.cx + cam.fx * sP_[0] * izs, sv = cam.cy + cam.fy * sP_[1] * izs;
+  const double eu = cam.cx + cam.fx * eP_[0] * ize, ev = cam.cy + cam.fy * eP_[1] * ize;
+  dse[0] = o.le_obs[0] * su + o.le_obs[1] * sv + o.le_obs[2];
+  dse[1] = o.le_obs[0] * eu + o.le_obs[1] * ev + o.le_obs[2];
   return sqrt(dse[0] * dse[0] + dse[1] * dse[1]);
 }
 
@@ -174,16 +178,22 @@ __device__ __forceinline__ void warp_optimize_functions(const double* DT, const 
 #pragma unroll
   for (int i = 0; i < 28; i++) a.v[i] = 0.0;
   int N = 0;
+  // software-pipelined: the observation of the next round is loaded before this round's arithmetic
+  gfpl_pt_obs nxt;
+  uint8_t nxt_in = 0;
+  if (lane < o.npt) { nxt = o.pts[lane]; nxt_in = o.pin[lane]; }
   for (int k = lane; k < o.npt; k += 32) {
-    if (!o.pin[k]) continue;
+    const gfpl_pt_obs ob = nxt;
+    const uint8_t in = nxt_in;
+    if (k + 32 < o.npt) { nxt = o.pts[k + 32]; nxt_in = o.pin[k + 32]; }
+    if (!in) continue;
     double P_[3], d[2], J[6];
-    const gfpl_pt_obs ob = o.pts[k];
     const double r = point_residual(DT, ob, cam, P_, d);
     const double fgz2 = cam.fx / fmax(cfg.homog_th, P_[2] * P_[2]);
     jac6(fgz2, P_[0], P_[1], P_[2], d[0], d[1], J);
-    const double dn = fmax(cfg.homog_th, r);
+    const double idn = 1.0 / fmax(cfg.homog_th, r);
 #pragma unroll
-    for (int i = 0; i < 6; i++) J[i] = J[i] / dn;
+    for (int i = 0; i < 6; i++) J[i] = J[i] * idn;
     const double w = 1.0 / (1.0 + r * r * ob.sigma2);
     acc_add(a, J, r, w);
     N++;
@@ -195,9 +205,9 @@ __device__ __forceinline__ void warp_optimize_functions(const double* DT, const 
     const double r = line_residual(DT, ob, cam, sP_, eP_, d);
     jac6(cam.fx / fmax(cfg.homog_th, sP_[2] * sP_[2]), sP_[0], sP_[1], sP_[2], ob.le_obs[0], ob.le_obs[1], Js);
     jac6(cam.fx / fmax(cfg.homog_th, eP_[2] * eP_[2]), eP_[0], eP_[1], eP_[2], ob.le_obs[0], ob.le_obs[1], Je);
-    const double dn = fmax(cfg.homog_th, r);
+    const double idn = 1.0 / fmax(cfg.homog_th, r);
 #pragma unroll
-    for (int i = 0; i < 6; i++) J[i] = (Js[i] * d[0] + Je[i] * d[1]) / dn;
+    for (int i = 0; i < 6; i++) J[i] = (Js[i] * d[0] + Je[i] * d[1]) * idn;
     const double w = 1.0 / (1.0 + r * r * ob.sigma2);
     acc_add(a, J, r, w);
     N++;
