@@ -134,19 +134,23 @@ __device__ __forceinline__ double cut_metric(const gfpl_config& cfg, const doubl
 // ---------------------------------------------------------------------------------------------------------------
 constexpr double CUT_TAU = 1e-8;
 
-struct HalfFast {
-  double u[6];   // Jacobian column of this endpoint
-  double w[6];   // S^-1 u
-  double a;      // 1 / residual variance
-  double g;      // u' S^-1 u
-};
+// one published half: u[6] (Jacobian column), w[6] = S^-1 u, a = 1 / residual variance, g = u' S^-1 u
+constexpr int HF_U = 0, HF_W = 6, HF_A = 12, HF_G = 13, HF_SIZE = 14;
 
 __device__ __forceinline__ double dot3f(const double* a, const double* b) { return fma(a[2], b[2], fma(a[1], b[1], a[0] * b[0])); }
 
-// one endpoint of getPoseInfoOnLine at cut ratio c: A/SA = the endpoint that shrinks towards B/SB
+// reciprocal to ~1e-15 relative: float seed + 2 Newton steps (screening path only)
+__device__ __forceinline__ double rcp_fast(double x) {
+  double r = (double)__frcp_rn((float)x);
+  r = r * fma(-x, r, 2.0);
+  r = r * fma(-x, r, 2.0);
+  return r;
+}
+
+// one endpoint of getPoseInfoOnLine at cut ratio c: A/SA = the endpoint that shrinks towards B/SB.  Result -> out[HF_SIZE]
 __device__ __forceinline__ void half_fast(const gfpl_camera& cam, const gfpl_config& cfg, const double* DT, const double* A,
                                           const double* Bp, const double* SA, const double* SB, const double* le,
-                                          const double* Sinv, double c, HalfFast& h) {
+                                          const double* Sinv /*6x6 row-major*/, double c, double* out) {
   const double omc = 1.0 - c;
   double P[3], cur[3], cv[9];
 #pragma unroll
@@ -157,29 +161,41 @@ __device__ __forceinline__ void half_fast(const gfpl_camera& cam, const gfpl_con
 #pragma unroll
   for (int i = 0; i < 3; i++) cur[i] = fma(DT[i * 3 + 2], P[2], fma(DT[i * 3 + 1], P[1], fma(DT[i * 3], P[0], DT[9 + i])));
   // q = R^T Jp^T l  (3-vector), variance = q' cov q
-  const double f = cam.fx, iz = 1.0 / cur[2];
-  const double j0 = f * iz * le[0], j1 = f * iz * le[1], j2 = -(f * iz * iz) * fma(cur[1], le[1], cur[0] * le[0]);
+  const double f = cam.fx, iz = rcp_fast(cur[2]);
+  const double fiz = f * iz, lx = le[0], ly = le[1];
+  const double j0 = fiz * lx, j1 = fiz * ly, j2 = -(fiz * iz) * fma(cur[1], ly, cur[0] * lx);
   double q[3], t[3];
 #pragma unroll
   for (int k = 0; k < 3; k++) q[k] = fma(DT[6 + k], j2, fma(DT[3 + k], j1, DT[k] * j0));
 #pragma unroll
   for (int i = 0; i < 3; i++) t[i] = dot3f(&cv[i * 3], q);
-  h.a = 1.0 / dot3f(q, t);
-  jac6(cam.fx / fmax(cfg.homog_th, cur[2] * cur[2]), cur[0], cur[1], cur[2], le[0], le[1], h.u);
+  const double a = rcp_fast(dot3f(q, t));
+  // jac6 with k = fx / max(homog_th, Z^2)
+  const double gx = cur[0], gy = cur[1], gz = cur[2], gz2 = gz * gz;
+  const double kf = gz2 > cfg.homog_th ? fiz * iz : f / cfg.homog_th;
+  double u[6];
+  const double xl = gx * lx, yl = gy * ly;
+  u[0] = kf * lx * gz;
+  u[1] = kf * ly * gz;
+  u[2] = -kf * (xl + yl);
+  u[3] = -kf * fma(gy, xl + yl, gz2 * ly);
+  u[4] = kf * fma(gx, xl + yl, gz2 * lx);
+  u[5] = kf * gz * fma(gx, ly, -(gy * lx));
+  double g = 0.0;
 #pragma unroll
   for (int i = 0; i < 6; i++) {
     double sacc = 0.0;
 #pragma unroll
-    for (int k = 0; k < 6; k++) sacc = fma(Sinv[i >= k ? tri(i, k) : tri(k, i)], h.u[k], sacc);
-    h.w[i] = sacc;
+    for (int k = 0; k < 6; k++) sacc = fma(Sinv[i * 6 + k], u[k], sacc);
+    out[HF_U + i] = u[i];
+    out[HF_W + i] = sacc;
+    g = fma(u[i], sacc, g);
   }
-  double g = 0.0;
-#pragma unroll
-  for (int i = 0; i < 6; i++) g = fma(h.u[i], h.w[i], g);
-  h.g = g;
+  out[HF_A] = a;
+  out[HF_G] = g;
 }
 
-// S^-1 of the lower-packed SPD matrix S (21) by Cholesky; returns false when S is not safely positive definite
+// S^-1 (full 6x6 row-major) of the lower-packed SPD matrix S (21) by Cholesky; false when S is not safely positive definite
 __device__ __forceinline__ bool spd_inverse6(const double* S, double* Sinv) {
   double L[21];
 #pragma unroll
@@ -220,10 +236,10 @@ __device__ __forceinline__ bool spd_inverse6(const double* S, double* Sinv) {
       y[i] = sv * L[tri(i, i)];
     }
 #pragma unroll
-    for (int i = c; i < 6; i++) Sinv[tri(i, c)] = y[i];
+    for (int i = c; i < 6; i++) { Sinv[i * 6 + c] = y[i]; Sinv[c * 6 + i] = y[i]; }
   }
 #pragma unroll
-  for (int i = 0; i < 21; i++) ok = ok && (fabs(Sinv[i]) < 1e300);
+  for (int i = 0; i < 36; i++) ok = ok && (fabs(Sinv[i]) < 1e300);
   return ok;
 }
 
@@ -233,8 +249,9 @@ struct GroupState {
   double DT[12];        // R | t of DT_inv
   double L[LD_SIZE];    // current line
   double sum[21];       // invCov_sum, lower triangle
-  double Sinv[21];      // inverse of (invCov_sum - info(line)) for the screening path
-  double pad[2];
+  double sum0[21];      // invCov_sum before the current line's information is removed (exact metric of cut {0,0})
+  double Sinv[36];      // inverse of (invCov_sum - info(line)) for the screening path, row-major
+  double half[6][HF_SIZE];  // the six published halves of the current round
 };
 
 #ifndef CUT_MIN_BLOCKS
@@ -361,31 +378,33 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
       }
     }
     __syncwarp(gmask);
-    double metric_last = cut_metric(cfg, G.sum);
-    __syncwarp(gmask);
     {
       const double* info = C.invCovPose;
       for (int e = j; e < 21; e += CUT_GROUP) {
         int a = 0;
         while ((a + 1) * (a + 2) / 2 <= e) a++;
         const int b = e - a * (a + 1) / 2;
+        G.sum0[e] = G.sum[e];
         G.sum[e] = G.sum[e] - info[a * 6 + b];
       }
     }
     __syncwarp(gmask);
-    // screening set-up: S^-1 once per line (every lane computes it redundantly, lane 0 publishes it)
+    // screening set-up: S^-1 once per line (every lane computes it redundantly, lanes publish it together)
     bool fast_ok = cfg.max_vol_line_cut != 0;
     if (fast_ok) {
-      double Sinv[21];
+      double Sinv[36];
       fast_ok = spd_inverse6(G.sum, Sinv);
-      if (j == 0) {
 #pragma unroll
-        for (int e = 0; e < 21; e++) G.Sinv[e] = Sinv[e];
-      }
+      for (int e = 0; e < 36; e++)
+        if ((e & (CUT_GROUP - 1)) == j) G.Sinv[e] = Sinv[e];
     }
     __syncwarp(gmask);
     double cur0 = 0.0, cur1 = 0.0;
-    bool have_exact_last = true;   // metric_last holds the reference's metric of the current cut
+    double metric_last = 0.0;      // the reference's metric of the current cut; evaluated lazily (exact rounds only)
+    bool have_exact_last = false;
+    bool at_start = true;          // current cut is still {0,0}: its exact metric is logdet(sum0)
+    double dcur = 0.0;             // screening determinant factor of the current cut
+    bool have_dcur = false;
     while (cur0 + cur1 <= 1.0) {
       const double ct0 = cur0 + nb0, ct1 = cur1 + nb1;
       bool valid = !(ct0 + ct1 > 1.0);
@@ -395,53 +414,58 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
       bool decided = false;
       if (fast_ok) {
         // lanes 0..2: start-point halves at c0 - step, c0, c0 + step; lanes 3..5: end-point halves likewise
-        const bool isS = j < 3;
-        const int kk = (j % 3) - 1;
-        const double ch = (isS ? cur0 : cur1) + (kk < 0 ? -step : (kk > 0 ? step : 0.0));
-        HalfFast h;
-        half_fast(cam, cfg, G.DT, isS ? &G.L[LD_SP] : &G.L[LD_EP], isS ? &G.L[LD_EP] : &G.L[LD_SP],
-                  isS ? &G.L[LD_CS] : &G.L[LD_CE], isS ? &G.L[LD_CE] : &G.L[LD_CS], &G.L[LD_LE], G.Sinv, ch, h);
-        // gain of (si, ei): u, a, g from the s-half lane; w, b, g from the e-half lane
-        auto gain = [&](int si, int ei) {
+        if (j < 6) {
+          const bool isS = j < 3;
+          const int kk = (j % 3) - 1;
+          const double ch = (isS ? cur0 : cur1) + (kk < 0 ? -step : (kk > 0 ? step : 0.0));
+          half_fast(cam, cfg, G.DT, isS ? &G.L[LD_SP] : &G.L[LD_EP], isS ? &G.L[LD_EP] : &G.L[LD_SP],
+                    isS ? &G.L[LD_CS] : &G.L[LD_CE], isS ? &G.L[LD_CE] : &G.L[LD_CS], &G.L[LD_LE], G.Sinv, ch, G.half[j]);
+        }
+        __syncwarp(gmask);
+        // determinant factor of (si, ei): (1 + a u'S^-1u)(1 + b v'S^-1v) - a b (u'S^-1v)^2  (monotone in the metric)
+        auto factor = [&](int si, int ei) {
+          const double* hs = G.half[si];
+          const double* he = G.half[ei];
           double guv = 0.0;
 #pragma unroll
-          for (int i = 0; i < 6; i++)
-            guv = fma(shfl_f64(gmask, h.u[i], si, CUT_GROUP), shfl_f64(gmask, h.w[i], ei, CUT_GROUP), guv);
-          const double a = shfl_f64(gmask, h.a, si, CUT_GROUP), gu = shfl_f64(gmask, h.g, si, CUT_GROUP);
-          const double b = shfl_f64(gmask, h.a, ei, CUT_GROUP), gv = shfl_f64(gmask, h.g, ei, CUT_GROUP);
-          const double D = fma(-(a * b) * guv, guv, fma(a, gu, 1.0) * fma(b, gv, 1.0));
-          return log(D);
+          for (int i = 0; i < 6; i++) guv = fma(hs[HF_U + i], he[HF_W + i], guv);
+          const double a = hs[HF_A], b = he[HF_A];
+          return fma(-(a * b) * guv, guv, fma(a, hs[HF_G], 1.0) * fma(b, he[HF_G], 1.0));
         };
         const int si = (nb0 < 0.0) ? 0 : ((nb0 > 0.0) ? 2 : 1);
         const int ei = 3 + ((nb1 < 0.0) ? 0 : ((nb1 > 0.0) ? 2 : 1));
-        const double gj = gain(si, ei);      // this lane's candidate
-        const double gc = gain(1, 4);        // the current cut (same value in every lane)
-        // replay the reference's selection on the gains, but only if every comparison is clear by > CUT_TAU
-        double best = gc;
+        const double dj = factor(si, ei);          // this lane's candidate
+        if (!have_dcur) { dcur = factor(1, 4); have_dcur = true; }   // the current cut (same value in every lane)
+        __syncwarp(gmask);
+        // replay the reference's selection on the factors, but only if every comparison is clear by > CUT_TAU (relative)
+        double best = dcur;
         int bj = -1;
-        bool clear = (gc == gc) && fabs(gc) < 1e300;
+        bool clear = (dcur > 0.0) && dcur < 1e300;
 #pragma unroll
         for (int jj = 0; jj < CUT_GROUP; jj++) {
-          const double mj = shfl_f64(gmask, gj, jj, CUT_GROUP);
+          const double mj = shfl_f64(gmask, dj, jj, CUT_GROUP);
           const int vj = __shfl_sync(gmask, (int)valid, jj, CUT_GROUP);
           if (vj) {
-            clear = clear && (mj == mj) && fabs(mj) < 1e300 && fabs(mj - best) > CUT_TAU * (1.0 + fabs(best));
+            clear = clear && (mj > 0.0) && mj < 1e300 && fabs(mj - best) > CUT_TAU * best;
             if (mj > best) { best = mj; bj = jj; }
           }
         }
-        if (clear) { decided = true; cand = bj; have_exact_last = false; }
+        if (clear) { decided = true; cand = bj; have_exact_last = false; dcur = best; }
       }
       LineInfo I;
       if (!decided) {
         // exact round: the reference's arithmetic (also the only path for the min-eigenvalue metric)
         if (!have_exact_last) {  // metric of the current cut, needed as the running best
-          pose_info_on_line(cam, cfg, G.DT, G.L, cur0, cur1, I);
-          double M[21];
+          if (at_start) metric_last = cut_metric(cfg, G.sum0);
+          else {
+            pose_info_on_line(cam, cfg, G.DT, G.L, cur0, cur1, I);
+            double M[21];
 #pragma unroll
-          for (int a = 0; a < 6; a++)
+            for (int a = 0; a < 6; a++)
 #pragma unroll
-            for (int b = 0; b <= a; b++) M[tri(a, b)] = info_entry(I, a, b) + G.sum[tri(a, b)];
-          metric_last = cut_metric(cfg, M);
+              for (int b = 0; b <= a; b++) M[tri(a, b)] = info_entry(I, a, b) + G.sum[tri(a, b)];
+            metric_last = cut_metric(cfg, M);
+          }
           have_exact_last = true;
         }
         double metric = 0.0;
@@ -463,10 +487,12 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
           if (vj && mj > best) { best = mj; cand = jj; }
         }
         metric_last = best;
+        have_dcur = false;   // the screening factor of the new current cut is re-evaluated next round
       }
       if (cand < 0) break;  // early termination (:1741-1743)
       cur0 = shfl_f64(gmask, ct0, cand, CUT_GROUP);
       cur1 = shfl_f64(gmask, ct1, cand, CUT_GROUP);
+      at_start = false;
     }
     // invCovPose of the accepted cut, in the reference's arithmetic (cut {0,0} is already stored by pass 1)
     if (cur0 != 0.0 || cur1 != 0.0) {
