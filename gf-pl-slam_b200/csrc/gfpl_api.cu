@@ -418,6 +418,7 @@ struct gfpl_replay {
   DevStereoFrames prev{}, curr{};
   DevTrackObs obs{};
   gfpl_frame_state* state = nullptr;
+  gfpl_prev_frames slim{};   // staging for gfpl_replay_upload_slim (allocated on first use)
   gfpl_line_cut* cut = nullptr;
   gfpl_pose_result* pose = nullptr;
   StepWork w{};
@@ -724,6 +725,43 @@ int gfpl_replay_upload(gfpl_replay* rp, const gfpl_stereo_frames* prev, const gf
   H2D(rp->prev.ln, prev->ln, pl); H2D(rp->prev.ldesc, prev->ldesc, pl * 32);
   H2D(rp->state, state, B);
   return GFPL_OK;
+}
+
+static int upload_raw_and_state(gfpl_replay* rp, const gfpl_frame_state* state, const gfpl_raw_frames* raw) {
+  gfpl_ctx* ctx = rp->ctx;
+  size_t B = rp->B, np = B * rp->cap_pt, nl = B * rp->cap_ln;
+  H2D(rp->raw.n_pt_l, raw->n_pt_l, B); H2D(rp->raw.n_pt_r, raw->n_pt_r, B);
+  H2D(rp->raw.n_ln_l, raw->n_ln_l, B); H2D(rp->raw.n_ln_r, raw->n_ln_r, B);
+  H2D(rp->raw.pt_l, raw->pt_l, np); H2D(rp->raw.pt_r, raw->pt_r, np);
+  H2D(rp->raw.pdesc_l, raw->pdesc_l, np * 32); H2D(rp->raw.pdesc_r, raw->pdesc_r, np * 32);
+  H2D(rp->raw.ln_l, raw->ln_l, nl); H2D(rp->raw.ln_r, raw->ln_r, nl);
+  H2D(rp->raw.ldesc_l, raw->ldesc_l, nl * 32); H2D(rp->raw.ldesc_r, raw->ldesc_r, nl * 32);
+  H2D(rp->state, state, B);
+  return GFPL_OK;
+}
+
+int gfpl_replay_upload_slim(gfpl_replay* rp, const gfpl_prev_frames* prev, const gfpl_frame_state* state,
+                            const gfpl_raw_frames* raw) {
+  if (!rp) return GFPL_E_INVALID;
+  gfpl_ctx* ctx = rp->ctx;
+  REQUIRE(ctx, prev && state && raw);
+  REQUIRE(ctx, prev->B == rp->B && raw->B == rp->B);
+  REQUIRE(ctx, prev->cap_pt == rp->prev.cap_pt && prev->cap_ln == rp->prev.cap_ln);
+  REQUIRE(ctx, raw->cap_pt == rp->cap_pt && raw->cap_ln == rp->cap_ln);
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  const size_t B = rp->B, pp = B * rp->prev.cap_pt, pl = B * rp->prev.cap_ln;
+  if (!rp->slim.pt) {
+    rp->slim.B = rp->B; rp->slim.cap_pt = rp->prev.cap_pt; rp->slim.cap_ln = rp->prev.cap_ln;
+    rp->slim.n_pt = rp->alloc<int32_t>(B); rp->slim.n_ln = rp->alloc<int32_t>(B);
+    rp->slim.pt = rp->alloc<gfpl_prev_point>(pp); rp->slim.ln = rp->alloc<gfpl_prev_line>(pl);
+    REQUIRE_MEM(ctx, rp->slim.n_pt && rp->slim.n_ln && rp->slim.pt && rp->slim.ln);
+  }
+  rp->h2d = 0;
+  H2D(rp->slim.n_pt, prev->n_pt, B); H2D(rp->slim.n_ln, prev->n_ln, B);
+  H2D(rp->slim.pt, prev->pt, pp); H2D(rp->slim.ln, prev->ln, pl);
+  H2D(rp->prev.pdesc, prev->pdesc, pp * 32); H2D(rp->prev.ldesc, prev->ldesc, pl * 32);
+  CHECK(upload_raw_and_state(rp, state, raw));
+  return launch_expand_prev(ctx, rp->slim, rp->prev);
 }
 
 int gfpl_replay_run(gfpl_replay* rp, int32_t flags) {

@@ -78,6 +78,7 @@ int launch_radius_fill(gfpl_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t
 int launch_stereo_accept(gfpl_ctx* ctx, const DevRawFrames& raw, int variant, Knn2Out pt_lr, Knn2Out pt_rl,
                          Knn2Out ln_lr, Knn2Out ln_rl, DevStereoFrames out);
 int launch_stereo_uncertainty(gfpl_ctx* ctx, const DevStereoFrames& fr, gfpl_line_cov* out);
+int launch_expand_prev(gfpl_ctx* ctx, const gfpl_prev_frames& slim_dev, DevStereoFrames fr);
 
 // f2f: fused radius + projection-gate search (hybrid points), knn-candidate variant, and accept loops
 int launch_f2f_hybrid_points(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr,

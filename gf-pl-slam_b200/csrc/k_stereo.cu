@@ -280,6 +280,42 @@ __global__ void __launch_bounds__(128) stereo_uncertainty_kernel(DevStereoFrames
   out[(size_t)p * fr.cap_ln + i] = c;
 }
 
+// slim previous-frame records -> full feature records (fields the tracking step does not read are zeroed)
+__global__ void __launch_bounds__(128) expand_prev_kernel(gfpl_prev_frames slim, DevStereoFrames fr) {
+  const int p = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < slim.n_pt[p]) {
+    const gfpl_prev_point s = slim.pt[(size_t)p * slim.cap_pt + i];
+    gfpl_point_feature f{};
+    f.P[0] = s.P[0]; f.P[1] = s.P[1]; f.P[2] = s.P[2];
+    f.sigma2 = s.sigma2;
+    f.idx = i; f.src_l = f.src_r = -1;
+    fr.pt[(size_t)p * fr.cap_pt + i] = f;
+  }
+  if (i < slim.n_ln[p]) {
+    const gfpl_prev_line s = slim.ln[(size_t)p * slim.cap_ln + i];
+    gfpl_line_feature f{};
+#pragma unroll
+    for (int k = 0; k < 3; k++) { f.sP[k] = s.sP[k]; f.eP[k] = s.eP[k]; }
+    f.spl[0] = s.spl[0]; f.spl[1] = s.spl[1]; f.epl[0] = s.epl[0]; f.epl[1] = s.epl[1];
+    f.sdisp = s.sdisp; f.edisp = s.edisp;
+    f.le[0] = s.le0;
+    f.sigma2 = s.sigma2;
+    f.idx = -1; f.src_l = f.src_r = -1;
+    fr.ln[(size_t)p * fr.cap_ln + i] = f;
+  }
+  if (i == 0) { fr.n_pt[p] = slim.n_pt[p]; fr.n_ln[p] = slim.n_ln[p]; }
+}
+
+int launch_expand_prev(gfpl_ctx* ctx, const gfpl_prev_frames& slim, DevStereoFrames fr) {
+  if (slim.B <= 0) return GFPL_OK;
+  const int cap = slim.cap_pt > slim.cap_ln ? slim.cap_pt : slim.cap_ln;
+  dim3 grid((cap + 127) / 128, slim.B);
+  expand_prev_kernel<<<grid, 128, 0, ctx->stream>>>(slim, fr);
+  GFPL_LAUNCH_OK(ctx);
+  return GFPL_OK;
+}
+
 int launch_stereo_uncertainty(gfpl_ctx* ctx, const DevStereoFrames& fr, gfpl_line_cov* out) {
   if (fr.B <= 0 || fr.cap_ln <= 0) return GFPL_OK;
   dim3 grid((fr.cap_ln + 127) / 128, fr.B);

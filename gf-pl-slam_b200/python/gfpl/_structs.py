@@ -65,6 +65,10 @@ pose_result_dt = np.dtype([("DT", "f8", 16), ("Tfw", "f8", 16), ("DT_cov", "f8",
                            ("n_inliers_pt", "i4"), ("n_inliers_ls", "i4"), ("iters_first", "i4"),
                            ("iters_ref", "i4")], align=True)
 
+prev_point_dt = np.dtype([("P", "f8", 3), ("sigma2", "f8")], align=True)
+prev_line_dt = np.dtype([("sP", "f8", 3), ("eP", "f8", 3), ("spl", "f8", 2), ("epl", "f8", 2), ("sdisp", "f8"),
+                         ("edisp", "f8"), ("le0", "f8"), ("sigma2", "f8")], align=True)
+assert prev_point_dt.itemsize == 32 and prev_line_dt.itemsize == 112
 assert keypoint_dt.itemsize == 16 and keyline_dt.itemsize == 32
 assert point_feature_dt.itemsize == 72 and line_feature_dt.itemsize == 152
 assert line_cov_dt.itemsize == 144 and pt_obs_dt.itemsize == 56 and ln_obs_dt.itemsize == 88
@@ -81,6 +85,11 @@ class RawFrames(C.Structure):
 
 
 class StereoFrames(C.Structure):
+    _fields_ = [("B", C.c_int32), ("cap_pt", C.c_int32), ("cap_ln", C.c_int32),
+                ("n_pt", _vp), ("n_ln", _vp), ("pt", _vp), ("pdesc", _vp), ("ln", _vp), ("ldesc", _vp)]
+
+
+class PrevFrames(C.Structure):
     _fields_ = [("B", C.c_int32), ("cap_pt", C.c_int32), ("cap_ln", C.c_int32),
                 ("n_pt", _vp), ("n_ln", _vp), ("pt", _vp), ("pdesc", _vp), ("ln", _vp), ("ldesc", _vp)]
 
@@ -195,6 +204,28 @@ class StereoFramesNP:
         out.pt[:], out.pdesc[:] = self.pt[:, :cap_pt], self.pdesc[:, :cap_pt]
         out.ln[:], out.ldesc[:] = self.ln[:, :cap_ln], self.ldesc[:, :cap_ln]
         return out
+
+
+class PrevFramesNP:
+    """slim previous-frame records (gfpl_prev_frames): what the tracking step reads of the previous stereo frame"""
+    _keys = ("n_pt", "n_ln", "pt", "pdesc", "ln", "ldesc")
+
+    def __init__(self, full, pinned=False):
+        self.B, self.cap_pt, self.cap_ln = full.B, full.cap_pt, full.cap_ln
+        a = lambda s, d: _alloc(s, d, pinned)
+        self.n_pt, self.n_ln = a(self.B, "i4"), a(self.B, "i4")
+        self.pt, self.pdesc = a((self.B, self.cap_pt), prev_point_dt), a((self.B, self.cap_pt, 32), "u1")
+        self.ln, self.ldesc = a((self.B, self.cap_ln), prev_line_dt), a((self.B, self.cap_ln, 32), "u1")
+        self.n_pt[:], self.n_ln[:] = full.n_pt, full.n_ln
+        self.pt["P"], self.pt["sigma2"] = full.pt["P"], full.pt["sigma2"]
+        self.pdesc[:], self.ldesc[:] = full.pdesc, full.ldesc
+        for k in ("sP", "eP", "spl", "epl", "sdisp", "edisp", "sigma2"):
+            self.ln[k] = full.ln[k]
+        self.ln["le0"] = full.ln["le"][..., 0]
+
+    def view(self):
+        return PrevFrames(self.B, self.cap_pt, self.cap_ln, ptr(self.n_pt), ptr(self.n_ln), ptr(self.pt),
+                          ptr(self.pdesc), ptr(self.ln), ptr(self.ldesc))
 
 
 class TrackObsNP:

@@ -258,6 +258,10 @@ class Replay:
         pv, rv = prev.view(), raw.view()
         self.ctx._check(lib().gfpl_replay_upload(self._h, C.byref(pv), _vp(state), C.byref(rv)))
 
+    def upload_slim(self, prev_slim, state, raw):
+        pv, rv = prev_slim.view(), raw.view()
+        self.ctx._check(lib().gfpl_replay_upload_slim(self._h, C.byref(pv), _vp(state), C.byref(rv)))
+
     def run(self, flags):
         self.ctx._check(lib().gfpl_replay_run(self._h, flags))
 

@@ -193,6 +193,29 @@ typedef struct gfpl_line_cut {
   double sdisp, edisp;
 } gfpl_line_cut;
 
+/* The fields of a PREVIOUS frame's stereo features that the tracking step reads (f2f matching: P, sigma2, descriptor;
+ * line uncertainty / cut / GN: sP, eP, spl, epl, sdisp, edisp, le[0], sigma2).  A streaming replay uploads these slim
+ * records instead of the full gfpl_point_feature / gfpl_line_feature (32 B vs 72 B, 112 B vs 152 B per feature). */
+typedef struct gfpl_prev_point {
+  double P[3];
+  double sigma2;
+} gfpl_prev_point;
+typedef struct gfpl_prev_line {
+  double sP[3], eP[3];
+  double spl[2], epl[2];
+  double sdisp, edisp;
+  double le0;     /* le[0]: selects ratioDispSTD vs ratioDispSTDHor (stereoFrame.cpp:1462) */
+  double sigma2;
+} gfpl_prev_line;
+typedef struct gfpl_prev_frames {
+  int32_t B, cap_pt, cap_ln;
+  const int32_t *n_pt, *n_ln;    /* [B] */
+  const gfpl_prev_point* pt;     /* [B][cap_pt] */
+  const uint8_t* pdesc;          /* [B][cap_pt][32] */
+  const gfpl_prev_line* ln;      /* [B][cap_ln] */
+  const uint8_t* ldesc;          /* [B][cap_ln][32] */
+} gfpl_prev_frames;
+
 /* prev_frame->{Tfw,DT,DT_cov,Tfw_cov,time_stamp} (stereoFrame.h:212-221) + curr time stamp */
 typedef struct gfpl_frame_state {
   double Tfw[16];
@@ -396,6 +419,10 @@ void gfpl_replay_destroy(gfpl_replay* rp);
 /* async H2D of the step inputs on the context stream (pinned host memory recommended) */
 int gfpl_replay_upload(gfpl_replay* rp, const gfpl_stereo_frames* prev, const gfpl_frame_state* state,
                        const gfpl_raw_frames* curr_raw);
+/* same with slim previous-frame records (capacities = the prev capacities of gfpl_replay_create_ex); they are
+ * expanded to full feature records on the device */
+int gfpl_replay_upload_slim(gfpl_replay* rp, const gfpl_prev_frames* prev, const gfpl_frame_state* state,
+                            const gfpl_raw_frames* curr_raw);
 /* launch the whole step on the resident inputs (asynchronous; no host synchronisation inside) */
 int gfpl_replay_run(gfpl_replay* rp, int32_t flags);
 /* async D2H of the per-pair pose records (pose: [B]); obs/cut/curr optional (NULL to skip) */

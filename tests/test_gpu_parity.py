@@ -401,6 +401,13 @@ def test_replay_with_packed_previous_frames(ctx, orc):
     rp.download(pose)
     ctx.sync()
     assert pose.tobytes() == pg.tobytes()
+    # slim previous-frame records (gfpl_replay_upload_slim) give the same poses as well
+    rp.upload_slim(S.PrevFramesNP(packed), d["state"], d["curr_raw"])
+    rp.run(flags)
+    pose2 = np.zeros(32, S.pose_result_dt)
+    rp.download(pose2)
+    ctx.sync()
+    assert pose2.tobytes() == pg.tobytes()
 
 
 def test_linecut_decisions_exact_at_scale(ctx, orc):
