@@ -426,3 +426,64 @@ def test_linecut_decisions_exact_at_scale(ctx, orc):
     assert diff.sum() == 0, f"{diff.sum()} of {mask.sum()} lines with a different cut decision"
     assert close(cg["invCovPose"][mask], co["invCovPose"][mask])
     assert close(og.ln["sP"][mask], oo.ln["sP"][mask]) and close(og.ln["eP"][mask], oo.ln["eP"][mask])
+
+
+def test_track_dense_c4_and_kitti_shapes(orc):
+    """BASELINE configs[3] (2000 ORB + 500 lines per image) and the KITTI-shaped camera of configs[2], whole step"""
+    from gfpl import api
+    flags = S.TRACK_LINECUT | S.TRACK_SEED_GIVEN
+    for shape, n_pt, n_ln, B in (("euroc", 2000, 500, 3), ("kitti", 300, 100, 6)):
+        d = synth.make_pairs(B, n_pt=n_pt, n_ln=n_ln, shape=shape, seed=77)
+        c = api.Context(0, cam=d["cam"])
+        prev = orc.stereo_match(d["cam"], c.cfg, d["prev_raw"])
+        cg, og, kg, pg = c.track(prev, d["state"], d["curr_raw"], flags)
+        co, oo, ko, po = orc.track(d["cam"], c.cfg, prev, d["state"], d["curr_raw"], flags)
+        _cmp_stereo(cg, co)
+        assert np.array_equal(og.n_pt, oo.n_pt) and np.array_equal(og.n_ln, oo.n_ln)
+        assert (og.n_pt <= c.cfg.max_point_match_num).all() and (og.n_ln <= c.cfg.max_line_match_num).all()
+        if n_pt == 2000:
+            assert (og.n_pt == 500).all()                   # the 500-match budget of Config::maxPointMatchNum binds
+        for p in range(B):
+            assert np.array_equal(og.pt_inlier[p, :og.n_pt[p]], oo.pt_inlier[p, :oo.n_pt[p]])
+            assert np.array_equal(og.ln_inlier[p, :og.n_ln[p]], oo.ln_inlier[p, :oo.n_ln[p]])
+            assert np.array_equal(kg["cutRatio"][p, :og.n_ln[p]], ko["cutRatio"][p, :oo.n_ln[p]])
+        _cmp_pose(pg, po, B)
+
+
+def test_full_batch_properties(ctx):
+    """8192-pair replay (BASELINE configs[4]): size-independent properties — every pose is a rigid transform, Tfw
+    composes, the recovered motion is close to the simulated one, covariances are symmetric PSD, and a second
+    replay object fed the same inputs reproduces the records bit for bit (checksum of checksums)."""
+    from gfpl import api
+    import zlib
+    B = 8192
+    d = _data(B, 4242)
+    flags = S.TRACK_LINECUT | S.TRACK_SEED_GIVEN
+    prev = S.StereoFramesNP(B, 300, 100)
+    for lo in range(0, B, 2048):
+        part = ctx.stereo_match(d["prev_raw"].slice(lo, lo + 2048))
+        for k in S.StereoFramesNP._keys:
+            getattr(prev, k)[lo:lo + 2048] = getattr(part, k)
+    sums = []
+    for _ in range(2):
+        rp = api.Replay(ctx, B, 300, 100)
+        rp.upload(prev, d["state"], d["curr_raw"])
+        rp.run(flags)
+        pose = np.zeros(B, S.pose_result_dt)
+        rp.download(pose)
+        ctx.sync()
+        sums.append(zlib.crc32(np.array([zlib.crc32(pose[i].tobytes()) for i in range(B)], np.uint32).tobytes()))
+        rp.close()
+    assert sums[0] == sums[1]
+    ok = pose["status"] == 0
+    assert ok.mean() > 0.995
+    DT = pose["DT"].reshape(B, 4, 4)[ok]
+    R = DT[:, :3, :3]
+    assert np.abs(R @ R.transpose(0, 2, 1) - np.eye(3)).max() < 1e-9 and np.allclose(np.linalg.det(R), 1.0, atol=1e-9)
+    Tfw = pose["Tfw"].reshape(B, 4, 4)[ok]
+    assert np.abs(Tfw - d["state"]["Tfw"].reshape(B, 4, 4)[ok] @ DT).max() < 1e-9
+    err = np.abs(np.linalg.inv(DT) - d["DT_true"][ok]).max(axis=(1, 2))
+    assert np.median(err) < 5e-3 and (err < 5e-2).mean() > 0.99
+    cov = pose["DT_cov"].reshape(B, 6, 6)[ok]
+    assert np.abs(cov - cov.transpose(0, 2, 1)).max() <= 1e-9 * np.abs(cov).max()
+    assert (pose["DT_cov_eig"][ok][:, 0] > -1e-12).all()
