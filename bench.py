@@ -280,6 +280,12 @@ def main():
         alg_bytes = B * (2 * a.n_pt * 32 + 2 * a.n_pt * 16) if dom == 0 else None
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] \
             if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        traffic = None   # dram__bytes_read+write per launch of the dominant kernel, from the committed ncu --set full capture
+        tj = os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")
+        if os.path.exists(tj) and dom == 0 and B == 8192 and a.n_pt == 300:
+            t = json.load(open(tj))["per_launch"].get("knn2_kernel<6, 2>@16384")
+            if t:
+                traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
         roofline = {"bound": "alu", "pipe": "INT POPC pipe (16 lanes/clk/SM) + INT ALU pipe; not HBM-, not tensor-bound",
                     "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "T pairs/s (256-bit Hamming distances)",
                     "frac": achieved / peak,
@@ -288,7 +294,9 @@ def main():
                     "measured_pipe_peaks": {"popc_Tops": popc_peak, "alu_lop3_Tops": alu_peak},
                     "popc_equivalent": {"achieved_Tpopc": 8.0 * achieved, "frac_of_popc_peak": 8.0 * achieved / popc_peak,
                                         "note": "8 popc per pair is the naive algorithmic count; the kernel issues 5 (carry-save)"},
-                    "kernel_ms": k_ms[dom], "pairs_per_launch": pairs[dom], "traffic": None,
+                    "kernel_ms": k_ms[dom], "pairs_per_launch": pairs[dom], "traffic": traffic,
+                    "traffic_note": "bytes; DRAM read+write of one launch from profiles/r1_ncu_full_summary.md (same workload); "
+                                    "algorithmic bytes of the launch = %d" % (alg_bytes or 0),
                     "hbm": {"achieved_GBps": (alg_bytes / (k_ms[dom] * 1e-3) / 1e9) if alg_bytes else None,
                             "peak_GBps": hbm_peak, "note": "algorithmic bytes of this launch; shows the kernel is not HBM-bound"},
                     "all_matching_kernels_Tpairs": sum(pairs) / (sum(k_ms) * 1e-3) / 1e12}

@@ -496,6 +496,35 @@ int gfpl_f2f_match(gfpl_ctx* ctx, const gfpl_stereo_frames* prev, const gfpl_ste
   return finish(ctx);
 }
 
+int gfpl_kf_match(gfpl_ctx* ctx, const gfpl_stereo_frames* kf0, const gfpl_stereo_frames* kf1, const double* DT,
+                  gfpl_track_obs* out) {
+  if (!ctx) return GFPL_E_INVALID;
+  REQUIRE(ctx, kf0 && kf1 && DT && out && kf0->B == kf1->B && kf0->B == out->B && kf0->B >= 0);
+  REQUIRE(ctx, out->cap_pt > 0 && out->cap_ln > 0);
+  if (kf0->B == 0) return GFPL_OK;
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DevMem m(ctx);
+  DevStereoFrames d0, d1;
+  DevTrackObs dobs;
+  StepWork w;
+  const int B = kf0->B;
+  const int cp = kf0->cap_pt > kf1->cap_pt ? kf0->cap_pt : kf1->cap_pt;
+  const int cl = kf0->cap_ln > kf1->cap_ln ? kf0->cap_ln : kf1->cap_ln;
+  REQUIRE_MEM(ctx, mirror_stereo(m, kf0, &d0) && mirror_stereo(m, kf1, &d1) &&
+                       alloc_obs(m, B, out->cap_pt, out->cap_ln, &dobs) && alloc_work(m, B, cp, cl, &w));
+  double* dDT = m.upload(DT, (size_t)B * 16);
+  REQUIRE_MEM(ctx, dDT);
+  if (ctx->cfg.has_points)
+    CHECK(launch_knn2(ctx, B, d0.pdesc, d0.n_pt, d0.cap_pt, d1.pdesc, d1.n_pt, d1.cap_pt, GFPL_NORM_HAMMING, w.pt_12,
+                      ctx->cfg.best_lr_matches ? w.pt_21 : Knn2Out{}));
+  if (ctx->cfg.has_lines)
+    CHECK(launch_knn2(ctx, B, d0.ldesc, d0.n_ln, d0.cap_ln, d1.ldesc, d1.n_ln, d1.cap_ln, GFPL_NORM_HAMMING, w.ln_12,
+                      ctx->cfg.best_lr_matches ? w.ln_21 : Knn2Out{}));
+  CHECK(launch_kf_accept(ctx, d0, d1, dDT, w.pt_12, w.pt_21, w.ln_12, w.ln_21, dobs));
+  download_obs(ctx, out, dobs);
+  return finish(ctx);
+}
+
 int gfpl_linecut_submodular(gfpl_ctx* ctx, const double* DT_inv, gfpl_track_obs* obs, const gfpl_line_cov* prev_cov,
                             int32_t cov_cap, gfpl_line_cut* cut) {
   if (!ctx) return GFPL_E_INVALID;

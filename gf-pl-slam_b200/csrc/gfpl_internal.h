@@ -89,6 +89,9 @@ int launch_f2f_accept(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStere
                       const uint32_t* best_key, Knn2Out pt_12, Knn2Out pt_21, Knn2Out ln_12, Knn2Out ln_21,
                       DevTrackObs out);
 
+int launch_kf_accept(gfpl_ctx* ctx, const DevStereoFrames& kf0, const DevStereoFrames& kf1, const double* DT, Knn2Out pt_12,
+                     Knn2Out pt_21, Knn2Out ln_12, Knn2Out ln_21, DevTrackObs out);
+
 // K5: line cut.  DT_inv may be NULL: then it is formed from `state` (curr->Tfw^-1 * prev->Tfw with the
 // predicted curr->Tfw = prev->Tfw * prev->DT).
 int launch_linecut(gfpl_ctx* ctx, const double* DT_inv, const gfpl_frame_state* state, DevTrackObs obs,

@@ -367,6 +367,119 @@ f2f_accept_kernel(DevStereoFrames prev, DevStereoFrames curr, int mode, const ui
   }
 }
 
+// ---- KF <-> KF accept loop of MapHandler::lookForCommonMatches (mapHandler.cpp:245-337, 377-489) ---------------------
+// mutual check + ratio / MAD gap test + chi-square reprojection gate; accepted pairs in ascending kf0 index.
+__global__ void __launch_bounds__(ACC_THREADS)
+kf_accept_kernel(DevStereoFrames kf0, DevStereoFrames kf1, const double* __restrict__ DT_all, Knn2Out pt_12, Knn2Out pt_21,
+                 Knn2Out ln_12, Knn2Out ln_21, DevTrackObs out, gfpl_camera cam, gfpl_config cfg) {
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  float* s_v = reinterpret_cast<float*>(s_dyn);  // [kf0.cap_ln]
+  __shared__ int s_warp[ACC_THREADS / 32 + 1];
+  __shared__ float s_sel;
+  __shared__ double s_DT[16];
+  const int p = blockIdx.x;
+  const size_t op = (size_t)p * out.cap_pt, ol = (size_t)p * out.cap_ln;
+  if (threadIdx.x < 16) s_DT[threadIdx.x] = DT_all[(size_t)p * 16 + threadIdx.x];
+  __syncthreads();
+  const double chi = sqrt(7.815);
+  {
+    const int n0 = kf0.n_pt[p], n1 = kf1.n_pt[p];
+    int base = 0;
+    if (cfg.has_points && n0 >= 2 && n1 >= 2) {  // D3
+      for (int i0 = 0; i0 < n0; i0 += ACC_THREADS) {
+        const int i = i0 + threadIdx.x;
+        bool keep = false;
+        int tdx = 0;
+        if (i < n0) {
+          const int2 mi = pt_12.idx[(size_t)p * kf0.cap_pt + i];
+          const float2 md = pt_12.dist[(size_t)p * kf0.cap_pt + i];
+          tdx = mi.x;
+          const int rl = cfg.best_lr_matches ? pt_21.idx[(size_t)p * kf1.cap_pt + tdx].x : i;
+          const double dist_12 = (double)(md.x / md.y);
+          if (i == rl && dist_12 <= cfg.max_ratio_12_p) {
+            const gfpl_point_feature& f0 = kf0.pt[(size_t)p * kf0.cap_pt + i];
+            const gfpl_point_feature& f1 = kf1.pt[(size_t)p * kf1.cap_pt + tdx];
+            double P_[3], uv[2];
+            se3_apply(s_DT, f0.P, P_);
+            projection(cam, P_, uv);
+            const double dx = uv[0] - f1.pl[0], dy = uv[1] - f1.pl[1];
+            keep = sqrt(dx * dx + dy * dy) * sqrt(f0.sigma2) < chi;
+          }
+        }
+        const int slot = block_compact_acc(keep, base, s_warp);
+        if (keep && slot < out.cap_pt) {
+          write_pt_obs(kf0, kf1, p, i, tdx, &out.pt[op + slot]);
+          out.pt_inlier[op + slot] = 1;
+        }
+      }
+      base = min(base, out.cap_pt);
+    }
+    if (threadIdx.x == 0) out.n_pt[p] = base;
+    __syncthreads();
+  }
+  {
+    const int n0 = kf0.n_ln[p], n1 = kf1.n_ln[p];
+    int base = 0;
+    if (cfg.has_lines && n0 >= 2 && n1 >= 2) {  // D3
+      for (int jx = threadIdx.x; jx < n0; jx += ACC_THREADS) {
+        const float2 md = ln_12.dist[(size_t)p * kf0.cap_ln + jx];
+        s_v[jx] = fabsf((float)((double)(md.y - md.x) - cfg.mad_uninit_value));
+      }
+      __syncthreads();
+      const float med = block_select_acc(s_v, n0, n0 / 2, &s_sel);
+      const double nn12_dist_th = (1.4826 * (double)med) * cfg.desc_th_l;
+      for (int i0 = 0; i0 < n0; i0 += ACC_THREADS) {
+        const int i = i0 + threadIdx.x;
+        bool keep = false;
+        int tdx = 0;
+        if (i < n0) {
+          const int2 mi = ln_12.idx[(size_t)p * kf0.cap_ln + i];
+          const float2 md = ln_12.dist[(size_t)p * kf0.cap_ln + i];
+          tdx = mi.x;
+          const int rl = cfg.best_lr_matches ? ln_21.idx[(size_t)p * kf1.cap_ln + tdx].x : i;
+          const double dist_12 = (double)(md.y - md.x);
+          if (i == rl && dist_12 > nn12_dist_th) {
+            const gfpl_line_feature& f0 = kf0.ln[(size_t)p * kf0.cap_ln + i];
+            double sP_[3], eP_[3], sp[2], ep[2];
+            se3_apply(s_DT, f0.sP, sP_);
+            projection(cam, sP_, sp);
+            se3_apply(s_DT, f0.eP, eP_);
+            projection(cam, eP_, ep);
+            const double e0 = f0.le[0] * sp[0] + f0.le[1] * sp[1] + f0.le[2];   // kf0's own line equation (:398)
+            const double e1 = f0.le[0] * ep[0] + f0.le[1] * ep[1] + f0.le[2];
+            keep = sqrt(e0 * e0 + e1 * e1) * sqrt(f0.sigma2) < chi;
+          }
+        }
+        const int slot = block_compact_acc(keep, base, s_warp);
+        if (keep && slot < out.cap_ln) {
+          const gfpl_line_feature& f0 = kf0.ln[(size_t)p * kf0.cap_ln + i];
+          const gfpl_line_feature& f1 = kf1.ln[(size_t)p * kf1.cap_ln + tdx];
+          gfpl_ln_obs o;
+#pragma unroll
+          for (int k = 0; k < 3; k++) { o.sP[k] = f0.sP[k]; o.eP[k] = f0.eP[k]; o.le_obs[k] = f1.le[k]; }
+          o.sigma2 = f0.sigma2;
+          o.prev_idx = i; o.curr_idx = tdx;
+          out.ln[ol + slot] = o;
+          out.ln_inlier[ol + slot] = 1;
+        }
+      }
+      base = min(base, out.cap_ln);
+    }
+    if (threadIdx.x == 0) out.n_ln[p] = base;
+  }
+}
+
+int launch_kf_accept(gfpl_ctx* ctx, const DevStereoFrames& kf0, const DevStereoFrames& kf1, const double* DT, Knn2Out pt_12,
+                     Knn2Out pt_21, Knn2Out ln_12, Knn2Out ln_21, DevTrackObs out) {
+  if (kf0.B <= 0) return GFPL_OK;
+  const size_t smem = (size_t)(kf0.cap_ln > 0 ? kf0.cap_ln : 1) * 4;
+  if (smem > 48 * 1024)
+    GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(kf_accept_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kf_accept_kernel<<<kf0.B, ACC_THREADS, smem, ctx->stream>>>(kf0, kf1, DT, pt_12, pt_21, ln_12, ln_21, out, ctx->cam, ctx->cfg);
+  GFPL_LAUNCH_OK(ctx);
+  return GFPL_OK;
+}
+
 int launch_f2f_accept(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr, int mode,
                       const uint32_t* best_key, Knn2Out pt_12, Knn2Out pt_21, Knn2Out ln_12, Knn2Out ln_21,
                       DevTrackObs out) {

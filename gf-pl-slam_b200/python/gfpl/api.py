@@ -184,6 +184,14 @@ class Context:
         self._check(lib().gfpl_f2f_match(self._h, C.byref(pv), C.byref(cv), _vp(state), mode, C.byref(ov)))
         return out
 
+    def kf_match(self, kf0, kf1, DT):
+        """KF<->KF matching of MapHandler::lookForCommonMatches (matching + gates)"""
+        out = S.TrackObsNP(kf0.B, kf0.cap_pt, kf0.cap_ln)
+        DT = np.ascontiguousarray(DT, np.float64)
+        v0, v1, ov = kf0.view(), kf1.view(), out.view()
+        self._check(lib().gfpl_kf_match(self._h, C.byref(v0), C.byref(v1), _vp(DT), C.byref(ov)))
+        return out
+
     # ---- C1-C5 ----
     def linecut(self, DT_inv, obs, prev_cov):
         """obs is updated in place (sP/eP of cut lines); returns gfpl_line_cut records."""

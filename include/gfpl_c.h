@@ -357,6 +357,15 @@ int gfpl_stereo_uncertainty(gfpl_ctx* ctx, const gfpl_stereo_frames* frames, gfp
 int gfpl_f2f_match(gfpl_ctx* ctx, const gfpl_stereo_frames* prev, const gfpl_stereo_frames* curr,
                    const gfpl_frame_state* state /*[B]*/, int32_t mode, gfpl_track_obs* out);
 
+/* Key-frame to key-frame matching of MapHandler::lookForCommonMatches (mapHandler.cpp:211-490):
+ * knn k=2 both ways (NORM_HAMMING), mutual check, ratio test (points) / MAD gap test (lines), and the chi-square
+ * reprojection gate  error * sqrt(sigma2) < sqrt(7.815)  with DT = inverse_se3(kf1->T_kf_w) * kf0->T_kf_w
+ * (:197, row-major [B][16]).  out: accepted pairs in ascending kf0 index (prev_idx = kf0 index, curr_idx = kf1
+ * index; P/sP/eP/sigma2 from kf0, pl_obs/le_obs from kf1); out->cap_pt >= kf0->cap_pt, out->cap_ln >= kf0->cap_ln.
+ * The map bookkeeping that follows each accepted pair (new MapPoint / MapLine, graphs) stays on the host. */
+int gfpl_kf_match(gfpl_ctx* ctx, const gfpl_stereo_frames* kf0, const gfpl_stereo_frames* kf1,
+                  const double* DT /*[B][16]*/, gfpl_track_obs* out);
+
 /* ------------------------------------------------------------------------- */
 /* C1-C5 — good line cutting                                                  */
 /* ------------------------------------------------------------------------- */

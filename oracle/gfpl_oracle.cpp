@@ -562,6 +562,92 @@ extern "C" int orc_f2f_match(const gfpl_camera* cam, const gfpl_config* cfg, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// KF <-> KF matching of MapHandler::lookForCommonMatches (mapHandler.cpp:211-490), matching + gates only
+// ------------------------------------------------------------------------------------------------
+static void kf_match_one(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_stereo_frames* kf0,
+                         const gfpl_stereo_frames* kf1, const double* DT, gfpl_track_obs* out, int p) {
+  const size_t p0 = (size_t)p * kf0->cap_pt, l0 = (size_t)p * kf0->cap_ln;
+  const size_t p1 = (size_t)p * kf1->cap_pt, l1 = (size_t)p * kf1->cap_ln;
+  const size_t op = (size_t)p * out->cap_pt, ol = (size_t)p * out->cap_ln;
+  const double chi = std::sqrt(7.815);
+  int npt = 0, nln = 0;
+  {
+    const int n0 = kf0->n_pt[p], n1 = kf1->n_pt[p];
+    const gfpl_point_feature* f0 = kf0->pt + p0;
+    const gfpl_point_feature* f1 = kf1->pt + p1;
+    if (cfg->has_points && n0 >= 2 && n1 >= 2) {  // D3
+      std::vector<Knn2> m12, m21;
+      knn2_set(kf0->pdesc + p0 * 32, n0, kf1->pdesc + p1 * 32, n1, GFPL_NORM_HAMMING, m12);  // :213
+      if (cfg->best_lr_matches) knn2_set(kf1->pdesc + p1 * 32, n1, kf0->pdesc + p0 * 32, n0, GFPL_NORM_HAMMING, m21);
+      for (int i = 0; i < n0; i++) {
+        const int lr_qdx = i, lr_tdx = m12[i].i0;
+        const int rl_tdx = cfg->best_lr_matches ? m21[lr_tdx].i0 : lr_qdx;
+        const double dist_12 = m12[i].d0 / m12[i].d1;  // float / float (:257)
+        if (lr_qdx == rl_tdx && dist_12 <= cfg->max_ratio_12_p) {
+          double P_[3], uv[2];
+          se3_apply(DT, f0[lr_qdx].P, P_);
+          projection(cam, P_, uv);
+          const double dx = uv[0] - f1[lr_tdx].pl[0], dy = uv[1] - f1[lr_tdx].pl[1];
+          const double error = std::sqrt(dx * dx + dy * dy) * std::sqrt(f0[lr_qdx].sigma2);  // :264
+          if (error < chi) {
+            if (npt < out->cap_pt) fill_pt_obs(out->pt[op + npt], f0, f1, lr_qdx, lr_tdx);
+            npt++;
+          }
+        }
+      }
+    }
+  }
+  {
+    const int n0 = kf0->n_ln[p], n1 = kf1->n_ln[p];
+    const gfpl_line_feature* f0 = kf0->ln + l0;
+    const gfpl_line_feature* f1 = kf1->ln + l1;
+    if (cfg->has_lines && n0 >= 2 && n1 >= 2) {  // D3
+      std::vector<Knn2> m12, m21;
+      knn2_set(kf0->ldesc + l0 * 32, n0, kf1->ldesc + l1 * 32, n1, GFPL_NORM_HAMMING, m12);  // :345
+      if (cfg->best_lr_matches) knn2_set(kf1->ldesc + l1 * 32, n1, kf0->ldesc + l0 * 32, n0, GFPL_NORM_HAMMING, m21);
+      std::vector<float> d(2 * (size_t)n0);
+      for (int i = 0; i < n0; i++) { d[2 * i] = m12[i].d0; d[2 * i + 1] = m12[i].d1; }
+      const double nn12_dist_th = orc_line_descriptor_mad(d.data(), n0, cfg->mad_uninit_value) * cfg->desc_th_l;  // :370-371
+      for (int i = 0; i < n0; i++) {
+        const int lr_qdx = i, lr_tdx = m12[i].i0;
+        const int rl_tdx = cfg->best_lr_matches ? m21[lr_tdx].i0 : lr_qdx;
+        const double dist_12 = m12[i].d1 - m12[i].d0;
+        if (lr_qdx == rl_tdx && dist_12 > nn12_dist_th) {
+          double sP_[3], eP_[3], sp[2], ep[2];
+          se3_apply(DT, f0[lr_qdx].sP, sP_);
+          projection(cam, sP_, sp);
+          se3_apply(DT, f0[lr_qdx].eP, eP_);
+          projection(cam, eP_, ep);
+          const double* l_obs = f0[lr_qdx].le;  // :398 — the reference measures against kf0's OWN line equation
+          const double e0 = l_obs[0] * sp[0] + l_obs[1] * sp[1] + l_obs[2];
+          const double e1 = l_obs[0] * ep[0] + l_obs[1] * ep[1] + l_obs[2];
+          if (std::sqrt(e0 * e0 + e1 * e1) * std::sqrt(f0[lr_qdx].sigma2) < chi) {  // :403
+            if (nln < out->cap_ln) {
+              gfpl_ln_obs& o = out->ln[ol + nln];
+              for (int k = 0; k < 3; k++) { o.sP[k] = f0[lr_qdx].sP[k]; o.eP[k] = f0[lr_qdx].eP[k]; o.le_obs[k] = f1[lr_tdx].le[k]; }
+              o.sigma2 = f0[lr_qdx].sigma2;
+              o.prev_idx = lr_qdx; o.curr_idx = lr_tdx;
+            }
+            nln++;
+          }
+        }
+      }
+    }
+  }
+  out->n_pt[p] = std::min(npt, out->cap_pt);
+  out->n_ln[p] = std::min(nln, out->cap_ln);
+  for (int k = 0; k < out->n_pt[p]; k++) out->pt_inlier[op + k] = 1;
+  for (int k = 0; k < out->n_ln[p]; k++) out->ln_inlier[ol + k] = 1;
+}
+
+extern "C" int orc_kf_match(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_stereo_frames* kf0,
+                            const gfpl_stereo_frames* kf1, const double* DT, gfpl_track_obs* out) {
+  if (!cam || !cfg || !kf0 || !kf1 || !DT || !out) return GFPL_E_INVALID;
+  for (int p = 0; p < kf0->B; p++) kf_match_one(cam, cfg, kf0, kf1, DT + (size_t)p * 16, out, p);
+  return GFPL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // C2-C5: good line cutting
 // ------------------------------------------------------------------------------------------------
 // the 6-vector both optimizeFunctions and getPoseInfoOnLine build (stereoFrameHandler.cpp:1383-1388, 2150-2155)

@@ -33,6 +33,8 @@ int orc_stereo_uncertainty(const gfpl_camera* cam, const gfpl_config* cfg, const
                            gfpl_line_cov* out);
 int orc_f2f_match(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_stereo_frames* prev,
                   const gfpl_stereo_frames* curr, const gfpl_frame_state* state, int32_t mode, gfpl_track_obs* out);
+int orc_kf_match(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_stereo_frames* kf0,
+                 const gfpl_stereo_frames* kf1, const double* DT, gfpl_track_obs* out);
 int orc_linecut_submodular(const gfpl_camera* cam, const gfpl_config* cfg, const double* DT_inv, gfpl_track_obs* obs,
                            const gfpl_line_cov* prev_cov, int32_t cov_cap, gfpl_line_cut* cut);
 /* single evaluation of getPoseInfoOnLine / getPoseInfoPoint / logdet / min-eigenvalue (unit tests) */

@@ -118,6 +118,15 @@ def f2f_match(cam, cfg, prev, curr, state, mode=S.F2F_HYBRID):
     return out
 
 
+def kf_match(cam, cfg, kf0, kf1, DT):
+    out = S.TrackObsNP(kf0.B, kf0.cap_pt, kf0.cap_ln)
+    DT = np.ascontiguousarray(DT, np.float64)
+    v0, v1, ov = kf0.view(), kf1.view(), out.view()
+    rc = lib().orc_kf_match(C.byref(cam), C.byref(cfg), C.byref(v0), C.byref(v1), C.c_void_p(S.ptr(DT)), C.byref(ov))
+    assert rc == 0, rc
+    return out
+
+
 def linecut(cam, cfg, DT_inv, obs, prev_cov):
     """obs is updated in place (sP/eP of cut lines); returns the gfpl_line_cut records."""
     cut = np.zeros((obs.B, obs.cap_ln), S.line_cut_dt)

@@ -487,3 +487,17 @@ def test_full_batch_properties(ctx):
     cov = pose["DT_cov"].reshape(B, 6, 6)[ok]
     assert np.abs(cov - cov.transpose(0, 2, 1)).max() <= 1e-9 * np.abs(cov).max()
     assert (pose["DT_cov_eig"][ok][:, 0] > -1e-12).all()
+
+
+def test_kf_match_lookForCommonMatches(ctx, orc):
+    """KF<->KF matching + chi-square gates of MapHandler::lookForCommonMatches (mapHandler.cpp:211-490)"""
+    d = _data(12, 1300, ragged=True)
+    kf0, kf1 = _frames(orc, ctx.cfg, d)
+    rng = np.random.default_rng(5)
+    DT = d["DT_true"].copy()
+    DT[:, :3, 3] += rng.normal(0, 0.01, (12, 3))          # imperfect relative pose: the gate rejects some pairs
+    g = ctx.kf_match(kf0, kf1, DT.reshape(-1, 16))
+    o = orc.kf_match(d["cam"], ctx.cfg, kf0, kf1, DT.reshape(-1, 16))
+    # (the line gate compares the re-projected kf0 line with kf0's OWN 2-D line, mapHandler.cpp:398: few lines survive motion)
+    assert (o.n_pt > 50).all() and o.n_ln.sum() > 10 and (o.n_pt < kf0.n_pt).all()
+    _cmp_obs(g, o)
