@@ -111,6 +111,134 @@ static bool solve_dense(int n, vector<double>& A, vector<double>& B, int nrhs) {
   return ok;
 }
 
+// ---- lookForCommonMatches, KF <-> KF half (mapHandler.cpp:189-490) ---------------------------------------------
+static Vector3d transform_point(const Matrix4d& T, const Vector3d& P) {
+  Vector3d r;
+  for (int i = 0; i < 3; i++) r(i) = T(i, 0) * P(0) + T(i, 1) * P(1) + T(i, 2) * P(2) + T(i, 3);
+  return r;
+}
+static Vector3d normalized(const Vector3d& v) {
+  const double n = std::sqrt(v(0) * v(0) + v(1) * v(1) + v(2) * v(2));
+  Vector3d r;
+  for (int i = 0; i < 3; i++) r(i) = v(i) / n;
+  return r;
+}
+
+void MapHandler::lookForCommonMatches(KeyFrame* kf0, KeyFrame*& kf1) {
+  const int kf0_idx = kf0->kf_idx, kf1_idx = kf1->kf_idx;
+  const Matrix4d DT = inverse_se3(kf1->T_kf_w) * kf0->T_kf_w;   // :197
+  StVO::StereoFrame* f0 = kf0->stereo_frame;
+  StVO::StereoFrame* f1 = kf1->stereo_frame;
+  const int need = std::max(kf0_idx, kf1_idx) + 1;
+  if ((int)full_graph.size() < need) {
+    full_graph.resize(need);
+    map_points_kf_idx.resize(need);
+    map_lines_kf_idx.resize(need);
+  }
+  for (auto& row : full_graph) row.resize(full_graph.size(), 0);
+
+  // ---- matching + gates on the GPU ------------------------------------------------------------------
+  vector<gfpl_point_feature> p0, p1;
+  vector<gfpl_line_feature> l0, l1;
+  f0->exportStereo(p0, l0);
+  f1->exportStereo(p1, l1);
+  int32_t n0[2] = {(int32_t)f0->stereo_pt.size(), (int32_t)f0->stereo_ls.size()};
+  int32_t n1[2] = {(int32_t)f1->stereo_pt.size(), (int32_t)f1->stereo_ls.size()};
+  vector<uint8_t> pd0(p0.size() * 32), ld0(l0.size() * 32), pd1(p1.size() * 32), ld1(l1.size() * 32);
+  if (n0[0]) std::memcpy(pd0.data(), f0->pdesc_l.ptr(), (size_t)n0[0] * 32);
+  if (n0[1]) std::memcpy(ld0.data(), f0->ldesc_l.ptr(), (size_t)n0[1] * 32);
+  if (n1[0]) std::memcpy(pd1.data(), f1->pdesc_l.ptr(), (size_t)n1[0] * 32);
+  if (n1[1]) std::memcpy(ld1.data(), f1->ldesc_l.ptr(), (size_t)n1[1] * 32);
+  gfpl_stereo_frames v0{1, (int32_t)p0.size(), (int32_t)l0.size(), &n0[0], &n0[1], p0.data(), pd0.data(), l0.data(), ld0.data()};
+  gfpl_stereo_frames v1{1, (int32_t)p1.size(), (int32_t)l1.size(), &n1[0], &n1[1], p1.data(), pd1.data(), l1.data(), ld1.data()};
+  vector<gfpl_pt_obs> opt(p0.size());
+  vector<gfpl_ln_obs> oln(l0.size());
+  vector<uint8_t> pin(p0.size()), lin(l0.size());
+  int32_t on[2] = {0, 0};
+  gfpl_track_obs obs{1, (int32_t)p0.size(), (int32_t)l0.size(), &on[0], &on[1], opt.data(), pin.data(), oln.data(), lin.data()};
+  double DTr[16];
+  DT.to_row_major(DTr);
+  gfpl->check(gfpl_kf_match(gfpl->get(), &v0, &v1, DTr, &obs));
+
+  // ---- landmark / graph bookkeeping in the reference's loop order (ascending kf0 index) -------------------------
+  int common_pt = 0;
+  for (int k = 0; k < on[0]; k++) {  // :268-334
+    const int lr_qdx = opt[k].prev_idx, lr_tdx = opt[k].curr_idx;
+    StVO::PointFeature* a = f0->stereo_pt[lr_qdx];
+    StVO::PointFeature* b = f1->stereo_pt[lr_tdx];
+    common_pt++;
+    if (a->idx == -1) {
+      a->idx = max_pt_idx;
+      b->idx = max_pt_idx;
+      MapPoint* mp = new MapPoint();
+      mp->idx = max_pt_idx;
+      mp->point3D = transform_point(kf0->T_kf_w, a->P);
+      mp->addMapPointObservation(f0->pdesc_l.ptr(lr_qdx), kf0->kf_idx, a->pl, normalized(mp->point3D));
+      map_points_kf_idx.at(kf0->kf_idx).push_back(max_pt_idx);
+      mp->addMapPointObservation(f1->pdesc_l.ptr(lr_tdx), kf1->kf_idx, b->pl, normalized(transform_point(kf1->T_kf_w, b->P)));
+      if ((int)map_points.size() <= max_pt_idx) map_points.resize(max_pt_idx + 1, nullptr);
+      map_points[max_pt_idx] = mp;
+      max_pt_idx++;
+      full_graph[kf1_idx][kf0_idx]++;
+      full_graph[kf0_idx][kf1_idx]++;
+    } else {
+      const int lm_idx = a->idx;
+      if (lm_idx < (int)map_points.size() && map_points[lm_idx] != nullptr) {
+        b->idx = lm_idx;
+        map_points[lm_idx]->addMapPointObservation(f1->pdesc_l.ptr(lr_tdx), kf1->kf_idx, b->pl,
+                                                   normalized(transform_point(kf1->T_kf_w, b->P)));
+        for (int o : map_points[lm_idx]->kf_obs_list)
+          if (o != kf1_idx && o < (int)full_graph.size()) { full_graph[kf1_idx][o]++; full_graph[o][kf1_idx]++; }
+      }
+    }
+  }
+  int common_ls = 0;
+  for (int k = 0; k < on[1]; k++) {  // :405-487
+    const int lr_qdx = oln[k].prev_idx, lr_tdx = oln[k].curr_idx;
+    StVO::LineFeature* a = f0->stereo_ls[lr_qdx];
+    StVO::LineFeature* b = f1->stereo_ls[lr_tdx];
+    common_ls++;
+    auto mid_dir = [&](const Matrix4d& T, const StVO::LineFeature* l) {
+      Vector3d m;
+      for (int i = 0; i < 3; i++) m(i) = 0.5 * (l->sP(i) + l->eP(i));
+      return normalized(transform_point(T, m));
+    };
+    auto pts_of = [](const StVO::LineFeature* l) {
+      gfpl::Mat<4, 1> p;
+      p(0) = l->spl(0); p(1) = l->spl(1); p(2) = l->epl(0); p(3) = l->epl(1);
+      return p;
+    };
+    if (a->idx == -1) {
+      a->idx = max_ls_idx;
+      b->idx = max_ls_idx;
+      MapLine* ml = new MapLine();
+      ml->idx = max_ls_idx;
+      const Vector3d s3 = transform_point(kf0->T_kf_w, a->sP), e3 = transform_point(kf0->T_kf_w, a->eP);
+      for (int i = 0; i < 3; i++) { ml->line3D(i) = s3(i); ml->line3D(3 + i) = e3(i); }
+      Vector3d m;
+      for (int i = 0; i < 3; i++) m(i) = 0.5 * (s3(i) + e3(i));
+      ml->addMapLineObservation(f0->ldesc_l.ptr(lr_qdx), kf0->kf_idx, a->le, normalized(m), pts_of(a));
+      ml->addMapLineObservation(f1->ldesc_l.ptr(lr_tdx), kf1->kf_idx, b->le, mid_dir(kf1->T_kf_w, b), pts_of(b));
+      map_lines_kf_idx.at(kf0->kf_idx).push_back(max_ls_idx);
+      if ((int)map_lines.size() <= max_ls_idx) map_lines.resize(max_ls_idx + 1, nullptr);
+      map_lines[max_ls_idx] = ml;
+      max_ls_idx++;
+      full_graph[kf1_idx][kf0_idx]++;
+      full_graph[kf0_idx][kf1_idx]++;
+    } else {
+      const int lm_idx = a->idx;
+      if (lm_idx < (int)map_lines.size() && map_lines[lm_idx] != nullptr) {
+        b->idx = lm_idx;
+        map_lines[lm_idx]->addMapLineObservation(f1->ldesc_l.ptr(lr_tdx), kf1->kf_idx, b->le, mid_dir(kf1->T_kf_w, b), pts_of(b));
+        for (int o : map_lines[lm_idx]->kf_obs_list)
+          if (o != kf1_idx && o < (int)full_graph.size()) { full_graph[kf1_idx][o]++; full_graph[o][kf1_idx]++; }
+      }
+    }
+  }
+  last_common_pt = common_pt;
+  last_common_ls = common_ls;
+}
+
 // ---- localBundleAdjustment: gather (mapHandler.cpp:1108-1215) ------------------------------------------------------
 void MapHandler::localBundleAdjustment() {
   vector<double> X_aux;

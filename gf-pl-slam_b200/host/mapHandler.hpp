@@ -20,33 +20,57 @@ using std::vector;
 typedef std::array<int, 6> Vector6i;  // (lm_map, lm_loc, obs_idx, kf_map, kf_loc or -1, inlier)
 
 // the fields of include/keyFrame.h and include/mapFeatures.h that local BA reads and writes
+typedef std::array<uint8_t, GFPL_DESC_BYTES> Descriptor;
 struct KeyFrame {
   int kf_idx = 0;
   bool local = false;
   Matrix4d T_kf_w = Matrix4d::Identity();
   Vector6d x_kf_w;
+  StVO::StereoFrame* stereo_frame = nullptr;   // shares the feature pointers like the reference (keyFrame.cpp:38-39)
 };
-struct MapPoint {
+struct MapPoint {  // include/mapFeatures.h:36-62
   int idx = 0;
   bool local = false;
   Vector3d point3D;
   vector<Vector2d> obs_list;
+  vector<Vector3d> dir_list;
   vector<int> kf_obs_list;
   vector<double> sigma_list;
+  vector<Descriptor> desc_list;
+  void addMapPointObservation(const uint8_t* desc, int kf_idx, const Vector2d& obs, const Vector3d& dir) {  // mapFeatures.cpp:42-49
+    Descriptor d;
+    std::memcpy(d.data(), desc, GFPL_DESC_BYTES);
+    desc_list.push_back(d); obs_list.push_back(obs); kf_obs_list.push_back(kf_idx); dir_list.push_back(dir);
+    sigma_list.push_back(1.0);   // default sigma2_ = 1.f (mapFeatures.h:46,49)
+  }
 };
-struct MapLine {
+struct MapLine {   // include/mapFeatures.h:64-95
   int idx = 0;
   bool local = false;
   Vector6d line3D;
   vector<Vector3d> obs_list;
+  vector<Vector3d> dir_list;
+  vector<gfpl::Mat<4, 1>> pts_list;
   vector<int> kf_obs_list;
   vector<double> sigma_list;
+  vector<Descriptor> desc_list;
+  void addMapLineObservation(const uint8_t* desc, int kf_idx, const Vector3d& obs, const Vector3d& dir,
+                             const gfpl::Mat<4, 1>& pts) {  // mapFeatures.cpp:118-126
+    Descriptor d;
+    std::memcpy(d.data(), desc, GFPL_DESC_BYTES);
+    desc_list.push_back(d); obs_list.push_back(obs); kf_obs_list.push_back(kf_idx); dir_list.push_back(dir);
+    pts_list.push_back(pts); sigma_list.push_back(1.0);
+  }
 };
 
 class MapHandler {
  public:
   MapHandler(StVO::PinholeStereoCamera* cam_, StVO::GfplContext* gfpl_) : cam(cam_), gfpl(gfpl_) {}
 
+  // KF <-> KF half of lookForCommonMatches (mapHandler.cpp:189-490): matching + gates on the GPU (gfpl_kf_match),
+  // landmark / graph bookkeeping on the host exactly in the reference's loop order.  The local-map <-> KF half
+  // (:513-770) is not part of this round.
+  void lookForCommonMatches(KeyFrame* kf0, KeyFrame*& kf1);
   void localBundleAdjustment();  // mapHandler.cpp:1108-1215
   void levMarquardtOptimizationLBA(vector<double> X_aux, vector<int> kf_list, vector<int> pt_list, vector<int> ls_list,
                                    vector<Vector6i> pt_obs_list, vector<Vector6i> ls_obs_list);  // :1217-1712
@@ -56,6 +80,10 @@ class MapHandler {
   vector<MapLine*> map_lines;
   StVO::PinholeStereoCamera* cam;
   StVO::GfplContext* gfpl;
+  int max_pt_idx = 0, max_ls_idx = 0;
+  vector<vector<int>> full_graph;                       // covisibility counts (mapHandler.h:134)
+  vector<vector<int>> map_points_kf_idx, map_lines_kf_idx;
+  int last_common_pt = 0, last_common_ls = 0;
   int lba_iterations = 0;      // what the reference prints as "LBA Iterations"
   double lba_last_err = 0.0;
 };

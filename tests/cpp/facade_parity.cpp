@@ -168,6 +168,44 @@ static int test_tracking() {
   EXPECT(std::fabs(f1->err_norm - pose.err_norm) < 1e-9 * std::fabs(pose.err_norm), "err_norm");
   // the recovered motion is the simulated one (DT maps curr -> prev: inverse of the scene motion)
   EXPECT(std::fabs(f1->DT(0, 3) + 0.02) < 0.02 && std::fabs(f1->DT(2, 3) - 0.04) < 0.03, "recovered translation (%.3f %.3f %.3f)", f1->DT(0, 3), f1->DT(1, 3), f1->DT(2, 3));
+  // ---- MapHandler::lookForCommonMatches (KF <-> KF half) on the same two frames as key frames 0 and 1 ------------
+  {
+    for (auto* pf : f0->stereo_pt) pf->idx = -1;    // no landmark yet (the handler reused idx for f2f bookkeeping)
+    for (auto* pf : f1->stereo_pt) pf->idx = -1;
+    for (auto* lf : f0->stereo_ls) lf->idx = -1;
+    PLSLAM::MapHandler map(&cam, &gf);
+    PLSLAM::KeyFrame k0, k1;
+    k0.kf_idx = 0; k0.stereo_frame = f0; k0.T_kf_w = f0->Tfw;
+    k1.kf_idx = 1; k1.stereo_frame = f1; k1.T_kf_w = f1->Tfw;
+    PLSLAM::KeyFrame* k1p = &k1;
+    map.lookForCommonMatches(&k0, k1p);
+    // oracle: same matching + gates
+    gfpl::Matrix4d DTk = PLSLAM::inverse_se3(k1.T_kf_w) * k0.T_kf_w;
+    double DTr[16];
+    DTk.to_row_major(DTr);
+    std::vector<gfpl_pt_obs> kpt(NP); std::vector<gfpl_ln_obs> kln(NL); std::vector<uint8_t> kpin(NP), klin(NL);
+    int32_t kn[2];
+    gfpl_track_obs kobs{1, NP, NL, &kn[0], &kn[1], kpt.data(), kpin.data(), kln.data(), klin.data()};
+    // stereo frames as the facade sees them after tracking (line endpoints of f0 were cut in place)
+    std::vector<gfpl_point_feature> a0, a1; std::vector<gfpl_line_feature> b0, b1;
+    f0->exportStereo(a0, b0); f1->exportStereo(a1, b1);
+    int32_t m0[2] = {(int32_t)f0->stereo_pt.size(), (int32_t)f0->stereo_ls.size()}, m1[2] = {(int32_t)f1->stereo_pt.size(), (int32_t)f1->stereo_ls.size()};
+    gfpl_stereo_frames w0{1, (int32_t)a0.size(), (int32_t)b0.size(), &m0[0], &m0[1], a0.data(), const_cast<uint8_t*>(f0->pdesc_l.ptr()), b0.data(), const_cast<uint8_t*>(f0->ldesc_l.ptr())};
+    gfpl_stereo_frames w1{1, (int32_t)a1.size(), (int32_t)b1.size(), &m1[0], &m1[1], a1.data(), const_cast<uint8_t*>(f1->pdesc_l.ptr()), b1.data(), const_cast<uint8_t*>(f1->ldesc_l.ptr())};
+    orc_kf_match(&ccam, &cfg, &w0, &w1, DTr, &kobs);
+    printf("facade lookForCommonMatches: %d common points, %d common lines (oracle %d, %d), %d map points, %d map lines\n",
+           map.last_common_pt, map.last_common_ls, kn[0], kn[1], map.max_pt_idx, map.max_ls_idx);
+    EXPECT(map.last_common_pt == kn[0] && map.last_common_ls == kn[1], "common matches vs oracle");
+    EXPECT(kn[0] > 100, "enough common points (%d)", kn[0]);
+    EXPECT(map.max_pt_idx == kn[0] && (int)map.map_points.size() == kn[0], "one new MapPoint per accepted pair");
+    EXPECT(map.full_graph[0][1] == kn[0] + kn[1] && map.full_graph[1][0] == kn[0] + kn[1], "covisibility graph");
+    for (int k = 0; k < kn[0]; k++) {
+      EXPECT(f0->stereo_pt[kpt[k].prev_idx]->idx == k && f1->stereo_pt[kpt[k].curr_idx]->idx == k, "landmark index of pair %d", k);
+      EXPECT(map.map_points[k]->kf_obs_list.size() == 2 && map.map_points[k]->kf_obs_list[1] == 1, "observations of landmark %d", k);
+    }
+    for (auto* mp : map.map_points) delete mp;
+    for (auto* ml : map.map_lines) delete ml;
+  }
   StVO.updateFrame();
   EXPECT(StVO.prev_frame == f1 && StVO.curr_frame == nullptr, "updateFrame");
   delete f1;
