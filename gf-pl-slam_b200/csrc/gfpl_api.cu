@@ -192,6 +192,7 @@ void gfpl_config_default(gfpl_config* c) {
   c->lambda_lba_lm = 0.001; c->lambda_lba_k = 10.0;
   c->f2f_point_window = 10.0; c->budget_slack = 1.2; c->cut_step = 0.05; c->cut_rng[0] = 0; c->cut_rng[1] = 1.0;
   c->mad_uninit_value = 0.0;
+  c->max_kf_epip_p = 1.0; c->max_kf_epip_l = 1.0;
 }
 
 void gfpl_camera_euroc(gfpl_camera* c) {
@@ -522,6 +523,68 @@ int gfpl_kf_match(gfpl_ctx* ctx, const gfpl_stereo_frames* kf0, const gfpl_stere
                       ctx->cfg.best_lr_matches ? w.ln_21 : Knn2Out{}));
   CHECK(launch_kf_accept(ctx, d0, d1, dDT, w.pt_12, w.pt_21, w.ln_12, w.ln_21, dobs));
   download_obs(ctx, out, dobs);
+  return finish(ctx);
+}
+
+int gfpl_map_match(gfpl_ctx* ctx, const gfpl_local_map* map, const gfpl_stereo_frames* kf1, const double* Twf,
+                   gfpl_map_matches* out) {
+  if (!ctx) return GFPL_E_INVALID;
+  REQUIRE(ctx, map && kf1 && Twf && out && map->B == kf1->B && map->B == out->B && map->B >= 0);
+  REQUIRE(ctx, out->cap_pt > 0 && out->cap_ln > 0 && map->cap_pt > 0 && map->cap_ln > 0 && kf1->cap_pt > 0 && kf1->cap_ln > 0);
+  if (map->B == 0) return GFPL_OK;
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DevMem m(ctx);
+  const size_t B = map->B, mp = B * map->cap_pt, ml = B * map->cap_ln, kp = B * kf1->cap_pt, kl = B * kf1->cap_ln;
+  gfpl_local_map dm = *map;
+  dm.n_pt = m.upload(map->n_pt, B); dm.n_ln = m.upload(map->n_ln, B);
+  dm.pt3d = m.upload(map->pt3d, mp * 3); dm.pdesc = m.upload(map->pdesc, mp * 32);
+  dm.ln3d = m.upload(map->ln3d, ml * 6); dm.ldesc = m.upload(map->ldesc, ml * 32);
+  DevStereoFrames d1;
+  REQUIRE_MEM(ctx, dm.n_pt && dm.n_ln && dm.pt3d && dm.pdesc && dm.ln3d && dm.ldesc && mirror_stereo(m, kf1, &d1));
+  double* dT = m.upload(Twf, B * 16);
+  MapWork w;
+  w.n_sel_pt = m.alloc<int32_t>(B); w.n_un_pt = m.alloc<int32_t>(B);
+  w.n_sel_ln = m.alloc<int32_t>(B); w.n_un_ln = m.alloc<int32_t>(B);
+  w.sel_pt = m.alloc<int32_t>(mp); w.sel_ln = m.alloc<int32_t>(ml);
+  w.un_pt = m.alloc<int32_t>(kp); w.un_ln = m.alloc<int32_t>(kl);
+  w.dsel_pt = m.alloc<uint8_t>(mp * 32); w.dsel_ln = m.alloc<uint8_t>(ml * 32);
+  w.dun_pt = m.alloc<uint8_t>(kp * 32); w.dun_ln = m.alloc<uint8_t>(kl * 32);
+  Knn2Out pt_12, pt_21, ln_12, ln_21;
+  gfpl_map_matches dout = *out;
+  dout.n_pt = m.alloc<int32_t>(B); dout.n_ln = m.alloc<int32_t>(B);
+  dout.pt = m.alloc<gfpl_map_pair>(B * out->cap_pt); dout.ln = m.alloc<gfpl_map_pair>(B * out->cap_ln);
+  REQUIRE_MEM(ctx, dT && w.n_sel_pt && w.n_un_pt && w.n_sel_ln && w.n_un_ln && w.sel_pt && w.sel_ln && w.un_pt && w.un_ln &&
+                       w.dsel_pt && w.dsel_ln && w.dun_pt && w.dun_ln && alloc_knn(m, mp, &pt_12) && alloc_knn(m, kp, &pt_21) &&
+                       alloc_knn(m, ml, &ln_12) && alloc_knn(m, kl, &ln_21) && dout.n_pt && dout.n_ln && dout.pt && dout.ln);
+  CHECK(launch_map_select(ctx, dm, d1, dT, w));
+  if (ctx->cfg.has_points)
+    CHECK(launch_knn2(ctx, map->B, w.dsel_pt, w.n_sel_pt, map->cap_pt, w.dun_pt, w.n_un_pt, kf1->cap_pt, GFPL_NORM_HAMMING,
+                      pt_12, ctx->cfg.best_lr_matches ? pt_21 : Knn2Out{}));
+  if (ctx->cfg.has_lines)
+    CHECK(launch_knn2(ctx, map->B, w.dsel_ln, w.n_sel_ln, map->cap_ln, w.dun_ln, w.n_un_ln, kf1->cap_ln, GFPL_NORM_HAMMING,
+                      ln_12, ctx->cfg.best_lr_matches ? ln_21 : Knn2Out{}));
+  CHECK(launch_map_accept(ctx, dm, d1, dT, w, pt_12, pt_21, ln_12, ln_21, dout));
+  download(ctx, out->n_pt, dout.n_pt, B);
+  download(ctx, out->n_ln, dout.n_ln, B);
+  download(ctx, out->pt, dout.pt, B * out->cap_pt);
+  download(ctx, out->ln, dout.ln, B * out->cap_ln);
+  return finish(ctx);
+}
+
+int gfpl_medoid_desc(gfpl_ctx* ctx, const uint8_t* desc, const int32_t* offsets, int32_t L, int32_t* out_idx) {
+  if (!ctx) return GFPL_E_INVALID;
+  REQUIRE(ctx, desc && offsets && out_idx && L >= 0);
+  if (L == 0) return GFPL_OK;
+  REQUIRE(ctx, offsets[0] == 0 && offsets[L] >= 0 && offsets[L] < (1 << 20));
+  for (int l = 0; l < L; l++) REQUIRE(ctx, offsets[l + 1] >= offsets[l]);
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DevMem m(ctx);
+  uint8_t* dd = m.upload(desc, (size_t)offsets[L] * 32);
+  int32_t* doff = m.upload(offsets, (size_t)L + 1);
+  int32_t* dout = m.alloc<int32_t>(L);
+  REQUIRE_MEM(ctx, dd && doff && dout);
+  CHECK(launch_medoid(ctx, dd, doff, L, dout));
+  download(ctx, out_idx, dout, (size_t)L);
   return finish(ctx);
 }
 

@@ -21,6 +21,14 @@ struct Knn2Out {  // knn k=2 results of one direction, [B][cap_q]
   float2* dist;   // (d0, d1), +inf when missing
 };
 
+// compacted sides of a local-map <-> KF matching problem (k_map.cu); all [B][cap] of the side they index
+struct MapWork {
+  int32_t *n_sel_pt, *n_un_pt, *n_sel_ln, *n_un_ln;  // [B]
+  int32_t *sel_pt, *sel_ln;                          // [B][map.cap_*]  original landmark index
+  int32_t *un_pt, *un_ln;                            // [B][kf1.cap_*]  original feature index
+  uint8_t *dsel_pt, *dsel_ln, *dun_pt, *dun_ln;      // compacted descriptor rows
+};
+
 void set_last_error(gfpl_ctx* ctx, const char* fmt, ...);
 
 }  // namespace gfpl
@@ -91,6 +99,12 @@ int launch_f2f_accept(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStere
 
 int launch_kf_accept(gfpl_ctx* ctx, const DevStereoFrames& kf0, const DevStereoFrames& kf1, const double* DT, Knn2Out pt_12,
                      Knn2Out pt_21, Knn2Out ln_12, Knn2Out ln_21, DevTrackObs out);
+
+int launch_map_select(gfpl_ctx* ctx, const gfpl_local_map& map, const DevStereoFrames& kf1, const double* Twf, MapWork w);
+int launch_map_accept(gfpl_ctx* ctx, const gfpl_local_map& map, const DevStereoFrames& kf1, const double* Twf, MapWork w,
+                      Knn2Out pt_12, Knn2Out pt_21, Knn2Out ln_12, Knn2Out ln_21, gfpl_map_matches out);
+
+int launch_medoid(gfpl_ctx* ctx, const uint8_t* desc, const int32_t* offsets, int L, int32_t* out);
 
 // K5: line cut.  DT_inv may be NULL: then it is formed from `state` (curr->Tfw^-1 * prev->Tfw with the
 // predicted curr->Tfw = prev->Tfw * prev->DT).

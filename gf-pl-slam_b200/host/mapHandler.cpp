@@ -235,8 +235,126 @@ void MapHandler::lookForCommonMatches(KeyFrame* kf0, KeyFrame*& kf1) {
       }
     }
   }
+  {
+    vector<int> tp, tl;
+    for (int k = 0; k < on[0]; k++) tp.push_back(f0->stereo_pt[opt[k].prev_idx]->idx);
+    for (int k = 0; k < on[1]; k++) tl.push_back(f0->stereo_ls[oln[k].prev_idx]->idx);
+    refreshMedoids(tp, tl);
+  }
+  matchLocalMap(kf1, common_pt, common_ls);
   last_common_pt = common_pt;
   last_common_ls = common_ls;
+}
+
+// ---- lookForCommonMatches, local map <-> KF half (mapHandler.cpp:509-770) ------------------------------------------
+void MapHandler::matchLocalMap(KeyFrame* kf1, int& common_pt, int& common_ls) {
+  const int kf1_idx = kf1->kf_idx;
+  StVO::StereoFrame* f1 = kf1->stereo_frame;
+  const Matrix4d Twf = inverse_se3(kf1->T_kf_w);  // :200
+  // host walk over the map: `local` and "last observer is not kf1" (:516-521, :636-643); the in-image test runs on the GPU
+  vector<MapPoint*> cand_pt;
+  vector<MapLine*> cand_ls;
+  for (MapPoint* mp : map_points)
+    if (mp && mp->local && mp->kf_obs_list.back() != kf1_idx) cand_pt.push_back(mp);
+  for (MapLine* ml : map_lines)
+    if (ml && ml->local && ml->kf_obs_list.back() != kf1_idx) cand_ls.push_back(ml);
+  const int32_t np = (int32_t)cand_pt.size(), nl = (int32_t)cand_ls.size();
+  const int32_t cp = std::max(np, 1), cl = std::max(nl, 1);
+  vector<double> X((size_t)cp * 3, 0.0), L((size_t)cl * 6, 0.0);
+  vector<uint8_t> dX((size_t)cp * 32, 0), dL((size_t)cl * 32, 0);
+  for (int i = 0; i < np; i++) {
+    for (int k = 0; k < 3; k++) X[3 * i + k] = cand_pt[i]->point3D(k);
+    std::memcpy(&dX[32 * (size_t)i], cand_pt[i]->med_desc.data(), 32);
+  }
+  for (int i = 0; i < nl; i++) {
+    for (int k = 0; k < 6; k++) L[6 * i + k] = cand_ls[i]->line3D(k);
+    std::memcpy(&dL[32 * (size_t)i], cand_ls[i]->med_desc.data(), 32);
+  }
+  vector<gfpl_point_feature> p1;
+  vector<gfpl_line_feature> l1;
+  f1->exportStereo(p1, l1);
+  int32_t n1[2] = {(int32_t)f1->stereo_pt.size(), (int32_t)f1->stereo_ls.size()};
+  if (p1.empty()) p1.resize(1);
+  if (l1.empty()) l1.resize(1);
+  vector<uint8_t> pd1(p1.size() * 32, 0), ld1(l1.size() * 32, 0);
+  if (n1[0]) std::memcpy(pd1.data(), f1->pdesc_l.ptr(), (size_t)n1[0] * 32);
+  if (n1[1]) std::memcpy(ld1.data(), f1->ldesc_l.ptr(), (size_t)n1[1] * 32);
+  gfpl_local_map lm{1, cp, cl, &np, &nl, X.data(), dX.data(), L.data(), dL.data()};
+  gfpl_stereo_frames v1{1, (int32_t)p1.size(), (int32_t)l1.size(), &n1[0], &n1[1], p1.data(), pd1.data(), l1.data(), ld1.data()};
+  vector<gfpl_map_pair> mpt(cp), mln(cl);
+  int32_t mn[2] = {0, 0};
+  gfpl_map_matches mm{1, cp, cl, &mn[0], &mn[1], mpt.data(), mln.data()};
+  double Tr[16];
+  Twf.to_row_major(Tr);
+  gfpl->check(gfpl_map_match(gfpl->get(), &lm, &v1, Tr, &mm));
+
+  // position of every stereo line inside the reference's `unmatched_lines` list (built before the loop, :663-674)
+  vector<int> un_pos(f1->stereo_ls.size(), -1);
+  {
+    int c = 0;
+    for (size_t i = 0; i < f1->stereo_ls.size(); i++)
+      if (f1->stereo_ls[i]->idx == -1) un_pos[i] = c++;
+  }
+  auto bump_graph = [&](const vector<int>& kf_obs_list) {
+    for (int o : kf_obs_list)
+      if (o != kf1_idx && o < (int)full_graph.size()) { full_graph[kf1_idx][o]++; full_graph[o][kf1_idx]++; }
+  };
+  vector<int> tp, tl;
+  for (int k = 0; k < mn[0]; k++) {  // :606-625
+    MapPoint* mp = cand_pt[mpt[k].map_idx];
+    StVO::PointFeature* b = f1->stereo_pt[mpt[k].kf_idx];
+    common_pt++;
+    b->idx = mp->idx;
+    const Vector3d dir_kf = transform_point(kf1->T_kf_w, normalized(b->P));   // R * dir + t as written at :613
+    mp->addMapPointObservation(f1->pdesc_l.ptr(mpt[k].kf_idx), kf1_idx, b->pl, dir_kf);
+    bump_graph(mp->kf_obs_list);
+    tp.push_back(mp->idx);
+  }
+  for (int k = 0; k < mn[1]; k++) {  // :745-765
+    MapLine* ml = cand_ls[mln[k].map_idx];
+    StVO::LineFeature* b = f1->stereo_ls[mln[k].kf_idx];
+    common_ls++;
+    b->idx = ml->idx;
+    Vector3d m;
+    for (int i = 0; i < 3; i++) m(i) = 0.5 * (b->sP(i) + b->eP(i));
+    const Vector3d mP3d = normalized(transform_point(kf1->T_kf_w, m));
+    gfpl::Mat<4, 1> pts;
+    pts(0) = b->spl(0); pts(1) = b->spl(1); pts(2) = b->epl(0); pts(3) = b->epl(1);
+    // the reference stores row `lr_tdx` of the FULL ldesc_l, lr_tdx being the position in the unmatched list (:755)
+    ml->addMapLineObservation(f1->ldesc_l.ptr(un_pos[mln[k].kf_idx]), kf1_idx, b->le, mP3d, pts);
+    bump_graph(ml->kf_obs_list);
+    tl.push_back(ml->idx);
+  }
+  refreshMedoids(tp, tl);
+}
+
+// ---- updateAverageDescDir for a set of landmarks (mapFeatures.cpp:51-92, 128-170) ----------------------------------
+void MapHandler::refreshMedoids(const vector<int>& pts, const vector<int>& lines) {
+  auto run = [&](auto& landmarks, const vector<int>& ids) {
+    vector<uint8_t> desc;
+    vector<int32_t> off{0};
+    vector<int> live;
+    for (int id : ids) {
+      if (id < 0 || id >= (int)landmarks.size() || !landmarks[id]) continue;
+      for (const Descriptor& d : landmarks[id]->desc_list) desc.insert(desc.end(), d.begin(), d.end());
+      off.push_back((int32_t)(desc.size() / 32));
+      live.push_back(id);
+    }
+    if (live.empty()) return;
+    vector<int32_t> med(live.size());
+    gfpl->check(gfpl_medoid_desc(gfpl->get(), desc.data(), off.data(), (int32_t)live.size(), med.data()));
+    for (size_t k = 0; k < live.size(); k++) {
+      auto* lm = landmarks[live[k]];
+      lm->med_desc = lm->desc_list[med[k]];
+      Vector3d s;                                   // the reference sums into an uninitialised Vector3d (:85-88): 0 here
+      for (int i = 0; i < 3; i++) s(i) = 0.0;
+      for (const Vector3d& d : lm->dir_list) for (int i = 0; i < 3; i++) s(i) += d(i);
+      const double n = (double)lm->dir_list.size();
+      for (int i = 0; i < 3; i++) lm->med_obs_dir(i) = s(i) / n;
+    }
+  };
+  run(map_points, pts);
+  run(map_lines, lines);
 }
 
 // ---- localBundleAdjustment: gather (mapHandler.cpp:1108-1215) ------------------------------------------------------

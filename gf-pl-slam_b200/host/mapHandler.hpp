@@ -37,6 +37,8 @@ struct MapPoint {  // include/mapFeatures.h:36-62
   vector<int> kf_obs_list;
   vector<double> sigma_list;
   vector<Descriptor> desc_list;
+  Descriptor med_desc{};          // representative descriptor (mapFeatures.cpp:51-82), refreshed by MapHandler::refreshMedoids
+  Vector3d med_obs_dir;
   void addMapPointObservation(const uint8_t* desc, int kf_idx, const Vector2d& obs, const Vector3d& dir) {  // mapFeatures.cpp:42-49
     Descriptor d;
     std::memcpy(d.data(), desc, GFPL_DESC_BYTES);
@@ -54,6 +56,8 @@ struct MapLine {   // include/mapFeatures.h:64-95
   vector<int> kf_obs_list;
   vector<double> sigma_list;
   vector<Descriptor> desc_list;
+  Descriptor med_desc{};
+  Vector3d med_obs_dir;
   void addMapLineObservation(const uint8_t* desc, int kf_idx, const Vector3d& obs, const Vector3d& dir,
                              const gfpl::Mat<4, 1>& pts) {  // mapFeatures.cpp:118-126
     Descriptor d;
@@ -67,10 +71,16 @@ class MapHandler {
  public:
   MapHandler(StVO::PinholeStereoCamera* cam_, StVO::GfplContext* gfpl_) : cam(cam_), gfpl(gfpl_) {}
 
-  // KF <-> KF half of lookForCommonMatches (mapHandler.cpp:189-490): matching + gates on the GPU (gfpl_kf_match),
-  // landmark / graph bookkeeping on the host exactly in the reference's loop order.  The local-map <-> KF half
-  // (:513-770) is not part of this round.
+  // lookForCommonMatches (mapHandler.cpp:189-772): matching + gates on the GPU (gfpl_kf_match for the KF <-> KF half,
+  // gfpl_map_match for the local-map <-> KF half), landmark / graph bookkeeping on the host exactly in the
+  // reference's loop order.  The optional pose refinement (:495-507, has_refinement is hard-wired false) is omitted.
   void lookForCommonMatches(KeyFrame* kf0, KeyFrame*& kf1);
+  void matchLocalMap(KeyFrame* kf1, int& common_pt, int& common_ls);   // :509-770
+  // MapPoint / MapLine::updateAverageDescDir (mapFeatures.cpp:51-92, 128-170) for the landmarks that gained an
+  // observation, batched into one gfpl_medoid_desc call per feature type.  The reference refreshes inside every
+  // add*Observation; med_desc is only read by the NEXT selection of local landmarks (:532, :656), which skips the
+  // landmarks just observed by kf1 (:520, :642), so refreshing once per half gives the same values.
+  void refreshMedoids(const vector<int>& pts, const vector<int>& lines);
   void localBundleAdjustment();  // mapHandler.cpp:1108-1215
   void levMarquardtOptimizationLBA(vector<double> X_aux, vector<int> kf_list, vector<int> pt_list, vector<int> ls_list,
                                    vector<Vector6i> pt_obs_list, vector<Vector6i> ls_obs_list);  // :1217-1712

@@ -39,7 +39,7 @@ class Config(C.Structure):
         ("motion_step_th", C.c_double), ("orb_scale_factor", C.c_double), ("lsd_scale", C.c_double),
         ("lambda_lba_lm", C.c_double), ("lambda_lba_k", C.c_double), ("f2f_point_window", C.c_double),
         ("budget_slack", C.c_double), ("cut_step", C.c_double), ("cut_rng", C.c_double * 2),
-        ("mad_uninit_value", C.c_double),
+        ("mad_uninit_value", C.c_double), ("max_kf_epip_p", C.c_double), ("max_kf_epip_l", C.c_double),
     ]
 
 
@@ -87,6 +87,19 @@ class RawFrames(C.Structure):
 class StereoFrames(C.Structure):
     _fields_ = [("B", C.c_int32), ("cap_pt", C.c_int32), ("cap_ln", C.c_int32),
                 ("n_pt", _vp), ("n_ln", _vp), ("pt", _vp), ("pdesc", _vp), ("ln", _vp), ("ldesc", _vp)]
+
+
+class LocalMap(C.Structure):
+    _fields_ = [("B", C.c_int32), ("cap_pt", C.c_int32), ("cap_ln", C.c_int32),
+                ("n_pt", _vp), ("n_ln", _vp), ("pt3d", _vp), ("pdesc", _vp), ("ln3d", _vp), ("ldesc", _vp)]
+
+
+class MapMatches(C.Structure):
+    _fields_ = [("B", C.c_int32), ("cap_pt", C.c_int32), ("cap_ln", C.c_int32),
+                ("n_pt", _vp), ("n_ln", _vp), ("pt", _vp), ("ln", _vp)]
+
+
+map_pair_dt = np.dtype([("map_idx", "i4"), ("kf_idx", "i4")], align=True)
 
 
 class PrevFrames(C.Structure):
@@ -160,6 +173,30 @@ class RawFramesNP:
                   "ldesc_l", "ldesc_r"):
             setattr(out, k, getattr(self, k)[lo:hi])
         return out
+
+
+class LocalMapNP:
+    """local landmarks handed to gfpl_map_match: world points / line endpoints + representative descriptors"""
+
+    def __init__(self, B, cap_pt, cap_ln):
+        self.B, self.cap_pt, self.cap_ln = B, cap_pt, cap_ln
+        self.n_pt, self.n_ln = np.zeros(B, "i4"), np.zeros(B, "i4")
+        self.pt3d, self.pdesc = np.zeros((B, cap_pt, 3)), np.zeros((B, cap_pt, 32), "u1")
+        self.ln3d, self.ldesc = np.zeros((B, cap_ln, 6)), np.zeros((B, cap_ln, 32), "u1")
+
+    def view(self):
+        return LocalMap(self.B, self.cap_pt, self.cap_ln, ptr(self.n_pt), ptr(self.n_ln), ptr(self.pt3d),
+                        ptr(self.pdesc), ptr(self.ln3d), ptr(self.ldesc))
+
+
+class MapMatchesNP:
+    def __init__(self, B, cap_pt, cap_ln):
+        self.B, self.cap_pt, self.cap_ln = B, cap_pt, cap_ln
+        self.n_pt, self.n_ln = np.zeros(B, "i4"), np.zeros(B, "i4")
+        self.pt, self.ln = np.zeros((B, cap_pt), map_pair_dt), np.zeros((B, cap_ln), map_pair_dt)
+
+    def view(self):
+        return MapMatches(self.B, self.cap_pt, self.cap_ln, ptr(self.n_pt), ptr(self.n_ln), ptr(self.pt), ptr(self.ln))
 
 
 class StereoFramesNP:

@@ -192,6 +192,22 @@ class Context:
         self._check(lib().gfpl_kf_match(self._h, C.byref(v0), C.byref(v1), _vp(DT), C.byref(ov)))
         return out
 
+    def map_match(self, lmap, kf1, Twf):
+        """local map <-> KF matching of MapHandler::lookForCommonMatches (selection + matching + gates)"""
+        out = S.MapMatchesNP(lmap.B, lmap.cap_pt, lmap.cap_ln)
+        Twf = np.ascontiguousarray(Twf, np.float64)
+        mv, v1, ov = lmap.view(), kf1.view(), out.view()
+        self._check(lib().gfpl_map_match(self._h, C.byref(mv), C.byref(v1), _vp(Twf), C.byref(ov)))
+        return out
+
+    def medoid_desc(self, desc, offsets):
+        """descriptor part of MapPoint/MapLine::updateAverageDescDir for L landmarks (CSR lists of 32-byte rows)"""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        out = np.zeros(len(offsets) - 1, np.int32)
+        self._check(lib().gfpl_medoid_desc(self._h, _vp(desc), _vp(offsets), len(out), _vp(out)))
+        return out
+
     # ---- C1-C5 ----
     def linecut(self, DT_inv, obs, prev_cov):
         """obs is updated in place (sP/eP of cut lines); returns gfpl_line_cut records."""

@@ -106,6 +106,9 @@ typedef struct gfpl_config {
   double cut_rng[2];           /* {0,1}, stereoFrameHandler.cpp:134 */
   /* defined semantics for reference UB */
   double mad_uninit_value;     /* D1: value of the uninitialised nn_dist_median, default 0.0 */
+  /* map matching (MapHandler::lookForCommonMatches) */
+  double max_kf_epip_p;        /* config.cpp:42 1.0 */
+  double max_kf_epip_l;        /* config.cpp:43 1.0 */
 } gfpl_config;
 
 void gfpl_config_default(gfpl_config* cfg);
@@ -365,6 +368,45 @@ int gfpl_f2f_match(gfpl_ctx* ctx, const gfpl_stereo_frames* prev, const gfpl_ste
  * The map bookkeeping that follows each accepted pair (new MapPoint / MapLine, graphs) stays on the host. */
 int gfpl_kf_match(gfpl_ctx* ctx, const gfpl_stereo_frames* kf0, const gfpl_stereo_frames* kf1,
                   const double* DT /*[B][16]*/, gfpl_track_obs* out);
+
+/* Local map <-> key-frame half of MapHandler::lookForCommonMatches (mapHandler.cpp:509-770).
+ * map: the landmarks the host walk of :516-521 / :636-643 keeps (local && last observer != kf1) with their
+ * representative descriptor med_desc.row(0); kf1: the key frame's stereo features, `idx == -1` marks the ones the
+ * KF<->KF half left unmatched (:538-546, :665-673).  On the device: the in-image test of :524-532 / :645-657 on
+ * Twf * X, compaction of both sides, knn k=2 both ways (NORM_HAMMING), mutual check, ratio <= maxRatio12P (points)
+ * or gap > lineDescriptorMAD * descThL (lines), depth > 0, and the gates of :596 (|proj - pl| < maxKFEpipP) and :743
+ * (signed l.p < maxKFEpipL for both endpoints).  Twf = inverse_se3(kf1->T_kf_w), row-major [B][16].
+ * out pairs come in the loop order of :579 / :709 (ascending selected-landmark order = ascending map_idx);
+ * map_idx indexes the arrays of `map`, kf_idx the features of `kf1`.  addMap*Observation / full_graph stay on the host. */
+typedef struct gfpl_local_map {
+  int32_t B, cap_pt, cap_ln;
+  const int32_t* n_pt;  /* [B] */
+  const int32_t* n_ln;  /* [B] */
+  const double* pt3d;   /* [B][cap_pt][3]  MapPoint::point3D (world) */
+  const uint8_t* pdesc; /* [B][cap_pt][32] */
+  const double* ln3d;   /* [B][cap_ln][6]  MapLine::line3D (world start, end) */
+  const uint8_t* ldesc; /* [B][cap_ln][32] */
+} gfpl_local_map;
+
+typedef struct gfpl_map_pair { int32_t map_idx, kf_idx; } gfpl_map_pair;
+
+typedef struct gfpl_map_matches {
+  int32_t B, cap_pt, cap_ln;  /* cap_pt >= map->cap_pt, cap_ln >= map->cap_ln */
+  int32_t* n_pt;              /* [B] */
+  int32_t* n_ln;              /* [B] */
+  gfpl_map_pair* pt;          /* [B][cap_pt] */
+  gfpl_map_pair* ln;          /* [B][cap_ln] */
+} gfpl_map_matches;
+
+int gfpl_map_match(gfpl_ctx* ctx, const gfpl_local_map* map, const gfpl_stereo_frames* kf1,
+                   const double* Twf /*[B][16]*/, gfpl_map_matches* out);
+
+/* Descriptor part of MapPoint / MapLine::updateAverageDescDir (mapFeatures.cpp:51-82, 128-160):
+ * for each of L landmarks, the observation whose ascending NORM_HAMMING distance row (self distance included) has the
+ * smallest element int(1 + 0.5 (n-1)); ties -> lowest observation.  desc: all desc_list rows back to back,
+ * offsets[L+1] (CSR).  out_idx[l] = position inside landmark l's list (0 when n < 2: the reference only runs it
+ * from add*Observation, i.e. with n >= 2).  med_desc = desc_list[out_idx]. */
+int gfpl_medoid_desc(gfpl_ctx* ctx, const uint8_t* desc, const int32_t* offsets, int32_t L, int32_t* out_idx);
 
 /* ------------------------------------------------------------------------- */
 /* C1-C5 — good line cutting                                                  */

@@ -39,6 +39,7 @@ extern "C" void orc_config_default(gfpl_config* c) {
   c->lambda_lba_lm = 0.001; c->lambda_lba_k = 10.0;
   c->f2f_point_window = 10.0; c->budget_slack = 1.2; c->cut_step = 0.05; c->cut_rng[0] = 0; c->cut_rng[1] = 1.0;
   c->mad_uninit_value = 0.0;
+  c->max_kf_epip_p = 1.0; c->max_kf_epip_l = 1.0;  // config.cpp:42-43
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -644,6 +645,140 @@ extern "C" int orc_kf_match(const gfpl_camera* cam, const gfpl_config* cfg, cons
                             const gfpl_stereo_frames* kf1, const double* DT, gfpl_track_obs* out) {
   if (!cam || !cfg || !kf0 || !kf1 || !DT || !out) return GFPL_E_INVALID;
   for (int p = 0; p < kf0->B; p++) kf_match_one(cam, cfg, kf0, kf1, DT + (size_t)p * 16, out, p);
+  return GFPL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// local map <-> KF matching of MapHandler::lookForCommonMatches (mapHandler.cpp:509-770), matching + gates only
+// ------------------------------------------------------------------------------------------------
+static inline bool in_image(const gfpl_camera* cam, const double* uv, double z) {  // :526, :649, :651
+  return uv[0] > 0 && uv[0] < cam->width && uv[1] > 0 && uv[1] < cam->height && z > 0.0;
+}
+
+static void map_match_one(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_local_map* map,
+                          const gfpl_stereo_frames* kf1, const double* Twf, gfpl_map_matches* out, int p) {
+  int npt = 0, nln = 0;
+  {
+    const double* X = map->pt3d + (size_t)p * map->cap_pt * 3;
+    const uint8_t* D = map->pdesc + (size_t)p * map->cap_pt * 32;
+    const gfpl_point_feature* f1 = kf1->pt + (size_t)p * kf1->cap_pt;
+    const uint8_t* D1 = kf1->pdesc + (size_t)p * kf1->cap_pt * 32;
+    std::vector<int> sel, un;                 // map_local_points (:513-533), unmatched_points (:536-547)
+    std::vector<uint8_t> dsel, dun;
+    for (int i = 0; i < map->n_pt[p]; i++) {
+      double Pf[3], pf[2];
+      se3_apply(Twf, X + 3 * i, Pf);
+      projection(cam, Pf, pf);
+      if (in_image(cam, pf, Pf[2])) { sel.push_back(i); dsel.insert(dsel.end(), D + 32 * i, D + 32 * i + 32); }
+    }
+    for (int i = 0; i < kf1->n_pt[p]; i++)
+      if (f1[i].idx == -1) { un.push_back(i); dun.insert(dun.end(), D1 + 32 * i, D1 + 32 * i + 32); }
+    const int n0 = (int)sel.size(), n1 = (int)un.size();
+    if (cfg->has_points && n0 >= 2 && n1 >= 2) {  // D3
+      std::vector<Knn2> m12, m21;
+      knn2_set(dsel.data(), n0, dun.data(), n1, GFPL_NORM_HAMMING, m12);  // :551
+      if (cfg->best_lr_matches) knn2_set(dun.data(), n1, dsel.data(), n0, GFPL_NORM_HAMMING, m21);
+      for (int i = 0; i < n0; i++) {
+        const int lr_qdx = i, lr_tdx = m12[i].i0;
+        const int rl_tdx = cfg->best_lr_matches ? m21[lr_tdx].i0 : lr_qdx;
+        const double dist_12 = m12[i].d0 / m12[i].d1;  // float / float (:588)
+        if (lr_qdx == rl_tdx && dist_12 <= cfg->max_ratio_12_p) {
+          double Pf_map[3], pf_map[2];
+          se3_apply(Twf, X + 3 * sel[lr_qdx], Pf_map);
+          if (Pf_map[2] > 0.0) {
+            projection(cam, Pf_map, pf_map);
+            const double dx = pf_map[0] - f1[un[lr_tdx]].pl[0], dy = pf_map[1] - f1[un[lr_tdx]].pl[1];
+            if (std::sqrt(dx * dx + dy * dy) < cfg->max_kf_epip_p) {  // :606-607
+              if (npt < out->cap_pt) out->pt[(size_t)p * out->cap_pt + npt] = gfpl_map_pair{sel[lr_qdx], un[lr_tdx]};
+              npt++;
+            }
+          }
+        }
+      }
+    }
+  }
+  {
+    const double* X = map->ln3d + (size_t)p * map->cap_ln * 6;
+    const uint8_t* D = map->ldesc + (size_t)p * map->cap_ln * 32;
+    const gfpl_line_feature* f1 = kf1->ln + (size_t)p * kf1->cap_ln;
+    const uint8_t* D1 = kf1->ldesc + (size_t)p * kf1->cap_ln * 32;
+    std::vector<int> sel, un;                 // map_local_lines (:634-660), unmatched_lines (:663-674)
+    std::vector<uint8_t> dsel, dun;
+    for (int i = 0; i < map->n_ln[p]; i++) {
+      double sPf[3], ePf[3], spf[2], epf[2];
+      se3_apply(Twf, X + 6 * i, sPf);
+      projection(cam, sPf, spf);
+      se3_apply(Twf, X + 6 * i + 3, ePf);
+      projection(cam, ePf, epf);
+      if (in_image(cam, spf, sPf[2]) && in_image(cam, epf, ePf[2])) {
+        sel.push_back(i); dsel.insert(dsel.end(), D + 32 * i, D + 32 * i + 32);
+      }
+    }
+    for (int i = 0; i < kf1->n_ln[p]; i++)
+      if (f1[i].idx == -1) { un.push_back(i); dun.insert(dun.end(), D1 + 32 * i, D1 + 32 * i + 32); }
+    const int n0 = (int)sel.size(), n1 = (int)un.size();
+    if (cfg->has_lines && n0 >= 2 && n1 >= 2) {  // D3
+      std::vector<Knn2> m12, m21;
+      knn2_set(dsel.data(), n0, dun.data(), n1, GFPL_NORM_HAMMING, m12);  // :679
+      if (cfg->best_lr_matches) knn2_set(dun.data(), n1, dsel.data(), n0, GFPL_NORM_HAMMING, m21);
+      std::vector<float> d(2 * (size_t)n0);
+      for (int i = 0; i < n0; i++) { d[2 * i] = m12[i].d0; d[2 * i + 1] = m12[i].d1; }
+      const double nn12_dist_th = orc_line_descriptor_mad(d.data(), n0, cfg->mad_uninit_value) * cfg->desc_th_l;  // :702-703
+      for (int i = 0; i < n0; i++) {
+        const int lr_qdx = i, lr_tdx = m12[i].i0;
+        const int rl_tdx = cfg->best_lr_matches ? m21[lr_tdx].i0 : lr_qdx;
+        const double dist_12 = m12[i].d1 - m12[i].d0;
+        if (lr_qdx == rl_tdx && dist_12 > nn12_dist_th) {
+          double sP_[3], eP_[3], sp[2], ep[2];
+          se3_apply(Twf, X + 6 * sel[lr_qdx], sP_);
+          projection(cam, sP_, sp);
+          se3_apply(Twf, X + 6 * sel[lr_qdx] + 3, eP_);
+          projection(cam, eP_, ep);
+          const double* l_obs = f1[un[lr_tdx]].le;
+          if (sP_[2] > 0.0 && eP_[2] > 0.0) {
+            const double e0 = l_obs[0] * sp[0] + l_obs[1] * sp[1] + l_obs[2];  // signed, no abs (:741-743)
+            const double e1 = l_obs[0] * ep[0] + l_obs[1] * ep[1] + l_obs[2];
+            if (e0 < cfg->max_kf_epip_l && e1 < cfg->max_kf_epip_l) {
+              if (nln < out->cap_ln) out->ln[(size_t)p * out->cap_ln + nln] = gfpl_map_pair{sel[lr_qdx], un[lr_tdx]};
+              nln++;
+            }
+          }
+        }
+      }
+    }
+  }
+  out->n_pt[p] = std::min(npt, out->cap_pt);
+  out->n_ln[p] = std::min(nln, out->cap_ln);
+}
+
+extern "C" int orc_map_match(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_local_map* map,
+                             const gfpl_stereo_frames* kf1, const double* Twf, gfpl_map_matches* out) {
+  if (!cam || !cfg || !map || !kf1 || !Twf || !out) return GFPL_E_INVALID;
+  for (int p = 0; p < map->B; p++) map_match_one(cam, cfg, map, kf1, Twf + (size_t)p * 16, out, p);
+  return GFPL_OK;
+}
+
+// MapPoint / MapLine::updateAverageDescDir, descriptor part (mapFeatures.cpp:51-82, 128-160)
+extern "C" int orc_medoid_desc(const uint8_t* desc, const int32_t* offsets, int32_t L, int32_t* out_idx) {
+  for (int l = 0; l < L; l++) {
+    const uint8_t* D = desc + (size_t)offsets[l] * 32;
+    const int n = offsets[l + 1] - offsets[l];
+    if (n < 2) { out_idx[l] = 0; continue; }   // only reached through add*Observation in the reference (n >= 2)
+    std::vector<int> conf((size_t)n * n, 0);
+    for (int i = 0; i < n; i++)
+      for (int j = i + 1; j < n; j++) {
+        const int d = hamming256(D + 32 * i, D + 32 * j);
+        conf[(size_t)i * n + j] = d; conf[(size_t)j * n + i] = d;
+      }
+    int max_dist = 99999, max_idx = 0;
+    for (int i = 0; i < n; i++) {
+      std::vector<int> dist_idx(conf.begin() + (size_t)i * n, conf.begin() + (size_t)(i + 1) * n);
+      std::sort(dist_idx.begin(), dist_idx.end());
+      const int idx_median = dist_idx[int(1 + 0.5 * (n - 1))];
+      if (idx_median < max_dist) { max_dist = idx_median; max_idx = i; }
+    }
+    out_idx[l] = max_idx;
+  }
   return GFPL_OK;
 }
 

@@ -35,6 +35,9 @@ int orc_f2f_match(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_ste
                   const gfpl_stereo_frames* curr, const gfpl_frame_state* state, int32_t mode, gfpl_track_obs* out);
 int orc_kf_match(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_stereo_frames* kf0,
                  const gfpl_stereo_frames* kf1, const double* DT, gfpl_track_obs* out);
+int orc_map_match(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_local_map* map,
+                  const gfpl_stereo_frames* kf1, const double* Twf, gfpl_map_matches* out);
+int orc_medoid_desc(const uint8_t* desc, const int32_t* offsets, int32_t L, int32_t* out_idx);
 int orc_linecut_submodular(const gfpl_camera* cam, const gfpl_config* cfg, const double* DT_inv, gfpl_track_obs* obs,
                            const gfpl_line_cov* prev_cov, int32_t cov_cap, gfpl_line_cut* cut);
 /* single evaluation of getPoseInfoOnLine / getPoseInfoPoint / logdet / min-eigenvalue (unit tests) */

@@ -127,6 +127,24 @@ def kf_match(cam, cfg, kf0, kf1, DT):
     return out
 
 
+def map_match(cam, cfg, lmap, kf1, Twf):
+    out = S.MapMatchesNP(lmap.B, lmap.cap_pt, lmap.cap_ln)
+    Twf = np.ascontiguousarray(Twf, np.float64)
+    mv, v1, ov = lmap.view(), kf1.view(), out.view()
+    rc = lib().orc_map_match(C.byref(cam), C.byref(cfg), C.byref(mv), C.byref(v1), C.c_void_p(S.ptr(Twf)), C.byref(ov))
+    assert rc == 0, rc
+    return out
+
+
+def medoid_desc(desc, offsets):
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    offsets = np.ascontiguousarray(offsets, np.int32)
+    out = np.zeros(len(offsets) - 1, np.int32)
+    rc = lib().orc_medoid_desc(C.c_void_p(S.ptr(desc)), C.c_void_p(S.ptr(offsets)), len(out), C.c_void_p(S.ptr(out)))
+    assert rc == 0, rc
+    return out
+
+
 def linecut(cam, cfg, DT_inv, obs, prev_cov):
     """obs is updated in place (sP/eP of cut lines); returns the gfpl_line_cut records."""
     cut = np.zeros((obs.B, obs.cap_ln), S.line_cut_dt)

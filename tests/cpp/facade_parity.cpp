@@ -203,6 +203,50 @@ static int test_tracking() {
       EXPECT(f0->stereo_pt[kpt[k].prev_idx]->idx == k && f1->stereo_pt[kpt[k].curr_idx]->idx == k, "landmark index of pair %d", k);
       EXPECT(map.map_points[k]->kf_obs_list.size() == 2 && map.map_points[k]->kf_obs_list[1] == 1, "observations of landmark %d", k);
     }
+    // ---- local-map <-> KF half (:509-770): kf1 forgets every second landmark, then finds it again through the map ----
+    {
+      std::vector<int> all_p, all_l;
+      for (auto* mp : map.map_points) {
+        mp->local = true;
+        all_p.push_back(mp->idx);
+        if (mp->idx % 2 == 0) { mp->desc_list.pop_back(); mp->obs_list.pop_back(); mp->kf_obs_list.pop_back(); mp->dir_list.pop_back(); mp->sigma_list.pop_back(); }
+      }
+      for (auto* ml : map.map_lines) {
+        ml->local = true;
+        all_l.push_back(ml->idx);
+        if (ml->idx % 2 == 0) { ml->desc_list.pop_back(); ml->obs_list.pop_back(); ml->kf_obs_list.pop_back(); ml->dir_list.pop_back(); ml->pts_list.pop_back(); ml->sigma_list.pop_back(); }
+      }
+      for (auto* pf : f1->stereo_pt) if (pf->idx >= 0 && pf->idx % 2 == 0) pf->idx = -1;
+      for (auto* lf : f1->stereo_ls) if (lf->idx >= 0 && lf->idx % 2 == 0) lf->idx = -1;
+      map.refreshMedoids(all_p, all_l);
+      std::vector<PLSLAM::MapPoint*> cp_; std::vector<PLSLAM::MapLine*> cl_;
+      for (auto* mp : map.map_points) if (mp->kf_obs_list.back() != 1) cp_.push_back(mp);
+      for (auto* ml : map.map_lines) if (ml->kf_obs_list.back() != 1) cl_.push_back(ml);
+      int32_t np_ = (int32_t)cp_.size(), nl_ = (int32_t)cl_.size();
+      std::vector<double> X(3 * (size_t)std::max(np_, 1)), L(6 * (size_t)std::max(nl_, 1));
+      std::vector<uint8_t> dX(32 * (size_t)std::max(np_, 1)), dL(32 * (size_t)std::max(nl_, 1));
+      for (int i = 0; i < np_; i++) { for (int k = 0; k < 3; k++) X[3 * i + k] = cp_[i]->point3D(k); std::memcpy(&dX[32 * i], cp_[i]->med_desc.data(), 32); }
+      for (int i = 0; i < nl_; i++) { for (int k = 0; k < 6; k++) L[6 * i + k] = cl_[i]->line3D(k); std::memcpy(&dL[32 * i], cl_[i]->med_desc.data(), 32); }
+      gfpl_local_map lm{1, std::max(np_, 1), std::max(nl_, 1), &np_, &nl_, X.data(), dX.data(), L.data(), dL.data()};
+      f1->exportStereo(a1, b1);
+      gfpl_stereo_frames w1b{1, (int32_t)a1.size(), (int32_t)b1.size(), &m1[0], &m1[1], a1.data(), const_cast<uint8_t*>(f1->pdesc_l.ptr()), b1.data(), const_cast<uint8_t*>(f1->ldesc_l.ptr())};
+      std::vector<gfpl_map_pair> mp_(lm.cap_pt), ml_(lm.cap_ln);
+      int32_t mn[2];
+      gfpl_map_matches mm{1, lm.cap_pt, lm.cap_ln, &mn[0], &mn[1], mp_.data(), ml_.data()};
+      double Tr[16];
+      PLSLAM::inverse_se3(k1.T_kf_w).to_row_major(Tr);
+      orc_map_match(&ccam, &cfg, &lm, &w1b, Tr, &mm);
+      int cpn = 0, cln = 0;
+      map.matchLocalMap(k1p, cpn, cln);
+      printf("facade matchLocalMap: %d of %d forgotten points and %d of %d lines found again (oracle %d, %d)\n", cpn, np_, cln, nl_, mn[0], mn[1]);
+      EXPECT(cpn == mn[0] && cln == mn[1], "local-map matches vs oracle");
+      EXPECT(mn[0] > 10, "enough local-map point matches (%d)", mn[0]);
+      for (int k = 0; k < mn[0]; k++) {
+        EXPECT(f1->stereo_pt[mp_[k].kf_idx]->idx == cp_[mp_[k].map_idx]->idx, "landmark id of local-map pair %d", k);
+        EXPECT(cp_[mp_[k].map_idx]->kf_obs_list.back() == 1 && cp_[mp_[k].map_idx]->desc_list.size() == 2, "observation added for pair %d", k);
+      }
+      for (int k = 0; k < mn[1]; k++) EXPECT(f1->stereo_ls[ml_[k].kf_idx]->idx == cl_[ml_[k].map_idx]->idx, "landmark id of local-map line pair %d", k);
+    }
     for (auto* mp : map.map_points) delete mp;
     for (auto* ml : map.map_lines) delete ml;
   }

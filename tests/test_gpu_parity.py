@@ -501,3 +501,81 @@ def test_kf_match_lookForCommonMatches(ctx, orc):
     # (the line gate compares the re-projected kf0 line with kf0's OWN 2-D line, mapHandler.cpp:398: few lines survive motion)
     assert (o.n_pt > 50).all() and o.n_ln.sum() > 10 and (o.n_pt < kf0.n_pt).all()
     _cmp_obs(g, o)
+
+
+def _local_map(d, kf0, kf1, seed):
+    """local map = kf0's stereo landmarks (world = kf0 frame) + landmarks outside kf1's view; some kf1 features
+    already carry a landmark id (idx != -1) as after the KF<->KF half"""
+    rng = np.random.default_rng(seed)
+    B = kf0.B
+    extra_p, extra_l = 40, 12
+    m = S.LocalMapNP(B, kf0.cap_pt + extra_p, kf0.cap_ln + extra_l)
+    kf1 = kf1.copy()
+    for p in range(B):
+        n, nl = int(kf0.n_pt[p]), int(kf0.n_ln[p])
+        X = np.concatenate([kf0.pt["P"][p, :n], rng.uniform(-30, 30, (extra_p, 3))])   # extras: behind / outside
+        D = np.concatenate([kf0.pdesc[p, :n], rng.integers(0, 256, (extra_p, 32), dtype=np.uint8)])
+        perm = rng.permutation(len(X))
+        m.n_pt[p] = len(X); m.pt3d[p, :len(X)] = X[perm]; m.pdesc[p, :len(X)] = D[perm]
+        L = np.concatenate([np.concatenate([kf0.ln["sP"][p, :nl], kf0.ln["eP"][p, :nl]], 1),
+                            rng.uniform(-30, 30, (extra_l, 6))])
+        DL = np.concatenate([kf0.ldesc[p, :nl], rng.integers(0, 256, (extra_l, 32), dtype=np.uint8)])
+        perm = rng.permutation(len(L))
+        m.n_ln[p] = len(L); m.ln3d[p, :len(L)] = L[perm]; m.ldesc[p, :len(L)] = DL[perm]
+        kf1.pt["idx"][p] = np.where(rng.random(kf1.cap_pt) < 0.6, -1, 7)
+        kf1.ln["idx"][p] = np.where(rng.random(kf1.cap_ln) < 0.7, -1, 3)
+    return m, kf1
+
+
+def _cmp_map_matches(g, o):
+    assert np.array_equal(g.n_pt, o.n_pt) and np.array_equal(g.n_ln, o.n_ln)
+    for p in range(g.B):
+        assert np.array_equal(g.pt[p, :g.n_pt[p]], o.pt[p, :o.n_pt[p]])
+        assert np.array_equal(g.ln[p, :g.n_ln[p]], o.ln[p, :o.n_ln[p]])
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_map_match_lookForCommonMatches(ctx, orc, ragged):
+    """local map <-> KF half of MapHandler::lookForCommonMatches (mapHandler.cpp:509-770): index pairs bit-exact"""
+    d = _data(10, 1400, ragged=ragged)
+    kf0, kf1 = _frames(orc, ctx.cfg, d)
+    lmap, kf1 = _local_map(d, kf0, kf1, 9)
+    Twf = d["DT_true"].copy()
+    Twf[:, :3, 3] += np.random.default_rng(6).normal(0, 0.002, (10, 3))
+    g = ctx.map_match(lmap, kf1, Twf.reshape(-1, 16))
+    o = orc.map_match(d["cam"], ctx.cfg, lmap, kf1, Twf.reshape(-1, 16))
+    assert (o.n_pt > 10).all() and o.n_ln.sum() > 10
+    assert (kf1.pt["idx"][np.arange(10)[:, None], o.pt["kf_idx"]][np.arange(o.cap_pt)[None] < o.n_pt[:, None]] == -1).all()
+    _cmp_map_matches(g, o)
+
+
+def test_map_match_degenerate(ctx, orc):
+    d = _data(4, 1401, n_pt=64, n_ln=24)
+    kf0, kf1 = _frames(orc, ctx.cfg, d)
+    lmap, kf1 = _local_map(d, kf0, kf1, 10)
+    lmap.n_pt[0] = 0; lmap.n_ln[1] = 1                      # empty / single-row map sides (D3)
+    kf1.pt["idx"][2] = 5; kf1.ln["idx"][3] = 5              # nothing unmatched
+    Twf = d["DT_true"].reshape(-1, 16)
+    g = ctx.map_match(lmap, kf1, Twf)
+    o = orc.map_match(d["cam"], ctx.cfg, lmap, kf1, Twf)
+    assert o.n_pt[0] == 0 and o.n_ln[1] == 0 and o.n_pt[2] == 0 and o.n_ln[3] == 0
+    _cmp_map_matches(g, o)
+
+
+def test_medoid_desc_updateAverageDescDir(ctx, orc):
+    """representative descriptor of a landmark (mapFeatures.cpp:51-82): index bit-exact, incl. ties and long lists"""
+    rng = np.random.default_rng(77)
+    ns = np.concatenate([rng.integers(2, 12, 3000), [2, 33, 64, 150, 1, 0, 2]])
+    off = np.concatenate([[0], np.cumsum(ns)]).astype(np.int32)
+    base = rng.integers(0, 256, (len(ns), 32), dtype=np.uint8)
+    desc = np.repeat(base, ns, axis=0)
+    flip = (rng.random((len(desc), 256)) < 0.05)
+    desc ^= np.packbits(flip, axis=1)
+    desc[off[5]:off[6]] = desc[off[5]]                       # all-equal list: every statistic ties -> index 0
+    g = ctx.medoid_desc(desc, off)
+    o = orc.medoid_desc(desc, off)
+    assert np.array_equal(g, o) and g[5] == 0 and len(np.unique(g)) > 5
+    # tie-stress: low-entropy descriptors
+    t = np.zeros((4000, 32), np.uint8); t[:, 0] = rng.integers(0, 4, 4000)
+    off2 = np.arange(0, 4001, 8, dtype=np.int32)
+    assert np.array_equal(ctx.medoid_desc(t, off2), orc.medoid_desc(t, off2))
