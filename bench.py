@@ -107,6 +107,46 @@ def cpu_reference(a, rank_seed=0):
     return n, cores, step
 
 
+def cpu_extras(a):
+    """the single-thread figure of the oracle port and the OpenCV matcher's time for the matching
+    stage alone (cv2.BFMatcher is the matcher the reference itself calls)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    from gfpl import synth, _structs as S
+    n = min(a.pairs, 128)
+    d = synth.make_pairs(n, n_pt=a.n_pt, n_ln=a.n_ln, seed=2000)
+    cfg = orc.default_config()
+    flags = (0 if a.no_linecut else S.TRACK_LINECUT) | S.TRACK_SEED_GIVEN
+    prev = orc.stereo_match(d["cam"], cfg, d["prev_raw"])
+    t0 = time.perf_counter()
+    curr = orc.track(d["cam"], cfg, prev, d["state"], d["curr_raw"], flags, n_threads=1)[0]
+    extras = {"single_thread": {"value": n / (time.perf_counter() - t0), "unit": UNIT, "sample": "%d pairs" % n}}
+    try:
+        import cv2
+        raw, m = d["curr_raw"], min(n, 32)
+        bp, bl = cv2.BFMatcher(cv2.NORM_HAMMING, False), cv2.BFMatcher(cv2.NORM_HAMMING2, False)
+        bf = cv2.BFMatcher(cv2.NORM_HAMMING, False)
+        t0 = time.perf_counter()
+        for p in range(m):
+            pl, pr = raw.pdesc_l[p, :raw.n_pt_l[p]], raw.pdesc_r[p, :raw.n_pt_r[p]]
+            ll, lr = raw.ldesc_l[p, :raw.n_ln_l[p]], raw.ldesc_r[p, :raw.n_ln_r[p]]
+            bp.knnMatch(pl, pr, 2); bp.knnMatch(pr, pl, 2)                    # stereoFrame.cpp:807-808
+            bl.knnMatch(ll, lr, 2); bl.knnMatch(lr, ll, 2)                    # :896-897
+            a0, a1 = prev.pdesc[p, :prev.n_pt[p]], curr.pdesc[p, :curr.n_pt[p]]
+            b0, b1 = prev.ldesc[p, :prev.n_ln[p]], curr.ldesc[p, :curr.n_ln[p]]
+            bf.radiusMatch(a0, a1, float(cfg.point_match_radius))            # stereoFrameHandler.cpp:477-480
+            bf.radiusMatch(a1, a0, float(cfg.point_match_radius))
+            if len(b0) >= 2 and len(b1) >= 2:
+                bf.knnMatch(b0, b1, 2); bf.knnMatch(b1, b0, 2)                # :622-623
+        dt = time.perf_counter() - t0
+        extras["cv2_bfmatcher_matching_only"] = {"value": m / dt, "unit": "frame_pairs/s (matching calls only)",
+                                                 "cv2": cv2.__version__, "cv2_threads": cv2.getNumThreads(),
+                                                 "sample": "%d pairs, the 8 BFMatcher calls of one tracked frame pair" % m}
+    except Exception as e:  # cv2 is optional: the figure is a side note
+        extras["cv2_bfmatcher_matching_only"] = {"unavailable": repr(e)}
+    return extras
+
+
 def run_reference(a, rank):
     if rank != 0:
         return
@@ -132,6 +172,25 @@ class DevArray:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
 
 
+def bind_to_gpu_numa(local):
+    """Pin this rank's host threads (and hence its pinned staging buffers, first-touch) to the CPUs NVML reports as
+    local to its GPU: with several ranks per node the H2D stream otherwise crosses the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = ((os.cpu_count() or 64) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [i * 64 + b for i, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -145,6 +204,7 @@ def main():
     import torch.distributed as dist
     from gfpl import api, synth, _structs as S
     torch.cuda.set_device(local)
+    numa_cpus = bind_to_gpu_numa(local) if world > 1 else 0
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = a.pairs
@@ -305,7 +365,8 @@ def main():
                "dtype": "u8/int32 matching + f64 optimisation", "data": "synthetic", "config": workload_config(a),
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                        "ms_per_step": e2e_ms / a.steps, "pipeline": "%d resident slots / streams: H2D of step k overlaps the kernels of earlier steps; results consumed %d steps later" % (NSLOT, LAG),
-                       "timing": "host wall clock around K x (upload+run+download) + final sync, max over ranks"},
+                       "timing": "host wall clock around K x (upload+run+download) + final sync, max over ranks",
+                       "host_affinity_cpus": numa_cpus},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                "kernel_ms_per_step": dict(zip(["knn_stereo_pt", "knn_stereo_ln", "stereo_accept", "f2f_pt_search", "knn_f2f_ln",
                                                "f2f_accept", "uncertainty+linecut", "pose_gn", "step"], [float(x) for x in stage])),
@@ -317,6 +378,7 @@ def main():
             out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": "%d of %d pairs, one pass, %d std::threads over pairs (oracle port of the "
                                              "reference algorithm)" % (n, B, cores)}
+            out["cpu_baseline"].update(cpu_extras(a))
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

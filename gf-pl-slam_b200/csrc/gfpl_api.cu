@@ -193,6 +193,7 @@ void gfpl_config_default(gfpl_config* c) {
   c->f2f_point_window = 10.0; c->budget_slack = 1.2; c->cut_step = 0.05; c->cut_rng[0] = 0; c->cut_rng[1] = 1.0;
   c->mad_uninit_value = 0.0;
   c->max_kf_epip_p = 1.0; c->max_kf_epip_l = 1.0;
+  c->orb_nlevels = 4;
 }
 
 void gfpl_camera_euroc(gfpl_camera* c) {
@@ -452,6 +453,35 @@ int gfpl_stereo_match(gfpl_ctx* ctx, const gfpl_raw_frames* raw, int32_t variant
                        alloc_work(m, raw->B, raw->cap_pt, raw->cap_ln, &w));
   CHECK(run_stereo(ctx, draw, variant, w, dcur));
   CHECK(launch_stereo_accept(ctx, draw, variant, w.pt_lr, w.pt_rl, w.ln_lr, w.ln_rl, dcur));
+  download_stereo(ctx, out, dcur);
+  return finish(ctx);
+}
+
+int gfpl_stereo_match_orbslam(gfpl_ctx* ctx, const gfpl_raw_frames* raw, const gfpl_pyramid* pyr, gfpl_stereo_frames* out) {
+  if (!ctx) return GFPL_E_INVALID;
+  REQUIRE(ctx, raw && pyr && out && raw->B >= 0 && raw->B == out->B);
+  REQUIRE(ctx, out->cap_pt >= raw->cap_pt && out->cap_ln >= raw->cap_ln);
+  REQUIRE(ctx, pyr->data && pyr->n_levels == ctx->cfg.orb_nlevels && pyr->n_levels >= 1 && pyr->n_levels <= GFPL_MAX_PYR_LEVELS);
+  for (int l = 0; l < pyr->n_levels; l++) {
+    REQUIRE(ctx, pyr->width[l] > 0 && pyr->height[l] > 0 && pyr->row_stride[l] >= pyr->width[l] && pyr->offset[l] >= 0);
+    REQUIRE(ctx, pyr->offset[l] + (int64_t)pyr->row_stride[l] * (pyr->height[l] - 1) + pyr->width[l] <= pyr->frame_stride);
+  }
+  if (raw->B == 0) return GFPL_OK;
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DevMem m(ctx);
+  DevRawFrames draw;
+  DevStereoFrames dcur;
+  StepWork w;
+  REQUIRE_MEM(ctx, mirror_raw(m, raw, &draw) && alloc_stereo(m, raw->B, raw->cap_pt, raw->cap_ln, &dcur) &&
+                       alloc_work(m, raw->B, raw->cap_pt, raw->cap_ln, &w));
+  gfpl_pyramid dpyr = *pyr;
+  dpyr.data = m.upload(pyr->data, (size_t)raw->B * (size_t)pyr->frame_stride);
+  REQUIRE_MEM(ctx, dpyr.data);
+  if (ctx->cfg.has_lines)   // :633-767 == the line part of _Brute
+    CHECK(launch_knn2(ctx, raw->B, draw.ldesc_l, draw.n_ln_l, draw.cap_ln, draw.ldesc_r, draw.n_ln_r, draw.cap_ln,
+                      GFPL_NORM_HAMMING2, w.ln_lr, ctx->cfg.best_lr_matches ? w.ln_rl : Knn2Out{}));
+  CHECK(launch_stereo_accept(ctx, draw, GFPL_STEREO_BRUTE, w.pt_lr, w.pt_rl, w.ln_lr, w.ln_rl, dcur, /*lines_only=*/true));
+  CHECK(launch_stereo_orbslam_points(ctx, draw, dpyr, dcur));
   download_stereo(ctx, out, dcur);
   return finish(ctx);
 }

@@ -84,7 +84,9 @@ int launch_radius_fill(gfpl_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t
 
 // K3: stereo accept loops (points + lines) for B frames, one CTA per frame
 int launch_stereo_accept(gfpl_ctx* ctx, const DevRawFrames& raw, int variant, Knn2Out pt_lr, Knn2Out pt_rl,
-                         Knn2Out ln_lr, Knn2Out ln_rl, DevStereoFrames out);
+                         Knn2Out ln_lr, Knn2Out ln_rl, DevStereoFrames out, bool lines_only = false);
+// point part of extractStereoFeatures_ORBSLAM (row-band search + SAD refinement); dpyr.data is a device pointer
+int launch_stereo_orbslam_points(gfpl_ctx* ctx, const DevRawFrames& raw, const gfpl_pyramid& dpyr, DevStereoFrames out);
 int launch_stereo_uncertainty(gfpl_ctx* ctx, const DevStereoFrames& fr, gfpl_line_cov* out);
 int launch_expand_prev(gfpl_ctx* ctx, const gfpl_prev_frames& slim_dev, DevStereoFrames fr);
 

@@ -235,13 +235,15 @@ stereo_accept_kernel(DevRawFrames raw, int variant, Knn2Out pt_lr, Knn2Out pt_rl
 }
 
 int launch_stereo_accept(gfpl_ctx* ctx, const DevRawFrames& raw, int variant, Knn2Out pt_lr, Knn2Out pt_rl,
-                         Knn2Out ln_lr, Knn2Out ln_rl, DevStereoFrames out) {
+                         Knn2Out ln_lr, Knn2Out ln_rl, DevStereoFrames out, bool lines_only) {
   if (raw.B <= 0) return GFPL_OK;
   const size_t smem = (size_t)(raw.cap_ln > 0 ? raw.cap_ln : 1) * sizeof(float);
   if (smem > 48 * 1024)
     GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(stereo_accept_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gfpl_config cfg = ctx->cfg;
+  if (lines_only) cfg.has_points = 0;  // the point part then only writes n_pt = 0 (overwritten by the caller's point kernel)
   stereo_accept_kernel<<<raw.B, ACCEPT_THREADS, smem, ctx->stream>>>(raw, variant, pt_lr, pt_rl, ln_lr, ln_rl, out,
-                                                                      ctx->cam, ctx->cfg);
+                                                                      ctx->cam, cfg);
   GFPL_LAUNCH_OK(ctx);
   return GFPL_OK;
 }

@@ -70,7 +70,10 @@ void StereoFrame::stereoMatch(int variant) {
   vector<uint8_t> pd((size_t)cap_pt * 32), ld((size_t)cap_ln * 32);
   int32_t n_pt = 0, n_ln = 0;
   gfpl_stereo_frames out{1, cap_pt, cap_ln, &n_pt, &n_ln, pt.data(), pd.data(), ln.data(), ld.data()};
-  gfpl_->check(gfpl_stereo_match(gfpl_->get(), &raw, variant, &out));
+  if (variant == GFPL_STEREO_ORBSLAM)
+    gfpl_->check(gfpl_stereo_match_orbslam(gfpl_->get(), &raw, &right_pyramid, &out));
+  else
+    gfpl_->check(gfpl_stereo_match(gfpl_->get(), &raw, variant, &out));
 
   for (auto* p : stereo_pt) delete p;
   for (auto* l : stereo_ls) delete l;
@@ -82,8 +85,10 @@ void StereoFrame::stereoMatch(int variant) {
     for (int i = 0; i < 3; i++) f->P(i) = pt[k].P[i];
     f->idx = pt[k].idx; f->level = pt[k].level; f->sigma2 = pt[k].sigma2;
     stereo_pt.push_back(f);
-    points_l[pt[k].src_l].class_id = k;
-    points_r[pt[k].src_r].class_id = k;
+    if (variant != GFPL_STEREO_ORBSLAM) {  // commented out in _ORBSLAM (:616-620)
+      points_l[pt[k].src_l].class_id = k;
+      points_r[pt[k].src_r].class_id = k;
+    }
   }
   pdesc_l.resize(n_pt);  // pdesc_l_.copyTo(pdesc_l) (:878): row k <-> stereo_pt[k]
   if (n_pt) std::memcpy(pdesc_l.ptr(), pd.data(), (size_t)n_pt * 32);
@@ -101,6 +106,7 @@ void StereoFrame::stereoMatch(int variant) {
 
 void StereoFrame::extractInitialStereoFeatures(int) { stereoMatch(GFPL_STEREO_INITIAL); }
 void StereoFrame::extractStereoFeatures_Brute(int) { stereoMatch(GFPL_STEREO_BRUTE); }
+void StereoFrame::extractStereoFeatures_ORBSLAM(int) { stereoMatch(GFPL_STEREO_ORBSLAM); }
 
 void StereoFrame::knn(int norm, const DescMat& a, const DescMat& b, vector<vector<DMatch>>& out) {
   out.clear();

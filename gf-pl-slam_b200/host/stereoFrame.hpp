@@ -123,6 +123,10 @@ class StereoFrame {
   // stereoFrame.h:104-106 — the matching half (knn both ways, accept loops, back-projection)
   void extractInitialStereoFeatures(int fast_th = 20);   // stereoFrame.cpp:148-336
   void extractStereoFeatures_Brute(int fast_th = 20);    // stereoFrame.cpp:770-1016
+  // stereoFrame.cpp:410-768 (the default of stereoFrameHandler.cpp:91); needs orbExtractor_r->mvImagePyramid:
+  void setRightPyramid(const gfpl_pyramid& pyr) { right_pyramid = pyr; }   // one frame (data -> that frame's block)
+  void extractStereoFeatures_ORBSLAM(int fast_th = 20);
+  gfpl_pyramid right_pyramid{};
 
   // stereoFrame.h:116-132 — cv::BFMatcher wrappers (stereoFrame.cpp:1229-1257)
   void matchPointFeatures(BFMatcher* bfm, const DescMat& pdesc_1, const DescMat& pdesc_2,

@@ -40,6 +40,7 @@ class Config(C.Structure):
         ("lambda_lba_lm", C.c_double), ("lambda_lba_k", C.c_double), ("f2f_point_window", C.c_double),
         ("budget_slack", C.c_double), ("cut_step", C.c_double), ("cut_rng", C.c_double * 2),
         ("mad_uninit_value", C.c_double), ("max_kf_epip_p", C.c_double), ("max_kf_epip_l", C.c_double),
+        ("orb_nlevels", C.c_int32), ("_pad0", C.c_int32),
     ]
 
 
@@ -87,6 +88,37 @@ class RawFrames(C.Structure):
 class StereoFrames(C.Structure):
     _fields_ = [("B", C.c_int32), ("cap_pt", C.c_int32), ("cap_ln", C.c_int32),
                 ("n_pt", _vp), ("n_ln", _vp), ("pt", _vp), ("pdesc", _vp), ("ln", _vp), ("ldesc", _vp)]
+
+
+MAX_PYR_LEVELS = 8
+
+
+class Pyramid(C.Structure):
+    _fields_ = [("n_levels", C.c_int32), ("width", C.c_int32 * MAX_PYR_LEVELS), ("height", C.c_int32 * MAX_PYR_LEVELS),
+                ("row_stride", C.c_int32 * MAX_PYR_LEVELS), ("offset", C.c_int64 * MAX_PYR_LEVELS),
+                ("frame_stride", C.c_int64), ("data", _vp)]
+
+
+class PyramidNP:
+    """right-image pyramids of B frames, levels packed back to back (row stride = width)"""
+
+    def __init__(self, B, sizes):
+        self.B, self.sizes = B, [(int(w), int(h)) for w, h in sizes]
+        self.offsets = np.concatenate([[0], np.cumsum([w * h for w, h in self.sizes])]).astype(np.int64)
+        self.data = np.zeros((B, int(self.offsets[-1])), np.uint8)
+
+    def level(self, p, l):
+        w, h = self.sizes[l]
+        return self.data[p, self.offsets[l]:self.offsets[l + 1]].reshape(h, w)
+
+    def view(self):
+        v = Pyramid()
+        v.n_levels = len(self.sizes)
+        for l, (w, h) in enumerate(self.sizes):
+            v.width[l], v.height[l], v.row_stride[l], v.offset[l] = w, h, w, int(self.offsets[l])
+        v.frame_stride = int(self.offsets[-1])
+        v.data = ptr(self.data)
+        return v
 
 
 class LocalMap(C.Structure):

@@ -171,6 +171,13 @@ class Context:
         self._check(lib().gfpl_stereo_match(self._h, C.byref(rv), variant, C.byref(ov)))
         return out
 
+    def stereo_match_orbslam(self, raw, pyr):
+        """extractStereoFeatures_ORBSLAM after detection: row-band point stereo + SAD refinement; lines as _Brute"""
+        out = S.StereoFramesNP(raw.B, raw.cap_pt, raw.cap_ln)
+        rv, pv, ov = raw.view(), pyr.view(), out.view()
+        self._check(lib().gfpl_stereo_match_orbslam(self._h, C.byref(rv), C.byref(pv), C.byref(ov)))
+        return out
+
     def stereo_uncertainty(self, frames):
         out = np.zeros((frames.B, frames.cap_ln), S.line_cov_dt)
         fv = frames.view()

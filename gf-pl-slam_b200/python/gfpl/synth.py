@@ -299,3 +299,23 @@ def make_lba_window(seed=0, shape="kitti", n_kf=10, n_pt=1000, n_ls=300, pt_obs_
                 pt_obs_fix=fix, pt_obs_uv=pt_uv, pt_obs_s2=np.ones(len(lm)), ls_obs_lm=llm, ls_obs_kf=lkf,
                 ls_obs_fix=lfix, ls_obs_le=le, ls_obs_s2=np.ones(len(llm)),
                 fix_Tkw=Tkw_all[n_kf:].reshape(n_fix, 16), cam=camera(shape))
+
+
+def make_right_pyramids(B, cam, n_levels=4, scale_factor=1.2, seed=0):
+    """Synthetic right-image pyramids (CV_8UC1) for the ORB-SLAM style stereo refinement: smooth random texture per
+    level, sizes as ORBextractor::ComputePyramid (ORBextractor.cc:1107-1112, float scale tables)."""
+    rng = np.random.default_rng(seed)
+    sf = [np.float32(1.0)]
+    for _ in range(1, n_levels):
+        sf.append(np.float32(sf[-1] * np.float32(scale_factor)))
+    isf = [np.float32(1.0) / s for s in sf]
+    sizes = [(int(np.rint(np.float32(cam.width) * s)), int(np.rint(np.float32(cam.height) * s))) for s in isf]
+    pyr = S.PyramidNP(B, sizes)
+    for p in range(B):
+        for l, (w, h) in enumerate(sizes):
+            coarse = rng.integers(0, 256, (h // 4 + 2, w // 4 + 2)).astype(np.float32)
+            img = np.kron(coarse, np.ones((4, 4), np.float32))[:h, :w]
+            img = 0.25 * (img + np.roll(img, 1, 0) + np.roll(img, 1, 1) + np.roll(img, (1, 1), (0, 1)))
+            img += rng.integers(-6, 7, (h, w))
+            pyr.level(p, l)[:] = np.clip(img, 0, 255).astype(np.uint8)
+    return pyr

@@ -109,6 +109,8 @@ typedef struct gfpl_config {
   /* map matching (MapHandler::lookForCommonMatches) */
   double max_kf_epip_p;        /* config.cpp:42 1.0 */
   double max_kf_epip_l;        /* config.cpp:43 1.0 */
+  int32_t orb_nlevels;         /* config.cpp:136 4 */
+  int32_t _pad0;
 } gfpl_config;
 
 void gfpl_config_default(gfpl_config* cfg);
@@ -341,6 +343,30 @@ int gfpl_radius_hamming256(gfpl_ctx* ctx, const uint8_t* q, int32_t nq, const ui
  * knn k=2 L->R and R->L, mutual check, ratio / gap test, epipolar, disparity, overlap and
  * covariance gates, back-projection, descriptor compaction.  Detection is injected through `raw`. */
 int gfpl_stereo_match(gfpl_ctx* ctx, const gfpl_raw_frames* raw, int32_t variant, gfpl_stereo_frames* out);
+
+/* StereoFrame::extractStereoFeatures_ORBSLAM after detectFeatures (stereoFrame.cpp:453-767) — the
+ * point stereo the reference runs by default (stereoFrameHandler.cpp:91).  Points: for every left key point the right
+ * key points of its row band (|octave difference| <= 1, uL - fx <= uR <= uL), best StereoFrame::descriptorDistance
+ * (stereoFrame.h:185-201, < 100, first minimum), accepted below thOrbDist = 80; 11x11 SAD sliding window +-5 px with
+ * parabola refinement on the pyramid level of the left key point (subPixelStereoRefine_ORBSLAM :340-404, which reads
+ * BOTH windows from the RIGHT extractor's pyramid, :358/:376 — reproduced); survivors sorted by (distance, left index),
+ * cut at 1.5*1.4*median distance; stereo_pt comes out in that order.  Lines: identical to GFPL_STEREO_BRUTE (:633-767).
+ * Defined where the reference would throw or read out of range: a window that leaves its pyramid level (cv::Mat
+ * rowRange / colRange assert) counts as "no refinement" (disparity -1); no accepted point at all (vDistIdx[0] of an
+ * empty vector, :587) gives an empty stereo_pt. */
+#define GFPL_STEREO_ORBSLAM 2 /* names the variant for callers; gfpl_stereo_match itself takes 0 or 1 only */
+#define GFPL_MAX_PYR_LEVELS 8
+typedef struct gfpl_pyramid {
+  int32_t n_levels;                      /* == cfg.orb_nlevels */
+  int32_t width[GFPL_MAX_PYR_LEVELS];    /* mvImagePyramid[l].cols */
+  int32_t height[GFPL_MAX_PYR_LEVELS];   /* mvImagePyramid[l].rows */
+  int32_t row_stride[GFPL_MAX_PYR_LEVELS]; /* bytes between rows of level l (Mat::step) */
+  int64_t offset[GFPL_MAX_PYR_LEVELS];   /* byte offset of pixel (0,0) of level l inside one frame's block */
+  int64_t frame_stride;                  /* bytes between the blocks of consecutive frames */
+  const uint8_t* data;                   /* [B] blocks: orbExtractor_r->mvImagePyramid of every frame (CV_8UC1) */
+} gfpl_pyramid;
+int gfpl_stereo_match_orbslam(gfpl_ctx* ctx, const gfpl_raw_frames* raw, const gfpl_pyramid* right_pyramid,
+                              gfpl_stereo_frames* out);
 
 /* StereoFrame::estimateStereoUncertainty (stereoFrame.cpp:1448-1484): covSpt3D/covEpt3D for
  * every stereo line. out: [B][cap_ln]. */

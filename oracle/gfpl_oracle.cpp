@@ -14,6 +14,7 @@
 #include "gfpl_oracle.h"
 #include "orc_math.h"
 
+#include <climits>
 #include <cstdlib>
 #include <map>
 #include <thread>
@@ -40,6 +41,7 @@ extern "C" void orc_config_default(gfpl_config* c) {
   c->f2f_point_window = 10.0; c->budget_slack = 1.2; c->cut_step = 0.05; c->cut_rng[0] = 0; c->cut_rng[1] = 1.0;
   c->mad_uninit_value = 0.0;
   c->max_kf_epip_p = 1.0; c->max_kf_epip_l = 1.0;  // config.cpp:42-43
+  c->orb_nlevels = 4;                              // :136
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -349,6 +351,163 @@ extern "C" int orc_stereo_match(const gfpl_camera* cam, const gfpl_config* cfg, 
                                 int32_t variant, gfpl_stereo_frames* out) {
   if (!cam || !cfg || !raw || !out || out->cap_pt < raw->cap_pt || out->cap_ln < raw->cap_ln) return GFPL_E_INVALID;
   for (int p = 0; p < raw->B; p++) stereo_match_one(cam, cfg, raw, variant, out, p);
+  return GFPL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// StereoFrame::extractStereoFeatures_ORBSLAM, point part (stereoFrame.cpp:453-630) + subPixelStereoRefine_ORBSLAM (:340-404)
+// ------------------------------------------------------------------------------------------------
+// ORBextractor's scale tables (ORBextractor.cc:415-431): float arithmetic, scaleFactor passed as float
+static void orb_scale_tables(const gfpl_config* cfg, int n, float* sf, float* isf) {
+  const float scaleFactor = (float)cfg->orb_scale_factor;
+  sf[0] = 1.0f;
+  for (int i = 1; i < n; i++) sf[i] = sf[i - 1] * scaleFactor;
+  for (int i = 0; i < n; i++) isf[i] = 1.0f / sf[i];
+}
+
+static void subpixel_refine_orbslam(const gfpl_pyramid* pyr, const uint8_t* frame, const float* sf, const float* isf,
+                                    const gfpl_keypoint& kpL, const gfpl_keypoint& kpR, float& disparity, float& bestuR) {
+  disparity = -1;
+  bestuR = kpR.x;
+  if (kpL.octave < 0 || kpL.octave >= pyr->n_levels) return;  // precondition of the reference (vector index)
+  const float uR0 = kpR.x;
+  const float scaleFactor = isf[kpL.octave];
+  const float scaleduL = roundf(kpL.x * scaleFactor);
+  const float scaledvL = roundf(kpL.y * scaleFactor);
+  const float scaleduR0 = roundf(uR0 * scaleFactor);
+  const int w = 5, L = 5;
+  const int W = pyr->width[kpL.octave], H = pyr->height[kpL.octave], step = pyr->row_stride[kpL.octave];
+  const uint8_t* img = frame + pyr->offset[kpL.octave];   // both windows come from the RIGHT pyramid (:358, :376)
+  const int r0 = (int)(scaledvL - w), r1 = (int)(scaledvL + w + 1);
+  const int cl0 = (int)(scaleduL - w), cl1 = (int)(scaleduL + w + 1);
+  if (r0 < 0 || r1 > H || cl0 < 0 || cl1 > W) return;       // defined: cv::Mat::rowRange/colRange would throw
+  const float iniu = scaleduR0 + L - w;
+  const float endu = scaleduR0 + L + w + 1;
+  if (iniu < 0 || endu >= W) return;                          // :370-371
+  if ((int)(scaleduR0 - L - w) < 0) return;                   // defined: first window's colRange would throw
+  float IL[11][11];
+  for (int i = 0; i < 11; i++)
+    for (int j = 0; j < 11; j++) IL[i][j] = (float)img[(size_t)(r0 + i) * step + cl0 + j];
+  const float cL = IL[w][w];
+  for (int i = 0; i < 11; i++)
+    for (int j = 0; j < 11; j++) IL[i][j] = IL[i][j] - cL;
+  int bestDist = INT_MAX, bestincR = 0;
+  float vDists[2 * 5 + 1];
+  for (int incR = -L; incR <= +L; incR++) {
+    const int c0 = (int)(scaleduR0 + incR - w);
+    const float cR = (float)img[(size_t)(r0 + w) * step + c0 + w];
+    double acc = 0.0;                                          // cv::norm(NORM_L1) on CV_32F accumulates in double
+    for (int i = 0; i < 11; i++)
+      for (int j = 0; j < 11; j++) {
+        const float ir = (float)img[(size_t)(r0 + i) * step + c0 + j] - cR;
+        acc += std::fabs(IL[i][j] - ir);
+      }
+    const float dist = (float)acc;
+    if (dist < bestDist) { bestDist = dist; bestincR = incR; }
+    vDists[L + incR] = dist;
+  }
+  if (bestincR == -L || bestincR == L) return;
+  const float dist1 = vDists[L + bestincR - 1], dist2 = vDists[L + bestincR], dist3 = vDists[L + bestincR + 1];
+  const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+  if (deltaR < -1 || deltaR > 1) return;
+  bestuR = sf[kpL.octave] * ((float)scaleduR0 + (float)bestincR + deltaR);
+  disparity = (kpL.x - bestuR);
+}
+
+static int stereo_points_orbslam(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_pyramid* pyr,
+                                 const uint8_t* frame, int N, const gfpl_keypoint* kl, const uint8_t* dl, int Nr,
+                                 const gfpl_keypoint* kr, const uint8_t* dr, gfpl_point_feature* out, uint8_t* out_desc) {
+  if (!cfg->has_points || N == 0 || Nr == 0) return 0;  // :453
+  float sf[GFPL_MAX_PYR_LEVELS], isf[GFPL_MAX_PYR_LEVELS];
+  orb_scale_tables(cfg, pyr->n_levels, sf, isf);
+  const int thOrbDist = 80;
+  const int nRows = pyr->height[0];
+  std::vector<std::vector<size_t>> vRowIndices(nRows);
+  std::vector<float> mvuRight(N, -1.0f), mvDepth(N, -1.0f);
+  std::vector<int> src_r(N, -1);
+  for (int iR = 0; iR < Nr; iR++) {
+    const float kpY = kr[iR].y;
+    const float r = 2.0f * sf[kr[iR].octave];
+    const int maxr = (int)ceilf(kpY + r);
+    const int minr = (int)floorf(kpY - r);
+    for (int yi = minr; yi <= maxr; yi++)
+      if (yi >= 0 && yi < nRows) vRowIndices[yi].push_back(iR);   // rows outside the table are UB in the reference
+  }
+  const float minD = 0;
+  const float maxD = cam->fx;
+  const float mbf = cam->fx * cam->b;
+  std::vector<std::pair<int, int>> vDistIdx;
+  for (int iL = 0; iL < N; iL++) {
+    const gfpl_keypoint& kpL = kl[iL];
+    const int levelL = kpL.octave;
+    const float vL = kpL.y, uL = kpL.x;
+    if (!(vL >= 0) || (size_t)vL >= (size_t)nRows) continue;      // vRowIndices[vL] out of range: UB in the reference
+    const std::vector<size_t>& vCandidates = vRowIndices[(size_t)vL];
+    if (vCandidates.empty()) continue;
+    const float minU = uL - maxD;
+    const float maxU = uL - minD;
+    if (maxU < 0) continue;
+    int bestDist = 100;
+    size_t bestIdxR = 0;
+    for (size_t iC = 0; iC < vCandidates.size(); iC++) {
+      const size_t iR = vCandidates[iC];
+      const gfpl_keypoint& kpR = kr[iR];
+      if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
+      const float uR = kpR.x;
+      if (uR >= minU && uR <= maxU) {
+        const int dist = hamming256(dl + (size_t)iL * 32, dr + iR * 32);   // descriptorDistance (stereoFrame.h:185-201)
+        if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+      }
+    }
+    if (bestDist < thOrbDist) {
+      float disparity, bestuR;
+      subpixel_refine_orbslam(pyr, frame, sf, isf, kpL, kr[bestIdxR], disparity, bestuR);
+      if (disparity >= minD && disparity < maxD) {
+        if (disparity <= 0) { disparity = 0.01; bestuR = uL - 0.01; }
+        mvDepth[iL] = mbf / disparity;
+        mvuRight[iL] = bestuR;
+        src_r[iL] = (int)bestIdxR;
+        vDistIdx.push_back(std::pair<int, int>(bestDist, iL));
+      }
+    }
+  }
+  if (vDistIdx.empty()) return 0;   // defined: the reference indexes vDistIdx[0] of an empty vector (:587)
+  std::sort(vDistIdx.begin(), vDistIdx.end());
+  const float median = vDistIdx[vDistIdx.size() / 2].first;
+  const float thDist = 1.5f * 1.4f * median;
+  int pt_idx = 0;
+  for (size_t i = 0; i < vDistIdx.size(); i++) {
+    if (vDistIdx[i].first >= thDist) break;
+    const int iL = vDistIdx[i].second;
+    const float disparity = mbf / mvDepth[iL];
+    if (disparity < 0) continue;
+    gfpl_point_feature& f = out[pt_idx];
+    f.pl[0] = kl[iL].x; f.pl[1] = kl[iL].y;
+    back_projection(cam, f.pl[0], f.pl[1], disparity, f.P);
+    f.disp = disparity;
+    f.level = kl[iL].octave;
+    f.sigma2 = level_sigma2(f.level, cfg->orb_scale_factor);
+    f.idx = pt_idx; f.src_l = iL; f.src_r = src_r[iL];
+    std::memcpy(out_desc + (size_t)pt_idx * 32, dl + (size_t)iL * 32, 32);
+    pt_idx++;
+  }
+  return pt_idx;
+}
+
+extern "C" int orc_stereo_match_orbslam(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_raw_frames* raw,
+                                        const gfpl_pyramid* pyr, gfpl_stereo_frames* out) {
+  if (!cam || !cfg || !raw || !pyr || !out || out->cap_pt < raw->cap_pt || out->cap_ln < raw->cap_ln) return GFPL_E_INVALID;
+  if (pyr->n_levels != cfg->orb_nlevels || pyr->n_levels < 1 || pyr->n_levels > GFPL_MAX_PYR_LEVELS) return GFPL_E_INVALID;
+  for (int p = 0; p < raw->B; p++) {
+    size_t op = (size_t)p * raw->cap_pt, ol = (size_t)p * raw->cap_ln;
+    size_t oop = (size_t)p * out->cap_pt, ool = (size_t)p * out->cap_ln;
+    out->n_pt[p] = stereo_points_orbslam(cam, cfg, pyr, pyr->data + (size_t)p * pyr->frame_stride, raw->n_pt_l[p],
+                                         raw->pt_l + op, raw->pdesc_l + op * 32, raw->n_pt_r[p], raw->pt_r + op,
+                                         raw->pdesc_r + op * 32, out->pt + oop, out->pdesc + oop * 32);
+    out->n_ln[p] = stereo_lines(cam, cfg, GFPL_STEREO_BRUTE, raw->n_ln_l[p], raw->ln_l + ol, raw->ldesc_l + ol * 32,
+                                raw->n_ln_r[p], raw->ln_r + ol, raw->ldesc_r + ol * 32, out->ln + ool,
+                                out->ldesc + ool * 32);   // :633-767 == :881-1014
+  }
   return GFPL_OK;
 }
 

@@ -29,6 +29,8 @@ double orc_vector_stdv_mad(const double* residues, int32_t n);
 
 int orc_stereo_match(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_raw_frames* raw, int32_t variant,
                      gfpl_stereo_frames* out);
+int orc_stereo_match_orbslam(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_raw_frames* raw,
+                             const gfpl_pyramid* right_pyramid, gfpl_stereo_frames* out);
 int orc_stereo_uncertainty(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_stereo_frames* frames,
                            gfpl_line_cov* out);
 int orc_f2f_match(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_stereo_frames* prev,

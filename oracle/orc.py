@@ -101,6 +101,14 @@ def stereo_match(cam, cfg, raw, variant=S.STEREO_BRUTE):
     return out
 
 
+def stereo_match_orbslam(cam, cfg, raw, pyr):
+    out = S.StereoFramesNP(raw.B, raw.cap_pt, raw.cap_ln)
+    rv, pv, ov = raw.view(), pyr.view(), out.view()
+    rc = lib().orc_stereo_match_orbslam(C.byref(cam), C.byref(cfg), C.byref(rv), C.byref(pv), C.byref(ov))
+    assert rc == 0, rc
+    return out
+
+
 def stereo_uncertainty(cam, cfg, frames):
     out = np.zeros((frames.B, frames.cap_ln), S.line_cov_dt)
     fv = frames.view()

@@ -77,6 +77,8 @@ static gfpl_raw_frames raw_view(const Raw& r, std::vector<gfpl_keypoint>& kl, st
   return gfpl_raw_frames{1, n[0], n[2], &n[0], &n[1], &n[2], &n[3], kl.data(), kr.data(), r.dl.ptr(), r.dr.ptr(), ll.data(), lr.data(), r.ldl.ptr(), r.ldr.ptr()};
 }
 
+static int test_orbslam_stereo(const Raw& r1, PinholeStereoCamera& cam, GfplContext& gf);
+
 static int test_tracking() {
   PinholeStereoCamera cam(752, 480, 458.654, 458.654, 367.215, 248.375, 0.110078);
   GfplContext gf(cam.c_abi());
@@ -250,9 +252,53 @@ static int test_tracking() {
     for (auto* mp : map.map_points) delete mp;
     for (auto* ml : map.map_lines) delete ml;
   }
+  if (test_orbslam_stereo(r1, cam, gf)) return 1;
   StVO.updateFrame();
   EXPECT(StVO.prev_frame == f1 && StVO.curr_frame == nullptr, "updateFrame");
   delete f1;
+  return 0;
+}
+
+// StereoFrame::extractStereoFeatures_ORBSLAM through the facade vs the oracle (same detector output + right pyramid)
+static int test_orbslam_stereo(const Raw& r1, PinholeStereoCamera& cam, GfplContext& gf) {
+  gfpl_camera ccam = cam.c_abi();
+  gfpl_config cfg;
+  orc_config_default(&cfg);
+  gfpl_pyramid pyr{};
+  pyr.n_levels = cfg.orb_nlevels;
+  float sf = 1.0f;
+  int64_t off = 0;
+  for (int l = 0; l < pyr.n_levels; l++) {
+    const float isf = 1.0f / sf;
+    pyr.width[l] = (int)std::lround(752.0f * isf); pyr.height[l] = (int)std::lround(480.0f * isf);
+    pyr.row_stride[l] = pyr.width[l] + 38;          // a bordered Mat like ORBextractor::ComputePyramid's (step > cols)
+    pyr.offset[l] = off;
+    off += (int64_t)pyr.row_stride[l] * pyr.height[l];
+    sf = sf * (float)cfg.orb_scale_factor;
+  }
+  pyr.frame_stride = off;
+  std::vector<uint8_t> img((size_t)off);
+  uint32_t x = 12345u;
+  for (size_t i = 0; i < img.size(); i++) { x = x * 1664525u + 1013904223u; img[i] = (uint8_t)(((i / 3) * 7 + (x >> 28)) & 0xff); }
+  pyr.data = img.data();
+  StereoFrame f(2, &cam, &gf, 0.1);
+  f.setFeatures(r1.pl, r1.dl, r1.pr, r1.dr, r1.ll, r1.ldl, r1.lr, r1.ldr);
+  f.setRightPyramid(pyr);
+  f.extractStereoFeatures_ORBSLAM();
+  std::vector<gfpl_keypoint> kl, kr; std::vector<gfpl_keyline> ll, lr;
+  int32_t n[4];
+  gfpl_raw_frames raw = raw_view(r1, kl, kr, ll, lr, n);
+  std::vector<gfpl_point_feature> pt(n[0]); std::vector<gfpl_line_feature> ln(n[2]);
+  std::vector<uint8_t> pd((size_t)n[0] * 32), ld((size_t)n[2] * 32);
+  int32_t on[2];
+  gfpl_stereo_frames out{1, n[0], n[2], &on[0], &on[1], pt.data(), pd.data(), ln.data(), ld.data()};
+  EXPECT(orc_stereo_match_orbslam(&ccam, &cfg, &raw, &pyr, &out) == 0, "oracle call");
+  printf("facade extractStereoFeatures_ORBSLAM: %zu points, %zu lines (oracle %d, %d)\n", f.stereo_pt.size(), f.stereo_ls.size(), on[0], on[1]);
+  EXPECT((int)f.stereo_pt.size() == on[0] && (int)f.stereo_ls.size() == on[1] && on[0] > 10, "counts vs oracle");
+  for (int k = 0; k < on[0]; k++) {
+    EXPECT(f.stereo_pt[k]->disp == pt[k].disp && f.stereo_pt[k]->P(2) == pt[k].P[2] && f.stereo_pt[k]->pl(0) == pt[k].pl[0], "stereo point %d", k);
+    EXPECT(std::memcmp(f.pdesc_l.ptr(k), &pd[(size_t)k * 32], 32) == 0, "descriptor row %d", k);
+  }
   return 0;
 }
 

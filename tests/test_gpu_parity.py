@@ -579,3 +579,36 @@ def test_medoid_desc_updateAverageDescDir(ctx, orc):
     t = np.zeros((4000, 32), np.uint8); t[:, 0] = rng.integers(0, 4, 4000)
     off2 = np.arange(0, 4001, 8, dtype=np.int32)
     assert np.array_equal(ctx.medoid_desc(t, off2), orc.medoid_desc(t, off2))
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_stereo_match_orbslam(ctx, orc, ragged):
+    """extractStereoFeatures_ORBSLAM (stereoFrame.cpp:453-767): row-band search, SAD refinement, median cut — bit-exact"""
+    d = _data(8, 1500, ragged=ragged)
+    pyr = synth.make_right_pyramids(8, d["cam"], seed=3)
+    g = ctx.stereo_match_orbslam(d["curr_raw"], pyr)
+    o = orc.stereo_match_orbslam(d["cam"], ctx.cfg, d["curr_raw"], pyr)
+    assert (o.n_pt > 15).all() and (o.n_ln > 3).all()
+    _cmp_stereo(g, o)
+    # output order = ascending (descriptor distance, left index): left indices are not monotone
+    assert any((np.diff(o.pt["src_l"][p, :o.n_pt[p]]) < 0).any() for p in range(8))
+
+
+def test_stereo_match_orbslam_dense_and_degenerate(ctx, orc):
+    d = _data(1, 1501, n_pt=2500, n_ln=40)               # > 8 key points per thread
+    pyr = synth.make_right_pyramids(1, d["cam"], seed=4)
+    o = orc.stereo_match_orbslam(d["cam"], ctx.cfg, d["curr_raw"], pyr)
+    assert o.n_pt[0] > 200
+    _cmp_stereo(ctx.stereo_match_orbslam(d["curr_raw"], pyr), o)
+    d = _data(4, 1502, n_pt=64, n_ln=24)
+    pyr = synth.make_right_pyramids(4, d["cam"], seed=5)
+    raw = d["curr_raw"]
+    raw.n_pt_l[0] = 0; raw.n_pt_r[1] = 0                                   # :453
+    raw.pdesc_r[2] = 255 - raw.pdesc_r[2]                                  # no candidate below thOrbDist -> empty vDistIdx
+    raw.pt_l["x"][3, :32] = 3.0                                            # windows leaving the level (defined: no match)
+    o = orc.stereo_match_orbslam(d["cam"], ctx.cfg, raw, pyr)
+    assert o.n_pt[0] == 0 and o.n_pt[1] == 0 and o.n_pt[2] == 0
+    _cmp_stereo(ctx.stereo_match_orbslam(raw, pyr), o)
+    with pytest.raises(Exception):
+        bad = synth.make_right_pyramids(4, d["cam"], n_levels=3, seed=5)   # n_levels != cfg.orb_nlevels
+        ctx.stereo_match_orbslam(raw, bad)
