@@ -973,36 +973,92 @@ int gfpl_timer_elapsed_ms(gfpl_ctx* ctx, int32_t a, int32_t b, float* ms) {
 }
 
 // ---- L2 ---------------------------------------------------------------------------------------------------
+// device copies of an LBA window and of its block storage
+static bool mirror_lba(DevMem& m, const gfpl_lba_problem* pb, gfpl_lba_problem* d, gfpl_lba_blocks* o) {
+  *d = *pb;
+  d->kf_Tkw = m.upload(pb->kf_Tkw, (size_t)pb->Nkf * 16);
+  d->X_pt = m.upload(pb->X_pt, (size_t)pb->Npt * 3);
+  d->X_ls = m.upload(pb->X_ls, (size_t)pb->Nls * 6);
+  d->pt_obs_lm = m.upload(pb->pt_obs_lm, pb->n_pt_obs); d->pt_obs_kf = m.upload(pb->pt_obs_kf, pb->n_pt_obs);
+  d->pt_obs_fix = m.upload(pb->pt_obs_fix, pb->n_pt_obs);
+  d->pt_obs_uv = m.upload(pb->pt_obs_uv, (size_t)pb->n_pt_obs * 2); d->pt_obs_s2 = m.upload(pb->pt_obs_s2, pb->n_pt_obs);
+  d->ls_obs_lm = m.upload(pb->ls_obs_lm, pb->n_ls_obs); d->ls_obs_kf = m.upload(pb->ls_obs_kf, pb->n_ls_obs);
+  d->ls_obs_fix = m.upload(pb->ls_obs_fix, pb->n_ls_obs);
+  d->ls_obs_le = m.upload(pb->ls_obs_le, (size_t)pb->n_ls_obs * 3); d->ls_obs_s2 = m.upload(pb->ls_obs_s2, pb->n_ls_obs);
+  d->fix_Tkw = m.upload(pb->fix_Tkw, (size_t)pb->n_fix * 16);
+  const size_t N = 6 * (size_t)pb->Nkf + 3 * (size_t)pb->Npt + 6 * (size_t)pb->Nls;
+  o->Hkk = m.alloc<double>((size_t)pb->Nkf * 36); o->Hpp = m.alloc<double>((size_t)pb->Npt * 9);
+  o->Hll = m.alloc<double>((size_t)pb->Nls * 36); o->Hpk = m.alloc<double>((size_t)pb->n_pt_obs * 18);
+  o->Hlk = m.alloc<double>((size_t)pb->n_ls_obs * 36); o->g = m.alloc<double>(N); o->err = m.alloc<double>(1);
+  return d->kf_Tkw && d->X_pt && d->X_ls && d->pt_obs_lm && d->pt_obs_kf && d->pt_obs_fix && d->pt_obs_uv &&
+         d->pt_obs_s2 && d->ls_obs_lm && d->ls_obs_kf && d->ls_obs_fix && d->ls_obs_le && d->ls_obs_s2 &&
+         d->fix_Tkw && o->Hkk && o->Hpp && o->Hll && o->Hpk && o->Hlk && o->g && o->err;
+}
+
 int gfpl_lba_assemble(gfpl_ctx* ctx, const gfpl_lba_problem* pb, gfpl_lba_blocks* out) {
   if (!ctx) return GFPL_E_INVALID;
   REQUIRE(ctx, pb && out && pb->Nkf >= 0 && pb->Npt >= 0 && pb->Nls >= 0 && pb->n_pt_obs >= 0 && pb->n_ls_obs >= 0);
   REQUIRE(ctx, out->Hkk && out->Hpp && out->Hll && out->Hpk && out->Hlk && out->g && out->err);
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   DevMem m(ctx);
-  gfpl_lba_problem d = *pb;
-  d.kf_Tkw = m.upload(pb->kf_Tkw, (size_t)pb->Nkf * 16);
-  d.X_pt = m.upload(pb->X_pt, (size_t)pb->Npt * 3);
-  d.X_ls = m.upload(pb->X_ls, (size_t)pb->Nls * 6);
-  d.pt_obs_lm = m.upload(pb->pt_obs_lm, pb->n_pt_obs); d.pt_obs_kf = m.upload(pb->pt_obs_kf, pb->n_pt_obs);
-  d.pt_obs_fix = m.upload(pb->pt_obs_fix, pb->n_pt_obs);
-  d.pt_obs_uv = m.upload(pb->pt_obs_uv, (size_t)pb->n_pt_obs * 2); d.pt_obs_s2 = m.upload(pb->pt_obs_s2, pb->n_pt_obs);
-  d.ls_obs_lm = m.upload(pb->ls_obs_lm, pb->n_ls_obs); d.ls_obs_kf = m.upload(pb->ls_obs_kf, pb->n_ls_obs);
-  d.ls_obs_fix = m.upload(pb->ls_obs_fix, pb->n_ls_obs);
-  d.ls_obs_le = m.upload(pb->ls_obs_le, (size_t)pb->n_ls_obs * 3); d.ls_obs_s2 = m.upload(pb->ls_obs_s2, pb->n_ls_obs);
-  d.fix_Tkw = m.upload(pb->fix_Tkw, (size_t)pb->n_fix * 16);
-  const size_t N = 6 * (size_t)pb->Nkf + 3 * (size_t)pb->Npt + 6 * (size_t)pb->Nls;
+  gfpl_lba_problem d;
   gfpl_lba_blocks o;
-  o.Hkk = m.alloc<double>((size_t)pb->Nkf * 36); o.Hpp = m.alloc<double>((size_t)pb->Npt * 9);
-  o.Hll = m.alloc<double>((size_t)pb->Nls * 36); o.Hpk = m.alloc<double>((size_t)pb->n_pt_obs * 18);
-  o.Hlk = m.alloc<double>((size_t)pb->n_ls_obs * 36); o.g = m.alloc<double>(N); o.err = m.alloc<double>(1);
-  REQUIRE_MEM(ctx, d.kf_Tkw && d.X_pt && d.X_ls && d.pt_obs_lm && d.pt_obs_kf && d.pt_obs_fix && d.pt_obs_uv &&
-                       d.pt_obs_s2 && d.ls_obs_lm && d.ls_obs_kf && d.ls_obs_fix && d.ls_obs_le && d.ls_obs_s2 &&
-                       d.fix_Tkw && o.Hkk && o.Hpp && o.Hll && o.Hpk && o.Hlk && o.g && o.err);
+  REQUIRE_MEM(ctx, mirror_lba(m, pb, &d, &o));
+  const size_t N = 6 * (size_t)pb->Nkf + 3 * (size_t)pb->Npt + 6 * (size_t)pb->Nls;
   CHECK(launch_lba_assemble(ctx, d, o));
   download(ctx, out->Hkk, o.Hkk, (size_t)pb->Nkf * 36); download(ctx, out->Hpp, o.Hpp, (size_t)pb->Npt * 9);
   download(ctx, out->Hll, o.Hll, (size_t)pb->Nls * 36); download(ctx, out->Hpk, o.Hpk, (size_t)pb->n_pt_obs * 18);
   download(ctx, out->Hlk, o.Hlk, (size_t)pb->n_ls_obs * 36); download(ctx, out->g, o.g, N);
   download(ctx, out->err, o.err, 1);
+  return finish(ctx);
+}
+
+// CSR offsets of an observation list sorted by landmark (the order localBundleAdjustment produces, :1146-1209)
+static bool landmark_offsets(const int32_t* lm, int n_obs, int n_lm, std::vector<int32_t>* off) {
+  off->assign((size_t)n_lm + 1, 0);
+  int prev = 0;
+  for (int o = 0; o < n_obs; o++) {
+    if (lm[o] < prev || lm[o] >= n_lm) return false;
+    prev = lm[o];
+    (*off)[(size_t)lm[o] + 1]++;
+  }
+  for (int j = 0; j < n_lm; j++) (*off)[(size_t)j + 1] += (*off)[j];
+  return true;
+}
+
+int gfpl_lba_step(gfpl_ctx* ctx, const gfpl_lba_problem* pb, double lambda, int32_t scale_by_hmax, double* DX,
+                  double* err_sum, double* lambda_eff) {
+  if (!ctx) return GFPL_E_INVALID;
+  REQUIRE(ctx, pb && DX && err_sum && lambda_eff && pb->Nkf >= 0 && pb->Npt >= 0 && pb->Nls >= 0 && pb->n_pt_obs >= 0 &&
+                   pb->n_ls_obs >= 0);
+  const size_t N = 6 * (size_t)pb->Nkf + 3 * (size_t)pb->Npt + 6 * (size_t)pb->Nls;
+  if (N == 0) { *err_sum = 0.0; *lambda_eff = lambda; return GFPL_OK; }
+  std::vector<int32_t> pt_off, ls_off;
+  if (!landmark_offsets(pb->pt_obs_lm, pb->n_pt_obs, pb->Npt, &pt_off) ||
+      !landmark_offsets(pb->ls_obs_lm, pb->n_ls_obs, pb->Nls, &ls_off)) {
+    set_last_error(ctx, "gfpl_lba_step: observations must be sorted by landmark index and index existing landmarks");
+    return GFPL_E_INVALID;
+  }
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DevMem m(ctx);
+  gfpl_lba_problem d;
+  gfpl_lba_blocks o;
+  REQUIRE_MEM(ctx, mirror_lba(m, pb, &d, &o));
+  int32_t* dpo = m.upload(pt_off.data(), pt_off.size());
+  int32_t* dlo = m.upload(ls_off.data(), ls_off.size());
+  const size_t nk = 6 * (size_t)pb->Nkf;
+  LbaSolveWork w;
+  w.S = m.alloc<double>(nk * nk);
+  w.Ypt = m.alloc<double>((size_t)pb->n_pt_obs * 18); w.Zpt = m.alloc<double>((size_t)pb->Npt * 3);
+  w.Yls = m.alloc<double>((size_t)pb->n_ls_obs * 36); w.Zls = m.alloc<double>((size_t)pb->Nls * 6);
+  double* dDX = m.alloc<double>(N);
+  double* dlam = m.alloc<double>(1);
+  REQUIRE_MEM(ctx, dpo && dlo && w.S && w.Ypt && w.Zpt && w.Yls && w.Zls && dDX && dlam);
+  CHECK(launch_lba_assemble(ctx, d, o));
+  CHECK(launch_lba_solve(ctx, d, o, dpo, dlo, lambda, scale_by_hmax, w, dDX, dlam));
+  download(ctx, DX, dDX, N);
+  download(ctx, err_sum, o.err, 1);
+  download(ctx, lambda_eff, dlam, 1);
   return finish(ctx);
 }
 

@@ -121,6 +121,18 @@ int launch_pose_optimize(gfpl_ctx* ctx, DevTrackObs obs, const gfpl_frame_state*
 // K6: LBA assembly (device copies of the flat problem)
 int launch_lba_assemble(gfpl_ctx* ctx, const gfpl_lba_problem& dprob, gfpl_lba_blocks dout);
 
+// scratch of the Schur-complement solve (k_lba_solve.cu)
+struct LbaSolveWork {
+  double* S;     // [6Nkf][6Nkf]
+  double *Ypt, *Zpt;  // [n_pt_obs][18], [Npt][3]
+  double *Yls, *Zls;  // [n_ls_obs][36], [Nls][6]
+};
+// DX (device, [6Nkf + 3Npt + 6Nls]) = (H + lambda_eff diag H)^-1 g ; pt_off / ls_off: CSR offsets of the landmark-sorted
+// observation lists; lambda_eff (device scalar) = lambda * (int)max|H_ii| if scale_by_hmax else lambda
+int launch_lba_solve(gfpl_ctx* ctx, const gfpl_lba_problem& pb, const gfpl_lba_blocks& H, const int32_t* pt_off,
+                     const int32_t* ls_off, double lambda, int scale_by_hmax, LbaSolveWork w, double* DX,
+                     double* lambda_eff);
+
 int launch_measure_peaks(gfpl_ctx* ctx, double* popc_tops, double* fp64_tflops);
 int launch_measure_alu_peak(gfpl_ctx* ctx, double* lop3_tops);
 

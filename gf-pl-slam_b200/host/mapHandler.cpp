@@ -84,33 +84,6 @@ Vector6d logmap_se3(const Matrix4d& T) {
   return x;
 }
 
-// ---- small dense solver: Gaussian elimination with partial pivoting, n x n, in place ---------------------------
-static bool solve_dense(int n, vector<double>& A, vector<double>& B, int nrhs) {
-  bool ok = true;
-  for (int k = 0; k < n; k++) {
-    int p = k;
-    for (int i = k + 1; i < n; i++) if (std::fabs(A[(size_t)i * n + k]) > std::fabs(A[(size_t)p * n + k])) p = i;
-    if (A[(size_t)p * n + k] == 0.0) { ok = false; continue; }
-    if (p != k) {
-      for (int j = 0; j < n; j++) std::swap(A[(size_t)k * n + j], A[(size_t)p * n + j]);
-      for (int j = 0; j < nrhs; j++) std::swap(B[(size_t)k * nrhs + j], B[(size_t)p * nrhs + j]);
-    }
-    for (int i = k + 1; i < n; i++) {
-      const double f = A[(size_t)i * n + k] / A[(size_t)k * n + k];
-      if (f == 0.0) continue;
-      for (int j = k; j < n; j++) A[(size_t)i * n + j] -= f * A[(size_t)k * n + j];
-      for (int j = 0; j < nrhs; j++) B[(size_t)i * nrhs + j] -= f * B[(size_t)k * nrhs + j];
-    }
-  }
-  for (int i = n - 1; i >= 0; i--)
-    for (int j = 0; j < nrhs; j++) {
-      double s = B[(size_t)i * nrhs + j];
-      for (int k = i + 1; k < n; k++) s -= A[(size_t)i * n + k] * B[(size_t)k * nrhs + j];
-      B[(size_t)i * nrhs + j] = A[(size_t)i * n + i] != 0.0 ? s / A[(size_t)i * n + i] : 0.0;
-    }
-  return ok;
-}
-
 // ---- lookForCommonMatches, KF <-> KF half (mapHandler.cpp:189-490) ---------------------------------------------
 static Vector3d transform_point(const Matrix4d& T, const Vector3d& P) {
   Vector3d r;
@@ -437,11 +410,12 @@ void MapHandler::levMarquardtOptimizationLBA(vector<double> X_aux, vector<int> k
     for (int i = 0; i < 6; i++) X_ls_map[6 * j + i] = map_lines[ls_list[j]]->line3D(i);
 
   vector<double> kf_T(16 * (size_t)std::max(Nkf, 1)), X_pt(3 * (size_t)std::max(Npt, 1));
-  vector<double> Hkk(36 * (size_t)std::max(Nkf, 1)), Hpp(9 * (size_t)std::max(Npt, 1)), Hll(36 * (size_t)std::max(Nls, 1));
-  vector<double> Hpk(18 * (size_t)std::max(npo, 1)), Hlk(36 * (size_t)std::max(nlo, 1)), g(std::max(N, 1));
   double err_sum = 0.0;
 
-  auto assemble = [&](bool first_pass) {
+  // one LM pass on the device: assembly at the current state + damped solve (gfpl_lba_step).  DX is computed in every
+  // pass, also in the one where the reference leaves the loop before solving (:1652-1653) — it is simply not used then.
+  double lambda_eff = 0.0;
+  auto step = [&](bool first_pass, double lambda, int scale_by_hmax) {
     for (int k = 0; k < Nkf; k++) {
       Matrix4d T;
       if (first_pass) T = map_keyframes[kf_list[k]]->T_kf_w;   // :1255
@@ -454,77 +428,7 @@ void MapHandler::levMarquardtOptimizationLBA(vector<double> X_aux, vector<int> k
     gfpl_lba_problem pb{Nkf, Npt, Nls, npo, nlo, kf_T.data(), X_pt.data(), X_ls_map.data(), pt_lm.data(), pt_kf.data(),
                         pt_fix.data(), pt_uv.data(), pt_s2.data(), ls_lm.data(), ls_kf.data(), ls_fix.data(), ls_le.data(),
                         ls_s2.data(), fix_T.data(), (int32_t)fix_ids.size()};
-    gfpl_lba_blocks out{Hkk.data(), Hpp.data(), Hll.data(), Hpk.data(), Hlk.data(), g.data(), &err_sum};
-    gfpl->check(gfpl_lba_assemble(gfpl->get(), &pb, &out));
-  };
-
-  // damped solve: (H + lambda*diag(H)) DX = g through the Schur complement of the landmark blocks
-  auto solve = [&](double lambda) {
-    const int nk = 6 * Nkf;
-    vector<double> S((size_t)nk * nk, 0.0), rhs(std::max(nk, 1), 0.0);
-    for (int k = 0; k < Nkf; k++)
-      for (int i = 0; i < 6; i++) {
-        for (int j = 0; j < 6; j++) S[(size_t)(6 * k + i) * nk + 6 * k + j] = Hkk[36 * (size_t)k + i * 6 + j];
-        S[(size_t)(6 * k + i) * nk + 6 * k + i] += lambda * Hkk[36 * (size_t)k + i * 7];
-        rhs[6 * k + i] = g[6 * k + i];
-      }
-    // per landmark: D^-1 [B | g_j], where B = sum of that landmark's off-diagonal blocks, one per observing local KF
-    struct Lm { int dim; vector<double> Dinv_B; vector<double> Dinv_g; vector<int> kfs; vector<double> B; };
-    vector<Lm> lms(Npt + Nls);
-    auto add_obs = [&](int lm_global, int dim, int kf, const double* blk) {
-      Lm& L = lms[lm_global];
-      L.dim = dim;
-      size_t s = 0;
-      for (; s < L.kfs.size(); s++) if (L.kfs[s] == kf) break;
-      if (s == L.kfs.size()) { L.kfs.push_back(kf); L.B.resize(L.B.size() + (size_t)dim * 6, 0.0); }
-      for (int i = 0; i < dim * 6; i++) L.B[s * dim * 6 + i] += blk[i];
-    };
-    for (int o = 0; o < npo; o++) if (pt_kf[o] >= 0) add_obs(pt_lm[o], 3, pt_kf[o], &Hpk[18 * (size_t)o]);
-    for (int o = 0; o < nlo; o++) if (ls_kf[o] >= 0) add_obs(Npt + ls_lm[o], 6, ls_kf[o], &Hlk[36 * (size_t)o]);
-    for (int j = 0; j < Npt + Nls; j++) {
-      Lm& L = lms[j];
-      const bool is_pt = j < Npt;
-      const int dim = is_pt ? 3 : 6;
-      L.dim = dim;
-      const double* D = is_pt ? &Hpp[9 * (size_t)j] : &Hll[36 * (size_t)(j - Npt)];
-      const double* gj = &g[6 * Nkf + (is_pt ? 3 * j : 3 * Npt + 6 * (j - Npt))];
-      const int nrhs = 6 * (int)L.kfs.size() + 1;
-      vector<double> A((size_t)dim * dim), R((size_t)dim * nrhs);
-      for (int i = 0; i < dim; i++) {
-        for (int c = 0; c < dim; c++) A[(size_t)i * dim + c] = D[i * dim + c] + (i == c ? lambda * D[i * dim + c] : 0.0);
-        for (size_t s = 0; s < L.kfs.size(); s++)
-          for (int c = 0; c < 6; c++) R[(size_t)i * nrhs + 6 * s + c] = L.B[s * dim * 6 + i * 6 + c];
-        R[(size_t)i * nrhs + nrhs - 1] = gj[i];
-      }
-      solve_dense(dim, A, R, nrhs);
-      L.Dinv_B.assign(R.begin(), R.end());   // [dim][nrhs]: D^-1 B (per KF) | D^-1 g_j
-      // S -= B^T D^-1 B ; rhs -= B^T D^-1 g_j
-      for (size_t a = 0; a < L.kfs.size(); a++)
-        for (int r = 0; r < 6; r++) {
-          double acc = 0.0;
-          for (int i = 0; i < dim; i++) acc += L.B[a * dim * 6 + i * 6 + r] * R[(size_t)i * nrhs + nrhs - 1];
-          rhs[6 * L.kfs[a] + r] -= acc;
-          for (size_t b = 0; b < L.kfs.size(); b++)
-            for (int c = 0; c < 6; c++) {
-              double v = 0.0;
-              for (int i = 0; i < dim; i++) v += L.B[a * dim * 6 + i * 6 + r] * R[(size_t)i * nrhs + 6 * b + c];
-              S[(size_t)(6 * L.kfs[a] + r) * nk + 6 * L.kfs[b] + c] -= v;
-            }
-        }
-    }
-    if (nk > 0) solve_dense(nk, S, rhs, 1);
-    for (int i = 0; i < nk; i++) DX[i] = rhs[i];
-    for (int j = 0; j < Npt + Nls; j++) {
-      const Lm& L = lms[j];
-      const int dim = L.dim, nrhs = 6 * (int)L.kfs.size() + 1;
-      const int off = 6 * Nkf + (j < Npt ? 3 * j : 3 * Npt + 6 * (j - Npt));
-      for (int i = 0; i < dim; i++) {
-        double v = L.Dinv_B[(size_t)i * nrhs + nrhs - 1];
-        for (size_t s = 0; s < L.kfs.size(); s++)
-          for (int c = 0; c < 6; c++) v -= L.Dinv_B[(size_t)i * nrhs + 6 * s + c] * DX[6 * L.kfs[s] + c];
-        DX[off + i] = v;
-      }
-    }
+    gfpl->check(gfpl_lba_step(gfpl->get(), &pb, lambda, scale_by_hmax, DX.data(), &err_sum, &lambda_eff));
   };
 
   auto update = [&]() {  // :1443-1451
@@ -542,23 +446,16 @@ void MapHandler::levMarquardtOptimizationLBA(vector<double> X_aux, vector<int> k
   double lambda = cfg.lambda_lba_lm;
   const double lambda_k = cfg.lambda_lba_k;
   const double eps = std::numeric_limits<double>::epsilon();
-  assemble(true);
+  step(true, lambda, 1);                     // :1243-1441; lambda *= (int)Hmax (quirk iii) happens inside
   err = err_sum / 0.0;                       // quirk (ii): Npt_obs + Nls_obs are never incremented (:1427)
-  int Hmax = 0;                              // quirk (iii): int (:1429-1435)
-  auto diag_scan = [&](double h) { if (h > Hmax || h < -Hmax) Hmax = (int)std::fabs(h); };
-  for (int k = 0; k < Nkf; k++) for (int i = 0; i < 6; i++) diag_scan(Hkk[36 * (size_t)k + i * 7]);
-  for (int j = 0; j < Npt; j++) for (int i = 0; i < 3; i++) diag_scan(Hpp[9 * (size_t)j + i * 4]);
-  for (int j = 0; j < Nls; j++) for (int i = 0; i < 6; i++) diag_scan(Hll[36 * (size_t)j + i * 7]);
-  lambda *= Hmax;
-  solve(lambda);
+  lambda = lambda_eff;
   update();
   err_prev = err;
   int iters;
   for (iters = 1; iters < cfg.max_iters_lba; iters++) {
-    assemble(false);
+    step(false, lambda, 0);
     err = err_sum / (Npt + Nls);             // :1650
     if (std::fabs(err - err_prev) < eps || err < eps) break;
-    solve(lambda);
     if (err > err_prev) lambda /= lambda_k;
     else { lambda *= lambda_k; update(); }
     double n2 = 0.0;

@@ -1,9 +1,9 @@
-// mapHandler.hpp — PLSLAM::MapHandler facade for local bundle adjustment (reference include/mapHandler.h:73-157,
-// src/mapHandler.cpp:1108-1712).  The residual / Jacobian / block-H assembly of every Levenberg-Marquardt pass
-// runs on the GPU (gfpl_lba_assemble); the gather of the local map (pointer chasing), the damping, the linear
-// solve and the state update stay on the host, as in the reference.  The reference solves the damped system
-// with Eigen::SimplicialLDLT on a dense->sparse copy (:1439-1441); here the same system is solved by
-// eliminating the block-diagonal landmark part (Schur complement), which is algebraically the same solution.
+// mapHandler.hpp — PLSLAM::MapHandler facade for map matching and local bundle adjustment (reference
+// include/mapHandler.h:73-157, src/mapHandler.cpp:189-772, 1108-1712).  Every Levenberg-Marquardt pass — residuals,
+// Jacobians, block-H assembly and the damped solve — runs on the GPU (gfpl_lba_step); the gather of the local map
+// (pointer chasing), the error accounting, the accept / reject of a step and the state update stay on the host, as in
+// the reference.  The reference solves the damped system with Eigen::SimplicialLDLT on a dense->sparse copy
+// (:1439-1441); the device eliminates the block-diagonal landmark part (Schur complement): the same solution.
 #pragma once
 #include <array>
 #include <vector>

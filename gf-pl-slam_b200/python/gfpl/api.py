@@ -264,6 +264,15 @@ class Context:
         self._check(lib().gfpl_lba_assemble(self._h, C.byref(p), C.byref(blk)))
         return out
 
+    def lba_step(self, prob_arrays, lam, scale_by_hmax):
+        """assembly + damped Schur-complement solve of one LM pass: (DX, err_sum, lambda_eff)"""
+        p, keep = S.lba_problem_from_arrays(prob_arrays)
+        N = 6 * p.Nkf + 3 * p.Npt + 6 * p.Nls
+        DX = np.zeros(N); err = np.zeros(1); lam_eff = np.zeros(1)
+        self._check(lib().gfpl_lba_step(self._h, C.byref(p), C.c_double(lam), int(scale_by_hmax), _vp(DX), _vp(err),
+                                        _vp(lam_eff)))
+        return DX, float(err[0]), float(lam_eff[0])
+
 
 class Replay:
     """gfpl_replay: device-resident batch of B frame pairs (upload once / run many / download)."""

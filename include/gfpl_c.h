@@ -567,6 +567,17 @@ typedef struct gfpl_lba_blocks {
  * on the host (mapHandler.cpp:1428-1453,1652-1685). */
 int gfpl_lba_assemble(gfpl_ctx* ctx, const gfpl_lba_problem* prob, gfpl_lba_blocks* out);
 
+/* One Levenberg-Marquardt pass of levMarquardtOptimizationLBA on the device: the assembly above followed by the damped
+ * solve  DX = (H + lambda_eff diag(H))^-1 g  (mapHandler.cpp:1436-1441 first pass, :1654-1660 later passes; SURVEY.md
+ * §8f rank 3).  The reference factorises a dense->sparse copy with Eigen::SimplicialLDLT; here the block-diagonal landmark
+ * part is eliminated (Schur complement) and the 6Nkf x 6Nkf remainder is factorised densely — the same solution.
+ * scale_by_hmax != 0: lambda_eff = lambda * (int)max|H_ii| (the first pass, :1429-1437, `int Hmax`); else lambda_eff = lambda.
+ * Observation lists must be sorted by landmark index (localBundleAdjustment emits them that way, :1146-1209).
+ * DX: [6Nkf + 3Npt + 6Nls] in the reference's state order; err_sum: sum of w r^2 of the pass (not normalised).
+ * Error accounting, the accept / reject of the step and the state update (:1443-1451, :1662-1685) stay on the host. */
+int gfpl_lba_step(gfpl_ctx* ctx, const gfpl_lba_problem* prob, double lambda, int32_t scale_by_hmax, double* DX,
+                  double* err_sum, double* lambda_eff);
+
 /* ------------------------------------------------------------------------- */
 /* Device micro-benchmarks used as roofline denominators          */
 /* ------------------------------------------------------------------------- */

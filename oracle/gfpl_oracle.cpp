@@ -1541,3 +1541,75 @@ extern "C" int orc_lba_assemble(const gfpl_camera* cam, const gfpl_config* cfg, 
 extern "C" void orc_expmap_se3(const double* x6, double* T16) { expmap_se3(x6, T16); }
 extern "C" void orc_logmap_se3(const double* T16, double* x6) { logmap_se3(T16, x6); }
 extern "C" void orc_inverse_se3(const double* T16, double* Tinv16) { inverse_se3(T16, Tinv16); }
+
+// One LM pass of levMarquardtOptimizationLBA: assembly + damped solve on the reference's DENSE system
+// (mapHandler.cpp:1428-1441 / 1652-1660).  The reference factorises with Eigen::SimplicialLDLT; this restatement solves the
+// same dense system by Gaussian elimination with partial pivoting (a different, independent route to the same DX).
+extern "C" int orc_lba_step(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_lba_problem* pb, double lambda,
+                            int32_t scale_by_hmax, double* DX, double* err_sum, double* lambda_eff) {
+  if (!cam || !cfg || !pb || !DX || !err_sum || !lambda_eff) return GFPL_E_INVALID;
+  const int Nkf = pb->Nkf, Npt = pb->Npt, Nls = pb->Nls;
+  const int N = 6 * Nkf + 3 * Npt + 6 * Nls;
+  std::vector<double> Hkk((size_t)Nkf * 36 + 1), Hpp((size_t)Npt * 9 + 1), Hll((size_t)Nls * 36 + 1),
+      Hpk((size_t)pb->n_pt_obs * 18 + 1), Hlk((size_t)pb->n_ls_obs * 36 + 1), g((size_t)N + 1);
+  gfpl_lba_blocks b{Hkk.data(), Hpp.data(), Hll.data(), Hpk.data(), Hlk.data(), g.data(), err_sum};
+  int rc = orc_lba_assemble(cam, cfg, pb, &b);
+  if (rc != GFPL_OK) return rc;
+  std::vector<double> H((size_t)N * N, 0.0);
+  auto at = [&](int r, int c) -> double& { return H[(size_t)r * N + c]; };
+  for (int k = 0; k < Nkf; k++)
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) at(6 * k + i, 6 * k + j) = Hkk[(size_t)k * 36 + i * 6 + j];
+  for (int p = 0; p < Npt; p++)
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) at(6 * Nkf + 3 * p + i, 6 * Nkf + 3 * p + j) = Hpp[(size_t)p * 9 + i * 3 + j];
+  for (int l = 0; l < Nls; l++)
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++)
+      at(6 * Nkf + 3 * Npt + 6 * l + i, 6 * Nkf + 3 * Npt + 6 * l + j) = Hll[(size_t)l * 36 + i * 6 + j];
+  for (int o = 0; o < pb->n_pt_obs; o++) {
+    const int kf = pb->pt_obs_kf[o], jdx = 6 * Nkf + 3 * pb->pt_obs_lm[o];
+    if (kf < 0) continue;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 6; j++) {
+      at(jdx + i, 6 * kf + j) += Hpk[(size_t)o * 18 + i * 6 + j];   // H.block(jdx,idx,3,6) += ... (:1308)
+      at(6 * kf + j, jdx + i) += Hpk[(size_t)o * 18 + i * 6 + j];   // and its transpose (:1309)
+    }
+  }
+  for (int o = 0; o < pb->n_ls_obs; o++) {
+    const int kf = pb->ls_obs_kf[o], jdx = 6 * Nkf + 3 * Npt + 6 * pb->ls_obs_lm[o];
+    if (kf < 0) continue;
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) {
+      at(jdx + i, 6 * kf + j) += Hlk[(size_t)o * 36 + i * 6 + j];
+      at(6 * kf + j, jdx + i) += Hlk[(size_t)o * 36 + i * 6 + j];
+    }
+  }
+  double lam = lambda;
+  if (scale_by_hmax) {
+    int Hmax = 0;  // `int Hmax` (:1429-1435)
+    for (int i = 0; i < N; i++)
+      if (at(i, i) > Hmax || at(i, i) < -Hmax) Hmax = (int)std::fabs(at(i, i));
+    lam = lam * Hmax;
+  }
+  *lambda_eff = lam;
+  for (int i = 0; i < N; i++) at(i, i) += lam * at(i, i);   // :1436-1437
+  std::vector<double> x(g.begin(), g.begin() + N);
+  for (int k = 0; k < N; k++) {
+    int piv = k;
+    for (int i = k + 1; i < N; i++) if (std::fabs(at(i, k)) > std::fabs(at(piv, k))) piv = i;
+    if (piv != k) {
+      for (int c = k; c < N; c++) std::swap(at(k, c), at(piv, c));
+      std::swap(x[k], x[piv]);
+    }
+    const double d = at(k, k);
+    for (int i = k + 1; i < N; i++) {
+      const double f = at(i, k) / d;
+      if (f == 0.0) continue;
+      for (int c = k; c < N; c++) at(i, c) -= f * at(k, c);
+      x[i] -= f * x[k];
+    }
+  }
+  for (int k = N - 1; k >= 0; k--) {
+    double s = x[k];
+    for (int c = k + 1; c < N; c++) s -= at(k, c) * x[c];
+    x[k] = s / at(k, k);
+  }
+  for (int i = 0; i < N; i++) DX[i] = x[i];
+  return GFPL_OK;
+}

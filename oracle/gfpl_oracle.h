@@ -65,6 +65,9 @@ int orc_track(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_stereo_
 int orc_lba_assemble(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_lba_problem* prob,
                      gfpl_lba_blocks* out);
 
+int orc_lba_step(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_lba_problem* prob, double lambda,
+                 int32_t scale_by_hmax, double* DX, double* err_sum, double* lambda_eff);
+
 /* SE(3) helpers exposed for unit tests (auxiliar.cpp:154-238) */
 void orc_expmap_se3(const double* x6, double* T16);
 void orc_logmap_se3(const double* T16, double* x6);

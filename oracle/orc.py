@@ -211,6 +211,16 @@ def lba_assemble(cam, cfg, prob_arrays):
     return out
 
 
+def lba_step(cam, cfg, prob_arrays, lam, scale_by_hmax):
+    p, keep = S.lba_problem_from_arrays(prob_arrays)
+    N = 6 * p.Nkf + 3 * p.Npt + 6 * p.Nls
+    DX = np.zeros(N); err = np.zeros(1); lam_eff = np.zeros(1)
+    rc = lib().orc_lba_step(C.byref(cam), C.byref(cfg), C.byref(p), C.c_double(lam), int(scale_by_hmax),
+                            C.c_void_p(S.ptr(DX)), C.c_void_p(S.ptr(err)), C.c_void_p(S.ptr(lam_eff)))
+    assert rc == 0, rc
+    return DX, float(err[0]), float(lam_eff[0])
+
+
 def expmap_se3(x):
     x = np.ascontiguousarray(x, np.float64); T = np.zeros(16)
     lib().orc_expmap_se3(C.c_void_p(S.ptr(x)), C.c_void_p(S.ptr(T)))

@@ -612,3 +612,50 @@ def test_stereo_match_orbslam_dense_and_degenerate(ctx, orc):
     with pytest.raises(Exception):
         bad = synth.make_right_pyramids(4, d["cam"], n_levels=3, seed=5)   # n_levels != cfg.orb_nlevels
         ctx.stereo_match_orbslam(raw, bad)
+
+
+def _lba_residual(w, blk, DX, lam):
+    """|| (H + lam diag H) DX - g || / || g ||  from the block-sparse assembly (numpy, no dense matrix)"""
+    Nkf, Npt, Nls = len(w["kf_Tkw"]), len(w["X_pt"]), len(w["X_ls"])
+    xk = DX[:6 * Nkf].reshape(Nkf, 6); xp = DX[6 * Nkf:6 * Nkf + 3 * Npt].reshape(Npt, 3); xl = DX[6 * Nkf + 3 * Npt:].reshape(Nls, 6)
+    damp = lambda Hb, n: Hb.reshape(-1, n, n) + lam * np.einsum("bii->bi", Hb.reshape(-1, n, n))[:, :, None] * np.eye(n)
+    rk = np.einsum("bij,bj->bi", damp(blk["Hkk"], 6), xk)
+    rp = np.einsum("bij,bj->bi", damp(blk["Hpp"], 3), xp)
+    rl = np.einsum("bij,bj->bi", damp(blk["Hll"], 6), xl)
+    for W, lm, kf, r_lm, x_lm, dim in ((blk["Hpk"].reshape(-1, 3, 6), w["pt_obs_lm"], w["pt_obs_kf"], rp, xp, 3),
+                                       (blk["Hlk"].reshape(-1, 6, 6), w["ls_obs_lm"], w["ls_obs_kf"], rl, xl, 6)):
+        ok = kf >= 0
+        np.add.at(r_lm, lm[ok], np.einsum("oij,oj->oi", W[ok], xk[kf[ok]]))
+        np.add.at(rk, kf[ok], np.einsum("oij,oi->oj", W[ok], x_lm[lm[ok]]))
+    r = np.concatenate([rk.ravel(), rp.ravel(), rl.ravel()]) - blk["g"]
+    return np.linalg.norm(r) / np.linalg.norm(blk["g"])
+
+
+def test_lba_step_schur_solve(ctx, orc):
+    """assembly + damped solve of one LM pass (mapHandler.cpp:1428-1441): DX vs the dense CPU solve, 1e-9 relative"""
+    from gfpl import api
+    try:
+        for seed, kw, lam, scale in ((3, dict(n_kf=6, n_pt=120, n_ls=30), 0.001, 1),
+                                     (4, dict(n_kf=3, n_pt=20, n_ls=5, n_fix=1), 0.001, 1),
+                                     (5, dict(n_kf=8, n_pt=150, n_ls=40), 37.5, 0),
+                                     (6, dict(n_kf=4, n_pt=60, n_ls=0), 0.5, 0),
+                                     (7, dict(n_kf=4, n_pt=0, n_ls=25), 0.5, 0)):
+            w = synth.make_lba_window(seed=seed, **kw)
+            ctx.set_camera(w["cam"])
+            DXg, eg, lg = ctx.lba_step(w, lam, scale)
+            DXo, eo, lo = orc.lba_step(w["cam"], ctx.cfg, w, lam, scale)
+            assert lg == lo and abs(eg - eo) <= 1e-9 * abs(eo)
+            assert np.isfinite(DXo).all() and np.abs(DXo).max() > 0
+            assert np.linalg.norm(DXg - DXo) <= 1e-9 * np.linalg.norm(DXo), (seed, np.linalg.norm(DXg - DXo) / np.linalg.norm(DXo))
+        # full C3 window: too large for the dense CPU solve -> residual of the damped system instead
+        w = synth.make_lba_window(seed=8, n_kf=10, n_pt=1000, n_ls=300)
+        ctx.set_camera(w["cam"])
+        DX, err, lam_eff = ctx.lba_step(w, 0.001, 1)
+        blk = ctx.lba_assemble(w)
+        assert lam_eff > 0 and _lba_residual(w, blk, DX, lam_eff) < 1e-9
+        # unsorted observation list is rejected, not mis-solved
+        w2 = dict(w); w2["pt_obs_lm"] = w["pt_obs_lm"][::-1].copy()
+        with pytest.raises(api.GfplError):
+            ctx.lba_step(w2, 0.001, 1)
+    finally:
+        ctx.set_camera(api.euroc_camera())
