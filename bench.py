@@ -330,11 +330,14 @@ def main():
         # issues POPC_PER_PAIR popc.b32 on the 16-lane POPC pipe (8 naive, 5 after the carry-save compression) and
         # ALU_PER_PAIR ops on the ALU pipe (SASS mix: profiles/r1_sass_mix.md).  Roofline = the slower pipe at the
         # MEASURED pipe rates (gfpl_measure_peaks / gfpl_measure_alu_peak, run live above).
-        POPC_PER_PAIR, ALU_PER_PAIR = 5.0, 20.0
+        # `pairs` counts DISTINCT distances (nq*nt per problem): both match directions come from one pass over the
+        # distance matrix (knn2_sym_kernel), where the reference's two knnMatch calls evaluate each distance twice.
+        # ALU ops per pair of the symmetric kernel: 15.6 LOP3 + 3 VIMNMX + 2.8 IADD3 + 1.8 ISETP + 0.7 SHF + 0.7 LEA.
+        POPC_PER_PAIR, ALU_PER_PAIR = 5.0, 24.6
         k_ms = [stage[0], stage[1], stage[3], stage[4]]
         dom = int(np.argmax(k_ms))
-        names = ["knn2 stereo points (2 directions)", "knn2 stereo lines NORM_HAMMING2 (2 directions)",
-                 "f2f hybrid fused radius+projection search", "knn2 f2f lines (2 directions)"]
+        names = ["knn2 stereo points (both directions from one pass)", "knn2 stereo lines NORM_HAMMING2 (both directions from one pass)",
+                 "f2f hybrid fused radius+projection search", "knn2 f2f lines (both directions from one pass)"]
         achieved = pairs[dom] / (k_ms[dom] * 1e-3) / 1e12                      # T pairs/s
         peak = min(popc_peak / POPC_PER_PAIR, alu_peak / ALU_PER_PAIR)         # T pairs/s
         alg_bytes = B * (2 * a.n_pt * 32 + 2 * a.n_pt * 16) if dom == 0 else None

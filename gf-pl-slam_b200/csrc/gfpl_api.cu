@@ -360,6 +360,7 @@ struct StepWork {
   Knn2Out pt_lr{}, pt_rl{}, ln_lr{}, ln_rl{};   // stereo knn (current frame)
   Knn2Out pt_12{}, pt_21{}, ln_12{}, ln_21{};   // f2f knn
   uint32_t* best_key = nullptr;                 // [B][cap_pt] hybrid point resolver
+  double* f2f_T = nullptr;                      // [B][32] prev Tfw | (predicted curr Tfw)^-1
   gfpl_line_cov* prev_cov = nullptr;            // [B][cap_ln]
 };
 
@@ -370,7 +371,8 @@ static bool alloc_work(DevMem& m, int B, int cap_pt, int cap_ln, StepWork* w) {
             alloc_knn(m, nl, &w->ln_12) && alloc_knn(m, nl, &w->ln_21);
   w->best_key = m.alloc<uint32_t>(np);
   w->prev_cov = m.alloc<gfpl_line_cov>(nl);
-  return ok && w->best_key && w->prev_cov;
+  w->f2f_T = m.alloc<double>((size_t)B * 32);
+  return ok && w->best_key && w->prev_cov && w->f2f_T;
 }
 
 static int run_stereo(gfpl_ctx* ctx, const DevRawFrames& raw, int variant, StepWork& w, DevStereoFrames curr,
@@ -378,12 +380,12 @@ static int run_stereo(gfpl_ctx* ctx, const DevRawFrames& raw, int variant, StepW
   const int B = raw.B;
   if (ctx->cfg.has_points)
     CHECK(launch_knn2(ctx, B, raw.pdesc_l, raw.n_pt_l, raw.cap_pt, raw.pdesc_r, raw.n_pt_r, raw.cap_pt,
-                      GFPL_NORM_HAMMING, w.pt_lr, ctx->cfg.best_lr_matches ? w.pt_rl : Knn2Out{}));
+                      GFPL_NORM_HAMMING, w.pt_lr, ctx->cfg.best_lr_matches ? w.pt_rl : Knn2Out{}, true));
   if (mid) cudaEventRecord(mid, ctx->stream);
   if (ctx->cfg.has_lines)
     CHECK(launch_knn2(ctx, B, raw.ldesc_l, raw.n_ln_l, raw.cap_ln, raw.ldesc_r, raw.n_ln_r, raw.cap_ln,
                       variant == GFPL_STEREO_INITIAL ? GFPL_NORM_HAMMING : GFPL_NORM_HAMMING2, w.ln_lr,
-                      ctx->cfg.best_lr_matches ? w.ln_rl : Knn2Out{}));
+                      ctx->cfg.best_lr_matches ? w.ln_rl : Knn2Out{}, true));
   return GFPL_OK;
 }
 
@@ -394,9 +396,9 @@ static int run_f2f_knn(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevSter
   if (ctx->cfg.has_points) {
     if (mode == GFPL_F2F_BRUTE)
       CHECK(launch_knn2(ctx, B, prev.pdesc, prev.n_pt, prev.cap_pt, curr.pdesc, curr.n_pt, curr.cap_pt,
-                        GFPL_NORM_HAMMING, w.pt_12, ctx->cfg.best_lr_matches ? w.pt_21 : Knn2Out{}));
+                        GFPL_NORM_HAMMING, w.pt_12, ctx->cfg.best_lr_matches ? w.pt_21 : Knn2Out{}, true));
     else if (use_radius)
-      CHECK(launch_f2f_hybrid_points(ctx, prev, curr, state, w.best_key));
+      CHECK(launch_f2f_hybrid_points(ctx, prev, curr, state, w.f2f_T, w.best_key));
     else {
       CHECK(launch_knn2(ctx, B, prev.pdesc, prev.n_pt, prev.cap_pt, curr.pdesc, curr.n_pt, curr.cap_pt,
                         GFPL_NORM_HAMMING, w.pt_12, Knn2Out{}));
@@ -406,7 +408,7 @@ static int run_f2f_knn(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevSter
   if (mid) cudaEventRecord(mid, ctx->stream);
   if (ctx->cfg.has_lines)
     CHECK(launch_knn2(ctx, B, prev.ldesc, prev.n_ln, prev.cap_ln, curr.ldesc, curr.n_ln, curr.cap_ln,
-                      GFPL_NORM_HAMMING, w.ln_12, ctx->cfg.best_lr_matches ? w.ln_21 : Knn2Out{}));
+                      GFPL_NORM_HAMMING, w.ln_12, ctx->cfg.best_lr_matches ? w.ln_21 : Knn2Out{}, true));
   return GFPL_OK;
 }
 
@@ -479,7 +481,7 @@ int gfpl_stereo_match_orbslam(gfpl_ctx* ctx, const gfpl_raw_frames* raw, const g
   REQUIRE_MEM(ctx, dpyr.data);
   if (ctx->cfg.has_lines)   // :633-767 == the line part of _Brute
     CHECK(launch_knn2(ctx, raw->B, draw.ldesc_l, draw.n_ln_l, draw.cap_ln, draw.ldesc_r, draw.n_ln_r, draw.cap_ln,
-                      GFPL_NORM_HAMMING2, w.ln_lr, ctx->cfg.best_lr_matches ? w.ln_rl : Knn2Out{}));
+                      GFPL_NORM_HAMMING2, w.ln_lr, ctx->cfg.best_lr_matches ? w.ln_rl : Knn2Out{}, true));
   CHECK(launch_stereo_accept(ctx, draw, GFPL_STEREO_BRUTE, w.pt_lr, w.pt_rl, w.ln_lr, w.ln_rl, dcur, /*lines_only=*/true));
   CHECK(launch_stereo_orbslam_points(ctx, draw, dpyr, dcur));
   download_stereo(ctx, out, dcur);
@@ -547,10 +549,10 @@ int gfpl_kf_match(gfpl_ctx* ctx, const gfpl_stereo_frames* kf0, const gfpl_stere
   REQUIRE_MEM(ctx, dDT);
   if (ctx->cfg.has_points)
     CHECK(launch_knn2(ctx, B, d0.pdesc, d0.n_pt, d0.cap_pt, d1.pdesc, d1.n_pt, d1.cap_pt, GFPL_NORM_HAMMING, w.pt_12,
-                      ctx->cfg.best_lr_matches ? w.pt_21 : Knn2Out{}));
+                      ctx->cfg.best_lr_matches ? w.pt_21 : Knn2Out{}, true));
   if (ctx->cfg.has_lines)
     CHECK(launch_knn2(ctx, B, d0.ldesc, d0.n_ln, d0.cap_ln, d1.ldesc, d1.n_ln, d1.cap_ln, GFPL_NORM_HAMMING, w.ln_12,
-                      ctx->cfg.best_lr_matches ? w.ln_21 : Knn2Out{}));
+                      ctx->cfg.best_lr_matches ? w.ln_21 : Knn2Out{}, true));
   CHECK(launch_kf_accept(ctx, d0, d1, dDT, w.pt_12, w.pt_21, w.ln_12, w.ln_21, dobs));
   download_obs(ctx, out, dobs);
   return finish(ctx);
@@ -589,10 +591,10 @@ int gfpl_map_match(gfpl_ctx* ctx, const gfpl_local_map* map, const gfpl_stereo_f
   CHECK(launch_map_select(ctx, dm, d1, dT, w));
   if (ctx->cfg.has_points)
     CHECK(launch_knn2(ctx, map->B, w.dsel_pt, w.n_sel_pt, map->cap_pt, w.dun_pt, w.n_un_pt, kf1->cap_pt, GFPL_NORM_HAMMING,
-                      pt_12, ctx->cfg.best_lr_matches ? pt_21 : Knn2Out{}));
+                      pt_12, ctx->cfg.best_lr_matches ? pt_21 : Knn2Out{}, true));
   if (ctx->cfg.has_lines)
     CHECK(launch_knn2(ctx, map->B, w.dsel_ln, w.n_sel_ln, map->cap_ln, w.dun_ln, w.n_un_ln, kf1->cap_ln, GFPL_NORM_HAMMING,
-                      ln_12, ctx->cfg.best_lr_matches ? ln_21 : Knn2Out{}));
+                      ln_12, ctx->cfg.best_lr_matches ? ln_21 : Knn2Out{}, true));
   CHECK(launch_map_accept(ctx, dm, d1, dT, w, pt_12, pt_21, ln_12, ln_21, dout));
   download(ctx, out->n_pt, dout.n_pt, B);
   download(ctx, out->n_ln, dout.n_ln, B);
@@ -787,9 +789,10 @@ int gfpl_replay_create_ex(gfpl_ctx* ctx, int32_t B, int32_t cap_pt, int32_t cap_
   for (Knn2Out* k : {&w.ln_lr, &w.ln_rl, &w.ln_12, &w.ln_21}) { k->idx = rp->alloc<int2>(nl); k->dist = rp->alloc<float2>(nl); }
   w.best_key = rp->alloc<uint32_t>(np);
   w.prev_cov = rp->alloc<gfpl_line_cov>(nl);
+  w.f2f_T = rp->alloc<double>((size_t)B * 32);
   bool ok = true;
   for (void* p : rp->owned) ok = ok && p;
-  ok = ok && rp->owned.size() == 12 + 12 + 6 + 3 + 16 + 2;
+  ok = ok && rp->owned.size() == 12 + 12 + 6 + 3 + 16 + 3;
   if (!ok || !w.prev_cov) {
     gfpl_replay_destroy(rp);
     set_last_error(ctx, "device allocation failed for a replay of %d pairs", B);
@@ -944,13 +947,14 @@ int gfpl_replay_pair_counts(gfpl_replay* rp, int64_t* pairs) {
   for (int k = 0; k < 8; k++)
     GFPL_CUDA_OK(ctx, cudaMemcpyAsync(n.data() + (size_t)k * B, src[k], (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CHECK(finish(ctx));
-  const bool both = ctx->cfg.best_lr_matches;
+  // distinct 256-bit distances: with best_lr_matches both directions are served by ONE pass over the nq x nt matrix
+  // (knn2_sym_kernel), so a distance is evaluated once (the reference evaluates it twice, once per knnMatch call)
   pairs[0] = pairs[1] = pairs[2] = pairs[3] = 0;
   for (int p = 0; p < B; p++) {
-    pairs[0] += (int64_t)n[p] * n[B + p] * (both ? 2 : 1);
-    pairs[1] += (int64_t)n[2 * B + p] * n[3 * B + p] * (both ? 2 : 1);
+    pairs[0] += (int64_t)n[p] * n[B + p];
+    pairs[1] += (int64_t)n[2 * B + p] * n[3 * B + p];
     pairs[2] += (int64_t)n[4 * B + p] * n[5 * B + p];  // hybrid fused search: one direction
-    pairs[3] += (int64_t)n[6 * B + p] * n[7 * B + p] * (both ? 2 : 1);
+    pairs[3] += (int64_t)n[6 * B + p] * n[7 * B + p];
   }
   return GFPL_OK;
 }

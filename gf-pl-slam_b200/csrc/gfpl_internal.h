@@ -73,8 +73,10 @@ namespace gfpl {
 
 // K1: knn k=2 for B problems, optionally both directions in one launch.
 // dir 0: queries = a (na rows), train = b (nb rows) -> out_ab ; dir 1 (if out_ba.idx): queries = b, train = a.
+// reverse_best_only: the caller reads only out_ba.idx[].x (mutual checks) — both directions then come from one pass over
+// the distance matrix (out_ba rows: idx = (best, -1), dist = (d0, +inf)).
 int launch_knn2(gfpl_ctx* ctx, int B, const uint8_t* a, const int32_t* na, int cap_a, const uint8_t* b,
-                const int32_t* nb, int cap_b, int norm, Knn2Out out_ab, Knn2Out out_ba);
+                const int32_t* nb, int cap_b, int norm, Knn2Out out_ab, Knn2Out out_ba, bool reverse_best_only = false);
 
 // K2: radius match for one problem (CSR), two passes
 int launch_radius_count(gfpl_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int norm, float radius,
@@ -92,7 +94,8 @@ int launch_expand_prev(gfpl_ctx* ctx, const gfpl_prev_frames& slim_dev, DevStere
 
 // f2f: fused radius + projection-gate search (hybrid points), knn-candidate variant, and accept loops
 int launch_f2f_hybrid_points(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr,
-                             const gfpl_frame_state* state, uint32_t* best_key /*[B][curr.cap_pt]*/);
+                             const gfpl_frame_state* state, double* T32 /*[B][32] scratch*/,
+                             uint32_t* best_key /*[B][curr.cap_pt]*/);
 int launch_f2f_hybrid_points_knn(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr,
                                  const gfpl_frame_state* state, Knn2Out pt_12, uint32_t* best_key);
 int launch_f2f_accept(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr, int mode,

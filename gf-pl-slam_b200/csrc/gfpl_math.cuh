@@ -211,6 +211,50 @@ __device__ __noinline__ void sym_eigenvalues(const double* Ain, double* ev) {
   }
 }
 
+// same arithmetic, p/q/k loops unrolled so that A stays in registers (3x3 endpoint covariances in the accept loop)
+template <int N>
+__device__ __forceinline__ void sym_eigenvalues_unrolled(const double* Ain, double* ev) {
+  double A[N * N];
+#pragma unroll
+  for (int i = 0; i < N * N; i++) A[i] = Ain[i];
+  for (int sweep = 0; sweep < 16; sweep++) {
+    double off = 0.0;
+#pragma unroll
+    for (int p = 0; p < N; p++)
+#pragma unroll
+      for (int q = p + 1; q < N; q++) off = off + A[p * N + q] * A[p * N + q];
+    if (off == 0.0) break;
+#pragma unroll
+    for (int p = 0; p < N; p++)
+#pragma unroll
+      for (int q = p + 1; q < N; q++) {
+        const double apq = A[p * N + q];
+        if (apq != 0.0) {
+          const double app = A[p * N + p], aqq = A[q * N + q];
+          const double tau = (aqq - app) / (2.0 * apq);
+          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
+#pragma unroll
+          for (int k = 0; k < N; k++) {
+            const double akp = A[k * N + p], akq = A[k * N + q];
+            A[k * N + p] = c * akp - s * akq;
+            A[k * N + q] = s * akp + c * akq;
+          }
+#pragma unroll
+          for (int k = 0; k < N; k++) {
+            const double apk = A[p * N + k], aqk = A[q * N + k];
+            A[p * N + k] = c * apk - s * aqk;
+            A[q * N + k] = s * apk + c * aqk;
+          }
+          A[p * N + q] = 0.0;
+          A[q * N + p] = 0.0;
+        }
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) ev[i] = A[i * N + i];
+}
+
 // ---- 6x6 pivoted LDLT solve (LDLT<Matrix6d>::solve, stereoFrameHandler.cpp:2045-2046) --------------
 static __device__ __noinline__ void ldlt6_solve(const double* Hin, const double* g, double* x) {
   const int n = 6;

@@ -16,7 +16,7 @@
 namespace gfpl {
 
 constexpr int F2F_TILE_ROWS = 256;
-constexpr int F2F_THREADS = 160;  // 300 current points -> 2 CTAs x 160 (94 % lane use)
+constexpr int F2F_THREADS = 160;  // 300 current points -> 2 CTAs x 160 (94 % lane use); 128 and 256 measured slower
 
 __device__ __forceinline__ void project_prev_point(const gfpl_camera& cam, const double* prev_Tfw,
                                                    const double* curr_Tfw_inv, const double* P, double* uv) {
@@ -27,16 +27,19 @@ __device__ __forceinline__ void project_prev_point(const gfpl_camera& cam, const
   projection(cam, c, uv);
 }
 
+// out of line: its ~50 live doubles must not set the register budget of the POPC loops that share the kernel
+__device__ __noinline__ void predicted_pose(const gfpl_frame_state* st, double* s_T /*[32]: prev Tfw | inverse of curr Tfw*/) {
+  double Tc[16], Tci[16];
+  matmul<4, 4, 4>(st->Tfw, st->DT, Tc);  // predictFramePose (stereoFrameHandler.cpp:157)
+  inverse4(Tc, Tci);
+  for (int i = 0; i < 16; i++) { s_T[i] = st->Tfw[i]; s_T[16 + i] = Tci[i]; }
+}
+
 // shared prologue: predicted pose, its inverse, and the projections of all previous points into smem
 __device__ __forceinline__ void stage_projections(const DevStereoFrames& prev, const gfpl_frame_state* state, int p,
                                                   int n_prev, const gfpl_camera& cam, double* s_T /*[32]*/,
                                                   double2* s_proj) {
-  if (threadIdx.x == 0) {
-    double Tc[16], Tci[16];
-    matmul<4, 4, 4>(state[p].Tfw, state[p].DT, Tc);  // predictFramePose (stereoFrameHandler.cpp:157)
-    inverse4(Tc, Tci);
-    for (int i = 0; i < 16; i++) { s_T[i] = state[p].Tfw[i]; s_T[16 + i] = Tci[i]; }
-  }
+  if (threadIdx.x == 0) predicted_pose(state + p, s_T);
   __syncthreads();
   for (int q = threadIdx.x; q < n_prev; q += blockDim.x) {
     double uv[2];
@@ -46,23 +49,35 @@ __device__ __forceinline__ void stage_projections(const DevStereoFrames& prev, c
   __syncthreads();
 }
 
-// rare path of the hybrid search (a previous descriptor within the radius): the 10 px projection gate of
-// stereoFrameHandler.cpp:534-538.  Out of line so that its fp64 registers are not live in the POPC loop.
-__device__ __noinline__ uint32_t f2f_gate(uint32_t best, uint32_t key, double2 pr, double plx, double ply, double window) {
-  const double dx = pr.x - plx, dy = pr.y - ply;
+// Per-problem pose pair of the projection gate, computed once by its own small kernel instead of serially by thread 0 of
+// every search CTA: T32[p] = { prev Tfw (16) | inverse of the predicted curr Tfw = (Tfw * DT)^-1 (16) }.
+__global__ void f2f_predict_kernel(const gfpl_frame_state* __restrict__ state, int B, double* __restrict__ T32) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < B) predicted_pose(state + p, T32 + (size_t)p * 32);
+}
+
+// path of the hybrid search for a previous descriptor within the radius: the 10 px projection gate of
+// stereoFrameHandler.cpp:534-538 with projectPrev3DPoint (stereoFrame.cpp:1550-1570) evaluated for this one candidate.
+// Out of line so that its fp64 registers are not live in the POPC loop.
+__device__ __noinline__ uint32_t f2f_gate(uint32_t best, uint32_t key, const gfpl_camera& cam, const double* __restrict__ T32,
+                                          const double* __restrict__ P, double plx, double ply, double window) {
+  double uv[2];
+  project_prev_point(cam, T32, T32 + 16, P, uv);
+  const double dx = uv[0] - plx, dy = uv[1] - ply;
   return (!(sqrt(dx * dx + dy * dy) > window)) ? min(best, key) : best;
 }
 
+#ifndef F2F_MIN_BLOCKS
+#define F2F_MIN_BLOCKS 6
+#endif
 constexpr int F2F_QPT = 2;  // current points per thread: halves the LDS traffic and the per-CTA projection prologue
+                            // (measured: 1 per thread with 256-thread CTAs is 20 % slower)
 
-__global__ void __launch_bounds__(F2F_THREADS, 6)
-f2f_hybrid_points_kernel(DevStereoFrames prev, DevStereoFrames curr, const gfpl_frame_state* __restrict__ state,
+__global__ void __launch_bounds__(F2F_THREADS, F2F_MIN_BLOCKS)
+f2f_hybrid_points_kernel(DevStereoFrames prev, DevStereoFrames curr, const double* __restrict__ T32_all,
                          uint32_t* __restrict__ best_key, gfpl_camera cam, gfpl_config cfg) {
-  extern __shared__ __align__(128) uint8_t s_dyn[];
-  uint8_t* s_train = s_dyn;                                                  // [2][TILE*32]
-  double2* s_proj = reinterpret_cast<double2*>(s_dyn + 2 * F2F_TILE_ROWS * 32);  // [prev.cap_pt]
+  __shared__ __align__(128) uint8_t s_train[2 * F2F_TILE_ROWS * 32];
   __shared__ __align__(8) uint64_t s_bar[2];
-  __shared__ double s_T[32];
 
   const int p = blockIdx.y;
   const int n_prev = prev.n_pt[p], n_curr = curr.n_pt[p];
@@ -75,7 +90,8 @@ f2f_hybrid_points_kernel(DevStereoFrames prev, DevStereoFrames curr, const gfpl_
 #pragma unroll
   for (int k = 0; k < F2F_QPT; k++) { best[k] = KEY_NONE; tq[k] = t0 + k * blockDim.x + threadIdx.x; }
   if (active) {
-    stage_projections(prev, state, p, n_prev, cam, s_T, s_proj);
+    const double* T32 = T32_all + (size_t)p * 32;
+    const gfpl_point_feature* prev_pt = prev.pt + (size_t)p * prev.cap_pt;
     Desc256 qd[F2F_QPT];
     double plx[F2F_QPT], ply[F2F_QPT];
 #pragma unroll
@@ -95,21 +111,35 @@ f2f_hybrid_points_kernel(DevStereoFrames prev, DevStereoFrames curr, const gfpl_
     uint32_t cnt[F2F_QPT];
 #pragma unroll
     for (int k = 0; k < F2F_QPT; k++) cnt[k] = 0;
+    const int warp_first = t0 + (threadIdx.x & ~31);   // first query of this warp's slot 0; slot 1 = + blockDim.x
+    const int warp_slots = (F2F_QPT == 2 && warp_first + (int)blockDim.x < n_curr) ? 2 : (warp_first < n_curr ? 1 : 0);
     TrainPipe<F2F_TILE_ROWS> pipe;
     pipe.init(s_train, s_bar, prev.pdesc + (size_t)p * prev.cap_pt * 32, n_prev);
     for (int tile = 0; tile < pipe.ntiles; tile++) {
       const uint4* rows = reinterpret_cast<const uint4*>(pipe.acquire(tile));
       const int n = pipe.rows_in(tile);
       const int q0 = tile * F2F_TILE_ROWS;
+      // the stereo survivors rarely fill the CTA's 2 x 160 slots: a warp whose second (or only) query slot lies past
+      // n_curr skips that slot's arithmetic (warp-uniform), it only keeps pace at the tile barriers
+      if (F2F_QPT == 2 && warp_slots == 2) {
 #pragma unroll 4
-      for (int r = 0; r < n; r++) {
-        const uint4 ra = rows[2 * r], rb = rows[2 * r + 1];
+        for (int r = 0; r < n; r++) {
+          const uint4 ra = rows[2 * r], rb = rows[2 * r + 1];
 #pragma unroll
-        for (int k = 0; k < F2F_QPT; k++) {
-          const uint32_t d = hamming256<GFPL_NORM_HAMMING>(qd[k], ra, rb);
+          for (int k = 0; k < F2F_QPT; k++) {
+            const uint32_t d = hamming256<GFPL_NORM_HAMMING>(qd[k], ra, rb);
+            const bool hit = (int)d <= rint;
+            cnt[k] += hit ? 1u : 0u;
+            best[k] = min(best[k], hit ? make_key(d, q0 + r) : KEY_NONE);
+          }
+        }
+      } else if (warp_slots == 1) {
+#pragma unroll 4
+        for (int r = 0; r < n; r++) {
+          const uint32_t d = hamming256<GFPL_NORM_HAMMING>(qd[0], rows[2 * r], rows[2 * r + 1]);
           const bool hit = (int)d <= rint;
-          cnt[k] += hit ? 1u : 0u;
-          best[k] = min(best[k], hit ? make_key(d, q0 + r) : KEY_NONE);
+          cnt[0] += hit ? 1u : 0u;
+          best[0] = min(best[0], hit ? make_key(d, q0 + r) : KEY_NONE);
         }
       }
       pipe.release(tile);
@@ -117,14 +147,14 @@ f2f_hybrid_points_kernel(DevStereoFrames prev, DevStereoFrames curr, const gfpl_
 #pragma unroll
     for (int k = 0; k < F2F_QPT; k++) {
       if (cnt[k] == 1) {
-        best[k] = f2f_gate(KEY_NONE, best[k], s_proj[best[k] & KEY_IDX_MASK], plx[k], ply[k], window);
+        best[k] = f2f_gate(KEY_NONE, best[k], cam, T32, prev_pt[best[k] & KEY_IDX_MASK].P, plx[k], ply[k], window);
       } else if (cnt[k] > 1) {
         uint32_t b = KEY_NONE;
         const uint8_t* rows_g = prev.pdesc + (size_t)p * prev.cap_pt * 32;
         for (int q = 0; q < n_prev; q++) {
           const uint4* rp = reinterpret_cast<const uint4*>(rows_g + (size_t)q * 32);
           const uint32_t d = hamming256<GFPL_NORM_HAMMING>(qd[k], __ldg(rp), __ldg(rp + 1));
-          if ((int)d <= rint) b = f2f_gate(b, make_key(d, q), s_proj[q], plx[k], ply[k], window);
+          if ((int)d <= rint) b = f2f_gate(b, make_key(d, q), cam, T32, prev_pt[q].P, plx[k], ply[k], window);
         }
         best[k] = b;
       }
@@ -136,14 +166,13 @@ f2f_hybrid_points_kernel(DevStereoFrames prev, DevStereoFrames curr, const gfpl_
 }
 
 int launch_f2f_hybrid_points(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr,
-                             const gfpl_frame_state* state, uint32_t* best_key) {
+                             const gfpl_frame_state* state, double* T32 /*[B][32] scratch*/, uint32_t* best_key) {
   if (prev.B <= 0 || curr.cap_pt <= 0) return GFPL_OK;
-  const size_t smem = 2 * F2F_TILE_ROWS * 32 + (size_t)prev.cap_pt * sizeof(double2);
-  if (smem > 48 * 1024)
-    GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(f2f_hybrid_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  f2f_predict_kernel<<<(prev.B + 63) / 64, 64, 0, ctx->stream>>>(state, prev.B, T32);
+  GFPL_LAUNCH_OK(ctx);
   const int per_cta = F2F_THREADS * F2F_QPT;
   dim3 grid((curr.cap_pt + per_cta - 1) / per_cta, prev.B);
-  f2f_hybrid_points_kernel<<<grid, F2F_THREADS, smem, ctx->stream>>>(prev, curr, state, best_key, ctx->cam, ctx->cfg);
+  f2f_hybrid_points_kernel<<<grid, F2F_THREADS, 0, ctx->stream>>>(prev, curr, T32, best_key, ctx->cam, ctx->cfg);
   GFPL_LAUNCH_OK(ctx);
   return GFPL_OK;
 }

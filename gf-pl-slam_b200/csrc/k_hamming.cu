@@ -77,6 +77,114 @@ __global__ void __launch_bounds__(256) knn2_kernel(const uint8_t* __restrict__ a
   }
 }
 
+// Both directions from ONE pass over the distance matrix (d(a_i, b_j) serves a->b and b->a): the forward direction keeps
+// the full k=2 result per query row as above; the reverse direction keeps only its best match — all that the mutual
+// checks of the accept loops read (stereoFrame.cpp:836, stereoFrameHandler.cpp:735, mapHandler.cpp:253) — as a column
+// minimum of the key (distance, query index): warp-wide redux.min, then one shared-memory atomicMin per warp and train
+// row.  Ties resolve to the lowest index on both sides, as two independent knnMatch calls would.
+// multi_tile: the query rows of a problem span several CTAs; column minima are merged with global atomicMin on
+// out_ba.idx[].x (pre-set to 0xFFFFFFFF) and decoded by knn2_decode_kernel.
+template <int NORM, int QPT>
+__global__ void __launch_bounds__(256) knn2_sym_kernel(const uint8_t* __restrict__ a, const int32_t* __restrict__ na,
+                                                       int cap_a, const uint8_t* __restrict__ b,
+                                                       const int32_t* __restrict__ nb, int cap_b, Knn2Out out_ab,
+                                                       Knn2Out out_ba, int multi_tile) {
+  extern __shared__ uint32_t s_col[];  // [cap_b]
+  __shared__ __align__(128) uint8_t s_train[2 * KNN_TILE_ROWS * GFPL_DESC_BYTES];
+  __shared__ __align__(8) uint64_t s_bar[2];
+
+  const int p = blockIdx.y;
+  const uint8_t* q_base = a + (size_t)p * cap_a * 32;
+  const uint8_t* t_base = b + (size_t)p * cap_b * 32;
+  const int nq = na[p], nt = nb[p];
+  const int q0 = blockIdx.x * (blockDim.x * QPT);
+  const float inf = __int_as_float(0x7f800000);
+  if (q0 >= nq) {  // uniform; a problem without query rows still owes the reverse direction its "no match" rows
+    if (!multi_tile && blockIdx.x == 0)
+      for (int j = threadIdx.x; j < nt; j += blockDim.x) {
+        out_ba.idx[(size_t)p * cap_b + j] = make_int2(-1, -1);
+        out_ba.dist[(size_t)p * cap_b + j] = make_float2(inf, inf);
+      }
+    return;
+  }
+  for (int j = threadIdx.x; j < nt; j += blockDim.x) s_col[j] = KEY_NONE;
+
+  Desc256 q[QPT];
+  int qi[QPT];
+  uint32_t qk[QPT];  // reverse-key low part; rows past nq get a key above every valid one
+#pragma unroll
+  for (int k = 0; k < QPT; k++) {
+    qi[k] = q0 + k * blockDim.x + threadIdx.x;
+    q[k] = load_desc_global(q_base + (size_t)min(qi[k], nq - 1) * 32);
+    qk[k] = qi[k] < nq ? (uint32_t)qi[k] : 0xE0000000u;
+  }
+  uint32_t k0[QPT], k1[QPT];
+#pragma unroll
+  for (int k = 0; k < QPT; k++) k0[k] = k1[k] = KEY_NONE;
+  const bool leader = (threadIdx.x & 31) == 0;
+  const bool warp_live = q0 + (int)(threadIdx.x & ~31u) < nq;  // slot 0 of this warp holds at least one real query
+
+  TrainPipe<KNN_TILE_ROWS> pipe;
+  pipe.init(s_train, s_bar, t_base, nt);  // (its __syncthreads also publishes s_col)
+  for (int tile = 0; tile < pipe.ntiles; tile++) {
+    const uint4* rows = reinterpret_cast<const uint4*>(pipe.acquire(tile));
+    const int n = pipe.rows_in(tile);
+    const uint32_t t0 = tile * KNN_TILE_ROWS;
+    // ragged problems: a warp whose query rows all lie past nq skips the arithmetic (warp-uniform) and only keeps
+    // pace at the tile barriers
+    if (warp_live) {
+#pragma unroll 4
+      for (int r = 0; r < n; r++) {
+        const uint4 ra = rows[2 * r], rb = rows[2 * r + 1];
+        uint32_t rk = KEY_NONE;
+#pragma unroll
+        for (int k = 0; k < QPT; k++) {
+          const uint32_t d = hamming256<NORM>(q[k], ra, rb);
+          top2_update(k0[k], k1[k], make_key(d, t0 + r));
+          rk = min(rk, (d << KEY_IDX_BITS) + qk[k]);
+        }
+        rk = __reduce_min_sync(0xffffffffu, rk);
+        if (leader) atomicMin(&s_col[t0 + r], rk);
+      }
+    }
+    pipe.release(tile);
+  }
+
+#pragma unroll
+  for (int k = 0; k < QPT; k++) {
+    if (qi[k] < nq) {
+      int2 idx;
+      float2 dist;
+      idx.x = k0[k] == KEY_NONE ? -1 : (int)(k0[k] & KEY_IDX_MASK);
+      idx.y = k1[k] == KEY_NONE ? -1 : (int)(k1[k] & KEY_IDX_MASK);
+      dist.x = k0[k] == KEY_NONE ? inf : (float)(k0[k] >> KEY_IDX_BITS);
+      dist.y = k1[k] == KEY_NONE ? inf : (float)(k1[k] >> KEY_IDX_BITS);
+      out_ab.idx[(size_t)p * cap_a + qi[k]] = idx;
+      out_ab.dist[(size_t)p * cap_a + qi[k]] = dist;
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nt; j += blockDim.x) {
+    const uint32_t key = s_col[j];
+    if (multi_tile) {
+      atomicMin(reinterpret_cast<unsigned int*>(&out_ba.idx[(size_t)p * cap_b + j].x), key);
+    } else {
+      out_ba.idx[(size_t)p * cap_b + j] = make_int2((int)(key & KEY_IDX_MASK), -1);
+      out_ba.dist[(size_t)p * cap_b + j] = make_float2((float)(key >> KEY_IDX_BITS), inf);
+    }
+  }
+}
+
+// multi-tile epilogue: merged keys -> (index, distance) rows of the reverse direction
+__global__ void knn2_decode_kernel(const int32_t* __restrict__ nb, int cap_b, Knn2Out out_ba) {
+  const int p = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nb[p]) return;
+  const float inf = __int_as_float(0x7f800000);
+  const uint32_t key = (uint32_t)out_ba.idx[(size_t)p * cap_b + j].x;
+  out_ba.idx[(size_t)p * cap_b + j] = key == KEY_NONE ? make_int2(-1, -1) : make_int2((int)(key & KEY_IDX_MASK), -1);
+  out_ba.dist[(size_t)p * cap_b + j] = key == KEY_NONE ? make_float2(inf, inf) : make_float2((float)(key >> KEY_IDX_BITS), inf);
+}
+
 // choose warps per CTA (2..8) so that tiles * warps * 32 * QPT covers `cap` with the least padding
 static void pick_tiling(int cap, int qpt, int* block, int* tiles) {
   int best_w = 4, best_waste = 1 << 30;
@@ -90,10 +198,42 @@ static void pick_tiling(int cap, int qpt, int* block, int* tiles) {
   *tiles = (cap + best_w * 32 * qpt - 1) / (best_w * 32 * qpt);
 }
 
+template <int NORM, int QPT>
+static int launch_knn2_sym(gfpl_ctx* ctx, dim3 grid, int block, size_t smem, const uint8_t* a, const int32_t* na, int cap_a,
+                           const uint8_t* b, const int32_t* nb, int cap_b, Knn2Out out_ab, Knn2Out out_ba, int multi) {
+  if (smem > 32 * 1024)
+    GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(knn2_sym_kernel<NORM, QPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  knn2_sym_kernel<NORM, QPT><<<grid, block, smem, ctx->stream>>>(a, na, cap_a, b, nb, cap_b, out_ab, out_ba, multi);
+  return GFPL_OK;
+}
+
 int launch_knn2(gfpl_ctx* ctx, int B, const uint8_t* a, const int32_t* na, int cap_a, const uint8_t* b,
-                const int32_t* nb, int cap_b, int norm, Knn2Out out_ab, Knn2Out out_ba) {
+                const int32_t* nb, int cap_b, int norm, Knn2Out out_ab, Knn2Out out_ba, bool reverse_best_only) {
   if (B <= 0 || cap_a <= 0 || cap_b <= 0) return GFPL_OK;
   const bool both = out_ba.idx != nullptr;
+  if (both && reverse_best_only && (size_t)cap_b * 4 <= 160 * 1024) {
+    const int qpt = cap_a >= 256 ? 2 : 1;
+    int block, tiles;
+    pick_tiling(cap_a, qpt, &block, &tiles);
+    const int multi = tiles > 1;
+    if (multi) GFPL_CUDA_OK(ctx, cudaMemsetAsync(out_ba.idx, 0xFF, (size_t)B * cap_b * sizeof(int2), ctx->stream));
+    dim3 grid(tiles, B, 1);
+    const size_t smem = (size_t)cap_b * 4;
+    int rc;
+    if (norm == GFPL_NORM_HAMMING2)
+      rc = qpt == 2 ? launch_knn2_sym<GFPL_NORM_HAMMING2, 2>(ctx, grid, block, smem, a, na, cap_a, b, nb, cap_b, out_ab, out_ba, multi)
+                    : launch_knn2_sym<GFPL_NORM_HAMMING2, 1>(ctx, grid, block, smem, a, na, cap_a, b, nb, cap_b, out_ab, out_ba, multi);
+    else
+      rc = qpt == 2 ? launch_knn2_sym<GFPL_NORM_HAMMING, 2>(ctx, grid, block, smem, a, na, cap_a, b, nb, cap_b, out_ab, out_ba, multi)
+                    : launch_knn2_sym<GFPL_NORM_HAMMING, 1>(ctx, grid, block, smem, a, na, cap_a, b, nb, cap_b, out_ab, out_ba, multi);
+    if (rc != GFPL_OK) return rc;
+    GFPL_LAUNCH_OK(ctx);
+    if (multi) {
+      knn2_decode_kernel<<<dim3((cap_b + 255) / 256, B), 256, 0, ctx->stream>>>(nb, cap_b, out_ba);
+      GFPL_LAUNCH_OK(ctx);
+    }
+    return GFPL_OK;
+  }
   const int cap_q = both ? (cap_a > cap_b ? cap_a : cap_b) : cap_a;
   const int qpt = cap_q >= 256 ? 2 : 1;
   int block, tiles;

@@ -15,7 +15,7 @@
 
 namespace gfpl {
 
-constexpr int ACCEPT_THREADS = 256;
+constexpr int ACCEPT_THREADS = 128;
 
 // ordered block compaction: returns the output slot of this thread's element (valid when pred), advances
 // `base` (uniform across the CTA) by the number of accepted elements of this round.
@@ -94,7 +94,14 @@ __device__ double endpoint_cov_max_eig(const gfpl_camera& cam, double px, double
   const double d4 = disp2 * disp2;
   for (int i = 0; i < 9; i++) c[i] = c[i] * cam.b * cam.b / d4;
   double ev[3];
-  sym_eigenvalues<3>(c, ev);
+  sym_eigenvalues_unrolled<3>(c, ev);   // unsorted diagonal
+  // ascending insertion sort of three values, written out (same comparisons as sym_eigenvalues, NaN included)
+  if (ev[0] > ev[1]) { const double t = ev[0]; ev[0] = ev[1]; ev[1] = t; }
+  if (ev[1] > ev[2]) {
+    const double v = ev[2];
+    ev[2] = ev[1];
+    if (ev[0] > v) { ev[1] = ev[0]; ev[0] = v; } else ev[1] = v;
+  }
   return ev[2];
 }
 

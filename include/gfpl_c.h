@@ -517,8 +517,9 @@ void* gfpl_replay_pose_device_ptr(gfpl_replay* rp);
  *   6 stereo uncertainty + line cut         7 pose optimisation                    8 whole step */
 #define GFPL_NUM_STAGES 9
 int gfpl_replay_stage_ms(gfpl_replay* rp, float* ms /*[GFPL_NUM_STAGES]*/);
-/* algorithmic work of the last uploaded batch: descriptor pairs compared by kernels 0,1,3,4 (each pair = 8 popc.b32);
- * valid after gfpl_replay_run + sync (counts of the current stereo stage are read back). pairs: [4] */
+/* algorithmic work of the last uploaded batch: DISTINCT descriptor pairs (256-bit distances) needed by kernels 0,1,3,4,
+ * i.e. nq*nt per problem — one pass over the distance matrix serves both match directions (the reference's two knnMatch
+ * calls evaluate every distance twice); valid after gfpl_replay_run + sync. pairs: [4] */
 int gfpl_replay_pair_counts(gfpl_replay* rp, int64_t* pairs /*[4]*/);
 
 /* CUDA-event stopwatch on the context stream: record slot a/b (0..7), then elapsed (synchronises on b) */
