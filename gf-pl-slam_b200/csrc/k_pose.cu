@@ -162,6 +162,60 @@ __device__ __forceinline__ void ldlt6_solve_reg(const double* Hin, const double*
   }
 }
 
+// H is symmetric positive definite whenever the pose is observable, and then the pivoted and the unpivoted LDL^T are the
+// same solve up to rounding (both backward stable; this translation unit is compared at 1e-9).  The unpivoted
+// factorisation needs no row / column exchanges — the predicated swaps above are ~4/5 of the instructions of the
+// pivoted routine, executed by every lane in every GN iteration.  It reports failure when a pivot is not safely positive
+// (relative to the largest diagonal entry); the caller then runs the pivoted routine, which is what Eigen would do.
+__device__ __forceinline__ bool ldlt6_solve_nopivot(const double* H, const double* g, double* x) {
+  double L[36], d[6], id[6];
+  double dmax = H[0];
+#pragma unroll
+  for (int i = 1; i < 6; i++) dmax = fmax(dmax, H[i * 6 + i]);
+  const double floor_ = 1e-11 * dmax;
+  bool ok = dmax > 0.0 && dmax < 1e300;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    double t[6];
+#pragma unroll
+    for (int j = 0; j < k; j++) t[j] = L[k * 6 + j] * d[j];
+    double dk = H[k * 6 + k];
+#pragma unroll
+    for (int j = 0; j < k; j++) dk = fma(-L[k * 6 + j], t[j], dk);
+    d[k] = dk;
+    ok = ok && (dk > floor_);
+    id[k] = 1.0 / dk;
+#pragma unroll
+    for (int i = k + 1; i < 6; i++) {
+      double v = H[i * 6 + k];
+#pragma unroll
+      for (int j = 0; j < k; j++) v = fma(-L[i * 6 + j], t[j], v);
+      L[i * 6 + k] = v * id[k];
+    }
+  }
+  double y[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    double v = g[i];
+#pragma unroll
+    for (int j = 0; j < i; j++) v = fma(-L[i * 6 + j], y[j], v);
+    y[i] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) y[i] = y[i] * id[i];
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    double v = y[i];
+#pragma unroll
+    for (int j = i + 1; j < 6; j++) v = fma(-L[j * 6 + i], x[j], v);
+    x[i] = v;
+  }
+  return ok;
+}
+
+// pivoted fallback, out of line (gfpl_math.cuh ldlt6_solve, local-memory arrays): only for H that is not safely SPD
+__device__ __noinline__ void ldlt6_solve_pivoted_slow(const double* H, const double* g, double* x) { ldlt6_solve(H, g, x); }
+
 struct PairObs {
   int npt, nln;
   const gfpl_pt_obs* pts;
@@ -238,7 +292,13 @@ __device__ __forceinline__ int warp_gauss_newton(double* DT, const PairObs& o, c
   for (; iters < max_iters; iters++) {
     warp_optimize_functions(DT, o, cam, cfg, H, g, &err);
     if ((fabs(err - err_prev) < cfg.min_error_change) || (err < cfg.min_error)) break;
-    ldlt6_solve_reg(H, g, inc);
+    if (!ldlt6_solve_nopivot(H, g, inc)) {
+      double Hm[36], gm[6], xm[6];
+      for (int i = 0; i < 36; i++) Hm[i] = H[i];
+      for (int i = 0; i < 6; i++) gm[i] = g[i];
+      ldlt6_solve_pivoted_slow(Hm, gm, xm);
+      for (int i = 0; i < 6; i++) inc[i] = xm[i];
+    }
     double E[16], Ei[16];
     expmap_se3(inc, E);
     inverse_se3(E, Ei);
@@ -253,35 +313,58 @@ __device__ __forceinline__ int warp_gauss_newton(double* DT, const PairObs& o, c
   return iters;
 }
 
-// element [rank] of the ascending sort of n non-negative doubles, without sorting: MSB-first binary search on
-// the IEEE bit patterns (monotone for x >= 0).  Every probe is one warp-wide count (REDUX.SUM).
-// `TRANSFORM` applies a = (double)fabsf((float)(x - median)) on the fly for the second pass.
-template <bool TRANSFORM>
-__device__ __forceinline__ double warp_select(const double* res, int n, int rank, double median) {
+// element [rank] of the ascending order of n unsigned keys, without sorting: MSB-first binary search on the key bits,
+// one warp-wide count (REDUX.SUM) per probe.  key k lives at keys[k * STRIDE]; with RESTRICT only the elements whose
+// companion word keys[k * STRIDE + 1] equals `hi` take part (ties of the high word of a double, see below).
+template <int STRIDE, bool RESTRICT, int TOP_BIT>
+__device__ __forceinline__ uint32_t warp_select_u32(const uint32_t* keys, int n, int rank, uint32_t hi) {
   const int lane = threadIdx.x & 31;
-  unsigned long long prefix = 0ull;
-  for (int bit = 62; bit >= 0; bit--) {
-    const unsigned long long trial = prefix | (1ull << bit);
-    const double tv = __longlong_as_double((long long)trial);
+  uint32_t prefix = 0u;
+  for (int bit = TOP_BIT; bit >= 0; bit--) {
+    const uint32_t trial = prefix | (1u << bit);
     int cnt = 0;
     for (int k = lane; k < n; k += 32) {
-      double x = res[k];
-      if (TRANSFORM) x = (double)fabsf((float)(x - median));
-      cnt += (x < tv) ? 1 : 0;
+      const bool in = !RESTRICT || keys[k * STRIDE + 1] == hi;
+      cnt += (in && keys[k * STRIDE] < trial) ? 1 : 0;
     }
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     if (cnt <= rank) prefix = trial;
   }
-  return __longlong_as_double((long long)prefix);
+  return prefix;
 }
 
 // 1.4826 * MAD of res[0..n) exactly as vector_stdv_mad (auxiliar.cpp:521-537) computes it:
 // median = sorted[n/2]; a = (double)fabsf(res - median) (float truncation); MAD = sorted(a)[n/2].
-__device__ __forceinline__ double warp_stdv_mad(const double* res, int n) {
+// Order statistics of non-negative IEEE values are order statistics of their bit patterns, so both selections run on
+// 32-bit integer keys: the median on the high words of the doubles (low words only among the elements that tie on the
+// high word), the MAD on the float patterns of `a`, staged once in `scratch` (n words).
+__device__ __forceinline__ double warp_stdv_mad(const double* res, int n, uint32_t* scratch) {
   if (n == 0) return 0.0;
-  const double median = warp_select<false>(res, n, n / 2, 0.0);
-  const double mad = warp_select<true>(res, n, n / 2, median);
-  return 1.4826 * mad;
+  const int lane = threadIdx.x & 31;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(res);  // little endian: w[2k] low word, w[2k+1] high word
+  const int rank = n / 2;
+  const uint32_t hi = warp_select_u32<2, false, 30>(w + 1, n, rank, 0u);
+  int below = 0, same = 0;
+  for (int k = lane; k < n; k += 32) {
+    below += w[2 * k + 1] < hi ? 1 : 0;
+    same += w[2 * k + 1] == hi ? 1 : 0;
+  }
+  below = __reduce_add_sync(0xffffffffu, below);
+  same = __reduce_add_sync(0xffffffffu, same);
+  uint32_t lo;
+  if (same == 1) {  // the usual case: the element with that high word is the median
+    uint32_t mine = 0u;
+    for (int k = lane; k < n; k += 32) mine = w[2 * k + 1] == hi ? w[2 * k] : mine;
+    lo = __reduce_max_sync(0xffffffffu, mine);
+  } else {
+    lo = warp_select_u32<2, true, 31>(w, n, rank - below, hi);
+  }
+  const double median = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+  for (int k = lane; k < n; k += 32) scratch[k] = __float_as_uint(fabsf((float)(res[k] - median)));
+  __syncwarp();
+  const uint32_t mad = warp_select_u32<1, false, 30>(scratch, n, rank, 0u);
+  __syncwarp();
+  return 1.4826 * (double)__uint_as_float(mad);
 }
 
 // removeOutliers (:2058-2116): returns the number of points / lines flagged
@@ -303,8 +386,9 @@ __device__ __forceinline__ void warp_remove_outliers(const double* DT, const Pai
     res_l[k] = r * sqrt(ob.sigma2);
   }
   __syncwarp();
-  const double th_p = cfg.inlier_k * warp_stdv_mad(res_p, o.npt);
-  const double th_l = cfg.inlier_k * warp_stdv_mad(res_l, o.nln);
+  uint32_t* scratch = reinterpret_cast<uint32_t*>(s_res + o.npt + o.nln);  // [max(npt, nln)] words behind the residuals
+  const double th_p = cfg.inlier_k * warp_stdv_mad(res_p, o.npt, scratch);
+  const double th_l = cfg.inlier_k * warp_stdv_mad(res_l, o.nln, scratch);
   int dp = 0, dl = 0;
   for (int k = lane; k < o.npt; k += 32)
     if (res_p[k] > th_p) { o.pin[k] = 0; dp++; }
@@ -354,14 +438,17 @@ __device__ __noinline__ void unccomp_se3(const double* T1, const double* covT1, 
     }
 }
 
+__host__ __device__ inline int pose_smem_doubles(int cap_pt, int cap_ln) { return cap_pt + cap_ln + (cap_pt + cap_ln + 1) / 2; }
+
 __global__ void __launch_bounds__(POSE_WARPS * 32, POSE_MIN_BLOCKS)
 pose_optimize_kernel(DevTrackObs obs, const gfpl_frame_state* __restrict__ state, const double* __restrict__ DT_ini,
                      int overload, PoseRaw* __restrict__ raw, gfpl_camera cam, gfpl_config cfg) {
-  extern __shared__ double s_res_all[];  // [POSE_WARPS][cap_pt + cap_ln]
+  extern __shared__ double s_res_all[];  // [POSE_WARPS][pose_smem_doubles(cap_pt, cap_ln)]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p = blockIdx.x * POSE_WARPS + warp;
   if (p >= obs.B) return;
-  double* s_res = s_res_all + (size_t)warp * (obs.cap_pt + obs.cap_ln);
+  // per warp: cap_pt + cap_ln residuals, then (cap_pt + cap_ln) / 2 doubles = cap_pt + cap_ln words of select scratch
+  double* s_res = s_res_all + (size_t)warp * pose_smem_doubles(obs.cap_pt, obs.cap_ln);
   PairObs o;
   o.npt = obs.n_pt[p]; o.nln = obs.n_ln[p];
   o.pts = obs.pt + (size_t)p * obs.cap_pt; o.pin = obs.pt_inlier + (size_t)p * obs.cap_pt;
@@ -477,7 +564,7 @@ int launch_pose_optimize(gfpl_ctx* ctx, DevTrackObs obs, const gfpl_frame_state*
   // the hand-off buffer lives in the (stream-ordered) default pool; it is tiny: 456 B per pair
   PoseRaw* raw = nullptr;
   GFPL_CUDA_OK(ctx, cudaMallocAsync((void**)&raw, (size_t)obs.B * sizeof(PoseRaw), ctx->stream));
-  const size_t smem = (size_t)POSE_WARPS * (obs.cap_pt + obs.cap_ln) * sizeof(double);
+  const size_t smem = (size_t)POSE_WARPS * pose_smem_doubles(obs.cap_pt, obs.cap_ln) * sizeof(double);
   if (smem > 48 * 1024)
     GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(pose_optimize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (obs.B + POSE_WARPS - 1) / POSE_WARPS;
