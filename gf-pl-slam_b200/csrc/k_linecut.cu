@@ -258,11 +258,44 @@ struct GroupState {
 #define CUT_MIN_BLOCKS 4
 #endif
 
+// ---- exact (reference-arithmetic) evaluations, out of line -----------------------------------------------------------
+// They run only in the rare rounds the screening cannot decide and once per cut line; keeping their ~100 live doubles
+// out of the round loop is what lets the loop run from registers.  cam / cfg are the CTA's shared-memory copies.
+__device__ __noinline__ double exact_metric_at(const gfpl_camera* cam, const gfpl_config* cfg, const GroupState* G,
+                                               double c0, double c1) {
+  LineInfo I;
+  pose_info_on_line(*cam, *cfg, G->DT, G->L, c0, c1, I);
+  double M[21];
+#pragma unroll
+  for (int a = 0; a < 6; a++)
+#pragma unroll
+    for (int b = 0; b <= a; b++) M[tri(a, b)] = info_entry(I, a, b) + G->sum[tri(a, b)];
+  return cut_metric(*cfg, M);
+}
+__device__ __noinline__ double exact_metric_start(const gfpl_config* cfg, const GroupState* G) { return cut_metric(*cfg, G->sum0); }
+__device__ __noinline__ void exact_info_store(const gfpl_camera* cam, const gfpl_config* cfg, const GroupState* G, double c0,
+                                              double c1, int j, double* invCovPose) {
+  LineInfo I;
+  pose_info_on_line(*cam, *cfg, G->DT, G->L, c0, c1, I);
+  for (int e = j; e < 36; e += CUT_GROUP) invCovPose[e] = info_entry(I, e / 6, e % 6);
+}
+
+__device__ __forceinline__ double shfl_up_f64(unsigned mask, double v, int delta, int width) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_up_sync(mask, lo, delta, width);
+  hi = __shfl_up_sync(mask, hi, delta, width);
+  return __hiloint2double(hi, lo);
+}
+
 __global__ void __launch_bounds__(CUT_THREADS, CUT_MIN_BLOCKS)
 linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __restrict__ state, DevTrackObs obs,
                const gfpl_line_cov* __restrict__ prev_cov, int cov_cap, gfpl_line_cut* __restrict__ cut_all,
                gfpl_camera cam, gfpl_config cfg) {
   __shared__ GroupState s_grp[CUT_THREADS / CUT_GROUP];
+  __shared__ gfpl_camera s_cam;
+  __shared__ gfpl_config s_cfg;
+  if (threadIdx.x == 0) { s_cam = cam; s_cfg = cfg; }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int j = lane & (CUT_GROUP - 1);             // neighbour index of this lane
   const int grp = lane / CUT_GROUP;                 // pair slot inside the warp
@@ -437,47 +470,33 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
         const double dj = factor(si, ei);          // this lane's candidate
         if (!have_dcur) { dcur = factor(1, 4); have_dcur = true; }   // the current cut (same value in every lane)
         __syncwarp(gmask);
-        // replay the reference's selection on the factors, but only if every comparison is clear by > CUT_TAU (relative)
-        double best = dcur;
-        int bj = -1;
-        bool clear = (dcur > 0.0) && dcur < 1e300;
+        // replay the reference's selection ("first strictly better in j order", :1722-1730) on the factors, but only if
+        // every comparison it makes is clear by > CUT_TAU (relative).  Candidate j is compared with the running best
+        // before it = max(current cut, valid candidates i < j): an exclusive prefix maximum over the group's lanes.
+        const double mv = valid ? dj : 0.0;   // usable factors are > 0: a masked lane never raises the maximum
+        double pre = mv;
 #pragma unroll
-        for (int jj = 0; jj < CUT_GROUP; jj++) {
-          const double mj = shfl_f64(gmask, dj, jj, CUT_GROUP);
-          const int vj = __shfl_sync(gmask, (int)valid, jj, CUT_GROUP);
-          if (vj) {
-            clear = clear && (mj > 0.0) && mj < 1e300 && fabs(mj - best) > CUT_TAU * best;
-            if (mj > best) { best = mj; bj = jj; }
-          }
+        for (int dlt = 1; dlt < CUT_GROUP; dlt <<= 1) {
+          const double t = shfl_up_f64(gmask, pre, dlt, CUT_GROUP);
+          pre = (j >= dlt) ? fmax(pre, t) : pre;
         }
+        const double excl = shfl_up_f64(gmask, pre, 1, CUT_GROUP);
+        const double before = (j == 0) ? dcur : fmax(dcur, excl);
+        const bool lane_clear = !valid || ((dj > 0.0) && dj < 1e300 && fabs(dj - before) > CUT_TAU * before);
+        const unsigned okmask = __ballot_sync(gmask, lane_clear) & gmask;
+        const bool clear = (dcur > 0.0) && dcur < 1e300 && okmask == gmask;
+        const double best = fmax(dcur, shfl_f64(gmask, pre, CUT_GROUP - 1, CUT_GROUP));
+        const unsigned winners = __ballot_sync(gmask, valid && dj == best) & gmask;
+        const int bj = (best > dcur && winners) ? (__ffs(winners) - 1) - grp * CUT_GROUP : -1;
         if (clear) { decided = true; cand = bj; have_exact_last = false; dcur = best; }
       }
-      LineInfo I;
       if (!decided) {
         // exact round: the reference's arithmetic (also the only path for the min-eigenvalue metric)
         if (!have_exact_last) {  // metric of the current cut, needed as the running best
-          if (at_start) metric_last = cut_metric(cfg, G.sum0);
-          else {
-            pose_info_on_line(cam, cfg, G.DT, G.L, cur0, cur1, I);
-            double M[21];
-#pragma unroll
-            for (int a = 0; a < 6; a++)
-#pragma unroll
-              for (int b = 0; b <= a; b++) M[tri(a, b)] = info_entry(I, a, b) + G.sum[tri(a, b)];
-            metric_last = cut_metric(cfg, M);
-          }
+          metric_last = at_start ? exact_metric_start(&s_cfg, &G) : exact_metric_at(&s_cam, &s_cfg, &G, cur0, cur1);
           have_exact_last = true;
         }
-        double metric = 0.0;
-        if (valid) {
-          pose_info_on_line(cam, cfg, G.DT, G.L, ct0, ct1, I);
-          double M[21];
-#pragma unroll
-          for (int a = 0; a < 6; a++)
-#pragma unroll
-            for (int b = 0; b <= a; b++) M[tri(a, b)] = info_entry(I, a, b) + G.sum[tri(a, b)];
-          metric = cut_metric(cfg, M);
-        }
+        const double metric = valid ? exact_metric_at(&s_cam, &s_cfg, &G, ct0, ct1) : 0.0;
         // "first strictly better in j order" (:1722-1730)
         double best = metric_last;
 #pragma unroll
@@ -495,11 +514,7 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
       at_start = false;
     }
     // invCovPose of the accepted cut, in the reference's arithmetic (cut {0,0} is already stored by pass 1)
-    if (cur0 != 0.0 || cur1 != 0.0) {
-      LineInfo I;
-      pose_info_on_line(cam, cfg, G.DT, G.L, cur0, cur1, I);
-      for (int e = j; e < 36; e += CUT_GROUP) C.invCovPose[e] = info_entry(I, e / 6, e % 6);
-    }
+    if (cur0 != 0.0 || cur1 != 0.0) exact_info_store(&s_cam, &s_cfg, &G, cur0, cur1, j, C.invCovPose);
     __syncwarp(gmask);
     // updateEndPointByRatio (:1451-1470) — lane 0 of the group writes the results
     if (j == 0) {
