@@ -252,6 +252,7 @@ struct GroupState {
   double sum0[21];      // invCov_sum before the current line's information is removed (exact metric of cut {0,0})
   double Sinv[36];      // inverse of (invCov_sum - info(line)) for the screening path, row-major
   double half[6][HF_SIZE];  // the six published halves of the current round
+  double J[CUT_GROUP][6];   // point Jacobians of the current chunk of the invCov_sum pass
 };
 
 #ifndef CUT_MIN_BLOCKS
@@ -374,19 +375,26 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
     for (int i = 0; i < 3; i++) {
       T4[i * 4 + 0] = G.DT[i * 3 + 0]; T4[i * 4 + 1] = G.DT[i * 3 + 1]; T4[i * 4 + 2] = G.DT[i * 3 + 2]; T4[i * 4 + 3] = G.DT[9 + i];
     }
-    for (int k = 0; k < npt; k++) {  // getPoseInfoPoint (:1414-1447)
-      double c[3], uv[2], J[6];
-      se3_apply(T4, pts[k].P, c);
-      projection(cam, c, uv);
-      const double dx = uv[0] - pts[k].pl_obs[0], dy = uv[1] - pts[k].pl_obs[1];
-      jac6(cam.fx / fmax(cfg.homog_th, c[2] * c[2]), c[0], c[1], c[2], dx, dy, J);
+    // getPoseInfoPoint (:1414-1447): the group's 8 lanes evaluate 8 Jacobians at a time (one point each) and publish
+    // them; every lane then adds its three products point by point, i.e. in the reference's order
+    for (int k0 = 0; k0 < npt; k0 += CUT_GROUP) {
+      if (k0 + j < npt) {
+        const gfpl_pt_obs& po = pts[k0 + j];
+        double c[3], uv[2], J[6];
+        se3_apply(T4, po.P, c);
+        projection(cam, c, uv);
+        const double dx = uv[0] - po.pl_obs[0], dy = uv[1] - po.pl_obs[1];
+        jac6(cam.fx / fmax(cfg.homog_th, c[2] * c[2]), c[0], c[1], c[2], dx, dy, J);
 #pragma unroll
-      for (int q = 0; q < 3; q++) {
-        double Ja = 0.0, Jb = 0.0;
-#pragma unroll
-        for (int i = 0; i < 6; i++) { Ja = (ea[q] == i) ? J[i] : Ja; Jb = (eb[q] == i) ? J[i] : Jb; }
-        acc[q] = acc[q] + Ja * Jb;
+        for (int i = 0; i < 6; i++) G.J[j][i] = J[i];
       }
+      __syncwarp(gmask);
+      const int nk = min(CUT_GROUP, npt - k0);
+      for (int k = 0; k < nk; k++) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) acc[q] = acc[q] + G.J[k][ea[q]] * G.J[k][eb[q]];
+      }
+      __syncwarp(gmask);
     }
 #pragma unroll
     for (int q = 0; q < 3; q++)
