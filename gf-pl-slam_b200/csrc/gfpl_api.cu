@@ -291,6 +291,39 @@ int gfpl_knn2_hamming256_batch(gfpl_ctx* ctx, int32_t B, const uint8_t* q, const
   return finish(ctx);
 }
 
+int gfpl_knn2_mutual_batch(gfpl_ctx* ctx, int32_t B, const uint8_t* q, const int32_t* nq, int32_t cap_q, const uint8_t* t,
+                           const int32_t* nt, int32_t cap_t, int32_t norm, int32_t* out_idx, float* out_dist,
+                           int32_t* out_best_idx, float* out_best_dist) {
+  if (!ctx) return GFPL_E_INVALID;
+  REQUIRE(ctx, B >= 0 && cap_q > 0 && cap_t > 0);
+  REQUIRE(ctx, norm == GFPL_NORM_HAMMING || norm == GFPL_NORM_HAMMING2);
+  if (B == 0) return GFPL_OK;
+  REQUIRE(ctx, q && nq && t && nt && out_idx && out_dist && out_best_idx && out_best_dist);
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DevMem m(ctx);
+  size_t nqt = (size_t)B * cap_q, ntt = (size_t)B * cap_t;
+  uint8_t* dq = m.upload(q, nqt * 32);
+  uint8_t* dt = m.upload(t, ntt * 32);
+  int32_t* dnq = m.upload(nq, B);
+  int32_t* dnt = m.upload(nt, B);
+  Knn2Out o{}, r{};
+  REQUIRE_MEM(ctx, dq && dt && dnq && dnt && alloc_knn(m, nqt, &o) && alloc_knn(m, ntt, &r));
+  GFPL_CUDA_OK(ctx, cudaMemsetAsync(o.idx, 0xFF, nqt * sizeof(int2), ctx->stream));
+  GFPL_CUDA_OK(ctx, cudaMemsetAsync(o.dist, 0, nqt * sizeof(float2), ctx->stream));
+  GFPL_CUDA_OK(ctx, cudaMemsetAsync(r.idx, 0xFF, ntt * sizeof(int2), ctx->stream));
+  GFPL_CUDA_OK(ctx, cudaMemsetAsync(r.dist, 0, ntt * sizeof(float2), ctx->stream));
+  CHECK(launch_knn2(ctx, B, dq, dnq, cap_q, dt, dnt, cap_t, norm, o, r, /*reverse_best_only=*/true));
+  download(ctx, (int2*)out_idx, o.idx, nqt);
+  download(ctx, (float2*)out_dist, o.dist, nqt);
+  std::vector<int2> ri(ntt);
+  std::vector<float2> rd(ntt);
+  download(ctx, ri.data(), r.idx, ntt);
+  download(ctx, rd.data(), r.dist, ntt);
+  CHECK(finish(ctx));
+  for (size_t k = 0; k < ntt; k++) { out_best_idx[k] = ri[k].x; out_best_dist[k] = rd[k].x; }
+  return GFPL_OK;
+}
+
 int gfpl_knn2_hamming256(gfpl_ctx* ctx, const uint8_t* q, int32_t nq, const uint8_t* t, int32_t nt, int32_t norm,
                          int32_t* out_idx, float* out_dist) {
   if (!ctx) return GFPL_E_INVALID;

@@ -78,6 +78,11 @@ namespace gfpl {
 int launch_knn2(gfpl_ctx* ctx, int B, const uint8_t* a, const int32_t* na, int cap_a, const uint8_t* b,
                 const int32_t* nb, int cap_b, int norm, Knn2Out out_ab, Knn2Out out_ba, bool reverse_best_only = false);
 
+// tensor-core form of the NORM_HAMMING both-directions call (k_hamming_tc.cu): forward k=2, reverse best
+bool knn2_tc_fits(int cap_a, int cap_b);
+int launch_knn2_tc(gfpl_ctx* ctx, int B, const uint8_t* a, const int32_t* na, int cap_a, const uint8_t* b, const int32_t* nb,
+                   int cap_b, Knn2Out out_ab, Knn2Out out_ba);
+
 // K2: radius match for one problem (CSR), two passes
 int launch_radius_count(gfpl_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int norm, float radius,
                         int32_t* counts);

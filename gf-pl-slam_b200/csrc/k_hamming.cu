@@ -9,6 +9,8 @@
 // streams the whole train set through a two-stage TMA-bulk ring in shared memory.  Result order follows
 // cv::BFMatcher: ascending distance, ties -> ascending trainIdx (packed-key min, see gfpl_hamming.cuh).
 // Algorithmic work per launch = sum over problems of nq*nt pair distances = 8 popc.b32 each.
+#include <cstdlib>
+
 #include "gfpl_hamming.cuh"
 #include "gfpl_internal.h"
 
@@ -211,6 +213,9 @@ int launch_knn2(gfpl_ctx* ctx, int B, const uint8_t* a, const int32_t* na, int c
                 const int32_t* nb, int cap_b, int norm, Knn2Out out_ab, Knn2Out out_ba, bool reverse_best_only) {
   if (B <= 0 || cap_a <= 0 || cap_b <= 0) return GFPL_OK;
   const bool both = out_ba.idx != nullptr;
+  static const bool no_tc = getenv("GFPL_NO_TC") != nullptr;   // A/B switch for measurements
+  if (both && reverse_best_only && norm == GFPL_NORM_HAMMING && !no_tc && knn2_tc_fits(cap_a, cap_b))
+    return launch_knn2_tc(ctx, B, a, na, cap_a, b, nb, cap_b, out_ab, out_ba);
   if (both && reverse_best_only && (size_t)cap_b * 4 <= 160 * 1024) {
     const int qpt = cap_a >= 256 ? 2 : 1;
     int block, tiles;

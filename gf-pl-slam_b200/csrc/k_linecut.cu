@@ -259,6 +259,32 @@ struct GroupState {
 #define CUT_MIN_BLOCKS 4
 #endif
 
+// once per line, out of line (57 live doubles): every lane computes S^-1 redundantly, the lanes publish it together
+__device__ __noinline__ bool spd_inverse6_publish(GroupState* G, int j) {
+  double Sinv[36];
+  const bool ok = spd_inverse6(G->sum, Sinv);
+#pragma unroll
+  for (int e = 0; e < 36; e++)
+    if ((e & (CUT_GROUP - 1)) == j) G->Sinv[e] = Sinv[e];
+  return ok;
+}
+
+// initial information of one line at cut {0,0} (:1638-1649), out of line
+__device__ __noinline__ void exact_info_initial(const gfpl_camera* cam, const gfpl_config* cfg, const double* DT,
+                                                const gfpl_ln_obs* o, const gfpl_line_cov* c, gfpl_line_cut* C) {
+  double Lr[LD_SIZE];
+  LineInfo I;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { Lr[LD_SP + k] = o->sP[k]; Lr[LD_EP + k] = o->eP[k]; }
+  Lr[LD_LE] = o->le_obs[0]; Lr[LD_LE + 1] = o->le_obs[1];
+#pragma unroll
+  for (int k = 0; k < 9; k++) { Lr[LD_CS + k] = c->covS[k]; Lr[LD_CE + k] = c->covE[k]; }
+  pose_info_on_line(*cam, *cfg, DT, Lr, 0.0, 0.0, I);
+  C->cutRatio[0] = 0.0; C->cutRatio[1] = 0.0;
+  for (int a = 0; a < 6; a++)
+    for (int b = 0; b < 6; b++) C->invCovPose[a * 6 + b] = info_entry(I, a, b);
+}
+
 // ---- exact (reference-arithmetic) evaluations, out of line -----------------------------------------------------------
 // They run only in the rare rounds the screening cannot decide and once per cut line; keeping their ~100 live doubles
 // out of the round loop is what lets the loop run from registers.  cam / cfg are the CTA's shared-memory copies.
@@ -335,22 +361,7 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
   const double nb1 = (j == 2 || j == 4 || j == 6) ? step : ((j == 3 || j == 5 || j == 7) ? -step : 0.0);
 
   // pass 1a: initial information of every line (cut = 0), lanes stride over the lines (:1638-1649)
-  for (int l = j; l < nln; l += CUT_GROUP) {
-    double Lr[LD_SIZE];
-    LineInfo I;
-    const gfpl_ln_obs& o = lns[l];
-    const gfpl_line_cov& c = cov[o.prev_idx];
-#pragma unroll
-    for (int k = 0; k < 3; k++) { Lr[LD_SP + k] = o.sP[k]; Lr[LD_EP + k] = o.eP[k]; }
-    Lr[LD_LE] = o.le_obs[0]; Lr[LD_LE + 1] = o.le_obs[1];
-#pragma unroll
-    for (int k = 0; k < 9; k++) { Lr[LD_CS + k] = c.covS[k]; Lr[LD_CE + k] = c.covE[k]; }
-    pose_info_on_line(cam, cfg, G.DT, Lr, 0.0, 0.0, I);
-    gfpl_line_cut& C = cut[l];
-    C.cutRatio[0] = 0.0; C.cutRatio[1] = 0.0;
-    for (int a = 0; a < 6; a++)
-      for (int b = 0; b < 6; b++) C.invCovPose[a * 6 + b] = info_entry(I, a, b);
-  }
+  for (int l = j; l < nln; l += CUT_GROUP) exact_info_initial(&s_cam, &s_cfg, G.DT, &lns[l], &cov[lns[l].prev_idx], &cut[l]);
   __syncwarp(gmask);
 
   // pass 1b/2: invCov_sum in the reference's order — lines, then points, each element summed sequentially.
@@ -432,13 +443,7 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
     __syncwarp(gmask);
     // screening set-up: S^-1 once per line (every lane computes it redundantly, lanes publish it together)
     bool fast_ok = cfg.max_vol_line_cut != 0;
-    if (fast_ok) {
-      double Sinv[36];
-      fast_ok = spd_inverse6(G.sum, Sinv);
-#pragma unroll
-      for (int e = 0; e < 36; e++)
-        if ((e & (CUT_GROUP - 1)) == j) G.Sinv[e] = Sinv[e];
-    }
+    if (fast_ok) fast_ok = spd_inverse6_publish(&G, j);
     __syncwarp(gmask);
     double cur0 = 0.0, cur1 = 0.0;
     double metric_last = 0.0;      // the reference's metric of the current cut; evaluated lazily (exact rounds only)

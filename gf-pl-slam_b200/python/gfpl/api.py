@@ -152,6 +152,17 @@ class Context:
                                                      _vp(idx), _vp(dist)))
         return idx, dist
 
+    def knn2_mutual(self, q, nq, t, nt, norm=S.NORM_HAMMING):
+        """q: [B][cap_q][32], t: [B][cap_t][32] -> forward (idx, dist) [B][cap_q][2] and reverse best (idx, dist) [B][cap_t]"""
+        q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+        nq = np.ascontiguousarray(nq, np.int32); nt = np.ascontiguousarray(nt, np.int32)
+        B, cap_q, cap_t = q.shape[0], q.shape[1], t.shape[1]
+        idx = np.empty((B, cap_q, 2), np.int32); dist = np.empty((B, cap_q, 2), np.float32)
+        bi = np.empty((B, cap_t), np.int32); bd = np.empty((B, cap_t), np.float32)
+        self._check(lib().gfpl_knn2_mutual_batch(self._h, B, _vp(q), _vp(nq), cap_q, _vp(t), _vp(nt), cap_t, norm, _vp(idx),
+                                                 _vp(dist), _vp(bi), _vp(bd)))
+        return idx, dist, bi, bd
+
     def radius(self, q, t, r, norm=S.NORM_HAMMING, cap=None):
         q, t = _u8(q), _u8(t)
         cap = len(q) * len(t) if cap is None else cap

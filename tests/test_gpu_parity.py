@@ -659,3 +659,30 @@ def test_lba_step_schur_solve(ctx, orc):
             ctx.lba_step(w2, 0.001, 1)
     finally:
         ctx.set_camera(api.euroc_camera())
+
+
+@pytest.mark.parametrize("norm", [S.NORM_HAMMING, S.NORM_HAMMING2])
+@pytest.mark.parametrize("tie", [False, True])
+def test_knn2_mutual_both_directions(ctx, orc, norm, tie):
+    """forward k=2 + reverse best match from one pass (NORM_HAMMING: tensor-core int8 +-1 product) == two knnMatch calls"""
+    rng = np.random.default_rng(41 + norm)
+    mk = (lambda n: synth.tie_stress_descriptors(rng, n)) if tie else (lambda n: rng.integers(0, 256, (n, 32), dtype=np.uint8))
+    for cap_q, cap_t, sizes in ((300, 310, [(300, 310), (257, 129), (128, 160), (2, 3), (0, 5), (7, 0), (130, 161)]),
+                                (1000, 900, [(1000, 900), (513, 321)]),
+                                (100, 100, [(100, 100), (64, 17), (2, 2)])):
+        B = len(sizes)
+        q = np.zeros((B, cap_q, 32), np.uint8); t = np.zeros((B, cap_t, 32), np.uint8)
+        nq = np.array([s[0] for s in sizes], np.int32); nt = np.array([s[1] for s in sizes], np.int32)
+        for p in range(B):
+            q[p, :nq[p]] = mk(nq[p]); t[p, :nt[p]] = mk(nt[p])
+            m = min(nq[p], nt[p]) // 2
+            t[p, :m] = q[p, :m] ^ np.packbits(rng.random((m, 256)) < 0.04, axis=1)     # true matches
+        idx, dist, bi, bd = ctx.knn2_mutual(q, nq, t, nt, norm)
+        for p in range(B):
+            if nq[p] and nt[p]:
+                oi, od = orc.knn2(q[p, :nq[p]], t[p, :nt[p]], norm)
+                ri, rd = orc.knn2(t[p, :nt[p]], q[p, :nq[p]], norm)
+                assert np.array_equal(idx[p, :nq[p]], oi) and np.array_equal(dist[p, :nq[p]], od), (cap_q, p)
+                assert np.array_equal(bi[p, :nt[p]], ri[:, 0]) and np.array_equal(bd[p, :nt[p]], rd[:, 0]), (cap_q, p)
+            else:
+                assert (idx[p, :nq[p]] == -1).all() and (bi[p, :nt[p]] == -1).all()
