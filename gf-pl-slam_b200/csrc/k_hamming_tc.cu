@@ -7,10 +7,10 @@
 // so D = A * B^T (M = queries, N = train rows, K = 256) gives all distances of the problem.  One CTA per problem:
 //   1. the 32-byte descriptors are expanded to int8 rows in shared memory, directly in the K-major no-swizzle UMMA
 //      layout (8-row x 16-byte core matrices: byte(r, k) at (r/8)*SBO + (k/16)*LBO + (r%8)*16 + k%16),
-//   2. one thread issues tcgen05.mma.kind::i8 (M = 128, N <= 160, K = 32 per instruction, 8 per tile) into TMEM and
-//      commits to an mbarrier,
-//   3. the CTA's 128 threads read their accumulator row with tcgen05.ld (thread = TMEM lane = query row) and keep the
-//      packed-key top-2 of the row — thread-local, no shuffles, no atomics.
+//   2. one thread issues tcgen05.mma.kind::i8 (M = 128, N <= 128, K = 32 per instruction, 8 per pass) into one of two
+//      TMEM accumulator buffers and commits to that buffer's mbarrier; the next pass is issued before this one is read,
+//   3. the CTA's 256 threads read accumulator rows with tcgen05.ld (TMEM lane = query row, two threads per row, half of
+//      the columns each) and keep the packed-key top-2 of the row — thread-local, no shuffles, no atomics.
 // The reverse direction (nearest query of every train row) is the same product with the roles swapped (tensor time is
 // nearly free here) and a top-1 selection.  Per distance the ALU pipe sees ~5 (+3 reverse) operations instead of ~25.
 // Results are bit-identical to k_hamming.cu: same keys (distance << 20 | index), same tie rule.
@@ -20,8 +20,9 @@
 namespace gfpl {
 
 constexpr int TC_M = 128;            // query rows per tile = TMEM lanes
-constexpr int TC_NPASS = 160;        // train rows per accumulator pass (TMEM columns used)
-constexpr int TC_TMEM_COLS = 256;    // allocation (power of two >= TC_NPASS): two CTAs share the SM's 512 columns
+constexpr int TC_THREADS = 256;      // warps w and w + 4 share the TMEM lanes 32 (w % 4) .. +31 and split the columns
+constexpr int TC_NPASS = 128;        // train rows per accumulator buffer (TMEM columns)
+constexpr int TC_TMEM_COLS = 256;    // two accumulator buffers; two CTAs share the SM's 512 columns
 constexpr int TC_ROW_BYTES = 256;    // one expanded descriptor
 constexpr int TC_LBO = 128;          // bytes between the 16-byte K chunks of a core-matrix row group
 constexpr int TC_SBO = 16 * TC_LBO;  // bytes between 8-row groups (16 K chunks of 128 B each)
@@ -45,16 +46,18 @@ __device__ __forceinline__ uint32_t expand_nibble(uint32_t nib) {
   return t | ((t ^ 0x01010101u) * 255u);
 }
 
-// one descriptor row (8 words, or zeros past the end) -> 16 chunks of 16 int8 in the UMMA layout; lut[byte] = its 8 int8
+// one descriptor row (8 words, or zeros past the end) -> 16 chunks of 16 int8 in the UMMA layout.  lut[nibble] = its 4
+// int8: 16 words in 16 different banks, so the look-ups of a warp never conflict.
 __device__ __forceinline__ void expand_row(uint8_t* tile, int r, const uint4& lo, const uint4& hi, bool zero,
-                                           const uint2* __restrict__ lut) {
+                                           const uint32_t* __restrict__ lut) {
   uint8_t* row = tile + (r >> 3) * TC_SBO + (r & 7) * 16;
   const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
   for (int c = 0; c < 16; c++) {
-    const uint32_t bits = (w[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
-    const uint2 a = lut[bits & 0xFFu], b = lut[bits >> 8];
-    *reinterpret_cast<uint4*>(row + c * TC_LBO) = zero ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(a.x, a.y, b.x, b.y);
+    const uint32_t bits = w[c >> 1] >> ((c & 1) * 16);
+    uint4 v = make_uint4(lut[bits & 15u], lut[(bits >> 4) & 15u], lut[(bits >> 8) & 15u], lut[(bits >> 12) & 15u]);
+    if (zero) v = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(row + c * TC_LBO) = v;
   }
 }
 
@@ -76,58 +79,73 @@ __device__ __forceinline__ void expand_row(uint8_t* tile, int r, const uint4& lo
 
 // One match direction: rows `m` (nm of them) against rows `n` (nn).  TOP2: keep the two best train rows per m-row
 // (forward direction, [i][0] and [i][1]); else only the best (reverse direction, [j][0]).  The n side is expanded in
-// full into sN, the m side tile by tile into sM; every thread owns one m-row = one TMEM lane, so the selection is
-// thread-local: no shuffles, no atomics.
+// full into sN, the m side tile by tile into sM.  Accumulators are double-buffered in TMEM: the products of pass i+1
+// are issued before pass i is reduced.  A thread owns one m-row (= TMEM lane) and half of the columns of every pass, so
+// the selection is thread-local; the two halves of a row are merged through shared memory once per tile.
 template <bool TOP2>
 __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base, int nm, const uint8_t* __restrict__ n_base,
                                              int nn, int2* __restrict__ out_idx, float2* __restrict__ out_dist, uint8_t* sM,
-                                             uint8_t* sN, const uint2* lut, uint64_t* bar, uint32_t& phase, uint32_t tmem) {
+                                             uint8_t* sN, const uint32_t* lut, uint64_t* bars /*[2]*/, uint32_t* phases /*[2]*/,
+                                             uint32_t tmem, uint2* s_merge /*[TC_M]*/) {
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & (TC_M - 1);     // m-row inside the tile = TMEM lane
+  const int half = tid >> 7;            // which half of a pass's columns this thread reduces
   const float inf = __int_as_float(0x7f800000);
   const int nnp = (nn + 15) & ~15;
-  for (int r = tid; r < nnp; r += TC_M) {
+  for (int r = tid; r < nnp; r += TC_THREADS) {
     const uint4* src = reinterpret_cast<const uint4*>(n_base + (size_t)min(r, nn - 1) * 32);
     expand_row(sN, r, __ldg(src), __ldg(src + 1), r >= nn, lut);
   }
   const uint32_t sM_addr = smem_u32(sM), sN_addr = smem_u32(sN);
-  const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const int npass = (nnp + TC_NPASS - 1) / TC_NPASS;
+
+  auto issue = [&](int pass) {  // thread 0: the 8 K-steps of one pass into buffer (pass & 1), then commit to its barrier
+    const int n0 = pass * TC_NPASS;
+    const int N = min(TC_NPASS, nnp - n0);
+    const uint32_t idesc = umma_idesc_i8(N);
+    const uint32_t d_tmem = tmem + (uint32_t)((pass & 1) * TC_NPASS);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) {  // K = 256 in steps of 32 int8 = two 16-byte chunks
+      const uint64_t da = umma_desc(sM_addr + ks * 2 * TC_LBO);
+      const uint64_t db = umma_desc(sN_addr + (n0 >> 3) * TC_SBO + ks * 2 * TC_LBO);
+      const uint32_t acc = ks > 0 ? 1u : 0u;
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "setp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+          "}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u)
+          : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[pass & 1]))
+                 : "memory");
+  };
+
   for (int m0 = 0; m0 < nm; m0 += TC_M) {
-    const int mi = m0 + tid;
-    {
+    if (tid < TC_M) {
+      const int mi = m0 + tid;
       const uint4* src = reinterpret_cast<const uint4*>(m_base + (size_t)min(mi, nm - 1) * 32);
       expand_row(sM, tid, __ldg(src), __ldg(src + 1), mi >= nm, lut);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the MMA
     __syncthreads();
+    if (tid == 0) issue(0);
     // two independent selection chains (even / odd columns), merged after the last pass
     uint32_t k0a = KEY_NONE, k1a = KEY_NONE, k0b = KEY_NONE, k1b = KEY_NONE;
-    for (int n0 = 0; n0 < nnp; n0 += TC_NPASS) {
+    for (int pass = 0; pass < npass; pass++) {
+      const int n0 = pass * TC_NPASS;
       const int N = min(TC_NPASS, nnp - n0);
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t idesc = umma_idesc_i8(N);
-#pragma unroll
-        for (int ks = 0; ks < 8; ks++) {  // K = 256 in steps of 32 int8 = two 16-byte chunks
-          const uint64_t da = umma_desc(sM_addr + ks * 2 * TC_LBO);
-          const uint64_t db = umma_desc(sN_addr + (n0 >> 3) * TC_SBO + ks * 2 * TC_LBO);
-          const uint32_t acc = ks > 0 ? 1u : 0u;
-          asm volatile(
-              "{\n\t"
-              ".reg .pred p;\n\t"
-              "setp.ne.b32 p, %4, 0;\n\t"
-              "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
-              "}\n" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u)
-              : "memory");
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                     : "memory");
-      }
-      mbar_wait(bar, phase);
-      phase ^= 1u;
+      if (tid == 0 && pass + 1 < npass) issue(pass + 1);  // its buffer was drained before the barrier that ended pass - 1
+      mbar_wait(&bars[pass & 1], phases[pass & 1]);
+      phases[pass & 1] ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-      // accumulator row of this thread, 16 columns at a time, next chunk in flight while this one is reduced
+      // this thread's share of the pass: columns [cbeg, cend) of the buffer, 16 at a time, next chunk in flight
+      const int cbeg = half * (TC_NPASS / 2), cend = min(N, cbeg + TC_NPASS / 2);
       const int nvalid = min(N, nn - n0);  // columns of this pass that are real train rows
+      const uint32_t taddr = tlane + (uint32_t)((pass & 1) * TC_NPASS);
       uint32_t va[16], vb[16];
       // key = (2 * hamming) << 19 | column = distance << 20 | column, with 2 * hamming = 256 - dot
       auto reduce16 = [&](const uint32_t* v, int c0) {
@@ -149,24 +167,32 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
           }
         }
       };
-      TC_LD16(va, taddr);
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        TC_WAIT16(va);
-        if (c0 + 16 < N) TC_LD16(vb, taddr + (uint32_t)(c0 + 16));
-        reduce16(va, c0);
-        if (c0 + 16 < N) {
-          TC_WAIT16(vb);
-          if (c0 + 32 < N) TC_LD16(va, taddr + (uint32_t)(c0 + 32));
-          reduce16(vb, c0 + 16);
+      if (cbeg < cend) {
+        TC_LD16(va, taddr + (uint32_t)cbeg);
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
+          TC_WAIT16(va);
+          if (c0 + 16 < cend) TC_LD16(vb, taddr + (uint32_t)(c0 + 16));
+          reduce16(va, c0);
+          if (c0 + 16 < cend) {
+            TC_WAIT16(vb);
+            if (c0 + 32 < cend) TC_LD16(va, taddr + (uint32_t)(c0 + 32));
+            reduce16(vb, c0 + 16);
+          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();  // every accumulator read is done before the next pass overwrites TMEM (and sM)
+      __syncthreads();  // this buffer is drained (pass + 2 may overwrite it); after the last pass sM is free as well
     }
-    if (mi < nm) {
-      uint32_t k0 = k0a, k1 = k1a;
-      if (TOP2) { top2_update(k0, k1, k0b); top2_update(k0, k1, k1b); }
-      else k0 = min(k0a, k0b);
+    uint32_t k0 = k0a, k1 = k1a;
+    if (TOP2) { top2_update(k0, k1, k0b); top2_update(k0, k1, k1b); }
+    else k0 = min(k0a, k0b);
+    if (half == 1) s_merge[row] = make_uint2(k0, k1);
+    __syncthreads();
+    const int mi = m0 + row;
+    if (half == 0 && mi < nm) {
+      const uint2 o = s_merge[row];
+      if (TOP2) { top2_update(k0, k1, o.x); top2_update(k0, k1, o.y); }
+      else k0 = min(k0, o.x);
       int2 idx;
       float2 dist;
       idx.x = (int)(k0 & KEY_IDX_MASK);
@@ -176,18 +202,20 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
       out_idx[mi] = idx;
       out_dist[mi] = dist;
     }
+    // (the next tile's first __syncthreads orders the s_merge reads above before its writes)
   }
 }
 
-__global__ void __launch_bounds__(TC_M)
+__global__ void __launch_bounds__(TC_THREADS)
 knn2_tc_kernel(const uint8_t* __restrict__ a, const int32_t* __restrict__ na, int cap_a, const uint8_t* __restrict__ b,
                const int32_t* __restrict__ nb, int cap_b, Knn2Out out_ab, Knn2Out out_ba) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sM = smem;                                   // [128][256] int8 tile of the "query" side, UMMA layout
   uint8_t* sN = smem + TC_M * TC_ROW_BYTES;             // [<= max(cap_a, cap_b) rounded to 16][256] "train" side
-  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ uint32_t s_tmem;
-  __shared__ uint2 s_lut[256];
+  __shared__ uint32_t s_lut[16];
+  __shared__ uint2 s_merge[TC_M];
 
   const int p = blockIdx.x;
   const int nq = na[p], nt = nb[p];
@@ -196,11 +224,11 @@ knn2_tc_kernel(const uint8_t* __restrict__ a, const int32_t* __restrict__ na, in
   const uint8_t* q_base = a + (size_t)p * cap_a * 32;
   const uint8_t* t_base = b + (size_t)p * cap_b * 32;
   if (nq == 0 || nt == 0) {  // nothing to multiply: "no match" rows on both sides (uniform exit, before any allocation)
-    for (int i = tid; i < nq; i += TC_M) {
+    for (int i = tid; i < nq; i += TC_THREADS) {
       out_ab.idx[(size_t)p * cap_a + i] = make_int2(-1, -1);
       out_ab.dist[(size_t)p * cap_a + i] = make_float2(inf, inf);
     }
-    for (int j = tid; j < nt; j += TC_M) {
+    for (int j = tid; j < nt; j += TC_THREADS) {
       out_ba.idx[(size_t)p * cap_b + j] = make_int2(-1, -1);
       out_ba.dist[(size_t)p * cap_b + j] = make_float2(inf, inf);
     }
@@ -211,20 +239,22 @@ knn2_tc_kernel(const uint8_t* __restrict__ a, const int32_t* __restrict__ na, in
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   if (tid == 0) {
-    mbar_init(&s_bar, 1);
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
     mbar_fence_init();
   }
-  for (int v = tid; v < 256; v += TC_M) s_lut[v] = make_uint2(expand_nibble(v & 15), expand_nibble(v >> 4));
+  if (tid < 16) s_lut[tid] = expand_nibble(tid);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = s_tmem;
-  uint32_t phase = 0;
+  uint32_t phases[2] = {0u, 0u};
   // forward: queries a, train b, two nearest; reverse: queries b, train a, nearest only (all the mutual checks read)
   tc_direction<true>(q_base, nq, t_base, nt, out_ab.idx + (size_t)p * cap_a, out_ab.dist + (size_t)p * cap_a, sM, sN, s_lut,
-                     &s_bar, phase, tmem);
+                     s_bar, phases, tmem, s_merge);
+  __syncthreads();
   tc_direction<false>(t_base, nt, q_base, nq, out_ba.idx + (size_t)p * cap_b, out_ba.dist + (size_t)p * cap_b, sM, sN, s_lut,
-                      &s_bar, phase, tmem);
+                      s_bar, phases, tmem, s_merge);
   __syncthreads();
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS));
@@ -236,14 +266,15 @@ static size_t knn2_tc_smem(int cap_a, int cap_b) {
 }
 
 bool knn2_tc_fits(int cap_a, int cap_b) {
-  return cap_a > 0 && cap_b > 0 && cap_a < (1 << 19) && cap_b < (1 << 19) && knn2_tc_smem(cap_a, cap_b) <= 200 * 1024;
+  // small problems are dominated by the fixed cost of a CTA (TMEM allocation, barriers): they stay on the integer pipes
+  return cap_a >= 128 && cap_b >= 128 && cap_a < (1 << 19) && cap_b < (1 << 19) && knn2_tc_smem(cap_a, cap_b) <= 200 * 1024;
 }
 
 int launch_knn2_tc(gfpl_ctx* ctx, int B, const uint8_t* a, const int32_t* na, int cap_a, const uint8_t* b, const int32_t* nb,
                    int cap_b, Knn2Out out_ab, Knn2Out out_ba) {
   const size_t smem = knn2_tc_smem(cap_a, cap_b);
   GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  knn2_tc_kernel<<<B, TC_M, smem, ctx->stream>>>(a, na, cap_a, b, nb, cap_b, out_ab, out_ba);
+  knn2_tc_kernel<<<B, TC_THREADS, smem, ctx->stream>>>(a, na, cap_a, b, nb, cap_b, out_ab, out_ba);
   GFPL_LAUNCH_OK(ctx);
   return GFPL_OK;
 }
