@@ -1,0 +1,231 @@
+// gfpl_tc.cuh — shared device code of the tensor-core Hamming kernels (k_hamming_tc.cu, k_f2f.cu): descriptor expansion
+// to int8 +-1 in the UMMA shared-memory layout, tcgen05.mma issue, TMEM read-back and the thread-local top-2 selection.
+#pragma once
+#include "gfpl_hamming.cuh"
+
+namespace gfpl {
+
+constexpr int TC_M = 128;            // query rows per tile = TMEM lanes
+constexpr int TC_THREADS = 256;      // warps w and w + 4 share the TMEM lanes 32 (w % 4) .. +31 and split the columns
+constexpr int TC_NPASS = 128;        // train rows per accumulator buffer (TMEM columns)
+constexpr int TC_TMEM_COLS = 256;    // two accumulator buffers; two CTAs share the SM's 512 columns
+constexpr int TC_ROW_BYTES = 256;    // one expanded descriptor
+constexpr int TC_LBO = 128;          // bytes between the 16-byte K chunks of a core-matrix row group
+constexpr int TC_SBO = 16 * TC_LBO;  // bytes between 8-row groups (16 K chunks of 128 B each)
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start >> 4 [0,14), LBO >> 4 [16,30), SBO >> 4 [32,46), version 1 [46,48),
+  // layout type SWIZZLE_NONE = 0 [61,64)
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(TC_LBO >> 4) << 16) | ((uint64_t)(TC_SBO >> 4) << 32) |
+         (1ull << 46);
+}
+
+__device__ __forceinline__ uint32_t umma_idesc_i8(int n) {
+  // InstrDescriptor: c_format S32 = 2 [4,6), a/b format INT8 signed = 1 [7,10) [10,13), K-major A and B, N >> 3 [17,23),
+  // M >> 4 [24,29)
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+}
+
+// 4 descriptor bits -> 4 int8: bit set -> +1 (0x01), clear -> -1 (0xFF)
+__device__ __forceinline__ uint32_t expand_nibble(uint32_t nib) {
+  const uint32_t t = (nib * 0x00204081u) & 0x01010101u;  // bit b of the nibble -> LSB of byte b
+  return t | ((t ^ 0x01010101u) * 255u);
+}
+
+// one descriptor row (8 words, or zeros past the end) -> 16 chunks of 16 int8 in the UMMA layout.  lut[nibble] = its 4
+// int8: 16 words in 16 different banks, so the look-ups of a warp never conflict.
+__device__ __forceinline__ void expand_row(uint8_t* tile, int r, const uint4& lo, const uint4& hi, bool zero,
+                                           const uint32_t* __restrict__ lut) {
+  uint8_t* row = tile + (r >> 3) * TC_SBO + (r & 7) * 16;
+  const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+  for (int c = 0; c < 16; c++) {
+    const uint32_t bits = w[c >> 1] >> ((c & 1) * 16);
+    uint4 v = make_uint4(lut[bits & 15u], lut[(bits >> 4) & 15u], lut[(bits >> 8) & 15u], lut[(bits >> 12) & 15u]);
+    if (zero) v = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(row + c * TC_LBO) = v;
+  }
+}
+// half a row (16 of its 32 bytes -> 8 chunks): two threads share one row of the 128-row tile
+__device__ __forceinline__ void expand_half_row(uint8_t* tile, int r, int h, const uint4& q, bool zero,
+                                                const uint32_t* __restrict__ lut) {
+  uint8_t* row = tile + (r >> 3) * TC_SBO + (r & 7) * 16 + h * 8 * TC_LBO;
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const uint32_t bits = w[c >> 1] >> ((c & 1) * 16);
+    uint4 v = make_uint4(lut[bits & 15u], lut[(bits >> 4) & 15u], lut[(bits >> 8) & 15u], lut[(bits >> 12) & 15u]);
+    if (zero) v = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(row + c * TC_LBO) = v;
+  }
+}
+
+#define TC_LD16(v, addr)                                                                                                  \
+  asm volatile(                                                                                                           \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n" \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),      \
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                          \
+      : "r"(addr))
+
+// tcgen05.ld is asynchronous: its destination registers are valid only after tcgen05.wait::ld.  Tying them to the wait
+// as read-write operands keeps the compiler from scheduling their uses above it.
+#define TC_WAIT16(v)                                                                                                     \
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"                                                                        \
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),          \
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])     \
+               :                                                                                                          \
+               : "memory")
+
+// One match direction: rows `m` (nm of them) against rows `n` (nn).  TOP2: keep the two best train rows per m-row
+// (forward direction, [i][0] and [i][1]); else only the best (reverse direction, [j][0]).  The n side is expanded in
+// full into sN, the m side tile by tile into sM.  Accumulators are double-buffered in TMEM: the products of pass i+1
+// are issued before pass i is reduced.  A thread owns one m-row (= TMEM lane) and half of the columns of every pass, so
+// the selection is thread-local; the two halves of a row are merged through shared memory once per tile and handed to
+// `emit(m_row, k0, k1)`.
+template <bool TOP2, class Emit>
+__device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base, int nm, const uint8_t* __restrict__ n_base,
+                                             int nn, uint8_t* sM, uint8_t* sN, const uint32_t* lut, uint64_t* bars /*[2]*/,
+                                             uint32_t* phases /*[2]*/, uint32_t tmem, uint2* s_merge /*[TC_M]*/, Emit emit) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & (TC_M - 1);     // m-row inside the tile = TMEM lane
+  const int half = tid >> 7;            // which half of a pass's columns this thread reduces
+  const int nnp = (nn + 15) & ~15;
+  for (int r = tid; r < nnp; r += TC_THREADS) {
+    const uint4* src = reinterpret_cast<const uint4*>(n_base + (size_t)min(r, nn - 1) * 32);
+    expand_row(sN, r, __ldg(src), __ldg(src + 1), r >= nn, lut);
+  }
+  const uint32_t sM_addr = smem_u32(sM), sN_addr = smem_u32(sN);
+  const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const int npass = (nnp + TC_NPASS - 1) / TC_NPASS;
+
+  auto issue = [&](int pass) {  // thread 0: the 8 K-steps of one pass into buffer (pass & 1), then commit to its barrier
+    const int n0 = pass * TC_NPASS;
+    const int N = min(TC_NPASS, nnp - n0);
+    const uint32_t idesc = umma_idesc_i8(N);
+    const uint32_t d_tmem = tmem + (uint32_t)((pass & 1) * TC_NPASS);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) {  // K = 256 in steps of 32 int8 = two 16-byte chunks
+      const uint64_t da = umma_desc(sM_addr + ks * 2 * TC_LBO);
+      const uint64_t db = umma_desc(sN_addr + (n0 >> 3) * TC_SBO + ks * 2 * TC_LBO);
+      const uint32_t acc = ks > 0 ? 1u : 0u;
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "setp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+          "}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u)
+          : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[pass & 1]))
+                 : "memory");
+  };
+
+  for (int m0 = 0; m0 < nm; m0 += TC_M) {
+    {
+      const int mi = m0 + row;
+      const uint4* src = reinterpret_cast<const uint4*>(m_base + (size_t)min(mi, nm - 1) * 32);
+      expand_half_row(sM, row, half, __ldg(src + half), mi >= nm, lut);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the MMA
+    __syncthreads();
+    if (tid == 0) issue(0);
+    // two independent selection chains (even / odd columns), merged after the last pass
+    uint32_t k0a = KEY_NONE, k1a = KEY_NONE, k0b = KEY_NONE, k1b = KEY_NONE;
+    for (int pass = 0; pass < npass; pass++) {
+      const int n0 = pass * TC_NPASS;
+      const int N = min(TC_NPASS, nnp - n0);
+      if (tid == 0 && pass + 1 < npass) issue(pass + 1);  // its buffer was drained before the barrier that ended pass - 1
+      mbar_wait(&bars[pass & 1], phases[pass & 1]);
+      phases[pass & 1] ^= 1u;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+      // this thread's share of the pass: columns [cbeg, cend) of the buffer, 16 at a time, next chunk in flight
+      const int cbeg = half * (TC_NPASS / 2), cend = min(N, cbeg + TC_NPASS / 2);
+      const int nvalid = min(N, nn - n0);  // columns of this pass that are real train rows
+      const uint32_t taddr = tlane + (uint32_t)((pass & 1) * TC_NPASS);
+      uint32_t va[16], vb[16];
+      // key = (2 * hamming) << 19 | column = distance << 20 | column, with 2 * hamming = 256 - dot
+      auto reduce16 = [&](const uint32_t* v, int c0) {
+        const uint32_t colbase = (uint32_t)(n0 + c0);
+        if (c0 + 16 <= nvalid) {
+#pragma unroll
+          for (int jx = 0; jx < 16; jx++) {
+            const uint32_t key = ((256u - v[jx]) << (KEY_IDX_BITS - 1)) + (colbase + jx);
+            if (TOP2) { if (jx & 1) top2_update(k0b, k1b, key); else top2_update(k0a, k1a, key); }
+            else { if (jx & 1) k0b = min(k0b, key); else k0a = min(k0a, key); }
+          }
+        } else {
+#pragma unroll
+          for (int jx = 0; jx < 16; jx++) {
+            if (c0 + jx < nvalid) {
+              const uint32_t key = ((256u - v[jx]) << (KEY_IDX_BITS - 1)) + (colbase + jx);
+              if (TOP2) top2_update(k0a, k1a, key); else k0a = min(k0a, key);
+            }
+          }
+        }
+      };
+      if (cbeg < cend) {
+        TC_LD16(va, taddr + (uint32_t)cbeg);
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
+          TC_WAIT16(va);
+          if (c0 + 16 < cend) TC_LD16(vb, taddr + (uint32_t)(c0 + 16));
+          reduce16(va, c0);
+          if (c0 + 16 < cend) {
+            TC_WAIT16(vb);
+            if (c0 + 32 < cend) TC_LD16(va, taddr + (uint32_t)(c0 + 32));
+            reduce16(vb, c0 + 16);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();  // this buffer is drained (pass + 2 may overwrite it); after the last pass sM is free as well
+    }
+    uint32_t k0 = k0a, k1 = k1a;
+    if (TOP2) { top2_update(k0, k1, k0b); top2_update(k0, k1, k1b); }
+    else k0 = min(k0a, k0b);
+    if (half == 1) s_merge[row] = make_uint2(k0, k1);
+    __syncthreads();
+    const int mi = m0 + row;
+    if (half == 0 && mi < nm) {
+      const uint2 o = s_merge[row];
+      if (TOP2) { top2_update(k0, k1, o.x); top2_update(k0, k1, o.y); }
+      else k0 = min(k0, o.x);
+      emit(mi, k0, k1);  // packed keys (distance << 20 | n-row); k1 == KEY_NONE without a second row (or !TOP2)
+    }
+    // (the next tile's first __syncthreads orders the s_merge reads above before its writes)
+  }
+}
+
+// CTA-wide set-up of the tensor path: TMEM allocation (warp 0), the two accumulator barriers, the nibble LUT
+struct TcShared {
+  uint64_t bar[2];
+  uint32_t tmem;
+  uint32_t lut[16];
+  uint2 merge[TC_M];
+};
+__device__ __forceinline__ uint32_t tc_begin(TcShared& S) {
+  const int tid = threadIdx.x;
+  if ((tid >> 5) == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem)), "r"(TC_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+    mbar_init(&S.bar[0], 1);
+    mbar_init(&S.bar[1], 1);
+    mbar_fence_init();
+  }
+  if (tid < 16) S.lut[tid] = expand_nibble(tid);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  return S.tmem;
+}
+__device__ __forceinline__ void tc_end(uint32_t tmem) {
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS));
+}
+inline size_t tc_smem_bytes(int cap_n) { return (size_t)TC_M * TC_ROW_BYTES + (size_t)((cap_n + 15) & ~15) * TC_ROW_BYTES; }
+
+}  // namespace gfpl

@@ -9,9 +9,11 @@
 // points under two gates, so it needs no variable-length lists: one thread per current point streams the
 // previous descriptors (TMA-bulk staged) and keeps min(distance<<20 | prev_idx) over gated candidates.
 // POPC-bound like K1; algorithmic work = n_prev*n_curr pair distances.
-#include "gfpl_hamming.cuh"
+#include <cstdlib>
+
 #include "gfpl_internal.h"
 #include "gfpl_math.cuh"
+#include "gfpl_tc.cuh"
 
 namespace gfpl {
 
@@ -165,11 +167,69 @@ f2f_hybrid_points_kernel(DevStereoFrames prev, DevStereoFrames curr, const doubl
     if (tq[k] < n_curr) best_key[(size_t)p * curr.cap_pt + tq[k]] = best[k];
 }
 
+// Tensor-core form of the search above (gfpl_tc.cuh): rows = current points, columns = previous points.  The radius
+// test needs the number of candidates and the smallest key among them; the two smallest keys of a row decide both:
+// none / exactly one / several candidates within the radius.  One candidate (the usual case) goes through the
+// projection gate, several are rescanned exactly as in the integer kernel.
+__global__ void __launch_bounds__(TC_THREADS)
+f2f_hybrid_points_tc_kernel(DevStereoFrames prev, DevStereoFrames curr, const double* __restrict__ T32_all,
+                            uint32_t* __restrict__ best_key, gfpl_camera cam, gfpl_config cfg) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sM = smem;
+  uint8_t* sN = smem + TC_M * TC_ROW_BYTES;
+  __shared__ __align__(8) TcShared S;
+  const int p = blockIdx.x;
+  const int n_prev = prev.n_pt[p], n_curr = curr.n_pt[p];
+  uint32_t* out = best_key + (size_t)p * curr.cap_pt;
+  if (!(cfg.has_points && n_prev > 0) || n_curr == 0) {
+    for (int t = threadIdx.x; t < n_curr; t += TC_THREADS) out[t] = KEY_NONE;
+    return;
+  }
+  const uint8_t* prev_desc = prev.pdesc + (size_t)p * prev.cap_pt * 32;
+  const uint8_t* curr_desc = curr.pdesc + (size_t)p * curr.cap_pt * 32;
+  const gfpl_point_feature* prev_pt = prev.pt + (size_t)p * prev.cap_pt;
+  const gfpl_point_feature* curr_pt = curr.pt + (size_t)p * curr.cap_pt;
+  const double* T32 = T32_all + (size_t)p * 32;
+  const float radius = (float)cfg.point_match_radius;
+  const int rint = radius >= 0.f ? (int)floorf(fminf(radius, 1024.f)) : -1;   // (float)d <= radius  <=>  d <= rint
+  const uint32_t lim = (uint32_t)(rint + 1) << KEY_IDX_BITS;                  // keys of candidates are < lim
+  const double window = cfg.f2f_point_window;
+  const uint32_t tmem = tc_begin(S);
+  uint32_t phases[2] = {0u, 0u};
+  tc_direction<true>(curr_desc, n_curr, prev_desc, n_prev, sM, sN, S.lut, S.bar, phases, tmem, S.merge,
+                     [&](int t, uint32_t k0, uint32_t k1) {
+                       uint32_t best = KEY_NONE;
+                       if (k0 < lim) {
+                         const double plx = curr_pt[t].pl[0], ply = curr_pt[t].pl[1];
+                         if (!(k1 < lim)) {
+                           best = f2f_gate(KEY_NONE, k0, cam, T32, prev_pt[k0 & KEY_IDX_MASK].P, plx, ply, window);
+                         } else {  // several previous points within the radius: every one of them is gated (:524-546)
+                           const Desc256 qd = load_desc_global(curr_desc + (size_t)t * 32);
+                           for (int q = 0; q < n_prev; q++) {
+                             const uint4* rp = reinterpret_cast<const uint4*>(prev_desc + (size_t)q * 32);
+                             const uint32_t d = hamming256<GFPL_NORM_HAMMING>(qd, __ldg(rp), __ldg(rp + 1));
+                             if ((int)d <= rint) best = f2f_gate(best, make_key(d, q), cam, T32, prev_pt[q].P, plx, ply, window);
+                           }
+                         }
+                       }
+                       out[t] = best;
+                     });
+  tc_end(tmem);
+}
+
 int launch_f2f_hybrid_points(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr,
                              const gfpl_frame_state* state, double* T32 /*[B][32] scratch*/, uint32_t* best_key) {
   if (prev.B <= 0 || curr.cap_pt <= 0) return GFPL_OK;
   f2f_predict_kernel<<<(prev.B + 63) / 64, 64, 0, ctx->stream>>>(state, prev.B, T32);
   GFPL_LAUNCH_OK(ctx);
+  static const bool no_tc = getenv("GFPL_NO_TC") != nullptr;   // A/B switch for measurements
+  const size_t tc_smem = tc_smem_bytes(prev.cap_pt);
+  if (!no_tc && prev.cap_pt >= 128 && curr.cap_pt >= 128 && prev.cap_pt < (1 << 19) && tc_smem <= 200 * 1024) {
+    GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(f2f_hybrid_points_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+    f2f_hybrid_points_tc_kernel<<<prev.B, TC_THREADS, tc_smem, ctx->stream>>>(prev, curr, T32, best_key, ctx->cam, ctx->cfg);
+    GFPL_LAUNCH_OK(ctx);
+    return GFPL_OK;
+  }
   const int per_cta = F2F_THREADS * F2F_QPT;
   dim3 grid((curr.cap_pt + per_cta - 1) / per_cta, prev.B);
   f2f_hybrid_points_kernel<<<grid, F2F_THREADS, 0, ctx->stream>>>(prev, curr, T32, best_key, ctx->cam, ctx->cfg);
