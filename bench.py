@@ -47,7 +47,7 @@ def workload_config(a):
                         "per image), good line cutting %s" % (a.n_pt, a.n_ln, "off" if a.no_linecut else "on"),
             "pairs_per_gpu": a.pairs, "points_per_image": a.n_pt, "lines_per_image": a.n_ln,
             "prev_frame_layout": "stereo survivors packed to the largest count in the batch; e2e uploads slim records (gfpl_prev_frames)",
-            "stages": "stereo knn+accept -> f2f hybrid search+accept -> stereo uncertainty+line cut -> pose GN(5)+MAD+GN(10)",
+            "stages": "stereo knn (points: tcgen05 int8, lines: popcount)+accept -> f2f hybrid search (tcgen05 int8)+accept -> stereo uncertainty+line cut -> pose GN(5)+MAD+GN(10)",
             "l2_policy": "inputs larger than L2 (>=700 MB read per step vs 126 MB L2)", "parallelism": "pairs sharded over ranks, NCCL all_gather of pose records only"}
 
 
@@ -159,7 +159,7 @@ def run_reference(a, rank):
     sample = "%d of %d pairs per step, %d std::threads over pairs" % (n, a.pairs, cores)
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
                       "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
-                      "vs_baseline": None, "dtype": "u8/int32 matching + f64 optimisation", "data": "synthetic",
+                      "vs_baseline": None, "dtype": "u8 descriptors -> int8 tensor-core / int32 popcount matching (exact) + f64 optimisation", "data": "synthetic",
                       "config": workload_config(a),
                       "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
                       "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -325,52 +325,72 @@ def main():
     if rank == 0:
         value = world * B * a.steps / (ms * 1e-3)
         e2e_value = world * B * a.steps / (e2e_ms * 1e-3)
-        # dominant kernel: the Hamming matching kernels (kernels 0,1,3,4 share one inner loop).  They are bound by two
-        # integer pipes, not by HBM and not by the tensor cores: per 256-bit pair the NORM_HAMMING loop
-        # issues POPC_PER_PAIR popc.b32 on the 16-lane POPC pipe (8 naive, 5 after the carry-save compression) and
-        # ALU_PER_PAIR ops on the ALU pipe (SASS mix: profiles/r1_sass_mix.md).  Roofline = the slower pipe at the
-        # MEASURED pipe rates (gfpl_measure_peaks / gfpl_measure_alu_peak, run live above).
-        # `pairs` counts DISTINCT distances (nq*nt per problem): both match directions come from one pass over the
-        # distance matrix (knn2_sym_kernel), where the reference's two knnMatch calls evaluate each distance twice.
-        # ALU ops per pair of the symmetric kernel: 15.6 LOP3 + 3 VIMNMX + 2.8 IADD3 + 1.8 ISETP + 0.7 SHF + 0.7 LEA.
-        POPC_PER_PAIR, ALU_PER_PAIR = 5.0, 24.6
-        k_ms = [stage[0], stage[1], stage[3], stage[4]]
-        dom = int(np.argmax(k_ms))
-        names = ["knn2 stereo points (both directions from one pass)", "knn2 stereo lines NORM_HAMMING2 (both directions from one pass)",
-                 "f2f hybrid fused radius+projection search", "knn2 f2f lines (both directions from one pass)"]
-        achieved = pairs[dom] / (k_ms[dom] * 1e-3) / 1e12                      # T pairs/s
-        peak = min(popc_peak / POPC_PER_PAIR, alu_peak / ALU_PER_PAIR)         # T pairs/s
-        alg_bytes = B * (2 * a.n_pt * 32 + 2 * a.n_pt * 16) if dom == 0 else None
-        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] \
-            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-        traffic = None   # dram__bytes_read+write per launch of the dominant kernel, from the committed ncu --set full capture
+        # ---- rooflines ---------------------------------------------------------------------------
+        # `pairs` counts DISTINCT 256-bit distances (nq*nt per problem).  Point matching (stereo knn, f2f search) runs
+        # on the tensor cores: every descriptor bit becomes an int8 +1/-1 and the distance matrix is the s32 product
+        # (dot = 256 - 2 hamming, exact); a distance costs 256 int8 MACs = 512 ops per direction.  Line matching
+        # (NORM_HAMMING2 / small problems) stays on the integer pipes: POPC (16 lanes/clk/SM) + ALU.
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        mp = json.load(open(peaks_file)) if os.path.exists(peaks_file) else {}
+        hbm_peak = mp.get("hbm_gbs", 6650.0)
+        bf16_peak = mp.get("bf16_tflops_sustained", 1590.0)       # kernel timed inside a long step -> sustained figure
+        int8_peak = 2.0 * bf16_peak                               # int8 dense = 2x bf16 dense on B200 (4.5 vs 2.25 P nominal)
+        tc_on = os.environ.get("GFPL_NO_TC") is None
+        pose_all = np.concatenate(pose_hosts)
+        ok = pose_all["status"] == 0
+        gn_flops = float(((pose_all["iters_first"] + pose_all["iters_ref"]) * (114.0 * pose_all["n_inliers_pt"] + 212.0 * pose_all["n_inliers_ls"]))[ok].sum()) / len(pose_hosts)
+
+        def tensor_roof(name, n_pairs, dirs, t_ms):
+            ops = n_pairs * 512.0 * dirs
+            return {"kernel": name, "bound": "tensor", "achieved": ops / (t_ms * 1e-3) / 1e12, "peak": int8_peak, "unit": "TOP/s (int8)",
+                    "frac": ops / (t_ms * 1e-3) / 1e12 / int8_peak, "kernel_ms": t_ms, "distances_per_launch": n_pairs,
+                    "distances_Tps": n_pairs * dirs / (t_ms * 1e-3) / 1e12,
+                    "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops_sustained (int8 dense rate = 2 x bf16)" if mp else "2 x fallback 1.59 PF"}
+
+        def int_roof(name, n_pairs, popc_pp, alu_pp, t_ms):
+            pk = min(popc_peak / popc_pp, alu_peak / alu_pp)
+            ach = n_pairs / (t_ms * 1e-3) / 1e12
+            return {"kernel": name, "bound": "alu", "achieved": ach, "peak": pk, "unit": "T distances/s", "frac": ach / pk, "kernel_ms": t_ms,
+                    "distances_per_launch": n_pairs,
+                    "peak_source": "min(measured popc rate / %g, measured lop3 rate / %g ALU ops per distance), micro-benchmarked live" % (popc_pp, alu_pp)}
+
+        by_kernel = [
+            tensor_roof("knn2_tc_kernel: stereo points, forward k=2 + reverse best", pairs[0], 2, stage[0]) if tc_on
+            else int_roof("knn2_sym_kernel<HAMMING,2>: stereo points", pairs[0], 5.0, 24.6, stage[0]),
+            int_roof("knn2_sym_kernel<HAMMING2,1>: stereo lines, both directions from one pass", pairs[1], 8.0, 35.0, stage[1]),
+            tensor_roof("f2f_hybrid_points_tc_kernel: radius + projection-gate search", pairs[2], 1, stage[3]) if tc_on
+            else int_roof("f2f_hybrid_points_kernel", pairs[2], 5.0, 21.0, stage[3]),
+            {"kernel": "linecut_kernel (+ stereo_uncertainty)", "bound": "fp64 latency", "kernel_ms": float(stage[6]),
+             "note": "sequential greedy search per pair; fp64 pipe ~27 % active, issue ~38 % (profiles/)"},
+            {"kernel": "pose_optimize_kernel (+ finalize)", "bound": "fp64 latency", "achieved": gn_flops / (stage[7] * 1e-3) / 1e12,
+             "peak": fp64_peak, "unit": "TFLOP/s (fp64)", "frac": gn_flops / (stage[7] * 1e-3) / 1e12 / fp64_peak, "kernel_ms": float(stage[7]),
+             "note": "algorithmic flops = GN iterations x (114 per inlier point + 212 per inlier line); one warp per pair, serial 6x6 solve per iteration"},
+        ]
+        roofline = dict(by_kernel[0])
+        alg_bytes = B * (2 * a.n_pt * 32 + 2 * a.n_pt * 16)
+        traffic = None   # dram__bytes_read+write per launch, from the committed ncu --set full capture of the same workload
         tj = os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")
-        if os.path.exists(tj) and dom == 0 and B == 8192 and a.n_pt == 300:
-            t = json.load(open(tj))["per_launch"].get("knn2_kernel<6, 2>@16384")
+        if os.path.exists(tj) and B == 8192 and a.n_pt == 300:
+            t = json.load(open(tj))["per_launch"].get("knn2_tc_kernel@8192" if tc_on else "knn2_sym_kernel<6, 2>@8192")
             if t:
                 traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
-        roofline = {"bound": "alu", "pipe": "INT POPC pipe (16 lanes/clk/SM) + INT ALU pipe; not HBM-, not tensor-bound",
-                    "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "T pairs/s (256-bit Hamming distances)",
-                    "frac": achieved / peak,
-                    "peak_source": "min(measured popc rate / %g popc per pair, measured lop3 rate / %g alu ops per pair), "
-                                   "both micro-benchmarked live in this run" % (POPC_PER_PAIR, ALU_PER_PAIR),
-                    "measured_pipe_peaks": {"popc_Tops": popc_peak, "alu_lop3_Tops": alu_peak},
-                    "popc_equivalent": {"achieved_Tpopc": 8.0 * achieved, "frac_of_popc_peak": 8.0 * achieved / popc_peak,
-                                        "note": "8 popc per pair is the naive algorithmic count; the kernel issues 5 (carry-save)"},
-                    "kernel_ms": k_ms[dom], "pairs_per_launch": pairs[dom], "traffic": traffic,
-                    "traffic_note": "bytes; DRAM read+write of one launch from profiles/r1_ncu_full_summary.md (same workload); "
-                                    "algorithmic bytes of the launch = %d" % (alg_bytes or 0),
-                    "hbm": {"achieved_GBps": (alg_bytes / (k_ms[dom] * 1e-3) / 1e9) if alg_bytes else None,
-                            "peak_GBps": hbm_peak, "note": "algorithmic bytes of this launch; shows the kernel is not HBM-bound"},
-                    "all_matching_kernels_Tpairs": sum(pairs) / (sum(k_ms) * 1e-3) / 1e12}
+        roofline.update({"traffic": traffic,
+                         "traffic_note": "bytes; DRAM read+write of one launch (profiles/r1_ncu_full_summary.md); algorithmic bytes = %d "
+                                         "(descriptors in, knn records out)" % alg_bytes,
+                         "hbm": {"achieved_GBps": alg_bytes / (stage[0] * 1e-3) / 1e9, "peak_GBps": hbm_peak,
+                                 "note": "algorithmic bytes of this launch: the kernel is not HBM-bound"},
+                         "why_this_kernel": "largest kernel of the matching path (north star); by single-kernel time linecut_kernel and "
+                                            "pose_optimize_kernel are larger, see roofline_by_kernel",
+                         "measured_pipe_peaks": {"popc_Tops": popc_peak, "alu_lop3_Tops": alu_peak, "fp64_TFLOPs": fp64_peak,
+                                                 "int8_tensor_TOPs": int8_peak}})
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "u8/int32 matching + f64 optimisation", "data": "synthetic", "config": workload_config(a),
+               "dtype": "u8 descriptors -> int8 tensor-core / int32 popcount matching (exact) + f64 optimisation", "data": "synthetic", "config": workload_config(a),
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                        "ms_per_step": e2e_ms / a.steps, "pipeline": "%d resident slots / streams: H2D of step k overlaps the kernels of earlier steps; results consumed %d steps later" % (NSLOT, LAG),
                        "timing": "host wall clock around K x (upload+run+download) + final sync, max over ranks",
                        "host_affinity_cpus": numa_cpus},
-               "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_by_kernel": by_kernel,
                "kernel_ms_per_step": dict(zip(["knn_stereo_pt", "knn_stereo_ln", "stereo_accept", "f2f_pt_search", "knn_f2f_ln",
                                                "f2f_accept", "uncertainty+linecut", "pose_gn", "step"], [float(x) for x in stage])),
                "peaks": {"popc_Tops": popc_peak, "alu_lop3_Tops": alu_peak, "fp64_TFLOPs": fp64_peak}}

@@ -165,7 +165,8 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
           }
         }
       };
-      if (cbeg < cend) {
+      // (a warp whose 32 rows all lie past nm has nothing to read: TMEM read bandwidth is what bounds this kernel)
+      if (cbeg < cend && m0 + (warp & 3) * 32 < nm) {
         TC_LD16(va, taddr + (uint32_t)cbeg);
         for (int c0 = cbeg; c0 < cend; c0 += 32) {
           TC_WAIT16(va);

@@ -25,7 +25,7 @@ with open(os.path.join(ROOT, "profiles", f"{tag}_launches_summary.md"), "w") as 
         f.write(f"| `{k}` | {n} | {t:.0f} | {100 * t / tot:.1f} % |\n")
     f.write(f"\nFirst 400 launches of the run: setup (stereo stage of the previous frames, 8 chunks), the pipe "
             f"micro-benchmarks (`popc_peak_kernel`, `lop3_peak_kernel`, `fp64_peak_kernel`), warm-up and timed steps "
-            f"(11 kernels per step).\n")
+            f"(12 kernels per step).\n")
 import shutil
 shutil.copy(launches, os.path.join(ROOT, "profiles", f"{tag}_launches.csv"))
 
@@ -37,7 +37,8 @@ keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
         "sm__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_fp64.sum",
-        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.sum",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.sum",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "smsp__thread_inst_executed_per_inst_executed.ratio",
         "sass__inst_executed_local_loads", "sass__inst_executed_local_stores"]
@@ -45,8 +46,8 @@ traffic = {}
 with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_summary.md"), "w") as f:
     f.write(f"# {tag}: `ncu --set full --clock-control none --import-source on` of the hot kernels\n\n"
             "Command: `python bench.py --steps 2 --warmup 1 --skip-cpu-baseline` (default workload: 8192 EuRoC-shaped pairs, "
-            "300 points + 100 lines per image, line cutting on), `-k regex:knn2_kernel|f2f_hybrid_points_kernel|linecut_kernel|"
-            "pose_optimize_kernel|stereo_accept_kernel -s 40 -c 8`. Numbers taken under the profiler are for diagnosis only; "
+            "300 points + 100 lines per image, line cutting on), `-k regex:knn2_tc_kernel|knn2_sym_kernel|f2f_hybrid_points_tc_kernel|"
+            "linecut_kernel|pose_optimize_kernel|stereo_accept_kernel -s 48 -c 8`. Numbers taken under the profiler are for diagnosis only; "
             "the timings in BENCH/README come from CUDA events without ncu.\n\n")
     seen = set()
     for r in rows[2:]:

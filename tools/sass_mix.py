@@ -9,7 +9,7 @@ print("# SASS mix of the Hamming matching kernels (cuobjdump -sass libgfpl.so, s
 print("Unrolled body = 4 train rows; counts below are per (query, train row) pair = per 256-bit distance.\n")
 for f in funcs:
     name = f.split("\n", 1)[0]
-    if not re.search(r"knn2_sym_kernelILi6ELi2E|knn2_sym_kernelILi7ELi1E|knn2_kernelILi6ELi2E|f2f_hybrid_points_kernel", name):
+    if not re.search(r"knn2_sym_kernelILi6ELi2E|knn2_sym_kernelILi7ELi1E|f2f_hybrid_points_kernelE", name):
         continue
     ops = re.findall(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", f, flags=re.M)
     c = collections.Counter(o.split(".")[0] if not o.startswith(("LDS", "UBLKCP", "SYNCS", "IMAD", "LOP3", "VIMNMX")) else o for o in ops)
