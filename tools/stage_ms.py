@@ -1,0 +1,25 @@
+"""Per-kernel CUDA-event times of the resident replay step, without bench.py's result checks (kernel experiments):
+   python tools/stage_ms.py [pairs] [steps]"""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gf-pl-slam_b200", "python"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+from gfpl import api, synth, _structs as S
+import orc
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+d = synth.make_pairs(B, n_pt=300, n_ln=100, seed=1000, pinned=True)
+ctx = api.Context(0, cam=d["cam"])
+prev = orc.stereo_match(d["cam"], ctx.cfg, d["prev_raw"]).repack()      # CPU: independent of the kernels under test
+rp = api.Replay(ctx, B, 300, 100, prev.cap_pt, prev.cap_ln)
+rp.upload(prev, d["state"], d["curr_raw"])
+flags = S.TRACK_LINECUT | S.TRACK_SEED_GIVEN
+acc = None
+for k in range(steps + 2):
+    rp.run(flags)
+    ms = np.array(rp.stage_ms())
+    if k >= 2:
+        acc = ms if acc is None else acc + ms
+names = ["knn_stereo_pt", "knn_stereo_ln", "stereo_accept", "f2f_pt_search", "knn_f2f_ln", "f2f_accept", "uncertainty+linecut", "pose_gn", "step"]
+print({n: round(float(v) / steps, 4) for n, v in zip(names, acc)}, "pairs", rp.pair_counts())
