@@ -46,7 +46,7 @@ def workload_config(a):
     return {"workload": "batched replay of independent EuRoC-shaped frame pairs (752x480, %d ORB pts + %d LSD lines "
                         "per image), good line cutting %s" % (a.n_pt, a.n_ln, "off" if a.no_linecut else "on"),
             "pairs_per_gpu": a.pairs, "points_per_image": a.n_pt, "lines_per_image": a.n_ln,
-            "prev_frame_layout": "stereo survivors packed to the largest count in the batch; e2e uploads slim records (gfpl_prev_frames)",
+            "prev_frame_layout": "stereo survivors packed to the largest count in the batch; e2e uploads the compact step input (gfpl_compact_input: 12 B key points, 24 B key lines, 16 B previous points, slim previous lines)",
             "stages": "stereo knn (points: tcgen05 int8, lines: popcount)+accept -> f2f hybrid search (tcgen05 int8)+accept -> stereo uncertainty+line cut -> pose GN(5)+MAD+GN(10)",
             "l2_policy": "inputs larger than L2 (>=700 MB read per step vs 126 MB L2)", "parallelism": "pairs sharded over ranks, NCCL all_gather of pose records only"}
 
@@ -224,7 +224,7 @@ def main():
     alu_peak = ctx.measure_alu_peak()
     # a previous frame holds only its stereo survivors: pack its rows with the tightest common stride
     prev = prev.repack(pinned=True)
-    prev_slim = S.PrevFramesNP(prev, pinned=True)   # e2e uploads the slim records (only the fields the step reads)
+    compact = S.CompactInputNP(d["curr_raw"], prev, pinned=True)   # e2e uploads the compact step input (gfpl_compact_input)
 
     rp = api.Replay(ctx, B, a.n_pt, a.n_ln, prev.cap_pt, prev.cap_ln)
     rp.upload(prev, d["state"], d["curr_raw"])
@@ -288,7 +288,7 @@ def main():
     def e2e_enqueue(k):
         nonlocal h2d, d2h
         c, r = slots[k % NSLOT]
-        r.upload_slim(prev_slim, d["state"], d["curr_raw"])
+        r.upload_compact(compact, d["state"])
         r.run(flags)
         r.download(pose_hosts[k % NSLOT])
         h2d, d2h = r.h2d_bytes(), r.d2h_bytes()

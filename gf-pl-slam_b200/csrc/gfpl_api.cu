@@ -456,6 +456,7 @@ struct gfpl_replay {
   DevTrackObs obs{};
   gfpl_frame_state* state = nullptr;
   gfpl_prev_frames slim{};   // staging for gfpl_replay_upload_slim (allocated on first use)
+  gfpl_compact_input compact{};  // staging for gfpl_replay_upload_compact (device copies of the compact records)
   gfpl_line_cut* cut = nullptr;
   gfpl_pose_result* pose = nullptr;
   StepWork w{};
@@ -920,6 +921,39 @@ int gfpl_replay_upload_slim(gfpl_replay* rp, const gfpl_prev_frames* prev, const
   H2D(rp->prev.pdesc, prev->pdesc, pp * 32); H2D(rp->prev.ldesc, prev->ldesc, pl * 32);
   CHECK(upload_raw_and_state(rp, state, raw));
   return launch_expand_prev(ctx, rp->slim, rp->prev);
+}
+
+int gfpl_replay_upload_compact(gfpl_replay* rp, const gfpl_compact_input* in, const gfpl_frame_state* state) {
+  if (!rp) return GFPL_E_INVALID;
+  gfpl_ctx* ctx = rp->ctx;
+  REQUIRE(ctx, in && state && in->B == rp->B);
+  REQUIRE(ctx, in->cap_pt == rp->cap_pt && in->cap_ln == rp->cap_ln);
+  REQUIRE(ctx, in->prev_cap_pt == rp->prev.cap_pt && in->prev_cap_ln == rp->prev.cap_ln);
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  const size_t B = rp->B, np = B * rp->cap_pt, nl = B * rp->cap_ln, pp = B * rp->prev.cap_pt, pl = B * rp->prev.cap_ln;
+  gfpl_compact_input& d = rp->compact;
+  if (!d.pt_l) {  // staging of the compact records; descriptors and counts go straight to their final buffers
+    d = *in;
+    d.pt_l = rp->alloc<gfpl_keypoint12>(np); d.pt_r = rp->alloc<gfpl_keypoint12>(np);
+    d.ln_l = rp->alloc<gfpl_keyline24>(nl); d.ln_r = rp->alloc<gfpl_keyline24>(nl);
+    d.prev_pt = rp->alloc<gfpl_prev_point16>(pp); d.prev_ln = rp->alloc<gfpl_prev_line>(pl);
+    REQUIRE_MEM(ctx, d.pt_l && d.pt_r && d.ln_l && d.ln_r && d.prev_pt && d.prev_ln);
+    d.n_pt_l = rp->raw.n_pt_l; d.n_pt_r = rp->raw.n_pt_r; d.n_ln_l = rp->raw.n_ln_l; d.n_ln_r = rp->raw.n_ln_r;
+    d.prev_n_pt = rp->prev.n_pt; d.prev_n_ln = rp->prev.n_ln;
+    d.pdesc_l = d.pdesc_r = d.ldesc_l = d.ldesc_r = d.prev_pdesc = d.prev_ldesc = nullptr;  // not staged
+  }
+  rp->h2d = 0;
+  H2D(rp->raw.n_pt_l, in->n_pt_l, B); H2D(rp->raw.n_pt_r, in->n_pt_r, B);
+  H2D(rp->raw.n_ln_l, in->n_ln_l, B); H2D(rp->raw.n_ln_r, in->n_ln_r, B);
+  H2D(rp->prev.n_pt, in->prev_n_pt, B); H2D(rp->prev.n_ln, in->prev_n_ln, B);
+  H2D(const_cast<gfpl_keypoint12*>(d.pt_l), in->pt_l, np); H2D(const_cast<gfpl_keypoint12*>(d.pt_r), in->pt_r, np);
+  H2D(const_cast<gfpl_keyline24*>(d.ln_l), in->ln_l, nl); H2D(const_cast<gfpl_keyline24*>(d.ln_r), in->ln_r, nl);
+  H2D(const_cast<gfpl_prev_point16*>(d.prev_pt), in->prev_pt, pp); H2D(const_cast<gfpl_prev_line*>(d.prev_ln), in->prev_ln, pl);
+  H2D(rp->raw.pdesc_l, in->pdesc_l, np * 32); H2D(rp->raw.pdesc_r, in->pdesc_r, np * 32);
+  H2D(rp->raw.ldesc_l, in->ldesc_l, nl * 32); H2D(rp->raw.ldesc_r, in->ldesc_r, nl * 32);
+  H2D(rp->prev.pdesc, in->prev_pdesc, pp * 32); H2D(rp->prev.ldesc, in->prev_ldesc, pl * 32);
+  H2D(rp->state, state, B);
+  return launch_expand_compact(ctx, d, rp->raw, rp->prev);
 }
 
 int gfpl_replay_run(gfpl_replay* rp, int32_t flags) {

@@ -96,6 +96,8 @@ int launch_stereo_accept(gfpl_ctx* ctx, const DevRawFrames& raw, int variant, Kn
 int launch_stereo_orbslam_points(gfpl_ctx* ctx, const DevRawFrames& raw, const gfpl_pyramid& dpyr, DevStereoFrames out);
 int launch_stereo_uncertainty(gfpl_ctx* ctx, const DevStereoFrames& fr, gfpl_line_cov* out);
 int launch_expand_prev(gfpl_ctx* ctx, const gfpl_prev_frames& slim_dev, DevStereoFrames fr);
+// compact step input (device staging copies) -> raw key points / key lines and previous-frame feature records
+int launch_expand_compact(gfpl_ctx* ctx, const gfpl_compact_input& c, DevRawFrames raw, DevStereoFrames prev);
 
 // f2f: fused radius + projection-gate search (hybrid points), knn-candidate variant, and accept loops
 int launch_f2f_hybrid_points(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr,

@@ -325,6 +325,64 @@ int launch_expand_prev(gfpl_ctx* ctx, const gfpl_prev_frames& slim, DevStereoFra
   return GFPL_OK;
 }
 
+// compact step input -> the records the kernels read.  blockIdx.y = pair, blockIdx.z selects the record type.
+__global__ void __launch_bounds__(128) expand_compact_kernel(gfpl_compact_input c, DevRawFrames raw, DevStereoFrames prev,
+                                                             gfpl_camera cam, gfpl_config cfg) {
+  const int p = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.z == 0) {  // key points, left and right
+    if (i < c.cap_pt) {
+      const size_t o = (size_t)p * c.cap_pt + i;
+      const gfpl_keypoint12 a = c.pt_l[o], b = c.pt_r[o];
+      const_cast<gfpl_keypoint*>(raw.pt_l)[o] = gfpl_keypoint{a.x, a.y, a.octave, -1};
+      const_cast<gfpl_keypoint*>(raw.pt_r)[o] = gfpl_keypoint{b.x, b.y, b.octave, -1};
+    }
+  } else if (blockIdx.z == 1) {  // key lines
+    if (i < c.cap_ln) {
+      const size_t o = (size_t)p * c.cap_ln + i;
+      const gfpl_keyline24 a = c.ln_l[o], b = c.ln_r[o];
+      const_cast<gfpl_keyline*>(raw.ln_l)[o] = gfpl_keyline{a.startPointX, a.startPointY, a.endPointX, a.endPointY, a.angle, a.octave, 0.f, 0.f};
+      const_cast<gfpl_keyline*>(raw.ln_r)[o] = gfpl_keyline{b.startPointX, b.startPointY, b.endPointX, b.endPointY, b.angle, b.octave, 0.f, 0.f};
+    }
+  } else if (blockIdx.z == 2) {  // previous stereo points: P and sigma2 by the expressions of the stereo stage
+    if (i < prev.n_pt[p]) {
+      const gfpl_prev_point16 s = c.prev_pt[(size_t)p * c.prev_cap_pt + i];
+      gfpl_point_feature f{};
+      f.pl[0] = s.x; f.pl[1] = s.y;
+      f.disp = s.disp;
+      back_projection(cam, f.pl[0], f.pl[1], (double)s.disp, f.P);
+      f.level = s.level;
+      f.sigma2 = level_sigma2(s.level, cfg.orb_scale_factor);
+      f.idx = i; f.src_l = f.src_r = -1;
+      prev.pt[(size_t)p * prev.cap_pt + i] = f;
+    }
+  } else {  // previous stereo lines (same slim record as gfpl_prev_frames)
+    if (i < prev.n_ln[p]) {
+      const gfpl_prev_line s = c.prev_ln[(size_t)p * c.prev_cap_ln + i];
+      gfpl_line_feature f{};
+#pragma unroll
+      for (int k = 0; k < 3; k++) { f.sP[k] = s.sP[k]; f.eP[k] = s.eP[k]; }
+      f.spl[0] = s.spl[0]; f.spl[1] = s.spl[1]; f.epl[0] = s.epl[0]; f.epl[1] = s.epl[1];
+      f.sdisp = s.sdisp; f.edisp = s.edisp;
+      f.le[0] = s.le0;
+      f.sigma2 = s.sigma2;
+      f.idx = -1; f.src_l = f.src_r = -1;
+      prev.ln[(size_t)p * prev.cap_ln + i] = f;
+    }
+  }
+}
+
+int launch_expand_compact(gfpl_ctx* ctx, const gfpl_compact_input& c, DevRawFrames raw, DevStereoFrames prev) {
+  if (c.B <= 0) return GFPL_OK;
+  int cap = c.cap_pt > c.cap_ln ? c.cap_pt : c.cap_ln;
+  cap = cap > c.prev_cap_pt ? cap : c.prev_cap_pt;
+  cap = cap > c.prev_cap_ln ? cap : c.prev_cap_ln;
+  dim3 grid((cap + 127) / 128, c.B, 4);
+  expand_compact_kernel<<<grid, 128, 0, ctx->stream>>>(c, raw, prev, ctx->cam, ctx->cfg);
+  GFPL_LAUNCH_OK(ctx);
+  return GFPL_OK;
+}
+
 int launch_stereo_uncertainty(gfpl_ctx* ctx, const DevStereoFrames& fr, gfpl_line_cov* out) {
   if (fr.B <= 0 || fr.cap_ln <= 0) return GFPL_OK;
   dim3 grid((fr.cap_ln + 127) / 128, fr.B);

@@ -297,6 +297,60 @@ class PrevFramesNP:
                           ptr(self.pdesc), ptr(self.ln), ptr(self.ldesc))
 
 
+keypoint12_dt = np.dtype([("x", "f4"), ("y", "f4"), ("octave", "i4")], align=True)
+keyline24_dt = np.dtype([("startPointX", "f4"), ("startPointY", "f4"), ("endPointX", "f4"), ("endPointY", "f4"),
+                         ("angle", "f4"), ("octave", "i4")], align=True)
+prev_point16_dt = np.dtype([("x", "f4"), ("y", "f4"), ("disp", "f4"), ("level", "i4")], align=True)
+assert keypoint12_dt.itemsize == 12 and keyline24_dt.itemsize == 24 and prev_point16_dt.itemsize == 16
+
+
+class CompactInput(C.Structure):
+    _fields_ = [("B", C.c_int32), ("cap_pt", C.c_int32), ("cap_ln", C.c_int32), ("prev_cap_pt", C.c_int32),
+                ("prev_cap_ln", C.c_int32)] + [(k, _vp) for k in (
+                    "n_pt_l", "n_pt_r", "n_ln_l", "n_ln_r", "pt_l", "pt_r", "pdesc_l", "pdesc_r", "ln_l", "ln_r", "ldesc_l",
+                    "ldesc_r", "prev_n_pt", "prev_n_ln", "prev_pt", "prev_pdesc", "prev_ln", "prev_ldesc")]
+
+
+class CompactInputNP:
+    """gfpl_compact_input of one step: raw current frames + previous stereo frames in their smallest exact form"""
+    _keys = ("n_pt_l", "n_pt_r", "n_ln_l", "n_ln_r", "pt_l", "pt_r", "pdesc_l", "pdesc_r", "ln_l", "ln_r", "ldesc_l", "ldesc_r",
+             "prev_n_pt", "prev_n_ln", "prev_pt", "prev_pdesc", "prev_ln", "prev_ldesc")
+
+    def __init__(self, raw, prev_full, pinned=False):
+        B = raw.B
+        self.B, self.cap_pt, self.cap_ln = B, raw.cap_pt, raw.cap_ln
+        self.prev_cap_pt, self.prev_cap_ln = prev_full.cap_pt, prev_full.cap_ln
+        a = lambda s, d: _alloc(s, d, pinned)
+        for k in ("n_pt_l", "n_pt_r", "n_ln_l", "n_ln_r"):
+            setattr(self, k, a(B, "i4")); getattr(self, k)[:] = getattr(raw, k)
+        for side in ("l", "r"):
+            kp = a((B, raw.cap_pt), keypoint12_dt); src = getattr(raw, "pt_" + side)
+            for f in ("x", "y", "octave"):
+                kp[f] = src[f]
+            setattr(self, "pt_" + side, kp)
+            kl = a((B, raw.cap_ln), keyline24_dt); src = getattr(raw, "ln_" + side)
+            for f in ("startPointX", "startPointY", "endPointX", "endPointY", "angle", "octave"):
+                kl[f] = src[f]
+            setattr(self, "ln_" + side, kl)
+            for k in ("pdesc_", "ldesc_"):
+                d = a(getattr(raw, k + side).shape, "u1"); d[:] = getattr(raw, k + side); setattr(self, k + side, d)
+        slim = PrevFramesNP(prev_full, pinned)
+        self.prev_n_pt, self.prev_n_ln, self.prev_pdesc, self.prev_ln, self.prev_ldesc = slim.n_pt, slim.n_ln, slim.pdesc, slim.ln, slim.ldesc
+        pp = a((B, prev_full.cap_pt), prev_point16_dt)
+        pl, disp = prev_full.pt["pl"], prev_full.pt["disp"]
+        pp["x"], pp["y"], pp["disp"], pp["level"] = pl[..., 0], pl[..., 1], disp, prev_full.pt["level"]
+        # the compact form is exact only when pl / disp are float values (output of the stereo stage)
+        assert np.array_equal(pp["x"].astype("f8"), pl[..., 0]) and np.array_equal(pp["disp"].astype("f8"), disp)
+        self.prev_pt = pp
+
+    def view(self):
+        return CompactInput(self.B, self.cap_pt, self.cap_ln, self.prev_cap_pt, self.prev_cap_ln,
+                            *[ptr(getattr(self, k)) for k in self._keys])
+
+    def nbytes(self):
+        return sum(getattr(self, k).nbytes for k in self._keys)
+
+
 class TrackObsNP:
     """matched_pt / matched_ls of B frame pairs as observation lists + inlier masks."""
     _keys = ("n_pt", "n_ln", "pt", "pt_inlier", "ln", "ln_inlier")

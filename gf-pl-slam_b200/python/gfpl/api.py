@@ -313,6 +313,10 @@ class Replay:
         pv, rv = prev_slim.view(), raw.view()
         self.ctx._check(lib().gfpl_replay_upload_slim(self._h, C.byref(pv), _vp(state), C.byref(rv)))
 
+    def upload_compact(self, compact, state):
+        cv = compact.view()
+        self.ctx._check(lib().gfpl_replay_upload_compact(self._h, C.byref(cv), _vp(state)))
+
     def run(self, flags):
         self.ctx._check(lib().gfpl_replay_run(self._h, flags))
 

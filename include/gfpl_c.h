@@ -221,6 +221,32 @@ typedef struct gfpl_prev_frames {
   const uint8_t* ldesc;          /* [B][cap_ln][32] */
 } gfpl_prev_frames;
 
+/* Compact host-side input of one tracking step (streaming replay): the same information as gfpl_raw_frames +
+ * gfpl_prev_frames in fewer bytes — the host-to-device copy is what bounds the end-to-end rate.
+ *  - key point: pt.x, pt.y, octave (12 B; class_id is not read by the path),
+ *  - key line: start / end point, angle, octave (24 B; lineLength, response are consumed by the detector-side
+ *    truncation of stereoFrame.cpp:1093-1102 only),
+ *  - previous stereo point: pl.x, pl.y, disp as the floats the stereo stage produced them from, and its level (16 B):
+ *    P = backProjection(pl, disp) (pinholeStereoCamera.cpp:133-141) and sigma2 (stereoFeatures.cpp:41-48) are
+ *    recomputed on the device by the same expressions, bit for bit.  Only valid for stereo points whose pl / disp are
+ *    float values (extractStereoFeatures_* output); otherwise use gfpl_prev_frames. */
+typedef struct gfpl_keypoint12 { float x, y; int32_t octave; } gfpl_keypoint12;
+typedef struct gfpl_keyline24 { float startPointX, startPointY, endPointX, endPointY, angle; int32_t octave; } gfpl_keyline24;
+typedef struct gfpl_prev_point16 { float x, y, disp; int32_t level; } gfpl_prev_point16;
+typedef struct gfpl_compact_input {
+  int32_t B, cap_pt, cap_ln, prev_cap_pt, prev_cap_ln;
+  const int32_t *n_pt_l, *n_pt_r, *n_ln_l, *n_ln_r;   /* [B] */
+  const gfpl_keypoint12 *pt_l, *pt_r;                  /* [B][cap_pt] */
+  const uint8_t *pdesc_l, *pdesc_r;                    /* [B][cap_pt][32] */
+  const gfpl_keyline24 *ln_l, *ln_r;                   /* [B][cap_ln] */
+  const uint8_t *ldesc_l, *ldesc_r;                    /* [B][cap_ln][32] */
+  const int32_t *prev_n_pt, *prev_n_ln;                /* [B] */
+  const gfpl_prev_point16* prev_pt;                    /* [B][prev_cap_pt] */
+  const uint8_t* prev_pdesc;                           /* [B][prev_cap_pt][32] */
+  const gfpl_prev_line* prev_ln;                       /* [B][prev_cap_ln] */
+  const uint8_t* prev_ldesc;                           /* [B][prev_cap_ln][32] */
+} gfpl_compact_input;
+
 /* prev_frame->{Tfw,DT,DT_cov,Tfw_cov,time_stamp} (stereoFrame.h:212-221) + curr time stamp */
 typedef struct gfpl_frame_state {
   double Tfw[16];
@@ -510,6 +536,8 @@ int gfpl_replay_upload(gfpl_replay* rp, const gfpl_stereo_frames* prev, const gf
  * expanded to full feature records on the device */
 int gfpl_replay_upload_slim(gfpl_replay* rp, const gfpl_prev_frames* prev, const gfpl_frame_state* state,
                             const gfpl_raw_frames* curr_raw);
+/* as gfpl_replay_upload_slim, from the compact records above (expanded on the device) */
+int gfpl_replay_upload_compact(gfpl_replay* rp, const gfpl_compact_input* in, const gfpl_frame_state* state /*[B]*/);
 /* launch the whole step on the resident inputs (asynchronous; no host synchronisation inside) */
 int gfpl_replay_run(gfpl_replay* rp, int32_t flags);
 /* async D2H of the per-pair pose records (pose: [B]); obs/cut/curr optional (NULL to skip) */

@@ -408,6 +408,19 @@ def test_replay_with_packed_previous_frames(ctx, orc):
     rp.download(pose2)
     ctx.sync()
     assert pose2.tobytes() == pg.tobytes()
+    # compact step input (gfpl_replay_upload_compact: 12 B key points, 24 B key lines, 16 B previous points whose P and
+    # sigma2 are recomputed on the device): same poses, in fewer host-to-device bytes
+    slim_bytes = rp.h2d_bytes()
+    comp = S.CompactInputNP(d["curr_raw"], packed)
+    rp.upload_compact(comp, d["state"])
+    assert rp.h2d_bytes() < 0.9 * slim_bytes
+    rp.run(flags)
+    pose3 = np.zeros(32, S.pose_result_dt)
+    curr3 = S.StereoFramesNP(32, d["curr_raw"].cap_pt, d["curr_raw"].cap_ln)
+    rp.download(pose3, curr=curr3)
+    ctx.sync()
+    assert pose3.tobytes() == pg.tobytes()
+    _cmp_stereo(curr3, orc.stereo_match(d["cam"], ctx.cfg, d["curr_raw"]))
 
 
 def test_linecut_decisions_exact_at_scale(ctx, orc):
