@@ -356,16 +356,21 @@ __global__ void __launch_bounds__(128) expand_compact_kernel(gfpl_compact_input 
       f.idx = i; f.src_l = f.src_r = -1;
       prev.pt[(size_t)p * prev.cap_pt + i] = f;
     }
-  } else {  // previous stereo lines (same slim record as gfpl_prev_frames)
+  } else {  // previous stereo lines: sP / eP, le[0] and sigma2 by the expressions of the stereo accept loop (:924-927, :1002)
     if (i < prev.n_ln[p]) {
-      const gfpl_prev_line s = c.prev_ln[(size_t)p * c.prev_cap_ln + i];
+      const gfpl_prev_line40 s = c.prev_ln[(size_t)p * c.prev_cap_ln + i];
       gfpl_line_feature f{};
-#pragma unroll
-      for (int k = 0; k < 3; k++) { f.sP[k] = s.sP[k]; f.eP[k] = s.eP[k]; }
-      f.spl[0] = s.spl[0]; f.spl[1] = s.spl[1]; f.epl[0] = s.epl[0]; f.epl[1] = s.epl[1];
+      const double sp_l[3] = {s.spl[0], s.spl[1], 1.0};
+      const double ep_l[3] = {s.epl[0], s.epl[1], 1.0};
+      const double l0 = sp_l[1] * ep_l[2] - sp_l[2] * ep_l[1], l1 = sp_l[2] * ep_l[0] - sp_l[0] * ep_l[2];
+      const double nrm = sqrt(l0 * l0 + l1 * l1);
+      f.le[0] = l0 / nrm;
+      f.spl[0] = sp_l[0]; f.spl[1] = sp_l[1]; f.epl[0] = ep_l[0]; f.epl[1] = ep_l[1];
       f.sdisp = s.sdisp; f.edisp = s.edisp;
-      f.le[0] = s.le0;
-      f.sigma2 = s.sigma2;
+      back_projection(cam, sp_l[0], sp_l[1], s.sdisp, f.sP);
+      back_projection(cam, ep_l[0], ep_l[1], s.edisp, f.eP);
+      f.level = s.level;
+      f.sigma2 = level_sigma2(s.level, cfg.lsd_scale);
       f.idx = -1; f.src_l = f.src_r = -1;
       prev.ln[(size_t)p * prev.cap_ln + i] = f;
     }

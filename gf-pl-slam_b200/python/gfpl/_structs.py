@@ -301,7 +301,10 @@ keypoint12_dt = np.dtype([("x", "f4"), ("y", "f4"), ("octave", "i4")], align=Tru
 keyline24_dt = np.dtype([("startPointX", "f4"), ("startPointY", "f4"), ("endPointX", "f4"), ("endPointY", "f4"),
                          ("angle", "f4"), ("octave", "i4")], align=True)
 prev_point16_dt = np.dtype([("x", "f4"), ("y", "f4"), ("disp", "f4"), ("level", "i4")], align=True)
+prev_line40_dt = np.dtype([("spl", "f4", 2), ("epl", "f4", 2), ("sdisp", "f8"), ("edisp", "f8"), ("level", "i4"), ("_pad", "i4")],
+                          align=True)
 assert keypoint12_dt.itemsize == 12 and keyline24_dt.itemsize == 24 and prev_point16_dt.itemsize == 16
+assert prev_line40_dt.itemsize == 40
 
 
 class CompactInput(C.Structure):
@@ -334,8 +337,16 @@ class CompactInputNP:
             setattr(self, "ln_" + side, kl)
             for k in ("pdesc_", "ldesc_"):
                 d = a(getattr(raw, k + side).shape, "u1"); d[:] = getattr(raw, k + side); setattr(self, k + side, d)
-        slim = PrevFramesNP(prev_full, pinned)
-        self.prev_n_pt, self.prev_n_ln, self.prev_pdesc, self.prev_ln, self.prev_ldesc = slim.n_pt, slim.n_ln, slim.pdesc, slim.ln, slim.ldesc
+        self.prev_n_pt, self.prev_n_ln = a(B, "i4"), a(B, "i4")
+        self.prev_n_pt[:], self.prev_n_ln[:] = prev_full.n_pt, prev_full.n_ln
+        self.prev_pdesc, self.prev_ldesc = a(prev_full.pdesc.shape, "u1"), a(prev_full.ldesc.shape, "u1")
+        self.prev_pdesc[:], self.prev_ldesc[:] = prev_full.pdesc, prev_full.ldesc
+        ln = a((B, prev_full.cap_ln), prev_line40_dt)
+        for k in ("spl", "epl", "sdisp", "edisp", "level"):
+            ln[k] = prev_full.ln[k]
+        # exact only for uncut stereo-stage lines: float end points, sP / eP = backProjection(end point, disparity)
+        assert np.array_equal(ln["spl"].astype("f8"), prev_full.ln["spl"]) and np.array_equal(ln["epl"].astype("f8"), prev_full.ln["epl"])
+        self.prev_ln = ln
         pp = a((B, prev_full.cap_pt), prev_point16_dt)
         pl, disp = prev_full.pt["pl"], prev_full.pt["disp"]
         pp["x"], pp["y"], pp["disp"], pp["level"] = pl[..., 0], pl[..., 1], disp, prev_full.pt["level"]

@@ -233,6 +233,11 @@ typedef struct gfpl_prev_frames {
 typedef struct gfpl_keypoint12 { float x, y; int32_t octave; } gfpl_keypoint12;
 typedef struct gfpl_keyline24 { float startPointX, startPointY, endPointX, endPointY, angle; int32_t octave; } gfpl_keyline24;
 typedef struct gfpl_prev_point16 { float x, y, disp; int32_t level; } gfpl_prev_point16;
+/*  - previous stereo line: the left end points as the floats of the key line, the two end-point disparities and the
+ *    level (40 B): sP / eP = backProjection(end point, disparity), le[0] (normalised line equation, stereoFrame.cpp:
+ *    924-927) and sigma2 are recomputed on the device by the stereo stage's expressions.  Only valid for stereo lines
+ *    that were not cut (updateEndPointByRatio edits sP / eP / spl / epl); otherwise use gfpl_prev_frames. */
+typedef struct gfpl_prev_line40 { float spl[2], epl[2]; double sdisp, edisp; int32_t level, _pad; } gfpl_prev_line40;
 typedef struct gfpl_compact_input {
   int32_t B, cap_pt, cap_ln, prev_cap_pt, prev_cap_ln;
   const int32_t *n_pt_l, *n_pt_r, *n_ln_l, *n_ln_r;   /* [B] */
@@ -243,7 +248,7 @@ typedef struct gfpl_compact_input {
   const int32_t *prev_n_pt, *prev_n_ln;                /* [B] */
   const gfpl_prev_point16* prev_pt;                    /* [B][prev_cap_pt] */
   const uint8_t* prev_pdesc;                           /* [B][prev_cap_pt][32] */
-  const gfpl_prev_line* prev_ln;                       /* [B][prev_cap_ln] */
+  const gfpl_prev_line40* prev_ln;                     /* [B][prev_cap_ln] */
   const uint8_t* prev_ldesc;                           /* [B][prev_cap_ln][32] */
 } gfpl_compact_input;
 
