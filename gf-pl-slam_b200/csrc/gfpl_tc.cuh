@@ -90,9 +90,23 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
   const int row = tid & (TC_M - 1);     // m-row inside the tile = TMEM lane
   const int half = tid >> 7;            // which half of a pass's columns this thread reduces
   const int nnp = (nn + 15) & ~15;
-  for (int r = tid; r < nnp; r += TC_THREADS) {
-    const uint4* src = reinterpret_cast<const uint4*>(n_base + (size_t)min(r, nn - 1) * 32);
-    expand_row(sN, r, __ldg(src), __ldg(src + 1), r >= nn, lut);
+  {  // both n-rows of this thread are fetched before either is expanded
+    uint4 lo[2], hi[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int r = tid + u * TC_THREADS;
+      const uint4* src = reinterpret_cast<const uint4*>(n_base + (size_t)min(r, nn - 1) * 32);
+      if (r < nnp) { lo[u] = __ldg(src); hi[u] = __ldg(src + 1); }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int r = tid + u * TC_THREADS;
+      if (r < nnp) expand_row(sN, r, lo[u], hi[u], r >= nn, lut);
+    }
+    for (int r = tid + 2 * TC_THREADS; r < nnp; r += TC_THREADS) {
+      const uint4* src = reinterpret_cast<const uint4*>(n_base + (size_t)min(r, nn - 1) * 32);
+      expand_row(sN, r, __ldg(src), __ldg(src + 1), r >= nn, lut);
+    }
   }
   const uint32_t sM_addr = smem_u32(sM), sN_addr = smem_u32(sN);
   const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
@@ -121,11 +135,15 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
                  : "memory");
   };
 
+  // this thread's half descriptor row of the NEXT tile is fetched before the current tile is reduced (global latency)
+  uint4 next_row = __ldg(reinterpret_cast<const uint4*>(m_base + (size_t)min(row, nm - 1) * 32) + half);
   for (int m0 = 0; m0 < nm; m0 += TC_M) {
     {
       const int mi = m0 + row;
-      const uint4* src = reinterpret_cast<const uint4*>(m_base + (size_t)min(mi, nm - 1) * 32);
-      expand_half_row(sM, row, half, __ldg(src + half), mi >= nm, lut);
+      const uint4 cur_row = next_row;
+      if (m0 + TC_M < nm)
+        next_row = __ldg(reinterpret_cast<const uint4*>(m_base + (size_t)min(mi + TC_M, nm - 1) * 32) + half);
+      expand_half_row(sM, row, half, cur_row, mi >= nm, lut);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the MMA
     __syncthreads();

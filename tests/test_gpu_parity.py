@@ -699,3 +699,15 @@ def test_knn2_mutual_both_directions(ctx, orc, norm, tie):
                 assert np.array_equal(bi[p, :nt[p]], ri[:, 0]) and np.array_equal(bd[p, :nt[p]], rd[:, 0]), (cap_q, p)
             else:
                 assert (idx[p, :nq[p]] == -1).all() and (bi[p, :nt[p]] == -1).all()
+
+
+def test_integer_pipe_paths_with_tensor_path_disabled():
+    """GFPL_NO_TC=1 routes point matching to the integer-pipe kernels (knn2_sym_kernel, f2f_hybrid_points_kernel):
+    the same parity tests must pass there (the switch is read once per process, hence the subprocess)"""
+    import subprocess, sys
+    env = dict(os.environ, GFPL_NO_TC="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k",
+                        "test_stereo_match or test_f2f_match or test_knn2_mutual or test_track_whole or test_kf_match or test_map_match"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "deselected" in r.stdout
