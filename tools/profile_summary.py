@@ -24,8 +24,8 @@ with open(os.path.join(ROOT, "profiles", f"{tag}_launches_summary.md"), "w") as 
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"| `{k}` | {n} | {t:.0f} | {100 * t / tot:.1f} % |\n")
     f.write(f"\nFirst 400 launches of the run: setup (stereo stage of the previous frames, 8 chunks), the pipe "
-            f"micro-benchmarks (`popc_peak_kernel`, `lop3_peak_kernel`, `fp64_peak_kernel`), warm-up and timed steps "
-            f"(12 kernels per step).\n")
+            f"micro-benchmarks (`popc_peak_kernel`, `lop3_peak_kernel`, `fp64_peak_kernel`), warm-up, timed steps "
+            f"(11 kernels per step), the streaming e2e steps (`expand_compact_kernel` + the same 11) and the LBA side note (`lba_*`).\n")
 import shutil
 shutil.copy(launches, os.path.join(ROOT, "profiles", f"{tag}_launches.csv"))
 
