@@ -169,8 +169,9 @@ lba_eliminate_kernel(int n_lm, const int32_t* __restrict__ obs_off, const int32_
   }
 }
 
-// dense LDL^T (no pivoting: S is SPD after damping) + solve, one CTA, in place in global memory.  n = 6 Nkf (tens).
-__global__ void __launch_bounds__(256) lba_dense_solve_kernel(int n, double* __restrict__ S, double* __restrict__ x) {
+// dense LDL^T (no pivoting: S is SPD after damping) + solve by one CTA.  n = 6 Nkf is a few tens: the matrix is staged in
+// shared memory when it fits (n <= 96), else factorised in place in global memory.
+__device__ __forceinline__ void ldlt_solve_cta(int n, double* __restrict__ S, double* __restrict__ x) {
   const int t = threadIdx.x;
   for (int k = 0; k < n; k++) {
     const double d = S[(size_t)k * n + k];
@@ -198,6 +199,23 @@ __global__ void __launch_bounds__(256) lba_dense_solve_kernel(int n, double* __r
     __syncthreads();
     for (int i = t; i < k; i += 256) x[i] -= S[(size_t)k * n + i] * xk;
     __syncthreads();
+  }
+}
+
+constexpr int LBA_SOLVE_SMEM_N = 96;
+
+__global__ void __launch_bounds__(256) lba_dense_solve_kernel(int n, double* __restrict__ S, double* __restrict__ x) {
+  extern __shared__ double s_mat[];  // [n*n + n] when n <= LBA_SOLVE_SMEM_N
+  if (n <= LBA_SOLVE_SMEM_N) {
+    double* sx = s_mat + (size_t)n * n;
+    for (int e = threadIdx.x; e < n * n; e += 256) s_mat[e] = S[e];
+    for (int e = threadIdx.x; e < n; e += 256) sx[e] = x[e];
+    __syncthreads();
+    ldlt_solve_cta(n, s_mat, sx);
+    __syncthreads();
+    for (int e = threadIdx.x; e < n; e += 256) x[e] = sx[e];
+  } else {
+    ldlt_solve_cta(n, S, x);
   }
 }
 
@@ -242,7 +260,10 @@ int launch_lba_solve(gfpl_ctx* ctx, const gfpl_lba_problem& pb, const gfpl_lba_b
     GFPL_LAUNCH_OK(ctx);
   }
   if (nk > 0) {
-    lba_dense_solve_kernel<<<1, 256, 0, ctx->stream>>>(nk, w.S, DX);
+    const size_t smem = nk <= LBA_SOLVE_SMEM_N ? ((size_t)nk * nk + nk) * sizeof(double) : 0;
+    if (smem > 48 * 1024)
+      GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(lba_dense_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lba_dense_solve_kernel<<<1, 256, smem, ctx->stream>>>(nk, w.S, DX);
     GFPL_LAUNCH_OK(ctx);
   }
   if (pb.Npt > 0) {
