@@ -46,7 +46,7 @@ def workload_config(a):
     return {"workload": "batched replay of independent EuRoC-shaped frame pairs (752x480, %d ORB pts + %d LSD lines "
                         "per image), good line cutting %s" % (a.n_pt, a.n_ln, "off" if a.no_linecut else "on"),
             "pairs_per_gpu": a.pairs, "points_per_image": a.n_pt, "lines_per_image": a.n_ln,
-            "prev_frame_layout": "stereo survivors packed to the largest count in the batch; e2e uploads the compact step input (gfpl_compact_input: 12 B key points, 24 B key lines, 16 B previous points, slim previous lines)",
+            "prev_frame_layout": "stereo survivors packed to the largest count in the batch; e2e uploads the compact step input (gfpl_compact_input: 8+1 B key points, 20+1 B key lines, 12+1 B previous points, 32+1 B previous lines, descriptors)",
             "stages": "stereo knn (points: tcgen05 int8, lines: popcount)+accept -> f2f hybrid search (tcgen05 int8)+accept -> stereo uncertainty+line cut -> pose GN(5)+MAD+GN(10)",
             "l2_policy": "inputs larger than L2 (>=700 MB read per step vs 126 MB L2)", "parallelism": "pairs sharded over ranks, NCCL all_gather of pose records only"}
 

@@ -934,10 +934,14 @@ int gfpl_replay_upload_compact(gfpl_replay* rp, const gfpl_compact_input* in, co
   gfpl_compact_input& d = rp->compact;
   if (!d.pt_l) {  // staging of the compact records; descriptors and counts go straight to their final buffers
     d = *in;
-    d.pt_l = rp->alloc<gfpl_keypoint12>(np); d.pt_r = rp->alloc<gfpl_keypoint12>(np);
-    d.ln_l = rp->alloc<gfpl_keyline24>(nl); d.ln_r = rp->alloc<gfpl_keyline24>(nl);
-    d.prev_pt = rp->alloc<gfpl_prev_point16>(pp); d.prev_ln = rp->alloc<gfpl_prev_line40>(pl);
-    REQUIRE_MEM(ctx, d.pt_l && d.pt_r && d.ln_l && d.ln_r && d.prev_pt && d.prev_ln);
+    d.pt_l = rp->alloc<gfpl_keypoint8>(np); d.pt_r = rp->alloc<gfpl_keypoint8>(np);
+    d.pt_oct_l = rp->alloc<uint8_t>(np); d.pt_oct_r = rp->alloc<uint8_t>(np);
+    d.ln_l = rp->alloc<gfpl_keyline20>(nl); d.ln_r = rp->alloc<gfpl_keyline20>(nl);
+    d.ln_oct_l = rp->alloc<uint8_t>(nl); d.ln_oct_r = rp->alloc<uint8_t>(nl);
+    d.prev_pt = rp->alloc<gfpl_prev_point12>(pp); d.prev_pt_level = rp->alloc<uint8_t>(pp);
+    d.prev_ln = rp->alloc<gfpl_prev_line32>(pl); d.prev_ln_level = rp->alloc<uint8_t>(pl);
+    REQUIRE_MEM(ctx, d.pt_l && d.pt_r && d.pt_oct_l && d.pt_oct_r && d.ln_l && d.ln_r && d.ln_oct_l && d.ln_oct_r && d.prev_pt &&
+                         d.prev_pt_level && d.prev_ln && d.prev_ln_level);
     d.n_pt_l = rp->raw.n_pt_l; d.n_pt_r = rp->raw.n_pt_r; d.n_ln_l = rp->raw.n_ln_l; d.n_ln_r = rp->raw.n_ln_r;
     d.prev_n_pt = rp->prev.n_pt; d.prev_n_ln = rp->prev.n_ln;
     d.pdesc_l = d.pdesc_r = d.ldesc_l = d.ldesc_r = d.prev_pdesc = d.prev_ldesc = nullptr;  // not staged
@@ -946,9 +950,12 @@ int gfpl_replay_upload_compact(gfpl_replay* rp, const gfpl_compact_input* in, co
   H2D(rp->raw.n_pt_l, in->n_pt_l, B); H2D(rp->raw.n_pt_r, in->n_pt_r, B);
   H2D(rp->raw.n_ln_l, in->n_ln_l, B); H2D(rp->raw.n_ln_r, in->n_ln_r, B);
   H2D(rp->prev.n_pt, in->prev_n_pt, B); H2D(rp->prev.n_ln, in->prev_n_ln, B);
-  H2D(const_cast<gfpl_keypoint12*>(d.pt_l), in->pt_l, np); H2D(const_cast<gfpl_keypoint12*>(d.pt_r), in->pt_r, np);
-  H2D(const_cast<gfpl_keyline24*>(d.ln_l), in->ln_l, nl); H2D(const_cast<gfpl_keyline24*>(d.ln_r), in->ln_r, nl);
-  H2D(const_cast<gfpl_prev_point16*>(d.prev_pt), in->prev_pt, pp); H2D(const_cast<gfpl_prev_line40*>(d.prev_ln), in->prev_ln, pl);
+  H2D(const_cast<gfpl_keypoint8*>(d.pt_l), in->pt_l, np); H2D(const_cast<gfpl_keypoint8*>(d.pt_r), in->pt_r, np);
+  H2D(const_cast<uint8_t*>(d.pt_oct_l), in->pt_oct_l, np); H2D(const_cast<uint8_t*>(d.pt_oct_r), in->pt_oct_r, np);
+  H2D(const_cast<gfpl_keyline20*>(d.ln_l), in->ln_l, nl); H2D(const_cast<gfpl_keyline20*>(d.ln_r), in->ln_r, nl);
+  H2D(const_cast<uint8_t*>(d.ln_oct_l), in->ln_oct_l, nl); H2D(const_cast<uint8_t*>(d.ln_oct_r), in->ln_oct_r, nl);
+  H2D(const_cast<gfpl_prev_point12*>(d.prev_pt), in->prev_pt, pp); H2D(const_cast<uint8_t*>(d.prev_pt_level), in->prev_pt_level, pp);
+  H2D(const_cast<gfpl_prev_line32*>(d.prev_ln), in->prev_ln, pl); H2D(const_cast<uint8_t*>(d.prev_ln_level), in->prev_ln_level, pl);
   H2D(rp->raw.pdesc_l, in->pdesc_l, np * 32); H2D(rp->raw.pdesc_r, in->pdesc_r, np * 32);
   H2D(rp->raw.ldesc_l, in->ldesc_l, nl * 32); H2D(rp->raw.ldesc_r, in->ldesc_r, nl * 32);
   H2D(rp->prev.pdesc, in->prev_pdesc, pp * 32); H2D(rp->prev.ldesc, in->prev_ldesc, pl * 32);

@@ -333,32 +333,36 @@ __global__ void __launch_bounds__(128) expand_compact_kernel(gfpl_compact_input 
   if (blockIdx.z == 0) {  // key points, left and right
     if (i < c.cap_pt) {
       const size_t o = (size_t)p * c.cap_pt + i;
-      const gfpl_keypoint12 a = c.pt_l[o], b = c.pt_r[o];
-      const_cast<gfpl_keypoint*>(raw.pt_l)[o] = gfpl_keypoint{a.x, a.y, a.octave, -1};
-      const_cast<gfpl_keypoint*>(raw.pt_r)[o] = gfpl_keypoint{b.x, b.y, b.octave, -1};
+      const gfpl_keypoint8 a = c.pt_l[o], b = c.pt_r[o];
+      const_cast<gfpl_keypoint*>(raw.pt_l)[o] = gfpl_keypoint{a.x, a.y, (int32_t)c.pt_oct_l[o], -1};
+      const_cast<gfpl_keypoint*>(raw.pt_r)[o] = gfpl_keypoint{b.x, b.y, (int32_t)c.pt_oct_r[o], -1};
     }
   } else if (blockIdx.z == 1) {  // key lines
     if (i < c.cap_ln) {
       const size_t o = (size_t)p * c.cap_ln + i;
-      const gfpl_keyline24 a = c.ln_l[o], b = c.ln_r[o];
-      const_cast<gfpl_keyline*>(raw.ln_l)[o] = gfpl_keyline{a.startPointX, a.startPointY, a.endPointX, a.endPointY, a.angle, a.octave, 0.f, 0.f};
-      const_cast<gfpl_keyline*>(raw.ln_r)[o] = gfpl_keyline{b.startPointX, b.startPointY, b.endPointX, b.endPointY, b.angle, b.octave, 0.f, 0.f};
+      const gfpl_keyline20 a = c.ln_l[o], b = c.ln_r[o];
+      const_cast<gfpl_keyline*>(raw.ln_l)[o] = gfpl_keyline{a.startPointX, a.startPointY, a.endPointX, a.endPointY, a.angle, (int32_t)c.ln_oct_l[o], 0.f, 0.f};
+      const_cast<gfpl_keyline*>(raw.ln_r)[o] = gfpl_keyline{b.startPointX, b.startPointY, b.endPointX, b.endPointY, b.angle, (int32_t)c.ln_oct_r[o], 0.f, 0.f};
     }
   } else if (blockIdx.z == 2) {  // previous stereo points: P and sigma2 by the expressions of the stereo stage
     if (i < prev.n_pt[p]) {
-      const gfpl_prev_point16 s = c.prev_pt[(size_t)p * c.prev_cap_pt + i];
+      const size_t o = (size_t)p * c.prev_cap_pt + i;
+      const gfpl_prev_point12 s = c.prev_pt[o];
+      const int level = c.prev_pt_level[o];
       gfpl_point_feature f{};
       f.pl[0] = s.x; f.pl[1] = s.y;
       f.disp = s.disp;
       back_projection(cam, f.pl[0], f.pl[1], (double)s.disp, f.P);
-      f.level = s.level;
-      f.sigma2 = level_sigma2(s.level, cfg.orb_scale_factor);
+      f.level = level;
+      f.sigma2 = level_sigma2(level, cfg.orb_scale_factor);
       f.idx = i; f.src_l = f.src_r = -1;
       prev.pt[(size_t)p * prev.cap_pt + i] = f;
     }
   } else {  // previous stereo lines: sP / eP, le[0] and sigma2 by the expressions of the stereo accept loop (:924-927, :1002)
     if (i < prev.n_ln[p]) {
-      const gfpl_prev_line40 s = c.prev_ln[(size_t)p * c.prev_cap_ln + i];
+      const size_t o = (size_t)p * c.prev_cap_ln + i;
+      const gfpl_prev_line32 s = c.prev_ln[o];
+      const int level = c.prev_ln_level[o];
       gfpl_line_feature f{};
       const double sp_l[3] = {s.spl[0], s.spl[1], 1.0};
       const double ep_l[3] = {s.epl[0], s.epl[1], 1.0};
@@ -369,8 +373,8 @@ __global__ void __launch_bounds__(128) expand_compact_kernel(gfpl_compact_input 
       f.sdisp = s.sdisp; f.edisp = s.edisp;
       back_projection(cam, sp_l[0], sp_l[1], s.sdisp, f.sP);
       back_projection(cam, ep_l[0], ep_l[1], s.edisp, f.eP);
-      f.level = s.level;
-      f.sigma2 = level_sigma2(s.level, cfg.lsd_scale);
+      f.level = level;
+      f.sigma2 = level_sigma2(level, cfg.lsd_scale);
       f.idx = -1; f.src_l = f.src_r = -1;
       prev.ln[(size_t)p * prev.cap_ln + i] = f;
     }

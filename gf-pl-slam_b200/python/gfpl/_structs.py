@@ -297,62 +297,66 @@ class PrevFramesNP:
                           ptr(self.pdesc), ptr(self.ln), ptr(self.ldesc))
 
 
-keypoint12_dt = np.dtype([("x", "f4"), ("y", "f4"), ("octave", "i4")], align=True)
-keyline24_dt = np.dtype([("startPointX", "f4"), ("startPointY", "f4"), ("endPointX", "f4"), ("endPointY", "f4"),
-                         ("angle", "f4"), ("octave", "i4")], align=True)
-prev_point16_dt = np.dtype([("x", "f4"), ("y", "f4"), ("disp", "f4"), ("level", "i4")], align=True)
-prev_line40_dt = np.dtype([("spl", "f4", 2), ("epl", "f4", 2), ("sdisp", "f8"), ("edisp", "f8"), ("level", "i4"), ("_pad", "i4")],
-                          align=True)
-assert keypoint12_dt.itemsize == 12 and keyline24_dt.itemsize == 24 and prev_point16_dt.itemsize == 16
-assert prev_line40_dt.itemsize == 40
+keypoint8_dt = np.dtype([("x", "f4"), ("y", "f4")], align=True)
+keyline20_dt = np.dtype([("startPointX", "f4"), ("startPointY", "f4"), ("endPointX", "f4"), ("endPointY", "f4"),
+                         ("angle", "f4")], align=True)
+prev_point12_dt = np.dtype([("x", "f4"), ("y", "f4"), ("disp", "f4")], align=True)
+prev_line32_dt = np.dtype([("spl", "f4", 2), ("epl", "f4", 2), ("sdisp", "f8"), ("edisp", "f8")], align=True)
+assert keypoint8_dt.itemsize == 8 and keyline20_dt.itemsize == 20 and prev_point12_dt.itemsize == 12
+assert prev_line32_dt.itemsize == 32
+
+_COMPACT_KEYS = ("n_pt_l", "n_pt_r", "n_ln_l", "n_ln_r", "pt_l", "pt_r", "pt_oct_l", "pt_oct_r", "pdesc_l", "pdesc_r", "ln_l", "ln_r",
+                 "ln_oct_l", "ln_oct_r", "ldesc_l", "ldesc_r", "prev_n_pt", "prev_n_ln", "prev_pt", "prev_pt_level", "prev_pdesc",
+                 "prev_ln", "prev_ln_level", "prev_ldesc")
 
 
 class CompactInput(C.Structure):
     _fields_ = [("B", C.c_int32), ("cap_pt", C.c_int32), ("cap_ln", C.c_int32), ("prev_cap_pt", C.c_int32),
-                ("prev_cap_ln", C.c_int32)] + [(k, _vp) for k in (
-                    "n_pt_l", "n_pt_r", "n_ln_l", "n_ln_r", "pt_l", "pt_r", "pdesc_l", "pdesc_r", "ln_l", "ln_r", "ldesc_l",
-                    "ldesc_r", "prev_n_pt", "prev_n_ln", "prev_pt", "prev_pdesc", "prev_ln", "prev_ldesc")]
+                ("prev_cap_ln", C.c_int32)] + [(k, _vp) for k in _COMPACT_KEYS]
 
 
 class CompactInputNP:
     """gfpl_compact_input of one step: raw current frames + previous stereo frames in their smallest exact form"""
-    _keys = ("n_pt_l", "n_pt_r", "n_ln_l", "n_ln_r", "pt_l", "pt_r", "pdesc_l", "pdesc_r", "ln_l", "ln_r", "ldesc_l", "ldesc_r",
-             "prev_n_pt", "prev_n_ln", "prev_pt", "prev_pdesc", "prev_ln", "prev_ldesc")
+    _keys = _COMPACT_KEYS
 
     def __init__(self, raw, prev_full, pinned=False):
         B = raw.B
         self.B, self.cap_pt, self.cap_ln = B, raw.cap_pt, raw.cap_ln
         self.prev_cap_pt, self.prev_cap_ln = prev_full.cap_pt, prev_full.cap_ln
         a = lambda s, d: _alloc(s, d, pinned)
+
+        def u8(x):
+            assert x.min() >= 0 and x.max() <= 255
+            out = a(x.shape, "u1"); out[:] = x
+            return out
         for k in ("n_pt_l", "n_pt_r", "n_ln_l", "n_ln_r"):
             setattr(self, k, a(B, "i4")); getattr(self, k)[:] = getattr(raw, k)
         for side in ("l", "r"):
-            kp = a((B, raw.cap_pt), keypoint12_dt); src = getattr(raw, "pt_" + side)
-            for f in ("x", "y", "octave"):
-                kp[f] = src[f]
-            setattr(self, "pt_" + side, kp)
-            kl = a((B, raw.cap_ln), keyline24_dt); src = getattr(raw, "ln_" + side)
-            for f in ("startPointX", "startPointY", "endPointX", "endPointY", "angle", "octave"):
+            kp = a((B, raw.cap_pt), keypoint8_dt); src = getattr(raw, "pt_" + side)
+            kp["x"], kp["y"] = src["x"], src["y"]
+            setattr(self, "pt_" + side, kp); setattr(self, "pt_oct_" + side, u8(src["octave"]))
+            kl = a((B, raw.cap_ln), keyline20_dt); src = getattr(raw, "ln_" + side)
+            for f in ("startPointX", "startPointY", "endPointX", "endPointY", "angle"):
                 kl[f] = src[f]
-            setattr(self, "ln_" + side, kl)
+            setattr(self, "ln_" + side, kl); setattr(self, "ln_oct_" + side, u8(src["octave"]))
             for k in ("pdesc_", "ldesc_"):
                 d = a(getattr(raw, k + side).shape, "u1"); d[:] = getattr(raw, k + side); setattr(self, k + side, d)
         self.prev_n_pt, self.prev_n_ln = a(B, "i4"), a(B, "i4")
         self.prev_n_pt[:], self.prev_n_ln[:] = prev_full.n_pt, prev_full.n_ln
         self.prev_pdesc, self.prev_ldesc = a(prev_full.pdesc.shape, "u1"), a(prev_full.ldesc.shape, "u1")
         self.prev_pdesc[:], self.prev_ldesc[:] = prev_full.pdesc, prev_full.ldesc
-        ln = a((B, prev_full.cap_ln), prev_line40_dt)
-        for k in ("spl", "epl", "sdisp", "edisp", "level"):
+        ln = a((B, prev_full.cap_ln), prev_line32_dt)
+        for k in ("spl", "epl", "sdisp", "edisp"):
             ln[k] = prev_full.ln[k]
         # exact only for uncut stereo-stage lines: float end points, sP / eP = backProjection(end point, disparity)
         assert np.array_equal(ln["spl"].astype("f8"), prev_full.ln["spl"]) and np.array_equal(ln["epl"].astype("f8"), prev_full.ln["epl"])
-        self.prev_ln = ln
-        pp = a((B, prev_full.cap_pt), prev_point16_dt)
+        self.prev_ln, self.prev_ln_level = ln, u8(np.where(np.arange(prev_full.cap_ln)[None] < prev_full.n_ln[:, None], prev_full.ln["level"], 0))
+        pp = a((B, prev_full.cap_pt), prev_point12_dt)
         pl, disp = prev_full.pt["pl"], prev_full.pt["disp"]
-        pp["x"], pp["y"], pp["disp"], pp["level"] = pl[..., 0], pl[..., 1], disp, prev_full.pt["level"]
+        pp["x"], pp["y"], pp["disp"] = pl[..., 0], pl[..., 1], disp
         # the compact form is exact only when pl / disp are float values (output of the stereo stage)
         assert np.array_equal(pp["x"].astype("f8"), pl[..., 0]) and np.array_equal(pp["disp"].astype("f8"), disp)
-        self.prev_pt = pp
+        self.prev_pt, self.prev_pt_level = pp, u8(np.where(np.arange(prev_full.cap_pt)[None] < prev_full.n_pt[:, None], prev_full.pt["level"], 0))
 
     def view(self):
         return CompactInput(self.B, self.cap_pt, self.cap_ln, self.prev_cap_pt, self.prev_cap_ln,

@@ -222,33 +222,38 @@ typedef struct gfpl_prev_frames {
 } gfpl_prev_frames;
 
 /* Compact host-side input of one tracking step (streaming replay): the same information as gfpl_raw_frames +
- * gfpl_prev_frames in fewer bytes — the host-to-device copy is what bounds the end-to-end rate.
- *  - key point: pt.x, pt.y, octave (12 B; class_id is not read by the path),
- *  - key line: start / end point, angle, octave (24 B; lineLength, response are consumed by the detector-side
- *    truncation of stereoFrame.cpp:1093-1102 only),
- *  - previous stereo point: pl.x, pl.y, disp as the floats the stereo stage produced them from, and its level (16 B):
+ * gfpl_prev_frames in fewer bytes — the host-to-device copy is what bounds the end-to-end rate.  Pyramid levels
+ * (octave / level, 0..255) travel as separate byte arrays.
+ *  - key point: pt.x, pt.y (8 B) + octave (1 B); class_id is not read by the path,
+ *  - key line: start / end point, angle (20 B) + octave (1 B); lineLength, response are consumed by the detector-side
+ *    truncation of stereoFrame.cpp:1093-1102 only,
+ *  - previous stereo point: pl.x, pl.y, disp as the floats the stereo stage produced them from (12 B) + level (1 B):
  *    P = backProjection(pl, disp) (pinholeStereoCamera.cpp:133-141) and sigma2 (stereoFeatures.cpp:41-48) are
  *    recomputed on the device by the same expressions, bit for bit.  Only valid for stereo points whose pl / disp are
- *    float values (extractStereoFeatures_* output); otherwise use gfpl_prev_frames. */
-typedef struct gfpl_keypoint12 { float x, y; int32_t octave; } gfpl_keypoint12;
-typedef struct gfpl_keyline24 { float startPointX, startPointY, endPointX, endPointY, angle; int32_t octave; } gfpl_keyline24;
-typedef struct gfpl_prev_point16 { float x, y, disp; int32_t level; } gfpl_prev_point16;
-/*  - previous stereo line: the left end points as the floats of the key line, the two end-point disparities and the
- *    level (40 B): sP / eP = backProjection(end point, disparity), le[0] (normalised line equation, stereoFrame.cpp:
+ *    float values (extractStereoFeatures_* output); otherwise use gfpl_prev_frames,
+ *  - previous stereo line: the left end points as the floats of the key line and the two end-point disparities (32 B)
+ *    + level (1 B): sP / eP = backProjection(end point, disparity), le[0] (normalised line equation, stereoFrame.cpp:
  *    924-927) and sigma2 are recomputed on the device by the stereo stage's expressions.  Only valid for stereo lines
  *    that were not cut (updateEndPointByRatio edits sP / eP / spl / epl); otherwise use gfpl_prev_frames. */
-typedef struct gfpl_prev_line40 { float spl[2], epl[2]; double sdisp, edisp; int32_t level, _pad; } gfpl_prev_line40;
+typedef struct gfpl_keypoint8 { float x, y; } gfpl_keypoint8;
+typedef struct gfpl_keyline20 { float startPointX, startPointY, endPointX, endPointY, angle; } gfpl_keyline20;
+typedef struct gfpl_prev_point12 { float x, y, disp; } gfpl_prev_point12;
+typedef struct gfpl_prev_line32 { float spl[2], epl[2]; double sdisp, edisp; } gfpl_prev_line32;
 typedef struct gfpl_compact_input {
   int32_t B, cap_pt, cap_ln, prev_cap_pt, prev_cap_ln;
   const int32_t *n_pt_l, *n_pt_r, *n_ln_l, *n_ln_r;   /* [B] */
-  const gfpl_keypoint12 *pt_l, *pt_r;                  /* [B][cap_pt] */
+  const gfpl_keypoint8 *pt_l, *pt_r;                   /* [B][cap_pt] */
+  const uint8_t *pt_oct_l, *pt_oct_r;                  /* [B][cap_pt] */
   const uint8_t *pdesc_l, *pdesc_r;                    /* [B][cap_pt][32] */
-  const gfpl_keyline24 *ln_l, *ln_r;                   /* [B][cap_ln] */
+  const gfpl_keyline20 *ln_l, *ln_r;                   /* [B][cap_ln] */
+  const uint8_t *ln_oct_l, *ln_oct_r;                  /* [B][cap_ln] */
   const uint8_t *ldesc_l, *ldesc_r;                    /* [B][cap_ln][32] */
   const int32_t *prev_n_pt, *prev_n_ln;                /* [B] */
-  const gfpl_prev_point16* prev_pt;                    /* [B][prev_cap_pt] */
+  const gfpl_prev_point12* prev_pt;                    /* [B][prev_cap_pt] */
+  const uint8_t* prev_pt_level;                        /* [B][prev_cap_pt] */
   const uint8_t* prev_pdesc;                           /* [B][prev_cap_pt][32] */
-  const gfpl_prev_line40* prev_ln;                     /* [B][prev_cap_ln] */
+  const gfpl_prev_line32* prev_ln;                     /* [B][prev_cap_ln] */
+  const uint8_t* prev_ln_level;                        /* [B][prev_cap_ln] */
   const uint8_t* prev_ldesc;                           /* [B][prev_cap_ln][32] */
 } gfpl_compact_input;
 

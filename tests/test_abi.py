@@ -42,8 +42,8 @@ def test_struct_layouts_match_c(tmp_path):
                "gfpl_track_obs": C.sizeof(S.TrackObs), "gfpl_lba_problem": C.sizeof(S.LbaProblem),
                "gfpl_lba_blocks": C.sizeof(S.LbaBlocks), "gfpl_local_map": C.sizeof(S.LocalMap),
                "gfpl_map_matches": C.sizeof(S.MapMatches), "gfpl_map_pair": S.map_pair_dt.itemsize, "gfpl_pyramid": C.sizeof(S.Pyramid), "gfpl_compact_input": C.sizeof(S.CompactInput),
-               "gfpl_keypoint12": S.keypoint12_dt.itemsize, "gfpl_keyline24": S.keyline24_dt.itemsize,
-               "gfpl_prev_point16": S.prev_point16_dt.itemsize, "gfpl_prev_line40": S.prev_line40_dt.itemsize}
+               "gfpl_keypoint8": S.keypoint8_dt.itemsize, "gfpl_keyline20": S.keyline20_dt.itemsize,
+               "gfpl_prev_point12": S.prev_point12_dt.itemsize, "gfpl_prev_line32": S.prev_line32_dt.itemsize}
     prog = '#include <stdio.h>\n#include "gfpl_c.h"\nint main(){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in structs) + \
         'printf("off_sigma2 %zu\\n", offsetof(gfpl_point_feature, sigma2));' \
