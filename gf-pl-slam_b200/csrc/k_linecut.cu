@@ -181,18 +181,27 @@ __device__ __forceinline__ void half_fast(const gfpl_camera& cam, const gfpl_con
   u[3] = -kf * fma(gy, xl + yl, gz2 * ly);
   u[4] = kf * fma(gx, xl + yl, gz2 * lx);
   u[5] = kf * gz * fma(gx, ly, -(gy * lx));
-  double g = 0.0;
+  double g = 0.0, w[6];
+  const double2* S2 = reinterpret_cast<const double2*>(Sinv);  // rows of 3 x 128 bit
 #pragma unroll
   for (int i = 0; i < 6; i++) {
-    double sacc = 0.0;
-#pragma unroll
-    for (int k = 0; k < 6; k++) sacc = fma(Sinv[i * 6 + k], u[k], sacc);
-    out[HF_U + i] = u[i];
-    out[HF_W + i] = sacc;
+    const double2 r0 = S2[i * 3], r1 = S2[i * 3 + 1], r2 = S2[i * 3 + 2];
+    double sacc = fma(r0.x, u[0], 0.0);
+    sacc = fma(r0.y, u[1], sacc);
+    sacc = fma(r1.x, u[2], sacc);
+    sacc = fma(r1.y, u[3], sacc);
+    sacc = fma(r2.x, u[4], sacc);
+    sacc = fma(r2.y, u[5], sacc);
+    w[i] = sacc;
     g = fma(u[i], sacc, g);
   }
-  out[HF_A] = a;
-  out[HF_G] = g;
+  double2* o2 = reinterpret_cast<double2*>(out);  // [u0..u5 | w0..w5 | a g]
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    o2[HF_U / 2 + i] = make_double2(u[2 * i], u[2 * i + 1]);
+    o2[HF_W / 2 + i] = make_double2(w[2 * i], w[2 * i + 1]);
+  }
+  o2[HF_A / 2] = make_double2(a, g);
 }
 
 // S^-1 (full 6x6 row-major) of the lower-packed SPD matrix S (21) by Cholesky; false when S is not safely positive definite
@@ -245,28 +254,66 @@ __device__ __forceinline__ bool spd_inverse6(const double* S, double* Sinv) {
 
 // per-group (one frame pair) state kept in shared memory: every lane of the group reads the same addresses
 // (broadcast), which frees ~120 registers per thread and lets 16 warps / SM hide the fp64 dependency chains.
-struct GroupState {
-  double DT[12];        // R | t of DT_inv
-  double L[LD_SIZE];    // current line
-  double sum[21];       // invCov_sum, lower triangle
-  double sum0[21];      // invCov_sum before the current line's information is removed (exact metric of cut {0,0})
-  double Sinv[36];      // inverse of (invCov_sum - info(line)) for the screening path, row-major
-  double half[6][HF_SIZE];  // the six published halves of the current round
+struct __align__(16) GroupState {
+  double Sinv[36];          // inverse of (invCov_sum - info(line)) for the screening path, row-major (16-byte aligned rows)
+  double half[6][HF_SIZE];  // the six published halves of the current round (112-byte rows)
+  double DT[12];            // R | t of DT_inv
+  double L[LD_SIZE];        // current line
   double J[CUT_GROUP][6];   // point Jacobians of the current chunk of the invCov_sum pass
+  double sum[21];           // invCov_sum, lower triangle
+  double sum0[21];          // invCov_sum before the current line's information is removed (exact metric of cut {0,0})
 };
+static_assert(sizeof(GroupState) % 16 == 0 && HF_SIZE % 2 == 0, "128-bit shared-memory accesses below");
 
 #ifndef CUT_MIN_BLOCKS
 #define CUT_MIN_BLOCKS 4
 #endif
 
-// once per line, out of line (57 live doubles): every lane computes S^-1 redundantly, the lanes publish it together
-__device__ __noinline__ bool spd_inverse6_publish(GroupState* G, int j) {
-  double Sinv[36];
-  const bool ok = spd_inverse6(G->sum, Sinv);
+// once per line, out of line: every lane factorises S (Cholesky, redundantly), lane j < 6 of the group then solves for
+// column j of S^-1 only and publishes it
+__device__ __noinline__ bool spd_inverse6_publish(GroupState* G, int j, unsigned gmask) {
+  double L[21];
 #pragma unroll
-  for (int e = 0; e < 36; e++)
-    if ((e & (CUT_GROUP - 1)) == j) G->Sinv[e] = Sinv[e];
-  return ok;
+  for (int i = 0; i < 21; i++) L[i] = G->sum[i];
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    double x = L[tri(k, k)];
+#pragma unroll
+    for (int jx = 0; jx < k; jx++) x = fma(-L[tri(k, jx)], L[tri(k, jx)], x);
+    ok = ok && (x > 0.0);
+    const double r = rsqrt(x);
+    L[tri(k, k)] = r;  // store 1/L_kk
+#pragma unroll
+    for (int i = k + 1; i < 6; i++) {
+      double sv = L[tri(i, k)];
+#pragma unroll
+      for (int jx = 0; jx < k; jx++) sv = fma(-L[tri(i, jx)], L[tri(k, jx)], sv);
+      L[tri(i, k)] = sv * r;
+    }
+  }
+  const int c = j < 6 ? j : 5;  // lanes 6, 7 repeat column 5 (not stored)
+  double y[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {  // L y = e_c
+    double sv = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < i; k++) sv = fma(-L[tri(i, k)], y[k], sv);
+    y[i] = (i < c) ? 0.0 : sv * L[tri(i, i)];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {  // L^T x = y
+    double sv = y[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; k++) sv = fma(-L[tri(k, i)], y[k], sv);
+    y[i] = sv * L[tri(i, i)];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    ok = ok && (fabs(y[i]) < 1e300);
+    if (j < 6) G->Sinv[i * 6 + c] = y[i];
+  }
+  return (__ballot_sync(gmask, ok) & gmask) == gmask;
 }
 
 // initial information of one line at cut {0,0} (:1638-1649), out of line
@@ -443,7 +490,7 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
     __syncwarp(gmask);
     // screening set-up: S^-1 once per line (every lane computes it redundantly, lanes publish it together)
     bool fast_ok = cfg.max_vol_line_cut != 0;
-    if (fast_ok) fast_ok = spd_inverse6_publish(&G, j);
+    if (fast_ok) fast_ok = spd_inverse6_publish(&G, j, gmask);
     __syncwarp(gmask);
     double cur0 = 0.0, cur1 = 0.0;
     double metric_last = 0.0;      // the reference's metric of the current cut; evaluated lazily (exact rounds only)
@@ -470,13 +517,18 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
         __syncwarp(gmask);
         // determinant factor of (si, ei): (1 + a u'S^-1u)(1 + b v'S^-1v) - a b (u'S^-1v)^2  (monotone in the metric)
         auto factor = [&](int si, int ei) {
-          const double* hs = G.half[si];
-          const double* he = G.half[ei];
+          const double2* hs = reinterpret_cast<const double2*>(G.half[si]);
+          const double2* he = reinterpret_cast<const double2*>(G.half[ei]);
           double guv = 0.0;
 #pragma unroll
-          for (int i = 0; i < 6; i++) guv = fma(hs[HF_U + i], he[HF_W + i], guv);
-          const double a = hs[HF_A], b = he[HF_A];
-          return fma(-(a * b) * guv, guv, fma(a, hs[HF_G], 1.0) * fma(b, he[HF_G], 1.0));
+          for (int i = 0; i < 3; i++) {
+            const double2 uu = hs[HF_U / 2 + i], ww = he[HF_W / 2 + i];
+            guv = fma(uu.x, ww.x, guv);
+            guv = fma(uu.y, ww.y, guv);
+          }
+          const double2 ags = hs[HF_A / 2], age = he[HF_A / 2];   // (a, g) of each half
+          const double a = ags.x, b = age.x;
+          return fma(-(a * b) * guv, guv, fma(a, ags.y, 1.0) * fma(b, age.y, 1.0));
         };
         const int si = (nb0 < 0.0) ? 0 : ((nb0 > 0.0) ? 2 : 1);
         const int ei = 3 + ((nb1 < 0.0) ? 0 : ((nb1 > 0.0) ? 2 : 1));
