@@ -18,7 +18,10 @@
 
 namespace gfpl {
 
-constexpr int CUT_THREADS = 128;
+#ifndef CUT_THREADS_N
+#define CUT_THREADS_N 64
+#endif
+constexpr int CUT_THREADS = CUT_THREADS_N;    // 64: 8 pairs per CTA, 8192 pairs = 1024 CTAs = one wave of 8 CTAs / SM
 constexpr int CUT_GROUP = 8;
 
 // StereoFrame::getJacob3D_2D rows 0-1 (stereoFrame.cpp:1394-1413)
@@ -57,10 +60,11 @@ struct LineInfo {  // what getPoseInfoOnLine needs to form info = [Js Je] * inv(
 // line data layout used by the evaluation: sP[3] eP[3] le[2] covS[9] covE[9] = 26 doubles
 constexpr int LD_SP = 0, LD_EP = 3, LD_LE = 6, LD_CS = 8, LD_CE = 17, LD_SIZE = 26;
 
-// getPoseInfoOnLine up to the two Jacobian columns and the 2x2 inverse.  `DT` = [R (9) | t (3)], `L` = line data;
-// both may live in shared memory (pass 3: one copy per 8-lane group) or be read straight from global (pass 1).
-__device__ __forceinline__ void pose_info_on_line(const gfpl_camera& cam, const gfpl_config& cfg, const double* DT,
-                                                  const double* L, double c0, double c1, LineInfo& out) {
+// One endpoint of getPoseInfoOnLine (:1347-1400): A / SA = the endpoint (and its covariance) that moves towards B / SB by
+// the cut ratio c.  Writes the Jacobian column J[6] and returns the residual variance.  `DT` = [R (9) | t (3)].
+__device__ __forceinline__ double pose_info_endpoint(const gfpl_camera& cam, const gfpl_config& cfg, const double* DT,
+                                                     const double* A, const double* Bp, const double* SA, const double* SB,
+                                                     const double* le, double c, double* J) {
   double R[9], T4[16];
 #pragma unroll
   for (int i = 0; i < 9; i++) R[i] = DT[i];
@@ -68,39 +72,36 @@ __device__ __forceinline__ void pose_info_on_line(const gfpl_camera& cam, const 
   for (int i = 0; i < 3; i++) {
     T4[i * 4 + 0] = R[i * 3 + 0]; T4[i * 4 + 1] = R[i * 3 + 1]; T4[i * 4 + 2] = R[i * 3 + 2]; T4[i * 4 + 3] = DT[9 + i];
   }
-  const double le[2] = {L[LD_LE], L[LD_LE + 1]};
-  double cov_sR, cov_eR;
-  {
-    double P[3], cur[3], cv[9], Jp[6];
-    const double a0 = (1 - c0) * (1 - c0), b0 = c0 * c0;
+  double P[3], cur[3], cv[9], Jp[6];
+  const double a0 = (1 - c) * (1 - c), b0 = c * c;
 #pragma unroll
-    for (int k = 0; k < 3; k++) P[k] = (1 - c0) * L[LD_SP + k] + c0 * L[LD_EP + k];
+  for (int k = 0; k < 3; k++) P[k] = (1 - c) * A[k] + c * Bp[k];
 #pragma unroll
-    for (int k = 0; k < 9; k++) cv[k] = a0 * L[LD_CS + k] + b0 * L[LD_CE + k];
-    se3_apply(T4, P, cur);
-    jacob3d_2d(cam, cur[0], cur[1], cur[2], Jp);
-    cov_sR = residual_var(Jp, R, cv, le);
-    jac6(cam.fx / fmax(cfg.homog_th, cur[2] * cur[2]), cur[0], cur[1], cur[2], le[0], le[1], out.Js);
-  }
-  {
-    double P[3], cur[3], cv[9], Jp[6];
-    const double a1 = (1 - c1) * (1 - c1), b1 = c1 * c1;
-#pragma unroll
-    for (int k = 0; k < 3; k++) P[k] = (1 - c1) * L[LD_EP + k] + c1 * L[LD_SP + k];
-#pragma unroll
-    for (int k = 0; k < 9; k++) cv[k] = a1 * L[LD_CE + k] + b1 * L[LD_CS + k];
-    se3_apply(T4, P, cur);
-    jacob3d_2d(cam, cur[0], cur[1], cur[2], Jp);
-    cov_eR = residual_var(Jp, R, cv, le);
-    jac6(cam.fx / fmax(cfg.homog_th, cur[2] * cur[2]), cur[0], cur[1], cur[2], le[0], le[1], out.Je);
-  }
-  // 2x2 inverse of diag(cov_sR, cov_eR) as adjugate * (1/det)
+  for (int k = 0; k < 9; k++) cv[k] = a0 * SA[k] + b0 * SB[k];
+  se3_apply(T4, P, cur);
+  jacob3d_2d(cam, cur[0], cur[1], cur[2], Jp);
+  const double var = residual_var(Jp, R, cv, le);
+  jac6(cam.fx / fmax(cfg.homog_th, cur[2] * cur[2]), cur[0], cur[1], cur[2], le[0], le[1], J);
+  return var;
+}
+
+// the 2x2 inverse of diag(cov_sR, cov_eR) as adjugate * (1/det), as the reference's Matrix2d::inverse() forms it
+__device__ __forceinline__ void pose_info_weights(double cov_sR, double cov_eR, LineInfo& out) {
   const double det = cov_sR * cov_eR - 0.0 * 0.0;
   const double invdet = 1.0 / det;
   out.i00 = cov_eR * invdet;
   out.i11 = cov_sR * invdet;
   out.i01 = -0.0 * invdet;
   out.i10 = -0.0 * invdet;
+}
+
+// getPoseInfoOnLine up to the two Jacobian columns and the 2x2 inverse.  `L` = line data; DT and L may live in shared
+// memory (pass 3: one copy per 8-lane group) or be read straight from global (pass 1).
+__device__ __forceinline__ void pose_info_on_line(const gfpl_camera& cam, const gfpl_config& cfg, const double* DT,
+                                                  const double* L, double c0, double c1, LineInfo& out) {
+  const double cov_sR = pose_info_endpoint(cam, cfg, DT, &L[LD_SP], &L[LD_EP], &L[LD_CS], &L[LD_CE], &L[LD_LE], c0, out.Js);
+  const double cov_eR = pose_info_endpoint(cam, cfg, DT, &L[LD_EP], &L[LD_SP], &L[LD_CE], &L[LD_CS], &L[LD_LE], c1, out.Je);
+  pose_info_weights(cov_sR, cov_eR, out);
 }
 
 __device__ __forceinline__ double info_entry(const LineInfo& I, int i, int j) {
@@ -134,8 +135,12 @@ __device__ __forceinline__ double cut_metric(const gfpl_config& cfg, const doubl
 // ---------------------------------------------------------------------------------------------------------------
 constexpr double CUT_TAU = 1e-8;
 
-// one published half: u[6] (Jacobian column), w[6] = S^-1 u, a = 1 / residual variance, g = u' S^-1 u
-constexpr int HF_U = 0, HF_W = 6, HF_A = 12, HF_G = 13, HF_SIZE = 14;
+// one cached half (8 doubles): vec[6], a = 1 / residual variance, g = u' S^-1 u.  vec is the Jacobian column u for the
+// start-point axis and w = S^-1 v for the end-point axis: a candidate's cross term u' S^-1 v is then one 6-element dot
+// product of its two halves.  A half depends on (line, axis, cut ratio) only — S^-1 is fixed while a line is searched —
+// so halves are cached per cut index (ratio = index * step) in a ring of HC_RING slots per axis and computed four per
+// axis at a time by the group's 8 lanes; a round then costs one dot product per lane instead of one half evaluation.
+constexpr int HC_VEC = 0, HC_A = 6, HC_G = 7, HC_SIZE = 8, HC_RING = 8, HC_CHUNK = 4;
 
 __device__ __forceinline__ double dot3f(const double* a, const double* b) { return fma(a[2], b[2], fma(a[1], b[1], a[0] * b[0])); }
 
@@ -147,10 +152,10 @@ __device__ __forceinline__ double rcp_fast(double x) {
   return r;
 }
 
-// one endpoint of getPoseInfoOnLine at cut ratio c: A/SA = the endpoint that shrinks towards B/SB.  Result -> out[HF_SIZE]
+// one endpoint of getPoseInfoOnLine at cut ratio c: A/SA = the endpoint that shrinks towards B/SB.  Result -> out[HC_SIZE]
 __device__ __forceinline__ void half_fast(const gfpl_camera& cam, const gfpl_config& cfg, const double* DT, const double* A,
                                           const double* Bp, const double* SA, const double* SB, const double* le,
-                                          const double* Sinv /*6x6 row-major*/, double c, double* out) {
+                                          const double* Sinv /*6x6 row-major*/, double c, bool store_w, double* out) {
   const double omc = 1.0 - c;
   double P[3], cur[3], cv[9];
 #pragma unroll
@@ -195,78 +200,28 @@ __device__ __forceinline__ void half_fast(const gfpl_camera& cam, const gfpl_con
     w[i] = sacc;
     g = fma(u[i], sacc, g);
   }
-  double2* o2 = reinterpret_cast<double2*>(out);  // [u0..u5 | w0..w5 | a g]
+  double2* o2 = reinterpret_cast<double2*>(out);  // [vec0..vec5 | a g]
 #pragma unroll
-  for (int i = 0; i < 3; i++) {
-    o2[HF_U / 2 + i] = make_double2(u[2 * i], u[2 * i + 1]);
-    o2[HF_W / 2 + i] = make_double2(w[2 * i], w[2 * i + 1]);
-  }
-  o2[HF_A / 2] = make_double2(a, g);
-}
-
-// S^-1 (full 6x6 row-major) of the lower-packed SPD matrix S (21) by Cholesky; false when S is not safely positive definite
-__device__ __forceinline__ bool spd_inverse6(const double* S, double* Sinv) {
-  double L[21];
-#pragma unroll
-  for (int i = 0; i < 21; i++) L[i] = S[i];
-  bool ok = true;
-#pragma unroll
-  for (int k = 0; k < 6; k++) {
-    double x = L[tri(k, k)];
-#pragma unroll
-    for (int jx = 0; jx < k; jx++) x = fma(-L[tri(k, jx)], L[tri(k, jx)], x);
-    ok = ok && (x > 0.0);
-    const double r = rsqrt(x);
-    L[tri(k, k)] = r;  // store 1/L_kk
-#pragma unroll
-    for (int i = k + 1; i < 6; i++) {
-      double sv = L[tri(i, k)];
-#pragma unroll
-      for (int jx = 0; jx < k; jx++) sv = fma(-L[tri(i, jx)], L[tri(k, jx)], sv);
-      L[tri(i, k)] = sv * r;
-    }
-  }
-  // columns of S^-1: solve L y = e_c, L^T x = y
-#pragma unroll
-  for (int c = 0; c < 6; c++) {
-    double y[6];
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-      double sv = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-      for (int k = 0; k < i; k++) sv = fma(-L[tri(i, k)], y[k], sv);
-      y[i] = (i < c) ? 0.0 : sv * L[tri(i, i)];
-    }
-#pragma unroll
-    for (int i = 5; i >= 0; i--) {
-      double sv = y[i];
-#pragma unroll
-      for (int k = i + 1; k < 6; k++) sv = fma(-L[tri(k, i)], y[k], sv);
-      y[i] = sv * L[tri(i, i)];
-    }
-#pragma unroll
-    for (int i = c; i < 6; i++) { Sinv[i * 6 + c] = y[i]; Sinv[c * 6 + i] = y[i]; }
-  }
-#pragma unroll
-  for (int i = 0; i < 36; i++) ok = ok && (fabs(Sinv[i]) < 1e300);
-  return ok;
+  for (int i = 0; i < 3; i++)
+    o2[HC_VEC / 2 + i] = store_w ? make_double2(w[2 * i], w[2 * i + 1]) : make_double2(u[2 * i], u[2 * i + 1]);
+  o2[HC_A / 2] = make_double2(a, g);
 }
 
 // per-group (one frame pair) state kept in shared memory: every lane of the group reads the same addresses
 // (broadcast), which frees ~120 registers per thread and lets 16 warps / SM hide the fp64 dependency chains.
 struct __align__(16) GroupState {
   double Sinv[36];          // inverse of (invCov_sum - info(line)) for the screening path, row-major (16-byte aligned rows)
-  double half[6][HF_SIZE];  // the six published halves of the current round (112-byte rows)
+  double hc[2][HC_RING][HC_SIZE];  // cached halves: [axis][cut index & (HC_RING - 1)] (64-byte rows)
   double DT[12];            // R | t of DT_inv
   double L[LD_SIZE];        // current line
   double J[CUT_GROUP][6];   // point Jacobians of the current chunk of the invCov_sum pass
   double sum[21];           // invCov_sum, lower triangle
   double sum0[21];          // invCov_sum before the current line's information is removed (exact metric of cut {0,0})
 };
-static_assert(sizeof(GroupState) % 16 == 0 && HF_SIZE % 2 == 0, "128-bit shared-memory accesses below");
+static_assert(sizeof(GroupState) % 16 == 0 && HC_SIZE % 2 == 0 && HC_CHUNK * 2 == CUT_GROUP, "128-bit shared-memory accesses below");
 
-#ifndef CUT_MIN_BLOCKS
-#define CUT_MIN_BLOCKS 4
+#ifndef CUT_MAX_REGS
+#define CUT_MAX_REGS 128   // 8 CTAs (16 warps) per SM
 #endif
 
 // once per line, out of line: every lane factorises S (Cholesky, redundantly), lane j < 6 of the group then solves for
@@ -316,6 +271,18 @@ __device__ __noinline__ bool spd_inverse6_publish(GroupState* G, int j, unsigned
   return (__ballot_sync(gmask, ok) & gmask) == gmask;
 }
 
+// HC_CHUNK halves per axis from index b0 (start-point axis, lanes 0..3) / b1 (end-point axis, lanes 4..7) into the
+// group's cache.  Out of line: it runs once per ~4 rounds and its ~80 live doubles stay out of the round loop.
+__device__ __noinline__ void fill_halves(const gfpl_camera* cam, const gfpl_config* cfg, GroupState* G, int j, int b0, int b1,
+                                         bool go0, bool go1, double step) {
+  const bool isS = j < HC_CHUNK;
+  const int k = (isS ? b0 : b1) + (j & (HC_CHUNK - 1));
+  if (isS ? go0 : go1)
+    half_fast(*cam, *cfg, G->DT, isS ? &G->L[LD_SP] : &G->L[LD_EP], isS ? &G->L[LD_EP] : &G->L[LD_SP],
+              isS ? &G->L[LD_CS] : &G->L[LD_CE], isS ? &G->L[LD_CE] : &G->L[LD_CS], &G->L[LD_LE], G->Sinv,
+              (double)k * step, !isS, G->hc[isS ? 0 : 1][k & (HC_RING - 1)]);
+}
+
 // initial information of one line at cut {0,0} (:1638-1649), out of line
 __device__ __noinline__ void exact_info_initial(const gfpl_camera* cam, const gfpl_config* cfg, const double* DT,
                                                 const gfpl_ln_obs* o, const gfpl_line_cov* c, gfpl_line_cut* C) {
@@ -347,21 +314,32 @@ __device__ __noinline__ double exact_metric_at(const gfpl_camera* cam, const gfp
   return cut_metric(*cfg, M);
 }
 __device__ __noinline__ double exact_metric_start(const gfpl_config* cfg, const GroupState* G) { return cut_metric(*cfg, G->sum0); }
-__device__ __noinline__ void exact_info_store(const gfpl_camera* cam, const gfpl_config* cfg, const GroupState* G, double c0,
-                                              double c1, int j, double* invCovPose) {
+// Information of the accepted cut (once per cut line).  The two endpoints are independent until the 6x6 product: lanes
+// 0..3 evaluate the start point, lanes 4..7 the end point (same operations as pose_info_on_line, so the same bits), the
+// halves meet in the group's half cache (free at the end of a line's search), then every lane forms its entries.
+__device__ __noinline__ void exact_info_store(const gfpl_camera* cam, const gfpl_config* cfg, GroupState* G, double c0,
+                                              double c1, int j, unsigned gmask, double* invCovPose) {
+  const bool isS = j < CUT_GROUP / 2;
+  double J[6];
+  const double var = pose_info_endpoint(*cam, *cfg, G->DT, isS ? &G->L[LD_SP] : &G->L[LD_EP], isS ? &G->L[LD_EP] : &G->L[LD_SP],
+                                        isS ? &G->L[LD_CS] : &G->L[LD_CE], isS ? &G->L[LD_CE] : &G->L[LD_CS], &G->L[LD_LE],
+                                        isS ? c0 : c1, J);
+  double* xs = &G->hc[0][0][0];   // [Js (6) cov_sR . | Je (6) cov_eR .]
+  if ((j & (CUT_GROUP / 2 - 1)) == 0) {
+    double* o = xs + (isS ? 0 : 8);
+#pragma unroll
+    for (int i = 0; i < 6; i++) o[i] = J[i];
+    o[6] = var;
+  }
+  __syncwarp(gmask);
   LineInfo I;
-  pose_info_on_line(*cam, *cfg, G->DT, G->L, c0, c1, I);
+#pragma unroll
+  for (int i = 0; i < 6; i++) { I.Js[i] = xs[i]; I.Je[i] = xs[8 + i]; }
+  pose_info_weights(xs[6], xs[14], I);
   for (int e = j; e < 36; e += CUT_GROUP) invCovPose[e] = info_entry(I, e / 6, e % 6);
 }
 
-__device__ __forceinline__ double shfl_up_f64(unsigned mask, double v, int delta, int width) {
-  int lo = __double2loint(v), hi = __double2hiint(v);
-  lo = __shfl_up_sync(mask, lo, delta, width);
-  hi = __shfl_up_sync(mask, hi, delta, width);
-  return __hiloint2double(hi, lo);
-}
-
-__global__ void __launch_bounds__(CUT_THREADS, CUT_MIN_BLOCKS)
+__global__ void __maxnreg__(CUT_MAX_REGS)
 linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __restrict__ state, DevTrackObs obs,
                const gfpl_line_cov* __restrict__ prev_cov, int cov_cap, gfpl_line_cut* __restrict__ cut_all,
                gfpl_camera cam, gfpl_config cfg) {
@@ -406,6 +384,8 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
   const double step = cfg.cut_step;
   const double nb0 = (j == 0 || j == 4 || j == 5) ? step : ((j == 1 || j == 6 || j == 7) ? -step : 0.0);
   const double nb1 = (j == 2 || j == 4 || j == 6) ? step : ((j == 3 || j == 5 || j == 7) ? -step : 0.0);
+  const int d0 = (j == 0 || j == 4 || j == 5) ? 1 : ((j == 1 || j == 6 || j == 7) ? -1 : 0);   // the same in steps
+  const int d1 = (j == 2 || j == 4 || j == 6) ? 1 : ((j == 3 || j == 5 || j == 7) ? -1 : 0);
 
   // pass 1a: initial information of every line (cut = 0), lanes stride over the lines (:1638-1649)
   for (int l = j; l < nln; l += CUT_GROUP) exact_info_initial(&s_cam, &s_cfg, G.DT, &lns[l], &cov[lns[l].prev_idx], &cut[l]);
@@ -493,93 +473,125 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
     if (fast_ok) fast_ok = spd_inverse6_publish(&G, j, gmask);
     __syncwarp(gmask);
     double cur0 = 0.0, cur1 = 0.0;
+    int i0 = 0, i1 = 0;            // the same cut as integer multiples of the step (indices of the cached halves)
+    int lo0 = -1, hi0 = -1, lo1 = -1, hi1 = -1;   // cached index ranges [lo, hi) per axis, hi - lo <= HC_RING
     double metric_last = 0.0;      // the reference's metric of the current cut; evaluated lazily (exact rounds only)
     bool have_exact_last = false;
     bool at_start = true;          // current cut is still {0,0}: its exact metric is logdet(sum0)
     double dcur = 0.0;             // screening determinant factor of the current cut
     bool have_dcur = false;
-    while (cur0 + cur1 <= 1.0) {
+    // The search alternates between a call-free loop of screened rounds (everything it carries stays in registers) and
+    // the rare out-of-line work it stops for: a refill of the half cache or a round in the reference's arithmetic.
+    enum { STOP, REFILL, EXACT };
+    for (;;) {
+      int why = STOP;
+      if (!fast_ok) why = (cur0 + cur1 <= 1.0) ? EXACT : STOP;
+      else
+        while (cur0 + cur1 <= 1.0) {
+          // a round reads the halves at index - 1, index, index + 1 of both axes
+          if (i0 - 1 < lo0 || i0 + 1 >= hi0 || i1 - 1 < lo1 || i1 + 1 >= hi1) { why = REFILL; break; }
+          const double ct0 = cur0 + nb0, ct1 = cur1 + nb1;
+          bool valid = !(ct0 + ct1 > 1.0);
+          valid = valid && !(ct0 < cfg.cut_rng[0] || ct0 > cfg.cut_rng[1]);
+          valid = valid && !(ct1 < cfg.cut_rng[0] || ct1 > cfg.cut_rng[1]);
+          // determinant factor of (si, ei): (1 + a u'S^-1u)(1 + b v'S^-1v) - a b (u'S^-1v)^2  (monotone in the metric)
+          auto factor = [&](int si, int ei) {
+            const double2* hs = reinterpret_cast<const double2*>(G.hc[0][si & (HC_RING - 1)]);
+            const double2* he = reinterpret_cast<const double2*>(G.hc[1][ei & (HC_RING - 1)]);
+            double guv = 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+              const double2 uu = hs[HC_VEC / 2 + i], ww = he[HC_VEC / 2 + i];
+              guv = fma(uu.x, ww.x, guv);
+              guv = fma(uu.y, ww.y, guv);
+            }
+            const double2 ags = hs[HC_A / 2], age = he[HC_A / 2];   // (a, g) of each half
+            const double a = ags.x, b = age.x;
+            return fma(-(a * b) * guv, guv, fma(a, ags.y, 1.0) * fma(b, age.y, 1.0));
+          };
+          const double dj = factor(i0 + d0, i1 + d1);                  // this lane's candidate
+          if (!have_dcur) { dcur = factor(i0, i1); have_dcur = true; }   // the current cut (same value in every lane)
+          // The reference keeps the first candidate (in j order) that is strictly better than everything before it,
+          // i.e. the arg-max with ties to the lowest j, or none if no candidate beats the current cut (:1722-1730).
+          // The factors decide that when the largest one is clear of every other candidate and of the current cut by
+          // more than CUT_TAU (relative), or when the current cut is clear of all candidates.  Usable factors are
+          // positive, so their order is the order of their bit patterns: the maximum is two 32-bit butterflies.
+          const bool usable = dj > 0.0 && dj < 1e300;
+          const unsigned hj = valid ? (unsigned)__double2hiint(dj) : 0u, lj = valid ? (unsigned)__double2loint(dj) : 0u;
+          unsigned mh = hj;
+#pragma unroll
+          for (int dlt = 1; dlt < CUT_GROUP; dlt <<= 1) mh = max(mh, __shfl_xor_sync(gmask, mh, dlt, CUT_GROUP));
+          unsigned ml = (hj == mh) ? lj : 0u;
+#pragma unroll
+          for (int dlt = 1; dlt < CUT_GROUP; dlt <<= 1) ml = max(ml, __shfl_xor_sync(gmask, ml, dlt, CUT_GROUP));
+          const double best = __hiloint2double((int)mh, (int)ml);   // largest candidate factor (0: no valid candidate)
+          // flags of this lane: bit j = "I am the maximum", bit 8 = a factor that cannot be used, bit 9 = too close to it
+          const bool is_max = valid && hj == mh && lj == ml;
+          unsigned fl = is_max ? (1u << j) : 0u;
+          if (valid && !usable) fl |= 1u << 8;
+          if (valid && !is_max && !(best - dj > CUT_TAU * best)) fl |= 1u << 9;
+#pragma unroll
+          for (int dlt = 1; dlt < CUT_GROUP; dlt <<= 1) fl |= __shfl_xor_sync(gmask, fl, dlt, CUT_GROUP);
+          const bool sane = dcur > 0.0 && dcur < 1e300 && !(fl & (1u << 8)) && !(best >= 1e300);
+          const unsigned winners = fl & 0xFFu;
+          int cand;
+          if (sane && best - dcur > CUT_TAU * best && !(fl & (1u << 9)) && (winners & (winners - 1u)) == 0u)
+            cand = __ffs(winners) - 1;                         // one candidate is clearly the best
+          else if (sane && dcur - best > CUT_TAU * dcur) break;  // every candidate is clearly worse: the search stops (STOP)
+          else { why = EXACT; break; }
+          have_exact_last = false; dcur = best;
+          // the winner's cut: the same additions lane `cand` made (cur + nb), so every lane can make them itself
+          const int c0d = (int)((0xA52u >> (2 * cand)) & 3u) - 1, c1d = (int)((0x2225u >> (2 * cand)) & 3u) - 1;
+          cur0 = cur0 + (c0d > 0 ? step : (c0d < 0 ? -step : 0.0));
+          cur1 = cur1 + (c1d > 0 ? step : (c1d < 0 ? -step : 0.0));
+          i0 += c0d; i1 += c1d;
+          at_start = false;
+        }
+      if (why == STOP) break;
+      if (why == REFILL) {
+        // per axis: append HC_CHUNK indices at hi (if that does not evict index - 1), or restart the range at index - 1
+        int b0 = hi0, b1 = hi1;
+        bool go0 = true, go1 = true;
+        if (i0 - 1 < lo0 || i0 - 1 > hi0) { lo0 = i0 - 1; b0 = lo0; }
+        else if (hi0 + HC_CHUNK - HC_RING > i0 - 1) go0 = false;
+        if (i1 - 1 < lo1 || i1 - 1 > hi1) { lo1 = i1 - 1; b1 = lo1; }
+        else if (hi1 + HC_CHUNK - HC_RING > i1 - 1) go1 = false;
+        fill_halves(&s_cam, &s_cfg, &G, j, b0, b1, go0, go1, step);
+        if (go0) { hi0 = b0 + HC_CHUNK; lo0 = max(lo0, hi0 - HC_RING); }
+        if (go1) { hi1 = b1 + HC_CHUNK; lo1 = max(lo1, hi1 - HC_RING); }
+        __syncwarp(gmask);
+        continue;
+      }
+      // exact round: the reference's arithmetic (also the only path for the min-eigenvalue metric)
       const double ct0 = cur0 + nb0, ct1 = cur1 + nb1;
       bool valid = !(ct0 + ct1 > 1.0);
       valid = valid && !(ct0 < cfg.cut_rng[0] || ct0 > cfg.cut_rng[1]);
       valid = valid && !(ct1 < cfg.cut_rng[0] || ct1 > cfg.cut_rng[1]);
+      if (!have_exact_last) {  // metric of the current cut, needed as the running best
+        metric_last = at_start ? exact_metric_start(&s_cfg, &G) : exact_metric_at(&s_cam, &s_cfg, &G, cur0, cur1);
+        have_exact_last = true;
+      }
+      const double metric = valid ? exact_metric_at(&s_cam, &s_cfg, &G, ct0, ct1) : 0.0;
+      // "first strictly better in j order" (:1722-1730)
       int cand = -1;
-      bool decided = false;
-      if (fast_ok) {
-        // lanes 0..2: start-point halves at c0 - step, c0, c0 + step; lanes 3..5: end-point halves likewise
-        if (j < 6) {
-          const bool isS = j < 3;
-          const int kk = (j % 3) - 1;
-          const double ch = (isS ? cur0 : cur1) + (kk < 0 ? -step : (kk > 0 ? step : 0.0));
-          half_fast(cam, cfg, G.DT, isS ? &G.L[LD_SP] : &G.L[LD_EP], isS ? &G.L[LD_EP] : &G.L[LD_SP],
-                    isS ? &G.L[LD_CS] : &G.L[LD_CE], isS ? &G.L[LD_CE] : &G.L[LD_CS], &G.L[LD_LE], G.Sinv, ch, G.half[j]);
-        }
-        __syncwarp(gmask);
-        // determinant factor of (si, ei): (1 + a u'S^-1u)(1 + b v'S^-1v) - a b (u'S^-1v)^2  (monotone in the metric)
-        auto factor = [&](int si, int ei) {
-          const double2* hs = reinterpret_cast<const double2*>(G.half[si]);
-          const double2* he = reinterpret_cast<const double2*>(G.half[ei]);
-          double guv = 0.0;
+      double best = metric_last;
 #pragma unroll
-          for (int i = 0; i < 3; i++) {
-            const double2 uu = hs[HF_U / 2 + i], ww = he[HF_W / 2 + i];
-            guv = fma(uu.x, ww.x, guv);
-            guv = fma(uu.y, ww.y, guv);
-          }
-          const double2 ags = hs[HF_A / 2], age = he[HF_A / 2];   // (a, g) of each half
-          const double a = ags.x, b = age.x;
-          return fma(-(a * b) * guv, guv, fma(a, ags.y, 1.0) * fma(b, age.y, 1.0));
-        };
-        const int si = (nb0 < 0.0) ? 0 : ((nb0 > 0.0) ? 2 : 1);
-        const int ei = 3 + ((nb1 < 0.0) ? 0 : ((nb1 > 0.0) ? 2 : 1));
-        const double dj = factor(si, ei);          // this lane's candidate
-        if (!have_dcur) { dcur = factor(1, 4); have_dcur = true; }   // the current cut (same value in every lane)
-        __syncwarp(gmask);
-        // replay the reference's selection ("first strictly better in j order", :1722-1730) on the factors, but only if
-        // every comparison it makes is clear by > CUT_TAU (relative).  Candidate j is compared with the running best
-        // before it = max(current cut, valid candidates i < j): an exclusive prefix maximum over the group's lanes.
-        const double mv = valid ? dj : 0.0;   // usable factors are > 0: a masked lane never raises the maximum
-        double pre = mv;
-#pragma unroll
-        for (int dlt = 1; dlt < CUT_GROUP; dlt <<= 1) {
-          const double t = shfl_up_f64(gmask, pre, dlt, CUT_GROUP);
-          pre = (j >= dlt) ? fmax(pre, t) : pre;
-        }
-        const double excl = shfl_up_f64(gmask, pre, 1, CUT_GROUP);
-        const double before = (j == 0) ? dcur : fmax(dcur, excl);
-        const bool lane_clear = !valid || ((dj > 0.0) && dj < 1e300 && fabs(dj - before) > CUT_TAU * before);
-        const unsigned okmask = __ballot_sync(gmask, lane_clear) & gmask;
-        const bool clear = (dcur > 0.0) && dcur < 1e300 && okmask == gmask;
-        const double best = fmax(dcur, shfl_f64(gmask, pre, CUT_GROUP - 1, CUT_GROUP));
-        const unsigned winners = __ballot_sync(gmask, valid && dj == best) & gmask;
-        const int bj = (best > dcur && winners) ? (__ffs(winners) - 1) - grp * CUT_GROUP : -1;
-        if (clear) { decided = true; cand = bj; have_exact_last = false; dcur = best; }
+      for (int jj = 0; jj < CUT_GROUP; jj++) {
+        const double mj = shfl_f64(gmask, metric, jj, CUT_GROUP);
+        const int vj = __shfl_sync(gmask, (int)valid, jj, CUT_GROUP);
+        if (vj && mj > best) { best = mj; cand = jj; }
       }
-      if (!decided) {
-        // exact round: the reference's arithmetic (also the only path for the min-eigenvalue metric)
-        if (!have_exact_last) {  // metric of the current cut, needed as the running best
-          metric_last = at_start ? exact_metric_start(&s_cfg, &G) : exact_metric_at(&s_cam, &s_cfg, &G, cur0, cur1);
-          have_exact_last = true;
-        }
-        const double metric = valid ? exact_metric_at(&s_cam, &s_cfg, &G, ct0, ct1) : 0.0;
-        // "first strictly better in j order" (:1722-1730)
-        double best = metric_last;
-#pragma unroll
-        for (int jj = 0; jj < CUT_GROUP; jj++) {
-          const double mj = shfl_f64(gmask, metric, jj, CUT_GROUP);
-          const int vj = __shfl_sync(gmask, (int)valid, jj, CUT_GROUP);
-          if (vj && mj > best) { best = mj; cand = jj; }
-        }
-        metric_last = best;
-        have_dcur = false;   // the screening factor of the new current cut is re-evaluated next round
-      }
+      metric_last = best;
+      have_dcur = false;   // the screening factor of the new current cut is re-evaluated next round
       if (cand < 0) break;  // early termination (:1741-1743)
-      cur0 = shfl_f64(gmask, ct0, cand, CUT_GROUP);
-      cur1 = shfl_f64(gmask, ct1, cand, CUT_GROUP);
+      const int c0d = (int)((0xA52u >> (2 * cand)) & 3u) - 1, c1d = (int)((0x2225u >> (2 * cand)) & 3u) - 1;
+      cur0 = cur0 + (c0d > 0 ? step : (c0d < 0 ? -step : 0.0));
+      cur1 = cur1 + (c1d > 0 ? step : (c1d < 0 ? -step : 0.0));
+      i0 += c0d; i1 += c1d;
       at_start = false;
     }
     // invCovPose of the accepted cut, in the reference's arithmetic (cut {0,0} is already stored by pass 1)
-    if (cur0 != 0.0 || cur1 != 0.0) exact_info_store(&s_cam, &s_cfg, &G, cur0, cur1, j, C.invCovPose);
+    if (cur0 != 0.0 || cur1 != 0.0) exact_info_store(&s_cam, &s_cfg, &G, cur0, cur1, j, gmask, C.invCovPose);
     __syncwarp(gmask);
     // updateEndPointByRatio (:1451-1470) — lane 0 of the group writes the results
     if (j == 0) {

@@ -12,7 +12,8 @@ import numpy as np
 from . import _structs as S
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-LIB_PATH = os.path.join(_ROOT, "lib", "libgfpl.so")
+# GFPL_LIB: another build of the same library (kernel experiments, tools/stage_ms.py); there is no other implementation
+LIB_PATH = os.environ.get("GFPL_LIB") or os.path.join(_ROOT, "lib", "libgfpl.so")
 _LIB = None
 
 
