@@ -4,21 +4,32 @@
 // (:2032-2056), removeOutliers (:2058-2116) + vector_stdv_mad (auxiliar.cpp:521-537) and both
 // optimizePose overloads (:1864-2030).
 //
-// One warp owns one frame pair for the whole optimisation (both GN stages and the outlier pass), so the
-// kernel is persistent across iterations: the observation lists are read from L1/L2, the pose and the
-// 28 normal-equation partials (21 lower-triangle H + 6 g + 1 e) live in registers, and each iteration
-// ends in a fixed xor-butterfly of fp64 warp shuffles — every lane ends with bit-identical H, g, e and
-// the result is run-to-run reproducible.  All lanes then run the 6x6 pivoted LDLT solve and the SE(3)
-// update redundantly (no broadcast, no divergence).  FP64-ALU / latency bound:
-// flops per iteration ~ 114 per point + 212 per line.
+// A group of POSE_GROUP lanes (16: two pairs per warp) owns one frame pair for the whole optimisation (both GN stages
+// and the outlier pass), so the kernel is persistent across iterations: the observation lists are read from L1/L2, the
+// pose and the 28 normal-equation partials (21 lower-triangle H + 6 g + 1 e) live in registers, and each iteration ends
+// in a fixed xor-butterfly of fp64 shuffles inside the group — every lane ends with bit-identical H, g, e and the result
+// is run-to-run reproducible.  All lanes then run the 6x6 LDL^T solve and the SE(3) update redundantly (no broadcast):
+// that serial part costs a warp the same instructions whether it serves one pair or several, which is why a warp serves
+// several.  The groups of a warp stay convergent (full-mask shuffles): a group that has stopped iterating is predicated
+// off, the warp leaves a loop when all its groups have.  FP64-ALU / latency bound: flops per iteration ~ 114 per point
+// + 212 per line.
 #include "gfpl_internal.h"
 #include "gfpl_math.cuh"
 
 namespace gfpl {
 
-constexpr int POSE_WARPS = 4;
-#ifndef POSE_MIN_BLOCKS
-#define POSE_MIN_BLOCKS 3  // <= 168 registers (measured: 1.70 ms vs 1.98 ms at 4 blocks = 128 registers with spills in the GN loop)
+constexpr int POSE_WARPS = 2;
+#ifndef POSE_GROUP
+#define POSE_GROUP 16     // lanes per frame pair
+#endif
+#ifndef POSE_DT_SMEM
+#define POSE_DT_SMEM 1   // re-read the pose from shared memory per observation (0: let the compiler keep it in registers)
+#endif
+#ifndef POSE_PINGPONG
+#define POSE_PINGPONG 0
+#endif
+#ifndef POSE_MAX_REGS
+#define POSE_MAX_REGS 144  // 7 CTAs = 14 warps per SM: 8192 pairs at 2 pairs per warp are exactly two waves of 148 SMs
 #endif
 
 // hand-off record between the GN kernel and the finalize kernel
@@ -43,6 +54,24 @@ __device__ __forceinline__ void acc_add(Acc& a, const double* J, double r, doubl
     a.v[21 + i] = fma(J[i], rw, a.v[21 + i]);
   }
   a.v[27] = fma(r, rw, a.v[27]);
+}
+
+// Branch-free reciprocal and reciprocal square root: the hardware seed (MUFU.RCP64H / MUFU.RSQ64H, > 20 good bits)
+// and one third-order correction, i.e. a relative error far below 2^-53 before the final rounding.  `1.0 / x` and
+// sqrt() compile to the same seed plus a longer refinement and a slow-path call behind a branch (five of those per point
+// in the first version of this file).  Zero, infinite and NaN arguments end as NaN or Inf; the callers' guards
+// (max(homog_th, .)) take those cases before the value is used.
+__device__ __forceinline__ double rcp_nr(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y, 1.0);
+  return fma(y, fma(e, e, e), y);
+}
+__device__ __forceinline__ double rsqrt_nr(double s) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+  const double e = fma(-s, y * y, 1.0);
+  return fma(y * e, fma(e, 0.375, 0.5), y);
 }
 
 // This translation unit is tolerance-compared (1e-9) and compiled with FMA contraction: divisions that the
@@ -167,11 +196,11 @@ __device__ __forceinline__ void ldlt6_solve_reg(const double* Hin, const double*
 // factorisation needs no row / column exchanges — the predicated swaps above are ~4/5 of the instructions of the
 // pivoted routine, executed by every lane in every GN iteration.  It reports failure when a pivot is not safely positive
 // (relative to the largest diagonal entry); the caller then runs the pivoted routine, which is what Eigen would do.
-__device__ __forceinline__ bool ldlt6_solve_nopivot(const double* H, const double* g, double* x) {
+__device__ __forceinline__ bool ldlt6_solve_nopivot(const double* Hp /*lower triangle, packed*/, const double* g, double* x) {
   double L[36], d[6], id[6];
-  double dmax = H[0];
+  double dmax = Hp[0];
 #pragma unroll
-  for (int i = 1; i < 6; i++) dmax = fmax(dmax, H[i * 6 + i]);
+  for (int i = 1; i < 6; i++) dmax = fmax(dmax, Hp[tri(i, i)]);
   const double floor_ = 1e-11 * dmax;
   bool ok = dmax > 0.0 && dmax < 1e300;
 #pragma unroll
@@ -179,15 +208,15 @@ __device__ __forceinline__ bool ldlt6_solve_nopivot(const double* H, const doubl
     double t[6];
 #pragma unroll
     for (int j = 0; j < k; j++) t[j] = L[k * 6 + j] * d[j];
-    double dk = H[k * 6 + k];
+    double dk = Hp[tri(k, k)];
 #pragma unroll
     for (int j = 0; j < k; j++) dk = fma(-L[k * 6 + j], t[j], dk);
     d[k] = dk;
     ok = ok && (dk > floor_);
-    id[k] = 1.0 / dk;
+    id[k] = rcp_nr(dk);
 #pragma unroll
     for (int i = k + 1; i < 6; i++) {
-      double v = H[i * 6 + k];
+      double v = Hp[tri(i, k)];
 #pragma unroll
       for (int j = 0; j < k; j++) v = fma(-L[i * 6 + j], t[j], v);
       L[i * 6 + k] = v * id[k];
@@ -224,110 +253,224 @@ struct PairObs {
   uint8_t* lin;
 };
 
-// optimizeFunctions for one pair by one warp.  Returns H (full 6x6), g, e in every lane.
-__device__ __forceinline__ void warp_optimize_functions(const double* DT, const PairObs& o, const gfpl_camera& cam,
-                                        const gfpl_config& cfg, double* H, double* g, double* e) {
-  const int lane = threadIdx.x & 31;
-  Acc a;
+// ---- reductions inside a group of G lanes (full-mask shuffles: the groups of a warp call them together) -------------
+template <int G>
+__device__ __forceinline__ int group_sum(int v) {
+  if (G == 32) return __reduce_add_sync(0xffffffffu, v);
+#pragma unroll
+  for (int s = G / 2; s >= 1; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  return v;
+}
+template <int G>
+__device__ __forceinline__ uint32_t group_max(uint32_t v) {
+  if (G == 32) return __reduce_max_sync(0xffffffffu, v);
+#pragma unroll
+  for (int s = G / 2; s >= 1; s >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, s));
+  return v;
+}
+
+struct PoseConst {  // loop invariants of the observation terms
+  double hth, inv_hth, fx_over_hth;
+};
+
+// The pose under optimisation lives in the pair's shared-memory slot (12 doubles, rows of [R | t]).  The observation
+// loop re-reads it per observation with 128-bit shared loads (same address in every lane of the group: a broadcast)
+// instead of carrying it in 24 registers across the loop — with the 56 registers of partial sums that is what lets the
+// kernel run 14 warps per SM without local-memory traffic.  Every lane of a group stores the same values.
+__device__ __forceinline__ void pose_load(const double* DTs, double* T /*16*/) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(DTs);
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#if POSE_DT_SMEM
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(T[2 * i]), "=d"(T[2 * i + 1]) : "r"(a + 16u * i));
+#else
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(T[2 * i]), "=d"(T[2 * i + 1]) : "r"(a + 16u * i));
+#endif
+  T[12] = 0.0; T[13] = 0.0; T[14] = 0.0; T[15] = 1.0;   // poses are SE(3)
+}
+__device__ __forceinline__ void pose_store(double* DTs, const double* T) {
+#pragma unroll
+  for (int i = 0; i < 12; i++) DTs[i] = T[i];
+}
+
+// point term (stereoFrameHandler.cpp:2131-2167) added to the partial sums
+__device__ __forceinline__ void point_term(const double* DTs, const gfpl_pt_obs& ob, const gfpl_camera& cam, const PoseConst& c,
+                                           Acc& a) {
+  double DT[16], P_[3], J[6];
+  pose_load(DTs, DT);
+  se3_apply(DT, ob.P, P_);
+  const double iz = rcp_nr(P_[2]);
+  const double dx = (cam.cx + cam.fx * P_[0] * iz) - ob.pl_obs[0];
+  const double dy = (cam.cy + cam.fy * P_[1] * iz) - ob.pl_obs[1];
+  const double s = dx * dx + dy * dy;
+  double fgz2 = cam.fx * iz * iz;                     // fx / max(homog_th, Z^2)
+  if (!(P_[2] * P_[2] > c.hth)) fgz2 = c.fx_over_hth;
+  double idn = rsqrt_nr(s), r = s * idn;              // r = |err|, idn = 1 / max(homog_th, r)
+  if (!(r > c.hth)) { r = sqrt(s); idn = c.inv_hth; }
+  jac6(fgz2, P_[0], P_[1], P_[2], dx, dy, J);
+#pragma unroll
+  for (int i = 0; i < 6; i++) J[i] = J[i] * idn;
+  const double w = rcp_nr(1.0 + s * ob.sigma2);
+  acc_add(a, J, r, w);
+}
+
+// line term (:2171-2235)
+__device__ __forceinline__ void line_term(const double* DTs, const gfpl_ln_obs& ob, const gfpl_camera& cam, const PoseConst& c,
+                                          Acc& a) {
+  double DT[16], sP_[3], eP_[3], Js[6], Je[6], J[6];
+  pose_load(DTs, DT);
+  se3_apply(DT, ob.sP, sP_);
+  se3_apply(DT, ob.eP, eP_);
+  const double izs = rcp_nr(sP_[2]), ize = rcp_nr(eP_[2]);
+  const double su = cam.cx + cam.fx * sP_[0] * izs, sv = cam.cy + cam.fy * sP_[1] * izs;
+  const double eu = cam.cx + cam.fx * eP_[0] * ize, ev = cam.cy + cam.fy * eP_[1] * ize;
+  const double ds = ob.le_obs[0] * su + ob.le_obs[1] * sv + ob.le_obs[2];
+  const double de = ob.le_obs[0] * eu + ob.le_obs[1] * ev + ob.le_obs[2];
+  const double s = ds * ds + de * de;
+  double ks = cam.fx * izs * izs, ke = cam.fx * ize * ize;
+  if (!(sP_[2] * sP_[2] > c.hth)) ks = c.fx_over_hth;
+  if (!(eP_[2] * eP_[2] > c.hth)) ke = c.fx_over_hth;
+  double idn = rsqrt_nr(s), r = s * idn;
+  if (!(r > c.hth)) { r = sqrt(s); idn = c.inv_hth; }
+  jac6(ks, sP_[0], sP_[1], sP_[2], ob.le_obs[0], ob.le_obs[1], Js);
+  jac6(ke, eP_[0], eP_[1], eP_[2], ob.le_obs[0], ob.le_obs[1], Je);
+#pragma unroll
+  for (int i = 0; i < 6; i++) J[i] = (Js[i] * ds + Je[i] * de) * idn;
+  const double w = rcp_nr(1.0 + s * ob.sigma2);
+  acc_add(a, J, r, w);
+}
+
+// optimizeFunctions for one pair by one group of G lanes: a.v = [H lower triangle, packed (21) | g (6) | e] (nothing is
+// evaluated for a group that is not `act`: its sums are zero).  Every lane of the group ends with the same values.
+template <int G>
+__device__ __forceinline__ void group_optimize_functions(const double* DTs, const PairObs& o, bool act, const gfpl_camera& cam,
+                                                         const gfpl_config& cfg, Acc& a) {
+  const int lg = threadIdx.x & (G - 1);
+  const int npt = act ? o.npt : 0, nln = act ? o.nln : 0;
+  PoseConst c;
+  c.hth = cfg.homog_th; c.inv_hth = 1.0 / cfg.homog_th; c.fx_over_hth = cam.fx / cfg.homog_th;
 #pragma unroll
   for (int i = 0; i < 28; i++) a.v[i] = 0.0;
   int N = 0;
-  // software-pipelined: the observation of the next round is loaded before this round's arithmetic
-  gfpl_pt_obs nxt;
-  uint8_t nxt_in = 0;
-  if (lane < o.npt) { nxt = o.pts[lane]; nxt_in = o.pin[lane]; }
-  for (int k = lane; k < o.npt; k += 32) {
-    const gfpl_pt_obs ob = nxt;
-    const uint8_t in = nxt_in;
-    if (k + 32 < o.npt) { nxt = o.pts[k + 32]; nxt_in = o.pin[k + 32]; }
-    if (!in) continue;
-    double P_[3], d[2], J[6];
-    const double r = point_residual(DT, ob, cam, P_, d);
-    const double fgz2 = cam.fx / fmax(cfg.homog_th, P_[2] * P_[2]);
-    jac6(fgz2, P_[0], P_[1], P_[2], d[0], d[1], J);
-    const double idn = 1.0 / fmax(cfg.homog_th, r);
-#pragma unroll
-    for (int i = 0; i < 6; i++) J[i] = J[i] * idn;
-    const double w = 1.0 / (1.0 + r * r * ob.sigma2);
-    acc_add(a, J, r, w);
-    N++;
+  {
+#if POSE_PINGPONG
+    // two observations in flight: the one after the next is loaded before the current one is evaluated, and the two
+    // buffers swap roles in the unrolled body (no register copies)
+    const gfpl_pt_obs* pp = o.pts + lg;
+    const uint8_t* pi = o.pin + lg;
+    gfpl_pt_obs A{}, Bq{};
+    uint8_t ia = 0, ib = 0;
+    if (lg < npt) { A = pp[0]; ia = pi[0]; }
+    for (int k = lg; k < npt; k += 2 * G, pp += 2 * G, pi += 2 * G) {
+      ib = 0;
+      if (k + G < npt) { Bq = pp[G]; ib = pi[G]; }
+      if (ia) { point_term(DTs, A, cam, c, a); N++; }
+      ia = 0;
+      if (k + 2 * G < npt) { A = pp[2 * G]; ia = pi[2 * G]; }
+      if (ib) { point_term(DTs, Bq, cam, c, a); N++; }
+    }
+#else
+    // no software prefetch: the observation lists sit in L1 after the first iteration, and the registers a second
+    // buffer would take are what keeps the partial sums out of local memory at 14 warps per SM
+    const gfpl_pt_obs* pp = o.pts + lg;
+    const uint8_t* pi = o.pin + lg;
+    for (int k = lg; k < npt; k += G, pp += G, pi += G) {
+      if (!*pi) continue;
+      const gfpl_pt_obs ob = *pp;
+      point_term(DTs, ob, cam, c, a);
+      N++;
+    }
+#endif
   }
-  for (int k = lane; k < o.nln; k += 32) {
+  for (int k = lg; k < nln; k += G) {
     if (!o.lin[k]) continue;
-    double sP_[3], eP_[3], d[2], Js[6], Je[6], J[6];
     const gfpl_ln_obs ob = o.lns[k];
-    const double r = line_residual(DT, ob, cam, sP_, eP_, d);
-    jac6(cam.fx / fmax(cfg.homog_th, sP_[2] * sP_[2]), sP_[0], sP_[1], sP_[2], ob.le_obs[0], ob.le_obs[1], Js);
-    jac6(cam.fx / fmax(cfg.homog_th, eP_[2] * eP_[2]), eP_[0], eP_[1], eP_[2], ob.le_obs[0], ob.le_obs[1], Je);
-    const double idn = 1.0 / fmax(cfg.homog_th, r);
-#pragma unroll
-    for (int i = 0; i < 6; i++) J[i] = (Js[i] * d[0] + Je[i] * d[1]) * idn;
-    const double w = 1.0 / (1.0 + r * r * ob.sigma2);
-    acc_add(a, J, r, w);
+    line_term(DTs, ob, cam, c, a);
     N++;
   }
   // fixed xor-butterfly: identical association in every lane, deterministic run to run
 #pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
+  for (int s = G / 2; s >= 1; s >>= 1) {
 #pragma unroll
     for (int i = 0; i < 28; i++) a.v[i] = a.v[i] + shfl_xor_f64(0xffffffffu, a.v[i], s);
     N += __shfl_xor_sync(0xffffffffu, N, s);
   }
-#pragma unroll
-  for (int i = 0; i < 6; i++) {
-#pragma unroll
-    for (int j = 0; j <= i; j++) { H[i * 6 + j] = a.v[tri(i, j)]; H[j * 6 + i] = a.v[tri(i, j)]; }
-    g[i] = a.v[21 + i];
-  }
-  *e = a.v[27] / (double)N;  // e /= (N_l + N_p), 0/0 -> NaN like the reference
+  a.v[27] = a.v[27] / (double)N;  // e /= (N_l + N_p), 0/0 -> NaN like the reference
 }
 
-// gaussNewtonOptimization (:2032-2056); H of the last evaluation is returned for DT_cov = H^-1
-__device__ __forceinline__ int warp_gauss_newton(double* DT, const PairObs& o, const gfpl_camera& cam, const gfpl_config& cfg,
-                                 int max_iters, double* H, double* err_) {
-  double g[6], inc[6];
+// gaussNewtonOptimization (:2032-2056) for the groups of a warp together; H of the last evaluation is returned for
+// DT_cov = H^-1.  A group without a problem to solve (`alive` false) only takes part in the shuffles.
+template <int G>
+__device__ __forceinline__ int group_gauss_newton(double* DTs /*shared, 12*/, const PairObs& o, bool alive, const gfpl_camera& cam,
+                                                  const gfpl_config& cfg, int max_iters, double* Hs /*shared, 21*/, double* err_) {
+  const int lg = threadIdx.x & (G - 1);
+  double inc[6];
   double err = 0.0, err_prev = 999999999.9;
-  for (int i = 0; i < 36; i++) H[i] = 0.0;
-  int iters = 0;
-  for (; iters < max_iters; iters++) {
-    warp_optimize_functions(DT, o, cam, cfg, H, g, &err);
-    if ((fabs(err - err_prev) < cfg.min_error_change) || (err < cfg.min_error)) break;
-    if (!ldlt6_solve_nopivot(H, g, inc)) {
-      double Hm[36], gm[6], xm[6];
-      for (int i = 0; i < 36; i++) Hm[i] = H[i];
-      for (int i = 0; i < 6; i++) gm[i] = g[i];
-      ldlt6_solve_pivoted_slow(Hm, gm, xm);
-      for (int i = 0; i < 6; i++) inc[i] = xm[i];
-    }
-    double E[16], Ei[16];
-    expmap_se3(inc, E);
-    inverse_se3(E, Ei);
-    matmul<4, 4, 4>(DT, Ei, DT);
-    double nrm = 0.0;
+  if (alive && lg == 0) {
 #pragma unroll
-    for (int i = 0; i < 6; i++) nrm = nrm + inc[i] * inc[i];
-    if (sqrt(nrm) < 2.220446049250313e-16) break;
-    err_prev = err;
+    for (int i = 0; i < 21; i++) Hs[i] = 0.0;
   }
-  *err_ = err;
+  bool act = alive;
+  int iters = 0;
+  for (int it = 0; it < max_iters; it++) {
+    if (!__any_sync(0xffffffffu, act)) break;
+    Acc a;
+    group_optimize_functions<G>(DTs, o, act, cam, cfg, a);
+    if (act) {  // H of the last evaluation is kept in the pair's shared-memory slot, not in 42 registers across the loop
+      err = a.v[27];
+      if (lg == 0) {
+#pragma unroll
+        for (int i = 0; i < 21; i++) Hs[i] = a.v[i];
+      }
+    }
+    bool go = act && !((fabs(err - err_prev) < cfg.min_error_change) || (err < cfg.min_error));
+    const bool solved = ldlt6_solve_nopivot(a.v, a.v + 21, inc);
+    if (go) {
+      if (!solved) {
+        double Hm[36], gm[6], xm[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+          for (int j = 0; j < 6; j++) Hm[i * 6 + j] = a.v[i >= j ? tri(i, j) : tri(j, i)];
+#pragma unroll
+        for (int i = 0; i < 6; i++) gm[i] = a.v[21 + i];
+        ldlt6_solve_pivoted_slow(Hm, gm, xm);
+#pragma unroll
+        for (int i = 0; i < 6; i++) inc[i] = xm[i];
+      }
+      double E[16], Ei[16], DT[16];
+      expmap_se3(inc, E);
+      inverse_se3(E, Ei);
+      pose_load(DTs, DT);
+      matmul<4, 4, 4>(DT, Ei, DT);
+      pose_store(DTs, DT);
+      double nrm = 0.0;
+#pragma unroll
+      for (int i = 0; i < 6; i++) nrm = nrm + inc[i] * inc[i];
+      if (sqrt(nrm) < 2.220446049250313e-16) go = false;
+      else { err_prev = err; iters++; }
+    }
+    act = go;
+  }
+  if (alive) *err_ = err;
   return iters;
 }
 
 // element [rank] of the ascending order of n unsigned keys, without sorting: MSB-first binary search on the key bits,
-// one warp-wide count (REDUX.SUM) per probe.  key k lives at keys[k * STRIDE]; with RESTRICT only the elements whose
-// companion word keys[k * STRIDE + 1] equals `hi` take part (ties of the high word of a double, see below).
-template <int STRIDE, bool RESTRICT, int TOP_BIT>
-__device__ __forceinline__ uint32_t warp_select_u32(const uint32_t* keys, int n, int rank, uint32_t hi) {
-  const int lane = threadIdx.x & 31;
+// one group-wide count per probe.  key k lives at keys[k * STRIDE]; with RESTRICT only the elements whose companion word
+// keys[k * STRIDE + 1] equals `hi` take part (ties of the high word of a double, see below).
+template <int G, int STRIDE, bool RESTRICT, int TOP_BIT>
+__device__ __forceinline__ uint32_t group_select_u32(const uint32_t* keys, int n, int rank, uint32_t hi) {
+  const int lg = threadIdx.x & (G - 1);
   uint32_t prefix = 0u;
   for (int bit = TOP_BIT; bit >= 0; bit--) {
     const uint32_t trial = prefix | (1u << bit);
     int cnt = 0;
-    for (int k = lane; k < n; k += 32) {
+    for (int k = lg; k < n; k += G) {
       const bool in = !RESTRICT || keys[k * STRIDE + 1] == hi;
       cnt += (in && keys[k * STRIDE] < trial) ? 1 : 0;
     }
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    cnt = group_sum<G>(cnt);
     if (cnt <= rank) prefix = trial;
   }
   return prefix;
@@ -337,70 +480,69 @@ __device__ __forceinline__ uint32_t warp_select_u32(const uint32_t* keys, int n,
 // median = sorted[n/2]; a = (double)fabsf(res - median) (float truncation); MAD = sorted(a)[n/2].
 // Order statistics of non-negative IEEE values are order statistics of their bit patterns, so both selections run on
 // 32-bit integer keys: the median on the high words of the doubles (low words only among the elements that tie on the
-// high word), the MAD on the float patterns of `a`, staged once in `scratch` (n words).
-__device__ __forceinline__ double warp_stdv_mad(const double* res, int n, uint32_t* scratch) {
-  if (n == 0) return 0.0;
-  const int lane = threadIdx.x & 31;
+// high word), the MAD on the float patterns of `a`, staged once in `scratch` (n words).  n == 0 gives 0.
+template <int G>
+__device__ __forceinline__ double group_stdv_mad(const double* res, int n, uint32_t* scratch) {
+  const int lg = threadIdx.x & (G - 1);
   const uint32_t* w = reinterpret_cast<const uint32_t*>(res);  // little endian: w[2k] low word, w[2k+1] high word
   const int rank = n / 2;
-  const uint32_t hi = warp_select_u32<2, false, 30>(w + 1, n, rank, 0u);
+  const uint32_t hi = group_select_u32<G, 2, false, 30>(w + 1, n, rank, 0u);
   int below = 0, same = 0;
-  for (int k = lane; k < n; k += 32) {
+  uint32_t mine = 0u;
+  for (int k = lg; k < n; k += G) {
     below += w[2 * k + 1] < hi ? 1 : 0;
     same += w[2 * k + 1] == hi ? 1 : 0;
+    mine = w[2 * k + 1] == hi ? w[2 * k] : mine;
   }
-  below = __reduce_add_sync(0xffffffffu, below);
-  same = __reduce_add_sync(0xffffffffu, same);
-  uint32_t lo;
-  if (same == 1) {  // the usual case: the element with that high word is the median
-    uint32_t mine = 0u;
-    for (int k = lane; k < n; k += 32) mine = w[2 * k + 1] == hi ? w[2 * k] : mine;
-    lo = __reduce_max_sync(0xffffffffu, mine);
-  } else {
-    lo = warp_select_u32<2, true, 31>(w, n, rank - below, hi);
+  below = group_sum<G>(below);
+  same = group_sum<G>(same);
+  uint32_t lo = group_max<G>(mine);   // the usual case: one element has that high word and it is the median
+  const bool ties = n > 0 && same != 1;
+  if (__any_sync(0xffffffffu, ties)) {
+    const uint32_t lo2 = group_select_u32<G, 2, true, 31>(w, n, rank - below, hi);
+    if (ties) lo = lo2;
   }
   const double median = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
-  for (int k = lane; k < n; k += 32) scratch[k] = __float_as_uint(fabsf((float)(res[k] - median)));
+  for (int k = lg; k < n; k += G) scratch[k] = __float_as_uint(fabsf((float)(res[k] - median)));
   __syncwarp();
-  const uint32_t mad = warp_select_u32<1, false, 30>(scratch, n, rank, 0u);
+  const uint32_t mad = group_select_u32<G, 1, false, 30>(scratch, n, rank, 0u);
   __syncwarp();
-  return 1.4826 * (double)__uint_as_float(mad);
+  return n == 0 ? 0.0 : 1.4826 * (double)__uint_as_float(mad);
 }
 
 // removeOutliers (:2058-2116): returns the number of points / lines flagged
-__device__ __forceinline__ void warp_remove_outliers(const double* DT, const PairObs& o, const gfpl_camera& cam,
-                                     const gfpl_config& cfg, double* s_res, int* drop_pt, int* drop_ln) {
-  const int lane = threadIdx.x & 31;
+template <int G>
+__device__ __forceinline__ void group_remove_outliers(const double* DTs, const PairObs& o, bool alive, const gfpl_camera& cam,
+                                                      const gfpl_config& cfg, double* s_res, int* drop_pt, int* drop_ln) {
+  const int lg = threadIdx.x & (G - 1);
+  const int npt = alive ? o.npt : 0, nln = alive ? o.nln : 0;
   double* res_p = s_res;
-  double* res_l = s_res + o.npt;
-  for (int k = lane; k < o.npt; k += 32) {
+  double* res_l = s_res + npt;
+  double DT[16];
+  pose_load(DTs, DT);
+  for (int k = lg; k < npt; k += G) {
     double P_[3], d[2];
     const gfpl_pt_obs ob = o.pts[k];
     const double r = point_residual(DT, ob, cam, P_, d);
     res_p[k] = r * sqrt(ob.sigma2);
   }
-  for (int k = lane; k < o.nln; k += 32) {
+  for (int k = lg; k < nln; k += G) {
     double sP_[3], eP_[3], d[2];
     const gfpl_ln_obs ob = o.lns[k];
     const double r = line_residual(DT, ob, cam, sP_, eP_, d);
     res_l[k] = r * sqrt(ob.sigma2);
   }
   __syncwarp();
-  uint32_t* scratch = reinterpret_cast<uint32_t*>(s_res + o.npt + o.nln);  // [max(npt, nln)] words behind the residuals
-  const double th_p = cfg.inlier_k * warp_stdv_mad(res_p, o.npt, scratch);
-  const double th_l = cfg.inlier_k * warp_stdv_mad(res_l, o.nln, scratch);
+  uint32_t* scratch = reinterpret_cast<uint32_t*>(s_res + npt + nln);  // [max(npt, nln)] words behind the residuals
+  const double th_p = cfg.inlier_k * group_stdv_mad<G>(res_p, npt, scratch);
+  const double th_l = cfg.inlier_k * group_stdv_mad<G>(res_l, nln, scratch);
   int dp = 0, dl = 0;
-  for (int k = lane; k < o.npt; k += 32)
+  for (int k = lg; k < npt; k += G)
     if (res_p[k] > th_p) { o.pin[k] = 0; dp++; }
-  for (int k = lane; k < o.nln; k += 32)
+  for (int k = lg; k < nln; k += G)
     if (res_l[k] > th_l) { o.lin[k] = 0; dl++; }
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    dp += __shfl_xor_sync(0xffffffffu, dp, s);
-    dl += __shfl_xor_sync(0xffffffffu, dl, s);
-  }
-  *drop_pt = dp;
-  *drop_ln = dl;
+  *drop_pt = group_sum<G>(dp);
+  *drop_ln = group_sum<G>(dl);
   __syncwarp();
 }
 
@@ -440,69 +582,68 @@ __device__ __noinline__ void unccomp_se3(const double* T1, const double* covT1, 
 
 __host__ __device__ inline int pose_smem_doubles(int cap_pt, int cap_ln) { return cap_pt + cap_ln + (cap_pt + cap_ln + 1) / 2; }
 
-__global__ void __launch_bounds__(POSE_WARPS * 32, POSE_MIN_BLOCKS)
+template <int G>
+__global__ void __maxnreg__(POSE_MAX_REGS)
 pose_optimize_kernel(DevTrackObs obs, const gfpl_frame_state* __restrict__ state, const double* __restrict__ DT_ini,
                      int overload, PoseRaw* __restrict__ raw, gfpl_camera cam, gfpl_config cfg) {
-  extern __shared__ double s_res_all[];  // [POSE_WARPS][pose_smem_doubles(cap_pt, cap_ln)]
+  extern __shared__ double s_res_all[];  // [POSE_WARPS * 32 / G][pose_smem_doubles(cap_pt, cap_ln)]
+  constexpr int PER_WARP = 32 / G;
+  __shared__ double s_H[POSE_WARPS * PER_WARP][21];   // H of the last evaluation, per pair
+  __shared__ __align__(16) double s_DT[POSE_WARPS * PER_WARP][12];   // the pose under optimisation, per pair
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p = blockIdx.x * POSE_WARPS + warp;
-  if (p >= obs.B) return;
-  // per warp: cap_pt + cap_ln residuals, then (cap_pt + cap_ln) / 2 doubles = cap_pt + cap_ln words of select scratch
-  double* s_res = s_res_all + (size_t)warp * pose_smem_doubles(obs.cap_pt, obs.cap_ln);
+  const int slot = warp * PER_WARP + lane / G;                 // pair slot inside the CTA
+  if ((blockIdx.x * POSE_WARPS + warp) * PER_WARP >= obs.B) return;   // the whole warp is past the batch
+  const int p_slot = blockIdx.x * (POSE_WARPS * PER_WARP) + slot;
+  const bool exists = p_slot < obs.B;       // a group past the batch only takes part in the shuffles
+  const int p = exists ? p_slot : obs.B - 1;
+  // per pair: cap_pt + cap_ln residuals, then (cap_pt + cap_ln) / 2 doubles = cap_pt + cap_ln words of select scratch
+  double* s_res = s_res_all + (size_t)slot * pose_smem_doubles(obs.cap_pt, obs.cap_ln);
   PairObs o;
   o.npt = obs.n_pt[p]; o.nln = obs.n_ln[p];
   o.pts = obs.pt + (size_t)p * obs.cap_pt; o.pin = obs.pt_inlier + (size_t)p * obs.cap_pt;
   o.lns = obs.ln + (size_t)p * obs.cap_ln; o.lin = obs.ln_inlier + (size_t)p * obs.cap_ln;
   const gfpl_frame_state& st = state[p];
 
-  double DT[16], H[36], err = 0.0;
+  double DT[16], err = 0.0;
+  double* Hs = s_H[slot];
+  double* DTs = s_DT[slot];
   const double* seed = (overload == GFPL_POSE_SEED_GIVEN && DT_ini) ? DT_ini + (size_t)p * 16 : st.DT;
+  if ((lane & (G - 1)) == 0) {
 #pragma unroll
-  for (int i = 0; i < 16; i++) DT[i] = seed[i];
+    for (int i = 0; i < 21; i++) Hs[i] = 0.0;
+  }
   int n_inliers_pt = o.npt, n_inliers_ls = o.nln, n_inliers = o.npt + o.nln;
   int status = GFPL_POSE_OK, it1 = 0, it2 = 0;
   bool cov_from_H = false;  // DT_cov ends as H^-1 of the refinement or as zero (:1889-1906)
-  if (n_inliers > cfg.min_features) {
-    // two GN stages share one inlined loop body: stage 0 = first estimate on a copy (5 iterations) followed by
-    // the MAD outlier pass, stage 1 = refinement restarting from the seed (D8) (10 iterations)
-    double DTw[16];
-    for (int stage = 0; stage < 2; stage++) {
-#pragma unroll
-      for (int i = 0; i < 16; i++) DTw[i] = DT[i];
-      const int iters = warp_gauss_newton(DTw, o, cam, cfg, stage == 0 ? cfg.max_iters : cfg.max_iters_ref, H, &err);
-      if (stage == 1) {
-        it2 = iters;
-        cov_from_H = true;
-#pragma unroll
-        for (int i = 0; i < 16; i++) DT[i] = DTw[i];
-        break;
-      }
-      it1 = iters;
-      if (!is_finite16(DTw)) {
-        eye4(DT);
-        status |= GFPL_POSE_NONFINITE_1;
-        break;
-      }
-      int dp, dl;
-      warp_remove_outliers(DTw, o, cam, cfg, s_res, &dp, &dl);
+  bool alive = exists && n_inliers > cfg.min_features;
+  if (!alive) status |= GFPL_POSE_FEW_FEATURES;
+  // stage 0: first estimate on a copy of the seed (max_iters iterations), then the MAD outlier pass
+  pose_store(DTs, seed);
+  it1 = group_gauss_newton<G>(DTs, o, alive, cam, cfg, cfg.max_iters, Hs, &err);
+  pose_load(DTs, DT);
+  if (alive && !is_finite16(DT)) { status |= GFPL_POSE_NONFINITE_1; alive = false; }
+  {
+    int dp, dl;
+    group_remove_outliers<G>(DTs, o, alive, cam, cfg, s_res, &dp, &dl);
+    if (alive) {
       n_inliers_pt -= dp; n_inliers_ls -= dl; n_inliers -= dp + dl;
-      if (!(n_inliers > cfg.min_features)) {
-        eye4(DT);
-        status |= GFPL_POSE_FEW_INLIERS;
-        break;
-      }
+      if (!(n_inliers > cfg.min_features)) { status |= GFPL_POSE_FEW_INLIERS; alive = false; }
     }
-  } else {
-    eye4(DT);
-    status |= GFPL_POSE_FEW_FEATURES;
   }
+  // stage 1: refinement restarting from the seed (D8) (max_iters_ref iterations)
+  pose_store(DTs, seed);
+  it2 = group_gauss_newton<G>(DTs, o, alive, cam, cfg, cfg.max_iters_ref, Hs, &err);
+  if (alive) { cov_from_H = true; pose_load(DTs, DT); }
+  else eye4(DT);
 
-  if (lane != 0) return;
+  if ((lane & (G - 1)) != 0 || !exists) return;
   PoseRaw& w = raw[p];
 #pragma unroll
   for (int i = 0; i < 16; i++) w.DT[i] = DT[i];
 #pragma unroll
-  for (int i = 0; i < 36; i++) w.H[i] = H[i];
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j < 6; j++) w.H[i * 6 + j] = Hs[i >= j ? tri(i, j) : tri(j, i)];   // written by this lane
   w.err = err;
   w.status = status; w.cov_from_H = cov_from_H ? 1 : 0;
   w.n_inliers = n_inliers; w.n_inliers_pt = n_inliers_pt; w.n_inliers_ls = n_inliers_ls;
@@ -564,11 +705,12 @@ int launch_pose_optimize(gfpl_ctx* ctx, DevTrackObs obs, const gfpl_frame_state*
   // the hand-off buffer lives in the (stream-ordered) default pool; it is tiny: 456 B per pair
   PoseRaw* raw = nullptr;
   GFPL_CUDA_OK(ctx, cudaMallocAsync((void**)&raw, (size_t)obs.B * sizeof(PoseRaw), ctx->stream));
-  const size_t smem = (size_t)POSE_WARPS * pose_smem_doubles(obs.cap_pt, obs.cap_ln) * sizeof(double);
+  constexpr int G = POSE_GROUP, PAIRS_PER_CTA = POSE_WARPS * 32 / G;
+  const size_t smem = (size_t)PAIRS_PER_CTA * pose_smem_doubles(obs.cap_pt, obs.cap_ln) * sizeof(double);
   if (smem > 48 * 1024)
-    GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(pose_optimize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (obs.B + POSE_WARPS - 1) / POSE_WARPS;
-  pose_optimize_kernel<<<grid, POSE_WARPS * 32, smem, ctx->stream>>>(obs, state, DT_ini, overload, raw, ctx->cam, ctx->cfg);
+    GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(pose_optimize_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (obs.B + PAIRS_PER_CTA - 1) / PAIRS_PER_CTA;
+  pose_optimize_kernel<G><<<grid, POSE_WARPS * 32, smem, ctx->stream>>>(obs, state, DT_ini, overload, raw, ctx->cam, ctx->cfg);
   GFPL_LAUNCH_OK(ctx);
   pose_finalize_kernel<<<(obs.B + 127) / 128, 128, 0, ctx->stream>>>(obs.B, raw, state, overload, out, ctx->cfg);
   GFPL_LAUNCH_OK(ctx);
@@ -587,12 +729,18 @@ pose_hg_kernel(DevTrackObs obs, const double* __restrict__ DT_all, double* __res
   o.npt = obs.n_pt[p]; o.nln = obs.n_ln[p];
   o.pts = obs.pt + (size_t)p * obs.cap_pt; o.pin = obs.pt_inlier + (size_t)p * obs.cap_pt;
   o.lns = obs.ln + (size_t)p * obs.cap_ln; o.lin = obs.ln_inlier + (size_t)p * obs.cap_ln;
-  double DT[16], H[36], g[6], e;
-#pragma unroll
-  for (int i = 0; i < 16; i++) DT[i] = DT_all[(size_t)p * 16 + i];
-  warp_optimize_functions(DT, o, cam, cfg, H, g, &e);
+  __shared__ __align__(16) double s_DT[POSE_WARPS][12];
+  Acc a;
+  pose_store(s_DT[warp], DT_all + (size_t)p * 16);
+  group_optimize_functions<32>(s_DT[warp], o, true, cam, cfg, a);
+  const double* Hp = a.v;
+  const double* g = a.v + 21;
+  const double e = a.v[27];
   if (lane == 0) {
-    for (int i = 0; i < 36; i++) Hout[(size_t)p * 36 + i] = H[i];
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+      for (int j = 0; j < 6; j++) Hout[(size_t)p * 36 + i * 6 + j] = Hp[i >= j ? tri(i, j) : tri(j, i)];
     for (int i = 0; i < 6; i++) gout[(size_t)p * 6 + i] = g[i];
     eout[p] = e;
   }
