@@ -25,11 +25,14 @@ constexpr int POSE_WARPS = 2;
 #ifndef POSE_DT_SMEM
 #define POSE_DT_SMEM 1   // re-read the pose from shared memory per observation (0: let the compiler keep it in registers)
 #endif
+#ifndef POSE_DUAL
+#define POSE_DUAL 1
+#endif
 #ifndef POSE_PINGPONG
 #define POSE_PINGPONG 0
 #endif
 #ifndef POSE_MAX_REGS
-#define POSE_MAX_REGS 144  // 7 CTAs = 14 warps per SM: 8192 pairs at 2 pairs per warp are exactly two waves of 148 SMs
+#define POSE_MAX_REGS 168  // 6 CTAs = 12 warps per SM, nothing in local memory (144 = 14 warps: 0.92 ms against 0.89 ms)
 #endif
 
 // hand-off record between the GN kernel and the finalize kernel
@@ -293,24 +296,32 @@ __device__ __forceinline__ void pose_store(double* DTs, const double* T) {
   for (int i = 0; i < 12; i++) DTs[i] = T[i];
 }
 
-// point term (stereoFrameHandler.cpp:2131-2167) added to the partial sums
-__device__ __forceinline__ void point_term(const double* DTs, const gfpl_pt_obs& ob, const gfpl_camera& cam, const PoseConst& c,
-                                           Acc& a) {
-  double DT[16], P_[3], J[6];
+// point term (stereoFrameHandler.cpp:2131-2167): J (already divided by max(homog_th, r)), r and the weight.  Branch-free,
+// so that two observations evaluated back to back interleave in one basic block.  `on` false (outlier, or past the end
+// of the list) gives an all-zero term.
+__device__ __forceinline__ void point_front(const double* DTs, const gfpl_pt_obs& ob, bool on, const gfpl_camera& cam,
+                                            const PoseConst& c, double* J, double& r, double& w) {
+  double DT[16], P_[3];
   pose_load(DTs, DT);
   se3_apply(DT, ob.P, P_);
   const double iz = rcp_nr(P_[2]);
   const double dx = (cam.cx + cam.fx * P_[0] * iz) - ob.pl_obs[0];
   const double dy = (cam.cy + cam.fy * P_[1] * iz) - ob.pl_obs[1];
   const double s = dx * dx + dy * dy;
-  double fgz2 = cam.fx * iz * iz;                     // fx / max(homog_th, Z^2)
-  if (!(P_[2] * P_[2] > c.hth)) fgz2 = c.fx_over_hth;
-  double idn = rsqrt_nr(s), r = s * idn;              // r = |err|, idn = 1 / max(homog_th, r)
-  if (!(r > c.hth)) { r = sqrt(s); idn = c.inv_hth; }
+  const double fgz2 = (P_[2] * P_[2] > c.hth) ? cam.fx * iz * iz : c.fx_over_hth;   // fx / max(homog_th, Z^2)
+  const double rs = rsqrt_nr(s);
+  r = (s == 0.0) ? 0.0 : s * rs;                       // |err|
+  const double idn = (r > c.hth) ? rs : c.inv_hth;     // 1 / max(homog_th, r)
   jac6(fgz2, P_[0], P_[1], P_[2], dx, dy, J);
 #pragma unroll
-  for (int i = 0; i < 6; i++) J[i] = J[i] * idn;
-  const double w = rcp_nr(1.0 + s * ob.sigma2);
+  for (int i = 0; i < 6; i++) J[i] = on ? J[i] * idn : 0.0;
+  w = on ? rcp_nr(1.0 + s * ob.sigma2) : 0.0;
+  r = on ? r : 0.0;
+}
+__device__ __forceinline__ void point_term(const double* DTs, const gfpl_pt_obs& ob, const gfpl_camera& cam, const PoseConst& c,
+                                           Acc& a) {
+  double J[6], r, w;
+  point_front(DTs, ob, true, cam, c, J, r, w);
   acc_add(a, J, r, w);
 }
 
@@ -330,8 +341,9 @@ __device__ __forceinline__ void line_term(const double* DTs, const gfpl_ln_obs& 
   double ks = cam.fx * izs * izs, ke = cam.fx * ize * ize;
   if (!(sP_[2] * sP_[2] > c.hth)) ks = c.fx_over_hth;
   if (!(eP_[2] * eP_[2] > c.hth)) ke = c.fx_over_hth;
-  double idn = rsqrt_nr(s), r = s * idn;
-  if (!(r > c.hth)) { r = sqrt(s); idn = c.inv_hth; }
+  const double rs = rsqrt_nr(s);
+  const double r = (s == 0.0) ? 0.0 : s * rs;
+  const double idn = (r > c.hth) ? rs : c.inv_hth;
   jac6(ks, sP_[0], sP_[1], sP_[2], ob.le_obs[0], ob.le_obs[1], Js);
   jac6(ke, eP_[0], eP_[1], eP_[2], ob.le_obs[0], ob.le_obs[1], Je);
 #pragma unroll
@@ -353,7 +365,22 @@ __device__ __forceinline__ void group_optimize_functions(const double* DTs, cons
   for (int i = 0; i < 28; i++) a.v[i] = 0.0;
   int N = 0;
   {
-#if POSE_PINGPONG
+#if POSE_DUAL
+    // two observations per lane and round in one basic block: their dependency chains (transform, reciprocal, projection,
+    // reciprocal square root, Jacobian) interleave, which is where a latency-bound warp gets its instruction-level
+    // parallelism from; an observation that is an outlier or past the end contributes zeros
+    for (int k = lg; k < npt; k += 2 * G) {
+      const int k2 = (k + G < npt) ? k + G : k;
+      const gfpl_pt_obs A = o.pts[k], Bq = o.pts[k2];
+      const bool onA = o.pin[k] != 0, onB = (k + G < npt) && o.pin[k2] != 0;
+      double JA[6], JB[6], rA, rB, wA, wB;
+      point_front(DTs, A, onA, cam, c, JA, rA, wA);
+      point_front(DTs, Bq, onB, cam, c, JB, rB, wB);
+      acc_add(a, JA, rA, wA);
+      acc_add(a, JB, rB, wB);
+      N += (onA ? 1 : 0) + (onB ? 1 : 0);
+    }
+#elif POSE_PINGPONG
     // two observations in flight: the one after the next is loaded before the current one is evaluated, and the two
     // buffers swap roles in the unrolled body (no register copies)
     const gfpl_pt_obs* pp = o.pts + lg;
