@@ -358,7 +358,10 @@ def test_replay_matches_track_and_is_deterministic(ctx, orc):
         poses.append(pose.copy())
     assert poses[0].tobytes() == poses[1].tobytes()                    # run-to-run bit-reproducible
     assert poses[0].tobytes() == pg.tobytes()                          # resident path == host-pointer path
-    assert np.array_equal(obs.pt_inlier, og.pt_inlier)
+    assert np.array_equal(obs.n_pt, og.n_pt) and np.array_equal(obs.n_ln, og.n_ln)
+    for p in range(64):   # slots past n_pt / n_ln are never written on either path
+        assert np.array_equal(obs.pt_inlier[p, :obs.n_pt[p]], og.pt_inlier[p, :og.n_pt[p]])
+        assert np.array_equal(obs.ln_inlier[p, :obs.n_ln[p]], og.ln_inlier[p, :og.n_ln[p]])
     assert rp.h2d_bytes() > 0 and rp.d2h_bytes() > 0
     ms = rp.stage_ms()
     assert len(ms) == S.NUM_STAGES and ms[-1] > 0
