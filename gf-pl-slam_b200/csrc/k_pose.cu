@@ -452,6 +452,9 @@ __device__ __forceinline__ int group_gauss_newton(double* DTs /*shared, 12*/, co
     }
     bool go = act && !((fabs(err - err_prev) < cfg.min_error_change) || (err < cfg.min_error));
     const bool solved = ldlt6_solve_nopivot(a.v, a.v + 21, inc);
+    double DT[16];
+    pose_load(DTs, DT);
+    const bool upd = go;
     if (go) {
       if (!solved) {
         double Hm[36], gm[6], xm[6];
@@ -465,18 +468,19 @@ __device__ __forceinline__ int group_gauss_newton(double* DTs /*shared, 12*/, co
 #pragma unroll
         for (int i = 0; i < 6; i++) inc[i] = xm[i];
       }
-      double E[16], Ei[16], DT[16];
+      double E[16], Ei[16];
       expmap_se3(inc, E);
       inverse_se3(E, Ei);
-      pose_load(DTs, DT);
       matmul<4, 4, 4>(DT, Ei, DT);
-      pose_store(DTs, DT);
       double nrm = 0.0;
 #pragma unroll
       for (int i = 0; i < 6; i++) nrm = nrm + inc[i] * inc[i];
       if (sqrt(nrm) < 2.220446049250313e-16) go = false;
       else { err_prev = err; iters++; }
     }
+    __syncwarp();               // every lane of the group has read the pose before any lane replaces it
+    if (upd) pose_store(DTs, DT);
+    __syncwarp();
     act = go;
   }
   if (alive) *err_ = err;

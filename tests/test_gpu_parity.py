@@ -266,6 +266,47 @@ def test_linecut(ctx, orc, max_vol):
     assert flips <= (0 if max_vol else 2), f"{flips} pairs with differing cut decisions"
 
 
+@pytest.mark.parametrize("step,rng", [(0.1, (0.0, 1.0)), (0.02, (0.0, 1.0)), (0.3, (0.0, 1.0)), (0.05, (0.0, 0.35))])
+def test_linecut_other_steps_and_ranges(orc, step, rng):
+    """the half cache of the screening path is indexed by cut step: other step sizes (2..50 steps per axis) and a
+    range that clips the search must leave every decision as the oracle makes it"""
+    from gfpl import api
+    d = _data(6, 520)
+    cfg = api.default_config()
+    cfg.cut_step = step
+    cfg.cut_rng[0], cfg.cut_rng[1] = rng
+    c2 = api.Context(0, cam=d["cam"], cfg=cfg)
+    prev, curr, obs = _obs(orc, cfg, d)
+    cov = orc.stereo_uncertainty(d["cam"], cfg, prev)
+    DT_inv = _dt_inv(d["state"])
+    og, oo = obs.copy(), obs.copy()
+    cg = c2.linecut(DT_inv, og, cov)
+    co = orc.linecut(d["cam"], cfg, DT_inv, oo, cov)
+    moved = 0
+    for p in range(6):
+        n = obs.n_ln[p]
+        assert np.array_equal(cg["cutRatio"][p, :n], co["cutRatio"][p, :n]), f"cut decisions differ in pair {p}"
+        assert close(cg["invCovPose"][p, :n], co["invCovPose"][p, :n])
+        assert close(og.ln[p, :n]["sP"], oo.ln[p, :n]["sP"]) and close(og.ln[p, :n]["eP"], oo.ln[p, :n]["eP"])
+        assert (co["cutRatio"][p, :n] <= rng[1] + 1e-12).all()
+        moved += int((co["cutRatio"][p, :n] > 0).any())
+    assert moved > 0
+
+
+@pytest.mark.parametrize("B", [1, 2, 3, 5, 7])
+def test_pose_optimize_batch_tails(ctx, orc, B):
+    """two frame pairs share a warp and four a CTA: batches that leave lane groups, warps and CTAs partly empty"""
+    d = _data(B, 740 + B, ragged=True)
+    prev, curr, obs = _obs(orc, ctx.cfg, d)
+    og, oo = obs.copy(), obs.copy()
+    ini = d["state"]["DT"].copy()
+    pg = ctx.pose_optimize(og, d["state"], ini, S.POSE_SEED_GIVEN)
+    po = orc.pose_optimize(d["cam"], ctx.cfg, oo, d["state"], ini, S.POSE_SEED_GIVEN)
+    assert np.array_equal(pg["status"], po["status"])
+    assert np.array_equal(og.pt_inlier, oo.pt_inlier) and np.array_equal(og.ln_inlier, oo.ln_inlier)
+    _cmp_pose(pg, po, B)
+
+
 def test_pose_hg(ctx, orc):
     d = _data(16, 600, ragged=True)
     prev, curr, obs = _obs(orc, ctx.cfg, d)
