@@ -26,10 +26,15 @@ __device__ __forceinline__ uint32_t umma_idesc_i8(int n) {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 }
 
-// 4 descriptor bits -> 4 int8: bit set -> +1 (0x01), clear -> -1 (0xFF)
-__device__ __forceinline__ uint32_t expand_nibble(uint32_t nib) {
+// 4 descriptor bits -> 4 int8 of magnitude 64.  Train side (n): bit set -> +64 (0x40), clear -> -64 (0xC0); query side
+// (m): the negation.  A product of the two is then  -4096 * (256 - 2 * hamming) = 8192 * hamming - 2^20 : the accumulator
+// already is the sort key's distance field (hamming << 13), and the selection only adds the column index.
+constexpr int TC_KEY_SHIFT = 13;                 // accumulator = (hamming << 13) - 2^20; train rows per problem < 8192
+constexpr int TC_KEY_BIAS = 1 << 20;
+__device__ __forceinline__ uint32_t expand_nibble(uint32_t nib, bool negate) {
   const uint32_t t = (nib * 0x00204081u) & 0x01010101u;  // bit b of the nibble -> LSB of byte b
-  return t | ((t ^ 0x01010101u) * 255u);
+  const uint32_t set = negate ? (t ^ 0x01010101u) : t;   // bytes that become +64
+  return set * 0x40u + (set ^ 0x01010101u) * 0xC0u;
 }
 
 // one descriptor row (8 words, or zeros past the end) -> 16 chunks of 16 int8 in the UMMA layout.  lut[nibble] = its 4
@@ -84,7 +89,7 @@ __device__ __forceinline__ void expand_half_row(uint8_t* tile, int r, int h, con
 // `emit(m_row, k0, k1)`.
 template <bool TOP2, class Emit>
 __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base, int nm, const uint8_t* __restrict__ n_base,
-                                             int nn, uint8_t* sM, uint8_t* sN, const uint32_t* lut, uint64_t* bars /*[2]*/,
+                                             int nn, uint8_t* sM, uint8_t* sN, const uint32_t* lut /*[32]: train side, query side*/, uint64_t* bars /*[2]*/,
                                              uint32_t* phases /*[2]*/, uint32_t tmem, uint2* s_merge /*[TC_M]*/, Emit emit) {
   const int tid = threadIdx.x, warp = tid >> 5;
   const int row = tid & (TC_M - 1);     // m-row inside the tile = TMEM lane
@@ -143,13 +148,19 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
       const uint4 cur_row = next_row;
       if (m0 + TC_M < nm)
         next_row = __ldg(reinterpret_cast<const uint4*>(m_base + (size_t)min(mi + TC_M, nm - 1) * 32) + half);
-      expand_half_row(sM, row, half, cur_row, mi >= nm, lut);
+      expand_half_row(sM, row, half, cur_row, mi >= nm, lut + 16);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the MMA
     __syncthreads();
     if (tid == 0) issue(0);
-    // two independent selection chains (even / odd columns), merged after the last pass
-    uint32_t k0a = KEY_NONE, k1a = KEY_NONE, k0b = KEY_NONE, k1b = KEY_NONE;
+    // Two independent selection chains (even / odd columns), merged after the last pass.  Keys are signed and RELATIVE:
+    // key = accumulator + column - kbase, where kbase (the first column of the 16-column chunk being reduced) is
+    // subtracted from the running keys instead of being added to every new one — a new key is then `accumulator + jx`
+    // with jx a compile-time constant, which the add-min-max instruction (VIADDMNMX) fuses: 3 instructions per
+    // distance for the two nearest, 1 for the nearest.
+    constexpr int KNONE = 0x3FFFFFFF;          // stays above every real key (< 2^22) however often kbase moves
+    int k0a = KNONE, k1a = KNONE, k0b = KNONE, k1b = KNONE;
+    int kbase = 0;
     for (int pass = 0; pass < npass; pass++) {
       const int n0 = pass * TC_NPASS;
       const int N = min(TC_NPASS, nnp - n0);
@@ -163,22 +174,29 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
       const int nvalid = min(N, nn - n0);  // columns of this pass that are real train rows
       const uint32_t taddr = tlane + (uint32_t)((pass & 1) * TC_NPASS);
       uint32_t va[16], vb[16];
-      // key = (2 * hamming) << 19 | column = distance << 20 | column, with 2 * hamming = 256 - dot
       auto reduce16 = [&](const uint32_t* v, int c0) {
-        const uint32_t colbase = (uint32_t)(n0 + c0);
+        const int shift = (n0 + c0) - kbase;
+        kbase = n0 + c0;
+        k0a -= shift; k0b -= shift;
+        if (TOP2) { k1a -= shift; k1b -= shift; }
         if (c0 + 16 <= nvalid) {
 #pragma unroll
           for (int jx = 0; jx < 16; jx++) {
-            const uint32_t key = ((256u - v[jx]) << (KEY_IDX_BITS - 1)) + (colbase + jx);
-            if (TOP2) { if (jx & 1) top2_update(k0b, k1b, key); else top2_update(k0a, k1a, key); }
-            else { if (jx & 1) k0b = min(k0b, key); else k0a = min(k0a, key); }
+            const int acc = (int)v[jx];
+            if (TOP2) {
+              if (jx & 1) { k1b = min(k1b, max(acc + jx, k0b)); k0b = min(acc + jx, k0b); }
+              else { k1a = min(k1a, max(acc + jx, k0a)); k0a = min(acc + jx, k0a); }
+            } else {
+              if (jx & 1) k0b = min(acc + jx, k0b); else k0a = min(acc + jx, k0a);
+            }
           }
         } else {
 #pragma unroll
           for (int jx = 0; jx < 16; jx++) {
             if (c0 + jx < nvalid) {
-              const uint32_t key = ((256u - v[jx]) << (KEY_IDX_BITS - 1)) + (colbase + jx);
-              if (TOP2) top2_update(k0a, k1a, key); else k0a = min(k0a, key);
+              const int acc = (int)v[jx];
+              if (TOP2) { k1a = min(k1a, max(acc + jx, k0a)); k0a = min(acc + jx, k0a); }
+              else k0a = min(acc + jx, k0a);
             }
           }
         }
@@ -200,9 +218,15 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();  // this buffer is drained (pass + 2 may overwrite it); after the last pass sM is free as well
     }
-    uint32_t k0 = k0a, k1 = k1a;
-    if (TOP2) { top2_update(k0, k1, k0b); top2_update(k0, k1, k1b); }
-    else k0 = min(k0a, k0b);
+    // relative signed keys -> the packed keys of the integer kernels: distance << 20 | train row
+    auto canonical = [&](int k) -> uint32_t {
+      if (k >= (KNONE >> 1)) return KEY_NONE;
+      const uint32_t kabs = (uint32_t)(k + kbase + TC_KEY_BIAS);   // hamming << 13 | train row
+      return ((kabs >> TC_KEY_SHIFT) << KEY_IDX_BITS) | (kabs & ((1u << TC_KEY_SHIFT) - 1u));
+    };
+    uint32_t k0 = canonical(k0a), k1 = TOP2 ? canonical(k1a) : KEY_NONE;
+    if (TOP2) { top2_update(k0, k1, canonical(k0b)); top2_update(k0, k1, canonical(k1b)); }
+    else k0 = min(k0, canonical(k0b));
     if (half == 1) s_merge[row] = make_uint2(k0, k1);
     __syncthreads();
     const int mi = m0 + row;
@@ -220,7 +244,7 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
 struct TcShared {
   uint64_t bar[2];
   uint32_t tmem;
-  uint32_t lut[16];
+  uint32_t lut[32];   // nibble -> 4 int8: [0,16) train side, [16,32) query side (negated)
   uint2 merge[TC_M];
 };
 __device__ __forceinline__ uint32_t tc_begin(TcShared& S) {
@@ -234,7 +258,7 @@ __device__ __forceinline__ uint32_t tc_begin(TcShared& S) {
     mbar_init(&S.bar[1], 1);
     mbar_fence_init();
   }
-  if (tid < 16) S.lut[tid] = expand_nibble(tid);
+  if (tid < 32) S.lut[tid] = expand_nibble(tid & 15, tid >= 16);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
