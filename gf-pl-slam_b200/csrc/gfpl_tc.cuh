@@ -181,13 +181,18 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
         if (TOP2) { k1a -= shift; k1b -= shift; }
         if (c0 + 16 <= nvalid) {
 #pragma unroll
-          for (int jx = 0; jx < 16; jx++) {
-            const int acc = (int)v[jx];
+          for (int jx = 0; jx < 16; jx += 4) {   // DPX: fused add-min / add-max and three-input minimum
+            const int a0 = (int)v[jx], a1 = (int)v[jx + 1], a2 = (int)v[jx + 2], a3 = (int)v[jx + 3];
             if (TOP2) {
-              if (jx & 1) { k1b = min(k1b, max(acc + jx, k0b)); k0b = min(acc + jx, k0b); }
-              else { k1a = min(k1a, max(acc + jx, k0a)); k0a = min(acc + jx, k0a); }
+              const int ta0 = __viaddmax_s32(a0, jx, k0a);      k0a = __viaddmin_s32(a0, jx, k0a);
+              const int tb0 = __viaddmax_s32(a1, jx + 1, k0b);  k0b = __viaddmin_s32(a1, jx + 1, k0b);
+              const int ta1 = __viaddmax_s32(a2, jx + 2, k0a);  k0a = __viaddmin_s32(a2, jx + 2, k0a);
+              const int tb1 = __viaddmax_s32(a3, jx + 3, k0b);  k0b = __viaddmin_s32(a3, jx + 3, k0b);
+              k1a = __vimin3_s32(k1a, ta0, ta1);
+              k1b = __vimin3_s32(k1b, tb0, tb1);
             } else {
-              if (jx & 1) k0b = min(acc + jx, k0b); else k0a = min(acc + jx, k0a);
+              k0a = __viaddmin_s32(a0, jx, k0a);      k0b = __viaddmin_s32(a1, jx + 1, k0b);
+              k0a = __viaddmin_s32(a2, jx + 2, k0a);  k0b = __viaddmin_s32(a3, jx + 3, k0b);
             }
           }
         } else {
