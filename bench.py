@@ -361,10 +361,10 @@ def main():
             tensor_roof("f2f_hybrid_points_tc_kernel: radius + projection-gate search", pairs[2], 1, stage[3]) if tc_on
             else int_roof("f2f_hybrid_points_kernel", pairs[2], 5.0, 21.0, stage[3]),
             {"kernel": "linecut_kernel (+ stereo_uncertainty)", "bound": "fp64 latency", "kernel_ms": float(stage[6]),
-             "note": "sequential greedy search per pair; fp64 pipe ~27 % active, issue ~38 % (profiles/)"},
+             "note": "sequential greedy search per pair (8 lanes per pair, ~250 rounds of 8 candidates); one wave of 16 warps / SM, bound by the latency of the per-pair chain (profiles/)"},
             {"kernel": "pose_optimize_kernel (+ finalize)", "bound": "fp64 latency", "achieved": gn_flops / (stage[7] * 1e-3) / 1e12,
              "peak": fp64_peak, "unit": "TFLOP/s (fp64)", "frac": gn_flops / (stage[7] * 1e-3) / 1e12 / fp64_peak, "kernel_ms": float(stage[7]),
-             "note": "algorithmic flops = GN iterations x (114 per inlier point + 212 per inlier line); one warp per pair, serial 6x6 solve per iteration"},
+             "note": "algorithmic flops = GN iterations x (114 per inlier point + 212 per inlier line); 16 lanes per pair (two pairs per warp), serial 6x6 solve per iteration"},
         ]
         roofline = dict(by_kernel[0])
         alg_bytes = B * (2 * a.n_pt * 32 + 2 * a.n_pt * 16)
