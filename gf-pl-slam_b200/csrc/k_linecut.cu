@@ -339,6 +339,135 @@ __device__ __noinline__ void exact_info_store(const gfpl_camera* cam, const gfpl
   for (int e = j; e < 36; e += CUT_GROUP) invCovPose[e] = info_entry(I, e / 6, e % 6);
 }
 
+// The greedy search of one line (:1662-1763), out of line: its loop-carried state then has the register file to itself
+// (inlined in the kernel, part of it lived in local memory).  Returns the accepted cut {c0, c1}.
+__device__ __noinline__ double2 search_line(const gfpl_camera* cam, const gfpl_config* cfg, GroupState* G, int j, unsigned gmask,
+                                            bool fast_ok) {
+  const double step = cfg->cut_step, rng0 = cfg->cut_rng[0], rng1 = cfg->cut_rng[1];
+  const int d0 = (j == 0 || j == 4 || j == 5) ? 1 : ((j == 1 || j == 6 || j == 7) ? -1 : 0);   // neighbour j, in steps
+  const int d1 = (j == 2 || j == 4 || j == 6) ? 1 : ((j == 3 || j == 5 || j == 7) ? -1 : 0);
+  const double nb0 = d0 > 0 ? step : (d0 < 0 ? -step : 0.0), nb1 = d1 > 0 ? step : (d1 < 0 ? -step : 0.0);
+  double cur0 = 0.0, cur1 = 0.0;
+  int i0 = 0, i1 = 0;            // the same cut as integer multiples of the step (indices of the cached halves)
+  int lo0 = -1, hi0 = -1, lo1 = -1, hi1 = -1;   // cached index ranges [lo, hi) per axis, hi - lo <= HC_RING
+  double metric_last = 0.0;      // the reference's metric of the current cut; evaluated lazily (exact rounds only)
+  bool have_exact_last = false;
+  bool at_start = true;          // current cut is still {0,0}: its exact metric is logdet(sum0)
+  double dcur = 0.0;             // screening determinant factor of the current cut
+  bool have_dcur = false;
+  // The search alternates between a call-free loop of screened rounds (everything it carries stays in registers) and
+  // the rare out-of-line work it stops for: a refill of the half cache or a round in the reference's arithmetic.
+  enum { STOP, REFILL, EXACT };
+  for (;;) {
+    int why = STOP;
+    if (!fast_ok) why = (cur0 + cur1 <= 1.0) ? EXACT : STOP;
+    else
+      while (cur0 + cur1 <= 1.0) {
+        // a round reads the halves at index - 1, index, index + 1 of both axes
+        if (i0 - 1 < lo0 || i0 + 1 >= hi0 || i1 - 1 < lo1 || i1 + 1 >= hi1) { why = REFILL; break; }
+        const double ct0 = cur0 + nb0, ct1 = cur1 + nb1;
+        bool valid = !(ct0 + ct1 > 1.0);
+        valid = valid && !(ct0 < rng0 || ct0 > rng1);
+        valid = valid && !(ct1 < rng0 || ct1 > rng1);
+        // determinant factor of (si, ei): (1 + a u'S^-1u)(1 + b v'S^-1v) - a b (u'S^-1v)^2  (monotone in the metric)
+        auto factor = [&](int si, int ei) {
+          const double2* hs = reinterpret_cast<const double2*>(G->hc[0][si & (HC_RING - 1)]);
+          const double2* he = reinterpret_cast<const double2*>(G->hc[1][ei & (HC_RING - 1)]);
+          double guv = 0.0;
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            const double2 uu = hs[HC_VEC / 2 + i], ww = he[HC_VEC / 2 + i];
+            guv = fma(uu.x, ww.x, guv);
+            guv = fma(uu.y, ww.y, guv);
+          }
+          const double2 ags = hs[HC_A / 2], age = he[HC_A / 2];   // (a, g) of each half
+          const double a = ags.x, b = age.x;
+          return fma(-(a * b) * guv, guv, fma(a, ags.y, 1.0) * fma(b, age.y, 1.0));
+        };
+        const double dj = factor(i0 + d0, i1 + d1);                  // this lane's candidate
+        if (!have_dcur) { dcur = factor(i0, i1); have_dcur = true; }   // the current cut (same value in every lane)
+        // The reference keeps the first candidate (in j order) that is strictly better than everything before it,
+        // i.e. the arg-max with ties to the lowest j, or none if no candidate beats the current cut (:1722-1730).
+        // The factors decide that when the largest one is clear of every other candidate and of the current cut by
+        // more than CUT_TAU (relative), or when the current cut is clear of all candidates.  Usable factors are
+        // positive, so their order is the order of their bit patterns: the maximum is two 32-bit butterflies.
+        const bool usable = dj > 0.0 && dj < 1e300;
+        const unsigned hj = valid ? (unsigned)__double2hiint(dj) : 0u, lj = valid ? (unsigned)__double2loint(dj) : 0u;
+        unsigned mh = hj;
+#pragma unroll
+        for (int dlt = 1; dlt < CUT_GROUP; dlt <<= 1) mh = max(mh, __shfl_xor_sync(gmask, mh, dlt, CUT_GROUP));
+        unsigned ml = (hj == mh) ? lj : 0u;
+#pragma unroll
+        for (int dlt = 1; dlt < CUT_GROUP; dlt <<= 1) ml = max(ml, __shfl_xor_sync(gmask, ml, dlt, CUT_GROUP));
+        const double best = __hiloint2double((int)mh, (int)ml);   // largest candidate factor (0: no valid candidate)
+        // flags of this lane: bit j = "I am the maximum", bit 8 = a factor that cannot be used, bit 9 = too close to it
+        const bool is_max = valid && hj == mh && lj == ml;
+        unsigned fl = is_max ? (1u << j) : 0u;
+        if (valid && !usable) fl |= 1u << 8;
+        if (valid && !is_max && !(best - dj > CUT_TAU * best)) fl |= 1u << 9;
+#pragma unroll
+        for (int dlt = 1; dlt < CUT_GROUP; dlt <<= 1) fl |= __shfl_xor_sync(gmask, fl, dlt, CUT_GROUP);
+        const bool sane = dcur > 0.0 && dcur < 1e300 && !(fl & (1u << 8)) && !(best >= 1e300);
+        const unsigned winners = fl & 0xFFu;
+        int cand;
+        if (sane && best - dcur > CUT_TAU * best && !(fl & (1u << 9)) && (winners & (winners - 1u)) == 0u)
+          cand = __ffs(winners) - 1;                         // one candidate is clearly the best
+        else if (sane && dcur - best > CUT_TAU * dcur) break;  // every candidate is clearly worse: the search stops (STOP)
+        else { why = EXACT; break; }
+        have_exact_last = false; dcur = best;
+        // the winner's cut: the same additions lane `cand` made (cur + nb), so every lane can make them itself
+        const int c0d = (int)((0xA52u >> (2 * cand)) & 3u) - 1, c1d = (int)((0x2225u >> (2 * cand)) & 3u) - 1;
+        cur0 = cur0 + (c0d > 0 ? step : (c0d < 0 ? -step : 0.0));
+        cur1 = cur1 + (c1d > 0 ? step : (c1d < 0 ? -step : 0.0));
+        i0 += c0d; i1 += c1d;
+        at_start = false;
+      }
+    if (why == STOP) break;
+    if (why == REFILL) {
+      // per axis: append HC_CHUNK indices at hi (if that does not evict index - 1), or restart the range at index - 1
+      int b0 = hi0, b1 = hi1;
+      bool go0 = true, go1 = true;
+      if (i0 - 1 < lo0 || i0 - 1 > hi0) { lo0 = i0 - 1; b0 = lo0; }
+      else if (hi0 + HC_CHUNK - HC_RING > i0 - 1) go0 = false;
+      if (i1 - 1 < lo1 || i1 - 1 > hi1) { lo1 = i1 - 1; b1 = lo1; }
+      else if (hi1 + HC_CHUNK - HC_RING > i1 - 1) go1 = false;
+      fill_halves(cam, cfg, G, j, b0, b1, go0, go1, step);
+      if (go0) { hi0 = b0 + HC_CHUNK; lo0 = max(lo0, hi0 - HC_RING); }
+      if (go1) { hi1 = b1 + HC_CHUNK; lo1 = max(lo1, hi1 - HC_RING); }
+      __syncwarp(gmask);
+      continue;
+    }
+    // exact round: the reference's arithmetic (also the only path for the min-eigenvalue metric)
+    const double ct0 = cur0 + nb0, ct1 = cur1 + nb1;
+    bool valid = !(ct0 + ct1 > 1.0);
+    valid = valid && !(ct0 < rng0 || ct0 > rng1);
+    valid = valid && !(ct1 < rng0 || ct1 > rng1);
+    if (!have_exact_last) {  // metric of the current cut, needed as the running best
+      metric_last = at_start ? exact_metric_start(cfg, G) : exact_metric_at(cam, cfg, G, cur0, cur1);
+      have_exact_last = true;
+    }
+    const double metric = valid ? exact_metric_at(cam, cfg, G, ct0, ct1) : 0.0;
+    // "first strictly better in j order" (:1722-1730)
+    int cand = -1;
+    double best = metric_last;
+#pragma unroll
+    for (int jj = 0; jj < CUT_GROUP; jj++) {
+      const double mj = shfl_f64(gmask, metric, jj, CUT_GROUP);
+      const int vj = __shfl_sync(gmask, (int)valid, jj, CUT_GROUP);
+      if (vj && mj > best) { best = mj; cand = jj; }
+    }
+    metric_last = best;
+    have_dcur = false;   // the screening factor of the new current cut is re-evaluated next round
+    if (cand < 0) break;  // early termination (:1741-1743)
+    const int c0d = (int)((0xA52u >> (2 * cand)) & 3u) - 1, c1d = (int)((0x2225u >> (2 * cand)) & 3u) - 1;
+    cur0 = cur0 + (c0d > 0 ? step : (c0d < 0 ? -step : 0.0));
+    cur1 = cur1 + (c1d > 0 ? step : (c1d < 0 ? -step : 0.0));
+    i0 += c0d; i1 += c1d;
+    at_start = false;
+  }
+  return make_double2(cur0, cur1);
+}
+
 __global__ void __maxnreg__(CUT_MAX_REGS)
 linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __restrict__ state, DevTrackObs obs,
                const gfpl_line_cov* __restrict__ prev_cov, int cov_cap, gfpl_line_cut* __restrict__ cut_all,
@@ -381,28 +510,24 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
   }
   __syncwarp(gmask);
 
-  const double step = cfg.cut_step;
-  const double nb0 = (j == 0 || j == 4 || j == 5) ? step : ((j == 1 || j == 6 || j == 7) ? -step : 0.0);
-  const double nb1 = (j == 2 || j == 4 || j == 6) ? step : ((j == 3 || j == 5 || j == 7) ? -step : 0.0);
-  const int d0 = (j == 0 || j == 4 || j == 5) ? 1 : ((j == 1 || j == 6 || j == 7) ? -1 : 0);   // the same in steps
-  const int d1 = (j == 2 || j == 4 || j == 6) ? 1 : ((j == 3 || j == 5 || j == 7) ? -1 : 0);
-
   // pass 1a: initial information of every line (cut = 0), lanes stride over the lines (:1638-1649)
   for (int l = j; l < nln; l += CUT_GROUP) exact_info_initial(&s_cam, &s_cfg, G.DT, &lns[l], &cov[lns[l].prev_idx], &cut[l]);
   __syncwarp(gmask);
 
   // pass 1b/2: invCov_sum in the reference's order — lines, then points, each element summed sequentially.
   // Lane j owns lower-triangle elements e = j, j+8, j+16.
-  {
-    int ea[3], eb[3];
-    double acc[3] = {0.0, 0.0, 0.0};
+  // lane j owns the lower-triangle elements e = j, j + 8, j + 16 of the 6x6 sums: (row, column) of each, once per kernel
+  int ea[3], eb[3];
 #pragma unroll
-    for (int q = 0; q < 3; q++) {
-      const int e = min(j + 8 * q, 20);
-      int a = 0;
-      while ((a + 1) * (a + 2) / 2 <= e) a++;
-      ea[q] = a; eb[q] = e - a * (a + 1) / 2;
-    }
+  for (int q = 0; q < 3; q++) {
+    const int e = min(j + 8 * q, 20);
+    int a = 0;
+#pragma unroll
+    for (int t = 1; t < 6; t++) a += ((t * (t + 1)) / 2 <= e) ? 1 : 0;
+    ea[q] = a; eb[q] = e - a * (a + 1) / 2;
+  }
+  {
+    double acc[3] = {0.0, 0.0, 0.0};
     for (int l = 0; l < nln; l++) {
       const double* info = cut[l].invCovPose;
 #pragma unroll
@@ -459,12 +584,13 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
     __syncwarp(gmask);
     {
       const double* info = C.invCovPose;
-      for (int e = j; e < 21; e += CUT_GROUP) {
-        int a = 0;
-        while ((a + 1) * (a + 2) / 2 <= e) a++;
-        const int b = e - a * (a + 1) / 2;
-        G.sum0[e] = G.sum[e];
-        G.sum[e] = G.sum[e] - info[a * 6 + b];
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        const int e = j + 8 * q;
+        if (e < 21) {
+          G.sum0[e] = G.sum[e];
+          G.sum[e] = G.sum[e] - info[ea[q] * 6 + eb[q]];
+        }
       }
     }
     __syncwarp(gmask);
@@ -472,124 +598,8 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
     bool fast_ok = cfg.max_vol_line_cut != 0;
     if (fast_ok) fast_ok = spd_inverse6_publish(&G, j, gmask);
     __syncwarp(gmask);
-    double cur0 = 0.0, cur1 = 0.0;
-    int i0 = 0, i1 = 0;            // the same cut as integer multiples of the step (indices of the cached halves)
-    int lo0 = -1, hi0 = -1, lo1 = -1, hi1 = -1;   // cached index ranges [lo, hi) per axis, hi - lo <= HC_RING
-    double metric_last = 0.0;      // the reference's metric of the current cut; evaluated lazily (exact rounds only)
-    bool have_exact_last = false;
-    bool at_start = true;          // current cut is still {0,0}: its exact metric is logdet(sum0)
-    double dcur = 0.0;             // screening determinant factor of the current cut
-    bool have_dcur = false;
-    // The search alternates between a call-free loop of screened rounds (everything it carries stays in registers) and
-    // the rare out-of-line work it stops for: a refill of the half cache or a round in the reference's arithmetic.
-    enum { STOP, REFILL, EXACT };
-    for (;;) {
-      int why = STOP;
-      if (!fast_ok) why = (cur0 + cur1 <= 1.0) ? EXACT : STOP;
-      else
-        while (cur0 + cur1 <= 1.0) {
-          // a round reads the halves at index - 1, index, index + 1 of both axes
-          if (i0 - 1 < lo0 || i0 + 1 >= hi0 || i1 - 1 < lo1 || i1 + 1 >= hi1) { why = REFILL; break; }
-          const double ct0 = cur0 + nb0, ct1 = cur1 + nb1;
-          bool valid = !(ct0 + ct1 > 1.0);
-          valid = valid && !(ct0 < cfg.cut_rng[0] || ct0 > cfg.cut_rng[1]);
-          valid = valid && !(ct1 < cfg.cut_rng[0] || ct1 > cfg.cut_rng[1]);
-          // determinant factor of (si, ei): (1 + a u'S^-1u)(1 + b v'S^-1v) - a b (u'S^-1v)^2  (monotone in the metric)
-          auto factor = [&](int si, int ei) {
-            const double2* hs = reinterpret_cast<const double2*>(G.hc[0][si & (HC_RING - 1)]);
-            const double2* he = reinterpret_cast<const double2*>(G.hc[1][ei & (HC_RING - 1)]);
-            double guv = 0.0;
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-              const double2 uu = hs[HC_VEC / 2 + i], ww = he[HC_VEC / 2 + i];
-              guv = fma(uu.x, ww.x, guv);
-              guv = fma(uu.y, ww.y, guv);
-            }
-            const double2 ags = hs[HC_A / 2], age = he[HC_A / 2];   // (a, g) of each half
-            const double a = ags.x, b = age.x;
-            return fma(-(a * b) * guv, guv, fma(a, ags.y, 1.0) * fma(b, age.y, 1.0));
-          };
-          const double dj = factor(i0 + d0, i1 + d1);                  // this lane's candidate
-          if (!have_dcur) { dcur = factor(i0, i1); have_dcur = true; }   // the current cut (same value in every lane)
-          // The reference keeps the first candidate (in j order) that is strictly better than everything before it,
-          // i.e. the arg-max with ties to the lowest j, or none if no candidate beats the current cut (:1722-1730).
-          // The factors decide that when the largest one is clear of every other candidate and of the current cut by
-          // more than CUT_TAU (relative), or when the current cut is clear of all candidates.  Usable factors are
-          // positive, so their order is the order of their bit patterns: the maximum is two 32-bit butterflies.
-          const bool usable = dj > 0.0 && dj < 1e300;
-          const unsigned hj = valid ? (unsigned)__double2hiint(dj) : 0u, lj = valid ? (unsigned)__double2loint(dj) : 0u;
-          unsigned mh = hj;
-#pragma unroll
-          for (int dlt = 1; dlt < CUT_GROUP; dlt <<= 1) mh = max(mh, __shfl_xor_sync(gmask, mh, dlt, CUT_GROUP));
-          unsigned ml = (hj == mh) ? lj : 0u;
-#pragma unroll
-          for (int dlt = 1; dlt < CUT_GROUP; dlt <<= 1) ml = max(ml, __shfl_xor_sync(gmask, ml, dlt, CUT_GROUP));
-          const double best = __hiloint2double((int)mh, (int)ml);   // largest candidate factor (0: no valid candidate)
-          // flags of this lane: bit j = "I am the maximum", bit 8 = a factor that cannot be used, bit 9 = too close to it
-          const bool is_max = valid && hj == mh && lj == ml;
-          unsigned fl = is_max ? (1u << j) : 0u;
-          if (valid && !usable) fl |= 1u << 8;
-          if (valid && !is_max && !(best - dj > CUT_TAU * best)) fl |= 1u << 9;
-#pragma unroll
-          for (int dlt = 1; dlt < CUT_GROUP; dlt <<= 1) fl |= __shfl_xor_sync(gmask, fl, dlt, CUT_GROUP);
-          const bool sane = dcur > 0.0 && dcur < 1e300 && !(fl & (1u << 8)) && !(best >= 1e300);
-          const unsigned winners = fl & 0xFFu;
-          int cand;
-          if (sane && best - dcur > CUT_TAU * best && !(fl & (1u << 9)) && (winners & (winners - 1u)) == 0u)
-            cand = __ffs(winners) - 1;                         // one candidate is clearly the best
-          else if (sane && dcur - best > CUT_TAU * dcur) break;  // every candidate is clearly worse: the search stops (STOP)
-          else { why = EXACT; break; }
-          have_exact_last = false; dcur = best;
-          // the winner's cut: the same additions lane `cand` made (cur + nb), so every lane can make them itself
-          const int c0d = (int)((0xA52u >> (2 * cand)) & 3u) - 1, c1d = (int)((0x2225u >> (2 * cand)) & 3u) - 1;
-          cur0 = cur0 + (c0d > 0 ? step : (c0d < 0 ? -step : 0.0));
-          cur1 = cur1 + (c1d > 0 ? step : (c1d < 0 ? -step : 0.0));
-          i0 += c0d; i1 += c1d;
-          at_start = false;
-        }
-      if (why == STOP) break;
-      if (why == REFILL) {
-        // per axis: append HC_CHUNK indices at hi (if that does not evict index - 1), or restart the range at index - 1
-        int b0 = hi0, b1 = hi1;
-        bool go0 = true, go1 = true;
-        if (i0 - 1 < lo0 || i0 - 1 > hi0) { lo0 = i0 - 1; b0 = lo0; }
-        else if (hi0 + HC_CHUNK - HC_RING > i0 - 1) go0 = false;
-        if (i1 - 1 < lo1 || i1 - 1 > hi1) { lo1 = i1 - 1; b1 = lo1; }
-        else if (hi1 + HC_CHUNK - HC_RING > i1 - 1) go1 = false;
-        fill_halves(&s_cam, &s_cfg, &G, j, b0, b1, go0, go1, step);
-        if (go0) { hi0 = b0 + HC_CHUNK; lo0 = max(lo0, hi0 - HC_RING); }
-        if (go1) { hi1 = b1 + HC_CHUNK; lo1 = max(lo1, hi1 - HC_RING); }
-        __syncwarp(gmask);
-        continue;
-      }
-      // exact round: the reference's arithmetic (also the only path for the min-eigenvalue metric)
-      const double ct0 = cur0 + nb0, ct1 = cur1 + nb1;
-      bool valid = !(ct0 + ct1 > 1.0);
-      valid = valid && !(ct0 < cfg.cut_rng[0] || ct0 > cfg.cut_rng[1]);
-      valid = valid && !(ct1 < cfg.cut_rng[0] || ct1 > cfg.cut_rng[1]);
-      if (!have_exact_last) {  // metric of the current cut, needed as the running best
-        metric_last = at_start ? exact_metric_start(&s_cfg, &G) : exact_metric_at(&s_cam, &s_cfg, &G, cur0, cur1);
-        have_exact_last = true;
-      }
-      const double metric = valid ? exact_metric_at(&s_cam, &s_cfg, &G, ct0, ct1) : 0.0;
-      // "first strictly better in j order" (:1722-1730)
-      int cand = -1;
-      double best = metric_last;
-#pragma unroll
-      for (int jj = 0; jj < CUT_GROUP; jj++) {
-        const double mj = shfl_f64(gmask, metric, jj, CUT_GROUP);
-        const int vj = __shfl_sync(gmask, (int)valid, jj, CUT_GROUP);
-        if (vj && mj > best) { best = mj; cand = jj; }
-      }
-      metric_last = best;
-      have_dcur = false;   // the screening factor of the new current cut is re-evaluated next round
-      if (cand < 0) break;  // early termination (:1741-1743)
-      const int c0d = (int)((0xA52u >> (2 * cand)) & 3u) - 1, c1d = (int)((0x2225u >> (2 * cand)) & 3u) - 1;
-      cur0 = cur0 + (c0d > 0 ? step : (c0d < 0 ? -step : 0.0));
-      cur1 = cur1 + (c1d > 0 ? step : (c1d < 0 ? -step : 0.0));
-      i0 += c0d; i1 += c1d;
-      at_start = false;
-    }
+    const double2 cr = search_line(&s_cam, &s_cfg, &G, j, gmask, fast_ok);
+    const double cur0 = cr.x, cur1 = cr.y;
     // invCovPose of the accepted cut, in the reference's arithmetic (cut {0,0} is already stored by pass 1)
     if (cur0 != 0.0 || cur1 != 0.0) exact_info_store(&s_cam, &s_cfg, &G, cur0, cur1, j, gmask, C.invCovPose);
     __syncwarp(gmask);
@@ -621,11 +631,10 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
     }
     {
       const double* info = C.invCovPose;
-      for (int e = j; e < 21; e += CUT_GROUP) {
-        int a = 0;
-        while ((a + 1) * (a + 2) / 2 <= e) a++;
-        const int b = e - a * (a + 1) / 2;
-        G.sum[e] = G.sum[e] + info[a * 6 + b];
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        const int e = j + 8 * q;
+        if (e < 21) G.sum[e] = G.sum[e] + info[ea[q] * 6 + eb[q]];
       }
     }
     __syncwarp(gmask);
