@@ -18,7 +18,10 @@
 
 namespace gfpl {
 
-constexpr int POSE_WARPS = 2;
+#ifndef POSE_WARPS_N
+#define POSE_WARPS_N 2
+#endif
+constexpr int POSE_WARPS = POSE_WARPS_N;
 #ifndef POSE_GROUP
 #define POSE_GROUP 16     // lanes per frame pair
 #endif
