@@ -25,15 +25,6 @@ constexpr int POSE_WARPS = POSE_WARPS_N;
 #ifndef POSE_GROUP
 #define POSE_GROUP 16     // lanes per frame pair
 #endif
-#ifndef POSE_DT_SMEM
-#define POSE_DT_SMEM 1   // re-read the pose from shared memory per observation (0: let the compiler keep it in registers)
-#endif
-#ifndef POSE_DUAL
-#define POSE_DUAL 1
-#endif
-#ifndef POSE_PINGPONG
-#define POSE_PINGPONG 0
-#endif
 #ifndef POSE_MAX_REGS
 #define POSE_MAX_REGS 168  // 6 CTAs = 12 warps per SM, nothing in local memory (144 = 14 warps: 0.92 ms against 0.89 ms)
 #endif
@@ -106,96 +97,6 @@ __device__ __forceinline__ double line_residual(const double* DT, const gfpl_ln_
   return sqrt(dse[0] * dse[0] + dse[1] * dse[1]);
 }
 
-
-// ---- LDLT<Matrix6d>(H).solve(g) in registers ------------------------------------------------------------
-// Same algorithm as Eigen's ldlt_inplace<Lower>::unblocked (largest |diagonal| pivot, left-looking update,
-// D^-1 with a zero-pivot guard) but fully unrolled: the runtime pivot index is applied with predicated
-// swaps, so nothing is indexed dynamically and nothing spills to local memory.
-__device__ __forceinline__ void swap_rc(double* A, int* perm, int k, int p, bool doit) {
-#pragma unroll
-  for (int j = 0; j < 6; j++) {
-    const double a = A[k * 6 + j], b = A[p * 6 + j];
-    A[k * 6 + j] = doit ? b : a;
-    A[p * 6 + j] = doit ? a : b;
-  }
-#pragma unroll
-  for (int i = 0; i < 6; i++) {
-    const double a = A[i * 6 + k], b = A[i * 6 + p];
-    A[i * 6 + k] = doit ? b : a;
-    A[i * 6 + p] = doit ? a : b;
-  }
-  const int pa = perm[k], pb = perm[p];
-  perm[k] = doit ? pb : pa;
-  perm[p] = doit ? pa : pb;
-}
-
-__device__ __forceinline__ void ldlt6_solve_reg(const double* Hin, const double* g, double* x) {
-  double A[36];
-  int perm[6];
-#pragma unroll
-  for (int i = 0; i < 36; i++) A[i] = Hin[i];
-#pragma unroll
-  for (int i = 0; i < 6; i++) perm[i] = i;
-#pragma unroll
-  for (int k = 0; k < 6; k++) {
-    int p = k;
-    double best = fabs(A[k * 6 + k]);
-#pragma unroll
-    for (int i = k + 1; i < 6; i++) {
-      const double v = fabs(A[i * 6 + i]);
-      if (v > best) { best = v; p = i; }
-    }
-#pragma unroll
-    for (int pp = k + 1; pp < 6; pp++) swap_rc(A, perm, k, pp, p == pp);
-    double temp[6];
-#pragma unroll
-    for (int j = 0; j < k; j++) temp[j] = A[j * 6 + j] * A[k * 6 + j];
-    if (k > 0) {
-      double dot = A[k * 6 + 0] * temp[0];
-#pragma unroll
-      for (int j = 1; j < k; j++) dot = dot + A[k * 6 + j] * temp[j];
-      A[k * 6 + k] = A[k * 6 + k] - dot;
-    }
-    const double d = A[k * 6 + k];
-#pragma unroll
-    for (int i = k + 1; i < 6; i++) {
-      double sv = A[i * 6 + k];
-      if (k > 0) {
-        double dot = A[i * 6 + 0] * temp[0];
-#pragma unroll
-        for (int j = 1; j < k; j++) dot = dot + A[i * 6 + j] * temp[j];
-        sv = sv - dot;
-      }
-      A[i * 6 + k] = (fabs(d) > 0.0) ? sv / d : sv;
-    }
-  }
-  double y[6];
-#pragma unroll
-  for (int i = 0; i < 6; i++) {
-    double v = 0.0;
-#pragma unroll
-    for (int j = 0; j < 6; j++) v = (perm[i] == j) ? g[j] : v;
-    y[i] = v;
-  }
-#pragma unroll
-  for (int i = 0; i < 6; i++)
-#pragma unroll
-    for (int j = 0; j < i; j++) y[i] = y[i] - A[i * 6 + j] * y[j];
-  const double tol = 1.0 / 1.7976931348623157e308;
-#pragma unroll
-  for (int i = 0; i < 6; i++) y[i] = (fabs(A[i * 6 + i]) > tol) ? y[i] / A[i * 6 + i] : 0.0;
-#pragma unroll
-  for (int i = 5; i >= 0; i--)
-#pragma unroll
-    for (int j = i + 1; j < 6; j++) y[i] = y[i] - A[j * 6 + i] * y[j];
-#pragma unroll
-  for (int j = 0; j < 6; j++) {
-    double v = 0.0;
-#pragma unroll
-    for (int i = 0; i < 6; i++) v = (perm[i] == j) ? y[i] : v;
-    x[j] = v;
-  }
-}
 
 // H is symmetric positive definite whenever the pose is observable, and then the pivoted and the unpivoted LDL^T are the
 // same solve up to rounding (both backward stable; this translation unit is compared at 1e-9).  The unpivoted
@@ -287,11 +188,7 @@ __device__ __forceinline__ void pose_load(const double* DTs, double* T /*16*/) {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(DTs);
 #pragma unroll
   for (int i = 0; i < 6; i++)
-#if POSE_DT_SMEM
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(T[2 * i]), "=d"(T[2 * i + 1]) : "r"(a + 16u * i));
-#else
-    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(T[2 * i]), "=d"(T[2 * i + 1]) : "r"(a + 16u * i));
-#endif
   T[12] = 0.0; T[13] = 0.0; T[14] = 0.0; T[15] = 1.0;   // poses are SE(3)
 }
 __device__ __forceinline__ void pose_store(double* DTs, const double* T) {
@@ -321,13 +218,6 @@ __device__ __forceinline__ void point_front(const double* DTs, const gfpl_pt_obs
   w = on ? rcp_nr(1.0 + s * ob.sigma2) : 0.0;
   r = on ? r : 0.0;
 }
-__device__ __forceinline__ void point_term(const double* DTs, const gfpl_pt_obs& ob, const gfpl_camera& cam, const PoseConst& c,
-                                           Acc& a) {
-  double J[6], r, w;
-  point_front(DTs, ob, true, cam, c, J, r, w);
-  acc_add(a, J, r, w);
-}
-
 // line term (:2171-2235)
 __device__ __forceinline__ void line_term(const double* DTs, const gfpl_ln_obs& ob, const gfpl_camera& cam, const PoseConst& c,
                                           Acc& a) {
@@ -368,7 +258,6 @@ __device__ __forceinline__ void group_optimize_functions(const double* DTs, cons
   for (int i = 0; i < 28; i++) a.v[i] = 0.0;
   int N = 0;
   {
-#if POSE_DUAL
     // two observations per lane and round in one basic block: their dependency chains (transform, reciprocal, projection,
     // reciprocal square root, Jacobian) interleave, which is where a latency-bound warp gets its instruction-level
     // parallelism from; an observation that is an outlier or past the end contributes zeros
@@ -383,34 +272,6 @@ __device__ __forceinline__ void group_optimize_functions(const double* DTs, cons
       acc_add(a, JB, rB, wB);
       N += (onA ? 1 : 0) + (onB ? 1 : 0);
     }
-#elif POSE_PINGPONG
-    // two observations in flight: the one after the next is loaded before the current one is evaluated, and the two
-    // buffers swap roles in the unrolled body (no register copies)
-    const gfpl_pt_obs* pp = o.pts + lg;
-    const uint8_t* pi = o.pin + lg;
-    gfpl_pt_obs A{}, Bq{};
-    uint8_t ia = 0, ib = 0;
-    if (lg < npt) { A = pp[0]; ia = pi[0]; }
-    for (int k = lg; k < npt; k += 2 * G, pp += 2 * G, pi += 2 * G) {
-      ib = 0;
-      if (k + G < npt) { Bq = pp[G]; ib = pi[G]; }
-      if (ia) { point_term(DTs, A, cam, c, a); N++; }
-      ia = 0;
-      if (k + 2 * G < npt) { A = pp[2 * G]; ia = pi[2 * G]; }
-      if (ib) { point_term(DTs, Bq, cam, c, a); N++; }
-    }
-#else
-    // no software prefetch: the observation lists sit in L1 after the first iteration, and the registers a second
-    // buffer would take are what keeps the partial sums out of local memory at 14 warps per SM
-    const gfpl_pt_obs* pp = o.pts + lg;
-    const uint8_t* pi = o.pin + lg;
-    for (int k = lg; k < npt; k += G, pp += G, pi += G) {
-      if (!*pi) continue;
-      const gfpl_pt_obs ob = *pp;
-      point_term(DTs, ob, cam, c, a);
-      N++;
-    }
-#endif
   }
   for (int k = lg; k < nln; k += G) {
     if (!o.lin[k]) continue;

@@ -79,7 +79,7 @@ __device__ __forceinline__ double line_segment_overlap_stereo(double spl_obs, do
 }
 
 // analytic endpoint covariance and its largest eigenvalue (stereoFrame.cpp:956-998)
-__device__ double endpoint_cov_max_eig(const gfpl_camera& cam, double px, double py, double disp) {
+__device__ __noinline__ double endpoint_cov_max_eig(const gfpl_camera& cam, double px, double py, double disp) {
   const double f = cam.fx;
   const double px_hat = px - cam.cx, py_hat = py - cam.cy;
   const double disp2 = disp * disp;
@@ -103,6 +103,20 @@ __device__ double endpoint_cov_max_eig(const gfpl_camera& cam, double px, double
     if (ev[0] > v) { ev[1] = ev[0]; ev[0] = v; } else ev[1] = v;
   }
   return ev[2];
+}
+
+// The endpoint covariance is  k (2 v v^T + diag(d^2, d^2, 0))  with v = (x - cx, y - cy, f), d the disparity and
+// k = b^2 / d^4, so by Weyl's inequalities its largest eigenvalue lies in [2 k |v|^2, k (2 |v|^2 + d^2)] — an interval of
+// relative width d^2 / (2 |v|^2) < 1e-4.  +1: surely below `th`, -1: surely not below, 0: inside the interval (or not
+// finite) — only then is the Jacobi iteration of the reference run.  Margins of 1e-9 cover the rounding of both sides.
+__device__ __forceinline__ int endpoint_cov_screen(const gfpl_camera& cam, double px, double py, double disp, double th) {
+  const double x = px - cam.cx, y = py - cam.cy, d2 = disp * disp;
+  const double k = cam.b * cam.b / (d2 * d2);
+  const double v2 = x * x + y * y + cam.fx * cam.fx;
+  const double lo = 2.0 * k * v2, hi = k * (2.0 * v2 + d2);
+  if (hi < th * (1.0 - 1e-9)) return 1;
+  if (lo > th * (1.0 + 1e-9) && lo < 1e300) return -1;
+  return 0;
 }
 
 __global__ void __launch_bounds__(ACCEPT_THREADS)
@@ -209,9 +223,15 @@ stereo_accept_kernel(DevRawFrames raw, int variant, Knn2Out pt_lr, Knn2Out pt_rl
                 overlap > cfg.stereo_overlap_th) {
               keep = true;
               if (variant != GFPL_STEREO_INITIAL) {
-                const double max_eig = fmax(endpoint_cov_max_eig(cam, sp_l[0], sp_l[1], disp_s),
-                                            endpoint_cov_max_eig(cam, ep_l[0], ep_l[1], disp_e));
-                keep = max_eig < cfg.line_cov_th;
+                const int ss = endpoint_cov_screen(cam, sp_l[0], sp_l[1], disp_s, cfg.line_cov_th);
+                const int se = endpoint_cov_screen(cam, ep_l[0], ep_l[1], disp_e, cfg.line_cov_th);
+                if (ss < 0 || se < 0) keep = false;          // one end point alone puts the maximum at or above the threshold
+                else if (ss > 0 && se > 0) keep = true;
+                else {
+                  const double max_eig = fmax(endpoint_cov_max_eig(cam, sp_l[0], sp_l[1], disp_s),
+                                              endpoint_cov_max_eig(cam, ep_l[0], ep_l[1], disp_e));
+                  keep = max_eig < cfg.line_cov_th;
+                }
               }
               if (keep) {
                 f.spl[0] = sp_l[0]; f.spl[1] = sp_l[1]; f.epl[0] = ep_l[0]; f.epl[1] = ep_l[1];
