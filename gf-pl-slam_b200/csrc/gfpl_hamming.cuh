@@ -74,6 +74,11 @@ __device__ __forceinline__ void top2_update(uint32_t& k0, uint32_t& k1, uint32_t
   k1 = min(k1, m);
 }
 
+// Problems of the "both sides <= 128 rows" class that the small tensor-core kernel leaves to the integer kernel: empty
+// ones and those too small to be worth a product round trip.
+constexpr int TC_TINY = 40;
+__device__ __forceinline__ bool tc_small_skips(int nq, int nt) { return (nq <= TC_TINY && nt <= TC_TINY) || nq == 0 || nt == 0; }
+
 // ---- mbarrier + 1-D bulk TMA ----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -99,6 +99,9 @@ __global__ void __launch_bounds__(256) knn2_sym_kernel(const uint8_t* __restrict
   const uint8_t* q_base = a + (size_t)p * cap_a * 32;
   const uint8_t* t_base = b + (size_t)p * cap_b * 32;
   const int nq = na[p], nt = nb[p];
+  // multi_tile bit 1: this launch only serves the problems the small tensor-core kernel leaves out (tc_small_skips)
+  if ((multi_tile & 2) && !tc_small_skips(nq, nt)) return;
+  multi_tile &= 1;
   const int q0 = blockIdx.x * (blockDim.x * QPT);
   const float inf = __int_as_float(0x7f800000);
   if (q0 >= nq) {  // uniform; a problem without query rows still owes the reverse direction its "no match" rows
@@ -216,12 +219,16 @@ int launch_knn2(gfpl_ctx* ctx, int B, const uint8_t* a, const int32_t* na, int c
   static const bool no_tc = getenv("GFPL_NO_TC") != nullptr;   // A/B switch for measurements
   if (both && reverse_best_only && norm == GFPL_NORM_HAMMING && !no_tc && knn2_tc_fits(cap_a, cap_b))
     return launch_knn2_tc(ctx, B, a, na, cap_a, b, nb, cap_b, out_ab, out_ba);
+  // both sides <= 128 rows (line descriptors): the persistent small tensor-core kernel takes the problems that are worth
+  // a product round trip, the integer kernel below the tiny and the empty ones (a few dozen rows: counts are only known
+  // on the device, so both are launched and each skips the other's problems)
+  const bool tc_small = both && reverse_best_only && !no_tc && knn2_tc_small_fits(cap_a, cap_b);
   if (both && reverse_best_only && (size_t)cap_b * 4 <= 160 * 1024) {
     const int qpt = cap_a >= 256 ? 2 : 1;
     int block, tiles;
     pick_tiling(cap_a, qpt, &block, &tiles);
-    const int multi = tiles > 1;
-    if (multi) GFPL_CUDA_OK(ctx, cudaMemsetAsync(out_ba.idx, 0xFF, (size_t)B * cap_b * sizeof(int2), ctx->stream));
+    const int multi = (tiles > 1 ? 1 : 0) | (tc_small ? 2 : 0);   // (tc_small implies one tile)
+    if (multi & 1) GFPL_CUDA_OK(ctx, cudaMemsetAsync(out_ba.idx, 0xFF, (size_t)B * cap_b * sizeof(int2), ctx->stream));
     dim3 grid(tiles, B, 1);
     const size_t smem = (size_t)cap_b * 4;
     int rc;
@@ -233,10 +240,11 @@ int launch_knn2(gfpl_ctx* ctx, int B, const uint8_t* a, const int32_t* na, int c
                     : launch_knn2_sym<GFPL_NORM_HAMMING, 1>(ctx, grid, block, smem, a, na, cap_a, b, nb, cap_b, out_ab, out_ba, multi);
     if (rc != GFPL_OK) return rc;
     GFPL_LAUNCH_OK(ctx);
-    if (multi) {
+    if (multi & 1) {
       knn2_decode_kernel<<<dim3((cap_b + 255) / 256, B), 256, 0, ctx->stream>>>(nb, cap_b, out_ba);
       GFPL_LAUNCH_OK(ctx);
     }
+    if (tc_small) return launch_knn2_tc_small(ctx, B, a, na, cap_a, b, nb, cap_b, norm, out_ab, out_ba);
     return GFPL_OK;
   }
   const int cap_q = both ? (cap_a > cap_b ? cap_a : cap_b) : cap_a;

@@ -59,6 +59,217 @@ knn2_tc_kernel(const uint8_t* __restrict__ a, const int32_t* __restrict__ na, in
   tc_end(tmem);
 }
 
+// ---- small problems (both sides <= 128 rows: line descriptors), both norms -----------------------------------------
+// One query tile, one pass, and the SAME expanded rows serve both products (both operands of an UMMA are K-major here):
+// D = A B^T gives the two nearest b-rows of every a-row (warps 0..3, one TMEM lane = one a-row), D^T = B A^T the nearest
+// a-row of every b-row (warps 4..7) — nothing is expanded twice and no warp idles.  Both sides carry +64 / -64, so a
+// product is 4096 * (#equal - #different) and the NEAREST row has the LARGEST accumulator: the selection keeps maxima of
+// `accumulator - column` (ties -> lowest column, OpenCV's rule).
+// NORM_HAMMING2 (number of differing 2-bit groups) is bilinear too: append to the 256 bit values the 128 products of the
+// two bits of every group (in +-1 arithmetic the XOR of two bits is their product).  Per group the three terms add up to
+// 3 when the groups are equal and to -1 otherwise (the vertices of a tetrahedron), i.e. K = 384 and
+// accumulator = 4096 * (4 * #equal groups - 128) = 4096 * 384 - 16384 * distance.
+template <int NORM> struct TcSmall {
+  static constexpr int KB = NORM == GFPL_NORM_HAMMING2 ? 384 : 256;   // int8 per expanded row
+  static constexpr int CH = KB / 16;                                  // 16-byte K chunks per row
+  static constexpr int SBO = CH * TC_LBO;                             // bytes between 8-row groups
+  static constexpr int KSTEPS = KB / 32;
+  static constexpr int ACC0 = 4096 * KB;                              // accumulator at distance 0
+  static constexpr int SHIFT = NORM == GFPL_NORM_HAMMING2 ? 14 : 13;  // accumulator = ACC0 - (distance << SHIFT)
+  static constexpr size_t SMEM = 2 * (size_t)(TC_M / 8) * SBO;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_sbo(uint32_t smem_addr, int sbo) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(TC_LBO >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+
+template <int NORM>
+__device__ __forceinline__ void expand_row_small(uint8_t* tile, int r, const uint8_t* __restrict__ src, const uint32_t* __restrict__ lut) {
+  using T = TcSmall<NORM>;
+  const uint4 lo = __ldg(reinterpret_cast<const uint4*>(src)), hi = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+  uint8_t* row = tile + (r >> 3) * T::SBO + (r & 7) * 16;
+  const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+  for (int c = 0; c < 16; c++) {
+    const uint32_t bits = w[c >> 1] >> ((c & 1) * 16);
+    *reinterpret_cast<uint4*>(row + c * TC_LBO) =
+        make_uint4(lut[bits & 15u], lut[(bits >> 4) & 15u], lut[(bits >> 8) & 15u], lut[(bits >> 12) & 15u]);
+  }
+  if (NORM == GFPL_NORM_HAMMING2) {
+#pragma unroll
+    for (int c = 0; c < 8; c++) {   // XOR of the two bits of each group of word c, compressed to 16 contiguous bits
+      uint32_t x = (w[c] ^ (w[c] >> 1)) & 0x55555555u;
+      x = (x | (x >> 1)) & 0x33333333u;
+      x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+      x = (x | (x >> 4)) & 0x00FF00FFu;
+      x = (x | (x >> 8)) & 0x0000FFFFu;
+      *reinterpret_cast<uint4*>(row + (16 + c) * TC_LBO) =
+          make_uint4(lut[x & 15u], lut[(x >> 4) & 15u], lut[(x >> 8) & 15u], lut[(x >> 12) & 15u]);
+    }
+  }
+}
+
+template <int NORM>
+__global__ void __launch_bounds__(TC_THREADS)
+knn2_tc_small_kernel(int B, const uint8_t* __restrict__ a, const int32_t* __restrict__ na, int cap_a, const uint8_t* __restrict__ b,
+                     const int32_t* __restrict__ nb, int cap_b, Knn2Out out_ab, Knn2Out out_ba) {
+  using T = TcSmall<NORM>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                               // rows of a, expanded
+  uint8_t* sB = smem + (TC_M / 8) * T::SBO;         // rows of b
+  __shared__ __align__(8) TcShared S;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const float inf = __int_as_float(0x7f800000);
+  const int dir = tid >> 7;                         // 0: rows of a against b (two nearest), 1: rows of b against a (nearest)
+  const int row = tid & (TC_M - 1);
+  {  // a CTA whose problems are all left to the integer kernel (e.g. frame-to-frame lines) returns before any set-up
+    __shared__ int s_any;
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    for (int p = blockIdx.x + tid * gridDim.x; p < B; p += gridDim.x * TC_THREADS)
+      if (!tc_small_skips(na[p], nb[p])) s_any = 1;
+    __syncthreads();
+    if (!s_any) return;
+  }
+  // persistent over problems: TMEM, barriers and the LUT are set up once per CTA
+  const uint32_t tmem = tc_begin(S);                // S.lut[0..16): bit set -> +64, clear -> -64
+  uint32_t phase = 0u;
+  for (int p = blockIdx.x; p < B; p += gridDim.x) {
+    const int nq = na[p], nt = nb[p];
+    const uint8_t* a_base = a + (size_t)p * cap_a * 32;
+    const uint8_t* b_base = b + (size_t)p * cap_b * 32;
+    int2* idx_o = dir == 0 ? out_ab.idx + (size_t)p * cap_a : out_ba.idx + (size_t)p * cap_b;
+    float2* dist_o = dir == 0 ? out_ab.dist + (size_t)p * cap_a : out_ba.dist + (size_t)p * cap_b;
+    const int nrows = dir == 0 ? nq : nt;            // rows of this thread's direction
+    const int ncols = dir == 0 ? nt : nq;            // the rows they are matched against
+    const uint8_t* my_rows = dir == 0 ? a_base : b_base;
+    if (tc_small_skips(nq, nt)) continue;   // CTA-uniform: served by the integer kernel launched beside this one
+    // threads 0..127: row tid of a, threads 128..255: row tid - 128 of b.  Rows past the end are never read back.
+    if (row < nrows) expand_row_small<NORM>(dir == 0 ? sA : sB, row, my_rows + (size_t)row * 32, S.lut);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const int nq16 = (nq + 15) & ~15, nt16 = (nt + 15) & ~15;
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int d = 0; d < 2; d++) {   // d 0: D = A B^T -> columns [0, 128); d 1: D^T = B A^T -> columns [128, 256)
+        const uint32_t mA = smem_u32(d == 0 ? sA : sB), nA = smem_u32(d == 0 ? sB : sA);
+        const uint32_t idesc = umma_idesc_i8(d == 0 ? nt16 : nq16);
+        const uint32_t d_tmem = tmem + (uint32_t)(d * TC_NPASS);
+#pragma unroll
+        for (int ks = 0; ks < T::KSTEPS; ks++) {
+          const uint64_t da = umma_desc_sbo(mA + ks * 2 * TC_LBO, T::SBO);
+          const uint64_t db = umma_desc_sbo(nA + ks * 2 * TC_LBO, T::SBO);
+          const uint32_t acc = ks > 0 ? 1u : 0u;
+          asm volatile(
+              "{\n\t"
+              ".reg .pred p;\n\t"
+              "setp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+              "}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u)
+              : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&S.bar[d])) : "memory");
+      }
+    }
+    // selection: warps 0..3 the rows of a (two nearest), warps 4..7 the rows of b (nearest); TMEM lane = row
+    const int ncols16 = dir == 0 ? nt16 : nq16;
+    constexpr int KNONE = -0x3FFFFFFF;               // stays below every real key however often kbase moves
+    int k0a = KNONE, k1a = KNONE, k0b = KNONE, k1b = KNONE;
+    int kbase = 0;                                   // keys are relative: accumulator - (column - kbase)
+    mbar_wait(&S.bar[dir], phase);
+    phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if ((warp & 3) * 32 < nrows) {
+      const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(dir * TC_NPASS);
+      uint32_t va[16], vb[16];
+      auto reduce16 = [&](const uint32_t* v, int c0) {
+        const int shift = c0 - kbase;
+        kbase = c0;
+        k0a += shift; k0b += shift; k1a += shift; k1b += shift;
+        if (c0 + 16 <= ncols) {
+#pragma unroll
+          for (int jx = 0; jx < 16; jx += 4) {
+            const int a0 = (int)v[jx], a1 = (int)v[jx + 1], a2 = (int)v[jx + 2], a3 = (int)v[jx + 3];
+            if (dir == 0) {
+              const int ta0 = __viaddmin_s32(a0, -jx, k0a);        k0a = __viaddmax_s32(a0, -jx, k0a);
+              const int tb0 = __viaddmin_s32(a1, -(jx + 1), k0b);  k0b = __viaddmax_s32(a1, -(jx + 1), k0b);
+              const int ta1 = __viaddmin_s32(a2, -(jx + 2), k0a);  k0a = __viaddmax_s32(a2, -(jx + 2), k0a);
+              const int tb1 = __viaddmin_s32(a3, -(jx + 3), k0b);  k0b = __viaddmax_s32(a3, -(jx + 3), k0b);
+              k1a = __vimax3_s32(k1a, ta0, ta1);
+              k1b = __vimax3_s32(k1b, tb0, tb1);
+            } else {
+              k0a = __viaddmax_s32(a0, -jx, k0a);        k0b = __viaddmax_s32(a1, -(jx + 1), k0b);
+              k0a = __viaddmax_s32(a2, -(jx + 2), k0a);  k0b = __viaddmax_s32(a3, -(jx + 3), k0b);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int jx = 0; jx < 16; jx++) {
+            if (c0 + jx < ncols) {
+              const int key = (int)v[jx] - jx;
+              const int t = min(k0a, key);
+              k0a = max(k0a, key);
+              k1a = max(k1a, t);
+            }
+          }
+        }
+      };
+      TC_LD16(va, taddr);
+      for (int c0 = 0; c0 < ncols16; c0 += 32) {
+        TC_WAIT16(va);
+        if (c0 + 16 < ncols16) TC_LD16(vb, taddr + (uint32_t)(c0 + 16));
+        reduce16(va, c0);
+        if (c0 + 16 < ncols16) {
+          TC_WAIT16(vb);
+          if (c0 + 32 < ncols16) TC_LD16(va, taddr + (uint32_t)(c0 + 32));
+          reduce16(vb, c0 + 16);
+        }
+      }
+      if (row < nrows) {
+        // merge the two chains (largest first), then relative signed keys -> (distance, column)
+        const int k0 = max(k0a, k0b);
+        const int k1 = max(max(k1a, k1b), min(k0a, k0b));
+        const bool has0 = k0 > (KNONE >> 1), has1 = dir == 0 && k1 > (KNONE >> 1);
+        const uint32_t u0 = (uint32_t)(T::ACC0 - (k0 - kbase)), u1 = (uint32_t)(T::ACC0 - (k1 - kbase));   // distance << SHIFT | column
+        const int i0 = has0 ? (int)(u0 & ((1u << T::SHIFT) - 1u)) : -1, i1 = has1 ? (int)(u1 & ((1u << T::SHIFT) - 1u)) : -1;
+        const float d0 = has0 ? (float)(u0 >> T::SHIFT) : inf, d1 = has1 ? (float)(u1 >> T::SHIFT) : inf;
+        idx_o[row] = make_int2(i0, i1);
+        dist_o[row] = make_float2(d0, d1);
+      }
+    }
+    // the accumulators are drained and every product has completed: the next problem may overwrite TMEM and the rows
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_end(tmem);
+}
+
+bool knn2_tc_small_fits(int cap_a, int cap_b) { return cap_a <= TC_M && cap_b <= TC_M && cap_a >= 32 && cap_b >= 32; }
+
+int launch_knn2_tc_small(gfpl_ctx* ctx, int B, const uint8_t* a, const int32_t* na, int cap_a, const uint8_t* b, const int32_t* nb,
+                         int cap_b, int norm, Knn2Out out_ab, Knn2Out out_ba) {
+  // persistent CTAs: two per SM (256 TMEM columns each), each walks the batch with the grid as stride
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const int grid = B < 2 * sms ? B : 2 * sms;
+  if (norm == GFPL_NORM_HAMMING2) {
+    GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(knn2_tc_small_kernel<GFPL_NORM_HAMMING2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)TcSmall<GFPL_NORM_HAMMING2>::SMEM));
+    knn2_tc_small_kernel<GFPL_NORM_HAMMING2><<<grid, TC_THREADS, TcSmall<GFPL_NORM_HAMMING2>::SMEM, ctx->stream>>>(B, a, na, cap_a, b, nb, cap_b,
+                                                                                                                    out_ab, out_ba);
+  } else {
+    GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(knn2_tc_small_kernel<GFPL_NORM_HAMMING>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)TcSmall<GFPL_NORM_HAMMING>::SMEM));
+    knn2_tc_small_kernel<GFPL_NORM_HAMMING><<<grid, TC_THREADS, TcSmall<GFPL_NORM_HAMMING>::SMEM, ctx->stream>>>(B, a, na, cap_a, b, nb, cap_b,
+                                                                                                                  out_ab, out_ba);
+  }
+  GFPL_LAUNCH_OK(ctx);
+  return GFPL_OK;
+}
+
 bool knn2_tc_fits(int cap_a, int cap_b) {
   // small problems are dominated by the fixed cost of a CTA (TMEM allocation, barriers): they stay on the integer pipes
   return cap_a >= 128 && cap_b >= 128 && cap_a < (1 << 19) && cap_b < (1 << 19) &&

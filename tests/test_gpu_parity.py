@@ -160,6 +160,41 @@ def test_stereo_match_dense_and_degenerate(ctx, orc):
     assert g.n_pt[0] == 0 and g.n_pt[1] == 0 and g.n_ln[2] == 0 and g.n_ln[3] == 0
 
 
+def test_stereo_line_covariance_gate_sweep(orc):
+    """the largest-eigenvalue gate of the stereo lines (stereoFrame.cpp:965-1000) is decided by bounds and only falls
+    back to the Jacobi iteration inside them: sweep the threshold through the eigenvalues of a batch so that both
+    branches and their borders are exercised; accepted line lists must stay identical to the oracle's"""
+    from gfpl import api
+    d = _data(6, 131)
+    seen = set()
+    for th in np.geomspace(0.05, 400.0, 60):
+        cfg = api.default_config()
+        cfg.line_cov_th = float(th)
+        c2 = api.Context(0, cam=d["cam"], cfg=cfg)
+        g, o = c2.stereo_match(d["curr_raw"]), orc.stereo_match(d["cam"], cfg, d["curr_raw"])
+        assert np.array_equal(g.n_ln, o.n_ln), th
+        for p in range(6):
+            assert np.array_equal(g.ln[p, :g.n_ln[p]]["src_l"], o.ln[p, :o.n_ln[p]]["src_l"]), (th, p)
+        seen.add(int(o.n_ln.sum()))
+    assert len(seen) > 10          # the threshold really cuts through the batch
+    # thresholds INSIDE the bounds of chosen end points (largest eigenvalue in [2 k |v|^2, k (2 |v|^2 + d^2)]): the
+    # Jacobi fallback decides those lines
+    cam = d["cam"]
+    base = orc.stereo_match(cam, api.default_config(), d["curr_raw"])
+    for p in range(3):
+        for i in range(0, int(base.n_ln[p]), 7):
+            ln = base.ln[p, i]
+            x, y, dd = ln["spl"][0] - cam.cx, ln["spl"][1] - cam.cy, ln["sdisp"]
+            k = cam.b * cam.b / dd ** 4
+            lo = 2.0 * k * (x * x + y * y + cam.fx * cam.fx)
+            cfg = api.default_config()
+            cfg.line_cov_th = float(lo + 0.5 * k * dd * dd)
+            c2 = api.Context(0, cam=cam, cfg=cfg)
+            g, o = c2.stereo_match(d["curr_raw"]), orc.stereo_match(cam, cfg, d["curr_raw"])
+            assert np.array_equal(g.n_ln, o.n_ln)
+            assert np.array_equal(g.ln[p, :g.n_ln[p]]["src_l"], o.ln[p, :o.n_ln[p]]["src_l"])
+
+
 def test_stereo_uncertainty(ctx, orc):
     d = _data(6, 11)
     fr = orc.stereo_match(d["cam"], ctx.cfg, d["prev_raw"])
