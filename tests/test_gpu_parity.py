@@ -780,6 +780,43 @@ def test_knn2_mutual_both_directions(ctx, orc, norm, tie):
                 assert (idx[p, :nq[p]] == -1).all() and (bi[p, :nt[p]] == -1).all()
 
 
+@pytest.mark.parametrize("norm", [6, 7])
+@pytest.mark.parametrize("tie", [False, True])
+def test_knn2_mutual_small_problems_persistent(ctx, orc, norm, tie):
+    """both sides <= 128 rows: the persistent small tensor-core kernel (NORM_HAMMING2 as a K = 384 product) next to the
+    integer kernel that takes the tiny / empty problems — 700 ragged problems (more than the persistent grid), every
+    border of the split (40 / 41 rows, 1 row, empty sides, 16-column chunk borders, full 128)"""
+    rng = np.random.default_rng(97 + norm + 2 * tie)
+    mk = (lambda n: synth.tie_stress_descriptors(rng, n)) if tie else (lambda n: rng.integers(0, 256, (n, 32), dtype=np.uint8))
+    fixed = [(128, 128), (41, 1), (1, 41), (40, 41), (41, 40), (40, 40), (0, 50), (50, 0), (97, 113), (33, 128), (128, 33),
+             (48, 48), (49, 47), (112, 16), (17, 127), (2, 64), (64, 2)]
+    B = 700
+    nq = rng.integers(0, 129, B).astype(np.int32); nt = rng.integers(0, 129, B).astype(np.int32)
+    for p, (x, y) in enumerate(fixed):
+        nq[p], nt[p] = x, y
+    q = np.zeros((B, 128, 32), np.uint8); t = np.zeros((B, 128, 32), np.uint8)
+    for p in range(B):
+        q[p, :nq[p]] = mk(nq[p]); t[p, :nt[p]] = mk(nt[p])
+        m = min(nq[p], nt[p]) // 2
+        t[p, :m] = q[p, :m] ^ np.packbits(rng.random((m, 256)) < 0.04, axis=1)
+    idx, dist, bi, bd = ctx.knn2_mutual(q, nq, t, nt, norm)
+    for p in range(B):
+        if nq[p] and nt[p] >= 2:
+            oi, od = orc.knn2(q[p, :nq[p]], t[p, :nt[p]], norm)
+            assert np.array_equal(idx[p, :nq[p]], oi) and np.array_equal(dist[p, :nq[p]], od), (p, nq[p], nt[p])
+        elif nq[p] and nt[p] == 1:
+            assert (idx[p, :nq[p], 0] == 0).all() and (idx[p, :nq[p], 1] == -1).all() and np.isinf(dist[p, :nq[p], 1]).all()
+        else:
+            assert (idx[p, :nq[p]] == -1).all()
+        if nt[p] and nq[p] >= 2:
+            ri, rd = orc.knn2(t[p, :nt[p]], q[p, :nq[p]], norm)
+            assert np.array_equal(bi[p, :nt[p]], ri[:, 0]) and np.array_equal(bd[p, :nt[p]], rd[:, 0]), (p, nq[p], nt[p])
+        elif nt[p] and nq[p] == 1:
+            assert (bi[p, :nt[p]] == 0).all()
+        else:
+            assert (bi[p, :nt[p]] == -1).all()
+
+
 def test_integer_pipe_paths_with_tensor_path_disabled():
     """GFPL_NO_TC=1 routes point matching to the integer-pipe kernels (knn2_sym_kernel, f2f_hybrid_points_kernel):
     the same parity tests must pass there (the switch is read once per process, hence the subprocess)"""
