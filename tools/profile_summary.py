@@ -25,7 +25,7 @@ with open(os.path.join(ROOT, "profiles", f"{tag}_launches_summary.md"), "w") as 
         f.write(f"| `{k}` | {n} | {t:.0f} | {100 * t / tot:.1f} % |\n")
     f.write(f"\nFirst 400 launches of the run: setup (stereo stage of the previous frames, 8 chunks), the pipe "
             f"micro-benchmarks (`popc_peak_kernel`, `lop3_peak_kernel`, `fp64_peak_kernel`), warm-up, timed steps "
-            f"(11 kernels per step), the streaming e2e steps (`expand_compact_kernel` + the same 11) and the LBA side note (`lba_*`).\n")
+            f"(13 kernels per step), the streaming e2e steps (`expand_compact_kernel` + the same 13) and the LBA side note (`lba_*`).\n")
 import shutil
 shutil.copy(launches, os.path.join(ROOT, "profiles", f"{tag}_launches.csv"))
 
@@ -46,7 +46,7 @@ traffic = {}
 with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_summary.md"), "w") as f:
     f.write(f"# {tag}: `ncu --set full --clock-control none --import-source on` of the hot kernels\n\n"
             "Command: `python bench.py --steps 2 --warmup 1 --skip-cpu-baseline` (default workload: 8192 EuRoC-shaped pairs, "
-            "300 points + 100 lines per image, line cutting on), `-k regex:knn2_tc_kernel|knn2_sym_kernel|f2f_hybrid_points_tc_kernel|"
+            "300 points + 100 lines per image, line cutting on), `-k regex:knn2_tc_kernel|knn2_tc_small_kernel|knn2_sym_kernel|f2f_hybrid_points_tc_kernel|"
             "linecut_kernel|pose_optimize_kernel|stereo_accept_kernel -s 48 -c 8`. Numbers taken under the profiler are for diagnosis only; "
             "the timings in BENCH/README come from CUDA events without ncu.\n\n")
     seen = set()
