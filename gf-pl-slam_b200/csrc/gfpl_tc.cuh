@@ -26,42 +26,50 @@ __device__ __forceinline__ uint32_t umma_idesc_i8(int n) {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 }
 
-// 4 descriptor bits -> 4 int8 of magnitude 64.  Train side (n): bit set -> +64 (0x40), clear -> -64 (0xC0); query side
-// (m): the negation.  A product of the two is then  -4096 * (256 - 2 * hamming) = 8192 * hamming - 2^20 : the accumulator
-// already is the sort key's distance field (hamming << 13), and the selection only adds the column index.
+// Descriptor bits -> int8 of magnitude 64.  Train side (n): bit set -> +64 (0x40), clear -> -64 (0xC0); query side (m): the
+// negation.  A product of the two is then  -4096 * (256 - 2 * hamming) = 8192 * hamming - 2^20 : the accumulator already is
+// the sort key's distance field (hamming << 13), and the selection only adds the column index.
 constexpr int TC_KEY_SHIFT = 13;                 // accumulator = (hamming << 13) - 2^20; train rows per problem < 8192
 constexpr int TC_KEY_BIAS = 1 << 20;
-__device__ __forceinline__ uint32_t expand_nibble(uint32_t nib, bool negate) {
-  const uint32_t t = (nib * 0x00204081u) & 0x01010101u;  // bit b of the nibble -> LSB of byte b
-  const uint32_t set = negate ? (t ^ 0x01010101u) : t;   // bytes that become +64
-  return set * 0x40u + (set ^ 0x01010101u) * 0xC0u;
+constexpr uint32_t TC_PAIR_TRAIN = 0x000040C0u;  // byte 0 = the int8 of a clear bit, byte 1 = of a set bit
+constexpr uint32_t TC_PAIR_QUERY = 0x0000C040u;  // negated
+
+// One descriptor word (32 bits) -> 32 int8 = two 16-byte K chunks, with byte permutes instead of table look-ups:
+// (w >> s) & 0x11111111 holds bits s, s + 4, ..., s + 28 in its eight nibbles, and a nibble that is 0 or 1 is exactly a
+// PRMT selector for byte 0 or 1 of `pair`.  Within a word the K positions come out permuted (chunk lo: bits
+// 0,4,8,12 | 1,5,9,13 | 2,6,10,14 | 3,7,11,15; chunk hi: the same + 16) — the same permutation for every row of both
+// operands, which a dot product does not see.  19 ALU instructions per word against 8 shared-memory look-ups + ~24.
+__device__ __forceinline__ void expand_word(uint32_t w, uint32_t pair, uint4& lo, uint4& hi) {
+  const uint32_t t0 = w & 0x11111111u, t1 = (w >> 1) & 0x11111111u, t2 = (w >> 2) & 0x11111111u, t3 = (w >> 3) & 0x11111111u;
+  lo = make_uint4(__byte_perm(pair, 0u, t0), __byte_perm(pair, 0u, t1), __byte_perm(pair, 0u, t2), __byte_perm(pair, 0u, t3));
+  hi = make_uint4(__byte_perm(pair, 0u, t0 >> 16), __byte_perm(pair, 0u, t1 >> 16), __byte_perm(pair, 0u, t2 >> 16),
+                  __byte_perm(pair, 0u, t3 >> 16));
 }
 
-// one descriptor row (8 words, or zeros past the end) -> 16 chunks of 16 int8 in the UMMA layout.  lut[nibble] = its 4
-// int8: 16 words in 16 different banks, so the look-ups of a warp never conflict.
-__device__ __forceinline__ void expand_row(uint8_t* tile, int r, const uint4& lo, const uint4& hi, bool zero,
-                                           const uint32_t* __restrict__ lut) {
+// one descriptor row (8 words, or zeros past the end) -> 16 chunks of 16 int8 in the UMMA layout
+__device__ __forceinline__ void expand_row(uint8_t* tile, int r, const uint4& lo, const uint4& hi, bool zero, uint32_t pair) {
   uint8_t* row = tile + (r >> 3) * TC_SBO + (r & 7) * 16;
   const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-  for (int c = 0; c < 16; c++) {
-    const uint32_t bits = w[c >> 1] >> ((c & 1) * 16);
-    uint4 v = make_uint4(lut[bits & 15u], lut[(bits >> 4) & 15u], lut[(bits >> 8) & 15u], lut[(bits >> 12) & 15u]);
-    if (zero) v = make_uint4(0u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(row + c * TC_LBO) = v;
+  for (int c = 0; c < 8; c++) {
+    uint4 a, b;
+    expand_word(w[c], pair, a, b);
+    if (zero) { a = make_uint4(0u, 0u, 0u, 0u); b = a; }
+    *reinterpret_cast<uint4*>(row + (2 * c) * TC_LBO) = a;
+    *reinterpret_cast<uint4*>(row + (2 * c + 1) * TC_LBO) = b;
   }
 }
 // half a row (16 of its 32 bytes -> 8 chunks): two threads share one row of the 128-row tile
-__device__ __forceinline__ void expand_half_row(uint8_t* tile, int r, int h, const uint4& q, bool zero,
-                                                const uint32_t* __restrict__ lut) {
+__device__ __forceinline__ void expand_half_row(uint8_t* tile, int r, int h, const uint4& q, bool zero, uint32_t pair) {
   uint8_t* row = tile + (r >> 3) * TC_SBO + (r & 7) * 16 + h * 8 * TC_LBO;
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-  for (int c = 0; c < 8; c++) {
-    const uint32_t bits = w[c >> 1] >> ((c & 1) * 16);
-    uint4 v = make_uint4(lut[bits & 15u], lut[(bits >> 4) & 15u], lut[(bits >> 8) & 15u], lut[(bits >> 12) & 15u]);
-    if (zero) v = make_uint4(0u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(row + c * TC_LBO) = v;
+  for (int c = 0; c < 4; c++) {
+    uint4 a, b;
+    expand_word(w[c], pair, a, b);
+    if (zero) { a = make_uint4(0u, 0u, 0u, 0u); b = a; }
+    *reinterpret_cast<uint4*>(row + (2 * c) * TC_LBO) = a;
+    *reinterpret_cast<uint4*>(row + (2 * c + 1) * TC_LBO) = b;
   }
 }
 
@@ -89,7 +97,7 @@ __device__ __forceinline__ void expand_half_row(uint8_t* tile, int r, int h, con
 // `emit(m_row, k0, k1)`.
 template <bool TOP2, class Emit>
 __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base, int nm, const uint8_t* __restrict__ n_base,
-                                             int nn, uint8_t* sM, uint8_t* sN, const uint32_t* lut /*[32]: train side, query side*/, uint64_t* bars /*[2]*/,
+                                             int nn, uint8_t* sM, uint8_t* sN, uint64_t* bars /*[2]*/,
                                              uint32_t* phases /*[2]*/, uint32_t tmem, uint2* s_merge /*[TC_M]*/, Emit emit) {
   const int tid = threadIdx.x, warp = tid >> 5;
   const int row = tid & (TC_M - 1);     // m-row inside the tile = TMEM lane
@@ -106,11 +114,11 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
 #pragma unroll
     for (int u = 0; u < 2; u++) {
       const int r = tid + u * TC_THREADS;
-      if (r < nnp) expand_row(sN, r, lo[u], hi[u], r >= nn, lut);
+      if (r < nnp) expand_row(sN, r, lo[u], hi[u], r >= nn, TC_PAIR_TRAIN);
     }
     for (int r = tid + 2 * TC_THREADS; r < nnp; r += TC_THREADS) {
       const uint4* src = reinterpret_cast<const uint4*>(n_base + (size_t)min(r, nn - 1) * 32);
-      expand_row(sN, r, __ldg(src), __ldg(src + 1), r >= nn, lut);
+      expand_row(sN, r, __ldg(src), __ldg(src + 1), r >= nn, TC_PAIR_TRAIN);
     }
   }
   const uint32_t sM_addr = smem_u32(sM), sN_addr = smem_u32(sN);
@@ -148,7 +156,7 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
       const uint4 cur_row = next_row;
       if (m0 + TC_M < nm)
         next_row = __ldg(reinterpret_cast<const uint4*>(m_base + (size_t)min(mi + TC_M, nm - 1) * 32) + half);
-      expand_half_row(sM, row, half, cur_row, mi >= nm, lut + 16);
+      expand_half_row(sM, row, half, cur_row, mi >= nm, TC_PAIR_QUERY);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the MMA
     __syncthreads();
@@ -249,7 +257,6 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
 struct TcShared {
   uint64_t bar[2];
   uint32_t tmem;
-  uint32_t lut[32];   // nibble -> 4 int8: [0,16) train side, [16,32) query side (negated)
   uint2 merge[TC_M];
 };
 __device__ __forceinline__ uint32_t tc_begin(TcShared& S) {
@@ -263,7 +270,6 @@ __device__ __forceinline__ uint32_t tc_begin(TcShared& S) {
     mbar_init(&S.bar[1], 1);
     mbar_fence_init();
   }
-  if (tid < 32) S.lut[tid] = expand_nibble(tid & 15, tid >= 16);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

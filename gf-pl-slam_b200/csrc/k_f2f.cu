@@ -196,7 +196,7 @@ f2f_hybrid_points_tc_kernel(DevStereoFrames prev, DevStereoFrames curr, const do
   const double window = cfg.f2f_point_window;
   const uint32_t tmem = tc_begin(S);
   uint32_t phases[2] = {0u, 0u};
-  tc_direction<true>(curr_desc, n_curr, prev_desc, n_prev, sM, sN, S.lut, S.bar, phases, tmem, S.merge,
+  tc_direction<true>(curr_desc, n_curr, prev_desc, n_prev, sM, sN, S.bar, phases, tmem, S.merge,
                      [&](int t, uint32_t k0, uint32_t k1) {
                        uint32_t best = KEY_NONE;
                        if (k0 < lim) {

@@ -45,13 +45,13 @@ knn2_tc_kernel(const uint8_t* __restrict__ a, const int32_t* __restrict__ na, in
   const uint32_t tmem = tc_begin(S);
   uint32_t phases[2] = {0u, 0u};
   // forward: queries a, train b, two nearest; reverse: queries b, train a, nearest only (all the mutual checks read)
-  tc_direction<true>(q_base, nq, t_base, nt, sM, sN, S.lut, S.bar, phases, tmem, S.merge,
+  tc_direction<true>(q_base, nq, t_base, nt, sM, sN, S.bar, phases, tmem, S.merge,
                      [&](int i, uint32_t k0, uint32_t k1) {
                        idx_ab[i] = make_int2((int)(k0 & KEY_IDX_MASK), k1 != KEY_NONE ? (int)(k1 & KEY_IDX_MASK) : -1);
                        dist_ab[i] = make_float2((float)(k0 >> KEY_IDX_BITS), k1 != KEY_NONE ? (float)(k1 >> KEY_IDX_BITS) : inf);
                      });
   __syncthreads();
-  tc_direction<false>(t_base, nt, q_base, nq, sM, sN, S.lut, S.bar, phases, tmem, S.merge,
+  tc_direction<false>(t_base, nt, q_base, nq, sM, sN, S.bar, phases, tmem, S.merge,
                       [&](int j, uint32_t k0, uint32_t) {
                         idx_ba[j] = make_int2((int)(k0 & KEY_IDX_MASK), -1);
                         dist_ba[j] = make_float2((float)(k0 >> KEY_IDX_BITS), inf);
@@ -84,27 +84,26 @@ __device__ __forceinline__ uint64_t umma_desc_sbo(uint32_t smem_addr, int sbo) {
 }
 
 template <int NORM>
-__device__ __forceinline__ void expand_row_small(uint8_t* tile, int r, const uint8_t* __restrict__ src, const uint32_t* __restrict__ lut) {
+__device__ __forceinline__ void expand_row_small(uint8_t* tile, int r, const uint8_t* __restrict__ src) {
   using T = TcSmall<NORM>;
   const uint4 lo = __ldg(reinterpret_cast<const uint4*>(src)), hi = __ldg(reinterpret_cast<const uint4*>(src) + 1);
   uint8_t* row = tile + (r >> 3) * T::SBO + (r & 7) * 16;
   const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-  for (int c = 0; c < 16; c++) {
-    const uint32_t bits = w[c >> 1] >> ((c & 1) * 16);
-    *reinterpret_cast<uint4*>(row + c * TC_LBO) =
-        make_uint4(lut[bits & 15u], lut[(bits >> 4) & 15u], lut[(bits >> 8) & 15u], lut[(bits >> 12) & 15u]);
+  for (int c = 0; c < 8; c++) {
+    uint4 x, y;
+    expand_word(w[c], TC_PAIR_TRAIN, x, y);
+    *reinterpret_cast<uint4*>(row + (2 * c) * TC_LBO) = x;
+    *reinterpret_cast<uint4*>(row + (2 * c + 1) * TC_LBO) = y;
   }
   if (NORM == GFPL_NORM_HAMMING2) {
 #pragma unroll
-    for (int c = 0; c < 8; c++) {   // XOR of the two bits of each group of word c, compressed to 16 contiguous bits
-      uint32_t x = (w[c] ^ (w[c] >> 1)) & 0x55555555u;
-      x = (x | (x >> 1)) & 0x33333333u;
-      x = (x | (x >> 2)) & 0x0F0F0F0Fu;
-      x = (x | (x >> 4)) & 0x00FF00FFu;
-      x = (x | (x >> 8)) & 0x0000FFFFu;
-      *reinterpret_cast<uint4*>(row + (16 + c) * TC_LBO) =
-          make_uint4(lut[x & 15u], lut[(x >> 4) & 15u], lut[(x >> 8) & 15u], lut[(x >> 12) & 15u]);
+    for (int c = 0; c < 4; c++) {   // XOR of the two bits of each group: 16 group bits per word at the even positions
+      const uint32_t g0 = (w[2 * c] ^ (w[2 * c] >> 1)) & 0x55555555u, g1 = (w[2 * c + 1] ^ (w[2 * c + 1] >> 1)) & 0x55555555u;
+      uint4 x, y;
+      expand_word(g0 | (g1 << 1), TC_PAIR_TRAIN, x, y);   // the groups of two words interleaved: 32 group bits -> 32 int8
+      *reinterpret_cast<uint4*>(row + (16 + 2 * c) * TC_LBO) = x;
+      *reinterpret_cast<uint4*>(row + (16 + 2 * c + 1) * TC_LBO) = y;
     }
   }
 }
@@ -132,7 +131,7 @@ knn2_tc_small_kernel(int B, const uint8_t* __restrict__ a, const int32_t* __rest
     if (!s_any) return;
   }
   // persistent over problems: TMEM, barriers and the LUT are set up once per CTA
-  const uint32_t tmem = tc_begin(S);                // S.lut[0..16): bit set -> +64, clear -> -64
+  const uint32_t tmem = tc_begin(S);
   uint32_t phase = 0u;
   for (int p = blockIdx.x; p < B; p += gridDim.x) {
     const int nq = na[p], nt = nb[p];
@@ -145,7 +144,7 @@ knn2_tc_small_kernel(int B, const uint8_t* __restrict__ a, const int32_t* __rest
     const uint8_t* my_rows = dir == 0 ? a_base : b_base;
     if (tc_small_skips(nq, nt)) continue;   // CTA-uniform: served by the integer kernel launched beside this one
     // threads 0..127: row tid of a, threads 128..255: row tid - 128 of b.  Rows past the end are never read back.
-    if (row < nrows) expand_row_small<NORM>(dir == 0 ? sA : sB, row, my_rows + (size_t)row * 32, S.lut);
+    if (row < nrows) expand_row_small<NORM>(dir == 0 ? sA : sB, row, my_rows + (size_t)row * 32);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     const int nq16 = (nq + 15) & ~15, nt16 = (nt + 15) & ~15;
