@@ -182,6 +182,27 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
       const int nvalid = min(N, nn - n0);  // columns of this pass that are real train rows
       const uint32_t taddr = tlane + (uint32_t)((pass & 1) * TC_NPASS);
       uint32_t va[16], vb[16];
+      auto reduce16_full = [&](const uint32_t* v, int c0) {   // all 16 columns valid
+        const int shift = (n0 + c0) - kbase;
+        kbase = n0 + c0;
+        k0a -= shift; k0b -= shift;
+        if (TOP2) { k1a -= shift; k1b -= shift; }
+#pragma unroll
+        for (int jx = 0; jx < 16; jx += 4) {   // DPX: fused add-min / add-max and three-input minimum
+          const int a0 = (int)v[jx], a1 = (int)v[jx + 1], a2 = (int)v[jx + 2], a3 = (int)v[jx + 3];
+          if (TOP2) {
+            const int ta0 = __viaddmax_s32(a0, jx, k0a);      k0a = __viaddmin_s32(a0, jx, k0a);
+            const int tb0 = __viaddmax_s32(a1, jx + 1, k0b);  k0b = __viaddmin_s32(a1, jx + 1, k0b);
+            const int ta1 = __viaddmax_s32(a2, jx + 2, k0a);  k0a = __viaddmin_s32(a2, jx + 2, k0a);
+            const int tb1 = __viaddmax_s32(a3, jx + 3, k0b);  k0b = __viaddmin_s32(a3, jx + 3, k0b);
+            k1a = __vimin3_s32(k1a, ta0, ta1);
+            k1b = __vimin3_s32(k1b, tb0, tb1);
+          } else {
+            k0a = __viaddmin_s32(a0, jx, k0a);      k0b = __viaddmin_s32(a1, jx + 1, k0b);
+            k0a = __viaddmin_s32(a2, jx + 2, k0a);  k0b = __viaddmin_s32(a3, jx + 3, k0b);
+          }
+        }
+      };
       auto reduce16 = [&](const uint32_t* v, int c0) {
         const int shift = (n0 + c0) - kbase;
         kbase = n0 + c0;
@@ -215,7 +236,23 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
         }
       };
       // (a warp whose 32 rows all lie past nm has nothing to read: TMEM read bandwidth is what bounds this kernel)
-      if (cbeg < cend && m0 + (warp & 3) * 32 < nm) {
+      if (nvalid == TC_NPASS) {
+        // full pass (all 128 columns are train rows): this thread's four chunks straight-line, no per-chunk conditions
+        if (m0 + (warp & 3) * 32 < nm) {
+          TC_LD16(va, taddr + (uint32_t)cbeg);
+          TC_LD16(vb, taddr + (uint32_t)(cbeg + 16));
+          TC_WAIT16(va);
+          reduce16_full(va, cbeg);
+          TC_LD16(va, taddr + (uint32_t)(cbeg + 32));
+          TC_WAIT16(vb);
+          reduce16_full(vb, cbeg + 16);
+          TC_LD16(vb, taddr + (uint32_t)(cbeg + 48));
+          TC_WAIT16(va);
+          reduce16_full(va, cbeg + 32);
+          TC_WAIT16(vb);
+          reduce16_full(vb, cbeg + 48);
+        }
+      } else if (cbeg < cend && m0 + (warp & 3) * 32 < nm) {
         TC_LD16(va, taddr + (uint32_t)cbeg);
         for (int c0 = cbeg; c0 < cend; c0 += 32) {
           TC_WAIT16(va);
