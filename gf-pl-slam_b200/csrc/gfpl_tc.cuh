@@ -178,7 +178,9 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
       // this thread's share of the pass: columns [cbeg, cend) of the buffer, 16 at a time, next chunk in flight
-      const int cbeg = half * (TC_NPASS / 2), cend = min(N, cbeg + TC_NPASS / 2);
+      // (a short last pass is split evenly as well: the first ceil(chunks / 2) chunks to half 0, the others to half 1)
+      const int csplit = N == TC_NPASS ? TC_NPASS / 2 : 16 * (((N >> 4) + 1) >> 1);
+      const int cbeg = half ? csplit : 0, cend = half ? N : csplit;
       const int nvalid = min(N, nn - n0);  // columns of this pass that are real train rows
       const uint32_t taddr = tlane + (uint32_t)((pass & 1) * TC_NPASS);
       uint32_t va[16], vb[16];
