@@ -46,28 +46,27 @@ __device__ __forceinline__ void expand_word(uint32_t w, uint32_t pair, uint4& lo
                   __byte_perm(pair, 0u, t3 >> 16));
 }
 
-// one descriptor row (8 words, or zeros past the end) -> 16 chunks of 16 int8 in the UMMA layout
-__device__ __forceinline__ void expand_row(uint8_t* tile, int r, const uint4& lo, const uint4& hi, bool zero, uint32_t pair) {
+// one descriptor row (8 words) -> 16 chunks of 16 int8 in the UMMA layout.  Rows past the end of a side are not written
+// at all: as query rows they only produce accumulator lanes nobody reads, as train rows columns the selection masks.
+__device__ __forceinline__ void expand_row(uint8_t* tile, int r, const uint4& lo, const uint4& hi, uint32_t pair) {
   uint8_t* row = tile + (r >> 3) * TC_SBO + (r & 7) * 16;
   const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
   for (int c = 0; c < 8; c++) {
     uint4 a, b;
     expand_word(w[c], pair, a, b);
-    if (zero) { a = make_uint4(0u, 0u, 0u, 0u); b = a; }
     *reinterpret_cast<uint4*>(row + (2 * c) * TC_LBO) = a;
     *reinterpret_cast<uint4*>(row + (2 * c + 1) * TC_LBO) = b;
   }
 }
 // half a row (16 of its 32 bytes -> 8 chunks): two threads share one row of the 128-row tile
-__device__ __forceinline__ void expand_half_row(uint8_t* tile, int r, int h, const uint4& q, bool zero, uint32_t pair) {
+__device__ __forceinline__ void expand_half_row(uint8_t* tile, int r, int h, const uint4& q, uint32_t pair) {
   uint8_t* row = tile + (r >> 3) * TC_SBO + (r & 7) * 16 + h * 8 * TC_LBO;
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
   for (int c = 0; c < 4; c++) {
     uint4 a, b;
     expand_word(w[c], pair, a, b);
-    if (zero) { a = make_uint4(0u, 0u, 0u, 0u); b = a; }
     *reinterpret_cast<uint4*>(row + (2 * c) * TC_LBO) = a;
     *reinterpret_cast<uint4*>(row + (2 * c + 1) * TC_LBO) = b;
   }
@@ -108,17 +107,17 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
 #pragma unroll
     for (int u = 0; u < 2; u++) {
       const int r = tid + u * TC_THREADS;
-      const uint4* src = reinterpret_cast<const uint4*>(n_base + (size_t)min(r, nn - 1) * 32);
-      if (r < nnp) { lo[u] = __ldg(src); hi[u] = __ldg(src + 1); }
+      const uint4* src = reinterpret_cast<const uint4*>(n_base + (size_t)r * 32);
+      if (r < nn) { lo[u] = __ldg(src); hi[u] = __ldg(src + 1); }
     }
 #pragma unroll
     for (int u = 0; u < 2; u++) {
       const int r = tid + u * TC_THREADS;
-      if (r < nnp) expand_row(sN, r, lo[u], hi[u], r >= nn, TC_PAIR_TRAIN);
+      if (r < nn) expand_row(sN, r, lo[u], hi[u], TC_PAIR_TRAIN);
     }
-    for (int r = tid + 2 * TC_THREADS; r < nnp; r += TC_THREADS) {
-      const uint4* src = reinterpret_cast<const uint4*>(n_base + (size_t)min(r, nn - 1) * 32);
-      expand_row(sN, r, __ldg(src), __ldg(src + 1), r >= nn, TC_PAIR_TRAIN);
+    for (int r = tid + 2 * TC_THREADS; r < nn; r += TC_THREADS) {
+      const uint4* src = reinterpret_cast<const uint4*>(n_base + (size_t)r * 32);
+      expand_row(sN, r, __ldg(src), __ldg(src + 1), TC_PAIR_TRAIN);
     }
   }
   const uint32_t sM_addr = smem_u32(sM), sN_addr = smem_u32(sN);
@@ -156,7 +155,7 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
       const uint4 cur_row = next_row;
       if (m0 + TC_M < nm)
         next_row = __ldg(reinterpret_cast<const uint4*>(m_base + (size_t)min(mi + TC_M, nm - 1) * 32) + half);
-      expand_half_row(sM, row, half, cur_row, mi >= nm, TC_PAIR_QUERY);
+      if (mi < nm) expand_half_row(sM, row, half, cur_row, TC_PAIR_QUERY);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the MMA
     __syncthreads();
