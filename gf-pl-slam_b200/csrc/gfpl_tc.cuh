@@ -318,6 +318,6 @@ __device__ __forceinline__ void tc_end(uint32_t tmem) {
   if ((threadIdx.x >> 5) == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS));
 }
-inline size_t tc_smem_bytes(int cap_n) { return (size_t)TC_M * TC_ROW_BYTES + (size_t)((cap_n + 15) & ~15) * TC_ROW_BYTES; }
+__host__ __device__ inline size_t tc_smem_bytes(int cap_n) { return (size_t)TC_M * TC_ROW_BYTES + (size_t)((cap_n + 15) & ~15) * TC_ROW_BYTES; }
 
 }  // namespace gfpl

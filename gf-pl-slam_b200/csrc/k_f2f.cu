@@ -194,27 +194,33 @@ f2f_hybrid_points_tc_kernel(DevStereoFrames prev, DevStereoFrames curr, const do
   const int rint = radius >= 0.f ? (int)floorf(fminf(radius, 1024.f)) : -1;   // (float)d <= radius  <=>  d <= rint
   const uint32_t lim = (uint32_t)(rint + 1) << KEY_IDX_BITS;                  // keys of candidates are < lim
   const double window = cfg.f2f_point_window;
+  // The two smallest keys of every current point are parked in shared memory; the projection gate (fp64, with dependent
+  // global loads of the candidate's 3-D point) runs once at the end with all 256 threads, instead of after every query
+  // tile with half of them while the other half waits at the next barrier.
+  uint2* s_keys = reinterpret_cast<uint2*>(smem + tc_smem_bytes(prev.cap_pt));   // [curr.cap_pt]
   const uint32_t tmem = tc_begin(S);
   uint32_t phases[2] = {0u, 0u};
   tc_direction<true>(curr_desc, n_curr, prev_desc, n_prev, sM, sN, S.bar, phases, tmem, S.merge,
-                     [&](int t, uint32_t k0, uint32_t k1) {
-                       uint32_t best = KEY_NONE;
-                       if (k0 < lim) {
-                         const double plx = curr_pt[t].pl[0], ply = curr_pt[t].pl[1];
-                         if (!(k1 < lim)) {
-                           best = f2f_gate(KEY_NONE, k0, cam, T32, prev_pt[k0 & KEY_IDX_MASK].P, plx, ply, window);
-                         } else {  // several previous points within the radius: every one of them is gated (:524-546)
-                           const Desc256 qd = load_desc_global(curr_desc + (size_t)t * 32);
-                           for (int q = 0; q < n_prev; q++) {
-                             const uint4* rp = reinterpret_cast<const uint4*>(prev_desc + (size_t)q * 32);
-                             const uint32_t d = hamming256<GFPL_NORM_HAMMING>(qd, __ldg(rp), __ldg(rp + 1));
-                             if ((int)d <= rint) best = f2f_gate(best, make_key(d, q), cam, T32, prev_pt[q].P, plx, ply, window);
-                           }
-                         }
-                       }
-                       out[t] = best;
-                     });
-  tc_end(tmem);
+                     [&](int t, uint32_t k0, uint32_t k1) { s_keys[t] = make_uint2(k0, k1); });
+  tc_end(tmem);   // (CTA barrier inside: the keys are visible)
+  for (int t = threadIdx.x; t < n_curr; t += TC_THREADS) {
+    const uint32_t k0 = s_keys[t].x, k1 = s_keys[t].y;
+    uint32_t best = KEY_NONE;
+    if (k0 < lim) {
+      const double plx = curr_pt[t].pl[0], ply = curr_pt[t].pl[1];
+      if (!(k1 < lim)) {
+        best = f2f_gate(KEY_NONE, k0, cam, T32, prev_pt[k0 & KEY_IDX_MASK].P, plx, ply, window);
+      } else {  // several previous points within the radius: every one of them is gated (:524-546)
+        const Desc256 qd = load_desc_global(curr_desc + (size_t)t * 32);
+        for (int q = 0; q < n_prev; q++) {
+          const uint4* rp = reinterpret_cast<const uint4*>(prev_desc + (size_t)q * 32);
+          const uint32_t d = hamming256<GFPL_NORM_HAMMING>(qd, __ldg(rp), __ldg(rp + 1));
+          if ((int)d <= rint) best = f2f_gate(best, make_key(d, q), cam, T32, prev_pt[q].P, plx, ply, window);
+        }
+      }
+    }
+    out[t] = best;
+  }
 }
 
 int launch_f2f_hybrid_points(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr,
@@ -223,7 +229,7 @@ int launch_f2f_hybrid_points(gfpl_ctx* ctx, const DevStereoFrames& prev, const D
   f2f_predict_kernel<<<(prev.B + 63) / 64, 64, 0, ctx->stream>>>(state, prev.B, T32);
   GFPL_LAUNCH_OK(ctx);
   static const bool no_tc = getenv("GFPL_NO_TC") != nullptr;   // A/B switch for measurements
-  const size_t tc_smem = tc_smem_bytes(prev.cap_pt);
+  const size_t tc_smem = tc_smem_bytes(prev.cap_pt) + (size_t)curr.cap_pt * sizeof(uint2);
   if (!no_tc && prev.cap_pt >= 128 && curr.cap_pt >= 128 && prev.cap_pt < (1 << 19) && tc_smem <= 200 * 1024) {
     GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(f2f_hybrid_points_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
     f2f_hybrid_points_tc_kernel<<<prev.B, TC_THREADS, tc_smem, ctx->stream>>>(prev, curr, T32, best_key, ctx->cam, ctx->cfg);
