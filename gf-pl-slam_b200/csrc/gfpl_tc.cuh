@@ -102,6 +102,9 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
   const int row = tid & (TC_M - 1);     // m-row inside the tile = TMEM lane
   const int half = tid >> 7;            // which half of a pass's columns this thread reduces
   const int nnp = (nn + 15) & ~15;
+  // this thread's half descriptor row of the first query tile is requested before the train side is expanded, and that of
+  // the NEXT tile before the current tile is reduced (global latency)
+  uint4 next_row = __ldg(reinterpret_cast<const uint4*>(m_base + (size_t)min(row, nm - 1) * 32) + half);
   {  // both n-rows of this thread are fetched before either is expanded
     uint4 lo[2], hi[2];
 #pragma unroll
@@ -147,8 +150,6 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
                  : "memory");
   };
 
-  // this thread's half descriptor row of the NEXT tile is fetched before the current tile is reduced (global latency)
-  uint4 next_row = __ldg(reinterpret_cast<const uint4*>(m_base + (size_t)min(row, nm - 1) * 32) + half);
   for (int m0 = 0; m0 < nm; m0 += TC_M) {
     {
       const int mi = m0 + row;
