@@ -88,6 +88,113 @@ __device__ __forceinline__ void expand_half_row(uint8_t* tile, int r, int h, con
                :                                                                                                          \
                : "memory")
 
+// Relative signed selection keys (see tc_direction): key = accumulator + column - kbase.
+constexpr int TC_KNONE = 0x3FFFFFFF;          // stays above every real key (< 2^22) however often kbase moves
+struct TcKeys {
+  int k0a, k1a, k0b, k1b, kbase;
+  __device__ __forceinline__ void reset() { k0a = k1a = k0b = k1b = TC_KNONE; kbase = 0; }
+};
+__device__ __forceinline__ uint32_t tc_canonical(int k, int kbase) {   // -> distance << 20 | train row (KEY_NONE if unset)
+  if (k >= (TC_KNONE >> 1)) return KEY_NONE;
+  const uint32_t kabs = (uint32_t)(k + kbase + TC_KEY_BIAS);   // hamming << 13 | train row
+  return ((kabs >> TC_KEY_SHIFT) << KEY_IDX_BITS) | (kabs & ((1u << TC_KEY_SHIFT) - 1u));
+}
+
+// 16 accumulator columns [c0, c0 + 16) of one row -> the running keys.  `col0` = index of column 0 of the product in the
+// train side; FULL: all 16 columns are real rows.
+template <bool TOP2, bool FULL>
+__device__ __forceinline__ void tc_reduce16(TcKeys& K, const uint32_t* v, int col0, int c0, int nvalid) {
+  const int shift = (col0 + c0) - K.kbase;
+  K.kbase = col0 + c0;
+  K.k0a -= shift; K.k0b -= shift;
+  if (TOP2) { K.k1a -= shift; K.k1b -= shift; }
+  if (FULL || c0 + 16 <= nvalid) {
+#pragma unroll
+    for (int jx = 0; jx < 16; jx += 4) {   // DPX: fused add-min / add-max and three-input minimum
+      const int a0 = (int)v[jx], a1 = (int)v[jx + 1], a2 = (int)v[jx + 2], a3 = (int)v[jx + 3];
+      if (TOP2) {
+        const int ta0 = __viaddmax_s32(a0, jx, K.k0a);      K.k0a = __viaddmin_s32(a0, jx, K.k0a);
+        const int tb0 = __viaddmax_s32(a1, jx + 1, K.k0b);  K.k0b = __viaddmin_s32(a1, jx + 1, K.k0b);
+        const int ta1 = __viaddmax_s32(a2, jx + 2, K.k0a);  K.k0a = __viaddmin_s32(a2, jx + 2, K.k0a);
+        const int tb1 = __viaddmax_s32(a3, jx + 3, K.k0b);  K.k0b = __viaddmin_s32(a3, jx + 3, K.k0b);
+        K.k1a = __vimin3_s32(K.k1a, ta0, ta1);
+        K.k1b = __vimin3_s32(K.k1b, tb0, tb1);
+      } else {
+        K.k0a = __viaddmin_s32(a0, jx, K.k0a);      K.k0b = __viaddmin_s32(a1, jx + 1, K.k0b);
+        K.k0a = __viaddmin_s32(a2, jx + 2, K.k0a);  K.k0b = __viaddmin_s32(a3, jx + 3, K.k0b);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int jx = 0; jx < 16; jx++) {
+      if (c0 + jx < nvalid) {
+        const int key = (int)v[jx] + jx;
+        if (TOP2) { K.k1a = min(K.k1a, max(key, K.k0a)); K.k0a = min(key, K.k0a); }
+        else K.k0a = min(key, K.k0a);
+      }
+    }
+  }
+}
+
+// this thread's share (column half `half`) of one product of N columns (nvalid of them real) in the accumulator buffer at
+// `taddr` (TMEM lane = row already included): full products straight-line, short ones chunk by chunk
+template <bool TOP2>
+__device__ __forceinline__ void tc_reduce_product(TcKeys& K, uint32_t taddr, int half, int N, int nvalid, int col0) {
+  uint32_t va[16], vb[16];
+  if (nvalid == TC_NPASS) {
+    const int cbeg = half * (TC_NPASS / 2);
+    TC_LD16(va, taddr + (uint32_t)cbeg);
+    TC_LD16(vb, taddr + (uint32_t)(cbeg + 16));
+    TC_WAIT16(va);
+    tc_reduce16<TOP2, true>(K, va, col0, cbeg, nvalid);
+    TC_LD16(va, taddr + (uint32_t)(cbeg + 32));
+    TC_WAIT16(vb);
+    tc_reduce16<TOP2, true>(K, vb, col0, cbeg + 16, nvalid);
+    TC_LD16(vb, taddr + (uint32_t)(cbeg + 48));
+    TC_WAIT16(va);
+    tc_reduce16<TOP2, true>(K, va, col0, cbeg + 32, nvalid);
+    TC_WAIT16(vb);
+    tc_reduce16<TOP2, true>(K, vb, col0, cbeg + 48, nvalid);
+  } else {
+    // (a short product is split evenly as well: the first ceil(chunks / 2) chunks to half 0, the others to half 1)
+    const int csplit = N == TC_NPASS ? TC_NPASS / 2 : 16 * (((N >> 4) + 1) >> 1);
+    const int cbeg = half ? csplit : 0, cend = half ? N : csplit;
+    if (cbeg < cend) {
+      TC_LD16(va, taddr + (uint32_t)cbeg);
+      for (int c0 = cbeg; c0 < cend; c0 += 32) {
+        TC_WAIT16(va);
+        if (c0 + 16 < cend) TC_LD16(vb, taddr + (uint32_t)(c0 + 16));
+        tc_reduce16<TOP2, false>(K, va, col0, c0, nvalid);
+        if (c0 + 16 < cend) {
+          TC_WAIT16(vb);
+          if (c0 + 32 < cend) TC_LD16(va, taddr + (uint32_t)(c0 + 32));
+          tc_reduce16<TOP2, false>(K, vb, col0, c0 + 16, nvalid);
+        }
+      }
+    }
+  }
+}
+
+// thread 0: one 128 x N x 256 product (8 K-steps) into the accumulator buffer `d_tmem`, then commit to `bar`
+__device__ __forceinline__ void tc_issue_product(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, int N, uint64_t* bar) {
+  const uint32_t idesc = umma_idesc_i8(N);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+  for (int ks = 0; ks < 8; ks++) {  // K = 256 in steps of 32 int8 = two 16-byte chunks
+    const uint64_t da = umma_desc(a_addr + ks * 2 * TC_LBO);
+    const uint64_t db = umma_desc(b_addr + ks * 2 * TC_LBO);
+    const uint32_t acc = ks > 0 ? 1u : 0u;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u)
+        : "memory");
+  }
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // One match direction: rows `m` (nm of them) against rows `n` (nn).  TOP2: keep the two best train rows per m-row
 // (forward direction, [i][0] and [i][1]); else only the best (reverse direction, [j][0]).  The n side is expanded in
 // full into sN, the m side tile by tile into sM.  Accumulators are double-buffered in TMEM: the products of pass i+1

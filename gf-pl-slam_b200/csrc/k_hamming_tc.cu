@@ -19,17 +19,32 @@
 
 namespace gfpl {
 
+// Both directions from ONE expansion of each side.  The train rows b are expanded once into sN; a query tile of a in sM
+// then serves two families of products (both UMMA operands are K-major, so a tile can be either operand):
+//   forward  D  = sM x chunk_p(sN)^T : rows = the tile's a-rows, columns = 128 b-rows  -> two nearest b-rows of every a-row
+//   reverse  D' = chunk_i(sN) x sM^T : rows = 128 b-rows, columns = the tile's a-rows  -> nearest a-row of every b-row,
+//                                      kept across the tiles in s_rev[b-row]
+// i.e. 2 * ceil(nb / 128) products per tile in one uninterrupted pipeline over the two TMEM buffers, and half the
+// expansion work of two separate directions.  sM lies BEHIND sN: the 128-row M operand of the last reverse chunk may start
+// in sN's last rows and run into sM — inside the allocation, and those lanes are never read.
+__host__ __device__ inline size_t knn2_tc_smem_bytes(int cap_b) {
+  return (size_t)((cap_b + 15) & ~15) * TC_ROW_BYTES + (size_t)TC_M * TC_ROW_BYTES + 2 * (size_t)cap_b * sizeof(uint32_t);
+}
+
 __global__ void __launch_bounds__(TC_THREADS)
 knn2_tc_kernel(const uint8_t* __restrict__ a, const int32_t* __restrict__ na, int cap_a, const uint8_t* __restrict__ b,
                const int32_t* __restrict__ nb, int cap_b, Knn2Out out_ab, Knn2Out out_ba) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sM = smem;                                   // [128][256] int8 tile of the "query" side, UMMA layout
-  uint8_t* sN = smem + TC_M * TC_ROW_BYTES;             // [<= max(cap_a, cap_b) rounded to 16][256] "train" side
+  uint8_t* sN = smem;                                                        // [cap_b rounded to 16][256] rows of b
+  uint8_t* sM = smem + (size_t)((cap_b + 15) & ~15) * TC_ROW_BYTES;          // [128][256] one tile of a
+  uint32_t* s_rev = reinterpret_cast<uint32_t*>(sM + TC_M * TC_ROW_BYTES);   // [2][cap_b] best key of every b-row so far, per column half
   __shared__ __align__(8) TcShared S;
 
   const int p = blockIdx.x;
   const int nq = na[p], nt = nb[p];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & (TC_M - 1);     // row inside a tile = TMEM lane
+  const int half = tid >> 7;            // which half of a product's columns this thread reduces
   const float inf = __int_as_float(0x7f800000);
   const uint8_t* q_base = a + (size_t)p * cap_a * 32;
   const uint8_t* t_base = b + (size_t)p * cap_b * 32;
@@ -43,20 +58,92 @@ knn2_tc_kernel(const uint8_t* __restrict__ a, const int32_t* __restrict__ na, in
     return;
   }
   const uint32_t tmem = tc_begin(S);
+  uint2* s_merge = S.merge;             // [TC_M]: the column halves of an a-row meet here once per tile
+  // this thread's half descriptor row of the first a-tile is requested before b is expanded (global latency)
+  uint4 next_row = __ldg(reinterpret_cast<const uint4*>(q_base + (size_t)min(row, nq - 1) * 32) + half);
+  for (int r = tid; r < nt; r += TC_THREADS) {
+    const uint4* src = reinterpret_cast<const uint4*>(t_base + (size_t)r * 32);
+    expand_row(sN, r, __ldg(src), __ldg(src + 1), TC_PAIR_TRAIN);
+    s_rev[r] = KEY_NONE;
+    s_rev[cap_b + r] = KEY_NONE;
+  }
+  const uint32_t sM_addr = smem_u32(sM), sN_addr = smem_u32(sN);
+  const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const int nnp = (nt + 15) & ~15;
+  const int nchunk = (nnp + TC_NPASS - 1) / TC_NPASS;   // 128-row chunks of b: forward passes and reverse M tiles
+  const int P = 2 * nchunk;                             // products per a-tile
   uint32_t phases[2] = {0u, 0u};
-  // forward: queries a, train b, two nearest; reverse: queries b, train a, nearest only (all the mutual checks read)
-  tc_direction<true>(q_base, nq, t_base, nt, sM, sN, S.bar, phases, tmem, S.merge,
-                     [&](int i, uint32_t k0, uint32_t k1) {
-                       idx_ab[i] = make_int2((int)(k0 & KEY_IDX_MASK), k1 != KEY_NONE ? (int)(k1 & KEY_IDX_MASK) : -1);
-                       dist_ab[i] = make_float2((float)(k0 >> KEY_IDX_BITS), k1 != KEY_NONE ? (float)(k1 >> KEY_IDX_BITS) : inf);
-                     });
-  __syncthreads();
-  tc_direction<false>(t_base, nt, q_base, nq, sM, sN, S.bar, phases, tmem, S.merge,
-                      [&](int j, uint32_t k0, uint32_t) {
-                        idx_ba[j] = make_int2((int)(k0 & KEY_IDX_MASK), -1);
-                        dist_ba[j] = make_float2((float)(k0 >> KEY_IDX_BITS), inf);
-                      });
-  tc_end(tmem);
+  uint32_t prod = 0u;                                   // products so far: product t uses accumulator buffer t & 1
+
+  for (int m0 = 0; m0 < nq; m0 += TC_M) {
+    {
+      const int mi = m0 + row;
+      const uint4 cur_row = next_row;
+      if (m0 + TC_M < nq)
+        next_row = __ldg(reinterpret_cast<const uint4*>(q_base + (size_t)min(mi + TC_M, nq - 1) * 32) + half);
+      if (mi < nq) expand_half_row(sM, row, half, cur_row, TC_PAIR_QUERY);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the MMA
+    __syncthreads();
+    const int nqt = min(TC_M, nq - m0);            // a-rows of this tile
+    const int nqt16 = (nqt + 15) & ~15;
+    auto issue = [&](int t, uint32_t buf) {        // thread 0: product t of this tile into accumulator buffer buf
+      const uint32_t d_tmem = tmem + buf * TC_NPASS;
+      if (t < nchunk) tc_issue_product(d_tmem, sM_addr, sN_addr + (uint32_t)t * (TC_NPASS / 8) * TC_SBO, min(TC_NPASS, nnp - t * TC_NPASS), &S.bar[buf]);
+      else tc_issue_product(d_tmem, sN_addr + (uint32_t)(t - nchunk) * (TC_NPASS / 8) * TC_SBO, sM_addr, nqt16, &S.bar[buf]);
+    };
+    if (tid == 0) issue(0, prod & 1u);
+    TcKeys F;   // the two nearest b-rows of this thread's a-row, over the forward products of the tile
+    F.reset();
+    for (int t = 0; t < P; t++, prod++) {
+      const uint32_t buf = prod & 1u;
+      if (tid == 0 && t + 1 < P) issue(t + 1, buf ^ 1u);   // that buffer was drained before the barrier that ended product t - 1
+      mbar_wait(&S.bar[buf], phases[buf]);
+      phases[buf] ^= 1u;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tlane + buf * TC_NPASS;
+      const bool fwd = t < nchunk;
+      uint32_t k0 = KEY_NONE, k1 = KEY_NONE;
+      if (fwd) {
+        const int n0 = t * TC_NPASS;
+        const int N = min(TC_NPASS, nnp - n0);
+        if (m0 + (warp & 3) * 32 < nq) tc_reduce_product<true>(F, taddr, half, N, min(N, nt - n0), n0);
+        if (t == nchunk - 1) {   // last forward product of the tile: the row's two nearest are complete
+          k0 = tc_canonical(F.k0a, F.kbase); k1 = tc_canonical(F.k1a, F.kbase);
+          top2_update(k0, k1, tc_canonical(F.k0b, F.kbase));
+          top2_update(k0, k1, tc_canonical(F.k1b, F.kbase));
+          if (half == 1) s_merge[row] = make_uint2(k0, k1);
+        }
+      } else {
+        const int j0 = (t - nchunk) * TC_NPASS;     // first b-row of this reverse chunk
+        if (j0 + (warp & 3) * 32 < nt) {
+          TcKeys R;
+          R.reset();
+          tc_reduce_product<false>(R, taddr, half, nqt16, nqt, m0);
+          const int j = j0 + row;                   // this thread owns (b-row j, its column half) in every tile
+          if (j < nt) s_rev[half * cap_b + j] = min(s_rev[half * cap_b + j], min(tc_canonical(R.k0a, R.kbase), tc_canonical(R.k0b, R.kbase)));
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();  // this buffer is drained (the product after the next may overwrite it)
+      if (fwd && t == nchunk - 1 && half == 0) {
+        const int mi = m0 + row;
+        if (mi < nq) {
+          const uint2 o = s_merge[row];
+          top2_update(k0, k1, o.x); top2_update(k0, k1, o.y);
+          idx_ab[mi] = make_int2((int)(k0 & KEY_IDX_MASK), k1 != KEY_NONE ? (int)(k1 & KEY_IDX_MASK) : -1);
+          dist_ab[mi] = make_float2((float)(k0 >> KEY_IDX_BITS), k1 != KEY_NONE ? (float)(k1 >> KEY_IDX_BITS) : inf);
+        }
+      }
+    }
+    // (sM may be overwritten: every product of the tile has completed and was waited for by every thread)
+  }
+  tc_end(tmem);   // CTA barrier inside: s_rev is complete
+  for (int j = tid; j < nt; j += TC_THREADS) {
+    const uint32_t k0 = min(s_rev[j], s_rev[cap_b + j]);
+    idx_ba[j] = make_int2((int)(k0 & KEY_IDX_MASK), -1);
+    dist_ba[j] = make_float2((float)(k0 >> KEY_IDX_BITS), inf);
+  }
 }
 
 // ---- small problems (both sides <= 128 rows: line descriptors), both norms -----------------------------------------
@@ -270,14 +357,14 @@ int launch_knn2_tc_small(gfpl_ctx* ctx, int B, const uint8_t* a, const int32_t* 
 }
 
 bool knn2_tc_fits(int cap_a, int cap_b) {
-  // small problems are dominated by the fixed cost of a CTA (TMEM allocation, barriers): they stay on the integer pipes
-  return cap_a >= 128 && cap_b >= 128 && cap_a < (1 << 19) && cap_b < (1 << 19) &&
-         tc_smem_bytes(cap_a > cap_b ? cap_a : cap_b) <= 200 * 1024;
+  // small problems are dominated by the fixed cost of a CTA (TMEM allocation, barriers): they go to knn2_tc_small_kernel
+  return cap_a >= 128 && cap_b >= 128 && cap_a < (1 << TC_KEY_SHIFT) && cap_b < (1 << TC_KEY_SHIFT) &&
+         knn2_tc_smem_bytes(cap_b) <= 200 * 1024;
 }
 
 int launch_knn2_tc(gfpl_ctx* ctx, int B, const uint8_t* a, const int32_t* na, int cap_a, const uint8_t* b, const int32_t* nb,
                    int cap_b, Knn2Out out_ab, Knn2Out out_ba) {
-  const size_t smem = tc_smem_bytes(cap_a > cap_b ? cap_a : cap_b);
+  const size_t smem = knn2_tc_smem_bytes(cap_b);
   GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   knn2_tc_kernel<<<B, TC_THREADS, smem, ctx->stream>>>(a, na, cap_a, b, nb, cap_b, out_ab, out_ba);
   GFPL_LAUNCH_OK(ctx);
