@@ -1,18 +1,20 @@
-// k_hamming_tc.cu — NORM_HAMMING knn k=2 (forward) + best match (reverse) on the 5th-generation tensor cores.
+// k_hamming_tc.cu — knn k=2 (forward) + best match (reverse) of 256-bit descriptors on the 5th-generation tensor cores.
 //
 // The INT-pipe kernel of k_hamming.cu runs at ~85 % of the ALU pipe: 5 POPC + ~25 ALU operations per 256-bit distance.
 // The only higher ceiling on the chip for this arithmetic is the tensor pipe, and the distance matrix of one problem
-// IS a matrix product: with every descriptor bit mapped to an int8 +1 / -1,
-//     dot(a, b) = #equal bits - #different bits = 256 - 2 * hamming(a, b)          (exact in the s32 accumulator)
-// so D = A * B^T (M = queries, N = train rows, K = 256) gives all distances of the problem.  One CTA per problem:
-//   1. the 32-byte descriptors are expanded to int8 rows in shared memory, directly in the K-major no-swizzle UMMA
-//      layout (8-row x 16-byte core matrices: byte(r, k) at (r/8)*SBO + (k/16)*LBO + (r%8)*16 + k%16),
-//   2. one thread issues tcgen05.mma.kind::i8 (M = 128, N <= 128, K = 32 per instruction, 8 per pass) into one of two
-//      TMEM accumulator buffers and commits to that buffer's mbarrier; the next pass is issued before this one is read,
-//   3. the CTA's 256 threads read accumulator rows with tcgen05.ld (TMEM lane = query row, two threads per row, half of
-//      the columns each) and keep the packed-key top-2 of the row — thread-local, no shuffles, no atomics.
-// The reverse direction (nearest query of every train row) is the same product with the roles swapped (tensor time is
-// nearly free here) and a top-1 selection.  Per distance the ALU pipe sees ~5 (+3 reverse) operations instead of ~25.
+// IS a matrix product: with every descriptor bit mapped to an int8 +64 / -64 (query side negated),
+//     dot(a, b) = -4096 * (#equal bits - #different bits) = (hamming(a, b) << 13) - 2^20     (exact in the s32 accumulator)
+// so D = A * B^T (M = queries, N = train rows, K = 256) gives all distances of the problem, already in the form of the
+// distance field of a sort key.  One CTA per problem:
+//   1. the 32-byte descriptors are expanded to int8 rows in shared memory (byte permutes, gfpl_tc.cuh), directly in the
+//      K-major no-swizzle UMMA layout (8-row x 16-byte core matrices: byte(r, k) at (r/8)*SBO + (k/16)*LBO + (r%8)*16 + k%16),
+//   2. one thread issues tcgen05.mma.kind::i8 (M = 128, N <= 128, K = 32 per instruction, 8 per product) into one of two
+//      TMEM accumulator buffers and commits to that buffer's mbarrier; the next product is issued before this one is read,
+//   3. the CTA's 256 threads read accumulator rows with tcgen05.ld (TMEM lane = row, two threads per row, half of the
+//      columns each) and keep the top-2 (top-1) of the row with fused add-min/max instructions: 2.5 (1) per distance —
+//      thread-local, no shuffles, no atomics.
+// knn2_tc_kernel (128..~650 rows per side, NORM_HAMMING) expands each side once and takes both directions from it;
+// knn2_tc_small_kernel (<= 128 rows per side, both norms) is persistent over problems.
 // Results are bit-identical to k_hamming.cu: same keys (distance << 20 | index), same tie rule.
 #include "gfpl_internal.h"
 #include "gfpl_tc.cuh"
