@@ -468,6 +468,11 @@ __device__ __noinline__ double2 search_line(const gfpl_camera* cam, const gfpl_c
   return make_double2(cur0, cur1);
 }
 
+// The search is one dependent chain per pair, so every global round trip on it is exposed (ncu: two thirds of the stall
+// samples of the kernel body were long-scoreboard).  What the next step will read is pulled into L1 ahead of time with
+// prefetch.global.L1 — no registers, no dependence.
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 __global__ void __maxnreg__(CUT_MAX_REGS)
 linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __restrict__ state, DevTrackObs obs,
                const gfpl_line_cov* __restrict__ prev_cov, int cov_cap, gfpl_line_cut* __restrict__ cut_all,
@@ -541,6 +546,10 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
     // getPoseInfoPoint (:1414-1447): the group's 8 lanes evaluate 8 Jacobians at a time (one point each) and publish
     // them; every lane then adds its three products point by point, i.e. in the reference's order
     for (int k0 = 0; k0 < npt; k0 += CUT_GROUP) {
+      if (k0 + 2 * CUT_GROUP + j < npt) {   // the point this lane evaluates two rounds from now
+        const char* nx = reinterpret_cast<const char*>(&pts[k0 + 2 * CUT_GROUP + j]);
+        prefetch_l1(nx); prefetch_l1(nx + sizeof(gfpl_pt_obs) - 8);
+      }
       if (k0 + j < npt) {
         const gfpl_pt_obs& po = pts[k0 + j];
         double c[3], uv[2], J[6];
@@ -566,8 +575,19 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
   __syncwarp(gmask);
 
   // pass 3: sequential greedy search per line (:1662-1763)
+  int prev_idx_next = nln > 1 ? lns[1].prev_idx : 0;   // covariance record of line l + 1 (loaded one line ahead)
   for (int l = 0; l < nln; l++) {
     gfpl_line_cut& C = cut[l];
+    int prev_idx_next2 = 0;
+    if (l + 1 < nln) {   // line l + 1: observation (88 B), covariances (144 B), initial information (288 B of the cut record)
+      const char* o1 = reinterpret_cast<const char*>(&lns[l + 1]);
+      const char* c1 = reinterpret_cast<const char*>(&cov[prev_idx_next]);
+      const char* i1 = reinterpret_cast<const char*>(&cut[l + 1]);
+      if (j < 5) prefetch_l1(c1 + 32 * j); else prefetch_l1(o1 + 32 * (j - 5));
+      prefetch_l1(i1 + 32 * j);
+      if (j < 3) prefetch_l1(i1 + 256 + 32 * j);
+      if (l + 2 < nln) prev_idx_next2 = lns[l + 2].prev_idx;
+    }
     {  // stage the line into the group's shared memory
       const gfpl_ln_obs& o = lns[l];
       const gfpl_line_cov& c = cov[o.prev_idx];
@@ -638,6 +658,7 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
       }
     }
     __syncwarp(gmask);
+    prev_idx_next = prev_idx_next2;
   }
 }
 
