@@ -362,7 +362,8 @@ int gfpl_knn2_hamming256_batch(gfpl_ctx* ctx, int32_t B, const uint8_t* q, const
  * [i][0], [i][1] of the forward direction and only [j][0] of the reverse one (:836, :735, :253).
  * out_idx / out_dist: [B][cap_q][2] as gfpl_knn2_hamming256_batch; out_best_idx / out_best_dist: [B][cap_t] nearest query
  * row of every train row (ties -> lowest query index), -1 / +inf when nq[p] == 0.  NORM_HAMMING runs on the tensor cores
- * (int8 +-1 product, exact), NORM_HAMMING2 on the integer pipes. */
+ * (int8 +-64 product, exact); problems of at most 128 rows per side run there for both norms (NORM_HAMMING2 as a
+ * K = 384 product), larger NORM_HAMMING2 problems and tiny ones on the integer pipes. */
 int gfpl_knn2_mutual_batch(gfpl_ctx* ctx, int32_t B, const uint8_t* q, const int32_t* nq, int32_t cap_q,
                            const uint8_t* t, const int32_t* nt, int32_t cap_t, int32_t norm, int32_t* out_idx,
                            float* out_dist, int32_t* out_best_idx, float* out_best_dist);

@@ -756,7 +756,7 @@ def test_lba_step_schur_solve(ctx, orc):
 @pytest.mark.parametrize("norm", [S.NORM_HAMMING, S.NORM_HAMMING2])
 @pytest.mark.parametrize("tie", [False, True])
 def test_knn2_mutual_both_directions(ctx, orc, norm, tie):
-    """forward k=2 + reverse best match from one pass (NORM_HAMMING: tensor-core int8 +-1 product) == two knnMatch calls"""
+    """forward k=2 + reverse best match from one pass (tensor-core int8 +-64 products) == two knnMatch calls"""
     rng = np.random.default_rng(41 + norm)
     mk = (lambda n: synth.tie_stress_descriptors(rng, n)) if tie else (lambda n: rng.integers(0, 256, (n, 32), dtype=np.uint8))
     for cap_q, cap_t, sizes in ((300, 310, [(300, 310), (257, 129), (128, 160), (2, 3), (0, 5), (7, 0), (130, 161)]),
