@@ -158,6 +158,8 @@ struct PairObs {
   const gfpl_ln_obs* lns;
   uint8_t* pin;
   uint8_t* lin;
+  const uint32_t* plist;   // indices of the inlier points, ascending (shared memory), or nullptr: every point, flags in pin
+  int nplist;
 };
 
 // ---- reductions inside a group of G lanes (full-mask shuffles: the groups of a warp call them together) -------------
@@ -261,10 +263,15 @@ __device__ __forceinline__ void group_optimize_functions(const double* DTs, cons
     // two observations per lane and round in one basic block: their dependency chains (transform, reciprocal, projection,
     // reciprocal square root, Jacobian) interleave, which is where a latency-bound warp gets its instruction-level
     // parallelism from; an observation that is an outlier or past the end contributes zeros
-    for (int k = lg; k < npt; k += 2 * G) {
-      const int k2 = (k + G < npt) ? k + G : k;
-      const gfpl_pt_obs A = o.pts[k], Bq = o.pts[k2];
-      const bool onA = o.pin[k] != 0, onB = (k + G < npt) && o.pin[k2] != 0;
+    // (the optimiser walks the compacted list of inliers: after the MAD pass a fifth of the points are outliers, and a
+    // branch-free term costs the same whether it counts or not)
+    const int nwalk = o.plist ? (act ? o.nplist : 0) : npt;
+    for (int k = lg; k < nwalk; k += 2 * G) {
+      const bool twoB = k + G < nwalk;
+      const int k2 = twoB ? k + G : k;
+      const int iA = o.plist ? (int)o.plist[k] : k, iB = o.plist ? (int)o.plist[k2] : k2;
+      const gfpl_pt_obs A = o.pts[iA], Bq = o.pts[iB];
+      const bool onA = o.plist ? true : o.pin[iA] != 0, onB = twoB && (o.plist ? true : o.pin[iB] != 0);
       double JA[6], JB[6], rA, rB, wA, wB;
       point_front(DTs, A, onA, cam, c, JA, rA, wA);
       point_front(DTs, Bq, onB, cam, c, JB, rB, wB);
@@ -287,6 +294,25 @@ __device__ __forceinline__ void group_optimize_functions(const double* DTs, cons
     N += __shfl_xor_sync(0xffffffffu, N, s);
   }
   a.v[27] = a.v[27] / (double)N;  // e /= (N_l + N_p), 0/0 -> NaN like the reference
+}
+
+// Ascending list of the points whose inlier flag is set, for the groups of a warp together (ballot compaction per
+// group).  npt = 0 for a group without a problem.  Returns the length.
+template <int G>
+__device__ __forceinline__ int group_inlier_list(const uint8_t* pin, int npt, uint32_t* list) {
+  const int lane = threadIdx.x & 31, lg = lane & (G - 1), gfirst = lane & ~(G - 1);
+  const int nmax = __reduce_max_sync(0xffffffffu, npt);
+  int base = 0;
+  for (int k0 = 0; k0 < nmax; k0 += G) {
+    const int k = k0 + lg;
+    const bool keep = k < npt && pin[k] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const unsigned gb = G == 32 ? bal : ((bal >> gfirst) & ((1u << (G & 31)) - 1u));
+    if (keep) list[base + __popc(gb & ((1u << lg) - 1u))] = (uint32_t)k;
+    base += __popc(gb);
+  }
+  __syncwarp();
+  return base;
 }
 
 // gaussNewtonOptimization (:2032-2056) for the groups of a warp together; H of the last evaluation is returned for
@@ -497,6 +523,7 @@ pose_optimize_kernel(DevTrackObs obs, const gfpl_frame_state* __restrict__ state
   o.npt = obs.n_pt[p]; o.nln = obs.n_ln[p];
   o.pts = obs.pt + (size_t)p * obs.cap_pt; o.pin = obs.pt_inlier + (size_t)p * obs.cap_pt;
   o.lns = obs.ln + (size_t)p * obs.cap_ln; o.lin = obs.ln_inlier + (size_t)p * obs.cap_ln;
+  o.plist = nullptr; o.nplist = 0;
   const gfpl_frame_state& st = state[p];
 
   double DT[16], err = 0.0;
@@ -513,6 +540,10 @@ pose_optimize_kernel(DevTrackObs obs, const gfpl_frame_state* __restrict__ state
   bool alive = exists && n_inliers > cfg.min_features;
   if (!alive) status |= GFPL_POSE_FEW_FEATURES;
   // stage 0: first estimate on a copy of the seed (max_iters iterations), then the MAD outlier pass
+  // (the select scratch behind the residuals doubles as the inlier list: the two are never live together)
+  uint32_t* plist = reinterpret_cast<uint32_t*>(s_res + obs.cap_pt + obs.cap_ln);
+  o.nplist = group_inlier_list<G>(o.pin, alive ? o.npt : 0, plist);
+  o.plist = plist;
   pose_store(DTs, seed);
   it1 = group_gauss_newton<G>(DTs, o, alive, cam, cfg, cfg.max_iters, Hs, &err);
   pose_load(DTs, DT);
@@ -526,6 +557,7 @@ pose_optimize_kernel(DevTrackObs obs, const gfpl_frame_state* __restrict__ state
     }
   }
   // stage 1: refinement restarting from the seed (D8) (max_iters_ref iterations)
+  o.nplist = group_inlier_list<G>(o.pin, alive ? o.npt : 0, plist);
   pose_store(DTs, seed);
   it2 = group_gauss_newton<G>(DTs, o, alive, cam, cfg, cfg.max_iters_ref, Hs, &err);
   if (alive) { cov_from_H = true; pose_load(DTs, DT); }
@@ -624,6 +656,7 @@ pose_hg_kernel(DevTrackObs obs, const double* __restrict__ DT_all, double* __res
   o.npt = obs.n_pt[p]; o.nln = obs.n_ln[p];
   o.pts = obs.pt + (size_t)p * obs.cap_pt; o.pin = obs.pt_inlier + (size_t)p * obs.cap_pt;
   o.lns = obs.ln + (size_t)p * obs.cap_ln; o.lin = obs.ln_inlier + (size_t)p * obs.cap_ln;
+  o.plist = nullptr; o.nplist = 0;
   __shared__ __align__(16) double s_DT[POSE_WARPS][12];
   Acc a;
   pose_store(s_DT[warp], DT_all + (size_t)p * 16);
