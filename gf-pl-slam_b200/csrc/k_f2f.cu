@@ -359,10 +359,12 @@ f2f_accept_kernel(DevStereoFrames prev, DevStereoFrames curr, int mode, const ui
           const int t = t0 + threadIdx.x;
           const uint32_t key = t < n_curr ? best_key[(size_t)p * curr.cap_pt + t] : KEY_NONE;
           const bool keep = key != KEY_NONE;
+          const int q = (int)(key & KEY_IDX_MASK);
+          gfpl_pt_obs ob{};   // the record is read before the compaction's two CTA barriers, so its latency overlaps them
+          if (keep) write_pt_obs(prev, curr, p, q, t, &ob);
           const int slot = block_compact_acc(keep, base, s_warp);
           if (keep && slot < pt_cap) {
-            const int q = (int)(key & KEY_IDX_MASK);
-            write_pt_obs(prev, curr, p, q, t, &out.pt[op + slot]);
+            out.pt[op + slot] = ob;
             out.pt_inlier[op + slot] = 1;
             atomicMax(&s_last[q], t);
           }

@@ -141,14 +141,17 @@ stereo_accept_kernel(DevRawFrames raw, int variant, Knn2Out pt_lr, Knn2Out pt_rl
         float disp_sub = 0.f;
         gfpl_keypoint kl{};
         if (i < n_l) {
+          // The loads form two levels instead of four: the left key point goes out with the knn record, the reverse
+          // record and the right key point together once the match index is known (the kernel is bound by the latency
+          // of these dependent global loads: ncu long-scoreboard 56 %).
           const int2 mi = pt_lr.idx[rp + i];
           const float2 md = pt_lr.dist[rp + i];
+          kl = raw.pt_l[rp + i];
           tdx = mi.x;
           const int rl_tdx = cfg.best_lr_matches ? pt_rl.idx[rp + tdx].x : i;
+          const gfpl_keypoint kr = raw.pt_r[rp + tdx];
           const double dist_12 = (double)(md.x / md.y);  // float / float, widened (stereoFrame.cpp:219,842)
           if (i == rl_tdx && dist_12 <= cfg.max_ratio_12_p) {
-            kl = raw.pt_l[rp + i];
-            const gfpl_keypoint kr = raw.pt_r[rp + tdx];
             if ((double)fabsf(kl.y - kr.y) <= cfg.max_dist_epip) {
               const double disp_ = (double)(kl.x - kr.x);
               if (disp_ >= cfg.min_disp) {
@@ -198,11 +201,11 @@ stereo_accept_kernel(DevRawFrames raw, int variant, Knn2Out pt_lr, Knn2Out pt_rl
         if (i < n_matches) {
           const int tdx = ln_lr.idx[rl_ + i].x;
           const float2 md = ln_lr.dist[rl_ + i];
+          const gfpl_keyline L = raw.ln_l[rl_ + i];      // (two load levels, as for the points)
           const int rl_tdx = cfg.best_lr_matches ? ln_rl.idx[rl_ + tdx].x : i;
+          const gfpl_keyline R = raw.ln_r[rl_ + tdx];
           const double dist_12 = (double)(md.y - md.x);
           if (i == rl_tdx && dist_12 > nn12_dist_th) {
-            const gfpl_keyline L = raw.ln_l[rl_ + i];
-            const gfpl_keyline R = raw.ln_r[rl_ + tdx];
             const double sp_l[3] = {L.startPointX, L.startPointY, 1.0};
             const double ep_l[3] = {L.endPointX, L.endPointY, 1.0};
             double le_l[3] = {sp_l[1] * ep_l[2] - sp_l[2] * ep_l[1], sp_l[2] * ep_l[0] - sp_l[0] * ep_l[2],
