@@ -23,6 +23,8 @@ sys.path.insert(0, os.path.join(ROOT, "gf-pl-slam_b200", "python"))
 
 import numpy as np  # noqa: E402
 
+CPU_FLAGS = None
+COUNTERS_FILE = "r2_kernel_counters.json"
 METRIC = "stereo frame pairs/s (stereo+f2f Hamming matching, line cut, pose GN)"
 UNIT = "frame_pairs/s"
 
@@ -39,6 +41,8 @@ def parse():
     ap.add_argument("--no-linecut", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="pairs per step of the CPU reference arm")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=int(os.environ.get("GFPL_PIPELINE", "1")),
+                    help="sub-batches of the software pipeline of the resident step (1 = off)")
     return ap.parse_args()
 
 
@@ -48,6 +52,8 @@ def workload_config(a):
             "pairs_per_gpu": a.pairs, "points_per_image": a.n_pt, "lines_per_image": a.n_ln,
             "prev_frame_layout": "stereo survivors packed to the largest count in the batch; e2e uploads the compact step input (gfpl_compact_input: 8+1 B key points, 20+1 B key lines, 12+1 B previous points, 32+1 B previous lines, descriptors)",
             "stages": "stereo knn (points: tcgen05 int8, lines: popcount)+accept -> f2f hybrid search (tcgen05 int8)+accept -> stereo uncertainty+line cut -> pose GN(5)+MAD+GN(10)",
+            "pipeline": ("off: the kernels of a step run back to back on one stream (measured faster than the sub-batch pipeline, DESIGN.md §5)" if a.pipeline <= 1 else
+                         "%d sub-batches: matching kernels of sub-batch k+1 overlap line cut + pose GN of sub-batch k (gfpl_replay_set_pipeline)" % a.pipeline),
             "l2_policy": "inputs larger than L2 (>=700 MB read per step vs 126 MB L2)", "parallelism": "pairs sharded over ranks, NCCL all_gather of pose records only"}
 
 
@@ -93,6 +99,8 @@ def cpu_reference(a, rank_seed=0):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import orc
     from gfpl import synth, _structs as S
+    global CPU_FLAGS
+    CPU_FLAGS = orc.use_native_build()   # the reference's own flags (-O3 -march=native), built on this machine
     n = min(a.pairs, a.cpu_sample)
     cores = os.cpu_count() or 1
     d = synth.make_pairs(n, n_pt=a.n_pt, n_ln=a.n_ln, seed=1000 + rank_seed)
@@ -161,7 +169,7 @@ def run_reference(a, rank):
                       "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "u8 / int32 popcount matching + f64 optimisation (host CPU)", "data": "synthetic",
                       "config": workload_config(a),
-                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "build_flags": CPU_FLAGS},
                       "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -222,6 +230,7 @@ def main():
             getattr(prev, k)[lo:hi] = getattr(part, k)
     popc_peak, fp64_peak = ctx.measure_peaks()
     alu_peak = ctx.measure_alu_peak()
+    int8_peak_measured = ctx.measure_int8_peak()
     # a previous frame holds only its stereo survivors: pack its rows with the tightest common stride
     prev = prev.repack(pinned=True)
     compact = S.CompactInputNP(d["curr_raw"], prev, pinned=True)   # e2e uploads the compact step input (gfpl_compact_input)
@@ -234,11 +243,13 @@ def main():
     gather_out = torch.empty(world * pose_bytes, dtype=torch.uint8, device="cuda") if world > 1 else None
     pose_dev = torch.as_tensor(DevArray(rp.pose_device_ptr(), pose_bytes), device="cuda") if world > 1 else None
 
+    lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+
     def step():
         rp.run(flags)
-        if world > 1:                     # K7: the only collective — gather the per-pair pose records
-            ctx.sync()
-            dist.all_gather_into_tensor(gather_out, pose_dev)
+        if world > 1:                     # K7: the only collective — gather the per-pair pose records.  Ordered on the
+            with torch.cuda.stream(lib_stream):   # device behind the step (library stream), no host synchronisation
+                dist.all_gather_into_tensor(gather_out, pose_dev)
 
     def barrier():
         ctx.sync()
@@ -247,35 +258,45 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    # ---- per-kernel times: the step unpipelined (kernels strictly back to back on one stream), CUDA events between
+    # the kernels; not the headline — it explains it -----------------------------------------------------------------
+    for _ in range(a.warmup):
+        rp.run(flags)
+    barrier()
+    stage = np.zeros(S.NUM_STAGES)
+    nstage = max(3, min(a.steps, 10))
+    for _ in range(nstage):
+        rp.run(flags)
+        stage += np.array(rp.stage_ms())  # per-kernel CUDA-event times of this step (sync on the step's last event)
+    stage /= nstage
+    pairs = rp.pair_counts()
+    serial_ms = float(stage[-1])
+    # ---- value: inputs resident in HBM, K steps of the pipelined replay, CUDA events on the context stream ----------
+    rp.set_pipeline(a.pipeline)
     for _ in range(a.warmup):
         step()
     barrier()
-    # ---- value: inputs resident in HBM, K steps, CUDA events on the launching stream ----------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
     launches0 = ctx.launch_count()
-    stage = np.zeros(S.NUM_STAGES)
     barrier()
     ctx.timer_record(0)
     for _ in range(a.steps):
         step()
-        stage += np.array(rp.stage_ms())  # per-kernel CUDA-event times of this step (sync on the step's last event)
-    torch.cuda.synchronize()
-    ctx.timer_record(1)
+    ctx.timer_record(1)        # the context stream waits for every sub-batch of every step
     ms = ctx.timer_elapsed_ms(0, 1)
     barrier()
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    stage /= a.steps
-    pairs = rp.pair_counts()
+    rp.set_pipeline(1)
 
     # ---- e2e: host buffers in, pose records out.  Streaming replay: NSLOT resident slots (one context = one
     # stream each); step k uploads / runs / downloads in slot k % NSLOT, so the H2D copy of step k overlaps the
     # kernels of the steps before it.  Every step's copies are inside the timed region; the host consumes the
     # pose records of step k-LAG while step k is in flight. -----------------------------------------------------
-    NSLOT, LAG = 4, 3
+    NSLOT, LAG = 5, 3
     slots = [(ctx, rp)]
     for _ in range(NSLOT - 1):
         c = api.Context(local, cam=d["cam"])
@@ -283,6 +304,7 @@ def main():
     pose_hosts = [pose_host] + [S._alloc(B, S.pose_result_dt, True) for _ in range(NSLOT - 1)]
     pose_devs = [torch.as_tensor(DevArray(r.pose_device_ptr(), pose_bytes), device="cuda") if world > 1 else None
                  for _, r in slots]
+    slot_streams = [torch.cuda.ExternalStream(c.stream(), device=torch.device("cuda", local)) for c, _ in slots]
     h2d = d2h = 0
 
     def e2e_enqueue(k):
@@ -294,9 +316,10 @@ def main():
         h2d, d2h = r.h2d_bytes(), r.d2h_bytes()
 
     def e2e_consume(k):
-        slots[k % NSLOT][0].sync()        # step k's pose records are on the host now
-        if world > 1:
-            dist.all_gather_into_tensor(gather_out, pose_devs[k % NSLOT])
+        if world > 1:                     # gather behind step k on its slot's stream: the slot's next upload / run are
+            with torch.cuda.stream(slot_streams[k % NSLOT]):   # enqueued on the same stream, i.e. after the gather
+                dist.all_gather_into_tensor(gather_out, pose_devs[k % NSLOT])
+        slots[k % NSLOT][0].sync()        # step k's pose records are on the host now (and the gather has read them)
 
     def e2e_run(nsteps):
         for k in range(nsteps):
@@ -333,19 +356,32 @@ def main():
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         mp = json.load(open(peaks_file)) if os.path.exists(peaks_file) else {}
         hbm_peak = mp.get("hbm_gbs", 6650.0)
-        bf16_peak = mp.get("bf16_tflops_sustained", 1590.0)       # kernel timed inside a long step -> sustained figure
-        int8_peak = 2.0 * bf16_peak                               # int8 dense = 2x bf16 dense on B200 (4.5 vs 2.25 P nominal)
+        # tensor denominator: dense tcgen05.mma kind::i8 measured live by gfpl_measure_int8_peak (one CTA per SM, operands
+        # resident in shared memory); 2 x the driver-measured bf16 burst figure is printed beside it
+        int8_peak = int8_peak_measured
+        int8_from_bf16 = 2.0 * mp.get("bf16_tflops", 1620.7)
         tc_on = os.environ.get("GFPL_NO_TC") is None
         pose_all = np.concatenate(pose_hosts)
         ok = pose_all["status"] == 0
         gn_flops = float(((pose_all["iters_first"] + pose_all["iters_ref"]) * (114.0 * pose_all["n_inliers_pt"] + 212.0 * pose_all["n_inliers_ls"]))[ok].sum()) / len(pose_hosts)
+
+        # per-launch hardware counters of the same workload from the committed ncu --set full capture
+        counters, counters_match = {}, False
+        cj = os.path.join(ROOT, "profiles", COUNTERS_FILE)
+        if os.path.exists(cj):
+            cdoc = json.load(open(cj))
+            counters = cdoc.get("per_launch", {})
+            counters_match = cdoc.get("pairs") == B and cdoc.get("n_pt") == a.n_pt and cdoc.get("n_ln") == a.n_ln
+        lc = counters.get("linecut_kernel") if counters_match else None
+        linecut_flops = float(lc["fp64_flops"]) if lc and lc.get("fp64_flops") else None
 
         def tensor_roof(name, n_pairs, dirs, t_ms):
             ops = n_pairs * 512.0 * dirs
             return {"kernel": name, "bound": "tensor", "achieved": ops / (t_ms * 1e-3) / 1e12, "peak": int8_peak, "unit": "TOP/s (int8)",
                     "frac": ops / (t_ms * 1e-3) / 1e12 / int8_peak, "kernel_ms": t_ms, "distances_per_launch": n_pairs,
                     "distances_Tps": n_pairs * dirs / (t_ms * 1e-3) / 1e12,
-                    "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops_sustained (int8 dense rate = 2 x bf16)" if mp else "2 x fallback 1.59 PF"}
+                    "peak_source": "gfpl_measure_int8_peak: dense tcgen05.mma.kind::i8 M128 N256 K256 micro-kernel, measured in this run "
+                                   "(2 x MEASURED_PEAKS.json bf16 burst = %.0f)" % int8_from_bf16}
 
         def int_roof(name, n_pairs, popc_pp, alu_pp, t_ms):
             pk = min(popc_peak / popc_pp, alu_peak / alu_pp)
@@ -364,31 +400,28 @@ def main():
             else int_roof("knn2_sym_kernel<HAMMING2,1>: stereo lines, both directions from one pass", pairs[1], 8.0, 35.0, stage[1]),
             tensor_roof("f2f_hybrid_points_tc_kernel: radius + projection-gate search", pairs[2], 1, stage[3]) if tc_on
             else int_roof("f2f_hybrid_points_kernel", pairs[2], 5.0, 21.0, stage[3]),
-            {"kernel": "linecut_kernel (+ stereo_uncertainty)", "bound": "fp64 latency", "kernel_ms": float(stage[6]),
-             "note": "sequential greedy search per pair (8 lanes per pair, ~250 rounds of 8 candidates); one wave of 16 warps / SM, bound by the latency of the per-pair chain (profiles/)"},
-            {"kernel": "pose_optimize_kernel (+ finalize)", "bound": "fp64 latency", "achieved": gn_flops / (stage[7] * 1e-3) / 1e12,
+            (lambda fl: {"kernel": "linecut_kernel (+ stereo_uncertainty)", "bound": "fp64", "kernel_ms": float(stage[6]),
+                         "achieved": fl / (stage[6] * 1e-3) / 1e12 if fl else None, "peak": fp64_peak, "unit": "TFLOP/s (fp64)",
+                         "frac": fl / (stage[6] * 1e-3) / 1e12 / fp64_peak if fl else None,
+                         "flops_source": "executed fp64 flops of one launch (ncu sm__sass_thread_inst_executed_op_d{add,mul,fma}_pred_on, "
+                                         "fma = 2; profiles/%s) scaled by the batch size" % COUNTERS_FILE if fl else "no counter file for this workload",
+                         "note": "sequential greedy search per pair (8 lanes per pair, ~250 rounds of 8 candidates): latency of the per-pair chain"})(
+                linecut_flops),
+            {"kernel": "pose_optimize_kernel (+ finalize)", "bound": "fp64", "achieved": gn_flops / (stage[7] * 1e-3) / 1e12,
              "peak": fp64_peak, "unit": "TFLOP/s (fp64)", "frac": gn_flops / (stage[7] * 1e-3) / 1e12 / fp64_peak, "kernel_ms": float(stage[7]),
              "note": "algorithmic flops = GN iterations x (114 per inlier point + 212 per inlier line); 16 lanes per pair (two pairs per warp), serial 6x6 solve per iteration"},
         ]
-        roofline = dict(by_kernel[0])
+        # the bench line's `roofline` is the kernel with the largest share of the (unpipelined) step
+        roofline = dict(max(by_kernel, key=lambda r: r["kernel_ms"]))
         alg_bytes = B * (2 * a.n_pt * 32 + 2 * a.n_pt * 16)
-        traffic = None   # dram__bytes_read+write per launch, from the committed ncu --set full capture of the same workload
-        tj = os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")
-        if os.path.exists(tj) and B == 8192 and a.n_pt == 300:
-            t = json.load(open(tj))["per_launch"].get("knn2_tc_kernel@8192" if tc_on else "knn2_sym_kernel<6, 2>@8192")
-            if t:
-                traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
+        traffic = (counters.get(roofline["kernel"].split(":")[0].split(" ")[0], {}) or {}).get("dram_bytes") if counters_match else None
         roofline.update({"traffic": traffic,
-                         "traffic_note": "bytes; DRAM read+write of one launch (profiles/r1_ncu_full_summary.md); algorithmic bytes = %d "
-                                         "(descriptors in, knn records out)" % alg_bytes,
-                         "hbm": {"achieved_GBps": alg_bytes / (stage[0] * 1e-3) / 1e9, "peak_GBps": hbm_peak,
-                                 "note": "algorithmic bytes of this launch: the kernel is not HBM-bound"},
-                         "why_this_kernel": "largest kernel of the matching path (north star); by single-kernel time linecut_kernel and "
-                                            "pose_optimize_kernel are larger, see roofline_by_kernel",
+                         "traffic_note": "bytes; DRAM read+write of one launch of this kernel (profiles/%s)" % COUNTERS_FILE,
+                         "why_this_kernel": "largest kernel by time of the unpipelined step; every kernel >= 5 %% of the step is in roofline_by_kernel",
                          "measured_pipe_peaks": {"popc_Tops": popc_peak, "alu_lop3_Tops": alu_peak, "fp64_TFLOPs": fp64_peak,
-                                                 "int8_tensor_TOPs": int8_peak}})
+                                                 "int8_tensor_TOPs": int8_peak, "int8_2x_bf16_burst_TOPs": int8_from_bf16, "hbm_GBps": hbm_peak}})
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-               "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "ms_per_step": ms / a.steps, "ms_per_step_unpipelined": serial_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u8 descriptors -> int8 tensor-core / int32 popcount matching (exact) + f64 optimisation", "data": "synthetic", "config": workload_config(a),
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                        "ms_per_step": e2e_ms / a.steps, "pipeline": "%d resident slots / streams: H2D of step k overlaps the kernels of earlier steps; results consumed %d steps later" % (NSLOT, LAG),
@@ -397,7 +430,8 @@ def main():
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_by_kernel": by_kernel,
                "kernel_ms_per_step": dict(zip(["knn_stereo_pt", "knn_stereo_ln", "stereo_accept", "f2f_pt_search", "knn_f2f_ln",
                                                "f2f_accept", "uncertainty+linecut", "pose_gn", "step"], [float(x) for x in stage])),
-               "peaks": {"popc_Tops": popc_peak, "alu_lop3_Tops": alu_peak, "fp64_TFLOPs": fp64_peak}}
+               "kernel_ms_note": "CUDA events between the kernels of the UNPIPELINED step (one stream); the headline value runs the same kernels pipelined over %d sub-batches" % a.pipeline,
+               "peaks": {"popc_Tops": popc_peak, "alu_lop3_Tops": alu_peak, "fp64_TFLOPs": fp64_peak, "int8_tensor_TOPs": int8_peak}}
         # C3 side note: one Levenberg-Marquardt pass of local BA (assembly + damped Schur solve) on a
         # KITTI-shaped 10-key-frame window, through the C ABI with host buffers (copies included)
         try:
@@ -416,7 +450,7 @@ def main():
             n, cores, cstep = cpu_reference(a)
             cstep()
             dt = cstep()
-            out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port", "build_flags": CPU_FLAGS,
                                    "sample": "%d of %d pairs, one pass, %d std::threads over pairs (oracle port of the "
                                              "reference algorithm)" % (n, B, cores)}
             out["cpu_baseline"].update(cpu_extras(a))

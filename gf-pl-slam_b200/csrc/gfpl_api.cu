@@ -37,26 +37,63 @@ struct DevMem {
   T* alloc(size_t n) {
     void* p = nullptr;
     if (n == 0) n = 1;
-    if (cudaMallocAsync(&p, n * sizeof(T), ctx->stream) != cudaSuccess) return nullptr;
+    const cudaError_t e = ctx->pool ? cudaMallocFromPoolAsync(&p, n * sizeof(T), ctx->pool, ctx->stream)
+                                    : cudaMallocAsync(&p, n * sizeof(T), ctx->stream);
+    if (e != cudaSuccess) { cudaGetLastError(); return nullptr; }
     ptrs.push_back(p);
     return (T*)p;
   }
   template <typename T>
   T* upload(const T* host, size_t n) {
     T* d = alloc<T>(n);
-    if (d && n && host) cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+    if (d && n && host) {
+      const cudaError_t e = cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+      if (e != cudaSuccess) {   // reported as a failed mirror (REQUIRE_MEM) and again by finish()
+        if (ctx->pending_error == cudaSuccess) ctx->pending_error = e;
+        return nullptr;
+      }
+    }
     return d;
   }
 };
 
 template <typename T>
 static inline void download(gfpl_ctx* ctx, T* host, const T* dev, size_t n) {
-  if (host && n) cudaMemcpyAsync(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream);
+  if (host && n) {
+    const cudaError_t e = cudaMemcpyAsync(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e != cudaSuccess && ctx->pending_error == cudaSuccess) ctx->pending_error = e;
+  }
 }
 
+// end of a host-pointer entry point: results are on the host, and no copy of the call was dropped
 static int finish(gfpl_ctx* ctx) {
   GFPL_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->pending_error != cudaSuccess) {
+    const cudaError_t e = ctx->pending_error;
+    ctx->pending_error = cudaSuccess;
+    set_last_error(ctx, "an asynchronous copy of this call failed: %s", cudaGetErrorString(e));
+    return GFPL_E_CUDA;
+  }
   return GFPL_OK;
+}
+
+// per-problem counts of a batched view: every one within [0, cap] (the kernels size shared memory and output rows by
+// the capacities and trust the counts)
+static bool counts_ok(const int32_t* n, size_t B, int cap) {
+  if (!n) return false;
+  for (size_t p = 0; p < B; p++)
+    if (n[p] < 0 || n[p] > cap) return false;
+  return true;
+}
+static bool raw_counts_ok(const gfpl_raw_frames* h) {
+  return h->cap_pt >= 0 && h->cap_ln >= 0 && counts_ok(h->n_pt_l, h->B, h->cap_pt) && counts_ok(h->n_pt_r, h->B, h->cap_pt) &&
+         counts_ok(h->n_ln_l, h->B, h->cap_ln) && counts_ok(h->n_ln_r, h->B, h->cap_ln);
+}
+static bool stereo_counts_ok(const gfpl_stereo_frames* h) {
+  return h->cap_pt >= 0 && h->cap_ln >= 0 && counts_ok(h->n_pt, h->B, h->cap_pt) && counts_ok(h->n_ln, h->B, h->cap_ln);
+}
+static bool obs_counts_ok(const gfpl_track_obs* h) {
+  return h->cap_pt >= 0 && h->cap_ln >= 0 && counts_ok(h->n_pt, h->B, h->cap_pt) && counts_ok(h->n_ln, h->B, h->cap_ln);
 }
 
 // device mirrors of the batched views -------------------------------------------------------------
@@ -226,10 +263,20 @@ int gfpl_ctx_create(int device, const gfpl_camera* cam, const gfpl_config* cfg, 
     delete ctx;
     return GFPL_E_CUDA;
   }
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    uint64_t keep = ~0ull;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  {  // scratch of the host-pointer entry points: a pool of this context's own (cached between calls, returned to the
+     // driver by gfpl_ctx_destroy; the process-wide default pool is left alone)
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    if (cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+      cudaGetLastError();
+      ctx->pool = nullptr;   // fall back to the default pool with its default release policy
+    }
   }
   if (cam) ctx->cam = *cam; else gfpl_camera_euroc(&ctx->cam);
   if (cfg) ctx->cfg = *cfg; else gfpl_config_default(&ctx->cfg);
@@ -244,6 +291,7 @@ void gfpl_ctx_destroy(gfpl_ctx* ctx) {
   for (auto& e : ctx->timer)
     if (e) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   delete ctx;
 }
 
@@ -263,6 +311,7 @@ int gfpl_ctx_sync(gfpl_ctx* ctx) {
   return finish(ctx);
 }
 int64_t gfpl_ctx_launch_count(const gfpl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* gfpl_ctx_stream(gfpl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 // ---- M1/M2 --------------------------------------------------------------------------------------------
 int gfpl_knn2_hamming256_batch(gfpl_ctx* ctx, int32_t B, const uint8_t* q, const int32_t* nq, int32_t cap_q,
@@ -273,6 +322,8 @@ int gfpl_knn2_hamming256_batch(gfpl_ctx* ctx, int32_t B, const uint8_t* q, const
   REQUIRE(ctx, norm == GFPL_NORM_HAMMING || norm == GFPL_NORM_HAMMING2);
   if (B == 0 || cap_q == 0) return GFPL_OK;
   REQUIRE(ctx, q && nq && t && nt && out_idx && out_dist && cap_t > 0);
+  REQUIRE(ctx, cap_q < GFPL_MAX_KNN_ROWS && cap_t < GFPL_MAX_KNN_ROWS);   // the sort key packs a row index in 20 bits
+  REQUIRE(ctx, counts_ok(nq, B, cap_q) && counts_ok(nt, B, cap_t));
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   DevMem m(ctx);
   size_t nqt = (size_t)B * cap_q, ntt = (size_t)B * cap_t;
@@ -299,6 +350,8 @@ int gfpl_knn2_mutual_batch(gfpl_ctx* ctx, int32_t B, const uint8_t* q, const int
   REQUIRE(ctx, norm == GFPL_NORM_HAMMING || norm == GFPL_NORM_HAMMING2);
   if (B == 0) return GFPL_OK;
   REQUIRE(ctx, q && nq && t && nt && out_idx && out_dist && out_best_idx && out_best_dist);
+  REQUIRE(ctx, cap_q < GFPL_MAX_KNN_ROWS && cap_t < GFPL_MAX_KNN_ROWS);
+  REQUIRE(ctx, counts_ok(nq, B, cap_q) && counts_ok(nt, B, cap_t));
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   DevMem m(ctx);
   size_t nqt = (size_t)B * cap_q, ntt = (size_t)B * cap_t;
@@ -337,6 +390,7 @@ int gfpl_radius_hamming256(gfpl_ctx* ctx, const uint8_t* q, int32_t nq, const ui
                            float radius, int32_t* offsets, int32_t* out_idx, float* out_dist, int32_t cap) {
   if (!ctx) return GFPL_E_INVALID;
   REQUIRE(ctx, nq >= 0 && nt >= 0 && offsets && cap >= 0);
+  REQUIRE(ctx, nq < GFPL_MAX_KNN_ROWS && nt < GFPL_MAX_KNN_ROWS);
   REQUIRE(ctx, norm == GFPL_NORM_HAMMING || norm == GFPL_NORM_HAMMING2);
   offsets[0] = 0;
   if (nq == 0) return GFPL_OK;
@@ -375,6 +429,12 @@ int gfpl_measure_alu_peak(gfpl_ctx* ctx, double* lop3_tops) {
   return launch_measure_alu_peak(ctx, lop3_tops);
 }
 
+int gfpl_measure_int8_peak(gfpl_ctx* ctx, double* int8_tops) {
+  if (!ctx || !int8_tops) return GFPL_E_INVALID;
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  return launch_measure_int8_peak(ctx, int8_tops);
+}
+
 int gfpl_measure_peaks(gfpl_ctx* ctx, double* popc_tops, double* fp64_tflops) {
   if (!ctx || !popc_tops || !fp64_tflops) return GFPL_E_INVALID;
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
@@ -408,13 +468,50 @@ static bool alloc_work(DevMem& m, int B, int cap_pt, int cap_ln, StepWork* w) {
   return ok && w->best_key && w->prev_cov && w->f2f_T;
 }
 
+// ---- views of the pairs [lo, lo + n) of a batch (every array is [B][cap]: a view is a pointer offset) ---------
+static Knn2Out slice(const Knn2Out& k, size_t off) { return Knn2Out{k.idx ? k.idx + off : nullptr, k.dist ? k.dist + off : nullptr}; }
+static DevRawFrames slice(const DevRawFrames& r, int lo, int n) {
+  DevRawFrames v = r;
+  const size_t op = (size_t)lo * r.cap_pt, ol = (size_t)lo * r.cap_ln;
+  v.B = n;
+  v.n_pt_l += lo; v.n_pt_r += lo; v.n_ln_l += lo; v.n_ln_r += lo;
+  v.pt_l += op; v.pt_r += op; v.pdesc_l += op * 32; v.pdesc_r += op * 32;
+  v.ln_l += ol; v.ln_r += ol; v.ldesc_l += ol * 32; v.ldesc_r += ol * 32;
+  return v;
+}
+static DevStereoFrames slice(const DevStereoFrames& f, int lo, int n) {
+  DevStereoFrames v = f;
+  const size_t op = (size_t)lo * f.cap_pt, ol = (size_t)lo * f.cap_ln;
+  v.B = n;
+  v.n_pt += lo; v.n_ln += lo;
+  v.pt += op; v.pdesc += op * 32; v.ln += ol; v.ldesc += ol * 32;
+  return v;
+}
+static DevTrackObs slice(const DevTrackObs& o, int lo, int n) {
+  DevTrackObs v = o;
+  const size_t op = (size_t)lo * o.cap_pt, ol = (size_t)lo * o.cap_ln;
+  v.B = n;
+  v.n_pt += lo; v.n_ln += lo;
+  v.pt += op; v.pt_inlier += op; v.ln += ol; v.ln_inlier += ol;
+  return v;
+}
+// cap_pt / cap_ln: the strides the scratch was allocated with
+static StepWork slice(const StepWork& w, int lo, int cap_pt, int cap_ln) {
+  StepWork v = w;
+  const size_t op = (size_t)lo * cap_pt, ol = (size_t)lo * cap_ln;
+  v.pt_lr = slice(w.pt_lr, op); v.pt_rl = slice(w.pt_rl, op); v.pt_12 = slice(w.pt_12, op); v.pt_21 = slice(w.pt_21, op);
+  v.ln_lr = slice(w.ln_lr, ol); v.ln_rl = slice(w.ln_rl, ol); v.ln_12 = slice(w.ln_12, ol); v.ln_21 = slice(w.ln_21, ol);
+  v.best_key += op; v.prev_cov += ol; v.f2f_T += (size_t)lo * 32;
+  return v;
+}
+
 static int run_stereo(gfpl_ctx* ctx, const DevRawFrames& raw, int variant, StepWork& w, DevStereoFrames curr,
                       cudaEvent_t mid = nullptr) {
   const int B = raw.B;
   if (ctx->cfg.has_points)
     CHECK(launch_knn2(ctx, B, raw.pdesc_l, raw.n_pt_l, raw.cap_pt, raw.pdesc_r, raw.n_pt_r, raw.cap_pt,
                       GFPL_NORM_HAMMING, w.pt_lr, ctx->cfg.best_lr_matches ? w.pt_rl : Knn2Out{}, true));
-  if (mid) cudaEventRecord(mid, ctx->stream);
+  if (mid) GFPL_CUDA_OK(ctx, cudaEventRecord(mid, ctx->stream));
   if (ctx->cfg.has_lines)
     CHECK(launch_knn2(ctx, B, raw.ldesc_l, raw.n_ln_l, raw.cap_ln, raw.ldesc_r, raw.n_ln_r, raw.cap_ln,
                       variant == GFPL_STEREO_INITIAL ? GFPL_NORM_HAMMING : GFPL_NORM_HAMMING2, w.ln_lr,
@@ -438,7 +535,7 @@ static int run_f2f_knn(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevSter
       CHECK(launch_f2f_hybrid_points_knn(ctx, prev, curr, state, w.pt_12, w.best_key));
     }
   }
-  if (mid) cudaEventRecord(mid, ctx->stream);
+  if (mid) GFPL_CUDA_OK(ctx, cudaEventRecord(mid, ctx->stream));
   if (ctx->cfg.has_lines)
     CHECK(launch_knn2(ctx, B, prev.ldesc, prev.n_ln, prev.cap_ln, curr.ldesc, curr.n_ln, curr.cap_ln,
                       GFPL_NORM_HAMMING, w.ln_12, ctx->cfg.best_lr_matches ? w.ln_21 : Knn2Out{}, true));
@@ -463,6 +560,15 @@ struct gfpl_replay {
   cudaEvent_t ev[GFPL_NUM_STAGES] = {};
   int64_t h2d = 0, d2h = 0;
   bool timed = false;
+  void* pose_raw = nullptr;   // optimiser -> finalize hand-off, [B]
+  // software pipeline over sub-batches (gfpl_replay_set_pipeline)
+  int n_sub = 1;
+  cudaStream_t s_match = nullptr;
+  cudaStream_t s_solve[GFPL_MAX_SUBBATCHES] = {};
+  cudaEvent_t ev_match[GFPL_MAX_SUBBATCHES] = {}, ev_solve[GFPL_MAX_SUBBATCHES] = {};
+  cudaEvent_t ev_input = nullptr;
+  bool solve_pending[GFPL_MAX_SUBBATCHES] = {};   // ev_solve[k] was recorded by an earlier run
+  bool input_dirty = true;                        // the context stream touched the inputs since the last run
   template <typename T>
   T* alloc(size_t n) {
     void* p = nullptr;
@@ -480,6 +586,7 @@ int gfpl_stereo_match(gfpl_ctx* ctx, const gfpl_raw_frames* raw, int32_t variant
   REQUIRE(ctx, out->cap_pt >= raw->cap_pt && out->cap_ln >= raw->cap_ln);
   REQUIRE(ctx, variant == GFPL_STEREO_INITIAL || variant == GFPL_STEREO_BRUTE);
   if (raw->B == 0) return GFPL_OK;
+  REQUIRE(ctx, raw_counts_ok(raw) && raw->cap_pt < GFPL_MAX_KNN_ROWS && raw->cap_ln < GFPL_MAX_KNN_ROWS);
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   DevMem m(ctx);
   DevRawFrames draw;
@@ -503,6 +610,7 @@ int gfpl_stereo_match_orbslam(gfpl_ctx* ctx, const gfpl_raw_frames* raw, const g
     REQUIRE(ctx, pyr->offset[l] + (int64_t)pyr->row_stride[l] * (pyr->height[l] - 1) + pyr->width[l] <= pyr->frame_stride);
   }
   if (raw->B == 0) return GFPL_OK;
+  REQUIRE(ctx, raw_counts_ok(raw) && raw->cap_pt < GFPL_MAX_KNN_ROWS && raw->cap_ln < GFPL_MAX_KNN_ROWS);
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   DevMem m(ctx);
   DevRawFrames draw;
@@ -526,6 +634,7 @@ int gfpl_stereo_uncertainty(gfpl_ctx* ctx, const gfpl_stereo_frames* frames, gfp
   if (!ctx) return GFPL_E_INVALID;
   REQUIRE(ctx, frames && out && frames->B >= 0);
   if (frames->B == 0 || frames->cap_ln == 0) return GFPL_OK;
+  REQUIRE(ctx, stereo_counts_ok(frames));
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   DevMem m(ctx);
   DevStereoFrames d;
@@ -546,6 +655,9 @@ int gfpl_f2f_match(gfpl_ctx* ctx, const gfpl_stereo_frames* prev, const gfpl_ste
   REQUIRE(ctx, mode == GFPL_F2F_HYBRID || mode == GFPL_F2F_BRUTE);
   REQUIRE(ctx, out->cap_pt > 0 && out->cap_ln > 0);
   if (prev->B == 0) return GFPL_OK;
+  REQUIRE(ctx, stereo_counts_ok(prev) && stereo_counts_ok(curr));
+  REQUIRE(ctx, prev->cap_pt < GFPL_MAX_KNN_ROWS && curr->cap_pt < GFPL_MAX_KNN_ROWS && prev->cap_ln < GFPL_MAX_KNN_ROWS &&
+                   curr->cap_ln < GFPL_MAX_KNN_ROWS);
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   DevMem m(ctx);
   DevStereoFrames dp, dc;
@@ -569,6 +681,9 @@ int gfpl_kf_match(gfpl_ctx* ctx, const gfpl_stereo_frames* kf0, const gfpl_stere
   REQUIRE(ctx, kf0 && kf1 && DT && out && kf0->B == kf1->B && kf0->B == out->B && kf0->B >= 0);
   REQUIRE(ctx, out->cap_pt > 0 && out->cap_ln > 0);
   if (kf0->B == 0) return GFPL_OK;
+  REQUIRE(ctx, stereo_counts_ok(kf0) && stereo_counts_ok(kf1));
+  REQUIRE(ctx, kf0->cap_pt < GFPL_MAX_KNN_ROWS && kf1->cap_pt < GFPL_MAX_KNN_ROWS && kf0->cap_ln < GFPL_MAX_KNN_ROWS &&
+                   kf1->cap_ln < GFPL_MAX_KNN_ROWS);
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   DevMem m(ctx);
   DevStereoFrames d0, d1;
@@ -598,6 +713,9 @@ int gfpl_map_match(gfpl_ctx* ctx, const gfpl_local_map* map, const gfpl_stereo_f
   REQUIRE(ctx, map && kf1 && Twf && out && map->B == kf1->B && map->B == out->B && map->B >= 0);
   REQUIRE(ctx, out->cap_pt > 0 && out->cap_ln > 0 && map->cap_pt > 0 && map->cap_ln > 0 && kf1->cap_pt > 0 && kf1->cap_ln > 0);
   if (map->B == 0) return GFPL_OK;
+  REQUIRE(ctx, counts_ok(map->n_pt, map->B, map->cap_pt) && counts_ok(map->n_ln, map->B, map->cap_ln) && stereo_counts_ok(kf1));
+  REQUIRE(ctx, map->cap_pt < GFPL_MAX_KNN_ROWS && map->cap_ln < GFPL_MAX_KNN_ROWS && kf1->cap_pt < GFPL_MAX_KNN_ROWS &&
+                   kf1->cap_ln < GFPL_MAX_KNN_ROWS);
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   DevMem m(ctx);
   const size_t B = map->B, mp = B * map->cap_pt, ml = B * map->cap_ln, kp = B * kf1->cap_pt, kl = B * kf1->cap_ln;
@@ -659,6 +777,7 @@ int gfpl_linecut_submodular(gfpl_ctx* ctx, const double* DT_inv, gfpl_track_obs*
   if (!ctx) return GFPL_E_INVALID;
   REQUIRE(ctx, DT_inv && obs && prev_cov && cut && obs->B >= 0 && cov_cap > 0);
   if (obs->B == 0) return GFPL_OK;
+  REQUIRE(ctx, obs_counts_ok(obs));
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   DevMem m(ctx);
   DevTrackObs dobs;
@@ -679,6 +798,7 @@ int gfpl_pose_hg(gfpl_ctx* ctx, const double* DT, const gfpl_track_obs* obs, dou
   if (!ctx) return GFPL_E_INVALID;
   REQUIRE(ctx, DT && obs && H && g && e && obs->B >= 0);
   if (obs->B == 0) return GFPL_OK;
+  REQUIRE(ctx, obs_counts_ok(obs));
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   DevMem m(ctx);
   DevTrackObs dobs;
@@ -702,6 +822,7 @@ int gfpl_pose_optimize(gfpl_ctx* ctx, gfpl_track_obs* obs, const gfpl_frame_stat
   REQUIRE(ctx, obs && state && out && obs->B >= 0);
   REQUIRE(ctx, overload == GFPL_POSE_SEED_PREV_DT || overload == GFPL_POSE_SEED_GIVEN);
   if (obs->B == 0) return GFPL_OK;
+  REQUIRE(ctx, obs_counts_ok(obs));
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   DevMem m(ctx);
   DevTrackObs dobs;
@@ -719,29 +840,42 @@ int gfpl_pose_optimize(gfpl_ctx* ctx, gfpl_track_obs* obs, const gfpl_frame_stat
 }
 
 // ---- whole step ------------------------------------------------------------------------------------------
-static int run_step(gfpl_ctx* ctx, const DevStereoFrames& prev, const gfpl_frame_state* state, const DevRawFrames& raw,
-                    int flags, DevStereoFrames curr, DevTrackObs obs, gfpl_line_cut* cut, gfpl_pose_result* pose,
-                    StepWork& w, cudaEvent_t* ev) {
+// The step in two halves.  run_match: everything up to the matched observation lists (tensor / integer pipes);
+// run_solve: stereo uncertainty + line cut + pose optimisation (fp64, latency-bound).  ev: 9 stage events or NULL.
+static int run_match(gfpl_ctx* ctx, const DevStereoFrames& prev, const gfpl_frame_state* state, const DevRawFrames& raw,
+                     int flags, DevStereoFrames curr, DevTrackObs obs, StepWork& w, cudaEvent_t* ev) {
   const int variant = (flags & GFPL_TRACK_STEREO_INITIAL) ? GFPL_STEREO_INITIAL : GFPL_STEREO_BRUTE;
   const int mode = (flags & GFPL_TRACK_F2F_BRUTE) ? GFPL_F2F_BRUTE : GFPL_F2F_HYBRID;
-  if (ev) cudaEventRecord(ev[0], ctx->stream);
+  if (ev) GFPL_CUDA_OK(ctx, cudaEventRecord(ev[0], ctx->stream));
   CHECK(run_stereo(ctx, raw, variant, w, curr, ev ? ev[1] : nullptr));
-  if (ev) cudaEventRecord(ev[2], ctx->stream);
+  if (ev) GFPL_CUDA_OK(ctx, cudaEventRecord(ev[2], ctx->stream));
   CHECK(launch_stereo_accept(ctx, raw, variant, w.pt_lr, w.pt_rl, w.ln_lr, w.ln_rl, curr));
-  if (ev) cudaEventRecord(ev[3], ctx->stream);
+  if (ev) GFPL_CUDA_OK(ctx, cudaEventRecord(ev[3], ctx->stream));
   CHECK(run_f2f_knn(ctx, prev, curr, state, mode, w, ev ? ev[4] : nullptr));
-  if (ev) cudaEventRecord(ev[5], ctx->stream);
+  if (ev) GFPL_CUDA_OK(ctx, cudaEventRecord(ev[5], ctx->stream));
   CHECK(launch_f2f_accept(ctx, prev, curr, mode, w.best_key, w.pt_12, w.pt_21, w.ln_12, w.ln_21, obs));
-  if (ev) cudaEventRecord(ev[6], ctx->stream);
+  if (ev) GFPL_CUDA_OK(ctx, cudaEventRecord(ev[6], ctx->stream));
+  return GFPL_OK;
+}
+
+static int run_solve(gfpl_ctx* ctx, const DevStereoFrames& prev, const gfpl_frame_state* state, int flags, DevTrackObs obs,
+                     gfpl_line_cut* cut, gfpl_pose_result* pose, StepWork& w, cudaEvent_t* ev, void* pose_raw) {
   if ((flags & GFPL_TRACK_LINECUT) && ctx->cfg.use_line_conf_cut && cut) {
     CHECK(launch_stereo_uncertainty(ctx, prev, w.prev_cov));
     CHECK(launch_linecut(ctx, nullptr, state, obs, w.prev_cov, prev.cap_ln, cut));
   }
-  if (ev) cudaEventRecord(ev[7], ctx->stream);
+  if (ev) GFPL_CUDA_OK(ctx, cudaEventRecord(ev[7], ctx->stream));
   CHECK(launch_pose_optimize(ctx, obs, state, nullptr,
-                             (flags & GFPL_TRACK_SEED_GIVEN) ? GFPL_POSE_SEED_GIVEN : GFPL_POSE_SEED_PREV_DT, pose));
-  if (ev) cudaEventRecord(ev[8], ctx->stream);
+                             (flags & GFPL_TRACK_SEED_GIVEN) ? GFPL_POSE_SEED_GIVEN : GFPL_POSE_SEED_PREV_DT, pose, pose_raw));
+  if (ev) GFPL_CUDA_OK(ctx, cudaEventRecord(ev[8], ctx->stream));
   return GFPL_OK;
+}
+
+static int run_step(gfpl_ctx* ctx, const DevStereoFrames& prev, const gfpl_frame_state* state, const DevRawFrames& raw,
+                    int flags, DevStereoFrames curr, DevTrackObs obs, gfpl_line_cut* cut, gfpl_pose_result* pose,
+                    StepWork& w, cudaEvent_t* ev, void* pose_raw = nullptr) {
+  CHECK(run_match(ctx, prev, state, raw, flags, curr, obs, w, ev));
+  return run_solve(ctx, prev, state, flags, obs, cut, pose, w, ev, pose_raw);
 }
 
 int gfpl_track(gfpl_ctx* ctx, const gfpl_stereo_frames* prev, const gfpl_frame_state* state,
@@ -754,6 +888,9 @@ int gfpl_track(gfpl_ctx* ctx, const gfpl_stereo_frames* prev, const gfpl_frame_s
   REQUIRE(ctx, curr->cap_pt == curr_raw->cap_pt && curr->cap_ln == curr_raw->cap_ln);
   REQUIRE(ctx, obs->cap_pt > 0 && obs->cap_ln > 0);
   if (B == 0) return GFPL_OK;
+  REQUIRE(ctx, raw_counts_ok(curr_raw) && stereo_counts_ok(prev));
+  REQUIRE(ctx, curr_raw->cap_pt < GFPL_MAX_KNN_ROWS && curr_raw->cap_ln < GFPL_MAX_KNN_ROWS && prev->cap_pt < GFPL_MAX_KNN_ROWS &&
+                   prev->cap_ln < GFPL_MAX_KNN_ROWS);
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   DevMem m(ctx);
   DevRawFrames draw;
@@ -824,9 +961,10 @@ int gfpl_replay_create_ex(gfpl_ctx* ctx, int32_t B, int32_t cap_pt, int32_t cap_
   w.best_key = rp->alloc<uint32_t>(np);
   w.prev_cov = rp->alloc<gfpl_line_cov>(nl);
   w.f2f_T = rp->alloc<double>((size_t)B * 32);
+  rp->pose_raw = rp->alloc<uint8_t>(pose_raw_bytes(B));
   bool ok = true;
   for (void* p : rp->owned) ok = ok && p;
-  ok = ok && rp->owned.size() == 12 + 12 + 6 + 3 + 16 + 3;
+  ok = ok && rp->owned.size() == 12 + 12 + 6 + 3 + 16 + 3 + 1;
   if (!ok || !w.prev_cov) {
     gfpl_replay_destroy(rp);
     set_last_error(ctx, "device allocation failed for a replay of %d pairs", B);
@@ -842,9 +980,18 @@ void gfpl_replay_destroy(gfpl_replay* rp) {
   if (!rp) return;
   cudaSetDevice(rp->ctx->device);
   cudaStreamSynchronize(rp->ctx->stream);
+  if (rp->s_match) cudaStreamSynchronize(rp->s_match);
+  for (auto& st : rp->s_solve)
+    if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  if (rp->s_match) cudaStreamDestroy(rp->s_match);
   for (void* p : rp->owned) cudaFree(p);
   for (auto& e : rp->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : rp->ev_match)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : rp->ev_solve)
+    if (e) cudaEventDestroy(e);
+  if (rp->ev_input) cudaEventDestroy(rp->ev_input);
   delete rp;
 }
 
@@ -871,6 +1018,7 @@ int gfpl_replay_upload(gfpl_replay* rp, const gfpl_stereo_frames* prev, const gf
   REQUIRE(ctx, raw->cap_pt == rp->cap_pt && raw->cap_ln == rp->cap_ln);
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   rp->h2d = 0;
+  rp->input_dirty = true;
   size_t B = rp->B, np = B * rp->cap_pt, nl = B * rp->cap_ln;
   H2D(rp->raw.n_pt_l, raw->n_pt_l, B); H2D(rp->raw.n_pt_r, raw->n_pt_r, B);
   H2D(rp->raw.n_ln_l, raw->n_ln_l, B); H2D(rp->raw.n_ln_r, raw->n_ln_r, B);
@@ -916,6 +1064,7 @@ int gfpl_replay_upload_slim(gfpl_replay* rp, const gfpl_prev_frames* prev, const
     REQUIRE_MEM(ctx, rp->slim.n_pt && rp->slim.n_ln && rp->slim.pt && rp->slim.ln);
   }
   rp->h2d = 0;
+  rp->input_dirty = true;
   H2D(rp->slim.n_pt, prev->n_pt, B); H2D(rp->slim.n_ln, prev->n_ln, B);
   H2D(rp->slim.pt, prev->pt, pp); H2D(rp->slim.ln, prev->ln, pl);
   H2D(rp->prev.pdesc, prev->pdesc, pp * 32); H2D(rp->prev.ldesc, prev->ldesc, pl * 32);
@@ -947,6 +1096,7 @@ int gfpl_replay_upload_compact(gfpl_replay* rp, const gfpl_compact_input* in, co
     d.pdesc_l = d.pdesc_r = d.ldesc_l = d.ldesc_r = d.prev_pdesc = d.prev_ldesc = nullptr;  // not staged
   }
   rp->h2d = 0;
+  rp->input_dirty = true;
   H2D(rp->raw.n_pt_l, in->n_pt_l, B); H2D(rp->raw.n_pt_r, in->n_pt_r, B);
   H2D(rp->raw.n_ln_l, in->n_ln_l, B); H2D(rp->raw.n_ln_r, in->n_ln_r, B);
   H2D(rp->prev.n_pt, in->prev_n_pt, B); H2D(rp->prev.n_ln, in->prev_n_ln, B);
@@ -963,12 +1113,96 @@ int gfpl_replay_upload_compact(gfpl_replay* rp, const gfpl_compact_input* in, co
   return launch_expand_compact(ctx, d, rp->raw, rp->prev);
 }
 
+int gfpl_replay_set_pipeline(gfpl_replay* rp, int32_t n_sub) {
+  if (!rp) return GFPL_E_INVALID;
+  gfpl_ctx* ctx = rp->ctx;
+  REQUIRE(ctx, n_sub >= 1 && n_sub <= GFPL_MAX_SUBBATCHES);
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  if (n_sub > 1) {
+    int lo_prio = 0, hi_prio = 0;   // numerically lower = higher priority
+    GFPL_CUDA_OK(ctx, cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    if (!rp->s_match) GFPL_CUDA_OK(ctx, cudaStreamCreateWithPriority(&rp->s_match, cudaStreamNonBlocking, lo_prio));
+    if (!rp->ev_input) GFPL_CUDA_OK(ctx, cudaEventCreateWithFlags(&rp->ev_input, cudaEventDisableTiming));
+    for (int k = 0; k < n_sub; k++) {
+      if (!rp->s_solve[k]) GFPL_CUDA_OK(ctx, cudaStreamCreateWithPriority(&rp->s_solve[k], cudaStreamNonBlocking, hi_prio));
+      if (!rp->ev_match[k]) GFPL_CUDA_OK(ctx, cudaEventCreateWithFlags(&rp->ev_match[k], cudaEventDisableTiming));
+      if (!rp->ev_solve[k]) GFPL_CUDA_OK(ctx, cudaEventCreateWithFlags(&rp->ev_solve[k], cudaEventDisableTiming));
+    }
+  }
+  // changing the split: drain what is in flight so that no sub-batch of the old split is still being written
+  if (rp->s_match) GFPL_CUDA_OK(ctx, cudaStreamSynchronize(rp->s_match));
+  for (int k = 0; k < GFPL_MAX_SUBBATCHES; k++) {
+    if (rp->s_solve[k]) GFPL_CUDA_OK(ctx, cudaStreamSynchronize(rp->s_solve[k]));
+    rp->solve_pending[k] = false;
+  }
+  rp->n_sub = n_sub;
+  rp->input_dirty = true;
+  return GFPL_OK;
+}
+
+// RAII: the launchers enqueue on ctx->stream; the pipeline points it at the stream of the stage being enqueued
+namespace {
+struct StreamSwap {
+  gfpl_ctx* ctx;
+  cudaStream_t saved;
+  explicit StreamSwap(gfpl_ctx* c) : ctx(c), saved(c->stream) {}
+  ~StreamSwap() { ctx->stream = saved; }
+};
+}  // namespace
+
+static int replay_run_pipelined(gfpl_replay* rp, int32_t flags) {
+  gfpl_ctx* ctx = rp->ctx;
+  const int S = rp->n_sub, B = rp->B;
+  const int wcp = rp->cap_pt, wcl = rp->cap_ln;   // strides of the scratch arrays
+  cudaStream_t main = ctx->stream;
+  // What the caller ordered on the context stream before this call precedes the step: uploads and downloads (they
+  // touch what the matching reads and writes) hold back the whole step; anything else — e.g. an NCCL gather of the
+  // previous step's pose records enqueued behind gfpl_ctx_stream — only the optimiser stages, which own the records.
+  GFPL_CUDA_OK(ctx, cudaEventRecord(rp->ev_input, main));
+  if (rp->input_dirty) {
+    GFPL_CUDA_OK(ctx, cudaStreamWaitEvent(rp->s_match, rp->ev_input, 0));
+    rp->input_dirty = false;
+  }
+  StreamSwap swap(ctx);
+  int last = -1;
+  for (int k = 0; k < S; k++) {
+    const int lo = (int)((int64_t)B * k / S), hi = (int)((int64_t)B * (k + 1) / S), n = hi - lo;
+    if (n <= 0) continue;
+    const DevRawFrames raw = slice(rp->raw, lo, n);
+    const DevStereoFrames prev = slice(rp->prev, lo, n), curr = slice(rp->curr, lo, n);
+    const DevTrackObs obs = slice(rp->obs, lo, n);
+    StepWork w = slice(rp->w, lo, wcp, wcl);
+    // the matching of this sub-batch rewrites obs / scratch that the previous run's optimiser of the same sub-batch reads
+    if (rp->solve_pending[k]) GFPL_CUDA_OK(ctx, cudaStreamWaitEvent(rp->s_match, rp->ev_solve[k], 0));
+    ctx->stream = rp->s_match;
+    CHECK(run_match(ctx, prev, rp->state + lo, raw, flags, curr, obs, w, nullptr));
+    GFPL_CUDA_OK(ctx, cudaEventRecord(rp->ev_match[k], rp->s_match));
+    GFPL_CUDA_OK(ctx, cudaStreamWaitEvent(rp->s_solve[k], rp->ev_match[k], 0));
+    GFPL_CUDA_OK(ctx, cudaStreamWaitEvent(rp->s_solve[k], rp->ev_input, 0));
+    ctx->stream = rp->s_solve[k];
+    CHECK(run_solve(ctx, prev, rp->state + lo, flags, obs, rp->cut + (size_t)lo * rp->obs.cap_ln, rp->pose + lo, w, nullptr,
+                    (uint8_t*)rp->pose_raw + (size_t)lo * pose_raw_bytes(1)));
+    GFPL_CUDA_OK(ctx, cudaEventRecord(rp->ev_solve[k], rp->s_solve[k]));
+    rp->solve_pending[k] = true;
+    last = k;
+  }
+  ctx->stream = main;
+  // everything the caller enqueues on the context stream after this call sees the finished step
+  for (int k = 0; k <= last; k++)
+    if (rp->solve_pending[k]) GFPL_CUDA_OK(ctx, cudaStreamWaitEvent(main, rp->ev_solve[k], 0));
+  return GFPL_OK;
+}
+
 int gfpl_replay_run(gfpl_replay* rp, int32_t flags) {
   if (!rp) return GFPL_E_INVALID;
   gfpl_ctx* ctx = rp->ctx;
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  if (rp->n_sub > 1) {
+    rp->timed = false;
+    return replay_run_pipelined(rp, flags);
+  }
   rp->timed = true;
-  return run_step(ctx, rp->prev, rp->state, rp->raw, flags, rp->curr, rp->obs, rp->cut, rp->pose, rp->w, rp->ev);
+  return run_step(ctx, rp->prev, rp->state, rp->raw, flags, rp->curr, rp->obs, rp->cut, rp->pose, rp->w, rp->ev, rp->pose_raw);
 }
 
 int gfpl_replay_download(gfpl_replay* rp, gfpl_pose_result* pose, gfpl_track_obs* obs, gfpl_line_cut* cut,
@@ -978,6 +1212,7 @@ int gfpl_replay_download(gfpl_replay* rp, gfpl_pose_result* pose, gfpl_track_obs
   REQUIRE(ctx, pose);
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   rp->d2h = 0;
+  rp->input_dirty = true;   // the next pipelined run must not overwrite what these copies are still reading
   size_t B = rp->B;
   D2H(pose, rp->pose, B);
   if (obs) {

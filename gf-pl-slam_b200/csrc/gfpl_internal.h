@@ -46,6 +46,10 @@ struct gfpl_ctx {
   size_t scratch_bytes = 0;
   size_t scratch_used = 0;
   cudaEvent_t timer[8] = {};
+  // first failure of an asynchronous copy enqueued by an entry point (checked when the call synchronises)
+  cudaError_t pending_error = cudaSuccess;
+  // private stream-ordered pool of this context (scratch of the host-pointer entry points)
+  cudaMemPool_t pool = nullptr;
 };
 
 #define GFPL_CUDA_OK(ctx, expr)                                                              \
@@ -129,7 +133,8 @@ int launch_linecut(gfpl_ctx* ctx, const double* DT_inv, const gfpl_frame_state* 
 // K4: pose
 int launch_pose_hg(gfpl_ctx* ctx, const double* DT, const DevTrackObs& obs, double* H, double* g, double* e);
 int launch_pose_optimize(gfpl_ctx* ctx, DevTrackObs obs, const gfpl_frame_state* state, const double* DT_ini,
-                         int overload, gfpl_pose_result* out);
+                         int overload, gfpl_pose_result* out, void* raw_scratch = nullptr);
+size_t pose_raw_bytes(int B);   // size of the optimiser -> finalize hand-off buffer for B pairs
 
 // K6: LBA assembly (device copies of the flat problem)
 int launch_lba_assemble(gfpl_ctx* ctx, const gfpl_lba_problem& dprob, gfpl_lba_blocks dout);
@@ -148,5 +153,6 @@ int launch_lba_solve(gfpl_ctx* ctx, const gfpl_lba_problem& pb, const gfpl_lba_b
 
 int launch_measure_peaks(gfpl_ctx* ctx, double* popc_tops, double* fp64_tflops);
 int launch_measure_alu_peak(gfpl_ctx* ctx, double* lop3_tops);
+int launch_measure_int8_peak(gfpl_ctx* ctx, double* int8_tops);   // dense tcgen05.mma kind::i8, operands resident in smem
 
 }  // namespace gfpl

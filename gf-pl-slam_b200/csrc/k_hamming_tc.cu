@@ -358,6 +358,98 @@ int launch_knn2_tc_small(gfpl_ctx* ctx, int B, const uint8_t* a, const int32_t* 
   return GFPL_OK;
 }
 
+// ---- roofline denominator: dense tcgen05.mma kind::i8 throughput, measured ----------------------------------------
+// One CTA per SM, operands resident in shared memory (no loads in the loop), M = 128, N = 256, K = 256 per product
+// (8 instructions of K = 32), products issued back to back into the two halves of the SM's 512 TMEM columns; a commit +
+// wait every PEAK_BURST products keeps the issue queue bounded.  Operand bytes are pseudo-random (+-64 like the
+// matching operands would toggle fewer datapath bits and flatter the clock).  ops = 2 * 128 * 256 * 256 per product.
+constexpr int PEAK_N = 256, PEAK_BURST = 8;
+constexpr size_t PEAK_SMEM = (size_t)(TC_M + PEAK_N) * TC_ROW_BYTES;
+
+__global__ void __launch_bounds__(128) int8_peak_kernel(int products, uint32_t* sink) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x;
+  uint32_t x = (blockIdx.x * 128u + tid) * 2654435761u + 12345u;
+  for (size_t i = tid * 4; i < PEAK_SMEM; i += 128 * 4) {
+    x = x * 1664525u + 1013904223u;
+    *reinterpret_cast<uint32_t*>(smem + i) = x;
+  }
+  if ((tid >> 5) == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+  if (tid == 0) {
+    const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem + (size_t)TC_M * TC_ROW_BYTES);
+    const uint32_t idesc = umma_idesc_i8(PEAK_N);
+    uint32_t phase = 0u;
+    for (int p = 0; p < products; p += PEAK_BURST) {
+      for (int q = 0; q < PEAK_BURST; q++) {
+        const uint32_t d_tmem = tmem + (uint32_t)((q & 1) * PEAK_N);
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {
+          const uint64_t da = umma_desc(a_addr + ks * 2 * TC_LBO);
+          const uint64_t db = umma_desc(b_addr + ks * 2 * TC_LBO);
+          const uint32_t acc = ks > 0 ? 1u : 0u;
+          asm volatile(
+              "{\n\t"
+              ".reg .pred p;\n\t"
+              "setp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+              "}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u)
+              : "memory");
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+      mbar_wait(&bar, phase);
+      phase ^= 1u;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if ((tid >> 5) == 0) {   // read one accumulator word so that the products are observable
+    uint32_t v[16];
+    TC_LD16(v, tmem);
+    TC_WAIT16(v);
+    if (tid == 0) sink[blockIdx.x] = v[0];
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
+}
+
+int launch_measure_int8_peak(gfpl_ctx* ctx, double* int8_tops) {
+  const int blocks = ctx->sm_count, products = 2048;
+  uint32_t* sink = nullptr;
+  GFPL_CUDA_OK(ctx, cudaMalloc((void**)&sink, (size_t)blocks * sizeof(uint32_t)));
+  GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(int8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PEAK_SMEM));
+  cudaEvent_t e0, e1;
+  GFPL_CUDA_OK(ctx, cudaEventCreate(&e0));
+  GFPL_CUDA_OK(ctx, cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    float ms;
+    cudaEventRecord(e0, ctx->stream);
+    int8_peak_kernel<<<blocks, 128, PEAK_SMEM, ctx->stream>>>(products, sink);
+    cudaEventRecord(e1, ctx->stream);
+    GFPL_LAUNCH_OK(ctx);
+    GFPL_CUDA_OK(ctx, cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  *int8_tops = (double)blocks * products * 2.0 * TC_M * PEAK_N * 256.0 / (best * 1e-3) / 1e12;
+  return GFPL_OK;
+}
+
 bool knn2_tc_fits(int cap_a, int cap_b) {
   // small problems are dominated by the fixed cost of a CTA (TMEM allocation, barriers): they go to knn2_tc_small_kernel
   return cap_a >= 128 && cap_b >= 128 && cap_a < (1 << TC_KEY_SHIFT) && cap_b < (1 << TC_KEY_SHIFT) &&

@@ -626,12 +626,10 @@ pose_finalize_kernel(int B, const PoseRaw* __restrict__ raw, const gfpl_frame_st
   r.iters_first = w.iters_first; r.iters_ref = w.iters_ref;
 }
 
-int launch_pose_optimize(gfpl_ctx* ctx, DevTrackObs obs, const gfpl_frame_state* state, const double* DT_ini,
-                         int overload, gfpl_pose_result* out) {
-  if (obs.B <= 0) return GFPL_OK;
-  // the hand-off buffer lives in the (stream-ordered) default pool; it is tiny: 456 B per pair
-  PoseRaw* raw = nullptr;
-  GFPL_CUDA_OK(ctx, cudaMallocAsync((void**)&raw, (size_t)obs.B * sizeof(PoseRaw), ctx->stream));
+size_t pose_raw_bytes(int B) { return (size_t)(B > 0 ? B : 1) * sizeof(PoseRaw); }
+
+static int launch_pose_optimize_on(gfpl_ctx* ctx, DevTrackObs obs, const gfpl_frame_state* state, const double* DT_ini,
+                                   int overload, gfpl_pose_result* out, PoseRaw* raw) {
   constexpr int G = POSE_GROUP, PAIRS_PER_CTA = POSE_WARPS * 32 / G;
   const size_t smem = (size_t)PAIRS_PER_CTA * pose_smem_doubles(obs.cap_pt, obs.cap_ln) * sizeof(double);
   if (smem > 48 * 1024)
@@ -641,7 +639,21 @@ int launch_pose_optimize(gfpl_ctx* ctx, DevTrackObs obs, const gfpl_frame_state*
   GFPL_LAUNCH_OK(ctx);
   pose_finalize_kernel<<<(obs.B + 127) / 128, 128, 0, ctx->stream>>>(obs.B, raw, state, overload, out, ctx->cfg);
   GFPL_LAUNCH_OK(ctx);
-  GFPL_CUDA_OK(ctx, cudaFreeAsync(raw, ctx->stream));
+  return GFPL_OK;
+}
+
+// raw_scratch: pose_raw_bytes(obs.B) bytes of device memory owned by the caller (the resident replay), or NULL: the
+// hand-off buffer then comes from the stream-ordered pool and is returned to it on every exit path.
+int launch_pose_optimize(gfpl_ctx* ctx, DevTrackObs obs, const gfpl_frame_state* state, const double* DT_ini,
+                         int overload, gfpl_pose_result* out, void* raw_scratch) {
+  if (obs.B <= 0) return GFPL_OK;
+  if (raw_scratch) return launch_pose_optimize_on(ctx, obs, state, DT_ini, overload, out, (PoseRaw*)raw_scratch);
+  PoseRaw* raw = nullptr;
+  GFPL_CUDA_OK(ctx, cudaMallocAsync((void**)&raw, pose_raw_bytes(obs.B), ctx->stream));
+  const int rc = launch_pose_optimize_on(ctx, obs, state, DT_ini, overload, out, raw);
+  const cudaError_t fe = cudaFreeAsync(raw, ctx->stream);   // also on the error paths above
+  if (rc != GFPL_OK) return rc;
+  GFPL_CUDA_OK(ctx, fe);
   return GFPL_OK;
 }
 

@@ -35,6 +35,8 @@ def lib():
         L.gfpl_ctx_launch_count.restype = C.c_int64
         L.gfpl_ctx_launch_count.argtypes = [C.c_void_p]
         L.gfpl_ctx_destroy.argtypes = [C.c_void_p]
+        L.gfpl_ctx_stream.restype = C.c_void_p
+        L.gfpl_ctx_stream.argtypes = [C.c_void_p]
         if hasattr(L, "gfpl_replay_create"):
             L.gfpl_replay_h2d_bytes.restype = C.c_int64
             L.gfpl_replay_d2h_bytes.restype = C.c_int64
@@ -113,6 +115,10 @@ class Context:
     def sync(self):
         self._check(lib().gfpl_ctx_sync(self._h))
 
+    def stream(self):
+        """cudaStream_t of the context (an integer handle, e.g. for torch.cuda.ExternalStream)"""
+        return lib().gfpl_ctx_stream(self._h)
+
     def launch_count(self):
         return int(lib().gfpl_ctx_launch_count(self._h))
 
@@ -128,6 +134,11 @@ class Context:
         p, f = C.c_double(), C.c_double()
         self._check(lib().gfpl_measure_peaks(self._h, C.byref(p), C.byref(f)))
         return p.value, f.value
+
+    def measure_int8_peak(self):
+        p = C.c_double()
+        self._check(lib().gfpl_measure_int8_peak(self._h, C.byref(p)))
+        return p.value
 
     def measure_alu_peak(self):
         p = C.c_double()
@@ -320,6 +331,10 @@ class Replay:
 
     def run(self, flags):
         self.ctx._check(lib().gfpl_replay_run(self._h, flags))
+
+    def set_pipeline(self, n_sub):
+        """software pipeline over n_sub sub-batches: matching of sub-batch k+1 overlaps the fp64 stages of sub-batch k"""
+        self.ctx._check(lib().gfpl_replay_set_pipeline(self._h, int(n_sub)))
 
     def download(self, pose, obs=None, cut=None, curr=None):
         ov = obs.view() if obs is not None else None

@@ -36,6 +36,10 @@ extern "C" {
 #endif
 
 #define GFPL_ABI_VERSION 1
+/* Preconditions checked by every batched entry point (GFPL_E_INVALID otherwise): each per-problem count n_*[p] lies in
+ * [0, cap_*] (the kernels size shared memory and output rows by the capacities), and no side of a matching problem
+ * has GFPL_MAX_KNN_ROWS rows or more (the (distance, row) sort key holds the row index in 20 bits). */
+#define GFPL_MAX_KNN_ROWS (1 << 20)
 #define GFPL_DESC_BYTES 32 /* ORB (ORBextractor.cc:1037,1068) and LBD (binary_descriptor_custom.cpp:639) rows */
 
 /* cv::NormTypes values used by the reference's BFMatcher constructions */
@@ -336,6 +340,10 @@ int gfpl_ctx_set_config(gfpl_ctx* ctx, const gfpl_config* cfg);
 int gfpl_ctx_set_camera(gfpl_ctx* ctx, const gfpl_camera* cam);
 const char* gfpl_last_error(const gfpl_ctx* ctx); /* ctx may be NULL: thread-local last error of ctx-less calls */
 int gfpl_ctx_sync(gfpl_ctx* ctx);
+/* the context's cudaStream_t: every entry point orders its device work on it (the pipelined replay included), so a caller
+ * can enqueue its own work behind the library's without a host synchronisation — e.g. the NCCL gather of the pose
+ * records of a sharded replay */
+void* gfpl_ctx_stream(gfpl_ctx* ctx);
 /* number of kernels this context has launched since creation (bench.py gpu_launches) */
 int64_t gfpl_ctx_launch_count(const gfpl_ctx* ctx);
 
@@ -551,6 +559,16 @@ int gfpl_replay_upload_slim(gfpl_replay* rp, const gfpl_prev_frames* prev, const
 int gfpl_replay_upload_compact(gfpl_replay* rp, const gfpl_compact_input* in, const gfpl_frame_state* state /*[B]*/);
 /* launch the whole step on the resident inputs (asynchronous; no host synchronisation inside) */
 int gfpl_replay_run(gfpl_replay* rp, int32_t flags);
+/* Software pipeline of gfpl_replay_run over n_sub contiguous sub-batches of the B pairs (1 = off, the default; at most
+ * GFPL_MAX_SUBBATCHES).  The matching kernels (tensor / integer pipes, two large CTAs per SM) of sub-batch k+1 run on one
+ * stream while the fp64 latency-bound kernels (line cut, pose optimisation: < 20 % of an SM's warp slots) of sub-batch k
+ * run on high-priority streams of their own, so both kinds of work share the SMs; consecutive runs without an upload in
+ * between overlap the same way (the matching of step n+1 starts while the last sub-batches of step n are optimised).
+ * Pairs are independent, so the results are bit-identical to the unpipelined step.  Everything is ordered behind the
+ * context stream: uploads before a run, downloads / gfpl_ctx_sync / timers after it see the same state as without the
+ * pipeline.  gfpl_replay_stage_ms needs n_sub == 1. */
+#define GFPL_MAX_SUBBATCHES 16
+int gfpl_replay_set_pipeline(gfpl_replay* rp, int32_t n_sub);
 /* async D2H of the per-pair pose records (pose: [B]); obs/cut/curr optional (NULL to skip) */
 int gfpl_replay_download(gfpl_replay* rp, gfpl_pose_result* pose, gfpl_track_obs* obs, gfpl_line_cut* cut,
                          gfpl_stereo_frames* curr);
@@ -634,6 +652,9 @@ int gfpl_lba_step(gfpl_ctx* ctx, const gfpl_lba_problem* prob, double lambda, in
 
 /* measured popc.b32 throughput (T popc/s) and fp64 FMA throughput (TFLOP/s, FMA = 2 flop) */
 int gfpl_measure_peaks(gfpl_ctx* ctx, double* popc_tops, double* fp64_tflops);
+/* measured dense tcgen05.mma kind::i8 throughput (TOP/s, 2 ops per int8 MAC): one CTA per SM, M = 128, N = 256, operands
+ * resident in shared memory — the denominator of the tensor-core matching kernels' roofline */
+int gfpl_measure_int8_peak(gfpl_ctx* ctx, double* int8_tops);
 /* measured 3-input LOP3 throughput of the ALU pipe (T op/s): the second pipe of the matching loop */
 int gfpl_measure_alu_peak(gfpl_ctx* ctx, double* lop3_tops);
 

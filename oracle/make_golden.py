@@ -62,6 +62,9 @@ def main():
             i, d = knn(q, t, norm)
             off, ri, rd = radius(q, t, norm, r)
             out[f"knn_idx_{norm}"], out[f"knn_dist_{norm}"] = i, d
+            # the reverse call of a mutual check (knnMatch(t, q), stereoFrame.cpp:808): pins the direction the
+            # tensor-core kernels take from the transposed product
+            out[f"rknn_idx_{norm}"], out[f"rknn_dist_{norm}"] = knn(t, q, norm)
             out[f"rad_off_{norm}"], out[f"rad_idx_{norm}"], out[f"rad_dist_{norm}"] = off, ri, rd
         np.savez_compressed(os.path.join(OUT, f"bfmatcher_{name}.npz"), **out)
         print(name, q.shape, t.shape, "radius entries", int(out["rad_off_6"][-1]), int(out["rad_off_7"][-1]))

@@ -36,6 +36,34 @@ def lib():
     return _LIB
 
 
+NATIVE_FLAGS = "-O3 -march=native (the reference's CMAKE_CXX_FLAGS, CMakeLists.txt:67-68)"
+PARITY_FLAGS = "-O3 -march=x86-64-v2 -mpopcnt -ffp-contract=off"
+
+
+def use_native_build():
+    """bench.py's CPU arm: rebuild the oracle sources with -O3 -march=native on THIS machine and route every call of this
+    module to that library (timing only; the parity tests keep the -ffp-contract=off build).  Returns the flags in use;
+    falls back to the parity build if the compiler is missing."""
+    global _LIB
+    so = os.path.join(_HERE, "_build", "native", "libgfpl_oracle.so")
+    try:
+        # always rebuilt: a library built with -march=native on another machine (the snapshot travels) may not run here
+        if os.path.exists(so):
+            os.remove(so)
+        subprocess.check_call(["make", "-C", _HERE, "native"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        _LIB = None
+        native = C.CDLL(so)
+        lib_parity = lib()
+        for name in ("orc_line_descriptor_mad", "orc_budget_thres", "orc_vector_stdv_mad", "orc_logdet6", "orc_min_eig6"):
+            getattr(native, name).restype = C.c_double
+        _LIB = native
+        return NATIVE_FLAGS
+    except Exception:
+        _LIB = None
+        lib()
+        return PARITY_FLAGS
+
+
 def default_config():
     cfg = S.Config()
     lib().orc_config_default(C.byref(cfg))

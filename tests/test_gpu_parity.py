@@ -51,6 +51,31 @@ def test_knn2_radius_vs_cv2_golden(ctx, path, norm):
     assert np.array_equal(ri, g[f"rad_idx_{norm}"]) and np.array_equal(rd, g[f"rad_dist_{norm}"])
 
 
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[10:-4] for p in GOLDEN])
+@pytest.mark.parametrize("norm", [6, 7])
+def test_knn2_mutual_vs_cv2_golden(ctx, path, norm):
+    """the cv2.BFMatcher vectors through the both-directions entry point, i.e. through the kernels the tracking step
+    runs: knn2_tc_kernel (tcgen05, >= 128 rows per side, NORM_HAMMING), knn2_tc_small_kernel (<= 128 rows, both norms),
+    knn2_sym_kernel (NORM_HAMMING2 above 128 rows, tiny sides).  Forward = knnMatch(q, t, 2), reverse best =
+    knnMatch(t, q, 2)[j][0] (stereoFrame.cpp:807-808)."""
+    g = np.load(path)
+    q, t = g["q"], g["t"]
+    # the same problem twice, the second copy padded to a larger stride, plus an empty problem in between
+    cap_q, cap_t = len(q) + 5, len(t) + 9
+    Q = np.zeros((3, cap_q, 32), np.uint8); T = np.zeros((3, cap_t, 32), np.uint8)
+    Q[0, :len(q)] = q; T[0, :len(t)] = t; Q[2, :len(q)] = q; T[2, :len(t)] = t
+    nq = np.array([len(q), 0, len(q)], np.int32); nt = np.array([len(t), 0, len(t)], np.int32)
+    idx, dist, bi, bd = ctx.knn2_mutual(Q, nq, T, nt, norm)
+    for p in (0, 2):
+        assert np.array_equal(idx[p, :len(q)], g[f"knn_idx_{norm}"]) and np.array_equal(dist[p, :len(q)], g[f"knn_dist_{norm}"])
+        assert np.array_equal(bi[p, :len(t)], g[f"rknn_idx_{norm}"][:, 0])
+        assert np.array_equal(bd[p, :len(t)], g[f"rknn_dist_{norm}"][:, 0])
+    # exact strides as well (cap == n: the shapes the kernels' dispatch rules see in the step)
+    idx, dist, bi, bd = ctx.knn2_mutual(q[None], [len(q)], t[None], [len(t)], norm)
+    assert np.array_equal(idx[0], g[f"knn_idx_{norm}"]) and np.array_equal(dist[0], g[f"knn_dist_{norm}"])
+    assert np.array_equal(bi[0], g[f"rknn_idx_{norm}"][:, 0]) and np.array_equal(bd[0], g[f"rknn_dist_{norm}"][:, 0])
+
+
 @pytest.mark.parametrize("shape", [(300, 300), (100, 100), (2000, 2000), (500, 500), (1, 2), (37, 1025), (513, 255),
                                    (257, 256), (31, 33)])
 @pytest.mark.parametrize("norm", [6, 7])
@@ -442,6 +467,112 @@ def test_replay_matches_track_and_is_deterministic(ctx, orc):
     ms = rp.stage_ms()
     assert len(ms) == S.NUM_STAGES and ms[-1] > 0
     assert ctx.launch_count() > 0
+
+
+@pytest.mark.parametrize("n_sub", [2, 4, 7])
+def test_replay_pipelined_is_bit_identical(ctx, orc, n_sub):
+    """gfpl_replay_set_pipeline: matching of sub-batch k+1 on one stream, line cut + pose of sub-batch k on their own
+    high-priority streams, consecutive runs overlapping — every record must equal the unpipelined step bit for bit
+    (uneven split, ragged counts, three back-to-back runs, an upload in between)"""
+    from gfpl import api
+    B = 90
+    d = _data(B, 1300 + n_sub, ragged=True)
+    flags = S.TRACK_LINECUT | S.TRACK_SEED_GIVEN
+    prev = orc.stereo_match(d["cam"], ctx.cfg, d["prev_raw"])
+    rp = api.Replay(ctx, B, d["curr_raw"].cap_pt, d["curr_raw"].cap_ln)
+
+    def fetch():
+        pose = np.zeros(B, S.pose_result_dt)
+        obs = S.TrackObsNP(B, ctx.cfg.max_point_match_num, ctx.cfg.max_line_match_num)
+        cut = np.zeros((B, obs.cap_ln), S.line_cut_dt)
+        curr = S.StereoFramesNP(B, d["curr_raw"].cap_pt, d["curr_raw"].cap_ln)
+        rp.download(pose, obs, cut, curr)
+        ctx.sync()
+        return pose, obs, cut, curr
+
+    rp.upload(prev, d["state"], d["curr_raw"])
+    rp.run(flags)
+    ref = fetch()
+    rp.set_pipeline(n_sub)
+    for rounds in (3, 1):
+        rp.upload(prev, d["state"], d["curr_raw"])
+        for _ in range(rounds):
+            rp.run(flags)                       # back to back: step n+1's matching overlaps step n's optimiser
+        got = fetch()
+        assert got[0].tobytes() == ref[0].tobytes()
+        assert np.array_equal(got[1].n_pt, ref[1].n_pt) and np.array_equal(got[1].n_ln, ref[1].n_ln)
+        for p in range(B):
+            npt, nln = ref[1].n_pt[p], ref[1].n_ln[p]
+            assert got[1].pt[p, :npt].tobytes() == ref[1].pt[p, :npt].tobytes()
+            assert got[1].ln[p, :nln].tobytes() == ref[1].ln[p, :nln].tobytes()
+            assert np.array_equal(got[1].pt_inlier[p, :npt], ref[1].pt_inlier[p, :npt])
+            assert np.array_equal(got[1].ln_inlier[p, :nln], ref[1].ln_inlier[p, :nln])
+            assert got[2][p, :nln].tobytes() == ref[2][p, :nln].tobytes()
+        assert np.array_equal(got[3].n_pt, ref[3].n_pt) and np.array_equal(got[3].n_ln, ref[3].n_ln)
+    with pytest.raises(api.GfplError):
+        rp.stage_ms()                           # per-kernel events exist only for the unpipelined step
+    with pytest.raises(api.GfplError):
+        rp.set_pipeline(0)
+    rp.set_pipeline(1)
+    rp.run(flags)
+    assert fetch()[0].tobytes() == ref[0].tobytes() and rp.stage_ms()[-1] > 0
+
+
+def test_track_at_scale_no_flips(ctx, orc):
+    """4096 frame pairs through the whole step against the oracle (all host threads): the count of pairs whose inlier
+    masks, iteration counts, status words or cut decisions differ must be ZERO — k_pose.cu is built with FMA
+    contraction and hardware reciprocal seeds, so a residual within rounding of a MAD threshold would show up here."""
+    B = 4096
+    d = _data(B, 2024)
+    flags = S.TRACK_LINECUT | S.TRACK_SEED_GIVEN
+    prev = orc.stereo_match(d["cam"], ctx.cfg, d["prev_raw"])
+    co, oo, ko, po = orc.track(d["cam"], ctx.cfg, prev, d["state"], d["curr_raw"], flags, n_threads=os.cpu_count() or 1)
+    flips = dict(mask_pt=0, mask_ln=0, iters=0, status=0, cut=0, counts=0)
+    tol_bad = 0
+    for lo in range(0, B, 1024):
+        hi = lo + 1024
+        sl = lambda a: a[lo:hi]
+        cg, og, kg, pg = ctx.track(prev.slice(lo, hi), d["state"][lo:hi], d["curr_raw"].slice(lo, hi), flags)
+        for p in range(1024):
+            q = lo + p
+            npt, nln = oo.n_pt[q], oo.n_ln[q]
+            if og.n_pt[p] != npt or og.n_ln[p] != nln:
+                flips["counts"] += 1
+                continue
+            flips["mask_pt"] += int(not np.array_equal(og.pt_inlier[p, :npt], oo.pt_inlier[q, :npt]))
+            flips["mask_ln"] += int(not np.array_equal(og.ln_inlier[p, :nln], oo.ln_inlier[q, :nln]))
+            flips["cut"] += int(not np.array_equal(kg["cutRatio"][p, :nln], ko["cutRatio"][q, :nln]))
+            flips["iters"] += int(pg["iters_first"][p] != po["iters_first"][q] or pg["iters_ref"][p] != po["iters_ref"][q])
+            flips["status"] += int(pg["status"][p] != po["status"][q])
+            if pg["status"][p] == po["status"][q] and not close(pg["DT"][p], po["DT"][q]):
+                tol_bad += 1
+    assert (po["status"] == 0).mean() > 0.99
+    assert sum(flips.values()) == 0, f"pairs that differ from the oracle, of {B}: {flips}"
+    assert tol_bad == 0, f"{tol_bad} poses outside {RTOL}"
+
+
+def test_count_validation_rejects_out_of_range(ctx):
+    """a per-problem count outside [0, cap] or a side of 2^20 rows is GFPL_E_INVALID before anything is launched"""
+    from gfpl import api
+    d = _data(2, 5)
+    raw = d["curr_raw"]
+    good = raw.n_pt_l.copy()
+    for bad in (-1, raw.cap_pt + 1):
+        raw.n_pt_l[1] = bad
+        with pytest.raises(api.GfplError) as e:
+            ctx.stereo_match(raw)
+        assert e.value.code == S.E_INVALID
+    raw.n_pt_l[:] = good
+    prev = ctx.stereo_match(raw)
+    prev.n_ln[0] = prev.cap_ln + 3
+    with pytest.raises(api.GfplError):
+        ctx.track(prev, d["state"], raw, 0)
+    q = np.zeros((1, 4, 32), np.uint8)
+    with pytest.raises(api.GfplError):
+        ctx.knn2_mutual(q, [5], q, [4])
+    with pytest.raises(api.GfplError):
+        ctx.knn2_batch(q, [4], q, [-2])
+    ctx.stereo_match(raw)                        # the context is still usable
 
 
 def test_lba_assemble(ctx, orc):

@@ -23,3 +23,22 @@ for k in range(steps + 2):
         acc = ms if acc is None else acc + ms
 names = ["knn_stereo_pt", "knn_stereo_ln", "stereo_accept", "f2f_pt_search", "knn_f2f_ln", "f2f_accept", "uncertainty+linecut", "pose_gn", "step"]
 print({n: round(float(v) / steps, 4) for n, v in zip(names, acc)}, "pairs", rp.pair_counts())
+# software pipeline over sub-batches (gfpl_replay_set_pipeline): ms per step of back-to-back runs, checksum of the poses
+import zlib
+ref = None
+for n_sub in [int(x) for x in os.environ.get("GFPL_SWEEP", "1,2,4,6,8,12,16").split(",")]:
+    rp.set_pipeline(n_sub)
+    for _ in range(3):
+        rp.run(flags)
+    ctx.sync()
+    ctx.timer_record(0)
+    for _ in range(steps * 4):
+        rp.run(flags)
+    ctx.timer_record(1)
+    ms = ctx.timer_elapsed_ms(0, 1) / (steps * 4)
+    pose = np.zeros(B, S.pose_result_dt)
+    rp.download(pose)
+    ctx.sync()
+    crc = zlib.crc32(pose.tobytes())
+    ref = crc if ref is None else ref
+    print("pipeline n_sub=%2d  %.3f ms/step  %.2f M pairs/s  poses %s" % (n_sub, ms, B / ms / 1e3, "identical" if crc == ref else "DIFFER"))
