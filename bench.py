@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--no-linecut", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="pairs per step of the CPU reference arm")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--c4-pairs", type=int, default=2048, help="frame pairs of the dense-feature (configs[3]) side measurement; 0 = skip")
     ap.add_argument("--pipeline", type=int, default=int(os.environ.get("GFPL_PIPELINE", "1")),
                     help="sub-batches of the software pipeline of the resident step (1 = off)")
     return ap.parse_args()
@@ -171,6 +172,67 @@ def run_reference(a, rank):
                       "config": workload_config(a),
                       "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "build_flags": CPU_FLAGS},
                       "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def dense_c4(a, ctx, api, synth, S, int8_peak, skip_cpu):
+    """BASELINE.json configs[3] (dense-feature stress: 2000 ORB points + 500 lines per image, stereo + f2f matching with
+    cross-check) as a second measurement of the same path: resident replay of `--c4-pairs` pairs, per-kernel CUDA-event
+    times, the point-matching kernel's tensor roofline (column-blocked tcgen05 form) and the CPU port on a small sample."""
+    B, n_pt, n_ln = a.c4_pairs, 2000, 500
+    d = synth.make_pairs(B, n_pt=n_pt, n_ln=n_ln, seed=7000, pinned=False)
+    flags = S.TRACK_LINECUT | S.TRACK_SEED_GIVEN
+    prev = S.StereoFramesNP(B, n_pt, n_ln)
+    for lo in range(0, B, 256):
+        hi = min(B, lo + 256)
+        part = ctx.stereo_match(d["prev_raw"].slice(lo, hi))
+        for k in S.StereoFramesNP._keys:
+            getattr(prev, k)[lo:hi] = getattr(part, k)
+    prev = prev.repack()
+    rp = api.Replay(ctx, B, n_pt, n_ln, prev.cap_pt, prev.cap_ln)
+    rp.upload(prev, d["state"], d["curr_raw"])
+    for _ in range(2):
+        rp.run(flags)
+    ctx.sync()
+    K = 5
+    stage = np.zeros(S.NUM_STAGES)
+    ctx.timer_record(2)
+    for _ in range(K):
+        rp.run(flags)
+        stage += np.array(rp.stage_ms())
+    ctx.timer_record(3)
+    ms = ctx.timer_elapsed_ms(2, 3) / K
+    stage /= K
+    pairs = rp.pair_counts()
+    pose = np.zeros(B, S.pose_result_dt)
+    rp.download(pose)
+    ctx.sync()
+    rp.close()
+    names = ["knn_stereo_pt", "knn_stereo_ln", "stereo_accept", "f2f_pt_search", "knn_f2f_ln", "f2f_accept", "uncertainty+linecut", "pose_gn", "step"]
+    ops = pairs[0] * 512.0 * 2
+    out = {"workload": "dense-feature stress (BASELINE configs[3]): %d pairs, 2000 ORB pts + 500 LSD lines per image, stereo + f2f matching with cross-check, line cut, pose GN" % B,
+           "value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "tracked_ok": float((pose["status"] == 0).mean()),
+           "kernel_ms_per_step": dict(zip(names, [float(x) for x in stage])),
+           "distances_per_step": {"stereo_pt": pairs[0], "stereo_ln": pairs[1], "f2f_pt": pairs[2], "f2f_ln": pairs[3]},
+           "roofline": {"kernel": "knn2_tc_kernel<BLOCKED> + merge: stereo points 2000 x 2000, forward k=2 + reverse best (column blocks of 288 train rows)",
+                        "bound": "tensor", "achieved": ops / (stage[0] * 1e-3) / 1e12, "peak": int8_peak, "unit": "TOP/s (int8)",
+                        "frac": ops / (stage[0] * 1e-3) / 1e12 / int8_peak, "kernel_ms": float(stage[0])},
+           "f2f_roofline": {"kernel": "f2f_hybrid_points_tc_blocked_kernel + resolve", "bound": "tensor",
+                            "achieved": pairs[2] * 512.0 / (stage[3] * 1e-3) / 1e12, "peak": int8_peak, "unit": "TOP/s (int8)",
+                            "frac": pairs[2] * 512.0 / (stage[3] * 1e-3) / 1e12 / int8_peak, "kernel_ms": float(stage[3])}}
+    if not skip_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import orc
+        n = min(B, 64)
+        cores = os.cpu_count() or 1
+        cfg = orc.default_config()
+        sl = lambda x: x.slice(0, n)
+        prev_o = orc.stereo_match(d["cam"], cfg, sl(d["prev_raw"]))
+        t0 = time.perf_counter()
+        orc.track(d["cam"], cfg, prev_o, d["state"][:n], sl(d["curr_raw"]), flags, n_threads=cores)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port", "build_flags": CPU_FLAGS,
+                               "sample": "%d of %d pairs, one pass, %d std::threads over pairs" % (n, B, cores)}
+    return out
 
 
 class DevArray:
@@ -446,6 +508,18 @@ def main():
             ctx.set_camera(d["cam"])
         except Exception as e:  # a side note must not break the contract line
             out["lba_c3"] = {"unavailable": repr(e)}
+        if a.c4_pairs > 0:
+            try:
+                if not a.skip_cpu_baseline:
+                    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+                    import orc
+                    global CPU_FLAGS
+                    CPU_FLAGS = orc.use_native_build()
+                for _, r in slots[1:]:
+                    r.close()                                     # the e2e slots' device buffers are no longer needed
+                out["c4_dense"] = dense_c4(a, ctx, api, synth, S, int8_peak, a.skip_cpu_baseline)
+            except Exception as e:  # a side measurement must not break the contract line
+                out["c4_dense"] = {"unavailable": repr(e)}
         if not a.skip_cpu_baseline:
             n, cores, cstep = cpu_reference(a)
             cstep()

@@ -85,6 +85,7 @@ int launch_knn2(gfpl_ctx* ctx, int B, const uint8_t* a, const int32_t* na, int c
 // tensor-core form of the NORM_HAMMING both-directions call (k_hamming_tc.cu): forward k=2, reverse best
 bool knn2_tc_fits(int cap_a, int cap_b);
 bool knn2_tc_small_fits(int cap_a, int cap_b);
+void tc_column_blocks(int cap_n, int* nblk, int* blk);   // column-blocked tensor-core forms: blocks of the train side
 int launch_knn2_tc_small(gfpl_ctx* ctx, int B, const uint8_t* a, const int32_t* na, int cap_a, const uint8_t* b, const int32_t* nb,
                          int cap_b, int norm, Knn2Out out_ab, Knn2Out out_ba);
 int launch_knn2_tc(gfpl_ctx* ctx, int B, const uint8_t* a, const int32_t* na, int cap_a, const uint8_t* b, const int32_t* nb,

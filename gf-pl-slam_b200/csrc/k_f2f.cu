@@ -167,6 +167,30 @@ f2f_hybrid_points_kernel(DevStereoFrames prev, DevStereoFrames curr, const doubl
     if (tq[k] < n_curr) best_key[(size_t)p * curr.cap_pt + tq[k]] = best[k];
 }
 
+// Projection gate of one current point t, given the two smallest keys (k0 <= k1) of its row over ALL previous points:
+// none / exactly one / several candidates within the radius (keys of candidates are < lim).
+__device__ __forceinline__ uint32_t f2f_resolve_row(int t, uint32_t k0, uint32_t k1, uint32_t lim, int rint, int n_prev,
+                                                    const uint8_t* __restrict__ prev_desc, const uint8_t* __restrict__ curr_desc,
+                                                    const gfpl_point_feature* __restrict__ prev_pt,
+                                                    const gfpl_point_feature* __restrict__ curr_pt, const double* __restrict__ T32,
+                                                    const gfpl_camera& cam, double window) {
+  uint32_t best = KEY_NONE;
+  if (k0 < lim) {
+    const double plx = curr_pt[t].pl[0], ply = curr_pt[t].pl[1];
+    if (!(k1 < lim)) {
+      best = f2f_gate(KEY_NONE, k0, cam, T32, prev_pt[k0 & KEY_IDX_MASK].P, plx, ply, window);
+    } else {  // several previous points within the radius: every one of them is gated (:524-546)
+      const Desc256 qd = load_desc_global(curr_desc + (size_t)t * 32);
+      for (int q = 0; q < n_prev; q++) {
+        const uint4* rp = reinterpret_cast<const uint4*>(prev_desc + (size_t)q * 32);
+        const uint32_t d = hamming256<GFPL_NORM_HAMMING>(qd, __ldg(rp), __ldg(rp + 1));
+        if ((int)d <= rint) best = f2f_gate(best, make_key(d, q), cam, T32, prev_pt[q].P, plx, ply, window);
+      }
+    }
+  }
+  return best;
+}
+
 // Tensor-core form of the search above (gfpl_tc.cuh): rows = current points, columns = previous points.  The radius
 // test needs the number of candidates and the smallest key among them; the two smallest keys of a row decide both:
 // none / exactly one / several candidates within the radius.  One candidate (the usual case) goes through the
@@ -203,24 +227,57 @@ f2f_hybrid_points_tc_kernel(DevStereoFrames prev, DevStereoFrames curr, const do
   tc_direction<true>(curr_desc, n_curr, prev_desc, n_prev, sM, sN, S.bar, phases, tmem, S.merge,
                      [&](int t, uint32_t k0, uint32_t k1) { s_keys[t] = make_uint2(k0, k1); });
   tc_end(tmem);   // (CTA barrier inside: the keys are visible)
-  for (int t = threadIdx.x; t < n_curr; t += TC_THREADS) {
-    const uint32_t k0 = s_keys[t].x, k1 = s_keys[t].y;
-    uint32_t best = KEY_NONE;
-    if (k0 < lim) {
-      const double plx = curr_pt[t].pl[0], ply = curr_pt[t].pl[1];
-      if (!(k1 < lim)) {
-        best = f2f_gate(KEY_NONE, k0, cam, T32, prev_pt[k0 & KEY_IDX_MASK].P, plx, ply, window);
-      } else {  // several previous points within the radius: every one of them is gated (:524-546)
-        const Desc256 qd = load_desc_global(curr_desc + (size_t)t * 32);
-        for (int q = 0; q < n_prev; q++) {
-          const uint4* rp = reinterpret_cast<const uint4*>(prev_desc + (size_t)q * 32);
-          const uint32_t d = hamming256<GFPL_NORM_HAMMING>(qd, __ldg(rp), __ldg(rp + 1));
-          if ((int)d <= rint) best = f2f_gate(best, make_key(d, q), cam, T32, prev_pt[q].P, plx, ply, window);
-        }
-      }
-    }
-    out[t] = best;
+  for (int t = threadIdx.x; t < n_curr; t += TC_THREADS)
+    out[t] = f2f_resolve_row(t, s_keys[t].x, s_keys[t].y, lim, rint, n_prev, prev_desc, curr_desc, prev_pt, curr_pt, T32, cam, window);
+}
+
+// Column-blocked form for previous frames too large to sit expanded in shared memory (dense-feature stress: ~2000 stereo
+// survivors): grid = (blocks of previous points, problems); a CTA holds `blk` previous rows and walks all current tiles,
+// leaving the two smallest keys of every current point WITHIN its block (global previous indices) in `part`
+// [problem][block][curr.cap_pt]; f2f_resolve_kernel merges the blocks and applies the projection gate.
+__global__ void __launch_bounds__(TC_THREADS)
+f2f_hybrid_points_tc_blocked_kernel(DevStereoFrames prev, DevStereoFrames curr, int blk, uint2* __restrict__ part, gfpl_config cfg) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sM = smem;
+  uint8_t* sN = smem + TC_M * TC_ROW_BYTES;
+  __shared__ __align__(8) TcShared S;
+  const int p = blockIdx.y, j_first = blockIdx.x * blk;
+  const int n_prev = cfg.has_points ? max(0, min(blk, prev.n_pt[p] - j_first)) : 0, n_curr = curr.n_pt[p];
+  uint2* out = part + ((size_t)p * gridDim.x + blockIdx.x) * curr.cap_pt;
+  if (n_prev == 0 || n_curr == 0) {
+    for (int t = threadIdx.x; t < n_curr; t += TC_THREADS) out[t] = make_uint2(KEY_NONE, KEY_NONE);
+    return;
   }
+  const uint8_t* prev_desc = prev.pdesc + ((size_t)p * prev.cap_pt + j_first) * 32;
+  const uint8_t* curr_desc = curr.pdesc + (size_t)p * curr.cap_pt * 32;
+  const uint32_t tmem = tc_begin(S);
+  uint32_t phases[2] = {0u, 0u};
+  tc_direction<true>(curr_desc, n_curr, prev_desc, n_prev, sM, sN, S.bar, phases, tmem, S.merge,
+                     [&](int t, uint32_t k0, uint32_t k1) {   // block-local previous rows -> global (index = low 20 bits)
+                       out[t] = make_uint2(k0 + (uint32_t)j_first, k1 != KEY_NONE ? k1 + (uint32_t)j_first : KEY_NONE);
+                     });
+  tc_end(tmem);
+}
+
+__global__ void __launch_bounds__(128)
+f2f_resolve_kernel(DevStereoFrames prev, DevStereoFrames curr, int nblk, const uint2* __restrict__ part,
+                   const double* __restrict__ T32_all, uint32_t* __restrict__ best_key, gfpl_camera cam, gfpl_config cfg) {
+  const int p = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= curr.n_pt[p]) return;
+  const int n_prev = cfg.has_points ? prev.n_pt[p] : 0;
+  uint32_t k0 = KEY_NONE, k1 = KEY_NONE;
+  for (int c = 0; c < nblk; c++) {
+    const uint2 k = part[((size_t)p * nblk + c) * curr.cap_pt + t];
+    top2_update(k0, k1, k.x);
+    top2_update(k0, k1, k.y);
+  }
+  const float radius = (float)cfg.point_match_radius;
+  const int rint = radius >= 0.f ? (int)floorf(fminf(radius, 1024.f)) : -1;
+  const uint32_t lim = (uint32_t)(rint + 1) << KEY_IDX_BITS;
+  best_key[(size_t)p * curr.cap_pt + t] =
+      f2f_resolve_row(t, k0, k1, lim, rint, n_prev, prev.pdesc + (size_t)p * prev.cap_pt * 32, curr.pdesc + (size_t)p * curr.cap_pt * 32,
+                      prev.pt + (size_t)p * prev.cap_pt, curr.pt + (size_t)p * curr.cap_pt, T32_all + (size_t)p * 32, cam,
+                      cfg.f2f_point_window);
 }
 
 int launch_f2f_hybrid_points(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr,
@@ -230,11 +287,34 @@ int launch_f2f_hybrid_points(gfpl_ctx* ctx, const DevStereoFrames& prev, const D
   GFPL_LAUNCH_OK(ctx);
   static const bool no_tc = getenv("GFPL_NO_TC") != nullptr;   // A/B switch for measurements
   const size_t tc_smem = tc_smem_bytes(prev.cap_pt) + (size_t)curr.cap_pt * sizeof(uint2);
-  if (!no_tc && prev.cap_pt >= 128 && curr.cap_pt >= 128 && prev.cap_pt < (1 << 19) && tc_smem <= 200 * 1024) {
+  const bool tc_ok = !no_tc && prev.cap_pt >= 128 && curr.cap_pt >= 128 && prev.cap_pt < (1 << TC_KEY_SHIFT) && curr.cap_pt < (1 << TC_KEY_SHIFT);
+  if (tc_ok && tc_smem <= 113 * 1024) {   // previous frame resident in shared memory, two CTAs per SM
     GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(f2f_hybrid_points_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
     f2f_hybrid_points_tc_kernel<<<prev.B, TC_THREADS, tc_smem, ctx->stream>>>(prev, curr, T32, best_key, ctx->cam, ctx->cfg);
     GFPL_LAUNCH_OK(ctx);
     return GFPL_OK;
+  }
+  if (tc_ok) {
+    int nblk, blk;
+    tc_column_blocks(prev.cap_pt, &nblk, &blk);
+    uint2* part = nullptr;
+    const size_t part_bytes = (size_t)prev.B * nblk * curr.cap_pt * sizeof(uint2);
+    GFPL_CUDA_OK(ctx, ctx->pool ? cudaMallocFromPoolAsync((void**)&part, part_bytes, ctx->pool, ctx->stream)
+                                : cudaMallocAsync((void**)&part, part_bytes, ctx->stream));
+    int rc = GFPL_OK;
+    const size_t smem = tc_smem_bytes(blk);
+    if (cudaFuncSetAttribute(f2f_hybrid_points_tc_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      rc = GFPL_E_CUDA;
+    if (rc == GFPL_OK) {
+      f2f_hybrid_points_tc_blocked_kernel<<<dim3(nblk, prev.B), TC_THREADS, smem, ctx->stream>>>(prev, curr, blk, part, ctx->cfg);
+      f2f_resolve_kernel<<<dim3((curr.cap_pt + 127) / 128, prev.B), 128, 0, ctx->stream>>>(prev, curr, nblk, part, T32, best_key, ctx->cam,
+                                                                                            ctx->cfg);
+      ctx->launches += 2;
+      if (cudaGetLastError() != cudaSuccess) rc = GFPL_E_CUDA;
+    }
+    cudaFreeAsync(part, ctx->stream);
+    if (rc != GFPL_OK) set_last_error(ctx, "blocked tensor-core f2f search launch failed (%d blocks of %d rows)", nblk, blk);
+    return rc;
   }
   const int per_cta = F2F_THREADS * F2F_QPT;
   dim3 grid((curr.cap_pt + per_cta - 1) / per_cta, prev.B);

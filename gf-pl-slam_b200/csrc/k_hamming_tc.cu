@@ -33,29 +33,43 @@ __host__ __device__ inline size_t knn2_tc_smem_bytes(int cap_b) {
   return (size_t)((cap_b + 15) & ~15) * TC_ROW_BYTES + (size_t)TC_M * TC_ROW_BYTES + 2 * (size_t)cap_b * sizeof(uint32_t);
 }
 
+// BLOCKED (train sides too large to sit expanded in shared memory, e.g. 2000 x 2000 rows): grid = (column blocks, problems).
+// A CTA owns the b-rows [blockIdx.x * blk, + blk) of its problem — expanded once, resident — and walks ALL a-tiles against
+// them.  The reverse direction is complete inside the CTA (every a-row meets the block's b-rows); the forward direction
+// yields the two nearest b-rows WITHIN the block per a-row: packed keys (distance << 20 | global b-row) go to
+// `part` [problem][block][cap_a], and knn2_tc_merge_kernel takes the two smallest keys over the blocks (the integer order of
+// the keys is OpenCV's order, so the merged result is bit-identical to the unblocked one).  The a-tiles are re-expanded by
+// every block of the problem: +14 % ALU work at 288-row blocks against a train side that no longer has to fit.
+template <bool BLOCKED>
 __global__ void __launch_bounds__(TC_THREADS)
 knn2_tc_kernel(const uint8_t* __restrict__ a, const int32_t* __restrict__ na, int cap_a, const uint8_t* __restrict__ b,
-               const int32_t* __restrict__ nb, int cap_b, Knn2Out out_ab, Knn2Out out_ba) {
+               const int32_t* __restrict__ nb, int cap_b, Knn2Out out_ab, Knn2Out out_ba, int blk, uint2* __restrict__ part) {
+  const int cap_n = BLOCKED ? blk : cap_b;                                   // b-rows this CTA holds
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sN = smem;                                                        // [cap_b rounded to 16][256] rows of b
-  uint8_t* sM = smem + (size_t)((cap_b + 15) & ~15) * TC_ROW_BYTES;          // [128][256] one tile of a
-  uint32_t* s_rev = reinterpret_cast<uint32_t*>(sM + TC_M * TC_ROW_BYTES);   // [2][cap_b] best key of every b-row so far, per column half
+  uint8_t* sN = smem;                                                        // [cap_n rounded to 16][256] rows of b
+  uint8_t* sM = smem + (size_t)((cap_n + 15) & ~15) * TC_ROW_BYTES;          // [128][256] one tile of a
+  uint32_t* s_rev = reinterpret_cast<uint32_t*>(sM + TC_M * TC_ROW_BYTES);   // [2][cap_n] best key of every b-row so far, per column half
   __shared__ __align__(8) TcShared S;
 
-  const int p = blockIdx.x;
-  const int nq = na[p], nt = nb[p];
+  const int p = BLOCKED ? blockIdx.y : blockIdx.x;
+  const int j_first = BLOCKED ? blockIdx.x * blk : 0;                        // first b-row of this CTA
+  const int nq = na[p];
+  const int nt_all = nb[p];
+  const int nt = BLOCKED ? max(0, min(blk, nt_all - j_first)) : nt_all;     // b-rows of this CTA
   const int tid = threadIdx.x, warp = tid >> 5;
   const int row = tid & (TC_M - 1);     // row inside a tile = TMEM lane
   const int half = tid >> 7;            // which half of a product's columns this thread reduces
   const float inf = __int_as_float(0x7f800000);
   const uint8_t* q_base = a + (size_t)p * cap_a * 32;
-  const uint8_t* t_base = b + (size_t)p * cap_b * 32;
+  const uint8_t* t_base = b + ((size_t)p * cap_b + j_first) * 32;
   int2* idx_ab = out_ab.idx + (size_t)p * cap_a;
   float2* dist_ab = out_ab.dist + (size_t)p * cap_a;
-  int2* idx_ba = out_ba.idx + (size_t)p * cap_b;
-  float2* dist_ba = out_ba.dist + (size_t)p * cap_b;
+  int2* idx_ba = out_ba.idx + (size_t)p * cap_b + j_first;
+  float2* dist_ba = out_ba.dist + (size_t)p * cap_b + j_first;
+  uint2* part_p = BLOCKED ? part + ((size_t)p * gridDim.x + blockIdx.x) * cap_a : nullptr;
   if (nq == 0 || nt == 0) {  // nothing to multiply: "no match" rows on both sides (uniform exit, before any allocation)
-    for (int i = tid; i < nq; i += TC_THREADS) { idx_ab[i] = make_int2(-1, -1); dist_ab[i] = make_float2(inf, inf); }
+    if (BLOCKED) { for (int i = tid; i < nq; i += TC_THREADS) part_p[i] = make_uint2(KEY_NONE, KEY_NONE); }
+    else { for (int i = tid; i < nq; i += TC_THREADS) { idx_ab[i] = make_int2(-1, -1); dist_ab[i] = make_float2(inf, inf); } }
     for (int j = tid; j < nt; j += TC_THREADS) { idx_ba[j] = make_int2(-1, -1); dist_ba[j] = make_float2(inf, inf); }
     return;
   }
@@ -67,7 +81,7 @@ knn2_tc_kernel(const uint8_t* __restrict__ a, const int32_t* __restrict__ na, in
     const uint4* src = reinterpret_cast<const uint4*>(t_base + (size_t)r * 32);
     expand_row(sN, r, __ldg(src), __ldg(src + 1), TC_PAIR_TRAIN);
     s_rev[r] = KEY_NONE;
-    s_rev[cap_b + r] = KEY_NONE;
+    s_rev[cap_n + r] = KEY_NONE;
   }
   const uint32_t sM_addr = smem_u32(sM), sN_addr = smem_u32(sN);
   const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
@@ -123,7 +137,7 @@ knn2_tc_kernel(const uint8_t* __restrict__ a, const int32_t* __restrict__ na, in
           R.reset();
           tc_reduce_product<false>(R, taddr, half, nqt16, nqt, m0);
           const int j = j0 + row;                   // this thread owns (b-row j, its column half) in every tile
-          if (j < nt) s_rev[half * cap_b + j] = min(s_rev[half * cap_b + j], min(tc_canonical(R.k0a, R.kbase), tc_canonical(R.k0b, R.kbase)));
+          if (j < nt) s_rev[half * cap_n + j] = min(s_rev[half * cap_n + j], min(tc_canonical(R.k0a, R.kbase), tc_canonical(R.k0b, R.kbase)));
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -133,8 +147,12 @@ knn2_tc_kernel(const uint8_t* __restrict__ a, const int32_t* __restrict__ na, in
         if (mi < nq) {
           const uint2 o = s_merge[row];
           top2_update(k0, k1, o.x); top2_update(k0, k1, o.y);
-          idx_ab[mi] = make_int2((int)(k0 & KEY_IDX_MASK), k1 != KEY_NONE ? (int)(k1 & KEY_IDX_MASK) : -1);
-          dist_ab[mi] = make_float2((float)(k0 >> KEY_IDX_BITS), k1 != KEY_NONE ? (float)(k1 >> KEY_IDX_BITS) : inf);
+          if (BLOCKED) {   // keys carry block-local b-rows: make them global (the index field is the low 20 bits)
+            part_p[mi] = make_uint2(k0 + (uint32_t)j_first, k1 != KEY_NONE ? k1 + (uint32_t)j_first : KEY_NONE);
+          } else {
+            idx_ab[mi] = make_int2((int)(k0 & KEY_IDX_MASK), k1 != KEY_NONE ? (int)(k1 & KEY_IDX_MASK) : -1);
+            dist_ab[mi] = make_float2((float)(k0 >> KEY_IDX_BITS), k1 != KEY_NONE ? (float)(k1 >> KEY_IDX_BITS) : inf);
+          }
         }
       }
     }
@@ -142,10 +160,26 @@ knn2_tc_kernel(const uint8_t* __restrict__ a, const int32_t* __restrict__ na, in
   }
   tc_end(tmem);   // CTA barrier inside: s_rev is complete
   for (int j = tid; j < nt; j += TC_THREADS) {
-    const uint32_t k0 = min(s_rev[j], s_rev[cap_b + j]);
+    const uint32_t k0 = min(s_rev[j], s_rev[cap_n + j]);
     idx_ba[j] = make_int2((int)(k0 & KEY_IDX_MASK), -1);
     dist_ba[j] = make_float2((float)(k0 >> KEY_IDX_BITS), inf);
   }
+}
+
+// forward direction of the blocked form: the two smallest keys of every a-row over the column blocks
+__global__ void __launch_bounds__(256)
+knn2_tc_merge_kernel(const int32_t* __restrict__ na, int cap_a, int nblk, const uint2* __restrict__ part, Knn2Out out_ab) {
+  const int p = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= na[p]) return;
+  const float inf = __int_as_float(0x7f800000);
+  uint32_t k0 = KEY_NONE, k1 = KEY_NONE;
+  for (int c = 0; c < nblk; c++) {
+    const uint2 k = part[((size_t)p * nblk + c) * cap_a + i];
+    top2_update(k0, k1, k.x);
+    top2_update(k0, k1, k.y);
+  }
+  out_ab.idx[(size_t)p * cap_a + i] = make_int2(k0 != KEY_NONE ? (int)(k0 & KEY_IDX_MASK) : -1, k1 != KEY_NONE ? (int)(k1 & KEY_IDX_MASK) : -1);
+  out_ab.dist[(size_t)p * cap_a + i] = make_float2(k0 != KEY_NONE ? (float)(k0 >> KEY_IDX_BITS) : inf, k1 != KEY_NONE ? (float)(k1 >> KEY_IDX_BITS) : inf);
 }
 
 // ---- small problems (both sides <= 128 rows: line descriptors), both norms -----------------------------------------
@@ -450,19 +484,49 @@ int launch_measure_int8_peak(gfpl_ctx* ctx, double* int8_tops) {
   return GFPL_OK;
 }
 
+// a train side of up to TC_RESIDENT_ROWS rows sits expanded in shared memory with two CTAs per SM (304 rows: 112 KB)
+constexpr int TC_RESIDENT_ROWS = 320;
+constexpr int TC_BLOCK_ROWS = 288;     // column block of the blocked form: 2.25 accumulator passes, two CTAs per SM
+
 bool knn2_tc_fits(int cap_a, int cap_b) {
-  // small problems are dominated by the fixed cost of a CTA (TMEM allocation, barriers): they go to knn2_tc_small_kernel
-  return cap_a >= 128 && cap_b >= 128 && cap_a < (1 << TC_KEY_SHIFT) && cap_b < (1 << TC_KEY_SHIFT) &&
-         knn2_tc_smem_bytes(cap_b) <= 200 * 1024;
+  // small problems are dominated by the fixed cost of a CTA (TMEM allocation, barriers): they go to knn2_tc_small_kernel;
+  // larger train sides than the resident form holds go through the column-blocked form
+  return cap_a >= 128 && cap_b >= 128 && cap_a < (1 << TC_KEY_SHIFT) && cap_b < (1 << TC_KEY_SHIFT);
+}
+
+// number of column blocks and their size (a multiple of 16, as even as possible, at most TC_BLOCK_ROWS)
+void tc_column_blocks(int cap_n, int* nblk, int* blk) {
+  *nblk = (cap_n + TC_BLOCK_ROWS - 1) / TC_BLOCK_ROWS;
+  *blk = (((cap_n + *nblk - 1) / *nblk) + 15) & ~15;
 }
 
 int launch_knn2_tc(gfpl_ctx* ctx, int B, const uint8_t* a, const int32_t* na, int cap_a, const uint8_t* b, const int32_t* nb,
                    int cap_b, Knn2Out out_ab, Knn2Out out_ba) {
-  const size_t smem = knn2_tc_smem_bytes(cap_b);
-  GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  knn2_tc_kernel<<<B, TC_THREADS, smem, ctx->stream>>>(a, na, cap_a, b, nb, cap_b, out_ab, out_ba);
-  GFPL_LAUNCH_OK(ctx);
-  return GFPL_OK;
+  if (cap_b <= TC_RESIDENT_ROWS) {
+    const size_t smem = knn2_tc_smem_bytes(cap_b);
+    GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(knn2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn2_tc_kernel<false><<<B, TC_THREADS, smem, ctx->stream>>>(a, na, cap_a, b, nb, cap_b, out_ab, out_ba, 0, nullptr);
+    GFPL_LAUNCH_OK(ctx);
+    return GFPL_OK;
+  }
+  int nblk, blk;
+  tc_column_blocks(cap_b, &nblk, &blk);
+  uint2* part = nullptr;   // forward partials [B][nblk][cap_a], from the context's stream-ordered pool
+  const size_t part_bytes = (size_t)B * nblk * cap_a * sizeof(uint2);
+  GFPL_CUDA_OK(ctx, ctx->pool ? cudaMallocFromPoolAsync((void**)&part, part_bytes, ctx->pool, ctx->stream)
+                              : cudaMallocAsync((void**)&part, part_bytes, ctx->stream));
+  int rc = GFPL_OK;
+  const size_t smem = knn2_tc_smem_bytes(blk);
+  if (cudaFuncSetAttribute(knn2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) rc = GFPL_E_CUDA;
+  if (rc == GFPL_OK) {
+    knn2_tc_kernel<true><<<dim3(nblk, B), TC_THREADS, smem, ctx->stream>>>(a, na, cap_a, b, nb, cap_b, out_ab, out_ba, blk, part);
+    knn2_tc_merge_kernel<<<dim3((cap_a + 255) / 256, B), 256, 0, ctx->stream>>>(na, cap_a, nblk, part, out_ab);
+    ctx->launches += 2;
+    if (cudaGetLastError() != cudaSuccess) rc = GFPL_E_CUDA;
+  }
+  cudaFreeAsync(part, ctx->stream);   // stream-ordered: after the merge
+  if (rc != GFPL_OK) set_last_error(ctx, "blocked tensor-core knn launch failed (%d blocks of %d rows)", nblk, blk);
+  return rc;
 }
 
 }  // namespace gfpl

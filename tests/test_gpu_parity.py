@@ -891,7 +891,8 @@ def test_knn2_mutual_both_directions(ctx, orc, norm, tie):
     rng = np.random.default_rng(41 + norm)
     mk = (lambda n: synth.tie_stress_descriptors(rng, n)) if tie else (lambda n: rng.integers(0, 256, (n, 32), dtype=np.uint8))
     for cap_q, cap_t, sizes in ((300, 310, [(300, 310), (257, 129), (128, 160), (2, 3), (0, 5), (7, 0), (130, 161)]),
-                                (1000, 900, [(1000, 900), (513, 321)]),
+                                (1000, 900, [(1000, 900), (513, 321)]),                       # column-blocked tensor-core form
+                                (2000, 2000, [(2000, 2000), (1999, 577), (300, 2000), (129, 289), (2000, 0), (5, 1153)]),
                                 (100, 100, [(100, 100), (64, 17), (2, 2)])):
         B = len(sizes)
         q = np.zeros((B, cap_q, 32), np.uint8); t = np.zeros((B, cap_t, 32), np.uint8)

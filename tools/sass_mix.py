@@ -26,3 +26,19 @@ for f in funcs:
     print()
 print("Pipes: POPC -> 16 lanes/clk/SM; LOP3/IADD3/VIMNMX/SHF/ISETP -> ALU pipe (64 lanes/clk/SM); IMAD -> FMA pipe; "
       "LDS.128 (broadcast) -> LSU.  `UBLKCP` = cp.async.bulk (1-D TMA), `SYNCS.*` = mbarrier.")
+
+# ---- tensor-core kernels: proof of the tcgen05 / TMEM / bulk-copy path and the selection instruction mix ----------------
+print("\n# Tensor-core kernels (tcgen05.mma kind::i8 -> UTCIMMA, tcgen05.ld -> LDTM, tcgen05.commit -> UTCBAR, "
+      "tcgen05.alloc/dealloc -> UTCATOMSWS / UTCDEALLOC... as cuobjdump names them)\n")
+print("| kernel | UTCIMMA | LDTM | UTCBAR | SYNCS (mbarrier) | VIADDMNMX | VIMNMX3 | VIMNMX | PRMT | STS.128 | total |\n|---|---|---|---|---|---|---|---|---|---|---|")
+for f in funcs:
+    name = f.split("\n", 1)[0]
+    if not re.search(r"knn2_tc_kernel|knn2_tc_small_kernel|knn2_tc_stream_kernel|f2f_hybrid_points_tc_kernel|int8_peak_kernel", name):
+        continue
+    ops = re.findall(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", f, flags=re.M)
+    c = collections.Counter(ops)
+    def n(prefix):
+        return sum(v for k, v in c.items() if k.startswith(prefix))
+    short = re.sub(r"^_ZN4gfpl\d+", "", name)[:48]
+    print("| `%s` | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d |" % (short, n("UTCIMMA"), n("LDTM"), n("UTCBAR"), n("SYNCS"), n("VIADDMNMX"),
+          n("VIMNMX3"), n("VIMNMX") - n("VIMNMX3"), n("PRMT"), n("STS.128"), len(ops)))

@@ -9,10 +9,11 @@ from gfpl import api, synth, _structs as S
 import orc
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-d = synth.make_pairs(B, n_pt=300, n_ln=100, seed=1000, pinned=True)
+NPT, NLN = int(os.environ.get("GFPL_NPT", "300")), int(os.environ.get("GFPL_NLN", "100"))   # GFPL_NPT=2000 GFPL_NLN=500: config C4
+d = synth.make_pairs(B, n_pt=NPT, n_ln=NLN, seed=1000, pinned=True)
 ctx = api.Context(0, cam=d["cam"])
 prev = orc.stereo_match(d["cam"], ctx.cfg, d["prev_raw"]).repack()      # CPU: independent of the kernels under test
-rp = api.Replay(ctx, B, 300, 100, prev.cap_pt, prev.cap_ln)
+rp = api.Replay(ctx, B, NPT, NLN, prev.cap_pt, prev.cap_ln)
 rp.upload(prev, d["state"], d["curr_raw"])
 flags = S.TRACK_LINECUT | S.TRACK_SEED_GIVEN
 acc = None
