@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--no-linecut", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="pairs per step of the CPU reference arm")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--lba-windows", type=int, default=512, help="windows per call of the local-BA (configs[2]) side measurement")
     ap.add_argument("--c4-pairs", type=int, default=2048, help="frame pairs of the dense-feature (configs[3]) side measurement; 0 = skip")
     ap.add_argument("--pipeline", type=int, default=int(os.environ.get("GFPL_PIPELINE", "1")),
                     help="sub-batches of the software pipeline of the resident step (1 = off)")
@@ -94,14 +95,22 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def native_cpu_build():
+    global CPU_FLAGS
+    if CPU_FLAGS is None:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import orc
+        CPU_FLAGS = orc.use_native_build()
+    return CPU_FLAGS
+
+
 def cpu_reference(a, rank_seed=0):
     """The reference's CPU algorithm for the path: the oracle port (the reference itself cannot be built here,
     DESIGN.md §3), all host threads, on a bounded sample of the same workload."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import orc
     from gfpl import synth, _structs as S
-    global CPU_FLAGS
-    CPU_FLAGS = orc.use_native_build()   # the reference's own flags (-O3 -march=native), built on this machine
+    native_cpu_build()                   # the reference's own flags (-O3 -march=native), built on this machine
     n = min(a.pairs, a.cpu_sample)
     cores = os.cpu_count() or 1
     d = synth.make_pairs(n, n_pt=a.n_pt, n_ln=a.n_ln, seed=1000 + rank_seed)
@@ -232,6 +241,77 @@ def dense_c4(a, ctx, api, synth, S, int8_peak, skip_cpu):
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port", "build_flags": CPU_FLAGS,
                                "sample": "%d of %d pairs, one pass, %d std::threads over pairs" % (n, B, cores)}
+    return out
+
+
+def lba_c3(a, ctx, synth, hbm_peak, skip_cpu):
+    W, distinct = a.lba_windows, 16
+    base = [synth.make_lba_window(seed=300 + i, n_kf=10, n_pt=1000, n_ls=300) for i in range(distinct)]
+    wins = [base[i % distinct] for i in range(W)]
+    ctx.set_camera(base[0]["cam"])
+    h = ctx.lba_batch_prepare(wins)                       # ctypes views of the caller's arrays (no copies)
+    ctx.lba_step_batch_prepared(h, 0.001, 1)
+    reps, t_dev = 5, 0.0
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ctx.lba_step_batch_prepared(h, 0.001, 1)
+        t_dev += ctx.timer_elapsed_ms(6, 7)
+    wall = (time.perf_counter() - t0) / reps
+    t_dev /= reps
+    w0 = base[0]
+    npo, nlo, Npt, Nls, Nkf = len(w0["pt_obs_lm"]), len(w0["ls_obs_lm"]), len(w0["X_pt"]), len(w0["X_ls"]), len(w0["kf_Tkw"])
+    # algorithmic bytes of one pass (SURVEY.md §8d K6 + the solve): observations and indices in, state in, blocks out,
+    # blocks + Y in / out again for the elimination, DX out
+    alg = (npo * (12 + 16 + 8) + nlo * (12 + 24 + 8) + Nkf * 128 + Npt * 24 + Nls * 48
+           + 8 * (Nkf * 36 + Npt * 9 + Nls * 36 + npo * 18 + nlo * 36 + 6 * Nkf + 3 * Npt + 6 * Nls)
+           + 8 * 2 * (npo * 18 + nlo * 36) + 8 * (Npt * 9 + Nls * 36) + 8 * (6 * Nkf + 3 * Npt + 6 * Nls))
+    out = {"workload": "local BA, one LM pass (assembly + damped Schur-complement solve) of %d independent KITTI-shaped windows "
+                       "(%d distinct, repeated): 10 KF, 1000 points x 4 obs, 300 lines x 3 obs each" % (W, distinct),
+           "value": W / (t_dev * 1e-3), "unit": "windows/s", "kernel_ms_per_batch": t_dev,
+           "e2e": {"value": W / wall, "unit": "windows/s", "ms_per_batch": wall * 1e3,
+                   "path": "gfpl_lba_step_batch: pack + one H2D + 9 kernels for the whole batch + 3 D2H, host wall clock"},
+           "roofline": {"bound": "hbm", "achieved": W * alg / (t_dev * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": W * alg / (t_dev * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_window": alg,
+                        "note": "9 launches per batch; the pass is bound by the per-window chain (60 x 60 dense LDL^T by one CTA, "
+                                "fp64 atomics of the block reduction), not by HBM"}}
+    if not skip_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import orc
+        import scipy.sparse as sp
+        import scipy.sparse.linalg as spl
+        cfg = orc.default_config()
+        t0 = time.perf_counter()
+        blk = orc.lba_assemble(w0["cam"], cfg, w0)
+        t_asm = time.perf_counter() - t0
+        # the reference factorises the damped H with Eigen::SimplicialLDLT (mapHandler.cpp:1436-1441); SuperLU stands in
+        N = 6 * Nkf + 3 * Npt + 6 * Nls
+        rows, cols, vals = [], [], []
+
+        def add(r0, c0, B):
+            r, c = np.meshgrid(np.arange(B.shape[0]) + r0, np.arange(B.shape[1]) + c0, indexing="ij")
+            rows.append(r.ravel()); cols.append(c.ravel()); vals.append(B.ravel())
+        for k in range(Nkf):
+            add(6 * k, 6 * k, blk["Hkk"][k].reshape(6, 6))
+        for j in range(Npt):
+            add(6 * Nkf + 3 * j, 6 * Nkf + 3 * j, blk["Hpp"][j].reshape(3, 3))
+        for j in range(Nls):
+            add(6 * Nkf + 3 * Npt + 6 * j, 6 * Nkf + 3 * Npt + 6 * j, blk["Hll"][j].reshape(6, 6))
+        for o in np.nonzero(w0["pt_obs_kf"] >= 0)[0]:
+            Bk = blk["Hpk"][o].reshape(3, 6)
+            add(6 * Nkf + 3 * w0["pt_obs_lm"][o], 6 * w0["pt_obs_kf"][o], Bk); add(6 * w0["pt_obs_kf"][o], 6 * Nkf + 3 * w0["pt_obs_lm"][o], Bk.T)
+        for o in np.nonzero(w0["ls_obs_kf"] >= 0)[0]:
+            Bk = blk["Hlk"][o].reshape(6, 6)
+            add(6 * Nkf + 3 * Npt + 6 * w0["ls_obs_lm"][o], 6 * w0["ls_obs_kf"][o], Bk); add(6 * w0["ls_obs_kf"][o], 6 * Nkf + 3 * Npt + 6 * w0["ls_obs_lm"][o], Bk.T)
+        H = sp.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(N, N))
+        H = H + sp.diags(H.diagonal() * 0.001)
+        t0 = time.perf_counter()
+        spl.spsolve(H, blk["g"])
+        t_solve = time.perf_counter() - t0
+        cores = os.cpu_count() or 1
+        out["cpu_baseline"] = {"value": cores / (t_asm + t_solve), "unit": "windows/s", "cores": cores, "kind": "port",
+                               "sample": "one window on one thread: oracle assembly %.2f ms (%s) + SuperLU sparse solve %.2f ms "
+                                         "(stand-in for Eigen::SimplicialLDLT); windows are independent, so the figure is "
+                                         "cores / time per window" % (t_asm * 1e3, CPU_FLAGS, t_solve * 1e3)}
     return out
 
 
@@ -408,6 +488,8 @@ def main():
     ms, e2e_ms = float(t[0]), float(t[1])
 
     if rank == 0:
+        if not a.skip_cpu_baseline:   # CPU arm: the oracle sources rebuilt with the reference's flags on this machine
+            native_cpu_build()
         value = world * B * a.steps / (ms * 1e-3)
         e2e_value = world * B * a.steps / (e2e_ms * 1e-3)
         # ---- rooflines ---------------------------------------------------------------------------
@@ -494,27 +576,16 @@ def main():
                                                "f2f_accept", "uncertainty+linecut", "pose_gn", "step"], [float(x) for x in stage])),
                "kernel_ms_note": "CUDA events between the kernels of the UNPIPELINED step (one stream); the headline value runs the same kernels pipelined over %d sub-batches" % a.pipeline,
                "peaks": {"popc_Tops": popc_peak, "alu_lop3_Tops": alu_peak, "fp64_TFLOPs": fp64_peak, "int8_tensor_TOPs": int8_peak}}
-        # C3 side note: one Levenberg-Marquardt pass of local BA (assembly + damped Schur solve) on a
-        # KITTI-shaped 10-key-frame window, through the C ABI with host buffers (copies included)
+        # C3 (BASELINE configs[2]): local BA over 10-key-frame windows, KITTI-shaped.  One LM pass (assembly + damped Schur
+        # solve) of W independent windows per call of gfpl_lba_step_batch; windows/s with host buffers (copies included) and
+        # from the kernels' device time (CUDA events, timer slots 6 -> 7).
         try:
-            w = synth.make_lba_window(seed=1, n_kf=10, n_pt=1000, n_ls=300)
-            ctx.set_camera(w["cam"])
-            ctx.lba_step(w, 0.001, 1)
-            t0 = time.perf_counter()
-            for _ in range(20):
-                ctx.lba_step(w, 0.001, 1)
-            out["lba_c3"] = {"ms_per_lm_pass": (time.perf_counter() - t0) / 20 * 1e3, "window": "10 KF, 1000 points x 4 obs, 300 lines x 3 obs",
-                             "path": "gfpl_lba_step: H2D + lba_assemble_kernel + Schur-complement solve kernels + D2H"}
+            out["lba_c3"] = lba_c3(a, ctx, synth, hbm_peak, a.skip_cpu_baseline)
             ctx.set_camera(d["cam"])
-        except Exception as e:  # a side note must not break the contract line
+        except Exception as e:  # a side measurement must not break the contract line
             out["lba_c3"] = {"unavailable": repr(e)}
         if a.c4_pairs > 0:
             try:
-                if not a.skip_cpu_baseline:
-                    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-                    import orc
-                    global CPU_FLAGS
-                    CPU_FLAGS = orc.use_native_build()
                 for _, r in slots[1:]:
                     r.close()                                     # the e2e slots' device buffers are no longer needed
                 out["c4_dense"] = dense_c4(a, ctx, api, synth, S, int8_peak, a.skip_cpu_baseline)

@@ -292,6 +292,7 @@ void gfpl_ctx_destroy(gfpl_ctx* ctx) {
     if (e) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
+  if (ctx->staging) cudaFreeHost(ctx->staging);
   delete ctx;
 }
 
@@ -1285,40 +1286,179 @@ int gfpl_timer_elapsed_ms(gfpl_ctx* ctx, int32_t a, int32_t b, float* ms) {
   return GFPL_OK;
 }
 
-// ---- L2 ---------------------------------------------------------------------------------------------------
-// device copies of an LBA window and of its block storage
-static bool mirror_lba(DevMem& m, const gfpl_lba_problem* pb, gfpl_lba_problem* d, gfpl_lba_blocks* o) {
-  *d = *pb;
-  d->kf_Tkw = m.upload(pb->kf_Tkw, (size_t)pb->Nkf * 16);
-  d->X_pt = m.upload(pb->X_pt, (size_t)pb->Npt * 3);
-  d->X_ls = m.upload(pb->X_ls, (size_t)pb->Nls * 6);
-  d->pt_obs_lm = m.upload(pb->pt_obs_lm, pb->n_pt_obs); d->pt_obs_kf = m.upload(pb->pt_obs_kf, pb->n_pt_obs);
-  d->pt_obs_fix = m.upload(pb->pt_obs_fix, pb->n_pt_obs);
-  d->pt_obs_uv = m.upload(pb->pt_obs_uv, (size_t)pb->n_pt_obs * 2); d->pt_obs_s2 = m.upload(pb->pt_obs_s2, pb->n_pt_obs);
-  d->ls_obs_lm = m.upload(pb->ls_obs_lm, pb->n_ls_obs); d->ls_obs_kf = m.upload(pb->ls_obs_kf, pb->n_ls_obs);
-  d->ls_obs_fix = m.upload(pb->ls_obs_fix, pb->n_ls_obs);
-  d->ls_obs_le = m.upload(pb->ls_obs_le, (size_t)pb->n_ls_obs * 3); d->ls_obs_s2 = m.upload(pb->ls_obs_s2, pb->n_ls_obs);
-  d->fix_Tkw = m.upload(pb->fix_Tkw, (size_t)pb->n_fix * 16);
-  const size_t N = 6 * (size_t)pb->Nkf + 3 * (size_t)pb->Npt + 6 * (size_t)pb->Nls;
-  o->Hkk = m.alloc<double>((size_t)pb->Nkf * 36); o->Hpp = m.alloc<double>((size_t)pb->Npt * 9);
-  o->Hll = m.alloc<double>((size_t)pb->Nls * 36); o->Hpk = m.alloc<double>((size_t)pb->n_pt_obs * 18);
-  o->Hlk = m.alloc<double>((size_t)pb->n_ls_obs * 36); o->g = m.alloc<double>(N); o->err = m.alloc<double>(1);
-  return d->kf_Tkw && d->X_pt && d->X_ls && d->pt_obs_lm && d->pt_obs_kf && d->pt_obs_fix && d->pt_obs_uv &&
-         d->pt_obs_s2 && d->ls_obs_lm && d->ls_obs_kf && d->ls_obs_fix && d->ls_obs_le && d->ls_obs_s2 &&
-         d->fix_Tkw && o->Hkk && o->Hpp && o->Hll && o->Hpk && o->Hlk && o->g && o->err;
+// ---- L2 / §8f-3: local bundle adjustment, batched over windows ------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+// CSR offsets of an observation list sorted by landmark (the order localBundleAdjustment produces, :1146-1209)
+bool landmark_offsets(const int32_t* lm, int n_obs, int n_lm, int32_t* off) {
+  for (int j = 0; j <= n_lm; j++) off[j] = 0;
+  int prev = 0;
+  for (int o = 0; o < n_obs; o++) {
+    if (lm[o] < prev || lm[o] >= n_lm) return false;
+    prev = lm[o];
+    off[(size_t)lm[o] + 1]++;
+  }
+  for (int j = 0; j < n_lm; j++) off[(size_t)j + 1] += off[j];
+  return true;
 }
+
+// All windows of a batch in ONE device buffer: [ inputs (one H2D copy) | block storage (one memset) | solve scratch | DX |
+// lambda_eff | window descriptors ].  `host` is the packed image of the input region.
+struct LbaBatch {
+  int W = 0, max_kf = 0, max_pt = 0, max_ls = 0, max_pt_obs = 0, max_ls_obs = 0;
+  uint8_t* host = nullptr;           // packed image of the input region (pinned staging of the context)
+  std::vector<LbaWin> wins;          // device pointers
+  std::vector<size_t> dx_off;        // [W + 1] offsets (in doubles) of the windows' DX in the concatenated output
+  size_t in_bytes = 0, zero_off = 0, zero_bytes = 0, err_off = 0, dx_base = 0, lam_off = 0, wins_off = 0, total = 0;
+  uint8_t* dev = nullptr;
+
+  static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+  // pass 1 (dev == nullptr): sizes; pass 2: fill `host` and the device pointers
+  template <typename T>
+  const T* put(size_t& cur, const T* src, size_t n) {
+    const size_t off = cur;
+    cur = al(cur + n * sizeof(T));
+    if (dev) {
+      if (n) memcpy(host + off, src, n * sizeof(T));
+      return (const T*)(dev + off);
+    }
+    return nullptr;
+  }
+  template <typename T>
+  T* room(size_t& cur, size_t n) {
+    const size_t off = cur;
+    cur = al(cur + n * sizeof(T));
+    return dev ? (T*)(dev + off) : nullptr;
+  }
+
+  bool layout(const gfpl_lba_problem* probs, bool with_solve) {
+    size_t cur = 0;
+    for (int w = 0; w < W; w++) {   // ---- inputs
+      const gfpl_lba_problem& pb = probs[w];
+      LbaWin L{};
+      L.pb = pb;
+      L.pb.kf_Tkw = put(cur, pb.kf_Tkw, (size_t)pb.Nkf * 16);
+      L.pb.X_pt = put(cur, pb.X_pt, (size_t)pb.Npt * 3);
+      L.pb.X_ls = put(cur, pb.X_ls, (size_t)pb.Nls * 6);
+      L.pb.pt_obs_lm = put(cur, pb.pt_obs_lm, pb.n_pt_obs); L.pb.pt_obs_kf = put(cur, pb.pt_obs_kf, pb.n_pt_obs);
+      L.pb.pt_obs_fix = put(cur, pb.pt_obs_fix, pb.n_pt_obs);
+      L.pb.pt_obs_uv = put(cur, pb.pt_obs_uv, (size_t)pb.n_pt_obs * 2); L.pb.pt_obs_s2 = put(cur, pb.pt_obs_s2, pb.n_pt_obs);
+      L.pb.ls_obs_lm = put(cur, pb.ls_obs_lm, pb.n_ls_obs); L.pb.ls_obs_kf = put(cur, pb.ls_obs_kf, pb.n_ls_obs);
+      L.pb.ls_obs_fix = put(cur, pb.ls_obs_fix, pb.n_ls_obs);
+      L.pb.ls_obs_le = put(cur, pb.ls_obs_le, (size_t)pb.n_ls_obs * 3); L.pb.ls_obs_s2 = put(cur, pb.ls_obs_s2, pb.n_ls_obs);
+      L.pb.fix_Tkw = put(cur, pb.fix_Tkw, (size_t)pb.n_fix * 16);
+      if (with_solve) {
+        const size_t o_pt = cur;
+        L.pt_off = room<int32_t>(cur, (size_t)pb.Npt + 1);
+        const size_t o_ls = cur;
+        L.ls_off = room<int32_t>(cur, (size_t)pb.Nls + 1);
+        if (dev && (!landmark_offsets(pb.pt_obs_lm, pb.n_pt_obs, pb.Npt, (int32_t*)(host + o_pt)) ||
+                    !landmark_offsets(pb.ls_obs_lm, pb.n_ls_obs, pb.Nls, (int32_t*)(host + o_ls))))
+          return false;
+      }
+      if (dev) wins[w] = L;
+    }
+    in_bytes = cur;
+    zero_off = cur;
+    err_off = cur;
+    double* err_all = room<double>(cur, W);   // ---- block storage (zeroed): err of every window first, contiguous
+    for (int w = 0; w < W; w++) {
+      const gfpl_lba_problem& pb = probs[w];
+      const size_t N = 6 * (size_t)pb.Nkf + 3 * (size_t)pb.Npt + 6 * (size_t)pb.Nls;
+      gfpl_lba_blocks H{};
+      H.Hkk = room<double>(cur, (size_t)pb.Nkf * 36); H.Hpp = room<double>(cur, (size_t)pb.Npt * 9);
+      H.Hll = room<double>(cur, (size_t)pb.Nls * 36); H.Hpk = room<double>(cur, (size_t)pb.n_pt_obs * 18);
+      H.Hlk = room<double>(cur, (size_t)pb.n_ls_obs * 36); H.g = room<double>(cur, N);
+      H.err = dev ? err_all + w : nullptr;
+      if (dev) wins[w].H = H;
+    }
+    zero_bytes = cur - zero_off;
+    if (with_solve) {
+      for (int w = 0; w < W; w++) {   // ---- solve scratch
+        const gfpl_lba_problem& pb = probs[w];
+        const size_t nk = 6 * (size_t)pb.Nkf;
+        LbaSolveWork k{};
+        k.S = room<double>(cur, nk * nk);
+        k.Ypt = room<double>(cur, (size_t)pb.n_pt_obs * 18); k.Zpt = room<double>(cur, (size_t)pb.Npt * 3);
+        k.Yls = room<double>(cur, (size_t)pb.n_ls_obs * 36); k.Zls = room<double>(cur, (size_t)pb.Nls * 6);
+        if (dev) wins[w].w = k;
+      }
+      dx_base = cur;               // ---- DX of every window, concatenated (one D2H copy)
+      double* dx_all = room<double>(cur, dx_off[W]);
+      lam_off = cur;
+      double* lam_all = room<double>(cur, W);
+      if (dev)
+        for (int w = 0; w < W; w++) { wins[w].DX = dx_all + dx_off[w]; wins[w].lambda_eff = lam_all + w; }
+    }
+    wins_off = cur;
+    room<LbaWin>(cur, W);
+    total = cur;
+    return true;
+  }
+};
+
+// validate, lay out, upload and zero; on success b.dev holds everything and d_wins the device descriptor array
+int lba_batch_begin(gfpl_ctx* ctx, DevMem& m, int W, const gfpl_lba_problem* probs, bool with_solve, LbaBatch& b, const LbaWin** d_wins) {
+  b.W = W;
+  b.dx_off.assign((size_t)W + 1, 0);
+  for (int w = 0; w < W; w++) {
+    const gfpl_lba_problem& pb = probs[w];
+    REQUIRE(ctx, pb.Nkf >= 0 && pb.Npt >= 0 && pb.Nls >= 0 && pb.n_pt_obs >= 0 && pb.n_ls_obs >= 0 && pb.n_fix >= 0);
+    b.dx_off[(size_t)w + 1] = b.dx_off[w] + 6 * (size_t)pb.Nkf + 3 * (size_t)pb.Npt + 6 * (size_t)pb.Nls;
+    b.max_kf = pb.Nkf > b.max_kf ? pb.Nkf : b.max_kf;
+    b.max_pt = pb.Npt > b.max_pt ? pb.Npt : b.max_pt;
+    b.max_ls = pb.Nls > b.max_ls ? pb.Nls : b.max_ls;
+    b.max_pt_obs = pb.n_pt_obs > b.max_pt_obs ? pb.n_pt_obs : b.max_pt_obs;
+    b.max_ls_obs = pb.n_ls_obs > b.max_ls_obs ? pb.n_ls_obs : b.max_ls_obs;
+  }
+  b.layout(probs, with_solve);                       // sizes
+  b.dev = m.alloc<uint8_t>(b.total);
+  REQUIRE_MEM(ctx, b.dev);
+  // the previous call's H2D copy out of the staging buffer has completed: every entry point ends with a synchronisation
+  if (ctx->staging_bytes < b.in_bytes) {
+    if (ctx->staging) cudaFreeHost(ctx->staging);
+    ctx->staging = nullptr;
+    ctx->staging_bytes = 0;
+    const size_t want = b.in_bytes + b.in_bytes / 4;
+    if (cudaHostAlloc(&ctx->staging, want, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      set_last_error(ctx, "cannot allocate %zu bytes of pinned staging memory", want);
+      return GFPL_E_NOMEM;
+    }
+    ctx->staging_bytes = want;
+  }
+  b.host = (uint8_t*)ctx->staging;
+  b.wins.resize(W);
+  if (!b.layout(probs, with_solve)) {
+    set_last_error(ctx, "local BA: observations must be sorted by landmark index and index existing landmarks");
+    return GFPL_E_INVALID;
+  }
+  GFPL_CUDA_OK(ctx, cudaMemcpyAsync(b.dev, b.host, b.in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  GFPL_CUDA_OK(ctx, cudaMemcpyAsync(b.dev + b.wins_off, b.wins.data(), (size_t)W * sizeof(LbaWin), cudaMemcpyHostToDevice, ctx->stream));
+  GFPL_CUDA_OK(ctx, cudaMemsetAsync(b.dev + b.zero_off, 0, b.zero_bytes, ctx->stream));
+  *d_wins = (const LbaWin*)(b.dev + b.wins_off);
+  return GFPL_OK;
+}
+
+}  // namespace
+
+extern "C" {
 
 int gfpl_lba_assemble(gfpl_ctx* ctx, const gfpl_lba_problem* pb, gfpl_lba_blocks* out) {
   if (!ctx) return GFPL_E_INVALID;
-  REQUIRE(ctx, pb && out && pb->Nkf >= 0 && pb->Npt >= 0 && pb->Nls >= 0 && pb->n_pt_obs >= 0 && pb->n_ls_obs >= 0);
+  REQUIRE(ctx, pb && out);
   REQUIRE(ctx, out->Hkk && out->Hpp && out->Hll && out->Hpk && out->Hlk && out->g && out->err);
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   DevMem m(ctx);
-  gfpl_lba_problem d;
-  gfpl_lba_blocks o;
-  REQUIRE_MEM(ctx, mirror_lba(m, pb, &d, &o));
+  LbaBatch b;
+  const LbaWin* dw = nullptr;
+  CHECK(lba_batch_begin(ctx, m, 1, pb, false, b, &dw));
   const size_t N = 6 * (size_t)pb->Nkf + 3 * (size_t)pb->Npt + 6 * (size_t)pb->Nls;
-  CHECK(launch_lba_assemble(ctx, d, o));
+  CHECK(launch_lba_assemble(ctx, dw, 1, b.max_kf, b.max_pt_obs, b.max_ls_obs));
+  const gfpl_lba_blocks& o = b.wins[0].H;
   download(ctx, out->Hkk, o.Hkk, (size_t)pb->Nkf * 36); download(ctx, out->Hpp, o.Hpp, (size_t)pb->Npt * 9);
   download(ctx, out->Hll, o.Hll, (size_t)pb->Nls * 36); download(ctx, out->Hpk, o.Hpk, (size_t)pb->n_pt_obs * 18);
   download(ctx, out->Hlk, o.Hlk, (size_t)pb->n_ls_obs * 36); download(ctx, out->g, o.g, N);
@@ -1326,53 +1466,38 @@ int gfpl_lba_assemble(gfpl_ctx* ctx, const gfpl_lba_problem* pb, gfpl_lba_blocks
   return finish(ctx);
 }
 
-// CSR offsets of an observation list sorted by landmark (the order localBundleAdjustment produces, :1146-1209)
-static bool landmark_offsets(const int32_t* lm, int n_obs, int n_lm, std::vector<int32_t>* off) {
-  off->assign((size_t)n_lm + 1, 0);
-  int prev = 0;
-  for (int o = 0; o < n_obs; o++) {
-    if (lm[o] < prev || lm[o] >= n_lm) return false;
-    prev = lm[o];
-    (*off)[(size_t)lm[o] + 1]++;
-  }
-  for (int j = 0; j < n_lm; j++) (*off)[(size_t)j + 1] += (*off)[j];
-  return true;
+int gfpl_lba_step_batch(gfpl_ctx* ctx, int32_t W, const gfpl_lba_problem* probs, double lambda, int32_t scale_by_hmax, double* DX,
+                        double* err_sum, double* lambda_eff) {
+  if (!ctx) return GFPL_E_INVALID;
+  REQUIRE(ctx, W >= 0);
+  if (W == 0) return GFPL_OK;
+  REQUIRE(ctx, probs && DX && err_sum && lambda_eff);
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DevMem m(ctx);
+  LbaBatch b;
+  const LbaWin* dw = nullptr;
+  CHECK(lba_batch_begin(ctx, m, W, probs, true, b, &dw));
+  for (int k = 0; k < 2; k++)
+    if (!ctx->timer[6 + k]) GFPL_CUDA_OK(ctx, cudaEventCreate(&ctx->timer[6 + k]));
+  GFPL_CUDA_OK(ctx, cudaEventRecord(ctx->timer[6], ctx->stream));
+  CHECK(launch_lba_assemble(ctx, dw, W, b.max_kf, b.max_pt_obs, b.max_ls_obs));
+  CHECK(launch_lba_solve(ctx, dw, W, b.max_kf, b.max_pt, b.max_ls, lambda, scale_by_hmax));
+  GFPL_CUDA_OK(ctx, cudaEventRecord(ctx->timer[7], ctx->stream));
+  download(ctx, DX, (const double*)(b.dev + b.dx_base), b.dx_off[W]);
+  download(ctx, err_sum, (const double*)(b.dev + b.err_off), (size_t)W);
+  download(ctx, lambda_eff, (const double*)(b.dev + b.lam_off), (size_t)W);
+  CHECK(finish(ctx));
+  // a window without unknowns: the reference leaves lambda as it is and there is nothing to solve
+  for (int w = 0; w < W; w++)
+    if (b.dx_off[(size_t)w + 1] == b.dx_off[w]) { err_sum[w] = 0.0; lambda_eff[w] = lambda; }
+  return GFPL_OK;
 }
 
 int gfpl_lba_step(gfpl_ctx* ctx, const gfpl_lba_problem* pb, double lambda, int32_t scale_by_hmax, double* DX,
                   double* err_sum, double* lambda_eff) {
   if (!ctx) return GFPL_E_INVALID;
-  REQUIRE(ctx, pb && DX && err_sum && lambda_eff && pb->Nkf >= 0 && pb->Npt >= 0 && pb->Nls >= 0 && pb->n_pt_obs >= 0 &&
-                   pb->n_ls_obs >= 0);
-  const size_t N = 6 * (size_t)pb->Nkf + 3 * (size_t)pb->Npt + 6 * (size_t)pb->Nls;
-  if (N == 0) { *err_sum = 0.0; *lambda_eff = lambda; return GFPL_OK; }
-  std::vector<int32_t> pt_off, ls_off;
-  if (!landmark_offsets(pb->pt_obs_lm, pb->n_pt_obs, pb->Npt, &pt_off) ||
-      !landmark_offsets(pb->ls_obs_lm, pb->n_ls_obs, pb->Nls, &ls_off)) {
-    set_last_error(ctx, "gfpl_lba_step: observations must be sorted by landmark index and index existing landmarks");
-    return GFPL_E_INVALID;
-  }
-  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-  DevMem m(ctx);
-  gfpl_lba_problem d;
-  gfpl_lba_blocks o;
-  REQUIRE_MEM(ctx, mirror_lba(m, pb, &d, &o));
-  int32_t* dpo = m.upload(pt_off.data(), pt_off.size());
-  int32_t* dlo = m.upload(ls_off.data(), ls_off.size());
-  const size_t nk = 6 * (size_t)pb->Nkf;
-  LbaSolveWork w;
-  w.S = m.alloc<double>(nk * nk);
-  w.Ypt = m.alloc<double>((size_t)pb->n_pt_obs * 18); w.Zpt = m.alloc<double>((size_t)pb->Npt * 3);
-  w.Yls = m.alloc<double>((size_t)pb->n_ls_obs * 36); w.Zls = m.alloc<double>((size_t)pb->Nls * 6);
-  double* dDX = m.alloc<double>(N);
-  double* dlam = m.alloc<double>(1);
-  REQUIRE_MEM(ctx, dpo && dlo && w.S && w.Ypt && w.Zpt && w.Yls && w.Zls && dDX && dlam);
-  CHECK(launch_lba_assemble(ctx, d, o));
-  CHECK(launch_lba_solve(ctx, d, o, dpo, dlo, lambda, scale_by_hmax, w, dDX, dlam));
-  download(ctx, DX, dDX, N);
-  download(ctx, err_sum, o.err, 1);
-  download(ctx, lambda_eff, dlam, 1);
-  return finish(ctx);
+  REQUIRE(ctx, pb && DX && err_sum && lambda_eff);
+  return gfpl_lba_step_batch(ctx, 1, pb, lambda, scale_by_hmax, DX, err_sum, lambda_eff);
 }
 
 }  // extern "C"

@@ -41,10 +41,9 @@ struct gfpl_ctx {
   gfpl_config cfg{};
   int64_t launches = 0;
   std::string last_error;
-  // scratch arena for the host-pointer entry points (grown on demand, freed with the ctx)
-  void* scratch = nullptr;
-  size_t scratch_bytes = 0;
-  size_t scratch_used = 0;
+  // pinned host staging of the batched local-BA entry point (grown on demand, freed with the ctx)
+  void* staging = nullptr;
+  size_t staging_bytes = 0;
   cudaEvent_t timer[8] = {};
   // first failure of an asynchronous copy enqueued by an entry point (checked when the call synchronises)
   cudaError_t pending_error = cudaSuccess;
@@ -137,20 +136,25 @@ int launch_pose_optimize(gfpl_ctx* ctx, DevTrackObs obs, const gfpl_frame_state*
                          int overload, gfpl_pose_result* out, void* raw_scratch = nullptr);
 size_t pose_raw_bytes(int B);   // size of the optimiser -> finalize hand-off buffer for B pairs
 
-// K6: LBA assembly (device copies of the flat problem)
-int launch_lba_assemble(gfpl_ctx* ctx, const gfpl_lba_problem& dprob, gfpl_lba_blocks dout);
-
-// scratch of the Schur-complement solve (k_lba_solve.cu)
+// K6 / §8f-3: local BA over a BATCH of independent windows.  One LbaWin per window, all pointers DEVICE pointers (into
+// one buffer that holds every window's arrays); the kernels take the array and select their window by blockIdx.y.
 struct LbaSolveWork {
-  double* S;     // [6Nkf][6Nkf]
+  double* S;          // [6Nkf][6Nkf]
   double *Ypt, *Zpt;  // [n_pt_obs][18], [Npt][3]
   double *Yls, *Zls;  // [n_ls_obs][36], [Nls][6]
 };
-// DX (device, [6Nkf + 3Npt + 6Nls]) = (H + lambda_eff diag H)^-1 g ; pt_off / ls_off: CSR offsets of the landmark-sorted
-// observation lists; lambda_eff (device scalar) = lambda * (int)max|H_ii| if scale_by_hmax else lambda
-int launch_lba_solve(gfpl_ctx* ctx, const gfpl_lba_problem& pb, const gfpl_lba_blocks& H, const int32_t* pt_off,
-                     const int32_t* ls_off, double lambda, int scale_by_hmax, LbaSolveWork w, double* DX,
-                     double* lambda_eff);
+struct LbaWin {
+  gfpl_lba_problem pb;
+  gfpl_lba_blocks H;
+  const int32_t *pt_off, *ls_off;   // CSR offsets of the landmark-sorted observation lists
+  LbaSolveWork w;
+  double* DX;                       // [6Nkf + 3Npt + 6Nls]
+  double* lambda_eff;               // [1] lambda * (int)max|H_ii| if scale_by_hmax else lambda
+};
+// residual / Jacobian / block-H assembly of every window (block storage zeroed by the caller)
+int launch_lba_assemble(gfpl_ctx* ctx, const LbaWin* wins, int W, int max_kf, int max_pt_obs, int max_ls_obs);
+// DX = (H + lambda_eff diag H)^-1 g per window: landmark elimination (Schur complement), dense LDL^T, back substitution
+int launch_lba_solve(gfpl_ctx* ctx, const LbaWin* wins, int W, int max_kf, int max_pt, int max_ls, double lambda, int scale_by_hmax);
 
 int launch_measure_peaks(gfpl_ctx* ctx, double* popc_tops, double* fp64_tflops);
 int launch_measure_alu_peak(gfpl_ctx* ctx, double* lop3_tops);

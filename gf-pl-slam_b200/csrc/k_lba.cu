@@ -37,11 +37,15 @@ __device__ __forceinline__ void jt_times_R(const double* j3, const double* Tiw, 
   }
 }
 
+// grid = (observation tiles of the largest window, windows): blockIdx.y selects the window (independent local-BA problems
+// of a batched replay: one per key-frame insertion)
 template <bool LINES>
-__global__ void __launch_bounds__(LBA_THREADS) lba_assemble_kernel(gfpl_lba_problem pb, gfpl_lba_blocks out,
-                                                                   gfpl_camera cam, gfpl_config cfg) {
+__global__ void __launch_bounds__(LBA_THREADS) lba_assemble_kernel(const LbaWin* __restrict__ wins, gfpl_camera cam, gfpl_config cfg) {
   extern __shared__ double s_kf[];  // [Nkf][42]: 36 H + 6 g, when Nkf <= LBA_MAX_KF_SMEM
   __shared__ double s_err[LBA_THREADS / 32];
+  const gfpl_lba_problem pb = wins[blockIdx.y].pb;
+  const gfpl_lba_blocks out = wins[blockIdx.y].H;
+  if ((size_t)blockIdx.x * LBA_THREADS >= (size_t)(LINES ? pb.n_ls_obs : pb.n_pt_obs)) return;   // a smaller window of the batch
   const bool use_smem = pb.Nkf <= LBA_MAX_KF_SMEM;
   if (use_smem) {
     for (int i = threadIdx.x; i < pb.Nkf * 42; i += LBA_THREADS) s_kf[i] = 0.0;
@@ -151,24 +155,15 @@ __global__ void __launch_bounds__(LBA_THREADS) lba_assemble_kernel(gfpl_lba_prob
   }
 }
 
-int launch_lba_assemble(gfpl_ctx* ctx, const gfpl_lba_problem& pb, gfpl_lba_blocks out) {
-  const size_t N = 6 * (size_t)pb.Nkf + 3 * (size_t)pb.Npt + 6 * (size_t)pb.Nls;
-  GFPL_CUDA_OK(ctx, cudaMemsetAsync(out.Hkk, 0, (size_t)pb.Nkf * 36 * 8, ctx->stream));
-  GFPL_CUDA_OK(ctx, cudaMemsetAsync(out.Hpp, 0, (size_t)pb.Npt * 9 * 8, ctx->stream));
-  GFPL_CUDA_OK(ctx, cudaMemsetAsync(out.Hll, 0, (size_t)pb.Nls * 36 * 8, ctx->stream));
-  GFPL_CUDA_OK(ctx, cudaMemsetAsync(out.Hpk, 0, (size_t)pb.n_pt_obs * 18 * 8, ctx->stream));
-  GFPL_CUDA_OK(ctx, cudaMemsetAsync(out.Hlk, 0, (size_t)pb.n_ls_obs * 36 * 8, ctx->stream));
-  GFPL_CUDA_OK(ctx, cudaMemsetAsync(out.g, 0, N * 8, ctx->stream));
-  GFPL_CUDA_OK(ctx, cudaMemsetAsync(out.err, 0, 8, ctx->stream));
-  const size_t smem = pb.Nkf <= LBA_MAX_KF_SMEM ? (size_t)(pb.Nkf > 0 ? pb.Nkf : 1) * 42 * 8 : 8;
-  if (pb.n_pt_obs > 0) {
-    lba_assemble_kernel<false><<<(pb.n_pt_obs + LBA_THREADS - 1) / LBA_THREADS, LBA_THREADS, smem, ctx->stream>>>(
-        pb, out, ctx->cam, ctx->cfg);
+// block storage of every window must be zero on entry (the callers clear the one device buffer that holds them all)
+int launch_lba_assemble(gfpl_ctx* ctx, const LbaWin* wins, int W, int max_kf, int max_pt_obs, int max_ls_obs) {
+  const size_t smem = max_kf <= LBA_MAX_KF_SMEM ? (size_t)(max_kf > 0 ? max_kf : 1) * 42 * 8 : 8;
+  if (max_pt_obs > 0) {
+    lba_assemble_kernel<false><<<dim3((max_pt_obs + LBA_THREADS - 1) / LBA_THREADS, W), LBA_THREADS, smem, ctx->stream>>>(wins, ctx->cam, ctx->cfg);
     GFPL_LAUNCH_OK(ctx);
   }
-  if (pb.n_ls_obs > 0) {
-    lba_assemble_kernel<true><<<(pb.n_ls_obs + LBA_THREADS - 1) / LBA_THREADS, LBA_THREADS, smem, ctx->stream>>>(
-        pb, out, ctx->cam, ctx->cfg);
+  if (max_ls_obs > 0) {
+    lba_assemble_kernel<true><<<dim3((max_ls_obs + LBA_THREADS - 1) / LBA_THREADS, W), LBA_THREADS, smem, ctx->stream>>>(wins, ctx->cam, ctx->cfg);
     GFPL_LAUNCH_OK(ctx);
   }
   return GFPL_OK;

@@ -16,8 +16,11 @@ namespace gfpl {
 
 // lambda_eff = lambda * (int) max |H_ii|  (quirk iii: `int Hmax`, mapHandler.cpp:1429-1435), or lambda itself
 __global__ void __launch_bounds__(256)
-lba_lambda_kernel(gfpl_lba_problem pb, gfpl_lba_blocks H, double lambda, int scale_by_hmax, double* lambda_eff) {
+lba_lambda_kernel(const LbaWin* __restrict__ wins, double lambda, int scale_by_hmax) {
   __shared__ double s_max[8];
+  const gfpl_lba_problem pb = wins[blockIdx.x].pb;
+  const gfpl_lba_blocks H = wins[blockIdx.x].H;
+  double* lambda_eff = wins[blockIdx.x].lambda_eff;
   double m = 0.0;
   if (scale_by_hmax) {
     const int nk = pb.Nkf * 6, np = pb.Npt * 3, nl = pb.Nls * 6;
@@ -43,8 +46,12 @@ lba_lambda_kernel(gfpl_lba_problem pb, gfpl_lba_blocks H, double lambda, int sca
 }
 
 // S = damped block diagonal of Hkk, rhs = g[0 : 6 Nkf]
-__global__ void lba_schur_init_kernel(gfpl_lba_problem pb, gfpl_lba_blocks H, const double* __restrict__ lambda_eff,
-                                      double* __restrict__ S, double* __restrict__ rhs) {
+__global__ void lba_schur_init_kernel(const LbaWin* __restrict__ wins) {
+  const gfpl_lba_problem pb = wins[blockIdx.y].pb;
+  const gfpl_lba_blocks H = wins[blockIdx.y].H;
+  const double* lambda_eff = wins[blockIdx.y].lambda_eff;
+  double* S = wins[blockIdx.y].w.S;
+  double* rhs = wins[blockIdx.y].DX;
   const int nk = pb.Nkf * 6;
   const double lam = *lambda_eff;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < (size_t)nk * nk; e += (size_t)gridDim.x * blockDim.x) {
@@ -115,10 +122,20 @@ __device__ __forceinline__ void damped_inverse(const double* __restrict__ D, dou
 // rhs -= W_a^T z, S -= W_a^T Y_b.  obs_off: CSR offsets of the (landmark-sorted) observation list.
 template <int DIM>
 __global__ void __launch_bounds__(128)
-lba_eliminate_kernel(int n_lm, const int32_t* __restrict__ obs_off, const int32_t* __restrict__ obs_kf,
-                     const double* __restrict__ Dall, const double* __restrict__ Wall, const double* __restrict__ gj_all,
-                     const double* __restrict__ lambda_eff, int nk, double* __restrict__ S, double* __restrict__ rhs,
-                     double* __restrict__ Y /*[n_obs][DIM*6]*/, double* __restrict__ Z /*[n_lm][DIM]*/) {
+lba_eliminate_kernel(const LbaWin* __restrict__ wins) {
+  const LbaWin& wn = wins[blockIdx.y];
+  const int n_lm = DIM == 3 ? wn.pb.Npt : wn.pb.Nls;
+  const int32_t* __restrict__ obs_off = DIM == 3 ? wn.pt_off : wn.ls_off;
+  const int32_t* __restrict__ obs_kf = DIM == 3 ? wn.pb.pt_obs_kf : wn.pb.ls_obs_kf;
+  const double* __restrict__ Dall = DIM == 3 ? wn.H.Hpp : wn.H.Hll;
+  const double* __restrict__ Wall = DIM == 3 ? wn.H.Hpk : wn.H.Hlk;
+  const int nk = 6 * wn.pb.Nkf;
+  const double* __restrict__ gj_all = wn.H.g + nk + (DIM == 3 ? 0 : 3 * (size_t)wn.pb.Npt);
+  const double* __restrict__ lambda_eff = wn.lambda_eff;
+  double* __restrict__ S = wn.w.S;
+  double* __restrict__ rhs = wn.DX;
+  double* __restrict__ Y = DIM == 3 ? wn.w.Ypt : wn.w.Yls;   // [n_obs][DIM*6]
+  double* __restrict__ Z = DIM == 3 ? wn.w.Zpt : wn.w.Zls;   // [n_lm][DIM]
   const int j = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (j >= n_lm) return;
   double inv[DIM * DIM], z[DIM];
@@ -204,9 +221,13 @@ __device__ __forceinline__ void ldlt_solve_cta(int n, double* __restrict__ S, do
 
 constexpr int LBA_SOLVE_SMEM_N = 96;
 
-__global__ void __launch_bounds__(256) lba_dense_solve_kernel(int n, double* __restrict__ S, double* __restrict__ x) {
+__global__ void __launch_bounds__(256) lba_dense_solve_kernel(const LbaWin* __restrict__ wins, int smem_ok) {
   extern __shared__ double s_mat[];  // [n*n + n] when n <= LBA_SOLVE_SMEM_N
-  if (n <= LBA_SOLVE_SMEM_N) {
+  const int n = 6 * wins[blockIdx.x].pb.Nkf;
+  double* __restrict__ S = wins[blockIdx.x].w.S;
+  double* __restrict__ x = wins[blockIdx.x].DX;
+  if (n == 0) return;
+  if (smem_ok) {   // the launch sized shared memory for the largest window: (n * n + n) doubles
     double* sx = s_mat + (size_t)n * n;
     for (int e = threadIdx.x; e < n * n; e += 256) s_mat[e] = S[e];
     for (int e = threadIdx.x; e < n; e += 256) sx[e] = x[e];
@@ -221,9 +242,15 @@ __global__ void __launch_bounds__(256) lba_dense_solve_kernel(int n, double* __r
 
 // dx_j = z_j - sum_a Y_a dx_k(a)
 template <int DIM>
-__global__ void lba_backsub_kernel(int n_lm, const int32_t* __restrict__ obs_off, const int32_t* __restrict__ obs_kf,
-                                   const double* __restrict__ Y, const double* __restrict__ Z,
-                                   const double* __restrict__ dxk, double* __restrict__ dx /*[n_lm][DIM]*/) {
+__global__ void lba_backsub_kernel(const LbaWin* __restrict__ wins) {
+  const LbaWin& wn = wins[blockIdx.y];
+  const int n_lm = DIM == 3 ? wn.pb.Npt : wn.pb.Nls;
+  const int32_t* __restrict__ obs_off = DIM == 3 ? wn.pt_off : wn.ls_off;
+  const int32_t* __restrict__ obs_kf = DIM == 3 ? wn.pb.pt_obs_kf : wn.pb.ls_obs_kf;
+  const double* __restrict__ Y = DIM == 3 ? wn.w.Ypt : wn.w.Yls;
+  const double* __restrict__ Z = DIM == 3 ? wn.w.Zpt : wn.w.Zls;
+  const double* __restrict__ dxk = wn.DX;
+  double* __restrict__ dx = wn.DX + 6 * wn.pb.Nkf + (DIM == 3 ? 0 : 3 * (size_t)wn.pb.Npt);   // [n_lm][DIM]
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_lm * DIM) return;
   const int j = e / DIM, i = e % DIM;
@@ -237,43 +264,37 @@ __global__ void lba_backsub_kernel(int n_lm, const int32_t* __restrict__ obs_off
   dx[e] = v;
 }
 
-int launch_lba_solve(gfpl_ctx* ctx, const gfpl_lba_problem& pb, const gfpl_lba_blocks& H, const int32_t* pt_off,
-                     const int32_t* ls_off, double lambda, int scale_by_hmax, LbaSolveWork w, double* DX,
-                     double* lambda_eff) {
-  const int nk = 6 * pb.Nkf;
-  lba_lambda_kernel<<<1, 256, 0, ctx->stream>>>(pb, H, lambda, scale_by_hmax, lambda_eff);
+// every window of the batch: lambda, Schur complement, dense solve, back substitution.  max_*: the largest window's sizes
+int launch_lba_solve(gfpl_ctx* ctx, const LbaWin* wins, int W, int max_kf, int max_pt, int max_ls, double lambda, int scale_by_hmax) {
+  const int nk = 6 * max_kf;
+  lba_lambda_kernel<<<W, 256, 0, ctx->stream>>>(wins, lambda, scale_by_hmax);
   GFPL_LAUNCH_OK(ctx);
   if (nk > 0) {
     const int blocks = (int)(((size_t)nk * nk + 255) / 256);
-    lba_schur_init_kernel<<<blocks < 1024 ? blocks : 1024, 256, 0, ctx->stream>>>(pb, H, lambda_eff, w.S, DX);
+    lba_schur_init_kernel<<<dim3(blocks < 1024 ? blocks : 1024, W), 256, 0, ctx->stream>>>(wins);
     GFPL_LAUNCH_OK(ctx);
   }
-  if (pb.Npt > 0) {
-    lba_eliminate_kernel<3><<<(pb.Npt + 3) / 4, 128, 0, ctx->stream>>>(pb.Npt, pt_off, pb.pt_obs_kf, H.Hpp, H.Hpk, H.g + nk,
-                                                                       lambda_eff, nk, w.S, DX, w.Ypt, w.Zpt);
+  if (max_pt > 0) {
+    lba_eliminate_kernel<3><<<dim3((max_pt + 3) / 4, W), 128, 0, ctx->stream>>>(wins);
     GFPL_LAUNCH_OK(ctx);
   }
-  if (pb.Nls > 0) {
-    lba_eliminate_kernel<6><<<(pb.Nls + 3) / 4, 128, 0, ctx->stream>>>(pb.Nls, ls_off, pb.ls_obs_kf, H.Hll, H.Hlk,
-                                                                       H.g + nk + 3 * (size_t)pb.Npt, lambda_eff, nk, w.S, DX,
-                                                                       w.Yls, w.Zls);
+  if (max_ls > 0) {
+    lba_eliminate_kernel<6><<<dim3((max_ls + 3) / 4, W), 128, 0, ctx->stream>>>(wins);
     GFPL_LAUNCH_OK(ctx);
   }
   if (nk > 0) {
     const size_t smem = nk <= LBA_SOLVE_SMEM_N ? ((size_t)nk * nk + nk) * sizeof(double) : 0;
     if (smem > 48 * 1024)
       GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(lba_dense_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lba_dense_solve_kernel<<<1, 256, smem, ctx->stream>>>(nk, w.S, DX);
+    lba_dense_solve_kernel<<<W, 256, smem, ctx->stream>>>(wins, nk <= LBA_SOLVE_SMEM_N ? 1 : 0);
     GFPL_LAUNCH_OK(ctx);
   }
-  if (pb.Npt > 0) {
-    lba_backsub_kernel<3><<<(pb.Npt * 3 + 127) / 128, 128, 0, ctx->stream>>>(pb.Npt, pt_off, pb.pt_obs_kf, w.Ypt, w.Zpt, DX,
-                                                                             DX + nk);
+  if (max_pt > 0) {
+    lba_backsub_kernel<3><<<dim3((max_pt * 3 + 127) / 128, W), 128, 0, ctx->stream>>>(wins);
     GFPL_LAUNCH_OK(ctx);
   }
-  if (pb.Nls > 0) {
-    lba_backsub_kernel<6><<<(pb.Nls * 6 + 127) / 128, 128, 0, ctx->stream>>>(pb.Nls, ls_off, pb.ls_obs_kf, w.Yls, w.Zls, DX,
-                                                                             DX + nk + 3 * (size_t)pb.Npt);
+  if (max_ls > 0) {
+    lba_backsub_kernel<6><<<dim3((max_ls * 6 + 127) / 128, W), 128, 0, ctx->stream>>>(wins);
     GFPL_LAUNCH_OK(ctx);
   }
   return GFPL_OK;

@@ -297,6 +297,28 @@ class Context:
         return DX, float(err[0]), float(lam_eff[0])
 
 
+    def lba_batch_prepare(self, windows):
+        """host-side views of W windows (the caller's own arrays, no copies): reusable across lba_step_batch_prepared calls"""
+        W = len(windows)
+        built = [S.lba_problem_from_arrays(w) for w in windows]
+        probs = (S.LbaProblem * W)(*[b[0] for b in built])
+        sizes = [6 * p.Nkf + 3 * p.Npt + 6 * p.Nls for p, _ in built]
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        return {"W": W, "probs": probs, "keep": built, "off": off, "DX": np.zeros(int(off[-1])), "err": np.zeros(W), "lam": np.zeros(W)}
+
+    def lba_step_batch_prepared(self, h, lam, scale_by_hmax):
+        self._check(lib().gfpl_lba_step_batch(self._h, h["W"], h["probs"], C.c_double(lam), int(scale_by_hmax), _vp(h["DX"]),
+                                              _vp(h["err"]), _vp(h["lam"])))
+        return h["DX"], h["err"], h["lam"]
+
+    def lba_step_batch(self, windows, lam, scale_by_hmax):
+        """one LM pass (assembly + damped Schur solve) of W independent windows in one call:
+        ([DX_w], err_sum [W], lambda_eff [W])"""
+        h = self.lba_batch_prepare(windows)
+        DX, err, lam_eff = self.lba_step_batch_prepared(h, lam, scale_by_hmax)
+        return [DX[h["off"][w]:h["off"][w + 1]] for w in range(h["W"])], err, lam_eff
+
+
 class Replay:
     """gfpl_replay: device-resident batch of B frame pairs (upload once / run many / download)."""
 

@@ -646,6 +646,16 @@ int gfpl_lba_assemble(gfpl_ctx* ctx, const gfpl_lba_problem* prob, gfpl_lba_bloc
 int gfpl_lba_step(gfpl_ctx* ctx, const gfpl_lba_problem* prob, double lambda, int32_t scale_by_hmax, double* DX,
                   double* err_sum, double* lambda_eff);
 
+/* The same pass for W independent windows in one call (a batched replay runs one local BA per inserted key frame:
+ * mapHandler.cpp:1108-1838 is entered once per window, and the windows of different sequences share nothing).  Every
+ * window's arrays travel in one H2D copy, each kernel is launched once for the whole batch (grid.y = window), and the
+ * results come back in three D2H copies.  probs: [W] (host structs, host pointers; windows may differ in every size);
+ * DX: the windows' updates concatenated — window w starts at sum over v < w of (6 Nkf_v + 3 Npt_v + 6 Nls_v);
+ * err_sum, lambda_eff: [W].  The kernels' device time of the last call lies between timer slots 6 and 7
+ * (gfpl_timer_elapsed_ms(ctx, 6, 7, &ms)). */
+int gfpl_lba_step_batch(gfpl_ctx* ctx, int32_t W, const gfpl_lba_problem* probs, double lambda, int32_t scale_by_hmax,
+                        double* DX, double* err_sum /*[W]*/, double* lambda_eff /*[W]*/);
+
 /* ------------------------------------------------------------------------- */
 /* Device micro-benchmarks used as roofline denominators          */
 /* ------------------------------------------------------------------------- */

@@ -884,6 +884,47 @@ def test_lba_step_schur_solve(ctx, orc):
         ctx.set_camera(api.euroc_camera())
 
 
+def test_lba_step_batch_over_windows(ctx, orc):
+    """gfpl_lba_step_batch: ragged windows (different key-frame, landmark and observation counts, a points-only, a
+    lines-only and an EMPTY window) in one call == the windows solved one at a time (1e-9 vs the dense CPU solve, and the
+    same figures as the single-window entry point up to the order of the fp64 atomics)"""
+    from gfpl import api
+    specs = [dict(seed=11, n_kf=6, n_pt=120, n_ls=30), dict(seed=12, n_kf=3, n_pt=20, n_ls=5, n_fix=1),
+             dict(seed=13, n_kf=8, n_pt=150, n_ls=40), dict(seed=14, n_kf=4, n_pt=60, n_ls=0),
+             dict(seed=15, n_kf=4, n_pt=0, n_ls=25), dict(seed=16, n_kf=10, n_pt=300, n_ls=80)]
+    wins = [synth.make_lba_window(**kw) for kw in specs]
+    empty = {k: v[:0].copy() if isinstance(v, np.ndarray) else v for k, v in wins[1].items()}
+    wins.insert(2, empty)
+    try:
+        ctx.set_camera(wins[0]["cam"])
+        for lam, scale in ((0.001, 1), (0.5, 0)):
+            DXs, err, lam_eff = ctx.lba_step_batch(wins, lam, scale)
+            assert len(DXs) == len(wins)
+            for k, w in enumerate(wins):
+                if len(w["kf_Tkw"]) == 0:
+                    assert len(DXs[k]) == 0 and err[k] == 0.0 and lam_eff[k] == lam
+                    continue
+                DXo, eo, lo = orc.lba_step(w["cam"], ctx.cfg, w, lam, scale)
+                assert lam_eff[k] == lo and abs(err[k] - eo) <= 1e-9 * abs(eo), k
+                assert np.linalg.norm(DXs[k] - DXo) <= 1e-9 * np.linalg.norm(DXo), (k, np.linalg.norm(DXs[k] - DXo) / np.linalg.norm(DXo))
+                DX1, e1, l1 = ctx.lba_step(w, lam, scale)
+                assert l1 == lam_eff[k] and np.linalg.norm(DXs[k] - DX1) <= 1e-9 * np.linalg.norm(DX1)
+        # 64 full-size C3 windows: residual of every damped system
+        big = [synth.make_lba_window(seed=100 + i, n_kf=10, n_pt=1000, n_ls=300) for i in range(4)] * 16
+        DXs, err, lam_eff = ctx.lba_step_batch(big, 0.001, 1)
+        for k in (0, 1, 2, 3, 17, 63):
+            blk = ctx.lba_assemble(big[k])
+            assert lam_eff[k] > 0 and _lba_residual(big[k], blk, DXs[k], lam_eff[k]) < 1e-9
+        assert np.array_equal(lam_eff[:4], lam_eff[4:8])
+        assert ctx.timer_elapsed_ms(6, 7) > 0
+        bad = list(wins)
+        bad[3] = dict(wins[3]); bad[3]["pt_obs_lm"] = wins[3]["pt_obs_lm"][::-1].copy()
+        with pytest.raises(api.GfplError):
+            ctx.lba_step_batch(bad, 0.001, 1)
+    finally:
+        ctx.set_camera(api.euroc_camera())
+
+
 @pytest.mark.parametrize("norm", [S.NORM_HAMMING, S.NORM_HAMMING2])
 @pytest.mark.parametrize("tie", [False, True])
 def test_knn2_mutual_both_directions(ctx, orc, norm, tie):
