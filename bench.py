@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--no-linecut", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="pairs per step of the CPU reference arm")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--seq-len", type=int, default=7, help="frames per sequence of the sequence-chained e2e replay (>= 2)")
     ap.add_argument("--lba-windows", type=int, default=512, help="windows per call of the local-BA (configs[2]) side measurement")
     ap.add_argument("--c4-pairs", type=int, default=2048, help="frame pairs of the dense-feature (configs[3]) side measurement; 0 = skip")
     ap.add_argument("--pipeline", type=int, default=int(os.environ.get("GFPL_PIPELINE", "1")),
@@ -361,7 +362,10 @@ def main():
     flags = (0 if a.no_linecut else S.TRACK_LINECUT) | S.TRACK_SEED_GIVEN
 
     # ---- synthetic inputs in pinned host memory (detector output of B frame pairs) -----------------------
-    d = synth.make_pairs(B, n_pt=a.n_pt, n_ln=a.n_ln, seed=1000 + rank, pinned=True)
+    # B sequences of --seq-len frames: frames 0 / 1 are the (previous, current) frames of the independent-pair measurements,
+    # the whole sequences feed the sequence-chained e2e replay
+    seq = synth.make_sequences(B, a.seq_len - 1, n_pt=a.n_pt, n_ln=a.n_ln, seed=1000 + rank)
+    d = {"cam": seq["cam"], "prev_raw": seq["frames"][0], "curr_raw": seq["frames"][1], "state": seq["state"]}
     ctx = api.Context(local, cam=d["cam"])
     prev = S.StereoFramesNP(B, a.n_pt, a.n_ln, pinned=True)
     CH = 1024
@@ -373,9 +377,13 @@ def main():
     popc_peak, fp64_peak = ctx.measure_peaks()
     alu_peak = ctx.measure_alu_peak()
     int8_peak_measured = ctx.measure_int8_peak()
+    # sequence-chained e2e: first step of a sequence = full compact step input (frame 0's stereo survivors + frame 1),
+    # every later step = the next current frames only (gfpl_replay_upload_curr_compact)
+    seq_first = S.CompactInputNP(seq["frames"][1], prev, pinned=True)
+    seq_next = {k: S.CompactInputNP(seq["frames"][k], None, pinned=True) for k in range(2, a.seq_len)}
     # a previous frame holds only its stereo survivors: pack its rows with the tightest common stride
     prev = prev.repack(pinned=True)
-    compact = S.CompactInputNP(d["curr_raw"], prev, pinned=True)   # e2e uploads the compact step input (gfpl_compact_input)
+    compact = S.CompactInputNP(d["curr_raw"], prev, pinned=True)   # independent pairs: the compact step input (gfpl_compact_input)
 
     rp = api.Replay(ctx, B, a.n_pt, a.n_ln, prev.cap_pt, prev.cap_ln)
     rp.upload(prev, d["state"], d["curr_raw"])
@@ -439,23 +447,33 @@ def main():
     # kernels of the steps before it.  Every step's copies are inside the timed region; the host consumes the
     # pose records of step k-LAG while step k is in flight. -----------------------------------------------------
     NSLOT, LAG = 5, 3
-    slots = [(ctx, rp)]
-    for _ in range(NSLOT - 1):
-        c = api.Context(local, cam=d["cam"])
-        slots.append((c, api.Replay(c, B, a.n_pt, a.n_ln, prev.cap_pt, prev.cap_ln)))
+    ctxs = [ctx] + [api.Context(local, cam=d["cam"]) for _ in range(NSLOT - 1)]
     pose_hosts = [pose_host] + [S._alloc(B, S.pose_result_dt, True) for _ in range(NSLOT - 1)]
-    pose_devs = [torch.as_tensor(DevArray(r.pose_device_ptr(), pose_bytes), device="cuda") if world > 1 else None
-                 for _, r in slots]
-    slot_streams = [torch.cuda.ExternalStream(c.stream(), device=torch.device("cuda", local)) for c, _ in slots]
+    slot_streams = [torch.cuda.ExternalStream(c.stream(), device=torch.device("cuda", local)) for c in ctxs]
     h2d = d2h = 0
+    chained = False
+    L = a.seq_len - 1                       # steps per sequence
+    slot_phase = [0] * NSLOT
+
+    def make_slots(pcp, pcl):
+        slot_phase[:] = [0] * NSLOT
+        sl = [(c, api.Replay(c, B, a.n_pt, a.n_ln, pcp, pcl)) for c in ctxs]
+        pd = [torch.as_tensor(DevArray(r.pose_device_ptr(), pose_bytes), device="cuda") if world > 1 else None for _, r in sl]
+        return sl, pd
 
     def e2e_enqueue(k):
         nonlocal h2d, d2h
         c, r = slots[k % NSLOT]
-        r.upload_compact(compact, d["state"])
+        phase = slot_phase[k % NSLOT]       # step of this slot's sequences (the slots are staggered: steady-state byte mix)
+        slot_phase[k % NSLOT] = (phase + 1) % L
+        if not chained or phase == 0:
+            r.upload_compact(seq_first if chained else compact, d["state"])
+        else:                               # StereoFrameHandler::updateFrame on the device, then only the new current frames
+            r.advance(seq["stamps"][phase + 1])
+            r.upload_curr_compact(seq_next[phase + 1])
         r.run(flags)
         r.download(pose_hosts[k % NSLOT])
-        h2d, d2h = r.h2d_bytes(), r.d2h_bytes()
+        h2d += r.h2d_bytes(); d2h += r.d2h_bytes()
 
     def e2e_consume(k):
         if world > 1:                     # gather behind step k on its slot's stream: the slot's next upload / run are
@@ -472,20 +490,42 @@ def main():
             e2e_consume(k)
         torch.cuda.synchronize()
 
-    e2e_run(max(NSLOT, a.warmup))
-    barrier()
-    t0 = time.perf_counter()
-    e2e_run(a.steps)
-    e2e_s = time.perf_counter() - t0
-    barrier()
-    for ph in pose_hosts:
-        assert (ph["status"] == 0).mean() > 0.99, "tracking failed on the synthetic batch"
+    def e2e_measure():
+        nonlocal h2d, d2h
+        # warm-up: every slot starts its sequences (phase 0), then the slots are brought to different phases
+        e2e_run(max(NSLOT, a.warmup))
+        if chained:
+            for s_ in range(NSLOT):
+                for _ in range(s_ % L):
+                    e2e_enqueue(s_)
+            for s_ in range(NSLOT):
+                e2e_consume(s_)
+        barrier()
+        h2d = d2h = 0
+        t0 = time.perf_counter()
+        e2e_run(a.steps)
+        dt = time.perf_counter() - t0
+        barrier()
+        for ph in pose_hosts:
+            assert (ph["status"] == 0).mean() > 0.98, "tracking failed on the synthetic batch"
+        return dt, h2d / a.steps, d2h / a.steps
+
+    rp.close()
+    # (1) independent pairs: every step uploads previous + current frames (previous frames packed to their survivors)
+    slots, pose_devs = make_slots(prev.cap_pt, prev.cap_ln)
+    ind_s, ind_h2d, ind_d2h = e2e_measure()
+    for _, r in slots:
+        r.close()
+    # (2) sequence-chained: the headline e2e (BASELINE configs[0]/[1] are sequences; a frame is uploaded once)
+    chained = True
+    slots, pose_devs = make_slots(a.n_pt, a.n_ln)
+    e2e_s, h2d_avg, d2h_avg = e2e_measure()
 
     # ---- max over ranks ----------------------------------------------------------------------------------------
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, e2e_s * 1e3, ind_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
+    ms, e2e_ms, ind_ms = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         if not a.skip_cpu_baseline:   # CPU arm: the oracle sources rebuilt with the reference's flags on this machine
@@ -567,10 +607,19 @@ def main():
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": ms / a.steps, "ms_per_step_unpipelined": serial_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u8 descriptors -> int8 tensor-core / int32 popcount matching (exact) + f64 optimisation", "data": "synthetic", "config": workload_config(a),
-               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
-                       "ms_per_step": e2e_ms / a.steps, "pipeline": "%d resident slots / streams: H2D of step k overlaps the kernels of earlier steps; results consumed %d steps later" % (NSLOT, LAG),
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_avg) * world, "d2h_bytes_per_step": int(d2h_avg) * world,
+                       "ms_per_step": e2e_ms / a.steps,
+                       "mode": "sequence-chained streaming replay (StereoFrameHandler::updateFrame on the device): every slot tracks %d sequences of %d frames; "
+                               "the first step of a sequence uploads the previous frame's stereo survivors + the current frames (gfpl_replay_upload_compact), "
+                               "each later step only the new current frames (gfpl_replay_advance + gfpl_replay_upload_curr_compact); bytes are the average over the timed steps" % (B, a.seq_len),
+                       "pipeline": "%d resident slots / streams: H2D of step k overlaps the kernels of earlier steps; results consumed %d steps later" % (NSLOT, LAG),
                        "timing": "host wall clock around K x (upload+run+download) + final sync, max over ranks",
+                       "h2d_GBps_per_rank": h2d_avg / (e2e_ms / a.steps * 1e-3) / 1e9,
                        "host_affinity_cpus": numa_cpus},
+               "e2e_independent_pairs": {"value": world * B * a.steps / (ind_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(ind_h2d) * world,
+                                         "d2h_bytes_per_step": int(ind_d2h) * world, "ms_per_step": ind_ms / a.steps,
+                                         "h2d_GBps_per_rank": ind_h2d / (ind_ms / a.steps * 1e-3) / 1e9,
+                                         "mode": "every step uploads the previous frames' stereo survivors and the current frames (round 1's e2e)"},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_by_kernel": by_kernel,
                "kernel_ms_per_step": dict(zip(["knn_stereo_pt", "knn_stereo_ln", "stereo_accept", "f2f_pt_search", "knn_f2f_ln",
                                                "f2f_accept", "uncertainty+linecut", "pose_gn", "step"], [float(x) for x in stage])),
@@ -586,7 +635,7 @@ def main():
             out["lba_c3"] = {"unavailable": repr(e)}
         if a.c4_pairs > 0:
             try:
-                for _, r in slots[1:]:
+                for _, r in slots:
                     r.close()                                     # the e2e slots' device buffers are no longer needed
                 out["c4_dense"] = dense_c4(a, ctx, api, synth, S, int8_peak, a.skip_cpu_baseline)
             except Exception as e:  # a side measurement must not break the contract line

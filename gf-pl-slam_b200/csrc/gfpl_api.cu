@@ -562,6 +562,7 @@ struct gfpl_replay {
   int64_t h2d = 0, d2h = 0;
   bool timed = false;
   void* pose_raw = nullptr;   // optimiser -> finalize hand-off, [B]
+  double* stamps = nullptr;   // time stamps of the next current frames (gfpl_replay_advance)
   // software pipeline over sub-batches (gfpl_replay_set_pipeline)
   int n_sub = 1;
   cudaStream_t s_match = nullptr;
@@ -1073,45 +1074,106 @@ int gfpl_replay_upload_slim(gfpl_replay* rp, const gfpl_prev_frames* prev, const
   return launch_expand_prev(ctx, rp->slim, rp->prev);
 }
 
+// device staging of the compact records (descriptors and counts go straight to their final buffers).  Pointers are
+// published only when every allocation of a group succeeded, so a failed call can be retried.
+static int ensure_compact_staging(gfpl_replay* rp, bool with_prev) {
+  gfpl_ctx* ctx = rp->ctx;
+  const size_t B = rp->B, np = B * rp->cap_pt, nl = B * rp->cap_ln, pp = B * rp->prev.cap_pt, pl = B * rp->prev.cap_ln;
+  gfpl_compact_input& d = rp->compact;
+  if (!d.pt_l) {
+    gfpl_compact_input t{};
+    t.pt_l = rp->alloc<gfpl_keypoint8>(np); t.pt_r = rp->alloc<gfpl_keypoint8>(np);
+    t.pt_oct_l = rp->alloc<uint8_t>(np); t.pt_oct_r = rp->alloc<uint8_t>(np);
+    t.ln_l = rp->alloc<gfpl_keyline20>(nl); t.ln_r = rp->alloc<gfpl_keyline20>(nl);
+    t.ln_oct_l = rp->alloc<uint8_t>(nl); t.ln_oct_r = rp->alloc<uint8_t>(nl);
+    REQUIRE_MEM(ctx, t.pt_l && t.pt_r && t.pt_oct_l && t.pt_oct_r && t.ln_l && t.ln_r && t.ln_oct_l && t.ln_oct_r);
+    d.pt_l = t.pt_l; d.pt_r = t.pt_r; d.pt_oct_l = t.pt_oct_l; d.pt_oct_r = t.pt_oct_r;
+    d.ln_l = t.ln_l; d.ln_r = t.ln_r; d.ln_oct_l = t.ln_oct_l; d.ln_oct_r = t.ln_oct_r;
+  }
+  if (with_prev && !d.prev_pt) {
+    const gfpl_prev_point12* a = rp->alloc<gfpl_prev_point12>(pp);
+    const uint8_t* b = rp->alloc<uint8_t>(pp);
+    const gfpl_prev_line32* c = rp->alloc<gfpl_prev_line32>(pl);
+    const uint8_t* e = rp->alloc<uint8_t>(pl);
+    REQUIRE_MEM(ctx, a && b && c && e);
+    d.prev_pt = a; d.prev_pt_level = b; d.prev_ln = c; d.prev_ln_level = e;
+  }
+  d.B = rp->B; d.cap_pt = rp->cap_pt; d.cap_ln = rp->cap_ln; d.prev_cap_pt = rp->prev.cap_pt; d.prev_cap_ln = rp->prev.cap_ln;
+  d.n_pt_l = rp->raw.n_pt_l; d.n_pt_r = rp->raw.n_pt_r; d.n_ln_l = rp->raw.n_ln_l; d.n_ln_r = rp->raw.n_ln_r;
+  d.prev_n_pt = rp->prev.n_pt; d.prev_n_ln = rp->prev.n_ln;
+  d.pdesc_l = d.pdesc_r = d.ldesc_l = d.ldesc_r = d.prev_pdesc = d.prev_ldesc = nullptr;  // not staged
+  return GFPL_OK;
+}
+
+// current-frame part of a compact step input -> the raw buffers (counts, compact key points / key lines, descriptors)
+static int upload_compact_curr(gfpl_replay* rp, const gfpl_compact_input* in) {
+  gfpl_ctx* ctx = rp->ctx;
+  const size_t B = rp->B, np = B * rp->cap_pt, nl = B * rp->cap_ln;
+  gfpl_compact_input& d = rp->compact;
+  REQUIRE(ctx, counts_ok(in->n_pt_l, B, rp->cap_pt) && counts_ok(in->n_pt_r, B, rp->cap_pt) && counts_ok(in->n_ln_l, B, rp->cap_ln) &&
+                   counts_ok(in->n_ln_r, B, rp->cap_ln));
+  H2D(rp->raw.n_pt_l, in->n_pt_l, B); H2D(rp->raw.n_pt_r, in->n_pt_r, B);
+  H2D(rp->raw.n_ln_l, in->n_ln_l, B); H2D(rp->raw.n_ln_r, in->n_ln_r, B);
+  H2D(const_cast<gfpl_keypoint8*>(d.pt_l), in->pt_l, np); H2D(const_cast<gfpl_keypoint8*>(d.pt_r), in->pt_r, np);
+  H2D(const_cast<uint8_t*>(d.pt_oct_l), in->pt_oct_l, np); H2D(const_cast<uint8_t*>(d.pt_oct_r), in->pt_oct_r, np);
+  H2D(const_cast<gfpl_keyline20*>(d.ln_l), in->ln_l, nl); H2D(const_cast<gfpl_keyline20*>(d.ln_r), in->ln_r, nl);
+  H2D(const_cast<uint8_t*>(d.ln_oct_l), in->ln_oct_l, nl); H2D(const_cast<uint8_t*>(d.ln_oct_r), in->ln_oct_r, nl);
+  H2D(rp->raw.pdesc_l, in->pdesc_l, np * 32); H2D(rp->raw.pdesc_r, in->pdesc_r, np * 32);
+  H2D(rp->raw.ldesc_l, in->ldesc_l, nl * 32); H2D(rp->raw.ldesc_r, in->ldesc_r, nl * 32);
+  return GFPL_OK;
+}
+
 int gfpl_replay_upload_compact(gfpl_replay* rp, const gfpl_compact_input* in, const gfpl_frame_state* state) {
   if (!rp) return GFPL_E_INVALID;
   gfpl_ctx* ctx = rp->ctx;
   REQUIRE(ctx, in && state && in->B == rp->B);
   REQUIRE(ctx, in->cap_pt == rp->cap_pt && in->cap_ln == rp->cap_ln);
   REQUIRE(ctx, in->prev_cap_pt == rp->prev.cap_pt && in->prev_cap_ln == rp->prev.cap_ln);
+  REQUIRE(ctx, counts_ok(in->prev_n_pt, rp->B, rp->prev.cap_pt) && counts_ok(in->prev_n_ln, rp->B, rp->prev.cap_ln));
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-  const size_t B = rp->B, np = B * rp->cap_pt, nl = B * rp->cap_ln, pp = B * rp->prev.cap_pt, pl = B * rp->prev.cap_ln;
+  const size_t B = rp->B, pp = B * rp->prev.cap_pt, pl = B * rp->prev.cap_ln;
+  CHECK(ensure_compact_staging(rp, true));
   gfpl_compact_input& d = rp->compact;
-  if (!d.pt_l) {  // staging of the compact records; descriptors and counts go straight to their final buffers
-    d = *in;
-    d.pt_l = rp->alloc<gfpl_keypoint8>(np); d.pt_r = rp->alloc<gfpl_keypoint8>(np);
-    d.pt_oct_l = rp->alloc<uint8_t>(np); d.pt_oct_r = rp->alloc<uint8_t>(np);
-    d.ln_l = rp->alloc<gfpl_keyline20>(nl); d.ln_r = rp->alloc<gfpl_keyline20>(nl);
-    d.ln_oct_l = rp->alloc<uint8_t>(nl); d.ln_oct_r = rp->alloc<uint8_t>(nl);
-    d.prev_pt = rp->alloc<gfpl_prev_point12>(pp); d.prev_pt_level = rp->alloc<uint8_t>(pp);
-    d.prev_ln = rp->alloc<gfpl_prev_line32>(pl); d.prev_ln_level = rp->alloc<uint8_t>(pl);
-    REQUIRE_MEM(ctx, d.pt_l && d.pt_r && d.pt_oct_l && d.pt_oct_r && d.ln_l && d.ln_r && d.ln_oct_l && d.ln_oct_r && d.prev_pt &&
-                         d.prev_pt_level && d.prev_ln && d.prev_ln_level);
-    d.n_pt_l = rp->raw.n_pt_l; d.n_pt_r = rp->raw.n_pt_r; d.n_ln_l = rp->raw.n_ln_l; d.n_ln_r = rp->raw.n_ln_r;
-    d.prev_n_pt = rp->prev.n_pt; d.prev_n_ln = rp->prev.n_ln;
-    d.pdesc_l = d.pdesc_r = d.ldesc_l = d.ldesc_r = d.prev_pdesc = d.prev_ldesc = nullptr;  // not staged
-  }
   rp->h2d = 0;
   rp->input_dirty = true;
-  H2D(rp->raw.n_pt_l, in->n_pt_l, B); H2D(rp->raw.n_pt_r, in->n_pt_r, B);
-  H2D(rp->raw.n_ln_l, in->n_ln_l, B); H2D(rp->raw.n_ln_r, in->n_ln_r, B);
+  CHECK(upload_compact_curr(rp, in));
   H2D(rp->prev.n_pt, in->prev_n_pt, B); H2D(rp->prev.n_ln, in->prev_n_ln, B);
-  H2D(const_cast<gfpl_keypoint8*>(d.pt_l), in->pt_l, np); H2D(const_cast<gfpl_keypoint8*>(d.pt_r), in->pt_r, np);
-  H2D(const_cast<uint8_t*>(d.pt_oct_l), in->pt_oct_l, np); H2D(const_cast<uint8_t*>(d.pt_oct_r), in->pt_oct_r, np);
-  H2D(const_cast<gfpl_keyline20*>(d.ln_l), in->ln_l, nl); H2D(const_cast<gfpl_keyline20*>(d.ln_r), in->ln_r, nl);
-  H2D(const_cast<uint8_t*>(d.ln_oct_l), in->ln_oct_l, nl); H2D(const_cast<uint8_t*>(d.ln_oct_r), in->ln_oct_r, nl);
   H2D(const_cast<gfpl_prev_point12*>(d.prev_pt), in->prev_pt, pp); H2D(const_cast<uint8_t*>(d.prev_pt_level), in->prev_pt_level, pp);
   H2D(const_cast<gfpl_prev_line32*>(d.prev_ln), in->prev_ln, pl); H2D(const_cast<uint8_t*>(d.prev_ln_level), in->prev_ln_level, pl);
-  H2D(rp->raw.pdesc_l, in->pdesc_l, np * 32); H2D(rp->raw.pdesc_r, in->pdesc_r, np * 32);
-  H2D(rp->raw.ldesc_l, in->ldesc_l, nl * 32); H2D(rp->raw.ldesc_r, in->ldesc_r, nl * 32);
   H2D(rp->prev.pdesc, in->prev_pdesc, pp * 32); H2D(rp->prev.ldesc, in->prev_ldesc, pl * 32);
   H2D(rp->state, state, B);
-  return launch_expand_compact(ctx, d, rp->raw, rp->prev);
+  return launch_expand_compact(ctx, d, rp->raw, rp->prev, /*with_prev=*/true);
+}
+
+// ---- sequence-chained replay: StereoFrameHandler::updateFrame (stereoFrameHandler.cpp:926-961) ----------------------------
+int gfpl_replay_upload_curr_compact(gfpl_replay* rp, const gfpl_compact_input* in) {
+  if (!rp) return GFPL_E_INVALID;
+  gfpl_ctx* ctx = rp->ctx;
+  REQUIRE(ctx, in && in->B == rp->B && in->cap_pt == rp->cap_pt && in->cap_ln == rp->cap_ln);
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  CHECK(ensure_compact_staging(rp, false));
+  rp->h2d = 0;
+  rp->input_dirty = true;
+  CHECK(upload_compact_curr(rp, in));
+  return launch_expand_compact(ctx, rp->compact, rp->raw, rp->prev, /*with_prev=*/false);
+}
+
+int gfpl_replay_advance(gfpl_replay* rp, const double* time_stamp_next) {
+  if (!rp) return GFPL_E_INVALID;
+  gfpl_ctx* ctx = rp->ctx;
+  // prev_frame = curr_frame: the two frame sets trade places, which needs equal strides
+  REQUIRE(ctx, rp->prev.cap_pt == rp->curr.cap_pt && rp->prev.cap_ln == rp->curr.cap_ln);
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  double* dts = nullptr;
+  if (time_stamp_next) {
+    if (!rp->stamps) rp->stamps = rp->alloc<double>(rp->B);
+    REQUIRE_MEM(ctx, rp->stamps);
+    dts = rp->stamps;
+    H2D(dts, time_stamp_next, (size_t)rp->B);
+  }
+  rp->input_dirty = true;
+  std::swap(rp->prev, rp->curr);
+  return launch_advance_state(ctx, rp->B, rp->pose, dts, rp->state);
 }
 
 int gfpl_replay_set_pipeline(gfpl_replay* rp, int32_t n_sub) {

@@ -104,7 +104,9 @@ int launch_stereo_orbslam_points(gfpl_ctx* ctx, const DevRawFrames& raw, const g
 int launch_stereo_uncertainty(gfpl_ctx* ctx, const DevStereoFrames& fr, gfpl_line_cov* out);
 int launch_expand_prev(gfpl_ctx* ctx, const gfpl_prev_frames& slim_dev, DevStereoFrames fr);
 // compact step input (device staging copies) -> raw key points / key lines and previous-frame feature records
-int launch_expand_compact(gfpl_ctx* ctx, const gfpl_compact_input& c, DevRawFrames raw, DevStereoFrames prev);
+int launch_expand_compact(gfpl_ctx* ctx, const gfpl_compact_input& c, DevRawFrames raw, DevStereoFrames prev, bool with_prev = true);
+// updateFrame: pose records -> previous-frame state (stamps: device [B] or NULL)
+int launch_advance_state(gfpl_ctx* ctx, int B, const gfpl_pose_result* pose, const double* stamps, gfpl_frame_state* state);
 
 // f2f: fused radius + projection-gate search (hybrid points), knn-candidate variant, and accept loops
 int launch_f2f_hybrid_points(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStereoFrames& curr,

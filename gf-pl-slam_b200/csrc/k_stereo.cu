@@ -404,13 +404,39 @@ __global__ void __launch_bounds__(128) expand_compact_kernel(gfpl_compact_input 
   }
 }
 
-int launch_expand_compact(gfpl_ctx* ctx, const gfpl_compact_input& c, DevRawFrames raw, DevStereoFrames prev) {
+// with_prev = false: only the current frame's key points / key lines (sequence-chained replay: the previous frame is the
+// last step's current frame, already on the device)
+int launch_expand_compact(gfpl_ctx* ctx, const gfpl_compact_input& c, DevRawFrames raw, DevStereoFrames prev, bool with_prev) {
   if (c.B <= 0) return GFPL_OK;
   int cap = c.cap_pt > c.cap_ln ? c.cap_pt : c.cap_ln;
-  cap = cap > c.prev_cap_pt ? cap : c.prev_cap_pt;
-  cap = cap > c.prev_cap_ln ? cap : c.prev_cap_ln;
-  dim3 grid((cap + 127) / 128, c.B, 4);
+  if (with_prev) {
+    cap = cap > c.prev_cap_pt ? cap : c.prev_cap_pt;
+    cap = cap > c.prev_cap_ln ? cap : c.prev_cap_ln;
+  }
+  dim3 grid((cap + 127) / 128, c.B, with_prev ? 4 : 2);
   expand_compact_kernel<<<grid, 128, 0, ctx->stream>>>(c, raw, prev, ctx->cam, ctx->cfg);
+  GFPL_LAUNCH_OK(ctx);
+  return GFPL_OK;
+}
+
+// StereoFrameHandler::updateFrame (stereoFrameHandler.cpp:908-912): the current frame's pose record becomes the previous
+// frame's state.  stamps: time stamps of the NEXT current frames, or NULL: the same step again.
+__global__ void advance_state_kernel(int B, const gfpl_pose_result* __restrict__ pose, const double* __restrict__ stamps,
+                                     gfpl_frame_state* __restrict__ state) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= B) return;
+  gfpl_frame_state& s = state[p];
+  const gfpl_pose_result& r = pose[p];
+  for (int i = 0; i < 16; i++) { s.Tfw[i] = r.Tfw[i]; s.DT[i] = r.DT[i]; }
+  for (int i = 0; i < 36; i++) { s.DT_cov[i] = r.DT_cov[i]; s.Tfw_cov[i] = r.Tfw_cov[i]; }
+  const double t0 = s.time_stamp, t1 = s.time_stamp_curr;
+  s.time_stamp = t1;
+  s.time_stamp_curr = stamps ? stamps[p] : t1 + (t1 - t0);
+}
+
+int launch_advance_state(gfpl_ctx* ctx, int B, const gfpl_pose_result* pose, const double* stamps, gfpl_frame_state* state) {
+  if (B <= 0) return GFPL_OK;
+  advance_state_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(B, pose, stamps, state);
   GFPL_LAUNCH_OK(ctx);
   return GFPL_OK;
 }

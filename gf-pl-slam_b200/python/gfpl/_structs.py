@@ -319,10 +319,11 @@ class CompactInputNP:
     """gfpl_compact_input of one step: raw current frames + previous stereo frames in their smallest exact form"""
     _keys = _COMPACT_KEYS
 
-    def __init__(self, raw, prev_full, pinned=False):
+    def __init__(self, raw, prev_full=None, pinned=False):
+        """prev_full=None: current frames only (sequence-chained replay, gfpl_replay_upload_curr_compact)"""
         B = raw.B
         self.B, self.cap_pt, self.cap_ln = B, raw.cap_pt, raw.cap_ln
-        self.prev_cap_pt, self.prev_cap_ln = prev_full.cap_pt, prev_full.cap_ln
+        self.prev_cap_pt, self.prev_cap_ln = (prev_full.cap_pt, prev_full.cap_ln) if prev_full is not None else (raw.cap_pt, raw.cap_ln)
         a = lambda s, d: _alloc(s, d, pinned)
 
         def u8(x):
@@ -341,6 +342,11 @@ class CompactInputNP:
             setattr(self, "ln_" + side, kl); setattr(self, "ln_oct_" + side, u8(src["octave"]))
             for k in ("pdesc_", "ldesc_"):
                 d = a(getattr(raw, k + side).shape, "u1"); d[:] = getattr(raw, k + side); setattr(self, k + side, d)
+        if prev_full is None:
+            for k in self._keys:
+                if k.startswith("prev_"):
+                    setattr(self, k, None)
+            return
         self.prev_n_pt, self.prev_n_ln = a(B, "i4"), a(B, "i4")
         self.prev_n_pt[:], self.prev_n_ln[:] = prev_full.n_pt, prev_full.n_ln
         self.prev_pdesc, self.prev_ldesc = a(prev_full.pdesc.shape, "u1"), a(prev_full.ldesc.shape, "u1")
@@ -360,10 +366,10 @@ class CompactInputNP:
 
     def view(self):
         return CompactInput(self.B, self.cap_pt, self.cap_ln, self.prev_cap_pt, self.prev_cap_ln,
-                            *[ptr(getattr(self, k)) for k in self._keys])
+                            *[ptr(getattr(self, k)) if getattr(self, k) is not None else None for k in self._keys])
 
     def nbytes(self):
-        return sum(getattr(self, k).nbytes for k in self._keys)
+        return sum(getattr(self, k).nbytes for k in self._keys if getattr(self, k) is not None)
 
 
 class TrackObsNP:

@@ -351,6 +351,16 @@ class Replay:
         cv = compact.view()
         self.ctx._check(lib().gfpl_replay_upload_compact(self._h, C.byref(cv), _vp(state)))
 
+    def upload_curr_compact(self, compact):
+        """sequence-chained replay: the next current raw frames only"""
+        cv = compact.view()
+        self.ctx._check(lib().gfpl_replay_upload_curr_compact(self._h, C.byref(cv)))
+
+    def advance(self, time_stamp_next=None):
+        """updateFrame: prev <- curr on the device, pose records -> frame state"""
+        ts = np.ascontiguousarray(time_stamp_next, np.float64) if time_stamp_next is not None else None
+        self.ctx._check(lib().gfpl_replay_advance(self._h, _vp(ts)))
+
     def run(self, flags):
         self.ctx._check(lib().gfpl_replay_run(self._h, flags))
 

@@ -235,6 +235,52 @@ def make_pairs(B, n_pt=300, n_ln=100, shape="euroc", seed=0, cap_pt=None, cap_ln
     return dict(cam=camera(shape), prev_raw=prev, curr_raw=curr, state=state, DT_true=DT_true)
 
 
+def make_sequences(B, T, n_pt=300, n_ln=100, shape="euroc", seed=0, distractor_frac=0.1, noise_px=0.5, pinned=False):
+    """B independent sequences of T + 1 stereo frames (sequence-chained replay: frame k is the previous frame of step k).
+    One scene per sequence, near-constant velocity: the increment of step k is the sequence's base twist scaled by
+    U(0.95, 1.05).  Returns dict(cam, frames [T + 1] RawFramesNP, state (of frame 0), DT_true [T][B,4,4], stamps [T + 1][B])."""
+    c = EUROC if shape == "euroc" else KITTI
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tw = np.zeros((B, 6))
+    tdir = rng.normal(size=(B, 3))
+    tw[:, :3] = tdir / np.linalg.norm(tdir, axis=1, keepdims=True) * rng.uniform(0, 0.1, (B, 1))
+    wdir = rng.normal(size=(B, 3))
+    tw[:, 3:] = wdir / np.linalg.norm(wdir, axis=1, keepdims=True) * rng.uniform(0, 0.05, (B, 1))
+    n_lm_pt = max(int(round(n_pt * (1 - distractor_frac))), 0)
+    n_lm_ln = max(int(round(n_ln * (1 - distractor_frac))), 0)
+    P = _sample_points(rng, c, B, n_lm_pt)
+    code = rng.integers(0, 256, size=(B, n_lm_pt, 32), dtype=np.uint8)
+    Ps = _sample_points(rng, c, B, n_lm_ln)
+    dirs = rng.normal(size=(B, n_lm_ln, 3))
+    dirs /= np.linalg.norm(dirs, axis=-1, keepdims=True)
+    Pe = Ps + dirs * rng.uniform(0.3, 3.0, (B, n_lm_ln, 1))
+    Pe[..., 2] = np.maximum(Pe[..., 2], 1.0)
+    lcode = rng.integers(0, 256, size=(B, n_lm_ln, 32), dtype=np.uint8)
+    frames, DT_true = [], []
+    Tk = np.tile(np.eye(4), (B, 1, 1))            # frame-0 coordinates -> frame-k coordinates
+    for k in range(T + 1):
+        fr = S.RawFramesNP(B, n_pt, n_ln, pinned)
+        R, t = Tk[:, :3, :3], Tk[:, None, :3, 3]
+        _fill_points(rng, c, fr, fr.pt_l, fr.pt_r, fr.pdesc_l, fr.pdesc_r, np.einsum("bij,bnj->bni", R, P) + t, code, n_pt, n_lm_pt, noise_px)
+        _fill_lines(rng, c, fr.ln_l, fr.ln_r, fr.ldesc_l, fr.ldesc_r, np.einsum("bij,bnj->bni", R, Ps) + t,
+                    np.einsum("bij,bnj->bni", R, Pe) + t, lcode, n_ln, n_lm_ln, noise_px)
+        fr.n_pt_l[:] = n_pt; fr.n_pt_r[:] = n_pt; fr.n_ln_l[:] = n_ln; fr.n_ln_r[:] = n_ln
+        frames.append(fr)
+        if k < T:
+            inc = _expmap(tw * rng.uniform(0.95, 1.05, (B, 1)))
+            DT_true.append(inc)
+            Tk = inc @ Tk
+    state = S._alloc(B, S.frame_state_dt, pinned)
+    state["Tfw"] = _expmap(np.concatenate([rng.uniform(-5, 5, (B, 3)), rng.uniform(-0.5, 0.5, (B, 3))], axis=1)).reshape(B, 16)
+    state["DT"] = _inv(_expmap(tw * rng.uniform(0.9, 1.1, (B, 1)))).reshape(B, 16)
+    state["DT_cov"] = (np.eye(6) * 1e-4).reshape(36)
+    state["Tfw_cov"] = (np.eye(6) * 1e-3).reshape(36)
+    state["time_stamp"] = 0.0
+    state["time_stamp_curr"] = 0.05
+    stamps = [np.full(B, 0.05 * k) for k in range(T + 2)]
+    return dict(cam=camera(shape), frames=frames, state=state, DT_true=DT_true, stamps=stamps)
+
+
 def tie_stress_descriptors(rng, n):
     """descriptors whose bytes 2..31 are zero (SURVEY §8d tie-stress set): most queries have d0 == d1."""
     d = np.zeros((n, 32), np.uint8)

@@ -557,6 +557,17 @@ int gfpl_replay_upload_slim(gfpl_replay* rp, const gfpl_prev_frames* prev, const
                             const gfpl_raw_frames* curr_raw);
 /* as gfpl_replay_upload_slim, from the compact records above (expanded on the device) */
 int gfpl_replay_upload_compact(gfpl_replay* rp, const gfpl_compact_input* in, const gfpl_frame_state* state /*[B]*/);
+/* Sequence-chained replay: B sequences advance one frame per step, as StereoFrameHandler::updateFrame does
+ * (stereoFrameHandler.cpp:908-912, `prev_frame = curr_frame`).  After a run,
+ *   gfpl_replay_advance   turns the current stereo frames into the previous frames of the next step ON THE DEVICE and the
+ *                         pose records into the frame state (Tfw, DT, DT_cov, Tfw_cov of optimizePose's result; time_stamp
+ *                         <- time_stamp_curr; time_stamp_curr <- time_stamp_next[p], or one more equal step when NULL);
+ *   gfpl_replay_upload_curr_compact   uploads only the NEXT current raw frames (the current-frame fields of
+ *                         gfpl_compact_input; its prev_* fields are ignored and may be NULL),
+ * so a step costs 35 KB of host-to-device traffic per EuRoC-shaped pair instead of 51 KB.  Needs a replay created with equal
+ * capacities for both frame sets (gfpl_replay_create).  The first step of a sequence is a normal upload. */
+int gfpl_replay_advance(gfpl_replay* rp, const double* time_stamp_next /*[B] or NULL*/);
+int gfpl_replay_upload_curr_compact(gfpl_replay* rp, const gfpl_compact_input* in);
 /* launch the whole step on the resident inputs (asynchronous; no host synchronisation inside) */
 int gfpl_replay_run(gfpl_replay* rp, int32_t flags);
 /* Software pipeline of gfpl_replay_run over n_sub contiguous sub-batches of the B pairs (1 = off, the default; at most

@@ -518,6 +518,49 @@ def test_replay_pipelined_is_bit_identical(ctx, orc, n_sub):
     assert fetch()[0].tobytes() == ref[0].tobytes() and rp.stage_ms()[-1] > 0
 
 
+def test_sequence_chained_replay_updateFrame(ctx, orc):
+    """gfpl_replay_advance + gfpl_replay_upload_curr_compact (StereoFrameHandler::updateFrame: prev_frame <- curr_frame):
+    4 steps over 24 sequences; every step's records equal the oracle driven the same way on the host (the oracle's
+    current frame and pose become its next previous frame and state)"""
+    from gfpl import api
+    B, T = 24, 4
+    sq = synth.make_sequences(B, T, seed=31)
+    flags = S.TRACK_LINECUT | S.TRACK_SEED_GIVEN
+    prev_o = orc.stereo_match(sq["cam"], ctx.cfg, sq["frames"][0])
+    state_o = sq["state"].copy()
+    rp = api.Replay(ctx, B, 300, 100)
+    rp.upload(prev_o, sq["state"], sq["frames"][1])
+    for k in range(1, T + 1):
+        if k > 1:
+            rp.advance(sq["stamps"][k])
+            rp.upload_curr_compact(S.CompactInputNP(sq["frames"][k]))
+        rp.run(flags)
+        pose = np.zeros(B, S.pose_result_dt)
+        obs = S.TrackObsNP(B, ctx.cfg.max_point_match_num, ctx.cfg.max_line_match_num)
+        curr = S.StereoFramesNP(B, 300, 100)
+        rp.download(pose, obs, None, curr)
+        ctx.sync()
+        co, oo, ko, po = orc.track(sq["cam"], ctx.cfg, prev_o, state_o, sq["frames"][k], flags)
+        _cmp_stereo(curr, co)
+        assert np.array_equal(obs.n_pt, oo.n_pt) and np.array_equal(obs.n_ln, oo.n_ln), k
+        for p in range(B):
+            assert np.array_equal(obs.pt[p, :oo.n_pt[p]]["prev_idx"], oo.pt[p, :oo.n_pt[p]]["prev_idx"]), (k, p)
+            assert np.array_equal(obs.pt_inlier[p, :oo.n_pt[p]], oo.pt_inlier[p, :oo.n_pt[p]]), (k, p)
+            assert np.array_equal(obs.ln_inlier[p, :oo.n_ln[p]], oo.ln_inlier[p, :oo.n_ln[p]]), (k, p)
+        _cmp_pose(pose, po, B)
+        assert (po["status"] == 0).mean() > 0.9 and (oo.n_pt > 80).all()
+        # the tracked increment is the simulated one
+        err = np.abs(np.linalg.inv(pose["DT"].reshape(B, 4, 4)) - sq["DT_true"][k - 1]).max(axis=(1, 2))
+        assert np.median(err) < 1e-2
+        # oracle side of updateFrame
+        prev_o = co
+        for f in ("Tfw", "DT", "DT_cov", "Tfw_cov"):
+            state_o[f] = po[f]
+        state_o["time_stamp"] = state_o["time_stamp_curr"]
+        state_o["time_stamp_curr"] = sq["stamps"][k + 1]
+    assert rp.h2d_bytes() < 0.75 * (S.CompactInputNP(sq["frames"][1], prev_o).nbytes())
+
+
 def test_track_at_scale_no_flips(ctx, orc):
     """4096 frame pairs through the whole step against the oracle (all host threads): the count of pairs whose inlier
     masks, iteration counts, status words or cut decisions differ must be ZERO — k_pose.cu is built with FMA
