@@ -796,6 +796,28 @@ int gfpl_linecut_submodular(gfpl_ctx* ctx, const double* DT_inv, gfpl_track_obs*
   return finish(ctx);
 }
 
+int gfpl_linecut_descent(gfpl_ctx* ctx, const double* DT_inv, gfpl_track_obs* obs, const gfpl_line_cov* prev_cov,
+                         int32_t cov_cap, gfpl_line_cut_descent* out) {
+  if (!ctx) return GFPL_E_INVALID;
+  REQUIRE(ctx, DT_inv && obs && prev_cov && out && obs->B >= 0 && cov_cap > 0);
+  if (obs->B == 0) return GFPL_OK;
+  REQUIRE(ctx, obs_counts_ok(obs));
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DevMem m(ctx);
+  DevTrackObs dobs;
+  REQUIRE_MEM(ctx, mirror_obs(m, obs, &dobs));
+  size_t B = obs->B;
+  double* dDT = m.upload(DT_inv, B * 16);
+  gfpl_line_cov* dcov = m.upload(prev_cov, B * cov_cap);
+  gfpl_line_cut_descent* dout = m.alloc<gfpl_line_cut_descent>(B * obs->cap_ln);
+  REQUIRE_MEM(ctx, dDT && dcov && dout);
+  GFPL_CUDA_OK(ctx, cudaMemsetAsync(dout, 0, B * obs->cap_ln * sizeof(gfpl_line_cut_descent), ctx->stream));
+  CHECK(launch_linecut_descent(ctx, dDT, dobs, dcov, cov_cap, dout));
+  download(ctx, out, dout, B * obs->cap_ln);
+  download(ctx, obs->ln, dobs.ln, B * obs->cap_ln);
+  return finish(ctx);
+}
+
 int gfpl_pose_hg(gfpl_ctx* ctx, const double* DT, const gfpl_track_obs* obs, double* H, double* g, double* e) {
   if (!ctx) return GFPL_E_INVALID;
   REQUIRE(ctx, DT && obs && H && g && e && obs->B >= 0);
@@ -815,6 +837,22 @@ int gfpl_pose_hg(gfpl_ctx* ctx, const double* DT, const gfpl_track_obs* obs, dou
   download(ctx, H, dH, B * 36);
   download(ctx, g, dg, B * 6);
   download(ctx, e, de, B);
+  return finish(ctx);
+}
+
+int gfpl_vector_stdv_mad(gfpl_ctx* ctx, const double* res, const int32_t* n, int32_t B, int32_t cap, double* out) {
+  if (!ctx) return GFPL_E_INVALID;
+  REQUIRE(ctx, res && n && out && B >= 0 && cap > 0 && cap < (1 << 14));
+  if (B == 0) return GFPL_OK;
+  for (int p = 0; p < B; p++) REQUIRE(ctx, n[p] >= 0 && n[p] <= cap);
+  GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DevMem m(ctx);
+  double* dres = m.upload(res, (size_t)B * cap);
+  int32_t* dn = m.upload(n, (size_t)B);
+  double* dout = m.alloc<double>((size_t)B);
+  REQUIRE_MEM(ctx, dres && dn && dout);
+  CHECK(launch_stdv_mad(ctx, dres, dn, B, cap, dout));
+  download(ctx, out, dout, (size_t)B);
   return finish(ctx);
 }
 

@@ -132,10 +132,14 @@ int launch_medoid(gfpl_ctx* ctx, const uint8_t* desc, const int32_t* offsets, in
 int launch_linecut(gfpl_ctx* ctx, const double* DT_inv, const gfpl_frame_state* state, DevTrackObs obs,
                    const gfpl_line_cov* prev_cov, int cov_cap, gfpl_line_cut* cut);
 
+int launch_linecut_descent(gfpl_ctx* ctx, const double* DT_inv, DevTrackObs obs, const gfpl_line_cov* prev_cov, int cov_cap,
+                           gfpl_line_cut_descent* out);
+
 // K4: pose
 int launch_pose_hg(gfpl_ctx* ctx, const double* DT, const DevTrackObs& obs, double* H, double* g, double* e);
 int launch_pose_optimize(gfpl_ctx* ctx, DevTrackObs obs, const gfpl_frame_state* state, const double* DT_ini,
                          int overload, gfpl_pose_result* out, void* raw_scratch = nullptr);
+int launch_stdv_mad(gfpl_ctx* ctx, const double* res, const int32_t* n, int B, int cap, double* out);
 size_t pose_raw_bytes(int B);   // size of the optimiser -> finalize hand-off buffer for B pairs
 
 // K6 / §8f-3: local BA over a BATCH of independent windows.  One LbaWin per window, all pointers DEVICE pointers (into

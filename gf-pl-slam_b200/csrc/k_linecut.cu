@@ -672,4 +672,176 @@ int launch_linecut(gfpl_ctx* ctx, const double* DT_inv, const gfpl_frame_state* 
   return GFPL_OK;
 }
 
+// ---- C6: estimateProjUncertainty_descent (stereoFrameHandler.cpp:1476-1610) -------------------------------------------
+// Unlike the submodular search the lines of a pair do not see each other here: one THREAD per matched line, the whole
+// batch in one launch (B x n_ln independent chains).  A candidate = getPoseCovOnLine (:1249-1338) + the eigenvalues of
+// the 6x6 covariance (getEigenValue, linespec.cpp:37-51: sorted, the two largest multiplied); the Jacobi iteration runs
+// with the matrix in registers.  Same operations in the same order as the oracle, -fmad=false: the decisions replay
+// exactly.
+
+// full 3x3 getJacob3D_2D (stereoFrame.cpp:1394-1413), row-major
+__device__ __forceinline__ void jacob3d_2d_full(const gfpl_camera& cam, double px, double py, double pz, double* J) {
+  const double f = cam.fx, b = cam.b, pz_2 = pz * pz;
+  J[0] = f / pz; J[1] = 0.0; J[2] = -f * px / pz_2;
+  J[3] = 0.0; J[4] = f / pz; J[5] = -f * py / pz_2;
+  J[6] = 0.0; J[7] = 0.0; J[8] = -f * b / pz_2;
+}
+
+// volume of the pose covariance of line data L at cut {c0, c1}
+__device__ __noinline__ double descent_volume_at(const gfpl_camera* cam, const gfpl_config* cfg, const double* DT, const double* L,
+                                                 double c0, double c1) {
+  double Js[6], Je[6];
+  const double cov_sR = pose_info_endpoint(*cam, *cfg, DT, &L[LD_SP], &L[LD_EP], &L[LD_CS], &L[LD_CE], &L[LD_LE], c0, Js);
+  const double cov_eR = pose_info_endpoint(*cam, *cfg, DT, &L[LD_EP], &L[LD_SP], &L[LD_CE], &L[LD_CS], &L[LD_LE], c1, Je);
+  // G = J^T J, G^-1 = adjugate * (1 / det)
+  double g00 = Js[0] * Js[0], g01 = Js[0] * Je[0], g11 = Je[0] * Je[0];
+#pragma unroll
+  for (int i = 1; i < 6; i++) {
+    g00 = g00 + Js[i] * Js[i];
+    g01 = g01 + Js[i] * Je[i];
+    g11 = g11 + Je[i] * Je[i];
+  }
+  const double det = g00 * g11 - g01 * g01;
+  const double invdet = 1.0 / det;
+  const double i00 = g11 * invdet, i01 = -g01 * invdet, i10 = -g01 * invdet, i11 = g00 * invdet;
+  double Jinv[12], A[12], S[36];
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    Jinv[j] = i00 * Js[j] + i01 * Je[j];
+    Jinv[6 + j] = i10 * Js[j] + i11 * Je[j];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    A[i * 2 + 0] = Jinv[i] * cov_sR + Jinv[6 + i] * 0.0;
+    A[i * 2 + 1] = Jinv[i] * 0.0 + Jinv[6 + i] * cov_eR;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j <= i; j++) {   // the solver reads the lower triangle, mirrored
+      const double v = A[i * 2 + 0] * Jinv[j] + A[i * 2 + 1] * Jinv[6 + j];
+      S[i * 6 + j] = v; S[j * 6 + i] = v;
+    }
+  double ev[6];
+  sym_eigenvalues_unrolled<6>(S, ev);
+#pragma unroll
+  for (int i = 1; i < 6; i++) {   // ascending insertion sort (any correct sort gives the oracle's std::sort outcome)
+#pragma unroll
+    for (int j = i; j > 0; j--) {
+      const double a = ev[j - 1], b = ev[j];
+      const bool sw = a > b;
+      ev[j - 1] = sw ? b : a; ev[j] = sw ? a : b;
+    }
+  }
+  return ev[5] * ev[4];
+}
+
+__global__ void __launch_bounds__(64)
+linecut_descent_kernel(const double* __restrict__ DT_inv_all, DevTrackObs obs, const gfpl_line_cov* __restrict__ prev_cov,
+                       int cov_cap, gfpl_line_cut_descent* __restrict__ out_all, gfpl_camera cam, gfpl_config cfg) {
+  __shared__ gfpl_camera s_cam;
+  __shared__ gfpl_config s_cfg;
+  if (threadIdx.x == 0) { s_cam = cam; s_cfg = cfg; }
+  __syncthreads();
+  const int p = blockIdx.y, l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= obs.n_ln[p]) return;
+  gfpl_ln_obs& o = obs.ln[(size_t)p * obs.cap_ln + l];
+  const gfpl_line_cov& c = prev_cov[(size_t)p * cov_cap + o.prev_idx];
+  gfpl_line_cut_descent& C = out_all[(size_t)p * obs.cap_ln + l];
+  double DT[12], T4[16], L[LD_SIZE];
+#pragma unroll
+  for (int i = 0; i < 16; i++) T4[i] = DT_inv_all[(size_t)p * 16 + i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    DT[i * 3 + 0] = T4[i * 4 + 0]; DT[i * 3 + 1] = T4[i * 4 + 1]; DT[i * 3 + 2] = T4[i * 4 + 2];
+    DT[9 + i] = T4[i * 4 + 3];
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) { L[LD_SP + k] = o.sP[k]; L[LD_EP + k] = o.eP[k]; }
+  L[LD_LE] = o.le_obs[0]; L[LD_LE + 1] = o.le_obs[1];
+#pragma unroll
+  for (int k = 0; k < 9; k++) { L[LD_CS + k] = c.covS[k]; L[LD_CE + k] = c.covE[k]; }
+
+  const double step = cfg.cut_step, rng0 = cfg.cut_rng[0], rng1 = cfg.cut_rng[1];
+  double cut0 = 0.0, cut1 = 0.0;
+  double vol_last = descent_volume_at(&s_cam, &s_cfg, DT, L, cut0, cut1);
+  int n_vol = 1;
+  while (cut0 + cut1 < 1.0) {
+    bool hitLower = false;
+    for (int j = 0; j < 8; j++) {
+      const int d0 = (j == 0 || j == 4 || j == 5) ? 1 : ((j == 1 || j == 6 || j == 7) ? -1 : 0);
+      const int d1 = (j == 2 || j == 4 || j == 6) ? 1 : ((j == 3 || j == 5 || j == 7) ? -1 : 0);
+      const double ct0 = cut0 + (d0 > 0 ? step : (d0 < 0 ? -step : 0.0)), ct1 = cut1 + (d1 > 0 ? step : (d1 < 0 ? -step : 0.0));
+      if (ct0 + ct1 >= 1.0) continue;
+      if (ct0 < rng0 || ct0 > rng1) continue;
+      if (ct1 < rng0 || ct1 > rng1) continue;
+      const double vol = descent_volume_at(&s_cam, &s_cfg, DT, L, ct0, ct1);
+      if (vol < vol_last) {   // the cut moves at once: later neighbours of this round are taken around the new cut (:1545-1550)
+        vol_last = vol; n_vol++;
+        cut0 = ct0; cut1 = ct1;
+        hitLower = true;
+      }
+    }
+    if (!hitLower) break;
+  }
+  C.cutRatio[0] = cut0; C.cutRatio[1] = cut1;
+  C.volume = vol_last; C.n_volume = n_vol;
+  C.fst_idx = 0; C.lst_idx = 3; C.pad = 0;
+  // :1567-1606 — both end points move from the ORIGINAL end points
+  double sP_cut[3], eP_cut[3], cov_s[9], cov_e[9], R[9], Rt[9];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    sP_cut[k] = (1 - cut0) * L[LD_SP + k] + cut0 * L[LD_EP + k];
+    eP_cut[k] = (1 - cut1) * L[LD_EP + k] + cut1 * L[LD_SP + k];
+  }
+  const double a0 = (1 - cut0) * (1 - cut0), b0 = cut0 * cut0, a1 = (1 - cut1) * (1 - cut1), b1 = cut1 * cut1;
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    cov_s[k] = a0 * L[LD_CS + k] + b0 * L[LD_CE + k];
+    cov_e[k] = a1 * L[LD_CE + k] + b1 * L[LD_CS + k];
+    R[k] = DT[k];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) Rt[j * 3 + i] = R[i * 3 + j];
+  double cur_s[3], cur_e[3], cur_s0[3], cur_e0[3], Jp[9], Jpt[9], T1[9], T2[9], T3[9], out9[9];
+  se3_apply(T4, sP_cut, cur_s);
+  se3_apply(T4, eP_cut, cur_e);
+  se3_apply(T4, &L[LD_SP], cur_s0);
+  se3_apply(T4, &L[LD_EP], cur_e0);
+  for (int e = 0; e < 2; e++) {   // covlPt2D[1] / [2] = J_proj * J_dt * cov * J_dt^T * J_proj^T, left to right
+    const double* cur = e == 0 ? cur_s : cur_e;
+    jacob3d_2d_full(cam, cur[0], cur[1], cur[2], Jp);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) Jpt[j * 3 + i] = Jp[i * 3 + j];
+    matmul<3, 3, 3>(Jp, R, T1);
+    matmul<3, 3, 3>(T1, e == 0 ? cov_s : cov_e, T2);
+    matmul<3, 3, 3>(T2, Rt, T3);
+    matmul<3, 3, 3>(T3, Jpt, out9);
+    for (int k = 0; k < 9; k++) C.covlPt2D[e][k] = out9[k];
+  }
+  projection(cam, cur_s0, C.lPt2D[0]);
+  projection(cam, cur_s, C.lPt2D[1]);
+  projection(cam, cur_e, C.lPt2D[2]);
+  projection(cam, cur_e0, C.lPt2D[3]);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { o.sP[k] = sP_cut[k]; o.eP[k] = eP_cut[k]; }
+  projection(cam, sP_cut, C.spl);
+  projection(cam, eP_cut, C.epl);
+  C.sdisp = get_disparity(cam, sP_cut[2]);
+  C.edisp = get_disparity(cam, eP_cut[2]);
+}
+
+int launch_linecut_descent(gfpl_ctx* ctx, const double* DT_inv, DevTrackObs obs, const gfpl_line_cov* prev_cov, int cov_cap,
+                           gfpl_line_cut_descent* out) {
+  if (obs.B <= 0 || obs.cap_ln <= 0) return GFPL_OK;
+  dim3 grid((obs.cap_ln + 63) / 64, obs.B);
+  linecut_descent_kernel<<<grid, 64, 0, ctx->stream>>>(DT_inv, obs, prev_cov, cov_cap, out, ctx->cam, ctx->cfg);
+  GFPL_LAUNCH_OK(ctx);
+  return GFPL_OK;
+}
+
 }  // namespace gfpl

@@ -25,6 +25,9 @@ constexpr int POSE_WARPS = POSE_WARPS_N;
 #ifndef POSE_GROUP
 #define POSE_GROUP 16     // lanes per frame pair
 #endif
+#ifndef POSE_CARVEOUT
+#define POSE_CARVEOUT 100  // per cent of the SM's L1 / shared memory configured as shared memory
+#endif
 #ifndef POSE_MAX_REGS
 #define POSE_MAX_REGS 168  // 6 CTAs = 12 warps per SM, nothing in local memory (144 = 14 warps: 0.92 ms against 0.89 ms)
 #endif
@@ -149,8 +152,47 @@ __device__ __forceinline__ bool ldlt6_solve_nopivot(const double* Hp /*lower tri
   return ok;
 }
 
+// expmap_se3 (auxiliar.cpp:165-182) for this translation unit: the reference divides 27 matrix entries by theta
+// element-wise; here 1/theta is formed once (rcp_nr) and multiplied in — every fp64 division is ~25 instructions with a
+// slow-path call, and all lanes of a group execute this serial part in every iteration (ncu: 13 % of the kernel's
+// instructions before).  Tolerance-compared like the rest of the file.
+__device__ __forceinline__ void expmap_se3_fast(const double* x, double* T) {
+  const double w0 = x[3], w1 = x[4], w2 = x[5];
+  double t0 = x[0], t1 = x[1], t2 = x[2];
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  const double th2 = w0 * w0 + w1 * w1 + w2 * w2;
+  if (!(th2 < 0.000001 * 0.000001)) {   // theta >= 1e-6 (NaN takes this branch, as in the reference)
+    const double ith = rsqrt_nr(th2), theta = th2 * ith;
+    const double a0 = w0 * ith, a1 = w1 * ith, a2 = w2 * ith;          // unit axis: s = skew(a)
+    double sn, cs;
+    sincos(theta, &sn, &cs);
+    const double omc = 1.0 - cs, tms = theta - sn;
+    // s = skew(a), ss = s * s = a a^T - |a|^2 I
+    const double s[9] = {0.0, -a2, a1, a2, 0.0, -a0, -a1, a0, 0.0};
+    const double ss[9] = {-(a1 * a1 + a2 * a2), a0 * a1, a0 * a2, a1 * a0, -(a0 * a0 + a2 * a2), a1 * a2, a2 * a0, a2 * a1, -(a0 * a0 + a1 * a1)};
+    const double c1 = omc * ith, c2 = tms * ith;
+    double V[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+      const double I = (i % 4 == 0) ? 1.0 : 0.0;
+      R[i] = (I + s[i] * sn) + ss[i] * omc;
+      V[i] = (I + s[i] * c1) + ss[i] * c2;
+    }
+    const double n0 = V[0] * t0 + V[1] * t1 + V[2] * t2;
+    const double n1 = V[3] * t0 + V[4] * t1 + V[5] * t2;
+    const double n2 = V[6] * t0 + V[7] * t1 + V[8] * t2;
+    t0 = n0; t1 = n1; t2 = n2;
+  }
+  T[0] = R[0]; T[1] = R[1]; T[2] = R[2]; T[3] = t0;
+  T[4] = R[3]; T[5] = R[4]; T[6] = R[5]; T[7] = t1;
+  T[8] = R[6]; T[9] = R[7]; T[10] = R[8]; T[11] = t2;
+  T[12] = 0.0; T[13] = 0.0; T[14] = 0.0; T[15] = 1.0;
+}
+
 // pivoted fallback, out of line (gfpl_math.cuh ldlt6_solve, local-memory arrays): only for H that is not safely SPD
 __device__ __noinline__ void ldlt6_solve_pivoted_slow(const double* H, const double* g, double* x) { ldlt6_solve(H, g, x); }
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 struct PairObs {
   int npt, nln;
@@ -270,6 +312,13 @@ __device__ __forceinline__ void group_optimize_functions(const double* DTs, cons
       const bool twoB = k + G < nwalk;
       const int k2 = twoB ? k + G : k;
       const int iA = o.plist ? (int)o.plist[k] : k, iB = o.plist ? (int)o.plist[k2] : k2;
+      if (k + 2 * G < nwalk) {   // the records of the next round: pulled into L1 now, no registers held
+        const int k3 = k + 3 * G < nwalk ? k + 3 * G : k + 2 * G;
+        const char* nA = reinterpret_cast<const char*>(&o.pts[o.plist ? (int)o.plist[k + 2 * G] : k + 2 * G]);
+        const char* nB = reinterpret_cast<const char*>(&o.pts[o.plist ? (int)o.plist[k3] : k3]);
+        prefetch_l1(nA); prefetch_l1(nA + 48);
+        prefetch_l1(nB); prefetch_l1(nB + 48);
+      }
       const gfpl_pt_obs A = o.pts[iA], Bq = o.pts[iB];
       const bool onA = o.plist ? true : o.pin[iA] != 0, onB = twoB && (o.plist ? true : o.pin[iB] != 0);
       double JA[6], JB[6], rA, rB, wA, wB;
@@ -359,7 +408,7 @@ __device__ __forceinline__ int group_gauss_newton(double* DTs /*shared, 12*/, co
         for (int i = 0; i < 6; i++) inc[i] = xm[i];
       }
       double E[16], Ei[16];
-      expmap_se3(inc, E);
+      expmap_se3_fast(inc, E);
       inverse_se3(E, Ei);
       matmul<4, 4, 4>(DT, Ei, DT);
       double nrm = 0.0;
@@ -397,17 +446,93 @@ __device__ __forceinline__ uint32_t group_select_u32(const uint32_t* keys, int n
   return prefix;
 }
 
+// sum of small non-negative counts (< 65536 per group) inside a group: for two groups per warp ONE warp-wide integer
+// reduction serves both (each group's count in its own 16-bit field) instead of four dependent shuffle + add steps
+template <int G>
+__device__ __forceinline__ int group_sum_small(int v) {
+  if (G == 32) return __reduce_add_sync(0xffffffffu, v);
+  if (G == 16) {
+    const int sh = (threadIdx.x & 16);   // 0 for the warp's first group, 16 for the second
+    const unsigned both = __reduce_add_sync(0xffffffffu, (unsigned)v << sh);
+    return (int)((both >> sh) & 0xFFFFu);
+  }
+  return group_sum<G>(v);
+}
+
+// element [rank] of the ascending order of the n keys (< 2^31) of a COMPACT array in shared memory, 16-byte aligned and
+// padded with 0xFFFFFFFF to a multiple of four; the array is destroyed.  Same MSB-first search as group_select_u32 in two
+// phases: the upper SEL_HI_BITS bits against the whole array (128-bit loads, four keys per instruction), then — the keys
+// that share those bits with the answer are usually a handful — the candidates are compacted (ballots), each lane takes
+// one into a register, and the remaining bits cost a ballot + popc per probe.  More than G candidates (heavy ties): the
+// generic loop over the compacted array.
+constexpr int SEL_LO_BITS = 15;
+template <int G>
+__device__ __forceinline__ uint32_t group_select_compact(uint32_t* keys, int n, int rank) {
+  const int lane = threadIdx.x & 31, lg = lane & (G - 1), gfirst = lane & ~(G - 1);
+  const unsigned gbits = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+  const uint4* k4 = reinterpret_cast<const uint4*>(keys);
+  const int n4 = (n + 3) >> 2;
+  uint32_t prefix = 0u;
+  for (int bit = 30; bit >= SEL_LO_BITS; bit--) {
+    const uint32_t trial = prefix | (1u << bit);
+    int cnt = 0;
+    for (int q = lg; q < n4; q += G) {
+      const uint4 v = k4[q];
+      cnt += (v.x < trial ? 1 : 0) + (v.y < trial ? 1 : 0) + (v.z < trial ? 1 : 0) + (v.w < trial ? 1 : 0);
+    }
+    cnt = group_sum_small<G>(cnt);
+    if (cnt <= rank) prefix = trial;
+  }
+  // candidates: keys whose upper bits equal the prefix; `below` = keys in lower buckets
+  const int nmax = __reduce_max_sync(0xffffffffu, n);
+  int m = 0, below = 0;
+  for (int k0 = 0; k0 < nmax; k0 += G) {
+    const int k = k0 + lg;
+    const uint32_t key = k < n ? keys[k] : 0xFFFFFFFFu;
+    const bool cand = k < n && ((key ^ prefix) >> SEL_LO_BITS) == 0u;
+    const unsigned bc = (__ballot_sync(0xffffffffu, cand) >> gfirst) & gbits;
+    const unsigned bb = (__ballot_sync(0xffffffffu, k < n && key < prefix) >> gfirst) & gbits;
+    if (cand) keys[m + __popc(bc & ((1u << lg) - 1u))] = key;   // in place: never past the chunk just read
+    m += __popc(bc); below += __popc(bb);
+  }
+  __syncwarp();
+  const int r2 = rank - below;
+  if (__all_sync(0xffffffffu, m <= G)) {
+    const uint32_t ck = lg < m ? keys[lg] : 0xFFFFFFFFu;
+#pragma unroll
+    for (int bit = SEL_LO_BITS - 1; bit >= 0; bit--) {
+      const uint32_t trial = prefix | (1u << bit);
+      const int cnt = __popc((__ballot_sync(0xffffffffu, ck < trial) >> gfirst) & gbits);
+      if (cnt <= r2) prefix = trial;
+    }
+  } else {
+    for (int bit = SEL_LO_BITS - 1; bit >= 0; bit--) {
+      const uint32_t trial = prefix | (1u << bit);
+      int cnt = 0;
+      for (int k = lg; k < m; k += G) cnt += keys[k] < trial ? 1 : 0;
+      cnt = group_sum_small<G>(cnt);
+      if (cnt <= r2) prefix = trial;
+    }
+  }
+  __syncwarp();
+  return prefix;
+}
+
 // 1.4826 * MAD of res[0..n) exactly as vector_stdv_mad (auxiliar.cpp:521-537) computes it:
 // median = sorted[n/2]; a = (double)fabsf(res - median) (float truncation); MAD = sorted(a)[n/2].
 // Order statistics of non-negative IEEE values are order statistics of their bit patterns, so both selections run on
 // 32-bit integer keys: the median on the high words of the doubles (low words only among the elements that tie on the
-// high word), the MAD on the float patterns of `a`, staged once in `scratch` (n words).  n == 0 gives 0.
+// high word), the MAD on the float patterns of `a`; both key sets are staged in `scratch` (n words rounded up to a
+// multiple of four, 16-byte aligned) for group_select_compact.  n == 0 gives 0.
 template <int G>
 __device__ __forceinline__ double group_stdv_mad(const double* res, int n, uint32_t* scratch) {
   const int lg = threadIdx.x & (G - 1);
   const uint32_t* w = reinterpret_cast<const uint32_t*>(res);  // little endian: w[2k] low word, w[2k+1] high word
   const int rank = n / 2;
-  const uint32_t hi = group_select_u32<G, 2, false, 30>(w + 1, n, rank, 0u);
+  const int npad = (n + 3) & ~3;
+  for (int k = lg; k < npad; k += G) scratch[k] = k < n ? w[2 * k + 1] : 0xFFFFFFFFu;
+  __syncwarp();
+  const uint32_t hi = group_select_compact<G>(scratch, n, rank);
   int below = 0, same = 0;
   uint32_t mine = 0u;
   for (int k = lg; k < n; k += G) {
@@ -415,8 +540,8 @@ __device__ __forceinline__ double group_stdv_mad(const double* res, int n, uint3
     same += w[2 * k + 1] == hi ? 1 : 0;
     mine = w[2 * k + 1] == hi ? w[2 * k] : mine;
   }
-  below = group_sum<G>(below);
-  same = group_sum<G>(same);
+  below = group_sum_small<G>(below);
+  same = group_sum_small<G>(same);
   uint32_t lo = group_max<G>(mine);   // the usual case: one element has that high word and it is the median
   const bool ties = n > 0 && same != 1;
   if (__any_sync(0xffffffffu, ties)) {
@@ -424,10 +549,9 @@ __device__ __forceinline__ double group_stdv_mad(const double* res, int n, uint3
     if (ties) lo = lo2;
   }
   const double median = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
-  for (int k = lg; k < n; k += G) scratch[k] = __float_as_uint(fabsf((float)(res[k] - median)));
+  for (int k = lg; k < npad; k += G) scratch[k] = k < n ? __float_as_uint(fabsf((float)(res[k] - median))) : 0xFFFFFFFFu;
   __syncwarp();
-  const uint32_t mad = group_select_u32<G, 1, false, 30>(scratch, n, rank, 0u);
-  __syncwarp();
+  const uint32_t mad = group_select_compact<G>(scratch, n, rank);
   return n == 0 ? 0.0 : 1.4826 * (double)__uint_as_float(mad);
 }
 
@@ -454,7 +578,7 @@ __device__ __forceinline__ void group_remove_outliers(const double* DTs, const P
     res_l[k] = r * sqrt(ob.sigma2);
   }
   __syncwarp();
-  uint32_t* scratch = reinterpret_cast<uint32_t*>(s_res + npt + nln);  // [max(npt, nln)] words behind the residuals
+  uint32_t* scratch = reinterpret_cast<uint32_t*>(s_res + ((npt + nln + 1) & ~1));  // [max(npt, nln) + 3] words behind the residuals, 16-byte aligned
   const double th_p = cfg.inlier_k * group_stdv_mad<G>(res_p, npt, scratch);
   const double th_l = cfg.inlier_k * group_stdv_mad<G>(res_l, nln, scratch);
   int dp = 0, dl = 0;
@@ -501,13 +625,14 @@ __device__ __noinline__ void unccomp_se3(const double* T1, const double* covT1, 
     }
 }
 
-__host__ __device__ inline int pose_smem_doubles(int cap_pt, int cap_ln) { return cap_pt + cap_ln + (cap_pt + cap_ln + 1) / 2; }
+// an even number of doubles (16-byte aligned slots): residuals, select scratch / inlier list, padding of the scratch
+__host__ __device__ inline int pose_smem_doubles(int cap_pt, int cap_ln) { return (cap_pt + cap_ln + (cap_pt + cap_ln + 1) / 2 + 4 + 1) & ~1; }
 
 template <int G>
 __global__ void __maxnreg__(POSE_MAX_REGS)
 pose_optimize_kernel(DevTrackObs obs, const gfpl_frame_state* __restrict__ state, const double* __restrict__ DT_ini,
                      int overload, PoseRaw* __restrict__ raw, gfpl_camera cam, gfpl_config cfg) {
-  extern __shared__ double s_res_all[];  // [POSE_WARPS * 32 / G][pose_smem_doubles(cap_pt, cap_ln)]
+  extern __shared__ __align__(16) double s_res_all[];  // [POSE_WARPS * 32 / G][pose_smem_doubles(cap_pt, cap_ln)]
   constexpr int PER_WARP = 32 / G;
   __shared__ double s_H[POSE_WARPS * PER_WARP][21];   // H of the last evaluation, per pair
   __shared__ __align__(16) double s_DT[POSE_WARPS * PER_WARP][12];   // the pose under optimisation, per pair
@@ -539,27 +664,31 @@ pose_optimize_kernel(DevTrackObs obs, const gfpl_frame_state* __restrict__ state
   bool cov_from_H = false;  // DT_cov ends as H^-1 of the refinement or as zero (:1889-1906)
   bool alive = exists && n_inliers > cfg.min_features;
   if (!alive) status |= GFPL_POSE_FEW_FEATURES;
-  // stage 0: first estimate on a copy of the seed (max_iters iterations), then the MAD outlier pass
+  // stage 0: first estimate on a copy of the seed (max_iters iterations), then the MAD outlier pass; stage 1: refinement
+  // restarting from the seed (D8) (max_iters_ref iterations).  The stages are iterations of ONE loop that is not
+  // unrolled: two inlined copies of the optimiser doubled the code, and the warps of an SM are spread over all of it
+  // (ncu: 12 % of the stall samples were instruction-cache misses).
   // (the select scratch behind the residuals doubles as the inlier list: the two are never live together)
   uint32_t* plist = reinterpret_cast<uint32_t*>(s_res + obs.cap_pt + obs.cap_ln);
-  o.nplist = group_inlier_list<G>(o.pin, alive ? o.npt : 0, plist);
   o.plist = plist;
-  pose_store(DTs, seed);
-  it1 = group_gauss_newton<G>(DTs, o, alive, cam, cfg, cfg.max_iters, Hs, &err);
-  pose_load(DTs, DT);
-  if (alive && !is_finite16(DT)) { status |= GFPL_POSE_NONFINITE_1; alive = false; }
-  {
-    int dp, dl;
-    group_remove_outliers<G>(DTs, o, alive, cam, cfg, s_res, &dp, &dl);
-    if (alive) {
-      n_inliers_pt -= dp; n_inliers_ls -= dl; n_inliers -= dp + dl;
-      if (!(n_inliers > cfg.min_features)) { status |= GFPL_POSE_FEW_INLIERS; alive = false; }
-    }
+#pragma unroll 1
+  for (int stage = 0; stage < 2; stage++) {
+    o.nplist = group_inlier_list<G>(o.pin, alive ? o.npt : 0, plist);
+    pose_store(DTs, seed);
+    const int it = group_gauss_newton<G>(DTs, o, alive, cam, cfg, stage == 0 ? cfg.max_iters : cfg.max_iters_ref, Hs, &err);
+    if (stage == 0) {
+      it1 = it;
+      pose_load(DTs, DT);
+      if (alive && !is_finite16(DT)) { status |= GFPL_POSE_NONFINITE_1; alive = false; }
+      int dp, dl;
+      group_remove_outliers<G>(DTs, o, alive, cam, cfg, s_res, &dp, &dl);
+      if (alive) {
+        n_inliers_pt -= dp; n_inliers_ls -= dl; n_inliers -= dp + dl;
+        if (!(n_inliers > cfg.min_features)) { status |= GFPL_POSE_FEW_INLIERS; alive = false; }
+      }
+    } else
+      it2 = it;
   }
-  // stage 1: refinement restarting from the seed (D8) (max_iters_ref iterations)
-  o.nplist = group_inlier_list<G>(o.pin, alive ? o.npt : 0, plist);
-  pose_store(DTs, seed);
-  it2 = group_gauss_newton<G>(DTs, o, alive, cam, cfg, cfg.max_iters_ref, Hs, &err);
   if (alive) { cov_from_H = true; pose_load(DTs, DT); }
   else eye4(DT);
 
@@ -580,7 +709,8 @@ pose_optimize_kernel(DevTrackObs obs, const gfpl_frame_state* __restrict__ state
 // serial tail of optimizePose (:1984-2028): DT_cov = H^-1, inverse_se3, motion-step gate, Tfw, eigenvalues of
 // DT_cov, unccomp_se3.  One THREAD per pair (the GN kernel spends a warp per pair; this part has no
 // parallelism inside a pair, so it runs 32 pairs per warp here).
-__global__ void __launch_bounds__(128)
+constexpr int FINALIZE_THREADS = 32;   // one warp per CTA: 8192 pairs = 256 CTAs over all SMs (the kernel is one serial chain per thread)
+__global__ void __launch_bounds__(FINALIZE_THREADS)
 pose_finalize_kernel(int B, const PoseRaw* __restrict__ raw, const gfpl_frame_state* __restrict__ state, int overload,
                      gfpl_pose_result* __restrict__ out, gfpl_config cfg) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -609,7 +739,22 @@ pose_finalize_kernel(int B, const PoseRaw* __restrict__ raw, const gfpl_frame_st
   } else
     status |= GFPL_POSE_NONFINITE_2;
   for (int i = 0; i < 36; i++) r.DT_cov[i] = DT_cov[i];
-  sym_eigenvalues<6>(DT_cov, r.DT_cov_eig);
+  {  // eigenvalues of DT_cov: the cyclic Jacobi iteration with the matrix in registers (the out-of-line routine keeps it in
+     // local memory: every rotation then waits for ~50 dependent local loads), ascending insertion sort as before
+    double ev[6];
+    sym_eigenvalues_unrolled<6>(DT_cov, ev);
+#pragma unroll
+    for (int i = 1; i < 6; i++) {
+#pragma unroll
+      for (int j = i; j > 0; j--) {
+        const double a = ev[j - 1], b = ev[j];
+        const bool sw = a > b;
+        ev[j - 1] = sw ? b : a; ev[j] = sw ? a : b;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) r.DT_cov_eig[i] = ev[i];
+  }
   if (accept) {
     double Tfw[16];
     matmul<4, 4, 4>(st.Tfw, DTinv, Tfw);
@@ -634,10 +779,16 @@ static int launch_pose_optimize_on(gfpl_ctx* ctx, DevTrackObs obs, const gfpl_fr
   const size_t smem = (size_t)PAIRS_PER_CTA * pose_smem_doubles(obs.cap_pt, obs.cap_ln) * sizeof(double);
   if (smem > 48 * 1024)
     GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(pose_optimize_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // prefer shared memory over L1: with the default carve-out the scratch allowed 5 CTAs per SM, the registers allow 6
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(pose_optimize_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, POSE_CARVEOUT));
+    carveout_set = true;
+  }
   const int grid = (obs.B + PAIRS_PER_CTA - 1) / PAIRS_PER_CTA;
   pose_optimize_kernel<G><<<grid, POSE_WARPS * 32, smem, ctx->stream>>>(obs, state, DT_ini, overload, raw, ctx->cam, ctx->cfg);
   GFPL_LAUNCH_OK(ctx);
-  pose_finalize_kernel<<<(obs.B + 127) / 128, 128, 0, ctx->stream>>>(obs.B, raw, state, overload, out, ctx->cfg);
+  pose_finalize_kernel<<<(obs.B + FINALIZE_THREADS - 1) / FINALIZE_THREADS, FINALIZE_THREADS, 0, ctx->stream>>>(obs.B, raw, state, overload, out, ctx->cfg);
   GFPL_LAUNCH_OK(ctx);
   return GFPL_OK;
 }
@@ -654,6 +805,39 @@ int launch_pose_optimize(gfpl_ctx* ctx, DevTrackObs obs, const gfpl_frame_state*
   const cudaError_t fe = cudaFreeAsync(raw, ctx->stream);   // also on the error paths above
   if (rc != GFPL_OK) return rc;
   GFPL_CUDA_OK(ctx, fe);
+  return GFPL_OK;
+}
+
+// ---- vector_stdv_mad alone (auxiliar.cpp:521-537): B arrays, one lane group each — the selection of removeOutliers --------
+__global__ void __launch_bounds__(POSE_WARPS * 32)
+stdv_mad_kernel(const double* __restrict__ res_all, const int32_t* __restrict__ n_all, int B, int cap, double* __restrict__ out) {
+  extern __shared__ __align__(16) double s_mad[];   // per group: cap residuals (even count), then cap + 4 words of scratch
+  constexpr int G = POSE_GROUP, PER_CTA = POSE_WARPS * 32 / G;
+  const int slot = threadIdx.x / G, lg = threadIdx.x & (G - 1);
+  const int p = blockIdx.x * PER_CTA + slot;
+  const bool exists = p < B;                   // a group past the batch only takes part in the warp-wide operations
+  const int n = exists ? n_all[p] : 0;
+  const int cap2 = (cap + 1) & ~1;
+  const int per = (cap2 + (cap + 4 + 1) / 2 + 1 + 1) & ~1;   // doubles per group, even: 16-byte aligned groups
+  double* res = s_mad + (size_t)slot * per;
+  uint32_t* scratch = reinterpret_cast<uint32_t*>(res + cap2);
+  for (int k = lg; k < n; k += G) res[k] = res_all[(size_t)p * cap + k];
+  __syncwarp();
+  const double v = group_stdv_mad<G>(res, n, scratch);
+  if (exists && lg == 0) out[p] = v;
+}
+
+int launch_stdv_mad(gfpl_ctx* ctx, const double* res, const int32_t* n, int B, int cap, double* out) {
+  if (B <= 0) return GFPL_OK;
+  constexpr int PER_CTA = POSE_WARPS * 32 / POSE_GROUP;
+  const int cap2 = (cap + 1) & ~1;
+  size_t per = (size_t)(cap2 + (cap + 4 + 1) / 2 + 1);
+  per = (per + 1) & ~(size_t)1;                // 16-byte aligned groups
+  const size_t smem = PER_CTA * per * sizeof(double);
+  if (smem > 48 * 1024)
+    GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(stdv_mad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  stdv_mad_kernel<<<(B + PER_CTA - 1) / PER_CTA, POSE_WARPS * 32, smem, ctx->stream>>>(res, n, B, cap, out);
+  GFPL_LAUNCH_OK(ctx);
   return GFPL_OK;
 }
 

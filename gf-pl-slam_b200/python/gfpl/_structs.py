@@ -59,6 +59,9 @@ ln_obs_dt = np.dtype([("sP", "f8", 3), ("eP", "f8", 3), ("le_obs", "f8", 3), ("s
                       ("curr_idx", "i4")], align=True)
 line_cut_dt = np.dtype([("cutRatio", "f8", 2), ("invCovPose", "f8", 36), ("spl", "f8", 2), ("epl", "f8", 2),
                         ("sdisp", "f8"), ("edisp", "f8")], align=True)
+line_cut_descent_dt = np.dtype([("cutRatio", "f8", 2), ("volume", "f8"), ("n_volume", "i4"), ("fst_idx", "i4"), ("lst_idx", "i4"),
+                                ("pad", "i4"), ("covlPt2D", "f8", (2, 9)), ("lPt2D", "f8", (4, 2)), ("spl", "f8", 2), ("epl", "f8", 2),
+                                ("sdisp", "f8"), ("edisp", "f8")], align=True)
 frame_state_dt = np.dtype([("Tfw", "f8", 16), ("DT", "f8", 16), ("DT_cov", "f8", 36), ("Tfw_cov", "f8", 36),
                            ("time_stamp", "f8"), ("time_stamp_curr", "f8")], align=True)
 pose_result_dt = np.dtype([("DT", "f8", 16), ("Tfw", "f8", 16), ("DT_cov", "f8", 36), ("DT_cov_eig", "f8", 6),
@@ -73,6 +76,7 @@ assert prev_point_dt.itemsize == 32 and prev_line_dt.itemsize == 112
 assert keypoint_dt.itemsize == 16 and keyline_dt.itemsize == 32
 assert point_feature_dt.itemsize == 72 and line_feature_dt.itemsize == 152
 assert line_cov_dt.itemsize == 144 and pt_obs_dt.itemsize == 56 and ln_obs_dt.itemsize == 88
+assert line_cut_descent_dt.itemsize == 296
 assert line_cut_dt.itemsize == 352 and frame_state_dt.itemsize == 848 and pose_result_dt.itemsize == 912
 
 _vp = C.c_void_p

@@ -248,7 +248,23 @@ class Context:
                                                   prev_cov.shape[1], _vp(cut)))
         return cut
 
+    def linecut_descent(self, DT_inv, obs, prev_cov):
+        """C6, estimateProjUncertainty_descent: obs is updated in place (sP/eP of every line); returns gfpl_line_cut_descent records."""
+        out = np.zeros((obs.B, obs.cap_ln), S.line_cut_descent_dt)
+        DT_inv = np.ascontiguousarray(DT_inv, np.float64)
+        ov = obs.view()
+        self._check(lib().gfpl_linecut_descent(self._h, _vp(DT_inv), C.byref(ov), _vp(prev_cov), prev_cov.shape[1], _vp(out)))
+        return out
+
     # ---- P1-P4 ----
+    def vector_stdv_mad(self, res, n):
+        """res: [B][cap] float64, n: [B] -> 1.4826 * MAD per row (vector_stdv_mad, auxiliar.cpp:521-537)"""
+        res = np.ascontiguousarray(res, np.float64)
+        n = np.ascontiguousarray(n, np.int32)
+        out = np.zeros(len(n), np.float64)
+        self._check(lib().gfpl_vector_stdv_mad(self._h, _vp(res), _vp(n), len(n), res.shape[1], _vp(out)))
+        return out
+
     def pose_hg(self, DT, obs):
         DT = np.ascontiguousarray(DT, np.float64)
         H = np.zeros((obs.B, 36)); g = np.zeros((obs.B, 6)); e = np.zeros(obs.B)

@@ -202,6 +202,21 @@ typedef struct gfpl_line_cut {
   double sdisp, edisp;
 } gfpl_line_cut;
 
+/* Per matched line outputs of StereoFrameHandler::estimateProjUncertainty_descent (stereoFrameHandler.cpp:1476-1610):
+ * cutRatio, the last entry and the length of volumeArr, and the fields :1567-1606 rewrite — covlPt2D[1] / [2] (entries 0
+ * and 3 are the identity), lPt2D[0..3], fst_idx / lst_idx, spl / epl / sdisp / edisp of the cut end points.  296 B */
+typedef struct gfpl_line_cut_descent {
+  double cutRatio[2];
+  double volume;              /* volumeArr.back(): product of the two largest eigenvalues of the pose covariance */
+  int32_t n_volume;           /* volumeArr.size() */
+  int32_t fst_idx, lst_idx;   /* 0, 3 (:1599-1600) */
+  int32_t pad;
+  double covlPt2D[2][9];      /* row-major 3x3 */
+  double lPt2D[4][2];
+  double spl[2], epl[2];
+  double sdisp, edisp;
+} gfpl_line_cut_descent;
+
 /* The fields of a PREVIOUS frame's stereo features that the tracking step reads (f2f matching: P, sigma2, descriptor;
  * line uncertainty / cut / GN: sP, eP, spl, epl, sdisp, edisp, le[0], sigma2).  A streaming replay uploads these slim
  * records instead of the full gfpl_point_feature / gfpl_line_feature (32 B vs 72 B, 112 B vs 152 B per feature). */
@@ -502,6 +517,18 @@ int gfpl_medoid_desc(gfpl_ctx* ctx, const uint8_t* desc, const int32_t* offsets,
 int gfpl_linecut_submodular(gfpl_ctx* ctx, const double* DT_inv /*[B][16]*/, gfpl_track_obs* obs,
                             const gfpl_line_cov* prev_cov, int32_t cov_cap, gfpl_line_cut* cut);
 
+/* C6: StereoFrameHandler::estimateProjUncertainty_descent (stereoFrameHandler.cpp:1476-1610) with getPoseCovOnLine
+ * (:1249-1338): per matched line, independent of the other lines, a descent over the 8 neighbour cuts that takes every
+ * strictly smaller volume at once (the cut moves inside the neighbour loop, :1545-1550).  The volume is the product of
+ * the two largest eigenvalues of the rank-2 pose covariance; the reference takes the real parts of Eigen's general
+ * EigenSolver sorted in descending order (getEigenValue, linespec.cpp:37-51) — here: the eigenvalues of the symmetric
+ * matrix given by its lower triangle (cyclic Jacobi, as everywhere in this library), sorted, the two largest multiplied.
+ * Step and range come from gfpl_config.cut_step / cut_rng (the reference's call site passes 0.05 and rngCutRatio,
+ * :127).  Arguments as gfpl_linecut_submodular; obs->ln[].sP/eP are replaced by the cut end points (both taken from
+ * the ORIGINAL end points, :1567-1568); out: [B][obs->cap_ln]. */
+int gfpl_linecut_descent(gfpl_ctx* ctx, const double* DT_inv /*[B][16]*/, gfpl_track_obs* obs,
+                         const gfpl_line_cov* prev_cov, int32_t cov_cap, gfpl_line_cut_descent* out);
+
 /* ------------------------------------------------------------------------- */
 /* P1-P4 — pose optimisation                                                  */
 /* ------------------------------------------------------------------------- */
@@ -510,6 +537,11 @@ int gfpl_linecut_submodular(gfpl_ctx* ctx, const double* DT_inv /*[B][16]*/, gfp
  * g (6), e for B problems at poses DT[p] (4x4 row-major, maps prev -> curr). */
 int gfpl_pose_hg(gfpl_ctx* ctx, const double* DT /*[B][16]*/, const gfpl_track_obs* obs,
                  double* H /*[B][36]*/, double* g /*[B][6]*/, double* e /*[B]*/);
+
+/* vector_stdv_mad (auxiliar.cpp:521-537; the threshold of removeOutliers, stereoFrameHandler.cpp:2058-2116) for B arrays:
+ * out[p] = 1.4826 * sorted(fabsf(res - sorted(res)[n/2]))[n/2] of res[p][0..n[p]) (0 for n = 0), exact — the
+ * order statistics are taken on the IEEE bit patterns.  res: [B][cap], non-negative values, cap < 16384. */
+int gfpl_vector_stdv_mad(gfpl_ctx* ctx, const double* res, const int32_t* n /*[B]*/, int32_t B, int32_t cap, double* out /*[B]*/);
 
 #define GFPL_POSE_SEED_PREV_DT 0 /* optimizePose()            stereoFrameHandler.cpp:1864-1937 */
 #define GFPL_POSE_SEED_GIVEN 1   /* optimizePose(Matrix4d)    stereoFrameHandler.cpp:1939-2030 (adds the motion-step gate) */

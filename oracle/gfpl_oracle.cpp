@@ -1142,6 +1142,170 @@ extern "C" int orc_linecut_submodular(const gfpl_camera* cam, const gfpl_config*
   return GFPL_OK;
 }
 
+// ---- C6: estimateProjUncertainty_descent (stereoFrameHandler.cpp:1476-1610) ---------------------------------------
+// StereoFrameHandler::getPoseCovOnLine (stereoFrameHandler.cpp:1249-1338): the pose covariance a line contributes at a
+// cut, cov_pose = Jinv^T * diag(cov_sR, cov_eR) * Jinv with Jinv = (J^T J)^-1 J^T, J = [Jac_sr2x Jac_er2x] (6x2).
+static void pose_cov_on_line(const gfpl_camera* cam, const gfpl_config* cfg, const double* DT_inv, const double* sP,
+                             const double* eP, const double* le_obs, const gfpl_line_cov* cov, const double* cut,
+                             double* cov_pose) {
+  double J_loss[2] = {le_obs[0], le_obs[1]};
+  double sP_tmp[3], eP_tmp[3], cov_sP[9], cov_eP[9], R[9];
+  for (int k = 0; k < 3; k++) {
+    sP_tmp[k] = (1 - cut[0]) * sP[k] + cut[0] * eP[k];
+    eP_tmp[k] = (1 - cut[1]) * eP[k] + cut[1] * sP[k];
+  }
+  double a0 = (1 - cut[0]) * (1 - cut[0]), b0 = cut[0] * cut[0];
+  double a1 = (1 - cut[1]) * (1 - cut[1]), b1 = cut[1] * cut[1];
+  for (int k = 0; k < 9; k++) {
+    cov_sP[k] = a0 * cov->covS[k] + b0 * cov->covE[k];
+    cov_eP[k] = a1 * cov->covE[k] + b1 * cov->covS[k];
+  }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) R[i * 3 + j] = DT_inv[i * 4 + j];
+  double cur_s[3], cur_e[3], Jp[6];
+  se3_apply(DT_inv, sP_tmp, cur_s);
+  jacob3d_2d(cam, cur_s[0], cur_s[1], cur_s[2], Jp);
+  double cov_sR = residual_var(Jp, R, cov_sP, J_loss);
+  se3_apply(DT_inv, eP_tmp, cur_e);
+  jacob3d_2d(cam, cur_e[0], cur_e[1], cur_e[2], Jp);
+  double cov_eR = residual_var(Jp, R, cov_eP, J_loss);
+  double Js[6], Je[6];
+  double gz2 = cur_s[2] * cur_s[2];
+  jac6(cam->fx / std::max(cfg->homog_th, gz2), cur_s[0], cur_s[1], cur_s[2], J_loss[0], J_loss[1], Js);
+  gz2 = cur_e[2] * cur_e[2];
+  jac6(cam->fx / std::max(cfg->homog_th, gz2), cur_e[0], cur_e[1], cur_e[2], J_loss[0], J_loss[1], Je);
+  // G = J^T J (2x2, sequential dot products), G^-1 = adjugate * (1/det) (Eigen's 2x2 inverse)
+  double g00 = Js[0] * Js[0], g01 = Js[0] * Je[0], g11 = Je[0] * Je[0];
+  for (int i = 1; i < 6; i++) {
+    g00 = g00 + Js[i] * Js[i];
+    g01 = g01 + Js[i] * Je[i];
+    g11 = g11 + Je[i] * Je[i];
+  }
+  double det = g00 * g11 - g01 * g01;
+  double invdet = 1.0 / det;
+  double i00 = g11 * invdet, i01 = -g01 * invdet, i10 = -g01 * invdet, i11 = g00 * invdet;
+  double Jinv[12];  // 2x6: G^-1 * J^T
+  for (int j = 0; j < 6; j++) {
+    Jinv[j] = i00 * Js[j] + i01 * Je[j];
+    Jinv[6 + j] = i10 * Js[j] + i11 * Je[j];
+  }
+  // (Jinv^T * cov_r) * Jinv with cov_r = [cov_sR 0; 0 cov_eR]
+  double A[12];  // 6x2
+  for (int i = 0; i < 6; i++) {
+    A[i * 2 + 0] = Jinv[i] * cov_sR + Jinv[6 + i] * 0.0;
+    A[i * 2 + 1] = Jinv[i] * 0.0 + Jinv[6 + i] * cov_eR;
+  }
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < 6; j++) cov_pose[i * 6 + j] = A[i * 2 + 0] * Jinv[j] + A[i * 2 + 1] * Jinv[6 + j];
+}
+
+// getEigenValue (linespec.cpp:37-51) sorts the real parts of EigenSolver's eigenvalues in DESCENDING order; the descent
+// metric is ev[0] * ev[1].  cov_pose is symmetric (rank 2, positive semi-definite) up to rounding, so the symmetric solver
+// applied to its lower triangle returns the same spectrum; rule chosen here: Jacobi eigenvalues of the mirrored lower
+// triangle, sorted ascending, product of the two LARGEST (ev[5] * ev[4]).
+static double descent_volume(const double* cov_pose) {
+  double S[36], ev[6];
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j <= i; j++) { S[i * 6 + j] = cov_pose[i * 6 + j]; S[j * 6 + i] = cov_pose[i * 6 + j]; }
+  sym_eigenvalues<6>(S, ev);
+  return ev[5] * ev[4];
+}
+extern "C" void orc_pose_cov_on_line(const gfpl_camera* cam, const gfpl_config* cfg, const double* DT_inv,
+                                     const gfpl_ln_obs* ln, const gfpl_line_cov* cov, const double cut[2], double* cov36) {
+  pose_cov_on_line(cam, cfg, DT_inv, ln->sP, ln->eP, ln->le_obs, cov, cut, cov36);
+}
+extern "C" double orc_descent_volume(const double* cov36) { return descent_volume(cov36); }
+
+// full 3x3 getJacob3D_2D (stereoFrame.cpp:1394-1413), row-major
+static inline void jacob3d_2d_full(const gfpl_camera* cam, double px, double py, double pz, double* J) {
+  double f = cam->fx, b = cam->b, pz_2 = pz * pz;
+  J[0] = f / pz; J[1] = 0.0; J[2] = -f * px / pz_2;
+  J[3] = 0.0; J[4] = f / pz; J[5] = -f * py / pz_2;
+  J[6] = 0.0; J[7] = 0.0; J[8] = -f * b / pz_2;
+}
+
+// one line of estimateProjUncertainty_descent (:1503-1607).  The lines are independent of each other here (no information
+// sum): the cut moves as soon as a neighbour is better (inside the j loop, :1545-1550), so later neighbours of the same
+// round are taken around the cut that has already moved.
+static void linecut_descent_line(const gfpl_camera* cam, const gfpl_config* cfg, const double* DT_inv, gfpl_ln_obs* ln,
+                                 const gfpl_line_cov* cov, gfpl_line_cut_descent* C) {
+  const double step = cfg->cut_step;
+  const double* rng = cfg->cut_rng;
+  const double nb[8][2] = {{step, 0}, {-step, 0}, {0, step}, {0, -step}, {step, step}, {step, -step}, {-step, step}, {-step, -step}};
+  double cut[2] = {0, 0}, cov_x[36];
+  pose_cov_on_line(cam, cfg, DT_inv, ln->sP, ln->eP, ln->le_obs, cov, cut, cov_x);
+  double vol_last = descent_volume(cov_x);
+  int n_vol = 1;
+  while (cut[0] + cut[1] < 1.0) {
+    bool hitLower = false;
+    for (int j = 0; j < 8; j++) {
+      double ct[2] = {cut[0] + nb[j][0], cut[1] + nb[j][1]};
+      if (ct[0] + ct[1] >= 1.0) continue;
+      if (ct[0] < rng[0] || ct[0] > rng[1]) continue;
+      if (ct[1] < rng[0] || ct[1] > rng[1]) continue;
+      pose_cov_on_line(cam, cfg, DT_inv, ln->sP, ln->eP, ln->le_obs, cov, ct, cov_x);
+      double vol = descent_volume(cov_x);
+      if (vol < vol_last) {
+        vol_last = vol; n_vol++;
+        cut[0] = ct[0]; cut[1] = ct[1];
+        hitLower = true;
+      }
+    }
+    if (!hitLower) break;
+  }
+  C->cutRatio[0] = cut[0]; C->cutRatio[1] = cut[1];
+  C->volume = vol_last; C->n_volume = n_vol;
+  C->fst_idx = 0; C->lst_idx = 3; C->pad = 0;
+  // :1567-1606 — both end points move from the ORIGINAL end points (unlike updateEndPointByRatio)
+  double sP_cut[3], eP_cut[3], cov_s[9], cov_e[9], R[9], Rt[9];
+  for (int k = 0; k < 3; k++) {
+    sP_cut[k] = (1 - cut[0]) * ln->sP[k] + cut[0] * ln->eP[k];
+    eP_cut[k] = (1 - cut[1]) * ln->eP[k] + cut[1] * ln->sP[k];
+  }
+  double a0 = (1 - cut[0]) * (1 - cut[0]), b0 = cut[0] * cut[0];
+  double a1 = (1 - cut[1]) * (1 - cut[1]), b1 = cut[1] * cut[1];
+  for (int k = 0; k < 9; k++) {
+    cov_s[k] = a0 * cov->covS[k] + b0 * cov->covE[k];
+    cov_e[k] = a1 * cov->covE[k] + b1 * cov->covS[k];
+  }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) R[i * 3 + j] = DT_inv[i * 4 + j];
+  transpose<3, 3>(R, Rt);
+  double cur_s[3], cur_e[3], cur_s0[3], cur_e0[3], Jp[9], Jpt[9], T1[9], T2[9], T3[9];
+  se3_apply(DT_inv, sP_cut, cur_s);
+  se3_apply(DT_inv, eP_cut, cur_e);
+  se3_apply(DT_inv, ln->sP, cur_s0);
+  se3_apply(DT_inv, ln->eP, cur_e0);
+  // covlPt2D[1] / [2] = J_proj * J_dt * cov * J_dt^T * J_proj^T, left to right
+  jacob3d_2d_full(cam, cur_s[0], cur_s[1], cur_s[2], Jp);
+  transpose<3, 3>(Jp, Jpt);
+  matmul<3, 3, 3>(Jp, R, T1); matmul<3, 3, 3>(T1, cov_s, T2); matmul<3, 3, 3>(T2, Rt, T3); matmul<3, 3, 3>(T3, Jpt, C->covlPt2D[0]);
+  jacob3d_2d_full(cam, cur_e[0], cur_e[1], cur_e[2], Jp);
+  transpose<3, 3>(Jp, Jpt);
+  matmul<3, 3, 3>(Jp, R, T1); matmul<3, 3, 3>(T1, cov_e, T2); matmul<3, 3, 3>(T2, Rt, T3); matmul<3, 3, 3>(T3, Jpt, C->covlPt2D[1]);
+  projection(cam, cur_s0, C->lPt2D[0]);
+  projection(cam, cur_s, C->lPt2D[1]);
+  projection(cam, cur_e, C->lPt2D[2]);
+  projection(cam, cur_e0, C->lPt2D[3]);
+  for (int k = 0; k < 3; k++) { ln->sP[k] = sP_cut[k]; ln->eP[k] = eP_cut[k]; }
+  projection(cam, sP_cut, C->spl);
+  projection(cam, eP_cut, C->epl);
+  C->sdisp = get_disparity(cam, sP_cut[2]);
+  C->edisp = get_disparity(cam, eP_cut[2]);
+}
+
+extern "C" int orc_linecut_descent(const gfpl_camera* cam, const gfpl_config* cfg, const double* DT_inv, gfpl_track_obs* obs,
+                                   const gfpl_line_cov* prev_cov, int32_t cov_cap, gfpl_line_cut_descent* cut) {
+  if (!cam || !cfg || !DT_inv || !obs || !prev_cov || !cut) return GFPL_E_INVALID;
+  for (int p = 0; p < obs->B; p++)
+    for (int l = 0; l < obs->n_ln[p]; l++) {
+      gfpl_ln_obs* ln = obs->ln + (size_t)p * obs->cap_ln + l;
+      linecut_descent_line(cam, cfg, DT_inv + (size_t)p * 16, ln, prev_cov + (size_t)p * cov_cap + ln->prev_idx,
+                           cut + (size_t)p * obs->cap_ln + l);
+    }
+  return GFPL_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // P1-P4: pose optimisation
 // ------------------------------------------------------------------------------------------------

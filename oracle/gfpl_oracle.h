@@ -40,6 +40,11 @@ int orc_kf_match(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_ster
 int orc_map_match(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_local_map* map,
                   const gfpl_stereo_frames* kf1, const double* Twf, gfpl_map_matches* out);
 int orc_medoid_desc(const uint8_t* desc, const int32_t* offsets, int32_t L, int32_t* out_idx);
+int orc_linecut_descent(const gfpl_camera* cam, const gfpl_config* cfg, const double* DT_inv, gfpl_track_obs* obs,
+                        const gfpl_line_cov* prev_cov, int32_t cov_cap, gfpl_line_cut_descent* cut);
+void orc_pose_cov_on_line(const gfpl_camera* cam, const gfpl_config* cfg, const double* DT_inv, const gfpl_ln_obs* ln,
+                          const gfpl_line_cov* cov, const double cut[2], double* cov36);
+double orc_descent_volume(const double* cov36);
 int orc_linecut_submodular(const gfpl_camera* cam, const gfpl_config* cfg, const double* DT_inv, gfpl_track_obs* obs,
                            const gfpl_line_cov* prev_cov, int32_t cov_cap, gfpl_line_cut* cut);
 /* single evaluation of getPoseInfoOnLine / getPoseInfoPoint / logdet / min-eigenvalue (unit tests) */

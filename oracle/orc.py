@@ -33,6 +33,7 @@ def lib():
         _LIB.orc_vector_stdv_mad.restype = C.c_double
         _LIB.orc_logdet6.restype = C.c_double
         _LIB.orc_min_eig6.restype = C.c_double
+        _LIB.orc_descent_volume.restype = C.c_double
     return _LIB
 
 
@@ -54,7 +55,7 @@ def use_native_build():
         _LIB = None
         native = C.CDLL(so)
         lib_parity = lib()
-        for name in ("orc_line_descriptor_mad", "orc_budget_thres", "orc_vector_stdv_mad", "orc_logdet6", "orc_min_eig6"):
+        for name in ("orc_line_descriptor_mad", "orc_budget_thres", "orc_vector_stdv_mad", "orc_logdet6", "orc_min_eig6", "orc_descent_volume"):
             getattr(native, name).restype = C.c_double
         _LIB = native
         return NATIVE_FLAGS
@@ -190,6 +191,33 @@ def linecut(cam, cfg, DT_inv, obs, prev_cov):
                                       C.c_void_p(S.ptr(prev_cov)), prev_cov.shape[1], C.c_void_p(S.ptr(cut)))
     assert rc == 0, rc
     return cut
+
+
+def linecut_descent(cam, cfg, DT_inv, obs, prev_cov):
+    """C6: obs is updated in place (sP/eP of every line); returns the gfpl_line_cut_descent records."""
+    out = np.zeros((obs.B, obs.cap_ln), S.line_cut_descent_dt)
+    DT_inv = np.ascontiguousarray(DT_inv, np.float64)
+    ov = obs.view()
+    rc = lib().orc_linecut_descent(C.byref(cam), C.byref(cfg), C.c_void_p(S.ptr(DT_inv)), C.byref(ov),
+                                   C.c_void_p(S.ptr(prev_cov)), prev_cov.shape[1], C.c_void_p(S.ptr(out)))
+    assert rc == 0, rc
+    return out
+
+
+def pose_cov_on_line(cam, cfg, DT_inv, ln, cov, cut):
+    """getPoseCovOnLine for one line record (numpy scalars of ln_obs_dt / line_cov_dt) -> 6x6"""
+    out = np.zeros(36)
+    DT_inv = np.ascontiguousarray(DT_inv, np.float64)
+    ln = np.ascontiguousarray(ln).reshape(1); cov = np.ascontiguousarray(cov).reshape(1)
+    cut = np.ascontiguousarray(cut, np.float64)
+    lib().orc_pose_cov_on_line(C.byref(cam), C.byref(cfg), C.c_void_p(S.ptr(DT_inv)), C.c_void_p(S.ptr(ln)),
+                               C.c_void_p(S.ptr(cov)), C.c_void_p(S.ptr(cut)), C.c_void_p(S.ptr(out)))
+    return out.reshape(6, 6)
+
+
+def descent_volume(M):
+    M = np.ascontiguousarray(M, np.float64)
+    return float(lib().orc_descent_volume(C.c_void_p(S.ptr(M))))
 
 
 def pose_hg(cam, cfg, DT, obs):

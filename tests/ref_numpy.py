@@ -276,6 +276,72 @@ def linecut_submodular(cam, cfg, DT_inv, pts, lns, covs):
     return cut, info, sP, eP
 
 
+# ---- stereoFrameHandler.cpp:1249-1338 (getPoseCovOnLine), :1476-1610 (estimateProjUncertainty_descent), linespec.cpp:37-51 ------
+def pose_cov_on_line(cam, cfg, DT_inv, sP, eP, le_obs, covS, covE, cut):
+    c0, c1 = cut
+    sP_t = (1 - c0) * sP + c0 * eP
+    eP_t = (1 - c1) * eP + c1 * sP
+    cov_s = (1 - c0) ** 2 * covS + c0 ** 2 * covE
+    cov_e = (1 - c1) ** 2 * covE + c1 ** 2 * covS
+    Rm, t = DT_inv[:3, :3], DT_inv[:3, 3]
+    jl = le_obs[:2]
+    cols, var = [], []
+    for P_t, cov in ((sP_t, cov_s), (eP_t, cov_e)):
+        cur = Rm @ P_t + t
+        Jp = jacob_3d_2d(cam, *cur)[:2]
+        var.append(jl @ (Jp @ Rm @ cov @ Rm.T @ Jp.T) @ jl)
+        cols.append(_jac6(cam.fx / max(cfg.homog_th, cur[2] * cur[2]), cur[0], cur[1], cur[2], jl[0], jl[1]))
+    Jac = np.stack(cols, 1)                                          # Jac_r2x, 6 x 2
+    Jinv = np.linalg.inv(Jac.T @ Jac) @ Jac.T                        # 2 x 6
+    return Jinv.T @ np.diag(var) @ Jinv
+
+
+def eigen_values_desc(M):
+    """getEigenValue: real parts of the GENERAL eigen-solver's values, sorted descending (LAPACK dgeev for Eigen::EigenSolver)"""
+    return np.sort(np.linalg.eigvals(M).real)[::-1]
+
+
+def linecut_descent(cam, cfg, DT_inv, lns, covs):
+    """Per line (independent): returns cut [n][2], the volume track per line, and the rewritten fields."""
+    step, rng = cfg.cut_step, (cfg.cut_rng[0], cfg.cut_rng[1])
+    nb = [(step, 0), (-step, 0), (0, step), (0, -step), (step, step), (step, -step), (-step, step), (-step, -step)]
+    Rm, t = DT_inv[:3, :3], DT_inv[:3, 3]
+    out = []
+    for l in range(len(lns)):
+        sP, eP, le = lns["sP"][l], lns["eP"][l], lns["le_obs"][l]
+        covS, covE = covs[l]
+        cut = [0.0, 0.0]
+        ev = eigen_values_desc(pose_cov_on_line(cam, cfg, DT_inv, sP, eP, le, covS, covE, cut))
+        vols = [ev[0] * ev[1]]
+        margins = []                                               # relative gap of every comparison made (near ties)
+        while cut[0] + cut[1] < 1.0:
+            hit = False
+            for dx, dy in nb:
+                ct = (cut[0] + dx, cut[1] + dy)
+                if ct[0] + ct[1] >= 1.0 or ct[0] < rng[0] or ct[0] > rng[1] or ct[1] < rng[0] or ct[1] > rng[1]:
+                    continue
+                ev = eigen_values_desc(pose_cov_on_line(cam, cfg, DT_inv, sP, eP, le, covS, covE, ct))
+                v = ev[0] * ev[1]
+                margins.append(abs(v - vols[-1]) / max(abs(vols[-1]), 1e-300))
+                if v < vols[-1]:
+                    vols.append(v); cut = [ct[0], ct[1]]; hit = True   # the cut moves inside the neighbour loop
+            if not hit:
+                break
+        sP_cut = (1 - cut[0]) * sP + cut[0] * eP
+        eP_cut = (1 - cut[1]) * eP + cut[1] * sP
+        cov_s = (1 - cut[0]) ** 2 * covS + cut[0] ** 2 * covE
+        cov_e = (1 - cut[1]) ** 2 * covE + cut[1] ** 2 * covS
+        cur_s, cur_e = Rm @ sP_cut + t, Rm @ eP_cut + t
+        Js, Je = jacob_3d_2d(cam, *cur_s), jacob_3d_2d(cam, *cur_e)
+        out.append(dict(cut=np.array(cut), vols=vols, min_margin=min(margins) if margins else 1.0,
+                        covl=(Js @ Rm @ cov_s @ Rm.T @ Js.T, Je @ Rm @ cov_e @ Rm.T @ Je.T),
+                        lPt2D=np.stack([projection(cam, Rm @ sP + t), projection(cam, cur_s), projection(cam, cur_e),
+                                        projection(cam, Rm @ eP + t)]),
+                        sP=sP_cut, eP=eP_cut, spl=projection(cam, sP_cut), epl=projection(cam, eP_cut),
+                        sdisp=get_disparity(cam, sP_cut[2]), edisp=get_disparity(cam, eP_cut[2])))
+    return out
+
+
 # ---- stereoFrame.cpp:881-1014 (line part of extractStereoFeatures_Brute) -------------------------------------------------------
 def hamming2_matrix(a, b):
     """NORM_HAMMING2: number of differing 2-bit groups"""

@@ -37,6 +37,7 @@ def test_struct_layouts_match_c(tmp_path):
                "gfpl_point_feature": S.point_feature_dt.itemsize, "gfpl_line_feature": S.line_feature_dt.itemsize,
                "gfpl_line_cov": S.line_cov_dt.itemsize, "gfpl_pt_obs": S.pt_obs_dt.itemsize,
                "gfpl_ln_obs": S.ln_obs_dt.itemsize, "gfpl_line_cut": S.line_cut_dt.itemsize,
+               "gfpl_line_cut_descent": S.line_cut_descent_dt.itemsize,
                "gfpl_frame_state": S.frame_state_dt.itemsize, "gfpl_pose_result": S.pose_result_dt.itemsize,
                "gfpl_raw_frames": C.sizeof(S.RawFrames), "gfpl_stereo_frames": C.sizeof(S.StereoFrames),
                "gfpl_track_obs": C.sizeof(S.TrackObs), "gfpl_lba_problem": C.sizeof(S.LbaProblem),

@@ -212,6 +212,57 @@ def test_linecut_submodular_search_pin(orc, world):
     assert lines > 20 and moved > 3
 
 
+# ---- C6: estimateProjUncertainty_descent + getPoseCovOnLine (stereoFrameHandler.cpp:1476-1610, 1249-1338) -------------------
+def test_pose_cov_on_line_pin(orc, world):
+    """the rank-2 pose covariance and its volume: general eigen-solver (LAPACK dgeev, as Eigen::EigenSolver in getEigenValue)
+    against the oracle's symmetric Jacobi solver; closed form of the volume: cov_sR * cov_eR / det(J^T J)"""
+    cam, cfg, obs, cov = world["cam"], world["cfg"], world["obs"], world["cov"]
+    n = 0
+    for p in range(obs.B):
+        for l in range(min(obs.n_ln[p], 6)):
+            ln = obs.ln[p, l]
+            c = cov[p, ln["prev_idx"]]
+            for cut in ((0.0, 0.0), (0.05, 0.0), (0.25, 0.4), (0.0, 0.95)):
+                M = orc.pose_cov_on_line(cam, cfg, world["DT_inv"][p], ln, c, cut)
+                ref = R.pose_cov_on_line(cam, cfg, world["DT_inv"][p], ln["sP"], ln["eP"], ln["le_obs"], c["covS"].reshape(3, 3),
+                                         c["covE"].reshape(3, 3), cut)
+                # (J^T J)^-1 of two nearly parallel Jacobian columns: agreement is limited by cond(J^T J) * eps (adjugate
+                # inverse in the oracle / Eigen, LAPACK LU here), not by the formulas
+                assert rel(M, ref) <= 1e-9
+                ev = R.eigen_values_desc(ref)
+                assert abs(orc.descent_volume(M) - ev[0] * ev[1]) <= 1e-8 * abs(ev[0] * ev[1])
+                n += 1
+    assert n > 40
+
+
+def test_linecut_descent_search_pin(orc, world):
+    cam, cfg, cov = world["cam"], world["cfg"], world["cov"]
+    obs = world["obs"].copy()
+    before = world["obs"].copy()
+    out = orc.linecut_descent(cam, cfg, world["DT_inv"].reshape(-1, 16), obs, cov)
+    lines = moved = near_ties = 0
+    for p in range(obs.B):
+        n = obs.n_ln[p]
+        lns = before.ln[p, :n]
+        covs = [(cov[p, i]["covS"].reshape(3, 3), cov[p, i]["covE"].reshape(3, 3)) for i in lns["prev_idx"]]
+        ref = R.linecut_descent(cam, cfg, world["DT_inv"][p], lns, covs)
+        for l in range(n):
+            r, o = ref[l], out[p, l]
+            if r["min_margin"] < 1e-7:          # a comparison the two eigen-solvers may order differently: counted, not compared
+                near_ties += 1
+                continue
+            assert np.array_equal(np.round(o["cutRatio"] / cfg.cut_step), np.round(r["cut"] / cfg.cut_step)), (p, l)   # decisions
+            assert o["n_volume"] == len(r["vols"]) and abs(o["volume"] - r["vols"][-1]) <= 1e-8 * abs(r["vols"][-1])
+            assert o["fst_idx"] == 0 and o["lst_idx"] == 3
+            assert rel(o["covlPt2D"][0].reshape(3, 3), r["covl"][0]) <= 1e-11 and rel(o["covlPt2D"][1].reshape(3, 3), r["covl"][1]) <= 1e-11
+            assert rel(o["lPt2D"], r["lPt2D"]) <= RT
+            assert rel(obs.ln[p, l]["sP"], r["sP"]) <= RT and rel(obs.ln[p, l]["eP"], r["eP"]) <= RT
+            assert rel(o["spl"], r["spl"]) <= RT and rel(o["epl"], r["epl"]) <= RT
+            assert rel(o["sdisp"], r["sdisp"]) <= RT and rel(o["edisp"], r["edisp"]) <= RT
+            lines += 1; moved += int(np.abs(r["cut"]).max() > 1e-4)
+    assert lines > 20 and moved > 3 and near_ties <= lines // 10, (lines, moved, near_ties)
+
+
 # ---- P1-P4: optimizePose = GN(5) + removeOutliers + GN(10) + gates (stereoFrameHandler.cpp:1939-2116) -------------------------
 def _cmp_pose(pose, p, ref, tol=1e-9):
     # the iterates pass through a 6x6 solve per step (Eigen LDLT in the reference, LAPACK LU here, our own LDLT in the
