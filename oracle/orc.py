@@ -18,6 +18,8 @@ _LIB = None
 
 
 def build(force=False):
+    if os.environ.get("GFPL_ORACLE_LIB"):     # another build of the same sources (the ASan / UBSan build of `make asan`)
+        return os.environ["GFPL_ORACLE_LIB"]
     so = os.path.join(_HERE, "_build", "libgfpl_oracle.so")
     if force or not os.path.exists(so):
         subprocess.check_call(["make", "-C", _HERE, "all"], stdout=subprocess.DEVNULL)
