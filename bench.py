@@ -521,11 +521,35 @@ def main():
     slots, pose_devs = make_slots(a.n_pt, a.n_ln)
     e2e_s, h2d_avg, d2h_avg = e2e_measure()
 
+    # ---- copy floor: every rank copies the step's H2D / D2H bytes from pinned memory at the same time, nothing else running
+    # (what the host's PCIe / memory path gives N concurrent ranks: the bound of the e2e step) --------------------------
+    def copy_floor(h2d_bytes, d2h_bytes, reps=10):
+        hb = torch.empty(int(h2d_bytes), dtype=torch.uint8).pin_memory()
+        db = torch.empty(int(h2d_bytes), dtype=torch.uint8, device="cuda")
+        ho = torch.empty(int(d2h_bytes), dtype=torch.uint8).pin_memory()
+        do = torch.empty(int(d2h_bytes), dtype=torch.uint8, device="cuda")
+        st_in, st_out = torch.cuda.Stream(), torch.cuda.Stream()
+        for _ in range(2):
+            db.copy_(hb, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            with torch.cuda.stream(st_in):
+                db.copy_(hb, non_blocking=True)
+            with torch.cuda.stream(st_out):
+                ho.copy_(do, non_blocking=True)
+        st_in.synchronize(); st_out.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        barrier()
+        return dt
+    floor_s = copy_floor(h2d_avg, d2h_avg)
+    floor_ind_s = copy_floor(ind_h2d, ind_d2h)
+
     # ---- max over ranks ----------------------------------------------------------------------------------------
-    t = torch.tensor([ms, e2e_s * 1e3, ind_s * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, e2e_s * 1e3, ind_s * 1e3, floor_s * 1e3, floor_ind_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, ind_ms = float(t[0]), float(t[1]), float(t[2])
+    ms, e2e_ms, ind_ms, floor_ms, floor_ind_ms = (float(x) for x in t)
 
     if rank == 0:
         if not a.skip_cpu_baseline:   # CPU arm: the oracle sources rebuilt with the reference's flags on this machine
@@ -593,7 +617,11 @@ def main():
                 linecut_flops),
             {"kernel": "pose_optimize_kernel (+ finalize)", "bound": "fp64", "achieved": gn_flops / (stage[7] * 1e-3) / 1e12,
              "peak": fp64_peak, "unit": "TFLOP/s (fp64)", "frac": gn_flops / (stage[7] * 1e-3) / 1e12 / fp64_peak, "kernel_ms": float(stage[7]),
-             "note": "algorithmic flops = GN iterations x (114 per inlier point + 212 per inlier line); 16 lanes per pair (two pairs per warp), serial 6x6 solve per iteration"},
+             "executed_flops_frac": (lambda c: float(c["fp64_flops"]) / (stage[7] * 1e-3) / 1e12 / fp64_peak if c and c.get("fp64_flops") else None)(
+                 counters.get("pose_optimize_kernel<16>") if counters_match else None),
+             "note": "algorithmic flops = GN iterations x (114 per inlier point + 212 per inlier line); executed_flops_frac counts every fp64 "
+                     "instruction of one launch (profiles/%s: residual pass of removeOutliers, the redundant per-lane solve and SE(3) update, "
+                     "reciprocal refinements); 16 lanes per pair (two pairs per warp)" % COUNTERS_FILE},
         ]
         # the bench line's `roofline` is the kernel with the largest share of the (unpipelined) step
         roofline = dict(max(by_kernel, key=lambda r: r["kernel_ms"]))
@@ -615,10 +643,15 @@ def main():
                        "pipeline": "%d resident slots / streams: H2D of step k overlaps the kernels of earlier steps; results consumed %d steps later" % (NSLOT, LAG),
                        "timing": "host wall clock around K x (upload+run+download) + final sync, max over ranks",
                        "h2d_GBps_per_rank": h2d_avg / (e2e_ms / a.steps * 1e-3) / 1e9,
+                       "copy_floor": {"ms_per_step": floor_ms, "h2d_GBps_per_rank": h2d_avg / (floor_ms * 1e-3) / 1e9,
+                                      "e2e_over_floor": (e2e_ms / a.steps) / floor_ms,
+                                      "how": "all %d rank(s) copy this step's H2D and D2H bytes from / to pinned memory concurrently, no kernels "
+                                             "(max over ranks): what the host's PCIe / memory path allows" % world},
                        "host_affinity_cpus": numa_cpus},
                "e2e_independent_pairs": {"value": world * B * a.steps / (ind_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(ind_h2d) * world,
                                          "d2h_bytes_per_step": int(ind_d2h) * world, "ms_per_step": ind_ms / a.steps,
                                          "h2d_GBps_per_rank": ind_h2d / (ind_ms / a.steps * 1e-3) / 1e9,
+                                         "copy_floor_ms_per_step": floor_ind_ms, "e2e_over_floor": (ind_ms / a.steps) / floor_ind_ms,
                                          "mode": "every step uploads the previous frames' stereo survivors and the current frames (round 1's e2e)"},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_by_kernel": by_kernel,
                "kernel_ms_per_step": dict(zip(["knn_stereo_pt", "knn_stereo_ln", "stereo_accept", "f2f_pt_search", "knn_f2f_ln",

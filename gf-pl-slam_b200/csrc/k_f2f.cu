@@ -426,8 +426,9 @@ f2f_accept_kernel(DevStereoFrames prev, DevStereoFrames curr, int mode, const ui
   const int pt_cap = min(cfg.max_point_match_num, out.cap_pt);
   const int ln_cap = min(cfg.max_line_match_num, out.cap_ln);
 
+  // blockIdx.y = 0: the points of pair p, 1: its lines — two independent CTAs
   // ---- points --------------------------------------------------------------------------------------
-  {
+  if (blockIdx.y == 0) {
     const int n_prev = prev.n_pt[p], n_curr = curr.n_pt[p];
     int base = 0;
     if (mode == GFPL_F2F_HYBRID) {
@@ -492,7 +493,7 @@ f2f_accept_kernel(DevStereoFrames prev, DevStereoFrames curr, int mode, const ui
       }
     }
     if (threadIdx.x == 0) out.n_pt[p] = base;
-    __syncthreads();
+    return;
   }
 
   // ---- lines (stereoFrameHandler.cpp:607-686 == 775-851) -------------------------------------------------
@@ -665,7 +666,7 @@ int launch_f2f_accept(gfpl_ctx* ctx, const DevStereoFrames& prev, const DevStere
   const size_t smem = (size_t)(vcap > 0 ? vcap : 1) * 4 + (size_t)(prev.cap_pt > 0 ? prev.cap_pt : 1) * 4;
   if (smem > 48 * 1024)
     GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(f2f_accept_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  f2f_accept_kernel<<<prev.B, ACC_THREADS, smem, ctx->stream>>>(prev, curr, mode, best_key, pt_12, pt_21, ln_12, ln_21,
+  f2f_accept_kernel<<<dim3(prev.B, 2), ACC_THREADS, smem, ctx->stream>>>(prev, curr, mode, best_key, pt_12, pt_21, ln_12, ln_21,
                                                                out, ctx->cfg);
   GFPL_LAUNCH_OK(ctx);
   return GFPL_OK;

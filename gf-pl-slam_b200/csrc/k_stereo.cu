@@ -6,7 +6,7 @@
 // lineDescriptorMAD (:1287-1313), lineSegmentOverlapStereo (:1343-1371), estimateStereoUncertainty
 // (:1448-1484) with getCovMat2D_3D / getJacob2D_3D (:1375-1392, 1434-1446).
 //
-// One CTA per stereo frame.  Accepted features keep the reference's output order (ascending left index):
+// Two CTAs per stereo frame (points, lines).  Accepted features keep the reference's output order (ascending left index):
 // a block-wide ordered compaction (ballot + warp totals) assigns the output slot.  HBM-/latency-bound,
 // O(N) per frame: algorithmic bytes = knn results (16 B/query, two directions) + key points (16 B) +
 // key lines (32 B) in, feature records (72 B / 152 B) + 32 B descriptor out.
@@ -16,6 +16,7 @@
 namespace gfpl {
 
 constexpr int ACCEPT_THREADS = 128;
+constexpr int ACCEPT_UNROLL = 3;    // stereo points: elements per thread with their loads in flight together
 
 // ordered block compaction: returns the output slot of this thread's element (valid when pred), advances
 // `base` (uniform across the CTA) by the number of accepted elements of this round.
@@ -129,55 +130,74 @@ stereo_accept_kernel(DevRawFrames raw, int variant, Knn2Out pt_lr, Knn2Out pt_rl
   const size_t rp = (size_t)p * raw.cap_pt, rl_ = (size_t)p * raw.cap_ln;
   const size_t op = (size_t)p * out.cap_pt, ol = (size_t)p * out.cap_ln;
 
+  // blockIdx.y = 0: the points of frame p, 1: its lines — two independent CTAs (the halves share nothing, and a kernel
+  // bound by the latency of dependent global loads wants many small CTAs in flight)
   // ---- points (stereoFrame.cpp:206-245 / 829-878) -------------------------------------------------
-  {
+  if (blockIdx.y == 0) {
     const int n_l = raw.n_pt_l[p], n_r = raw.n_pt_r[p];
     int base = 0;
     if (cfg.has_points && n_l >= 2 && n_r >= 2) {  // D3
-      for (int i0 = 0; i0 < n_l; i0 += ACCEPT_THREADS) {
-        const int i = i0 + threadIdx.x;
-        bool keep = false;
-        int tdx = 0;
-        float disp_sub = 0.f;
-        gfpl_keypoint kl{};
-        if (i < n_l) {
-          // The loads form two levels instead of four: the left key point goes out with the knn record, the reverse
-          // record and the right key point together once the match index is known (the kernel is bound by the latency
-          // of these dependent global loads: ncu long-scoreboard 56 %).
-          const int2 mi = pt_lr.idx[rp + i];
-          const float2 md = pt_lr.dist[rp + i];
-          kl = raw.pt_l[rp + i];
-          tdx = mi.x;
-          const int rl_tdx = cfg.best_lr_matches ? pt_rl.idx[rp + tdx].x : i;
-          const gfpl_keypoint kr = raw.pt_r[rp + tdx];
-          const double dist_12 = (double)(md.x / md.y);  // float / float, widened (stereoFrame.cpp:219,842)
-          if (i == rl_tdx && dist_12 <= cfg.max_ratio_12_p) {
-            if ((double)fabsf(kl.y - kr.y) <= cfg.max_dist_epip) {
-              const double disp_ = (double)(kl.x - kr.x);
-              if (disp_ >= cfg.min_disp) {
-                disp_sub = (float)disp_;
-                keep = disp_sub >= 0.f;
+      // ACCEPT_UNROLL elements per thread and round: all their first-level loads (knn record, left key point) go out
+      // together, then all second-level loads (reverse record, right key point) — the loads form two levels instead of
+      // four per element, and ACCEPT_UNROLL elements share each level's latency (ncu: long-scoreboard 11 of 18 stall cycles
+      // per issue with one element per round)
+      for (int i0 = 0; i0 < n_l; i0 += ACCEPT_THREADS * ACCEPT_UNROLL) {
+        int2 mi[ACCEPT_UNROLL];
+        float2 md[ACCEPT_UNROLL];
+        gfpl_keypoint kl[ACCEPT_UNROLL], kr[ACCEPT_UNROLL];
+        int rl_tdx[ACCEPT_UNROLL];
+#pragma unroll
+        for (int u = 0; u < ACCEPT_UNROLL; u++) {
+          const int i = i0 + u * ACCEPT_THREADS + threadIdx.x;
+          if (i < n_l) { mi[u] = pt_lr.idx[rp + i]; md[u] = pt_lr.dist[rp + i]; kl[u] = raw.pt_l[rp + i]; }
+          else { mi[u] = make_int2(0, 0); md[u] = make_float2(0.f, 0.f); kl[u] = gfpl_keypoint{}; }
+        }
+#pragma unroll
+        for (int u = 0; u < ACCEPT_UNROLL; u++) {
+          const int i = i0 + u * ACCEPT_THREADS + threadIdx.x;
+          if (i < n_l) {
+            rl_tdx[u] = cfg.best_lr_matches ? pt_rl.idx[rp + mi[u].x].x : i;
+            kr[u] = raw.pt_r[rp + mi[u].x];
+          } else { rl_tdx[u] = -1; kr[u] = gfpl_keypoint{}; }
+        }
+#pragma unroll
+        for (int u = 0; u < ACCEPT_UNROLL; u++) {
+          const int i = i0 + u * ACCEPT_THREADS + threadIdx.x;
+          bool keep = false;
+          float disp_sub = 0.f;
+          const int tdx = mi[u].x;
+          if (i < n_l) {
+            const double dist_12 = (double)(md[u].x / md[u].y);  // float / float, widened (stereoFrame.cpp:219,842)
+            if (i == rl_tdx[u] && dist_12 <= cfg.max_ratio_12_p) {
+              if ((double)fabsf(kl[u].y - kr[u].y) <= cfg.max_dist_epip) {
+                const double disp_ = (double)(kl[u].x - kr[u].x);
+                if (disp_ >= cfg.min_disp) {
+                  disp_sub = (float)disp_;
+                  keep = disp_sub >= 0.f;
+                }
               }
             }
           }
-        }
-        const int slot = block_compact(keep, base, s_warp);
-        if (keep) {
-          gfpl_point_feature f;
-          f.pl[0] = kl.x; f.pl[1] = kl.y;
-          back_projection(cam, f.pl[0], f.pl[1], (double)disp_sub, f.P);
-          f.disp = disp_sub;
-          f.level = kl.octave;
-          f.sigma2 = level_sigma2(f.level, cfg.orb_scale_factor);
-          f.idx = slot; f.src_l = i; f.src_r = tdx;
-          out.pt[op + slot] = f;
-          const uint4* s = reinterpret_cast<const uint4*>(raw.pdesc_l + (rp + i) * 32);
-          uint4* d = reinterpret_cast<uint4*>(out.pdesc + (op + slot) * 32);
-          d[0] = s[0]; d[1] = s[1];
+          if (i0 + u * ACCEPT_THREADS >= n_l) break;   // CTA-uniform: no element of this sub-round exists
+          const int slot = block_compact(keep, base, s_warp);
+          if (keep) {
+            gfpl_point_feature f;
+            f.pl[0] = kl[u].x; f.pl[1] = kl[u].y;
+            back_projection(cam, f.pl[0], f.pl[1], (double)disp_sub, f.P);
+            f.disp = disp_sub;
+            f.level = kl[u].octave;
+            f.sigma2 = level_sigma2(f.level, cfg.orb_scale_factor);
+            f.idx = slot; f.src_l = i; f.src_r = tdx;
+            out.pt[op + slot] = f;
+            const uint4* sd = reinterpret_cast<const uint4*>(raw.pdesc_l + (rp + i) * 32);
+            uint4* d = reinterpret_cast<uint4*>(out.pdesc + (op + slot) * 32);
+            d[0] = sd[0]; d[1] = sd[1];
+          }
         }
       }
     }
     if (threadIdx.x == 0) out.n_pt[p] = base;
+    return;
   }
 
   // ---- lines (stereoFrame.cpp:248-334 / 881-1014) ---------------------------------------------------
@@ -272,7 +292,7 @@ int launch_stereo_accept(gfpl_ctx* ctx, const DevRawFrames& raw, int variant, Kn
     GFPL_CUDA_OK(ctx, cudaFuncSetAttribute(stereo_accept_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   gfpl_config cfg = ctx->cfg;
   if (lines_only) cfg.has_points = 0;  // the point part then only writes n_pt = 0 (overwritten by the caller's point kernel)
-  stereo_accept_kernel<<<raw.B, ACCEPT_THREADS, smem, ctx->stream>>>(raw, variant, pt_lr, pt_rl, ln_lr, ln_rl, out,
+  stereo_accept_kernel<<<dim3(raw.B, 2), ACCEPT_THREADS, smem, ctx->stream>>>(raw, variant, pt_lr, pt_rl, ln_lr, ln_rl, out,
                                                                       ctx->cam, cfg);
   GFPL_LAUNCH_OK(ctx);
   return GFPL_OK;
