@@ -243,6 +243,9 @@ __device__ __forceinline__ void pose_store(double* DTs, const double* T) {
 // point term (stereoFrameHandler.cpp:2131-2167): J (already divided by max(homog_th, r)), r and the weight.  Branch-free,
 // so that two observations evaluated back to back interleave in one basic block.  `on` false (outlier, or past the end
 // of the list) gives an all-zero term.
+// WEIGHT_ONLY: an `off` slot is known to hold a copy of a valid record (the padding slot of a round over the inlier
+// list), so a zero weight alone removes it — every term it contributes is a finite value times w.
+template <bool WEIGHT_ONLY>
 __device__ __forceinline__ void point_front(const double* DTs, const gfpl_pt_obs& ob, bool on, const gfpl_camera& cam,
                                             const PoseConst& c, double* J, double& r, double& w) {
   double DT[16], P_[3];
@@ -258,9 +261,9 @@ __device__ __forceinline__ void point_front(const double* DTs, const gfpl_pt_obs
   const double idn = (r > c.hth) ? rs : c.inv_hth;     // 1 / max(homog_th, r)
   jac6(fgz2, P_[0], P_[1], P_[2], dx, dy, J);
 #pragma unroll
-  for (int i = 0; i < 6; i++) J[i] = on ? J[i] * idn : 0.0;
+  for (int i = 0; i < 6; i++) J[i] = (WEIGHT_ONLY || on) ? J[i] * idn : 0.0;
   w = on ? rcp_nr(1.0 + s * ob.sigma2) : 0.0;
-  r = on ? r : 0.0;
+  r = (WEIGHT_ONLY || on) ? r : 0.0;
 }
 // line term (:2171-2235)
 __device__ __forceinline__ void line_term(const double* DTs, const gfpl_ln_obs& ob, const gfpl_camera& cam, const PoseConst& c,
@@ -291,7 +294,8 @@ __device__ __forceinline__ void line_term(const double* DTs, const gfpl_ln_obs& 
 
 // optimizeFunctions for one pair by one group of G lanes: a.v = [H lower triangle, packed (21) | g (6) | e] (nothing is
 // evaluated for a group that is not `act`: its sums are zero).  Every lane of the group ends with the same values.
-template <int G>
+// LISTED: the points are walked through the compacted inlier list o.plist (the optimiser); else all points, flags in o.pin
+template <int G, bool LISTED>
 __device__ __forceinline__ void group_optimize_functions(const double* DTs, const PairObs& o, bool act, const gfpl_camera& cam,
                                                          const gfpl_config& cfg, Acc& a) {
   const int lg = threadIdx.x & (G - 1);
@@ -307,23 +311,23 @@ __device__ __forceinline__ void group_optimize_functions(const double* DTs, cons
     // parallelism from; an observation that is an outlier or past the end contributes zeros
     // (the optimiser walks the compacted list of inliers: after the MAD pass a fifth of the points are outliers, and a
     // branch-free term costs the same whether it counts or not)
-    const int nwalk = o.plist ? (act ? o.nplist : 0) : npt;
+    const int nwalk = LISTED ? (act ? o.nplist : 0) : npt;
     for (int k = lg; k < nwalk; k += 2 * G) {
       const bool twoB = k + G < nwalk;
       const int k2 = twoB ? k + G : k;
-      const int iA = o.plist ? (int)o.plist[k] : k, iB = o.plist ? (int)o.plist[k2] : k2;
+      const int iA = LISTED ? (int)o.plist[k] : k, iB = LISTED ? (int)o.plist[k2] : k2;
       if (k + 2 * G < nwalk) {   // the records of the next round: pulled into L1 now, no registers held
         const int k3 = k + 3 * G < nwalk ? k + 3 * G : k + 2 * G;
-        const char* nA = reinterpret_cast<const char*>(&o.pts[o.plist ? (int)o.plist[k + 2 * G] : k + 2 * G]);
-        const char* nB = reinterpret_cast<const char*>(&o.pts[o.plist ? (int)o.plist[k3] : k3]);
+        const char* nA = reinterpret_cast<const char*>(&o.pts[LISTED ? (int)o.plist[k + 2 * G] : k + 2 * G]);
+        const char* nB = reinterpret_cast<const char*>(&o.pts[LISTED ? (int)o.plist[k3] : k3]);
         prefetch_l1(nA); prefetch_l1(nA + 48);
         prefetch_l1(nB); prefetch_l1(nB + 48);
       }
       const gfpl_pt_obs A = o.pts[iA], Bq = o.pts[iB];
-      const bool onA = o.plist ? true : o.pin[iA] != 0, onB = twoB && (o.plist ? true : o.pin[iB] != 0);
+      const bool onA = LISTED ? true : o.pin[iA] != 0, onB = twoB && (LISTED ? true : o.pin[iB] != 0);
       double JA[6], JB[6], rA, rB, wA, wB;
-      point_front(DTs, A, onA, cam, c, JA, rA, wA);
-      point_front(DTs, Bq, onB, cam, c, JB, rB, wB);
+      point_front<LISTED>(DTs, A, onA, cam, c, JA, rA, wA);
+      point_front<LISTED>(DTs, Bq, onB, cam, c, JB, rB, wB);
       acc_add(a, JA, rA, wA);
       acc_add(a, JB, rB, wB);
       N += (onA ? 1 : 0) + (onB ? 1 : 0);
@@ -381,7 +385,7 @@ __device__ __forceinline__ int group_gauss_newton(double* DTs /*shared, 12*/, co
   for (int it = 0; it < max_iters; it++) {
     if (!__any_sync(0xffffffffu, act)) break;
     Acc a;
-    group_optimize_functions<G>(DTs, o, act, cam, cfg, a);
+    group_optimize_functions<G, true>(DTs, o, act, cam, cfg, a);
     if (act) {  // H of the last evaluation is kept in the pair's shared-memory slot, not in 42 registers across the loop
       err = a.v[27];
       if (lg == 0) {
@@ -591,40 +595,6 @@ __device__ __forceinline__ void group_remove_outliers(const double* DTs, const P
   __syncwarp();
 }
 
-// lane-0 epilogue helpers (local-memory loops; executed once per pair)
-__device__ __noinline__ void unccomp_se3(const double* T1, const double* covT1, const double* covTinc, double* covT2) {
-  double Ad[36], tmp[36];
-  double sk[9], skR[9];
-  const double t[3] = {T1[3], T1[7], T1[11]};
-  skew(t, sk);
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) {
-      double s = sk[i * 3 + 0] * T1[0 * 4 + j];
-      s = s + sk[i * 3 + 1] * T1[1 * 4 + j];
-      s = s + sk[i * 3 + 2] * T1[2 * 4 + j];
-      skR[i * 3 + j] = s;
-    }
-  for (int i = 0; i < 36; i++) Ad[i] = 0.0;
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) {
-      Ad[i * 6 + j] = T1[i * 4 + j];
-      Ad[i * 6 + 3 + j] = skR[i * 3 + j];
-      Ad[(i + 3) * 6 + 3 + j] = T1[i * 4 + j];
-    }
-  for (int i = 0; i < 6; i++)
-    for (int j = 0; j < 6; j++) {
-      double s = Ad[i * 6 + 0] * covTinc[0 * 6 + j];
-      for (int k = 1; k < 6; k++) s = s + Ad[i * 6 + k] * covTinc[k * 6 + j];
-      tmp[i * 6 + j] = s;
-    }
-  for (int i = 0; i < 6; i++)
-    for (int j = 0; j < 6; j++) {
-      double s = tmp[i * 6 + 0] * Ad[j * 6 + 0];
-      for (int k = 1; k < 6; k++) s = s + tmp[i * 6 + k] * Ad[j * 6 + k];
-      covT2[i * 6 + j] = covT1[i * 6 + j] + s;
-    }
-}
-
 // an even number of doubles (16-byte aligned slots): residuals, select scratch / inlier list, padding of the scratch
 __host__ __device__ inline int pose_smem_doubles(int cap_pt, int cap_ln) { return (cap_pt + cap_ln + (cap_pt + cap_ln + 1) / 2 + 4 + 1) & ~1; }
 
@@ -706,14 +676,54 @@ pose_optimize_kernel(DevTrackObs obs, const gfpl_frame_state* __restrict__ state
   w.iters_first = it1; w.iters_ref = it2;
 }
 
-// serial tail of optimizePose (:1984-2028): DT_cov = H^-1, inverse_se3, motion-step gate, Tfw, eigenvalues of
-// DT_cov, unccomp_se3.  One THREAD per pair (the GN kernel spends a warp per pair; this part has no
-// parallelism inside a pair, so it runs 32 pairs per warp here).
-constexpr int FINALIZE_THREADS = 32;   // one warp per CTA: 8192 pairs = 256 CTAs over all SMs (the kernel is one serial chain per thread)
+// serial tail of optimizePose (:1984-2028): DT_cov = H^-1, inverse_se3, motion-step gate, Tfw, eigenvalues of DT_cov,
+// unccomp_se3.  No parallelism inside these pieces, but they are independent of each other once DT_cov exists: FOUR
+// lanes per pair — every lane inverts H itself (same operations, same bits), then lane 0 runs the Jacobi iteration for
+// the eigenvalues, lane 1 the pose / gate / counters, lanes 2 and 3 three rows each of the covariance propagation.
+// One thread per pair took 96 us per 8192 pairs (a chain of ~190 k cycles on 64 SMs), 72 us with the Jacobi matrix in registers.
+constexpr int FINALIZE_LANES = 4;
+constexpr int FINALIZE_THREADS = 64;
+
+// rows [r0, r1) of unccomp_se3 (auxiliar.cpp:221-238): covT2 = covT1 + Ad(T1) * covTinc * Ad(T1)^T
+__device__ __noinline__ void unccomp_se3_rows(const double* T1, const double* covT1, const double* covTinc, int r0, int r1, double* covT2) {
+  double Ad[36];
+  double sk[9], skR[9];
+  const double t[3] = {T1[3], T1[7], T1[11]};
+  skew(t, sk);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double s = sk[i * 3 + 0] * T1[0 * 4 + j];
+      s = s + sk[i * 3 + 1] * T1[1 * 4 + j];
+      s = s + sk[i * 3 + 2] * T1[2 * 4 + j];
+      skR[i * 3 + j] = s;
+    }
+  for (int i = 0; i < 36; i++) Ad[i] = 0.0;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      Ad[i * 6 + j] = T1[i * 4 + j];
+      Ad[i * 6 + 3 + j] = skR[i * 3 + j];
+      Ad[(i + 3) * 6 + 3 + j] = T1[i * 4 + j];
+    }
+  for (int i = r0; i < r1; i++) {
+    double tmp[6];
+    for (int j = 0; j < 6; j++) {
+      double s = Ad[i * 6 + 0] * covTinc[0 * 6 + j];
+      for (int k = 1; k < 6; k++) s = s + Ad[i * 6 + k] * covTinc[k * 6 + j];
+      tmp[j] = s;
+    }
+    for (int j = 0; j < 6; j++) {
+      double s = tmp[0] * Ad[j * 6 + 0];
+      for (int k = 1; k < 6; k++) s = s + tmp[k] * Ad[j * 6 + k];
+      covT2[i * 6 + j] = covT1[i * 6 + j] + s;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(FINALIZE_THREADS)
 pose_finalize_kernel(int B, const PoseRaw* __restrict__ raw, const gfpl_frame_state* __restrict__ state, int overload,
                      gfpl_pose_result* __restrict__ out, gfpl_config cfg) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = t / FINALIZE_LANES, sub = t % FINALIZE_LANES;
   if (p >= B) return;
   const PoseRaw& w = raw[p];
   const gfpl_frame_state& st = state[p];
@@ -721,9 +731,11 @@ pose_finalize_kernel(int B, const PoseRaw* __restrict__ raw, const gfpl_frame_st
   int status = w.status;
   double DT[16], DT_cov[36];
   for (int i = 0; i < 16; i++) DT[i] = w.DT[i];
-  if (w.cov_from_H) inverse6(w.H, DT_cov);
-  else
-    for (int i = 0; i < 36; i++) DT_cov[i] = 0.0;
+  if (sub != 1) {   // (lane 1 does not read DT_cov)
+    if (w.cov_from_H) inverse6(w.H, DT_cov);
+    else
+      for (int i = 0; i < 36; i++) DT_cov[i] = 0.0;
+  }
   bool accept = false;
   double DTinv[16];
   if (is_finite16(DT)) {
@@ -738,9 +750,10 @@ pose_finalize_kernel(int B, const PoseRaw* __restrict__ raw, const gfpl_frame_st
     }
   } else
     status |= GFPL_POSE_NONFINITE_2;
-  for (int i = 0; i < 36; i++) r.DT_cov[i] = DT_cov[i];
-  {  // eigenvalues of DT_cov: the cyclic Jacobi iteration with the matrix in registers (the out-of-line routine keeps it in
-     // local memory: every rotation then waits for ~50 dependent local loads), ascending insertion sort as before
+  if (sub == 0) {
+    for (int i = 0; i < 36; i++) r.DT_cov[i] = DT_cov[i];
+    // eigenvalues of DT_cov: the cyclic Jacobi iteration with the matrix in registers (the out-of-line routine keeps it in
+    // local memory: every rotation then waits for ~50 dependent local loads), ascending insertion sort as before
     double ev[6];
     sym_eigenvalues_unrolled<6>(DT_cov, ev);
 #pragma unroll
@@ -754,21 +767,25 @@ pose_finalize_kernel(int B, const PoseRaw* __restrict__ raw, const gfpl_frame_st
     }
 #pragma unroll
     for (int i = 0; i < 6; i++) r.DT_cov_eig[i] = ev[i];
-  }
-  if (accept) {
-    double Tfw[16];
-    matmul<4, 4, 4>(st.Tfw, DTinv, Tfw);
-    for (int i = 0; i < 16; i++) { r.DT[i] = DTinv[i]; r.Tfw[i] = Tfw[i]; }
-    unccomp_se3(st.Tfw, st.Tfw_cov, DT_cov, r.Tfw_cov);
-    r.err_norm = w.err;
+  } else if (sub == 1) {
+    if (accept) {
+      double Tfw[16];
+      matmul<4, 4, 4>(st.Tfw, DTinv, Tfw);
+      for (int i = 0; i < 16; i++) { r.DT[i] = DTinv[i]; r.Tfw[i] = Tfw[i]; }
+      r.err_norm = w.err;
+    } else {
+      for (int i = 0; i < 16; i++) { r.DT[i] = (i % 5 == 0) ? 1.0 : 0.0; r.Tfw[i] = st.Tfw[i]; }
+      r.err_norm = -1.0;
+    }
+    r.status = status;
+    r.n_inliers = w.n_inliers; r.n_inliers_pt = w.n_inliers_pt; r.n_inliers_ls = w.n_inliers_ls;
+    r.iters_first = w.iters_first; r.iters_ref = w.iters_ref;
   } else {
-    for (int i = 0; i < 16; i++) { r.DT[i] = (i % 5 == 0) ? 1.0 : 0.0; r.Tfw[i] = st.Tfw[i]; }
-    for (int i = 0; i < 36; i++) r.Tfw_cov[i] = st.Tfw_cov[i];
-    r.err_norm = -1.0;
+    const int r0 = (sub - 2) * 3, r1 = r0 + 3;
+    if (accept) unccomp_se3_rows(st.Tfw, st.Tfw_cov, DT_cov, r0, r1, r.Tfw_cov);
+    else
+      for (int i = r0 * 6; i < r1 * 6; i++) r.Tfw_cov[i] = st.Tfw_cov[i];
   }
-  r.status = status;
-  r.n_inliers = w.n_inliers; r.n_inliers_pt = w.n_inliers_pt; r.n_inliers_ls = w.n_inliers_ls;
-  r.iters_first = w.iters_first; r.iters_ref = w.iters_ref;
 }
 
 size_t pose_raw_bytes(int B) { return (size_t)(B > 0 ? B : 1) * sizeof(PoseRaw); }
@@ -788,7 +805,7 @@ static int launch_pose_optimize_on(gfpl_ctx* ctx, DevTrackObs obs, const gfpl_fr
   const int grid = (obs.B + PAIRS_PER_CTA - 1) / PAIRS_PER_CTA;
   pose_optimize_kernel<G><<<grid, POSE_WARPS * 32, smem, ctx->stream>>>(obs, state, DT_ini, overload, raw, ctx->cam, ctx->cfg);
   GFPL_LAUNCH_OK(ctx);
-  pose_finalize_kernel<<<(obs.B + FINALIZE_THREADS - 1) / FINALIZE_THREADS, FINALIZE_THREADS, 0, ctx->stream>>>(obs.B, raw, state, overload, out, ctx->cfg);
+  pose_finalize_kernel<<<(obs.B * FINALIZE_LANES + FINALIZE_THREADS - 1) / FINALIZE_THREADS, FINALIZE_THREADS, 0, ctx->stream>>>(obs.B, raw, state, overload, out, ctx->cfg);
   GFPL_LAUNCH_OK(ctx);
   return GFPL_OK;
 }
@@ -856,7 +873,7 @@ pose_hg_kernel(DevTrackObs obs, const double* __restrict__ DT_all, double* __res
   __shared__ __align__(16) double s_DT[POSE_WARPS][12];
   Acc a;
   pose_store(s_DT[warp], DT_all + (size_t)p * 16);
-  group_optimize_functions<32>(s_DT[warp], o, true, cam, cfg, a);
+  group_optimize_functions<32, false>(s_DT[warp], o, true, cam, cfg, a);
   const double* Hp = a.v;
   const double* g = a.v + 21;
   const double e = a.v[27];
