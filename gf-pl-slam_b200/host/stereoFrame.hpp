@@ -108,6 +108,11 @@ class LineFeature {
   Matrix3d covSpt3D, covEpt3D;
   double cutRatio[2] = {0, 0};
   gfpl::Mat<6, 6> invCovPose;
+  // written by estimateProjUncertainty_descent (stereoFeatures.h:116-123)
+  vector<double> volumeArr;        // here: {volume at cut {0,0} is not kept} -> the accepted volume, volumeArr.back()
+  vector<Vector2d> lPt2D;
+  vector<Matrix3d> covlPt2D;
+  int fst_idx = 0, lst_idx = 0;
 };
 
 // include/stereoFrame.h:89-260

@@ -232,6 +232,45 @@ void StereoFrameHandler::estimateProjUncertainty_submodular(const double stepCut
   }
 }
 
+// stereoFrameHandler.cpp:1476-1610: every matched line on its own (gfpl_linecut_descent: one device thread per line)
+void StereoFrameHandler::estimateProjUncertainty_descent(const double stepCutRatio, const double rngCutRatio[2]) {
+  if (matched_ls.empty()) return;  // :1479
+  gfpl_config& cfg = gfpl_->config();
+  cfg.cut_step = stepCutRatio; cfg.cut_rng[0] = rngCutRatio[0]; cfg.cut_rng[1] = rngCutRatio[1];
+  gfpl_->apply();
+  vector<gfpl_pt_obs> pt; vector<gfpl_ln_obs> ln; vector<uint8_t> pin, lin;
+  buildObs(pt, pin, ln, lin);
+  int32_t n_pt = (int32_t)matched_pt.size(), n_ln = (int32_t)matched_ls.size();
+  gfpl_track_obs obs{1, (int32_t)pt.size(), (int32_t)ln.size(), &n_pt, &n_ln, pt.data(), pin.data(), ln.data(), lin.data()};
+  vector<gfpl_line_cov> cov(ln.size());
+  size_t k = 0;
+  for (auto it = matched_ls.begin(); it != matched_ls.end(); ++it, ++k) cov_of(*it, cov[k]);
+  double DT_inv[16];
+  dt_inv_of(prev_frame, curr_frame, DT_inv);
+  vector<gfpl_line_cut_descent> cut(ln.size());
+  gfpl_->check(gfpl_linecut_descent(gfpl_->get(), DT_inv, &obs, cov.data(), (int32_t)cov.size(), cut.data()));
+  k = 0;
+  for (auto it = matched_ls.begin(); it != matched_ls.end(); ++it, ++k) {
+    LineFeature* l = *it;
+    const gfpl_line_cut_descent& c = cut[k];
+    l->cutRatio[0] = c.cutRatio[0]; l->cutRatio[1] = c.cutRatio[1];
+    l->volumeArr.assign(1, c.volume);              // the track's last entry; its length is c.n_volume
+    l->covlPt2D.assign(4, Matrix3d());             // :1578-1588: identity, start point, end point, identity
+    l->lPt2D.assign(4, Vector2d());
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        l->covlPt2D[0](i, j) = l->covlPt2D[3](i, j) = (i == j) ? 1.0 : 0.0;
+        l->covlPt2D[1](i, j) = c.covlPt2D[0][i * 3 + j];
+        l->covlPt2D[2](i, j) = c.covlPt2D[1][i * 3 + j];
+      }
+    for (int q = 0; q < 4; q++) { l->lPt2D[q](0) = c.lPt2D[q][0]; l->lPt2D[q](1) = c.lPt2D[q][1]; }
+    l->fst_idx = c.fst_idx; l->lst_idx = c.lst_idx;
+    for (int i = 0; i < 3; i++) { l->sP(i) = ln[k].sP[i]; l->eP(i) = ln[k].eP[i]; }   // :1601-1602, unconditional
+    l->spl(0) = c.spl[0]; l->spl(1) = c.spl[1]; l->epl(0) = c.epl[0]; l->epl(1) = c.epl[1];
+    l->sdisp = c.sdisp; l->edisp = c.edisp;
+  }
+}
+
 void StereoFrameHandler::getPoseInfoOnLine(const Matrix4d DT_inv, const Vector2d J_loss, const LineFeature* line,
                                            const double cutRatio[2], gfpl::Mat<6, 6>& info_pose) {
   // one evaluation == a cut problem with a single line, no points and the search range pinned to `cutRatio`:

@@ -30,6 +30,7 @@ class StereoFrameHandler {
 
   // stereoFrameHandler.h:76-104
   void estimateProjUncertainty_submodular(const double stepCutRatio, const double rngCutRatio[2]);  // :1618-1764
+  void estimateProjUncertainty_descent(const double stepCutRatio, const double rngCutRatio[2]);     // :1476-1610
   void getPoseInfoOnLine(const Matrix4d DT_inv, const Vector2d J_loss, const LineFeature* line, const double cutRatio[2],
                          gfpl::Mat<6, 6>& info_pose);   // :1342-1411 (one evaluation = a one-line cut problem)
   void updateEndPointByRatio(LineFeature* line);    // :1451-1470

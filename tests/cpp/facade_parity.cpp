@@ -170,6 +170,47 @@ static int test_tracking() {
   EXPECT(std::fabs(f1->err_norm - pose.err_norm) < 1e-9 * std::fabs(pose.err_norm), "err_norm");
   // the recovered motion is the simulated one (DT maps curr -> prev: inverse of the scene motion)
   EXPECT(std::fabs(f1->DT(0, 3) + 0.02) < 0.02 && std::fabs(f1->DT(2, 3) - 0.04) < 0.03, "recovered translation (%.3f %.3f %.3f)", f1->DT(0, 3), f1->DT(1, 3), f1->DT(2, 3));
+  // ---- C6: estimateProjUncertainty_descent through the facade vs the oracle, on the lines as the submodular cut left them ----
+  {
+    const size_t nl = StVO.matched_ls.size();
+    std::vector<gfpl_ln_obs> dl(std::max<size_t>(nl, 1));
+    std::vector<gfpl_line_cov> dc(dl.size());
+    std::vector<gfpl_pt_obs> dp(1); std::vector<uint8_t> dpin(1), dlin(dl.size(), 1);
+    size_t q = 0;
+    for (auto it = StVO.matched_ls.begin(); it != StVO.matched_ls.end(); ++it, ++q) {
+      for (int i = 0; i < 3; i++) { dl[q].sP[i] = (*it)->sP(i); dl[q].eP[i] = (*it)->eP(i); dl[q].le_obs[i] = (*it)->le_obs(i); }
+      dl[q].sigma2 = (*it)->sigma2; dl[q].prev_idx = (int32_t)q;
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) { dc[q].covS[i * 3 + j] = (*it)->covSpt3D(i, j); dc[q].covE[i * 3 + j] = (*it)->covEpt3D(i, j); }
+    }
+    double Tc[16], Tp[16], Ti[16], DTi[16];   // curr->Tfw^-1 * prev->Tfw with the facade's own operations (:1635)
+    f1->Tfw.to_row_major(Tc); f0->Tfw.to_row_major(Tp);
+    for (int i = 0; i < 16; i++) Ti[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    for (int i = 0; i < 3; i++) {
+      for (int j = 0; j < 3; j++) Ti[i * 4 + j] = Tc[j * 4 + i];
+      Ti[i * 4 + 3] = -(Tc[0 * 4 + i] * Tc[3] + Tc[1 * 4 + i] * Tc[7] + Tc[2 * 4 + i] * Tc[11]);
+    }
+    for (int i = 0; i < 4; i++)
+      for (int j = 0; j < 4; j++) { double a = 0; for (int kk = 0; kk < 4; kk++) a += Ti[i * 4 + kk] * Tp[kk * 4 + j]; DTi[i * 4 + j] = a; }
+    int32_t dn[2] = {0, (int32_t)nl};
+    gfpl_track_obs dobs{1, 1, (int32_t)dl.size(), &dn[0], &dn[1], dp.data(), dpin.data(), dl.data(), dlin.data()};
+    std::vector<gfpl_line_cut_descent> dout(dl.size());
+    orc_linecut_descent(&ccam, &cfg, DTi, &dobs, dc.data(), (int32_t)dc.size(), dout.data());
+    double rng[2] = {cfg.cut_rng[0], cfg.cut_rng[1]};
+    StVO.estimateProjUncertainty_descent(cfg.cut_step, rng);
+    int moved = 0;
+    q = 0;
+    for (auto it = StVO.matched_ls.begin(); it != StVO.matched_ls.end(); ++it, ++q) {
+      const LineFeature* l = *it;
+      EXPECT(l->cutRatio[0] == dout[q].cutRatio[0] && l->cutRatio[1] == dout[q].cutRatio[1], "descent cut ratio of line %zu", q);
+      EXPECT(l->volumeArr.size() == 1 && l->volumeArr.back() == dout[q].volume, "descent volume of line %zu", q);
+      EXPECT(l->sP(0) == dl[q].sP[0] && l->eP(2) == dl[q].eP[2] && l->spl(1) == dout[q].spl[1] && l->edisp == dout[q].edisp, "descent end points of line %zu", q);
+      EXPECT(l->covlPt2D.size() == 4 && l->covlPt2D[1](2, 2) == dout[q].covlPt2D[0][8] && l->covlPt2D[2](0, 1) == dout[q].covlPt2D[1][1], "descent covlPt2D of line %zu", q);
+      EXPECT(l->lPt2D.size() == 4 && l->lPt2D[3](0) == dout[q].lPt2D[3][0] && l->fst_idx == 0 && l->lst_idx == 3, "descent lPt2D of line %zu", q);
+      moved += (dout[q].cutRatio[0] > 0 || dout[q].cutRatio[1] > 0) ? 1 : 0;
+    }
+    printf("facade estimateProjUncertainty_descent: %zu lines, %d moved\n", nl, moved);
+  }
   // ---- MapHandler::lookForCommonMatches (KF <-> KF half) on the same two frames as key frames 0 and 1 ------------
   {
     for (auto* pf : f0->stereo_pt) pf->idx = -1;    // no landmark yet (the handler reused idx for f2f bookkeeping)
