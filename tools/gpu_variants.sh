@@ -5,7 +5,7 @@ TAG=${1:-var}
 KEXPR=${2:-"pose or track or replay"}
 O=gpurun_out
 mkdir -p $O
-python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "$KEXPR" > $O/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $O/${TAG}_pytest.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "$KEXPR" > $O/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $O/${TAG}_pytest.log
 echo "== default" | tee $O/${TAG}_stage.log
 GFPL_SWEEP=1 python tools/stage_ms.py 8192 5 2>&1 | tee -a $O/${TAG}_stage.log
 for d in gf-pl-slam_b200/lib/variants/*/; do
