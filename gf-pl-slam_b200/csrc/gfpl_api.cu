@@ -96,6 +96,16 @@ static bool obs_counts_ok(const gfpl_track_obs* h) {
   return h->cap_pt >= 0 && h->cap_ln >= 0 && counts_ok(h->n_pt, h->B, h->cap_pt) && counts_ok(h->n_ln, h->B, h->cap_ln);
 }
 
+// every matched line's prev_idx addresses a covariance record of its pair: 0 <= prev_idx < cov_cap
+static bool line_cov_indices_ok(const gfpl_track_obs* h, int32_t cov_cap) {
+  for (int p = 0; p < h->B; p++)
+    for (int l = 0; l < h->n_ln[p]; l++) {
+      const int32_t k = h->ln[(size_t)p * h->cap_ln + l].prev_idx;
+      if (k < 0 || k >= cov_cap) return false;
+    }
+  return true;
+}
+
 // device mirrors of the batched views -------------------------------------------------------------
 static bool mirror_raw(DevMem& m, const gfpl_raw_frames* h, DevRawFrames* d) {
   size_t B = h->B, np = B * h->cap_pt, nl = B * h->cap_ln;
@@ -780,6 +790,7 @@ int gfpl_linecut_submodular(gfpl_ctx* ctx, const double* DT_inv, gfpl_track_obs*
   REQUIRE(ctx, DT_inv && obs && prev_cov && cut && obs->B >= 0 && cov_cap > 0);
   if (obs->B == 0) return GFPL_OK;
   REQUIRE(ctx, obs_counts_ok(obs));
+  REQUIRE(ctx, line_cov_indices_ok(obs, cov_cap));
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   DevMem m(ctx);
   DevTrackObs dobs;
@@ -802,6 +813,7 @@ int gfpl_linecut_descent(gfpl_ctx* ctx, const double* DT_inv, gfpl_track_obs* ob
   REQUIRE(ctx, DT_inv && obs && prev_cov && out && obs->B >= 0 && cov_cap > 0);
   if (obs->B == 0) return GFPL_OK;
   REQUIRE(ctx, obs_counts_ok(obs));
+  REQUIRE(ctx, line_cov_indices_ok(obs, cov_cap));
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   DevMem m(ctx);
   DevTrackObs dobs;

@@ -678,6 +678,24 @@ def test_count_validation_rejects_out_of_range(ctx):
     ctx.stereo_match(raw)                        # the context is still usable
 
 
+def test_linecut_rejects_bad_covariance_index(ctx, orc):
+    """a matched line whose prev_idx lies outside the covariance array is GFPL_E_INVALID (both cut searches), not a device fault"""
+    from gfpl import api
+    d = _data(2, 531)
+    prev, curr, obs = _obs(orc, ctx.cfg, d)
+    cov = orc.stereo_uncertainty(d["cam"], ctx.cfg, prev)
+    DT_inv = _dt_inv(d["state"])
+    assert obs.n_ln[1] > 0
+    for bad in (-1, cov.shape[1]):
+        o = obs.copy()
+        o.ln[1, 0]["prev_idx"] = bad
+        for call in (ctx.linecut, ctx.linecut_descent):
+            with pytest.raises(api.GfplError) as e:
+                call(DT_inv, o, cov)
+            assert e.value.code == S.E_INVALID
+    ctx.linecut_descent(DT_inv, obs.copy(), cov)   # the context is still usable
+
+
 def test_lba_assemble(ctx, orc):
     for seed, kw in ((1, dict(n_kf=10, n_pt=1000, n_ls=300)), (2, dict(n_kf=3, n_pt=20, n_ls=5, n_fix=1))):
         w = synth.make_lba_window(seed=seed, **kw)
