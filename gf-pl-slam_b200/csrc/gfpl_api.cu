@@ -1109,11 +1109,13 @@ int gfpl_replay_upload_slim(gfpl_replay* rp, const gfpl_prev_frames* prev, const
   REQUIRE(ctx, raw->cap_pt == rp->cap_pt && raw->cap_ln == rp->cap_ln);
   GFPL_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   const size_t B = rp->B, pp = B * rp->prev.cap_pt, pl = B * rp->prev.cap_ln;
-  if (!rp->slim.pt) {
-    rp->slim.B = rp->B; rp->slim.cap_pt = rp->prev.cap_pt; rp->slim.cap_ln = rp->prev.cap_ln;
-    rp->slim.n_pt = rp->alloc<int32_t>(B); rp->slim.n_ln = rp->alloc<int32_t>(B);
-    rp->slim.pt = rp->alloc<gfpl_prev_point>(pp); rp->slim.ln = rp->alloc<gfpl_prev_line>(pl);
-    REQUIRE_MEM(ctx, rp->slim.n_pt && rp->slim.n_ln && rp->slim.pt && rp->slim.ln);
+  if (!rp->slim.pt) {   // staging, allocated on first use; published only when every allocation succeeded
+    gfpl_prev_frames st{};
+    st.B = rp->B; st.cap_pt = rp->prev.cap_pt; st.cap_ln = rp->prev.cap_ln;
+    st.n_pt = rp->alloc<int32_t>(B); st.n_ln = rp->alloc<int32_t>(B);
+    st.pt = rp->alloc<gfpl_prev_point>(pp); st.ln = rp->alloc<gfpl_prev_line>(pl);
+    REQUIRE_MEM(ctx, st.n_pt && st.n_ln && st.pt && st.ln);
+    rp->slim = st;
   }
   rp->h2d = 0;
   rp->input_dirty = true;

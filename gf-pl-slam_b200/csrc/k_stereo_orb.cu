@@ -133,6 +133,7 @@ stereo_orbslam_points_kernel(DevRawFrames raw, gfpl_pyramid pyr, ScaleTables st,
       uint32_t best = make_key(100u, 0u);  // bestDist = 100, strict <, candidates in ascending iR (:523-549)
       for (int iR = 0; iR < Nr; iR++) {
         const gfpl_keypoint kpR = kr[iR];
+        if (kpR.octave < 0 || kpR.octave >= pyr.n_levels) continue;   // not a level of this pyramid: no scale table entry
         const float r = 2.0f * st.sf[kpR.octave];
         const int maxr = (int)ceilf(kpR.y + r);
         const int minr = (int)floorf(kpR.y - r);

@@ -427,6 +427,7 @@ static int stereo_points_orbslam(const gfpl_camera* cam, const gfpl_config* cfg,
   std::vector<int> src_r(N, -1);
   for (int iR = 0; iR < Nr; iR++) {
     const float kpY = kr[iR].y;
+    if (kr[iR].octave < 0 || kr[iR].octave >= pyr->n_levels) continue;   // precondition of the reference (vector index): skipped
     const float r = 2.0f * sf[kr[iR].octave];
     const int maxr = (int)ceilf(kpY + r);
     const int minr = (int)floorf(kpY - r);
