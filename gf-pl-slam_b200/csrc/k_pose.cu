@@ -25,6 +25,9 @@ constexpr int POSE_WARPS = POSE_WARPS_N;
 #ifndef POSE_GROUP
 #define POSE_GROUP 16     // lanes per frame pair
 #endif
+#ifndef POSE_PF_DIST
+#define POSE_PF_DIST 1     // rounds between the L1 prefetch of an observation record and its use
+#endif
 #ifndef POSE_CARVEOUT
 #define POSE_CARVEOUT 100  // per cent of the SM's L1 / shared memory configured as shared memory
 #endif
@@ -316,9 +319,10 @@ __device__ __forceinline__ void group_optimize_functions(const double* DTs, cons
       const bool twoB = k + G < nwalk;
       const int k2 = twoB ? k + G : k;
       const int iA = LISTED ? (int)o.plist[k] : k, iB = LISTED ? (int)o.plist[k2] : k2;
-      if (k + 2 * G < nwalk) {   // the records of the next round: pulled into L1 now, no registers held
-        const int k3 = k + 3 * G < nwalk ? k + 3 * G : k + 2 * G;
-        const char* nA = reinterpret_cast<const char*>(&o.pts[LISTED ? (int)o.plist[k + 2 * G] : k + 2 * G]);
+      if (k + 2 * G * POSE_PF_DIST < nwalk) {   // the records of a later round: pulled into L1 now, no registers held
+        const int k2n = k + 2 * G * POSE_PF_DIST;
+        const int k3 = k2n + G < nwalk ? k2n + G : k2n;
+        const char* nA = reinterpret_cast<const char*>(&o.pts[LISTED ? (int)o.plist[k2n] : k2n]);
         const char* nB = reinterpret_cast<const char*>(&o.pts[LISTED ? (int)o.plist[k3] : k3]);
         prefetch_l1(nA); prefetch_l1(nA + 48);
         prefetch_l1(nB); prefetch_l1(nB + 48);
