@@ -688,6 +688,65 @@ pose_optimize_kernel(DevTrackObs obs, const gfpl_frame_state* __restrict__ state
 constexpr int FINALIZE_LANES = 4;
 constexpr int FINALIZE_THREADS = 64;
 
+// Eigenvalues of a symmetric 6x6 matrix by the cyclic Jacobi iteration of gfpl_math.cuh, matrix in registers, with the
+// divisions and square roots of a rotation (three divisions and two square roots, each a ~150-cycle dependent sequence:
+// the iteration was ~45 us of the finalize kernel's ~80 us chain) replaced by the reciprocal / reciprocal-square-root
+// refinements above.  A rotation that is orthogonal to ~1e-16 instead of exactly rounded changes the eigenvalues by
+// O(eps |A|); DT_cov_eig is compared at 1e-7 relative to the largest eigenvalue.  Unsorted diagonal -> ev.
+__device__ __forceinline__ void sym_eigenvalues6_fast(const double* Ain, double* ev) {
+  constexpr int N = 6;
+  double A[N * N];
+#pragma unroll
+  for (int i = 0; i < N * N; i++) A[i] = Ain[i];
+  for (int sweep = 0; sweep < 16; sweep++) {
+    double off = 0.0;
+#pragma unroll
+    for (int p = 0; p < N; p++)
+#pragma unroll
+      for (int q = p + 1; q < N; q++) off = off + A[p * N + q] * A[p * N + q];
+    if (off == 0.0) break;
+#pragma unroll
+    for (int p = 0; p < N; p++)
+#pragma unroll
+      for (int q = p + 1; q < N; q++) {
+        const double apq = A[p * N + q];
+        // the off-diagonal entries shrink quadratically and pass through the subnormal range on their way to zero, where
+        // the reciprocal seed flushes: below 1e-280 the rotation is the identity to every bit that matters (entries zeroed)
+        if (fabs(apq) < 1e-280) { A[p * N + q] = 0.0; A[q * N + p] = 0.0; }
+        else {   // (NaN takes this branch and propagates, as in the exact iteration)
+          const double app = A[p * N + p], aqq = A[q * N + q];
+          const double tau = (aqq - app) * 0.5 * rcp_nr(apq);
+          const double at = fabs(tau);
+          double t;
+          if (at < 1e100) {
+            const double s1 = fma(tau, tau, 1.0);
+            t = rcp_nr(at + s1 * rsqrt_nr(s1));          // 1 / (|tau| + sqrt(1 + tau^2))
+          } else
+            t = 0.5 * rcp_nr(at);                         // (tau^2 would overflow; also Inf / NaN from a tiny apq: t -> 0)
+          t = (tau >= 0.0) ? t : -t;
+          if (at > 1e300) t = 0.0;                        // apq so small that the rotation is the identity (NaN stays NaN)
+          const double c = rsqrt_nr(fma(t, t, 1.0)), sn = t * c;
+#pragma unroll
+          for (int k = 0; k < N; k++) {
+            const double akp = A[k * N + p], akq = A[k * N + q];
+            A[k * N + p] = c * akp - sn * akq;
+            A[k * N + q] = sn * akp + c * akq;
+          }
+#pragma unroll
+          for (int k = 0; k < N; k++) {
+            const double apk = A[p * N + k], aqk = A[q * N + k];
+            A[p * N + k] = c * apk - sn * aqk;
+            A[q * N + k] = sn * apk + c * aqk;
+          }
+          A[p * N + q] = 0.0;
+          A[q * N + p] = 0.0;
+        }
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) ev[i] = A[i * N + i];
+}
+
 // rows [r0, r1) of unccomp_se3 (auxiliar.cpp:221-238): covT2 = covT1 + Ad(T1) * covTinc * Ad(T1)^T
 __device__ __noinline__ void unccomp_se3_rows(const double* T1, const double* covT1, const double* covTinc, int r0, int r1, double* covT2) {
   double Ad[36];
@@ -759,7 +818,7 @@ pose_finalize_kernel(int B, const PoseRaw* __restrict__ raw, const gfpl_frame_st
     // eigenvalues of DT_cov: the cyclic Jacobi iteration with the matrix in registers (the out-of-line routine keeps it in
     // local memory: every rotation then waits for ~50 dependent local loads), ascending insertion sort as before
     double ev[6];
-    sym_eigenvalues_unrolled<6>(DT_cov, ev);
+    sym_eigenvalues6_fast(DT_cov, ev);
 #pragma unroll
     for (int i = 1; i < 6; i++) {
 #pragma unroll
