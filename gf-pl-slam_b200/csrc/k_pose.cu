@@ -84,10 +84,11 @@ __device__ __forceinline__ double rsqrt_nr(double s) {
 __device__ __forceinline__ double point_residual(const double* DT, const gfpl_pt_obs& o, const gfpl_camera& cam,
                                                  double* P_, double* dxy) {
   se3_apply(DT, o.P, P_);
-  const double iz = 1.0 / P_[2];
+  const double iz = rcp_nr(P_[2]);
   dxy[0] = (cam.cx + cam.fx * P_[0] * iz) - o.pl_obs[0];
   dxy[1] = (cam.cy + cam.fy * P_[1] * iz) - o.pl_obs[1];
-  return sqrt(dxy[0] * dxy[0] + dxy[1] * dxy[1]);
+  const double s = dxy[0] * dxy[0] + dxy[1] * dxy[1];
+  return (s == 0.0) ? 0.0 : s * rsqrt_nr(s);
 }
 
 // line term (:2171-2235)
@@ -95,12 +96,13 @@ __device__ __forceinline__ double line_residual(const double* DT, const gfpl_ln_
                                                 double* sP_, double* eP_, double* dse) {
   se3_apply(DT, o.sP, sP_);
   se3_apply(DT, o.eP, eP_);
-  const double izs = 1.0 / sP_[2], ize = 1.0 / eP_[2];
+  const double izs = rcp_nr(sP_[2]), ize = rcp_nr(eP_[2]);
   const double su = cam.cx + cam.fx * sP_[0] * izs, sv = cam.cy + cam.fy * sP_[1] * izs;
   const double eu = cam.cx + cam.fx * eP_[0] * ize, ev = cam.cy + cam.fy * eP_[1] * ize;
   dse[0] = o.le_obs[0] * su + o.le_obs[1] * sv + o.le_obs[2];
   dse[1] = o.le_obs[0] * eu + o.le_obs[1] * ev + o.le_obs[2];
-  return sqrt(dse[0] * dse[0] + dse[1] * dse[1]);
+  const double s = dse[0] * dse[0] + dse[1] * dse[1];
+  return (s == 0.0) ? 0.0 : s * rsqrt_nr(s);
 }
 
 
@@ -300,11 +302,9 @@ __device__ __forceinline__ void line_term(const double* DTs, const gfpl_ln_obs& 
 // LISTED: the points are walked through the compacted inlier list o.plist (the optimiser); else all points, flags in o.pin
 template <int G, bool LISTED>
 __device__ __forceinline__ void group_optimize_functions(const double* DTs, const PairObs& o, bool act, const gfpl_camera& cam,
-                                                         const gfpl_config& cfg, Acc& a) {
+                                                         const PoseConst& c, Acc& a) {
   const int lg = threadIdx.x & (G - 1);
   const int npt = act ? o.npt : 0, nln = act ? o.nln : 0;
-  PoseConst c;
-  c.hth = cfg.homog_th; c.inv_hth = 1.0 / cfg.homog_th; c.fx_over_hth = cam.fx / cfg.homog_th;
 #pragma unroll
   for (int i = 0; i < 28; i++) a.v[i] = 0.0;
   int N = 0;
@@ -376,7 +376,8 @@ __device__ __forceinline__ int group_inlier_list(const uint8_t* pin, int npt, ui
 // DT_cov = H^-1.  A group without a problem to solve (`alive` false) only takes part in the shuffles.
 template <int G>
 __device__ __forceinline__ int group_gauss_newton(double* DTs /*shared, 12*/, const PairObs& o, bool alive, const gfpl_camera& cam,
-                                                  const gfpl_config& cfg, int max_iters, double* Hs /*shared, 21*/, double* err_) {
+                                                  const gfpl_config& cfg, const PoseConst& pc, int max_iters, double* Hs /*shared, 21*/,
+                                                  double* err_) {
   const int lg = threadIdx.x & (G - 1);
   double inc[6];
   double err = 0.0, err_prev = 999999999.9;
@@ -389,7 +390,7 @@ __device__ __forceinline__ int group_gauss_newton(double* DTs /*shared, 12*/, co
   for (int it = 0; it < max_iters; it++) {
     if (!__any_sync(0xffffffffu, act)) break;
     Acc a;
-    group_optimize_functions<G, true>(DTs, o, act, cam, cfg, a);
+    group_optimize_functions<G, true>(DTs, o, act, cam, pc, a);
     if (act) {  // H of the last evaluation is kept in the pair's shared-memory slot, not in 42 registers across the loop
       err = a.v[27];
       if (lg == 0) {
@@ -422,7 +423,7 @@ __device__ __forceinline__ int group_gauss_newton(double* DTs /*shared, 12*/, co
       double nrm = 0.0;
 #pragma unroll
       for (int i = 0; i < 6; i++) nrm = nrm + inc[i] * inc[i];
-      if (sqrt(nrm) < 2.220446049250313e-16) go = false;
+      if (nrm < 2.220446049250313e-16 * 2.220446049250313e-16) go = false;   // |inc| < eps (:2051), without the square root
       else { err_prev = err; iters++; }
     }
     __syncwarp();               // every lane of the group has read the pose before any lane replaces it
@@ -577,13 +578,13 @@ __device__ __forceinline__ void group_remove_outliers(const double* DTs, const P
     double P_[3], d[2];
     const gfpl_pt_obs ob = o.pts[k];
     const double r = point_residual(DT, ob, cam, P_, d);
-    res_p[k] = r * sqrt(ob.sigma2);
+    res_p[k] = r * (ob.sigma2 * rsqrt_nr(ob.sigma2));   // r * sqrt(sigma2), sigma2 > 0
   }
   for (int k = lg; k < nln; k += G) {
     double sP_[3], eP_[3], d[2];
     const gfpl_ln_obs ob = o.lns[k];
     const double r = line_residual(DT, ob, cam, sP_, eP_, d);
-    res_l[k] = r * sqrt(ob.sigma2);
+    res_l[k] = r * (ob.sigma2 * rsqrt_nr(ob.sigma2));
   }
   __syncwarp();
   uint32_t* scratch = reinterpret_cast<uint32_t*>(s_res + ((npt + nln + 1) & ~1));  // [max(npt, nln) + 3] words behind the residuals, 16-byte aligned
@@ -645,11 +646,13 @@ pose_optimize_kernel(DevTrackObs obs, const gfpl_frame_state* __restrict__ state
   // (the select scratch behind the residuals doubles as the inlier list: the two are never live together)
   uint32_t* plist = reinterpret_cast<uint32_t*>(s_res + obs.cap_pt + obs.cap_ln);
   o.plist = plist;
+  PoseConst pc;   // loop invariants of the observation terms, once per kernel (two divisions)
+  pc.hth = cfg.homog_th; pc.inv_hth = 1.0 / cfg.homog_th; pc.fx_over_hth = cam.fx / cfg.homog_th;
 #pragma unroll 1
   for (int stage = 0; stage < 2; stage++) {
     o.nplist = group_inlier_list<G>(o.pin, alive ? o.npt : 0, plist);
     pose_store(DTs, seed);
-    const int it = group_gauss_newton<G>(DTs, o, alive, cam, cfg, stage == 0 ? cfg.max_iters : cfg.max_iters_ref, Hs, &err);
+    const int it = group_gauss_newton<G>(DTs, o, alive, cam, cfg, pc, stage == 0 ? cfg.max_iters : cfg.max_iters_ref, Hs, &err);
     if (stage == 0) {
       it1 = it;
       pose_load(DTs, DT);
@@ -936,7 +939,9 @@ pose_hg_kernel(DevTrackObs obs, const double* __restrict__ DT_all, double* __res
   __shared__ __align__(16) double s_DT[POSE_WARPS][12];
   Acc a;
   pose_store(s_DT[warp], DT_all + (size_t)p * 16);
-  group_optimize_functions<32, false>(s_DT[warp], o, true, cam, cfg, a);
+  PoseConst pc;
+  pc.hth = cfg.homog_th; pc.inv_hth = 1.0 / cfg.homog_th; pc.fx_over_hth = cam.fx / cfg.homog_th;
+  group_optimize_functions<32, false>(s_DT[warp], o, true, cam, pc, a);
   const double* Hp = a.v;
   const double* g = a.v + 21;
   const double e = a.v[27];
