@@ -632,6 +632,7 @@ def test_track_at_scale_no_flips(ctx, orc):
     co, oo, ko, po = orc.track(d["cam"], ctx.cfg, prev, d["state"], d["curr_raw"], flags, n_threads=os.cpu_count() or 1)
     flips = dict(mask_pt=0, mask_ln=0, iters=0, status=0, cut=0, counts=0)
     tol_bad = 0
+    tol_cov = dict(Tfw=0, DT_cov=0, Tfw_cov=0, err_norm=0, DT_cov_eig=0)
     for lo in range(0, B, 1024):
         hi = lo + 1024
         sl = lambda a: a[lo:hi]
@@ -647,11 +648,16 @@ def test_track_at_scale_no_flips(ctx, orc):
             flips["cut"] += int(not np.array_equal(kg["cutRatio"][p, :nln], ko["cutRatio"][q, :nln]))
             flips["iters"] += int(pg["iters_first"][p] != po["iters_first"][q] or pg["iters_ref"][p] != po["iters_ref"][q])
             flips["status"] += int(pg["status"][p] != po["status"][q])
-            if pg["status"][p] == po["status"][q] and not close(pg["DT"][p], po["DT"][q]):
-                tol_bad += 1
+            if pg["status"][p] == po["status"][q]:
+                tol_bad += int(not close(pg["DT"][p], po["DT"][q]))
+                for f in ("Tfw", "DT_cov", "Tfw_cov", "err_norm"):
+                    tol_cov[f] += int(not close(pg[f][p], po[f][q]))
+                tol_cov["DT_cov_eig"] += int(not close(pg["DT_cov_eig"][p], po["DT_cov_eig"][q], rtol=1e-7))
     assert (po["status"] == 0).mean() > 0.99
     assert sum(flips.values()) == 0, f"pairs that differ from the oracle, of {B}: {flips}"
     assert tol_bad == 0, f"{tol_bad} poses outside {RTOL}"
+    # the finalize kernel (LU inverse, covariance propagation, Jacobi eigenvalues on reciprocal refinements) at scale
+    assert sum(tol_cov.values()) == 0, f"pairs outside the tolerance, of {B}: {tol_cov}"
 
 
 def test_count_validation_rejects_out_of_range(ctx):
