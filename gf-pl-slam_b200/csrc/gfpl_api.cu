@@ -913,8 +913,8 @@ static int run_match(gfpl_ctx* ctx, const DevStereoFrames& prev, const gfpl_fram
 static int run_solve(gfpl_ctx* ctx, const DevStereoFrames& prev, const gfpl_frame_state* state, int flags, DevTrackObs obs,
                      gfpl_line_cut* cut, gfpl_pose_result* pose, StepWork& w, cudaEvent_t* ev, void* pose_raw) {
   if ((flags & GFPL_TRACK_LINECUT) && ctx->cfg.use_line_conf_cut && cut) {
-    CHECK(launch_stereo_uncertainty(ctx, prev, w.prev_cov));
-    CHECK(launch_linecut(ctx, nullptr, state, obs, w.prev_cov, prev.cap_ln, cut));
+    // (estimateStereoUncertainty runs inside the cut kernel, for the matched lines only)
+    CHECK(launch_linecut(ctx, nullptr, state, obs, w.prev_cov, prev.cap_ln, cut, prev.ln, prev.cap_ln));
   }
   if (ev) GFPL_CUDA_OK(ctx, cudaEventRecord(ev[7], ctx->stream));
   CHECK(launch_pose_optimize(ctx, obs, state, nullptr,

@@ -130,7 +130,8 @@ int launch_medoid(gfpl_ctx* ctx, const uint8_t* desc, const int32_t* offsets, in
 // K5: line cut.  DT_inv may be NULL: then it is formed from `state` (curr->Tfw^-1 * prev->Tfw with the
 // predicted curr->Tfw = prev->Tfw * prev->DT).
 int launch_linecut(gfpl_ctx* ctx, const double* DT_inv, const gfpl_frame_state* state, DevTrackObs obs,
-                   const gfpl_line_cov* prev_cov, int cov_cap, gfpl_line_cut* cut);
+                   gfpl_line_cov* prev_cov, int cov_cap, gfpl_line_cut* cut, const gfpl_line_feature* prev_ln = nullptr,
+                   int prev_cap_ln = 0);
 
 int launch_linecut_descent(gfpl_ctx* ctx, const double* DT_inv, DevTrackObs obs, const gfpl_line_cov* prev_cov, int cov_cap,
                            gfpl_line_cut_descent* out);

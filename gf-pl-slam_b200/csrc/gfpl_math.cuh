@@ -394,4 +394,35 @@ GFPL_DEV double shfl_f64(unsigned mask, double v, int src, int width = 32) {
   return __hiloint2double(hi, lo);
 }
 
+
+// ---- C1: estimateStereoUncertainty (stereoFrame.cpp:1448-1484) with getCovMat2D_3D / getJacob2D_3D (:1375-1392, 1434-1446) ----
+__device__ __forceinline__ void cov_mat_2d_3d(const gfpl_camera& cam, double u, double v, double u_std, double d,
+                                              double d_std, double* cov) {
+  double cov2D[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // D5: off-diagonals are zero
+  cov2D[0] = u_std * u_std; cov2D[4] = u_std * u_std; cov2D[8] = d_std * d_std;
+  const double b = cam.b, d_2 = d * d;
+  double J[9], Jt[9], tmp[9];
+  J[0] = b / d; J[3] = 0.0; J[6] = 0.0;
+  J[1] = 0.0; J[4] = b / d; J[7] = 0.0;
+  J[2] = -(u - cam.cx) * b / d_2;
+  J[5] = -(v - cam.cy) * b / d_2;
+  J[8] = -cam.fx * b / d_2;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) Jt[j * 3 + i] = J[i * 3 + j];
+  matmul<3, 3, 3>(J, cov2D, tmp);
+  matmul<3, 3, 3>(tmp, Jt, cov);
+}
+
+
+// covSpt3D / covEpt3D of one stereo line (stereoFrame.cpp:1458-1482)
+__device__ __forceinline__ void line_cov_from_feature(const gfpl_camera& cam, const gfpl_config& cfg, const gfpl_line_feature& l,
+                                                      gfpl_line_cov& c) {
+  const double ratio = fabs(l.le[0]) > 0.15 ? cfg.ratio_disp_std : cfg.ratio_disp_std_hor;
+  const double sdisp_std = ratio * l.sdisp, edisp_std = ratio * l.edisp;
+  cov_mat_2d_3d(cam, l.spl[0], l.spl[1], 1.0, l.sdisp, sdisp_std, c.covS);
+  cov_mat_2d_3d(cam, l.epl[0], l.epl[1], 1.0, l.edisp, edisp_std, c.covE);
+}
+
 }  // namespace gfpl

@@ -283,6 +283,13 @@ __device__ __noinline__ void fill_halves(const gfpl_camera* cam, const gfpl_conf
               (double)k * step, !isS, G->hc[isS ? 0 : 1][k & (HC_RING - 1)]);
 }
 
+// covSpt3D / covEpt3D of one previous-frame stereo line, out of line
+__device__ __noinline__ void line_cov_store(const gfpl_camera* cam, const gfpl_config* cfg, const gfpl_line_feature* l, gfpl_line_cov* out) {
+  gfpl_line_cov c;
+  line_cov_from_feature(*cam, *cfg, *l, c);
+  *out = c;
+}
+
 // initial information of one line at cut {0,0} (:1638-1649), out of line
 __device__ __noinline__ void exact_info_initial(const gfpl_camera* cam, const gfpl_config* cfg, const double* DT,
                                                 const gfpl_ln_obs* o, const gfpl_line_cov* c, gfpl_line_cut* C) {
@@ -475,8 +482,8 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 
 __global__ void __maxnreg__(CUT_MAX_REGS)
 linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __restrict__ state, DevTrackObs obs,
-               const gfpl_line_cov* __restrict__ prev_cov, int cov_cap, gfpl_line_cut* __restrict__ cut_all,
-               gfpl_camera cam, gfpl_config cfg) {
+               gfpl_line_cov* prev_cov, int cov_cap, const gfpl_line_feature* __restrict__ prev_ln, int prev_cap_ln,
+               gfpl_line_cut* __restrict__ cut_all, gfpl_camera cam, gfpl_config cfg) {
   __shared__ GroupState s_grp[CUT_THREADS / CUT_GROUP];
   __shared__ gfpl_camera s_cam;
   __shared__ gfpl_config s_cfg;
@@ -493,7 +500,7 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
   GroupState& G = s_grp[threadIdx.x / CUT_GROUP];
   gfpl_ln_obs* lns = obs.ln + (size_t)p * obs.cap_ln;
   const gfpl_pt_obs* pts = obs.pt + (size_t)p * obs.cap_pt;
-  const gfpl_line_cov* cov = prev_cov + (size_t)p * cov_cap;
+  gfpl_line_cov* cov = prev_cov + (size_t)p * cov_cap;
   gfpl_line_cut* cut = cut_all + (size_t)p * obs.cap_ln;
 
   if (j == 0) {
@@ -516,7 +523,14 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
   __syncwarp(gmask);
 
   // pass 1a: initial information of every line (cut = 0), lanes stride over the lines (:1638-1649)
-  for (int l = j; l < nln; l += CUT_GROUP) exact_info_initial(&s_cam, &s_cfg, G.DT, &lns[l], &cov[lns[l].prev_idx], &cut[l]);
+  // prev_ln given (the tracking step): estimateStereoUncertainty (stereoFrame.cpp:1448-1484) for the MATCHED lines only,
+  // evaluated here instead of by a kernel of its own over every stereo line of the previous frame; the records land in
+  // prev_cov, where pass 3 reads them
+  for (int l = j; l < nln; l += CUT_GROUP) {
+    const int pi = lns[l].prev_idx;
+    if (prev_ln) line_cov_store(&s_cam, &s_cfg, &prev_ln[(size_t)p * prev_cap_ln + pi], &cov[pi]);
+    exact_info_initial(&s_cam, &s_cfg, G.DT, &lns[l], &cov[pi], &cut[l]);
+  }
   __syncwarp(gmask);
 
   // pass 1b/2: invCov_sum in the reference's order — lines, then points, each element summed sequentially.
@@ -662,12 +676,13 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
   }
 }
 
+// prev_ln / prev_cap_ln: the previous frames' stereo lines, or nullptr: prev_cov already holds the covariances
 int launch_linecut(gfpl_ctx* ctx, const double* DT_inv, const gfpl_frame_state* state, DevTrackObs obs,
-                   const gfpl_line_cov* prev_cov, int cov_cap, gfpl_line_cut* cut) {
+                   gfpl_line_cov* prev_cov, int cov_cap, gfpl_line_cut* cut, const gfpl_line_feature* prev_ln, int prev_cap_ln) {
   if (obs.B <= 0 || obs.cap_ln <= 0) return GFPL_OK;
   const int pairs_per_cta = (CUT_THREADS / 32) * (32 / CUT_GROUP);
   const int grid = (obs.B + pairs_per_cta - 1) / pairs_per_cta;
-  linecut_kernel<<<grid, CUT_THREADS, 0, ctx->stream>>>(DT_inv, state, obs, prev_cov, cov_cap, cut, ctx->cam, ctx->cfg);
+  linecut_kernel<<<grid, CUT_THREADS, 0, ctx->stream>>>(DT_inv, state, obs, prev_cov, cov_cap, prev_ln, prev_cap_ln, cut, ctx->cam, ctx->cfg);
   GFPL_LAUNCH_OK(ctx);
   return GFPL_OK;
 }
