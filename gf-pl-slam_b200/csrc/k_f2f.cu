@@ -222,6 +222,14 @@ f2f_hybrid_points_tc_kernel(DevStereoFrames prev, DevStereoFrames curr, const do
   // global loads of the candidate's 3-D point) runs once at the end with all 256 threads, instead of after every query
   // tile with half of them while the other half waits at the next barrier.
   uint2* s_keys = reinterpret_cast<uint2*>(smem + tc_smem_bytes(prev.cap_pt));   // [curr.cap_pt]
+  // What the gate will read is requested before the matching starts: the 3-D points of the previous frame are pulled into
+  // L2 (which of them a thread needs is only known at the end: one dependent load, then an L2 hit instead of a DRAM round
+  // trip with the CTA's 105 KB of shared memory waiting for it).
+  for (int q = threadIdx.x; q < n_prev; q += TC_THREADS) {
+    const char* a = reinterpret_cast<const char*>(&prev_pt[q]);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 16));   // P[0..2] = bytes 0..23 of the 72-byte record: may straddle a sector
+  }
   const uint32_t tmem = tc_begin(S);
   uint32_t phases[2] = {0u, 0u};
   tc_direction<true>(curr_desc, n_curr, prev_desc, n_prev, sM, sN, S.bar, phases, tmem, S.merge,
