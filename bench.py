@@ -608,7 +608,7 @@ def main():
             else int_roof("knn2_sym_kernel<HAMMING2,1>: stereo lines, both directions from one pass", pairs[1], 8.0, 35.0, stage[1]),
             tensor_roof("f2f_hybrid_points_tc_kernel: radius + projection-gate search", pairs[2], 1, stage[3]) if tc_on
             else int_roof("f2f_hybrid_points_kernel", pairs[2], 5.0, 21.0, stage[3]),
-            (lambda fl: {"kernel": "linecut_kernel (+ stereo_uncertainty)", "bound": "fp64", "kernel_ms": float(stage[6]),
+            (lambda fl: {"kernel": "linecut_kernel (incl. estimateStereoUncertainty of the matched lines)", "bound": "fp64", "kernel_ms": float(stage[6]),
                          "achieved": fl / (stage[6] * 1e-3) / 1e12 if fl else None, "peak": fp64_peak, "unit": "TFLOP/s (fp64)",
                          "frac": fl / (stage[6] * 1e-3) / 1e12 / fp64_peak if fl else None,
                          "flops_source": "executed fp64 flops of one launch (ncu sm__sass_thread_inst_executed_op_d{add,mul,fma}_pred_on, "
