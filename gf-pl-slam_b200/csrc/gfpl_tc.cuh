@@ -271,11 +271,10 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
     // Two independent selection chains (even / odd columns), merged after the last pass.  Keys are signed and RELATIVE:
     // key = accumulator + column - kbase, where kbase (the first column of the 16-column chunk being reduced) is
     // subtracted from the running keys instead of being added to every new one — a new key is then `accumulator + jx`
-    // with jx a compile-time constant, which the add-min-max instruction (VIADDMNMX) fuses: 3 instructions per
-    // distance for the two nearest, 1 for the nearest.
-    constexpr int KNONE = 0x3FFFFFFF;          // stays above every real key (< 2^22) however often kbase moves
-    int k0a = KNONE, k1a = KNONE, k0b = KNONE, k1b = KNONE;
-    int kbase = 0;
+    // with jx a compile-time constant, which the add-min-max instruction (VIADDMNMX) fuses: 2.5 instructions per
+    // distance for the two nearest, 1 for the nearest (tc_reduce16).
+    TcKeys K;
+    K.reset();
     for (int pass = 0; pass < npass; pass++) {
       const int n0 = pass * TC_NPASS;
       const int N = min(TC_NPASS, nnp - n0);
@@ -283,109 +282,17 @@ __device__ __forceinline__ void tc_direction(const uint8_t* __restrict__ m_base,
       mbar_wait(&bars[pass & 1], phases[pass & 1]);
       phases[pass & 1] ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-      // this thread's share of the pass: columns [cbeg, cend) of the buffer, 16 at a time, next chunk in flight
-      // (a short last pass is split evenly as well: the first ceil(chunks / 2) chunks to half 0, the others to half 1)
-      const int csplit = N == TC_NPASS ? TC_NPASS / 2 : 16 * (((N >> 4) + 1) >> 1);
-      const int cbeg = half ? csplit : 0, cend = half ? N : csplit;
-      const int nvalid = min(N, nn - n0);  // columns of this pass that are real train rows
-      const uint32_t taddr = tlane + (uint32_t)((pass & 1) * TC_NPASS);
-      uint32_t va[16], vb[16];
-      auto reduce16_full = [&](const uint32_t* v, int c0) {   // all 16 columns valid
-        const int shift = (n0 + c0) - kbase;
-        kbase = n0 + c0;
-        k0a -= shift; k0b -= shift;
-        if (TOP2) { k1a -= shift; k1b -= shift; }
-#pragma unroll
-        for (int jx = 0; jx < 16; jx += 4) {   // DPX: fused add-min / add-max and three-input minimum
-          const int a0 = (int)v[jx], a1 = (int)v[jx + 1], a2 = (int)v[jx + 2], a3 = (int)v[jx + 3];
-          if (TOP2) {
-            const int ta0 = __viaddmax_s32(a0, jx, k0a);      k0a = __viaddmin_s32(a0, jx, k0a);
-            const int tb0 = __viaddmax_s32(a1, jx + 1, k0b);  k0b = __viaddmin_s32(a1, jx + 1, k0b);
-            const int ta1 = __viaddmax_s32(a2, jx + 2, k0a);  k0a = __viaddmin_s32(a2, jx + 2, k0a);
-            const int tb1 = __viaddmax_s32(a3, jx + 3, k0b);  k0b = __viaddmin_s32(a3, jx + 3, k0b);
-            k1a = __vimin3_s32(k1a, ta0, ta1);
-            k1b = __vimin3_s32(k1b, tb0, tb1);
-          } else {
-            k0a = __viaddmin_s32(a0, jx, k0a);      k0b = __viaddmin_s32(a1, jx + 1, k0b);
-            k0a = __viaddmin_s32(a2, jx + 2, k0a);  k0b = __viaddmin_s32(a3, jx + 3, k0b);
-          }
-        }
-      };
-      auto reduce16 = [&](const uint32_t* v, int c0) {
-        const int shift = (n0 + c0) - kbase;
-        kbase = n0 + c0;
-        k0a -= shift; k0b -= shift;
-        if (TOP2) { k1a -= shift; k1b -= shift; }
-        if (c0 + 16 <= nvalid) {
-#pragma unroll
-          for (int jx = 0; jx < 16; jx += 4) {   // DPX: fused add-min / add-max and three-input minimum
-            const int a0 = (int)v[jx], a1 = (int)v[jx + 1], a2 = (int)v[jx + 2], a3 = (int)v[jx + 3];
-            if (TOP2) {
-              const int ta0 = __viaddmax_s32(a0, jx, k0a);      k0a = __viaddmin_s32(a0, jx, k0a);
-              const int tb0 = __viaddmax_s32(a1, jx + 1, k0b);  k0b = __viaddmin_s32(a1, jx + 1, k0b);
-              const int ta1 = __viaddmax_s32(a2, jx + 2, k0a);  k0a = __viaddmin_s32(a2, jx + 2, k0a);
-              const int tb1 = __viaddmax_s32(a3, jx + 3, k0b);  k0b = __viaddmin_s32(a3, jx + 3, k0b);
-              k1a = __vimin3_s32(k1a, ta0, ta1);
-              k1b = __vimin3_s32(k1b, tb0, tb1);
-            } else {
-              k0a = __viaddmin_s32(a0, jx, k0a);      k0b = __viaddmin_s32(a1, jx + 1, k0b);
-              k0a = __viaddmin_s32(a2, jx + 2, k0a);  k0b = __viaddmin_s32(a3, jx + 3, k0b);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int jx = 0; jx < 16; jx++) {
-            if (c0 + jx < nvalid) {
-              const int acc = (int)v[jx];
-              if (TOP2) { k1a = min(k1a, max(acc + jx, k0a)); k0a = min(acc + jx, k0a); }
-              else k0a = min(acc + jx, k0a);
-            }
-          }
-        }
-      };
+      // this thread's share of the pass (tc_reduce_product): half of the buffer's columns, 16 at a time, next chunk in flight
       // (a warp whose 32 rows all lie past nm has nothing to read: TMEM read bandwidth is what bounds this kernel)
-      if (nvalid == TC_NPASS) {
-        // full pass (all 128 columns are train rows): this thread's four chunks straight-line, no per-chunk conditions
-        if (m0 + (warp & 3) * 32 < nm) {
-          TC_LD16(va, taddr + (uint32_t)cbeg);
-          TC_LD16(vb, taddr + (uint32_t)(cbeg + 16));
-          TC_WAIT16(va);
-          reduce16_full(va, cbeg);
-          TC_LD16(va, taddr + (uint32_t)(cbeg + 32));
-          TC_WAIT16(vb);
-          reduce16_full(vb, cbeg + 16);
-          TC_LD16(vb, taddr + (uint32_t)(cbeg + 48));
-          TC_WAIT16(va);
-          reduce16_full(va, cbeg + 32);
-          TC_WAIT16(vb);
-          reduce16_full(vb, cbeg + 48);
-        }
-      } else if (cbeg < cend && m0 + (warp & 3) * 32 < nm) {
-        TC_LD16(va, taddr + (uint32_t)cbeg);
-        for (int c0 = cbeg; c0 < cend; c0 += 32) {
-          TC_WAIT16(va);
-          if (c0 + 16 < cend) TC_LD16(vb, taddr + (uint32_t)(c0 + 16));
-          reduce16(va, c0);
-          if (c0 + 16 < cend) {
-            TC_WAIT16(vb);
-            if (c0 + 32 < cend) TC_LD16(va, taddr + (uint32_t)(c0 + 32));
-            reduce16(vb, c0 + 16);
-          }
-        }
-      }
+      if (m0 + (warp & 3) * 32 < nm)
+        tc_reduce_product<TOP2>(K, tlane + (uint32_t)((pass & 1) * TC_NPASS), half, N, min(N, nn - n0), n0);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();  // this buffer is drained (pass + 2 may overwrite it); after the last pass sM is free as well
     }
     // relative signed keys -> the packed keys of the integer kernels: distance << 20 | train row
-    auto canonical = [&](int k) -> uint32_t {
-      if (k >= (KNONE >> 1)) return KEY_NONE;
-      const uint32_t kabs = (uint32_t)(k + kbase + TC_KEY_BIAS);   // hamming << 13 | train row
-      return ((kabs >> TC_KEY_SHIFT) << KEY_IDX_BITS) | (kabs & ((1u << TC_KEY_SHIFT) - 1u));
-    };
-    uint32_t k0 = canonical(k0a), k1 = TOP2 ? canonical(k1a) : KEY_NONE;
-    if (TOP2) { top2_update(k0, k1, canonical(k0b)); top2_update(k0, k1, canonical(k1b)); }
-    else k0 = min(k0, canonical(k0b));
+    uint32_t k0 = tc_canonical(K.k0a, K.kbase), k1 = TOP2 ? tc_canonical(K.k1a, K.kbase) : KEY_NONE;
+    if (TOP2) { top2_update(k0, k1, tc_canonical(K.k0b, K.kbase)); top2_update(k0, k1, tc_canonical(K.k1b, K.kbase)); }
+    else k0 = min(k0, tc_canonical(K.k0b, K.kbase));
     if (half == 1) s_merge[row] = make_uint2(k0, k1);
     __syncthreads();
     const int mi = m0 + row;
