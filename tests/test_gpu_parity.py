@@ -355,7 +355,7 @@ def test_linecut_other_steps_and_ranges(orc, step, rng):
     assert moved > 0
 
 
-@pytest.mark.parametrize("step,rng,B", [(0.05, (0.0, 1.0), 48), (0.1, (0.0, 1.0), 6), (0.02, (0.0, 0.35), 6)])
+@pytest.mark.parametrize("step,rng,B", [(0.05, (0.0, 1.0), 48), (0.1, (0.0, 1.0), 6), (0.02, (0.0, 0.35), 6), (0.05, (0.0, 1.0), 512)])
 def test_linecut_descent(orc, step, rng, B):
     """C6, estimateProjUncertainty_descent: one thread per line, the oracle's operations in the oracle's order
     (-fmad=false, the same Jacobi iteration): cut decisions, volume tracks and every rewritten field bit-identical"""
