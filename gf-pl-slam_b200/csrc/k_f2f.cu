@@ -374,7 +374,10 @@ int launch_f2f_hybrid_points_knn(gfpl_ctx* ctx, const DevStereoFrames& prev, con
 }
 
 // ---- accept loops ------------------------------------------------------------------------------------
-constexpr int ACC_THREADS = 256;
+#ifndef ACC_THREADS_N
+#define ACC_THREADS_N 128   // 128: 0.113 ms per 8192 pairs (69 % of the HBM peak); 256: 0.143, 64: 0.114, 32: 0.125, 512: 0.231
+#endif
+constexpr int ACC_THREADS = ACC_THREADS_N;
 
 __device__ __forceinline__ int block_compact_acc(bool pred, int& base, int* s_warp) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

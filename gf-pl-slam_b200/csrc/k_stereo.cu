@@ -15,8 +15,14 @@
 
 namespace gfpl {
 
-constexpr int ACCEPT_THREADS = 128;
-constexpr int ACCEPT_UNROLL = 3;    // stereo points: elements per thread with their loads in flight together
+#ifndef ACCEPT_THREADS_N
+#define ACCEPT_THREADS_N 64    // 64: 0.189 ms per 8192 frames; 128: 0.192, 32: 0.191, 96: 0.212, 256: 0.285
+#endif
+constexpr int ACCEPT_THREADS = ACCEPT_THREADS_N;
+#ifndef ACCEPT_UNROLL_N
+#define ACCEPT_UNROLL_N 3
+#endif
+constexpr int ACCEPT_UNROLL = ACCEPT_UNROLL_N;    // stereo points: elements per thread with their loads in flight together
 
 // ordered block compaction: returns the output slot of this thread's element (valid when pred), advances
 // `base` (uniform across the CTA) by the number of accepted elements of this round.
