@@ -22,6 +22,7 @@ constexpr int ACCEPT_THREADS = ACCEPT_THREADS_N;
 #ifndef ACCEPT_UNROLL_N
 #define ACCEPT_UNROLL_N 3
 #endif
+constexpr int SIG_LEVELS = 16;      // pyramid levels with a precomputed sigma2 per CTA
 constexpr int ACCEPT_UNROLL = ACCEPT_UNROLL_N;    // stereo points: elements per thread with their loads in flight together
 
 // ordered block compaction: returns the output slot of this thread's element (valid when pred), advances
@@ -135,6 +136,11 @@ stereo_accept_kernel(DevRawFrames raw, int variant, Knn2Out pt_lr, Knn2Out pt_rl
   const int p = blockIdx.x;
   const size_t rp = (size_t)p * raw.cap_pt, rl_ = (size_t)p * raw.cap_ln;
   const size_t op = (size_t)p * out.cap_pt, ol = (size_t)p * out.cap_ln;
+  // sigma2 of the pyramid levels, once per CTA by the same sequence of products (the loop was 12 % of the kernel's
+  // instructions: up to eight dependent multiplications and a division per accepted feature)
+  __shared__ double s_sigma2[SIG_LEVELS];
+  if (threadIdx.x < SIG_LEVELS) s_sigma2[threadIdx.x] = level_sigma2(threadIdx.x, blockIdx.y == 0 ? cfg.orb_scale_factor : cfg.lsd_scale);
+  __syncthreads();
 
   // blockIdx.y = 0: the points of frame p, 1: its lines — two independent CTAs (the halves share nothing, and a kernel
   // bound by the latency of dependent global loads wants many small CTAs in flight)
@@ -152,11 +158,15 @@ stereo_accept_kernel(DevRawFrames raw, int variant, Knn2Out pt_lr, Knn2Out pt_rl
         float2 md[ACCEPT_UNROLL];
         gfpl_keypoint kl[ACCEPT_UNROLL], kr[ACCEPT_UNROLL];
         int rl_tdx[ACCEPT_UNROLL];
+        uint4 dlo[ACCEPT_UNROLL], dhi[ACCEPT_UNROLL];   // the left descriptor: requested with the first level, stored after the compaction
 #pragma unroll
         for (int u = 0; u < ACCEPT_UNROLL; u++) {
           const int i = i0 + u * ACCEPT_THREADS + threadIdx.x;
-          if (i < n_l) { mi[u] = pt_lr.idx[rp + i]; md[u] = pt_lr.dist[rp + i]; kl[u] = raw.pt_l[rp + i]; }
-          else { mi[u] = make_int2(0, 0); md[u] = make_float2(0.f, 0.f); kl[u] = gfpl_keypoint{}; }
+          if (i < n_l) {
+            mi[u] = pt_lr.idx[rp + i]; md[u] = pt_lr.dist[rp + i]; kl[u] = raw.pt_l[rp + i];
+            const uint4* sd = reinterpret_cast<const uint4*>(raw.pdesc_l + (rp + i) * 32);
+            dlo[u] = __ldg(sd); dhi[u] = __ldg(sd + 1);
+          } else { mi[u] = make_int2(0, 0); md[u] = make_float2(0.f, 0.f); kl[u] = gfpl_keypoint{}; dlo[u] = dhi[u] = make_uint4(0, 0, 0, 0); }
         }
 #pragma unroll
         for (int u = 0; u < ACCEPT_UNROLL; u++) {
@@ -192,12 +202,11 @@ stereo_accept_kernel(DevRawFrames raw, int variant, Knn2Out pt_lr, Knn2Out pt_rl
             back_projection(cam, f.pl[0], f.pl[1], (double)disp_sub, f.P);
             f.disp = disp_sub;
             f.level = kl[u].octave;
-            f.sigma2 = level_sigma2(f.level, cfg.orb_scale_factor);
+            f.sigma2 = ((unsigned)f.level < (unsigned)SIG_LEVELS) ? s_sigma2[f.level] : level_sigma2(f.level, cfg.orb_scale_factor);
             f.idx = slot; f.src_l = i; f.src_r = tdx;
             out.pt[op + slot] = f;
-            const uint4* sd = reinterpret_cast<const uint4*>(raw.pdesc_l + (rp + i) * 32);
             uint4* d = reinterpret_cast<uint4*>(out.pdesc + (op + slot) * 32);
-            d[0] = sd[0]; d[1] = sd[1];
+            d[0] = dlo[u]; d[1] = dhi[u];
           }
         }
       }
@@ -224,7 +233,10 @@ stereo_accept_kernel(DevRawFrames raw, int variant, Knn2Out pt_lr, Knn2Out pt_rl
         const int i = i0 + threadIdx.x;
         bool keep = false;
         gfpl_line_feature f{};
+        uint4 dlo = make_uint4(0, 0, 0, 0), dhi = dlo;   // the left descriptor: requested now, stored after the compaction
         if (i < n_matches) {
+          const uint4* sd = reinterpret_cast<const uint4*>(raw.ldesc_l + (rl_ + i) * 32);
+          dlo = __ldg(sd); dhi = __ldg(sd + 1);
           const int tdx = ln_lr.idx[rl_ + i].x;
           const float2 md = ln_lr.dist[rl_ + i];
           const gfpl_keyline L = raw.ln_l[rl_ + i];      // (two load levels, as for the points)
@@ -270,7 +282,7 @@ stereo_accept_kernel(DevRawFrames raw, int variant, Knn2Out pt_lr, Knn2Out pt_rl
                 f.le[0] = le_l[0]; f.le[1] = le_l[1]; f.le[2] = le_l[2];
                 f.angle = L.angle;
                 f.level = L.octave;
-                f.sigma2 = level_sigma2(f.level, cfg.lsd_scale);
+                f.sigma2 = ((unsigned)f.level < (unsigned)SIG_LEVELS) ? s_sigma2[f.level] : level_sigma2(f.level, cfg.lsd_scale);
                 f.src_l = i; f.src_r = tdx;
               }
             }
@@ -280,9 +292,8 @@ stereo_accept_kernel(DevRawFrames raw, int variant, Knn2Out pt_lr, Knn2Out pt_rl
         if (keep) {
           f.idx = variant == GFPL_STEREO_INITIAL ? slot : -1;
           out.ln[ol + slot] = f;
-          const uint4* s = reinterpret_cast<const uint4*>(raw.ldesc_l + (rl_ + i) * 32);
           uint4* d = reinterpret_cast<uint4*>(out.ldesc + (ol + slot) * 32);
-          d[0] = s[0]; d[1] = s[1];
+          d[0] = dlo; d[1] = dhi;
         }
       }
     }
