@@ -127,7 +127,10 @@ __device__ __forceinline__ int endpoint_cov_screen(const gfpl_camera& cam, doubl
   return 0;
 }
 
-__global__ void __launch_bounds__(ACCEPT_THREADS)
+#ifndef ACCEPT_MIN_CTAS
+#define ACCEPT_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(ACCEPT_THREADS, ACCEPT_MIN_CTAS)
 stereo_accept_kernel(DevRawFrames raw, int variant, Knn2Out pt_lr, Knn2Out pt_rl, Knn2Out ln_lr, Knn2Out ln_rl,
                      DevStereoFrames out, gfpl_camera cam, gfpl_config cfg) {
   extern __shared__ float s_v[];  // [raw.cap_ln] MAD scratch
