@@ -421,6 +421,21 @@ def main():
     stage /= nstage
     pairs = rp.pair_counts()
     serial_ms = float(stage[-1])
+    # counts of the accept loops' inputs and outputs (one untimed download): the algorithmic bytes of the two HBM-bound kernels
+    acc_counts = None
+    try:
+        obs_np = S.TrackObsNP(B, ctx.cfg.max_point_match_num, ctx.cfg.max_line_match_num)
+        curr_np = S.StereoFramesNP(B, a.n_pt, a.n_ln)
+        pose_np = np.zeros(B, S.pose_result_dt)
+        rp.download(pose_np, obs_np, None, curr_np)
+        ctx.sync()
+        raw = d["curr_raw"]
+        acc_counts = dict(raw_pt=int(raw.n_pt_l.sum() + raw.n_pt_r.sum()), raw_ln=int(raw.n_ln_l.sum() + raw.n_ln_r.sum()),
+                          stereo_pt=int(curr_np.n_pt.sum()), stereo_ln=int(curr_np.n_ln.sum()),
+                          prev_ln=int(prev.n_ln.sum()), matched_pt=int(obs_np.n_pt.sum()), matched_ln=int(obs_np.n_ln.sum()))
+        del obs_np, curr_np, pose_np
+    except Exception as e:  # the measurement goes on without these two roofline entries
+        acc_counts = None
     # ---- value: inputs resident in HBM, K steps of the pipelined replay, CUDA events on the context stream ----------
     rp.set_pipeline(a.pipeline)
     for _ in range(a.warmup):
@@ -626,6 +641,21 @@ def main():
                      "instruction of one launch (profiles/%s: residual pass of removeOutliers, the redundant per-lane solve and SE(3) update, "
                      "reciprocal refinements); 16 lanes per pair (two pairs per warp)" % COUNTERS_FILE},
         ]
+        if acc_counts:
+            c = acc_counts
+            # stereo accept: knn records (16 B, both directions) and key points / key lines (16 / 32 B) in; per accepted feature a
+            # 72 / 152 B record out and its 32 B descriptor in and out.  f2f accept: best keys (4 B per current point), line knn records,
+            # per matched feature the two feature records (72 / 152 B each) in and an observation (56 / 88 B + flag) out.
+            bytes_st = (16 + 16) * c["raw_pt"] + (16 + 32) * c["raw_ln"] + (72 + 64) * c["stereo_pt"] + (152 + 64) * c["stereo_ln"]
+            bytes_ff = 4 * c["stereo_pt"] + 16 * (c["prev_ln"] + c["stereo_ln"]) + (144 + 57) * c["matched_pt"] + (304 + 89) * c["matched_ln"]
+            for name, nbytes, t_ms, key in (("stereo_accept_kernel (points CTA + lines CTA per frame)", bytes_st, float(stage[2]), "stereo_accept_kernel"),
+                                            ("f2f_accept_kernel (points CTA + lines CTA per pair)", bytes_ff, float(stage[5]), "f2f_accept_kernel")):
+                cnt = counters.get(key) if counters_match else None
+                by_kernel.append({"kernel": name, "bound": "hbm", "achieved": nbytes / (t_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                  "frac": nbytes / (t_ms * 1e-3) / 1e9 / hbm_peak, "kernel_ms": t_ms, "algorithmic_bytes_per_launch": nbytes,
+                                  "traffic": cnt.get("dram_bytes") if cnt else None,
+                                  "traffic_frac": (cnt["dram_bytes"] / (t_ms * 1e-3) / 1e9 / hbm_peak) if cnt and cnt.get("dram_bytes") else None,
+                                  "note": "gathers of 16..152-byte records by match index; traffic = DRAM bytes of one launch (profiles/%s)" % COUNTERS_FILE})
         # the bench line's `roofline` is the kernel with the largest share of the (unpipelined) step
         roofline = dict(max(by_kernel, key=lambda r: r["kernel_ms"]))
         alg_bytes = B * (2 * a.n_pt * 32 + 2 * a.n_pt * 16)
