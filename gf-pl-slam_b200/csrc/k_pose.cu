@@ -689,7 +689,10 @@ pose_optimize_kernel(DevTrackObs obs, const gfpl_frame_state* __restrict__ state
 // the eigenvalues, lane 1 the pose / gate / counters, lanes 2 and 3 three rows each of the covariance propagation.
 // One thread per pair took 96 us per 8192 pairs (a chain of ~190 k cycles on 64 SMs), 72 us with the Jacobi matrix in registers.
 constexpr int FINALIZE_LANES = 4;
-constexpr int FINALIZE_THREADS = 64;
+#ifndef FINALIZE_THREADS_N
+#define FINALIZE_THREADS_N 64
+#endif
+constexpr int FINALIZE_THREADS = FINALIZE_THREADS_N;
 
 // Eigenvalues of a symmetric 6x6 matrix by the cyclic Jacobi iteration of gfpl_math.cuh, matrix in registers, with the
 // divisions and square roots of a rotation (three divisions and two square roots, each a ~150-cycle dependent sequence:
