@@ -6,7 +6,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
+#include <thread>
+#include <vector>
 #include <new>
 
 #include "gfpl_internal.h"
@@ -1448,9 +1451,9 @@ struct LbaBatch {
     return dev ? (T*)(dev + off) : nullptr;
   }
 
-  bool layout(const gfpl_lba_problem* probs, bool with_solve) {
-    size_t cur = 0;
-    for (int w = 0; w < W; w++) {   // ---- inputs
+  // inputs of window w from offset `cur` on (pass 2: copied into the staging image)
+  bool put_inputs(const gfpl_lba_problem* probs, bool with_solve, int w, size_t& cur) {
+    {
       const gfpl_lba_problem& pb = probs[w];
       LbaWin L{};
       L.pb = pb;
@@ -1474,6 +1477,39 @@ struct LbaBatch {
           return false;
       }
       if (dev) wins[w] = L;
+    }
+    return true;
+  }
+
+  std::vector<size_t> in_off;        // [W + 1] offsets of the windows' input regions (pass 1)
+
+  bool layout(const gfpl_lba_problem* probs, bool with_solve) {
+    size_t cur = 0;
+    if (!dev) {                      // pass 1: sizes
+      in_off.assign((size_t)W + 1, 0);
+      for (int w = 0; w < W; w++) { in_off[w] = cur; put_inputs(probs, with_solve, w, cur); }
+      in_off[W] = cur;
+    } else {
+      // pass 2: the packing is a host memcpy of every window's arrays (~230 KB per KITTI-shaped window) into the pinned
+      // image — split over a few threads for large batches (the windows' regions are disjoint)
+      const int nthr = W >= 64 ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+      std::vector<char> ok(nthr, 1);
+      auto work = [&](int t) {
+        for (int w = (int)((long long)W * t / nthr); w < (int)((long long)W * (t + 1) / nthr); w++) {
+          size_t c = in_off[w];
+          if (!put_inputs(probs, with_solve, w, c)) ok[t] = 0;
+        }
+      };
+      if (nthr == 1) work(0);
+      else {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthr; t++) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+      }
+      for (char c : ok)
+        if (!c) return false;
+      cur = in_off[W];
     }
     in_bytes = cur;
     zero_off = cur;
