@@ -5,6 +5,7 @@ loudly when the CUDA library has not been built, and Context() raises when no CU
 there is no CPU path in this package.
 """
 import ctypes as C
+import weakref
 import os
 
 import numpy as np
@@ -89,6 +90,9 @@ class Context:
             raise GfplError(rc, lib().gfpl_last_error(None).decode())
 
     def close(self):
+        # replays hold a pointer to their context: they go first (at interpreter shutdown the order of __del__ is arbitrary)
+        for r in list(getattr(self, "_replays", ())):
+            r.close()
         if self._h:
             lib().gfpl_ctx_destroy(self._h)
             self._h = C.c_void_p()
@@ -341,6 +345,9 @@ class Replay:
     def __init__(self, ctx, B, cap_pt, cap_ln, prev_cap_pt=None, prev_cap_ln=None):
         self.ctx, self.B, self.cap_pt, self.cap_ln = ctx, B, cap_pt, cap_ln
         self._h = C.c_void_p()
+        if not hasattr(ctx, "_replays"):
+            ctx._replays = weakref.WeakSet()
+        ctx._replays.add(self)
         ctx._check(lib().gfpl_replay_create_ex(ctx._h, B, cap_pt, cap_ln, prev_cap_pt or cap_pt, prev_cap_ln or cap_ln,
                                                C.byref(self._h)))
 

@@ -579,6 +579,7 @@ int gfpl_replay_create(gfpl_ctx* ctx, int32_t B, int32_t cap_pt, int32_t cap_ln,
  * stereo survivors, so its rows can be packed with a smaller stride than the raw detector output (less H2D traffic) */
 int gfpl_replay_create_ex(gfpl_ctx* ctx, int32_t B, int32_t cap_pt, int32_t cap_ln, int32_t prev_cap_pt,
                           int32_t prev_cap_ln, gfpl_replay** out);
+/* a replay holds a pointer to its context: destroy it BEFORE gfpl_ctx_destroy of that context */
 void gfpl_replay_destroy(gfpl_replay* rp);
 /* async H2D of the step inputs on the context stream (pinned host memory recommended) */
 int gfpl_replay_upload(gfpl_replay* rp, const gfpl_stereo_frames* prev, const gfpl_frame_state* state,
