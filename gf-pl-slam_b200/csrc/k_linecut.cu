@@ -220,6 +220,9 @@ struct __align__(16) GroupState {
 };
 static_assert(sizeof(GroupState) % 16 == 0 && HC_SIZE % 2 == 0 && HC_CHUNK * 2 == CUT_GROUP, "128-bit shared-memory accesses below");
 
+#ifndef CUT_BALANCE
+#define CUT_BALANCE 1     // pairs served in balanced order (descending line count, snake over the warps)
+#endif
 #ifndef CUT_MAX_REGS
 #define CUT_MAX_REGS 128   // 8 CTAs (16 warps) per SM
 #endif
@@ -483,7 +486,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 __global__ void __maxnreg__(CUT_MAX_REGS)
 linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __restrict__ state, DevTrackObs obs,
                gfpl_line_cov* prev_cov, int cov_cap, const gfpl_line_feature* __restrict__ prev_ln, int prev_cap_ln,
-               gfpl_line_cut* __restrict__ cut_all, gfpl_camera cam, gfpl_config cfg) {
+               gfpl_line_cut* __restrict__ cut_all, const int32_t* __restrict__ perm, gfpl_camera cam, gfpl_config cfg) {
   __shared__ GroupState s_grp[CUT_THREADS / CUT_GROUP];
   __shared__ gfpl_camera s_cam;
   __shared__ gfpl_config s_cfg;
@@ -493,8 +496,21 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
   const int j = lane & (CUT_GROUP - 1);             // neighbour index of this lane
   const int grp = lane / CUT_GROUP;                 // pair slot inside the warp
   const unsigned gmask = 0xFFu << (grp * CUT_GROUP);
-  const int p = (blockIdx.x * (CUT_THREADS / 32) + (threadIdx.x >> 5)) * (32 / CUT_GROUP) + grp;
-  if (p >= obs.B) return;
+  // Which pair this group serves.  The kernel is one wave and ends with its slowest warp; the pairs' chains differ (9..36
+  // matched lines around a mean of 20 on the EuRoC-shaped data).  `perm` lists the pairs by descending number of matched
+  // lines (linecut_order_kernel), and warp w takes ranks w, 2W-1-w, 2W+w, 4W-1-w (W warps): long and short chains share a
+  // warp, the sums are balanced.  perm == nullptr: natural order.
+  int p;
+  if (perm) {
+    const int w = blockIdx.x * (CUT_THREADS / 32) + (threadIdx.x >> 5);
+    const int W = gridDim.x * (CUT_THREADS / 32);     // every warp of the grid takes part (the grid fills the free warp slots
+    const int rank = grp * W + ((grp & 1) ? W - 1 - w : w);   // of one wave: the warps of the longest pairs then serve three pairs)
+    if (rank >= obs.B) return;
+    p = perm[rank];
+  } else {
+    p = (blockIdx.x * (CUT_THREADS / 32) + (threadIdx.x >> 5)) * (32 / CUT_GROUP) + grp;
+    if (p >= obs.B) return;
+  }
   const int nln = obs.n_ln[p], npt = obs.n_pt[p];
   if (nln == 0) return;  // :1621
   GroupState& G = s_grp[threadIdx.x / CUT_GROUP];
@@ -676,14 +692,45 @@ linecut_kernel(const double* __restrict__ DT_inv_all, const gfpl_frame_state* __
   }
 }
 
+// perm[rank] = pair index, pairs ordered by DESCENDING number of matched lines (counting sort by one CTA; the order among
+// equal counts is whatever the atomics give — it only decides which warp serves a pair, never a result)
+constexpr int ORDER_THREADS = 1024, ORDER_MAX_KEY = 2047;
+__global__ void __launch_bounds__(ORDER_THREADS) linecut_order_kernel(const int32_t* __restrict__ n_ln, int B, int32_t* __restrict__ perm) {
+  __shared__ int s_cnt[ORDER_MAX_KEY + 2];
+  for (int k = threadIdx.x; k < ORDER_MAX_KEY + 2; k += ORDER_THREADS) s_cnt[k] = 0;
+  __syncthreads();
+  for (int p = threadIdx.x; p < B; p += ORDER_THREADS) atomicAdd(&s_cnt[min(max(n_ln[p], 0), ORDER_MAX_KEY)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {   // exclusive offsets in descending key order (2 K additions: negligible next to the search)
+    int run = 0;
+    for (int k = ORDER_MAX_KEY; k >= 0; k--) { const int c = s_cnt[k]; s_cnt[k] = run; run += c; }
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < B; p += ORDER_THREADS) perm[atomicAdd(&s_cnt[min(max(n_ln[p], 0), ORDER_MAX_KEY)], 1)] = p;
+}
+
 // prev_ln / prev_cap_ln: the previous frames' stereo lines, or nullptr: prev_cov already holds the covariances
 int launch_linecut(gfpl_ctx* ctx, const double* DT_inv, const gfpl_frame_state* state, DevTrackObs obs,
                    gfpl_line_cov* prev_cov, int cov_cap, gfpl_line_cut* cut, const gfpl_line_feature* prev_ln, int prev_cap_ln) {
   if (obs.B <= 0 || obs.cap_ln <= 0) return GFPL_OK;
   const int pairs_per_cta = (CUT_THREADS / 32) * (32 / CUT_GROUP);
   const int grid = (obs.B + pairs_per_cta - 1) / pairs_per_cta;
-  linecut_kernel<<<grid, CUT_THREADS, 0, ctx->stream>>>(DT_inv, state, obs, prev_cov, cov_cap, prev_ln, prev_cap_ln, cut, ctx->cam, ctx->cfg);
-  GFPL_LAUNCH_OK(ctx);
+  // batches of more than a warp's worth of pairs are served in balanced order (see the kernel)
+  int32_t* perm = nullptr;
+  int grid_bal = grid;
+  if (obs.B > 4 * (32 / CUT_GROUP) && CUT_BALANCE) {
+    const int one_wave = ctx->sm_count * (65536 / (CUT_MAX_REGS * CUT_THREADS));   // CTAs resident at once (register-limited)
+    if (grid < one_wave) grid_bal = one_wave;      // spread over every warp slot of the wave
+    GFPL_CUDA_OK(ctx, ctx->pool ? cudaMallocFromPoolAsync((void**)&perm, (size_t)obs.B * sizeof(int32_t), ctx->pool, ctx->stream)
+                                : cudaMallocAsync((void**)&perm, (size_t)obs.B * sizeof(int32_t), ctx->stream));
+    linecut_order_kernel<<<1, ORDER_THREADS, 0, ctx->stream>>>(obs.n_ln, obs.B, perm);
+    ctx->launches++;
+  }
+  linecut_kernel<<<perm ? grid_bal : grid, CUT_THREADS, 0, ctx->stream>>>(DT_inv, state, obs, prev_cov, cov_cap, prev_ln, prev_cap_ln, cut, perm, ctx->cam, ctx->cfg);
+  const cudaError_t le = cudaGetLastError();
+  if (perm) cudaFreeAsync(perm, ctx->stream);   // stream-ordered: after the kernel
+  if (le != cudaSuccess) { set_last_error(ctx, "line-cut launch failed: %s", cudaGetErrorString(le)); return GFPL_E_CUDA; }
+  ctx->launches++;
   return GFPL_OK;
 }
 
