@@ -223,7 +223,7 @@ def dense_c4(a, ctx, api, synth, S, int8_peak, skip_cpu):
            "value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "tracked_ok": float((pose["status"] == 0).mean()),
            "kernel_ms_per_step": dict(zip(names, [float(x) for x in stage])),
            "distances_per_step": {"stereo_pt": pairs[0], "stereo_ln": pairs[1], "f2f_pt": pairs[2], "f2f_ln": pairs[3]},
-           "roofline": {"kernel": "knn2_tc_kernel<BLOCKED> + merge: stereo points 2000 x 2000, forward k=2 + reverse best (column blocks of 288 train rows)",
+           "roofline": {"kernel": "knn2_tc_kernel<BLOCKED> + merge: stereo points 2000 x 2000, forward k=2 + reverse best (column blocks of 256 train rows)",
                         "bound": "tensor", "achieved": ops / (stage[0] * 1e-3) / 1e12, "peak": int8_peak, "unit": "TOP/s (int8)",
                         "frac": ops / (stage[0] * 1e-3) / 1e12 / int8_peak, "kernel_ms": float(stage[0])},
            "f2f_roofline": {"kernel": "f2f_hybrid_points_tc_blocked_kernel + resolve", "bound": "tensor",

@@ -39,7 +39,7 @@ __host__ __device__ inline size_t knn2_tc_smem_bytes(int cap_b) {
 // yields the two nearest b-rows WITHIN the block per a-row: packed keys (distance << 20 | global b-row) go to
 // `part` [problem][block][cap_a], and knn2_tc_merge_kernel takes the two smallest keys over the blocks (the integer order of
 // the keys is OpenCV's order, so the merged result is bit-identical to the unblocked one).  The a-tiles are re-expanded by
-// every block of the problem: +14 % ALU work at 288-row blocks against a train side that no longer has to fit.
+// every block of the problem: ~+15 % ALU work at 256-row blocks against a train side that no longer has to fit.
 template <bool BLOCKED>
 __global__ void __launch_bounds__(TC_THREADS)
 knn2_tc_kernel(const uint8_t* __restrict__ a, const int32_t* __restrict__ na, int cap_a, const uint8_t* __restrict__ b,
@@ -486,7 +486,10 @@ int launch_measure_int8_peak(gfpl_ctx* ctx, double* int8_tops) {
 
 // a train side of up to TC_RESIDENT_ROWS rows sits expanded in shared memory with two CTAs per SM (304 rows: 112 KB)
 constexpr int TC_RESIDENT_ROWS = 320;
-constexpr int TC_BLOCK_ROWS = 288;     // column block of the blocked form: 2.25 accumulator passes, two CTAs per SM
+#ifndef TC_BLOCK_ROWS_N
+#define TC_BLOCK_ROWS_N 256   // 256: two full accumulator passes per block (2000 x 2000: 2.20 ms per 1024 problems); 288: 2.52, 224: 2.46
+#endif
+constexpr int TC_BLOCK_ROWS = TC_BLOCK_ROWS_N;     // column block of the blocked form, two CTAs per SM
 
 bool knn2_tc_fits(int cap_a, int cap_b) {
   // small problems are dominated by the fixed cost of a CTA (TMEM allocation, barriers): they go to knn2_tc_small_kernel;
